@@ -1,0 +1,172 @@
+"""ctypes wrapper of oracle/_ref/libqhgref.so (the unmodified reference step loop).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/ and by bench.py's cpu_baseline /
+`--impl reference` leg, never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libqhgref.so")
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.qref_create.restype = C.c_void_p
+        L.qref_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.qref_add_agents.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 7
+        L.qref_start.argtypes = [C.c_void_p]
+        L.qref_step.argtypes = [C.c_void_p, C.c_float]
+        L.qref_run.restype = C.c_double
+        L.qref_run.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.qref_num_agents.restype = C.c_long
+        L.qref_num_agents.argtypes = [C.c_void_p]
+        L.qref_get_agents.restype = C.c_long
+        L.qref_get_agents.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 9
+        L.qref_get_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.qref_get_weights.argtypes = [C.c_void_p, C.c_void_p]
+        L.qref_get_bd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qref_atan_prob.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.qref_geo_event.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+        L.qref_timers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qref_destroy.argtypes = [C.c_void_p]
+        L.qref_well_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.qref_polyline_eval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def well_sequence(state16, n):
+    st = np.ascontiguousarray(state16, dtype=np.uint32)
+    out = np.zeros(n, dtype=np.uint32)
+    lib().qref_well_sequence(_p(st), n, _p(out))
+    return out
+
+
+def polyline_eval(defn: str, x, float_cast=True):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    rc = lib().qref_polyline_eval(defn.encode(), len(x), _p(x), _p(out), int(float_cast))
+    if rc != 0:
+        raise ValueError(defn)
+    return out
+
+
+class RefSim:
+    """One `tut_EnvironAltPop` on a given grid, driven through PopLooper::doStep."""
+
+    def __init__(self, params, nbr, altitude, ice=None, threads=1, state16=None, quiet=True, layer_size=65536):
+        from qhg4_b200.params import DEFAULT_STATE
+        self.ncells = len(nbr)
+        self._nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        alt = np.ascontiguousarray(altitude, dtype=np.float64)
+        icea = None if ice is None else np.ascontiguousarray(ice, dtype=np.uint8)
+        st = np.ascontiguousarray(DEFAULT_STATE if state16 is None else state16, dtype=np.uint32)
+        with tempfile.NamedTemporaryFile("w", suffix=".xml", delete=False) as f:
+            f.write(params.to_xml())
+            path = f.name
+        try:
+            self.h = lib().qref_create(path.encode(), params.class_name.encode(), self.ncells, _p(self._nbr),
+                                       _p(alt), _p(icea), int(threads), _p(st), int(layer_size), int(quiet))
+        finally:
+            os.unlink(path)
+        if not self.h:
+            raise RuntimeError("qref_create failed")
+        self.threads = threads
+
+    def add_agents(self, pop: dict):
+        n = len(pop["cell"])
+        arrs = [np.ascontiguousarray(pop["cell"], np.int32), np.ascontiguousarray(pop["id"], np.int64),
+                np.ascontiguousarray(pop["birth"], np.float32), np.ascontiguousarray(pop["gender"], np.uint8),
+                np.ascontiguousarray(pop["age"], np.float32), np.ascontiguousarray(pop["last_birth"], np.float32),
+                np.ascontiguousarray(pop["life"], np.uint32)]
+        rc = lib().qref_add_agents(self.h, n, *[_p(a) for a in arrs])
+        assert rc == 0
+
+    def start(self):
+        rc = lib().qref_start(self.h)
+        if rc != 0:
+            raise RuntimeError(f"qref_start -> {rc}")
+
+    def step(self, t: float):
+        return lib().qref_step(self.h, float(t))
+
+    def run(self, t0: float, nsteps: int):
+        n = C.c_int64(0)
+        sec = lib().qref_run(self.h, float(t0), int(nsteps), C.byref(n))
+        return sec, n.value
+
+    def num_agents(self) -> int:
+        return int(lib().qref_num_agents(self.h))
+
+    def agents(self) -> dict:
+        n = self.num_agents()
+        out = dict(cell=np.zeros(n, np.int32), id=np.zeros(n, np.int64), birth=np.zeros(n, np.float32),
+                   gender=np.zeros(n, np.uint8), age=np.zeros(n, np.float32), last_birth=np.zeros(n, np.float32),
+                   life=np.zeros(n, np.uint32), mate=np.zeros(n, np.int32), slot=np.zeros(n, np.int32))
+        k = lib().qref_get_agents(self.h, n, *[_p(out[f]) for f in
+                                               ("cell", "id", "birth", "gender", "age", "last_birth", "life", "mate", "slot")])
+        assert k == n, (k, n)
+        return out
+
+    def counts(self):
+        out = np.zeros(self.ncells, np.uint64)
+        lib().qref_get_counts(self.h, _p(out))
+        return out
+
+    def weights(self):
+        out = np.zeros((self.ncells, 7), np.float64)
+        lib().qref_get_weights(self.h, _p(out))
+        return out
+
+    def bd(self):
+        b = np.zeros(self.ncells)
+        d = np.zeros(self.ncells)
+        rc = lib().qref_get_bd(self.h, _p(b), _p(d))
+        assert rc == 0
+        return b, d
+
+    def atan_prob(self, age):
+        age = np.ascontiguousarray(age, np.float32)
+        p = np.zeros(len(age))
+        lib().qref_atan_prob(self.h, len(age), _p(age), _p(p))
+        return p
+
+    def geo_event(self, altitude=None, ice=None, t=0.0):
+        a = None if altitude is None else np.ascontiguousarray(altitude, np.float64)
+        i = None if ice is None else np.ascontiguousarray(ice, np.uint8)
+        return lib().qref_geo_event(self.h, _p(a), _p(i), float(t))
+
+    def timers(self):
+        a, f = C.c_double(0), C.c_double(0)
+        lib().qref_timers(self.h, C.byref(a), C.byref(f))
+        return a.value, f.value
+
+    def close(self):
+        if self.h:
+            lib().qref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,105 @@
+"""Population parameter files: the reference's per-population XML, read and written.
+
+Format (`tutorial_data/xmldat/tut_EnvironAlt.xml`, parsed in the reference by
+`io/ParamProvider2.cpp` + `io/qhgXML.cpp`):
+
+    <class name="..." species_name="..." species_id="...">
+      <module name="ATanDeath" [id="Alt"]> <param name="ATanDeath_max_age" value="60.0"/> ... </module>
+      <priorities> <prio name="GetOld" value="1"/> ... </priorities>
+    </class>
+
+Action names are `Name` or `Name[id]` (`actions/Action.cpp:11-19`); they key both the
+`<prio>` table and the parameter groups.
+"""
+from __future__ import annotations
+
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+
+
+@dataclass
+class PopParams:
+    class_name: str
+    species_name: str = "sapiens"
+    species_id: int = 104
+    modules: dict = field(default_factory=dict)   # action name (with [id]) -> {param: value string}
+    prios: dict = field(default_factory=dict)     # action name -> int
+
+    def to_xml(self) -> str:
+        out = [f'<class name="{self.class_name}" species_name="{self.species_name}" species_id="{self.species_id}">']
+        for name, pars in self.modules.items():
+            if "[" in name:
+                base, ident = name[:-1].split("[", 1)
+                out.append(f'  <module name="{base}" id="{ident}">')
+            else:
+                out.append(f'  <module name="{name}">')
+            for k, v in pars.items():
+                out.append(f'    <param name="{k}" value="{v}"/>')
+            out.append("  </module>")
+        out.append("  <priorities>")
+        for name, p in self.prios.items():
+            out.append(f'    <prio name="{name}" value="{p}"/>')
+        out.append("  </priorities>")
+        out.append("</class>")
+        return "\n".join(out) + "\n"
+
+    def write(self, path: str) -> str:
+        with open(path, "w") as f:
+            f.write(self.to_xml())
+        return path
+
+    @staticmethod
+    def from_xml(text: str, class_name: str | None = None) -> "PopParams":
+        root = ET.fromstring(text)
+        classes = [root] if root.tag == "class" else list(root.iter("class"))
+        for c in classes:
+            if class_name is None or c.get("name") == class_name:
+                pp = PopParams(c.get("name"), c.get("species_name", ""), int(c.get("species_id", "0")))
+                for m in c.findall("module"):
+                    name = m.get("name")
+                    if m.get("id"):
+                        name = f'{name}[{m.get("id")}]'
+                    pp.modules[name] = {p.get("name"): p.get("value") for p in m.findall("param")}
+                pr = c.find("priorities")
+                if pr is not None:
+                    for p in pr.findall("prio"):
+                        pp.prios[p.get("name")] = int(p.get("value"))
+                return pp
+        raise KeyError(class_name)
+
+    def copy(self) -> "PopParams":
+        return PopParams(self.class_name, self.species_name, self.species_id,
+                         {k: dict(v) for k, v in self.modules.items()}, dict(self.prios))
+
+
+def tut_environ_alt(K: float = 20.0) -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_EnvironAlt.xml` (values restated, `Verhulst_K` adjustable)."""
+    return PopParams(
+        "tut_EnvironAltPop",
+        modules={
+            "ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"},
+            "WeightedMove": {"WeightedMove_prob": "0.07"},
+            "Fertility": {"Fertility_interbirth": "2.0", "Fertility_max_age": "50.0", "Fertility_min_age": "15.0"},
+            "Verhulst": {"Verhulst_b0": "0.8", "Verhulst_d0": "0.001", "Verhulst_theta": "0.1", "Verhulst_K": repr(float(K))},
+            "SingleEvaluator[Alt]": {"AltCapPref": "-0.1 0 0.1 0.01 1500 1.0 2000 1 3000 -9999"},
+        },
+        prios={"GetOld": 1, "ATanDeath": 2, "WeightedMove": 3, "SingleEvaluator[Alt]": 4,
+               "Fertility": 5, "RandomPair": 6, "Verhulst": 7},
+    )
+
+
+# default WELL512 state of the reference (app/SimParams.cpp:82-87): 16 words of seed material
+DEFAULT_STATE = (
+    0x2ef76080, 0x1bf121c5, 0xb222a768, 0x6c5d388b, 0xab99166e, 0x326c9f12, 0x3354197a, 0x7036b9a5,
+    0xb08c9e58, 0x3362d8d3, 0x037e5e95, 0x47a1ff2f, 0x740ebb34, 0xbf27ef0d, 0x70055204, 0xd24daa9a,
+)
+
+
+def seed_state(seed: int):
+    """16-word RNG state for an integer seed (seed 0 = the reference's default table)."""
+    import numpy as np
+    st = np.array(DEFAULT_STATE, dtype=np.uint32)
+    if seed:
+        rng = np.random.default_rng(int(seed))
+        st = st ^ rng.integers(0, 2 ** 32, size=16, dtype=np.uint64).astype(np.uint32)
+    return st
