@@ -1,0 +1,731 @@
+// oracle/qhg_oracle.cpp -- CPU restatement of QHG4's per-step agent update.
+//
+// TEST INFRASTRUCTURE ONLY (see qhg_oracle.h).  Single-threaded, plain C++; every function
+// cites the reference file:line it follows (paths relative to /root/reference/QHG4/).
+// Parity status: PINNED.  QOR_MODE_WELL is checked bit-exactly against the reference itself
+// (oracle/_ref, one OpenMP thread) in tests/test_oracle_vs_ref.py and against golden vectors
+// generated from it (tests/golden/, tests/make_golden.py).
+#include "qhg_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <numbers>
+#include <queue>
+#include <string>
+#include <vector>
+
+namespace {
+
+// life states, core/SPopulation.h:70-74
+constexpr uint32_t LIFE_DEAD = 0, LIFE_ALIVE = 1, LIFE_FERTILE = 5, LIFE_MOVING = 8;
+// event ids, utils_qhg/EventConsts.h:14-36
+constexpr int EVENT_ID_GEO = 2, EVENT_ID_FLUSH = 20;
+constexpr double PI = std::numbers::pi;   // utils/qhg_consts.h:71
+constexpr double ATAN_EPS = 0.001;        // actions/ATanDeath.h:14
+
+// ---------------------------------------------------------------------------------------------
+// WELL512 (utils/WELL512.cpp:70-86; Lomont's public-domain formulation)
+struct Well512 {
+    uint32_t s[16];
+    uint32_t idx = 0;
+    void seed(const uint32_t *st) { memcpy(s, st, sizeof(s)); idx = 0; }
+    uint32_t next() {
+        uint32_t a = s[idx];
+        uint32_t c = s[(idx + 13) & 15];
+        uint32_t b = a ^ c ^ (a << 16) ^ (c << 15);
+        c = s[(idx + 9) & 15];
+        c ^= (c >> 11);
+        a = s[idx] = b ^ c;
+        uint32_t d = a ^ ((a << 5) & 0xDA442D24u);
+        idx = (idx + 15) & 15;
+        a = s[idx];
+        s[idx] = a ^ b ^ d ^ (a << 2) ^ (b << 18) ^ (c << 28);
+        return s[idx];
+    }
+};
+
+// utils/WELL512.h:33-39: every real-valued draw is a 32-bit integer scaled by 2^-32
+inline double u2d(uint32_t x) { return (1.0 * x) / 4294967296.0; }
+inline double u2range(uint32_t x, double a, double b) { return a + ((b - a) * x) / 4294967296.0; }
+inline uint32_t u2int(uint32_t x, uint32_t a, uint32_t b) {  // wrandi(a,b) with s=1
+    uint32_t r = b - a;
+    return a + (uint32_t)((1.0 * r * x) / 4294967296.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011, public algorithm) -- the counter-based generator of the CUDA path
+inline void philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// draw streams of the counter mode (mirrored in qhg4_b200/csrc/qhg_rng.cuh)
+enum { STREAM_ACT0 = 0, STREAM_ACT1 = 1, STREAM_PAIR = 2, STREAM_BABY = 3 };
+// lanes of STREAM_ACT0 / STREAM_ACT1
+enum { L0_DEATH = 0, L0_MOVE = 1, L0_BIRTH = 2, L0_DEATH2 = 3 };
+enum { L1_MOVE2 = 0, L1_NAV = 1, L1_BRIDGE = 2, L1_OLDAGE = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// PolyLine (utils/PolyLine.cpp:60-89 getVal, :92-127 readFromString)
+struct PolyLine {
+    std::vector<double> x, v, a;
+    unsigned nseg = 0;
+    bool parse(const char *def) {
+        std::vector<double> d;
+        const char *p = def;
+        char *e;
+        while (true) {
+            while (*p == ' ' || *p == '\t') p++;
+            if (!*p) break;
+            double val = strtod(p, &e);
+            if (e == p) return false;
+            d.push_back(val);
+            p = e;
+        }
+        if (d.size() < 4 || (d.size() % 2)) return false;
+        size_t n = d.size() / 2;
+        x.resize(n); v.resize(n); a.assign(n, 0.0);
+        for (size_t i = 0; i < n; i++) { x[i] = d[2 * i]; v[i] = d[2 * i + 1]; }
+        nseg = (unsigned)n - 1;
+        for (unsigned i = 0; i < nseg; i++) a[i] = (v[i + 1] - v[i]) / (x[i + 1] - x[i]);  // utils/PolyLine.cpp addPoint
+        return true;
+    }
+    double val(double fx) const {
+        if (nseg == 0) return fx;
+        if (fx >= x[nseg]) return v[nseg];
+        unsigned i = 0;
+        while (i <= nseg && fx > x[i]) i++;
+        if (i == 0) return v[0];
+        if (i <= nseg) return v[i - 1] + a[i - 1] * (fx - x[i - 1]);
+        return v[nseg];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16-21
+    uint32_t life = 0;
+    int32_t cell = -1;
+    int64_t id = -1;
+    float birth = 0;
+    uint8_t gender = 0;
+    float age = 0;
+    float lastBirth = 0;
+    int32_t mate = -3;
+};
+
+enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH };
+
+struct Action {
+    std::string name;
+    ActKind kind;
+    int prio = -1;       // -1: no priority assigned -> never initialized/executed (core/Prioritizer.cpp:19-30)
+    bool enabled = true;
+};
+
+}  // namespace
+
+struct qor_pop {
+    std::string popClass;
+    int nCells = 0, maxNeigh = 6, mode = QOR_MODE_WELL;
+    std::vector<int32_t> nbr, gid;
+    std::vector<uint8_t> nNbr;
+    std::map<std::string, std::vector<double>> env;  // "Altitude", "Ice", ...
+    std::vector<Action> actions;
+
+    // parameters (names as in the reference's XML / QDF attributes)
+    double atanMaxAge = 0, atanRange = 0, atanSlope = 0, atanScale = 0;
+    double oadMaxAge = 0, oadUncertainty = 0;
+    double moveProb = 0;
+    float fertMinAge = 0, fertMaxAge = 0, fertInterbirth = 0;
+    double vB0 = -1024, vD0 = -1024, vTheta = -1024, vK = -1024;
+    PolyLine altPref;
+    bool havePoly = false;
+
+    // evaluator state (actions/SingleEvaluator.cpp:138-167,332-346)
+    bool evalFirst = true, evalNeedUpdate = false;
+
+    // storage: slots with holes, lowest-free-index allocation (utils/LBController.cpp:249-269 + utils/L2List.cpp:355-370:
+    // the PASSIVE list is kept in index order, so getFreeIndex returns the lowest free slot)
+    std::vector<Agent> slots;
+    std::vector<uint8_t> active;  // slot is linked in the ACTIVE list (includes last step's dead until they are unlinked)
+    std::priority_queue<int, std::vector<int>, std::greater<int>> freeHoles;
+    std::vector<int> prevDead, deathList, birthList, moveList;  // core/SPopulation.cpp:160-181 queues (one thread)
+    int64_t numUsed = 0;       // LBController::m_iNumUsed
+    int64_t maxID = 0, nextID = 0;
+    std::vector<uint64_t> counts;
+    std::vector<double> B, D, W;
+    float curTime = -1;
+    uint32_t stepIndex = 0;
+    std::vector<unsigned> levelsDone;
+    uint64_t totBirths = 0, totDeaths = 0, totMoves = 0, stepBirths = 0, stepDeaths = 0, stepMoves = 0;
+
+    // rng
+    uint32_t state16[16];
+    Well512 well;
+    uint32_t key[2] = {0, 0};
+
+    // ---- helpers -------------------------------------------------------------------------
+    Action *find(const std::string &n) {
+        for (auto &a : actions) if (a.name == n) return &a;
+        return nullptr;
+    }
+    int hi() const { return (int)slots.size(); }
+    void draw4(int64_t id, uint32_t stream, uint32_t out[4]) const {
+        uint32_t ctr[4] = {(uint32_t)((uint64_t)id & 0xffffffffu), (uint32_t)((uint64_t)id >> 32), stepIndex, stream};
+        philox(ctr, key, out);
+    }
+    // one 32-bit draw: sequential WELL stream, or lane `lane` of the agent's counter stream
+    uint32_t draw(int64_t id, uint32_t stream, int lane) {
+        if (mode == QOR_MODE_WELL) return well.next();
+        uint32_t o[4];
+        draw4(id, stream, o);
+        return o[lane];
+    }
+    int allocSlot() {  // LBController::getFreeIndex, utils/LBController.cpp:249-269
+        int i;
+        if (!freeHoles.empty()) { i = freeHoles.top(); freeHoles.pop(); }
+        else { i = hi(); slots.emplace_back(); active.push_back(0); }
+        active[i] = 1;
+        numUsed++;
+        return i;
+    }
+    void freeSlot(int i) {  // LBController::deleteElement, utils/LBController.cpp:276-290
+        active[i] = 0;
+        freeHoles.push(i);
+        numUsed--;
+    }
+
+    // core/SPopulation.cpp:926-938
+    void registerDeath(int i) { slots[i].life = LIFE_DEAD; deathList.push_back(i); }
+    // core/SPopulation.cpp:732-740
+    void registerBirth(int cell, int mother, int father) { birthList.push_back(cell); birthList.push_back(mother); birthList.push_back(father); }
+    // core/SPopulation.cpp:1035-1050
+    void registerMove(int from, int i, int to) { slots[i].life |= LIFE_MOVING; moveList.push_back(from); moveList.push_back(i); moveList.push_back(to); }
+
+    // core/SPopulation.cpp:509-536
+    void updateNumAgentsPerCell() {
+        std::fill(counts.begin(), counts.end(), 0);
+        for (int i = 0; i < hi(); i++) if (active[i] && slots[i].life > 0) counts[slots[i].cell]++;
+    }
+
+    // ---- initialize() of each action ---------------------------------------------------------
+    // actions/LinearBirth.cpp:90-115 and actions/LinearDeath.cpp:92-123 (constant K)
+    void verhulstInit() {
+        for (int c = 0; c < nCells; c++) {
+            B[c] = vB0 + (vTheta - vB0) * ((double)counts[c] / vK);
+            D[c] = vD0 + (vTheta - vD0) * ((double)counts[c] / vK);
+        }
+    }
+    // actions/SingleEvaluator.cpp:174-207 (calcValues) and :216-243 (exchangeAndCumulate), bCumulate = true
+    void evaluatorCompute() {
+        const int stride = maxNeigh + 1;
+        const std::vector<double> &in = env["Altitude"];
+        const std::vector<double> *ice = env.count("Ice") ? &env["Ice"] : nullptr;
+        std::fill(W.begin(), W.end(), 0.0);
+        for (int c = 0; c < nCells; c++) {
+            if (!ice || (*ice)[c] == 0) {
+                double dv = havePoly ? altPref.val((float)in[c]) : in[c];
+                W[(size_t)c * stride] = (dv > 0) ? dv : 0;
+            }
+        }
+        for (int c = 0; c < nCells; c++) {
+            double w = W[(size_t)c * stride];
+            for (int k = 0; k < maxNeigh; k++) {
+                double cw = 0;
+                int n = nbr[(size_t)c * maxNeigh + k];
+                if (n >= 0) cw = W[(size_t)n * stride];
+                cw = (cw > 0) ? cw : 0;
+                w = w + cw;
+                W[(size_t)c * stride + k + 1] = w;
+            }
+        }
+    }
+    void evaluatorInit() {
+        if (evalNeedUpdate || evalFirst) { evalFirst = false; evaluatorCompute(); }
+    }
+    // actions/RandomPair.cpp:107-128 (initialize) and :146-279 (findMates)
+    void randomPairInit() {
+        for (int i = 0; i < hi(); i++) if (active[i]) slots[i].mate = -3;
+        std::vector<std::vector<int>> F(nCells), M(nCells);
+        for (int i = 0; i < hi(); i++) {
+            if (!active[i]) continue;
+            const Agent &a = slots[i];
+            if (a.life > 0 && a.life == LIFE_FERTILE) {
+                if (a.gender == 0) F[a.cell].push_back(i);
+                else if (a.gender == 1) M[a.cell].push_back(i);
+            }
+        }
+        for (int c = 0; c < nCells; c++) {
+            int nf = (int)F[c].size(), nm = (int)M[c].size();
+            if (nf == 0 || nm == 0) continue;
+            if (mode == QOR_MODE_WELL) {
+                // slot-sorted buckets (already ascending), the smaller sex picks uniformly among the unpaired of the other
+                std::vector<int> &S = (nf <= nm) ? F[c] : M[c];   // iterated in order
+                std::vector<int> &L = (nf <= nm) ? M[c] : F[c];   // chosen from
+                int nl = (int)L.size();
+                std::vector<uint8_t> taken(nl, 0);
+                for (int s = 0; s < (int)S.size() && nl > 0; s++) {
+                    int choose = (int)u2range(well.next(), 0, nl);
+                    int seen = -1, j = -1;
+                    while (seen < choose) { j++; if (!taken[j]) seen++; }
+                    taken[j] = 1;
+                    slots[S[s]].mate = L[j];
+                    slots[L[j]].mate = S[s];
+                    nl--;
+                }
+            } else {
+                // counter mode: rank both sexes by (random key, id); equal ranks pair up -> a uniformly random
+                // injection of the smaller sex into the larger one, the same law as the sequential picking above
+                auto ranked = [&](std::vector<int> &v) {
+                    std::vector<std::pair<std::pair<uint32_t, int64_t>, int>> k;
+                    for (int i : v) { uint32_t o[4]; draw4(slots[i].id, STREAM_PAIR, o); k.push_back({{o[0], slots[i].id}, i}); }
+                    std::sort(k.begin(), k.end());
+                    for (size_t j = 0; j < v.size(); j++) v[j] = k[j].second;
+                };
+                ranked(F[c]); ranked(M[c]);
+                int np = std::min(nf, nm);
+                for (int r = 0; r < np; r++) { slots[F[c][r]].mate = M[c][r]; slots[M[c][r]].mate = F[c][r]; }
+            }
+        }
+    }
+
+    // ---- execute() of each action -------------------------------------------------------------
+    void execute(const Action &act, int i, float t) {
+        Agent &a = slots[i];
+        switch (act.kind) {
+        case A_GETOLD:  // actions/GetOld.cpp:37-48
+            if (a.life > 0) a.age = t - a.birth;
+            break;
+        case A_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
+            if (a.life > 0) {
+                a.age = t - a.birth;
+                double p = 0.5 + atanScale * atan(atanSlope * (a.age - atanMaxAge)) / PI;
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_DEATH));
+                if (r < p) registerDeath(i);
+            }
+            break;
+        }
+        case A_OLDAGEDEATH: {  // actions/OldAgeDeath.cpp:48-67
+            if (a.life > 0) {
+                a.age = t - a.birth;
+                double r = u2range(draw(a.id, STREAM_ACT1, L1_OLDAGE), 1 - oadUncertainty * oadMaxAge, 1 + oadUncertainty * oadMaxAge);
+                if (a.age > oadMaxAge + r) registerDeath(i);
+            }
+            break;
+        }
+        case A_WEIGHTEDMOVE: {  // actions/WeightedMove.cpp:45-106
+            if (a.life > 0) {
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_MOVE));
+                if (r < moveProb) {
+                    int c = a.cell;
+                    int nreal = nNbr[c];
+                    size_t off = (size_t)c * (maxNeigh + 1);
+                    int pick = -1;
+                    uint32_t u2 = draw(a.id, STREAM_ACT1, L1_MOVE2);
+                    if (W[off] == W[off + nreal]) {
+                        pick = (int)u2int(u2, 0, nreal + 1);
+                    } else {
+                        double r2 = u2d(u2) * W[off + nreal];
+                        for (int k = 0; k < nreal + 1; k++) if (r2 < W[off + k]) { pick = k; break; }
+                    }
+                    if (pick > 0) {
+                        int to = nbr[(size_t)c * maxNeigh + pick - 1];
+                        if (to >= 0) {
+                            bool iced = env.count("Ice") && env["Ice"][to] != 0;
+                            if (!iced) registerMove(c, i, to);
+                        }
+                    }
+                }
+            }
+            break;
+        }
+        case A_FERTILITY: {  // actions/Fertility.cpp:49-74 (overwrites the whole life state, incl. the MOVING bit)
+            if (a.life > 0) {
+                if (a.gender == 0) {
+                    a.life = (a.age > fertMinAge && a.age < fertMaxAge && (t - a.lastBirth) > fertInterbirth) ? LIFE_FERTILE : LIFE_ALIVE;
+                } else {
+                    a.life = (a.age > fertMinAge) ? LIFE_FERTILE : LIFE_ALIVE;
+                }
+            }
+            break;
+        }
+        case A_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168 then LinearDeath.cpp:131-153
+            if (a.life > 0) {
+                int c = a.cell;
+                if (B[c] > 0) {
+                    if (a.gender == 0 && a.mate >= 0) {
+                        double r = u2d(draw(a.id, STREAM_ACT0, L0_BIRTH));
+                        if (r < B[c]) registerBirth(c, i, a.mate);
+                    }
+                } else if (B[c] < 0) {
+                    double r = u2d(draw(a.id, STREAM_ACT0, L0_BIRTH));
+                    if (r < -B[c]) registerDeath(i);
+                }
+            }
+            if (a.life > 0) {
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_DEATH2));
+                if (r < D[a.cell]) registerDeath(i);
+            }
+            break;
+        }
+        case A_SINGLEEVAL:
+        case A_RANDOMPAIR:
+            break;  // execute() is empty for these (actions/Action.h:36 default)
+        }
+    }
+
+    // action order: priority ascending, same priority in name order (core/SPopulation.cpp:249-257 iterates a
+    // std::map<string,int>; core/Prioritizer.cpp:19-30 appends in that order)
+    std::vector<const Action *> ordered() const {
+        std::vector<const Action *> v;
+        for (auto &a : actions) if (a.prio >= 0) v.push_back(&a);
+        std::stable_sort(v.begin(), v.end(), [](const Action *x, const Action *y) {
+            if (x->prio != y->prio) return x->prio < y->prio;
+            return x->name < y->name;
+        });
+        return v;
+    }
+
+    // ---- the step ------------------------------------------------------------------------------
+    int initializeStep(float t) {  // core/SPopulation.cpp:394-417
+        curTime = t;
+        levelsDone.clear();
+        for (const Action *a : ordered()) {
+            if (!a->enabled) continue;
+            switch (a->kind) {
+            case A_VERHULST: verhulstInit(); break;
+            case A_RANDOMPAIR: randomPairInit(); break;
+            case A_SINGLEEVAL: evaluatorInit(); break;
+            default: break;
+            }
+        }
+        return 0;
+    }
+    int doActions(unsigned prio, float t) {  // core/SPopulation.cpp:554-577
+        for (const Action *a : ordered()) {
+            if ((unsigned)a->prio != prio || !a->enabled) continue;
+            for (int i = 0; i < hi(); i++) {
+                if (active[i] && slots[i].life > LIFE_DEAD) execute(*a, i, t);
+            }
+        }
+        return 0;
+    }
+
+    // core/SPopulation.cpp:880-918 (createAgentAtIndex + resetAgent) and populations/tut_EnvironAltPop.cpp:141-149
+    void makeBaby(int slot, int cell, int64_t id, uint32_t genderDraw) {
+        Agent &b = slots[slot];
+        b.id = id;
+        b.life = LIFE_ALIVE;
+        b.cell = cell;
+        b.birth = curTime;
+        b.gender = (uint8_t)(2 * u2d(genderDraw));
+        if (b.gender == 0) b.life = LIFE_FERTILE;
+        b.age = 0.0f;
+        b.lastBirth = 0.0f;
+        b.mate = -3;
+    }
+
+    // core/SPopulation.cpp:596-724 recycleDeadSpaceNew (+ performBirths :778-815, performDeaths :974-989)
+    void recycleDeadSpace() {
+        size_t nBirths = birthList.size() / 3, nDeaths = deathList.size();
+        stepBirths = nBirths; stepDeaths = nDeaths;
+        totBirths += nBirths; totDeaths += nDeaths;
+        // counter mode: newborn id = nextID + rank of (cell, mother id) among this step's births
+        std::vector<int64_t> babyId(nBirths);
+        if (mode == QOR_MODE_COUNTER) {
+            std::vector<size_t> ord(nBirths);
+            for (size_t k = 0; k < nBirths; k++) ord[k] = k;
+            std::sort(ord.begin(), ord.end(), [&](size_t x, size_t y) {
+                int cx = birthList[3 * x], cy = birthList[3 * y];
+                if (cx != cy) return cx < cy;
+                return slots[birthList[3 * x + 1]].id < slots[birthList[3 * y + 1]].id;
+            });
+            for (size_t r = 0; r < nBirths; r++) babyId[ord[r]] = nextID + (int64_t)r;
+            nextID += (int64_t)nBirths;
+        }
+        size_t nReuse = std::min(prevDead.size(), nBirths);
+        auto born = [&](int slot, size_t k) {
+            int64_t id;
+            uint32_t g;
+            if (mode == QOR_MODE_WELL) {  // IDGen::getID with one thread (core/IDGen.h:28), then the gender draw
+                id = nextID++;
+                g = well.next();
+            } else {
+                id = babyId[k];
+                uint32_t o[4];
+                draw4(id, STREAM_BABY, o);
+                g = o[0];
+            }
+            makeBaby(slot, birthList[3 * k], id, g);
+        };
+        for (size_t k = 0; k < nReuse; k++) born(prevDead[k], k);          // babies into last step's dead slots
+        for (size_t k = nReuse; k < nBirths; k++) born(allocSlot(), k);     // remaining births: lowest free index
+        for (size_t k = nReuse; k < prevDead.size(); k++) freeSlot(prevDead[k]);  // leftover dead are unlinked
+        prevDead = deathList;
+        for (int i : prevDead) slots[i].life = LIFE_DEAD;
+    }
+    // core/SPopulation.cpp:1014-1027,1058-1092
+    void performMoves() {
+        stepMoves = moveList.size() / 3;
+        totMoves += stepMoves;
+        for (size_t k = 0; k < moveList.size(); k += 3) {
+            Agent &a = slots[moveList[k + 1]];
+            a.cell = moveList[k + 2];
+            a.life &= ~LIFE_MOVING;
+        }
+    }
+    int finalizeStep() {  // core/SPopulation.cpp:439-477
+        for (const Action *a : ordered()) {
+            if (a->enabled && a->kind == A_SINGLEEVAL) evalNeedUpdate = false;  // actions/SingleEvaluator.cpp:125-130
+        }
+        recycleDeadSpace();
+        performMoves();
+        updateNumAgentsPerCell();
+        birthList.clear(); deathList.clear(); moveList.clear();
+        stepIndex++;
+        return 0;
+    }
+    int step(float t) {  // core/PopLooper.cpp:166-202 for one population
+        initializeStep(t);
+        std::vector<unsigned> levels;
+        for (const Action *a : ordered()) if (levels.empty() || levels.back() != (unsigned)a->prio) levels.push_back((unsigned)a->prio);
+        for (unsigned l : levels) doActions(l, t);
+        return finalizeStep();
+    }
+    // populations/tut_EnvironAltPop.cpp:93-127
+    int updateEvent(int ev, float) {
+        if (ev == EVENT_ID_GEO) {
+            const std::vector<double> &alt = env["Altitude"];
+            const std::vector<double> *ice = env.count("Ice") ? &env["Ice"] : nullptr;
+            for (int i = 0; i < hi(); i++) {
+                if (active[i] && slots[i].life > LIFE_DEAD) {
+                    int c = slots[i].cell;
+                    if (alt[c] < 0 || (ice && (*ice)[c] > 0)) registerDeath(i);
+                }
+            }
+            recycleDeadSpace();
+            updateNumAgentsPerCell();
+            birthList.clear(); deathList.clear(); moveList.clear();
+            evalNeedUpdate = true;  // actions/SingleEvaluator.cpp:332-346, trigger id EVENT_ID_GEO
+        }
+        return 0;
+    }
+};
+
+// =================================================================================================
+extern "C" {
+
+qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode) {
+    qor_pop *p = new qor_pop;
+    p->popClass = pop_class;
+    p->nCells = n_cells;
+    p->maxNeigh = max_neigh;
+    p->mode = mode;
+    p->counts.assign(n_cells, 0);
+    p->B.assign(n_cells, 0.0);
+    p->D.assign(n_cells, 0.0);
+    p->W.assign((size_t)n_cells * (max_neigh + 1), 0.0);
+    if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else {
+        delete p;
+        return nullptr;
+    }
+    static const uint32_t zero[16] = {0};
+    qor_set_seed(p, zero);
+    return p;
+}
+
+void qor_destroy(qor_pop *p) { delete p; }
+
+int qor_set_cells(qor_pop *p, const int32_t *nbr, const int32_t *global_id) {
+    size_t n = (size_t)p->nCells * p->maxNeigh;
+    p->nbr.assign(nbr, nbr + n);
+    p->nNbr.assign(p->nCells, 0);
+    p->gid.resize(p->nCells);
+    for (int c = 0; c < p->nCells; c++) {
+        int k = 0;
+        for (int j = 0; j < p->maxNeigh; j++) if (nbr[(size_t)c * p->maxNeigh + j] >= 0) k++;
+        p->nNbr[c] = (uint8_t)k;
+        p->gid[c] = global_id ? global_id[c] : c;
+    }
+    return 0;
+}
+
+int qor_set_env_array(qor_pop *p, const char *name, const double *v, int64_t n) {
+    if (n != p->nCells) return -1;
+    p->env[name].assign(v, v + n);
+    return 0;
+}
+
+int qor_set_attribute(qor_pop *p, const char *name, double v) {
+    std::string s(name);
+    if (s == "ATanDeath_max_age") p->atanMaxAge = v;
+    else if (s == "ATanDeath_range") p->atanRange = v;
+    else if (s == "ATanDeath_slope") p->atanSlope = v;
+    else if (s == "OAD_max_age") p->oadMaxAge = v;
+    else if (s == "OAD_uncertainty") p->oadUncertainty = v;
+    else if (s == "WeightedMove_prob") p->moveProb = v;
+    else if (s == "Fertility_min_age") p->fertMinAge = (float)v;
+    else if (s == "Fertility_max_age") p->fertMaxAge = (float)v;
+    else if (s == "Fertility_interbirth") p->fertInterbirth = (float)v;
+    else if (s == "Verhulst_b0") p->vB0 = v;
+    else if (s == "Verhulst_d0") p->vD0 = v;
+    else if (s == "Verhulst_theta") p->vTheta = v;
+    else if (s == "Verhulst_K") p->vK = v;
+    else return -1;
+    return 0;
+}
+
+int qor_set_attribute_str(qor_pop *p, const char *name, const char *v) {
+    if (std::string(name) == "AltCapPref") {
+        p->havePoly = p->altPref.parse(v);
+        return p->havePoly ? 0 : -1;
+    }
+    char *e;
+    double d = strtod(v, &e);
+    if (e == v) return -1;
+    return qor_set_attribute(p, name, d);
+}
+
+int qor_set_prio(qor_pop *p, const char *action, int prio) {
+    Action *a = p->find(action);
+    if (!a) return -1;
+    a->prio = prio;
+    return 0;
+}
+
+int qor_enable_action(qor_pop *p, const char *action, int enabled) {
+    Action *a = p->find(action);
+    if (!a) return -1;
+    a->enabled = enabled != 0;
+    return 0;
+}
+
+int qor_set_seed(qor_pop *p, const uint32_t *st) {
+    memcpy(p->state16, st, sizeof(p->state16));
+    uint32_t tmp[16];
+    for (int j = 0; j < 16; j++) tmp[j] = st[(0 + 13 * j) % 16];  // thread 0, core/SPopulation.cpp:171-176
+    p->well.seed(tmp);
+    p->key[0] = p->key[1] = 0;
+    for (int j = 0; j < 16; j += 2) { p->key[0] ^= st[j]; p->key[1] ^= st[j + 1]; }
+    return 0;
+}
+
+int qor_add_agents(qor_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth,
+                   const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life) {
+    for (int64_t j = 0; j < n; j++) {
+        if (cell[j] < 0 || cell[j] >= p->nCells) return -1;
+        int i = p->allocSlot();
+        Agent &a = p->slots[i];
+        a.life = life ? life[j] : LIFE_ALIVE;
+        a.cell = cell[j];
+        a.id = id[j];
+        a.birth = birth[j];
+        a.gender = gender[j];
+        a.age = age ? age[j] : 0.0f;
+        a.lastBirth = last_birth ? last_birth[j] : 0.0f;
+        a.mate = -3;
+        if (a.id > p->maxID) p->maxID = a.id;
+    }
+    return 0;
+}
+
+int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDeath.cpp:49-59 + app/Simulator.cpp:107-111
+    p->atanScale = (PI / 2 - ATAN_EPS) / atan(p->atanSlope * p->atanRange);
+    p->nextID = p->maxID + 1;
+    p->updateNumAgentsPerCell();
+    return 0;
+}
+
+int qor_initialize_step(qor_pop *p, float t) { return p->initializeStep(t); }
+int qor_do_actions(qor_pop *p, unsigned prio, float t) { return p->doActions(prio, t); }
+int qor_finalize_step(qor_pop *p) { return p->finalizeStep(); }
+int qor_step(qor_pop *p, float t) { return p->step(t); }
+int qor_update_event(qor_pop *p, int ev, float t) { return p->updateEvent(ev, t); }
+int qor_flush_events(qor_pop *, float) { return 0; }
+
+int64_t qor_get_num_agents_effective(qor_pop *p) { return p->numUsed - (int64_t)p->prevDead.size(); }  // core/SPopulation.h:148
+
+int qor_get_num_agents_array(qor_pop *p, uint64_t *out) {
+    memcpy(out, p->counts.data(), sizeof(uint64_t) * p->nCells);
+    return 0;
+}
+
+int64_t qor_get_agents(qor_pop *p, int64_t cap, int32_t *cell, int64_t *id, float *birth, uint8_t *gender,
+                       float *age, float *last_birth, uint32_t *life, int64_t *mate_id, int32_t *slot) {
+    int64_t k = 0;
+    for (int i = 0; i < p->hi(); i++) {
+        if (!p->active[i] || p->slots[i].life == LIFE_DEAD) continue;
+        const Agent &a = p->slots[i];
+        if (k < cap) {
+            if (cell) cell[k] = a.cell;
+            if (id) id[k] = a.id;
+            if (birth) birth[k] = a.birth;
+            if (gender) gender[k] = a.gender;
+            if (age) age[k] = a.age;
+            if (last_birth) last_birth[k] = a.lastBirth;
+            if (life) life[k] = a.life;
+            if (mate_id) mate_id[k] = (a.mate >= 0) ? p->slots[a.mate].id : (int64_t)a.mate;
+            if (slot) slot[k] = i;
+        }
+        k++;
+    }
+    return k;
+}
+
+int qor_get_env_weights(qor_pop *p, double *out) {
+    memcpy(out, p->W.data(), sizeof(double) * p->W.size());
+    return 0;
+}
+
+int qor_get_birth_death_probs(qor_pop *p, double *b, double *d) {
+    memcpy(b, p->B.data(), sizeof(double) * p->nCells);
+    memcpy(d, p->D.data(), sizeof(double) * p->nCells);
+    return 0;
+}
+
+int qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out) {
+    for (int i = 0; i < n; i++) out[i] = 0.5 + p->atanScale * atan(p->atanSlope * (age[i] - p->atanMaxAge)) / PI;
+    return 0;
+}
+
+int qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves) {
+    if (births) *births = p->stepBirths;
+    if (deaths) *deaths = p->stepDeaths;
+    if (moves) *moves = p->stepMoves;
+    return 0;
+}
+
+void qor_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox(ctr, key, out); }
+
+int qor_well_sequence(const uint32_t *state16, int n, uint32_t *out) {
+    Well512 w;
+    w.seed(state16);
+    for (int i = 0; i < n; i++) out[i] = w.next();
+    return 0;
+}
+
+int qor_polyline_eval(const char *def, int n, const double *x, double *out, int float_cast) {
+    PolyLine pl;
+    if (!pl.parse(def)) return -1;
+    for (int i = 0; i < n; i++) out[i] = float_cast ? pl.val((float)x[i]) : pl.val(x[i]);
+    return 0;
+}
+
+}  // extern "C"
