@@ -1,0 +1,150 @@
+/* qhg_b200.h -- C ABI of the B200-native per-step agent update for QHG4 populations.
+ *
+ * One `qhgb_pop` replaces one `SPopulation<T>` object of the reference behind its `PopBase`
+ * interface (core/PopBase.h:16-121): the host keeps calling initializeStep / doActions /
+ * finalizeStep once per step from ONE thread; agent storage, every action and the
+ * birth/death/move bookkeeping run as sm_100a CUDA kernels on device-resident
+ * structure-of-arrays state.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions follow the reference's: every call returns int 0 on success and non-zero
+ * (normally -1) on error, results may be summed by the caller (core/PopLooper.cpp:166-202),
+ * no exception crosses the boundary; `qhgb_last_error()` gives the text the reference would
+ * have printed.  All paths cited below are relative to /root/reference/QHG4/.
+ *
+ * There is NO CPU fallback: without a CUDA device `qhgb_create` fails.
+ */
+#ifndef QHG_B200_H
+#define QHG_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qhgb_pop qhgb_pop;
+
+/* event ids that cross the boundary (utils_qhg/EventConsts.h:14-36) */
+#define QHGB_EVENT_ID_GEO      2
+#define QHGB_EVENT_ID_CLIMATE  3
+#define QHGB_EVENT_ID_VEG      4
+#define QHGB_EVENT_ID_NAV      5
+#define QHGB_EVENT_ID_FLUSH   20
+
+/* life states in uploaded / downloaded agent records (core/SPopulation.h:70-74) */
+#define QHGB_LIFE_STATE_DEAD     0u
+#define QHGB_LIFE_STATE_ALIVE    1u
+#define QHGB_LIFE_STATE_FERTILE  5u
+
+/* per-step totals, the numbers the reference prints from recycleDeadSpaceNew / performMoves
+ * (core/SPopulation.cpp:605-607,1087) plus the live count */
+typedef struct qhgb_step_stats {
+    int64_t num_agents;   /* live agents after the step = getNumAgentsEffective(), core/SPopulation.h:148 */
+    int64_t births;
+    int64_t deaths;
+    int64_t moves;
+    int64_t next_id;      /* next agent id to be handed out (replaces IDGen, core/IDGen.h:17-36) */
+    int64_t steps_done;
+} qhgb_step_stats;
+
+/* ---- life cycle --------------------------------------------------------------------------------
+ * qhgb_create replaces the plugin's createPop(...) -> `new <Pop>(pCG, pPopFinder, iLayerSize, apIDG,
+ * aulState, aiSeeds)` (dynpops/WrapperTemplate.cpp.tmp:24-30, core/SPopulation.cpp:45-87).
+ * `pop_class` selects the action set and wiring of a shipped population class, e.g.
+ * "tut_EnvironAltPop" (populations/tut_EnvironAltPop.cpp:24-53).  `capacity_hint` = expected maximum
+ * number of live agents (0: grow on demand); it replaces iLayerSize. */
+int  qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, int64_t capacity_hint, qhgb_pop **out);
+int  qhgb_destroy(qhgb_pop *p);                     /* ~SPopulation, core/SPopulation.cpp:93-134 */
+const char *qhgb_last_error(void);
+const char *qhgb_version(void);
+
+/* ---- grid and environment (what the actions read through SCellGrid* / Geography*) -----------------
+ * nbr: n_cells*max_neigh cell indices, -1 padded  = SCell::m_aNeighbors (core/SCell.h:9-13);
+ * global_id: n_cells ids or NULL for id == index   = SCell::m_iGlobalID. */
+int  qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id);
+/* name: "Altitude" (Geography::m_adAltitude), "Ice" (m_abIce, non-zero = ice), "Water", "Coastal", "Latitude",
+ * "Longitude" (core/Geography.h:31-39), "NPP" ... one double per cell.  Calling it again after preLoop is
+ * how a changed array reaches the device; follow it with qhgb_update_event as the host does
+ * (app/Simulator.cpp:668-753). */
+int  qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n);
+
+/* ---- parameters --------------------------------------------------------------------------------
+ * Attribute names are the reference's XML / QDF attribute names, e.g. "ATanDeath_max_age",
+ * "Verhulst_K", "WeightedMove_prob" (actions/ATanDeath.h:9-12, actions/Verhulst.h:9-13, ...).
+ * qhgb_set_attribute     = Action<T>::tryGetAttributes / modifyAttributes for numeric values
+ *                          (actions/Action.h:27-58, core/SPopulation.cpp "modifyAttributes");
+ * qhgb_set_attribute_str = the same for string-valued ones (poly-lines such as "AltCapPref",
+ *                          utils/PolyLine.cpp:92-127);
+ * qhgb_set_prio          = one <prio name= value=> entry -> Prioritizer::setPrio (core/Prioritizer.cpp:19-30);
+ *                          action names are "Name" or "Name[id]" (actions/Action.cpp:11-19);
+ * qhgb_enable_action     = PopBase::enableAction / disableAction (core/PopBase.h:22-24);
+ * qhgb_set_seed          = the 16-word WELL state argument `aulState` of the constructor. */
+int  qhgb_set_attribute(qhgb_pop *p, const char *name, double value);
+int  qhgb_set_attribute_str(qhgb_pop *p, const char *name, const char *value);
+int  qhgb_set_prio(qhgb_pop *p, const char *action_name, int prio);
+int  qhgb_enable_action(qhgb_pop *p, const char *action_name, int enabled);
+int  qhgb_set_seed(qhgb_pop *p, const uint32_t *state16);
+
+/* ---- agents ------------------------------------------------------------------------------------
+ * Structure-of-arrays view of the reference's agent record (core/SPopulation.h:43-50 +
+ * populations/tut_EnvironAltPop.h:16-21).  qhgb_add_agents = SPopulation::addAgent /
+ * readAgentDataQDF (core/SPopulation.cpp:1149-1166,1689-1741); agents with life == 0 are skipped.
+ * qhgb_get_agents = what preWrite + writeAgentDataQDFSafe hand to the file layer
+ * (core/SPopulation.cpp:1465-1568): live agents, grouped by cell; any pointer may be NULL.
+ * It returns the number of live agents (and fills at most `cap` of them), or -1. */
+int     qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
+                        const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life_state);
+int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
+                        uint8_t *gender, float *age, float *last_birth, uint32_t *life_state, int64_t *mate_id);
+
+/* ---- the step (PopBase virtuals called by PopLooper::doStep, core/PopLooper.cpp:166-202) -----------
+ * qhgb_pre_loop        = PopBase::preLoop (core/SPopulation.cpp:273-292): uploads are sealed, agents are binned
+ *                        per cell, per-cell counts and derived parameters are computed.
+ * qhgb_initialize_step = initializeStep(t) (core/SPopulation.cpp:394-417): Verhulst b/d from last step's counts,
+ *                        pairing, cell weights if the environment changed.
+ * qhgb_do_actions      = doActions(prio, t) (core/SPopulation.cpp:554-577), once per priority level.  The device
+ *                        runs all levels that were requested during the step as ONE fused pass when
+ *                        qhgb_finalize_step is called; order and visibility rules are the reference's.
+ * qhgb_finalize_step   = finalizeStep() (core/SPopulation.cpp:439-477): births, deaths, moves, re-binning, counts.
+ * qhgb_step            = the three above for all of this population's levels (PopLooper::doStep for one pop). */
+int  qhgb_pre_loop(qhgb_pop *p);
+int  qhgb_initialize_step(qhgb_pop *p, float t);
+int  qhgb_do_actions(qhgb_pop *p, unsigned prio, float t);
+int  qhgb_finalize_step(qhgb_pop *p);
+int  qhgb_step(qhgb_pop *p, float t);
+/* n steps at t0, t0+1, ... without returning to the host in between (the bench's device-resident loop) */
+int  qhgb_run(qhgb_pop *p, float t0, int n_steps);
+int  qhgb_synchronize(qhgb_pop *p);
+
+/* updateEvent(id, data, t) / flushEvents(t) (populations/tut_EnvironAltPop.cpp:93-127) */
+int  qhgb_update_event(qhgb_pop *p, int event_id, float t);
+int  qhgb_flush_events(qhgb_pop *p, float t);
+
+/* ---- state read back by the host -------------------------------------------------------------------
+ * getNumAgentsEffective / getNumAgentsTotal (core/SPopulation.h:147-148), getNumAgentsArray / getNumAgents(cell)
+ * (:145-146; one ulong per cell). */
+int64_t qhgb_get_num_agents_effective(qhgb_pop *p);
+int     qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out);
+int     qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out);
+/* parity probes for the deterministic sub-steps: the arrays the reference keeps in
+ * m_adEnvWeights (n_cells*(max_neigh+1) doubles, actions/SingleEvaluator.cpp:174-243), LinearBirth::m_adB /
+ * LinearDeath::m_adD (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and the ATanDeath
+ * probability of actions/ATanDeath.cpp:75 evaluated on the device for given float ages. */
+int  qhgb_get_env_weights(qhgb_pop *p, double *out);
+int  qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d);
+int  qhgb_atan_death_prob(qhgb_pop *p, int n, const float *age, double *out);
+
+/* ---- measurement hooks ------------------------------------------------------------------------------
+ * number of kernels launched by this population since creation, and the CUDA stream they run on */
+int64_t qhgb_get_launch_count(qhgb_pop *p);
+void   *qhgb_get_stream(qhgb_pop *p);
+/* device time (ms, CUDA events on the population's stream) accumulated per kernel name since the last reset;
+ * names/ms/calls hold up to cap entries; returns the number of kernels known */
+int  qhgb_get_kernel_times(qhgb_pop *p, int cap, const char **names, double *ms, int64_t *calls);
+int  qhgb_reset_kernel_times(qhgb_pop *p, int enable);
+/* CUDA events on the population's stream: record into slot 0..7, elapsed ms between two recorded slots (-1 on error) */
+int    qhgb_event_record(qhgb_pop *p, int slot);
+double qhgb_event_elapsed_ms(qhgb_pop *p, int slot_a, int slot_b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -73,6 +73,45 @@ inline void philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// atan used by the counter mode: argument reduction + odd polynomial (the classic fdlibm scheme), evaluated in
+// exactly the operation order of qhg4_b200/csrc/qhg_rng.cuh::atan_rn (this file is built with
+// -ffp-contract=off, the device code with explicitly rounded intrinsics), so both give identical bits.
+// WELL mode keeps libm's atan like the reference.
+inline double atan_portable(double x) {
+    static const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                                  -1.11111104054623557880e-01, 9.09088713343650656196e-02, -7.69187620504482999495e-02,
+                                  6.66107313738753120669e-02, -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                                  -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    static const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    static const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    const bool neg = x < 0;
+    const double ax = std::fabs(x);
+    int idx;
+    double xx;
+    if (ax >= 73786976294838206464.0) { double r = hi[3] + lo[3]; return neg ? -r : r; }
+    if (ax < 0.4375) {
+        if (ax < 7.450580596923828125e-9) return x;
+        idx = -1; xx = ax;
+    } else if (ax < 1.1875) {
+        if (ax < 0.6875) { idx = 0; xx = (2.0 * ax + -1.0) / (2.0 + ax); }
+        else             { idx = 1; xx = (ax + -1.0) / (ax + 1.0); }
+    } else {
+        if (ax < 2.4375) { idx = 2; xx = (ax + -1.5) / (1.0 + 1.5 * ax); }
+        else             { idx = 3; xx = -1.0 / ax; }
+    }
+    const double z = xx * xx, w = z * z;
+    double s1 = aT[10];
+    s1 = aT[8] + w * s1; s1 = aT[6] + w * s1; s1 = aT[4] + w * s1; s1 = aT[2] + w * s1; s1 = aT[0] + w * s1;
+    s1 = z * s1;
+    double s2 = aT[9];
+    s2 = aT[7] + w * s2; s2 = aT[5] + w * s2; s2 = aT[3] + w * s2; s2 = aT[1] + w * s2;
+    s2 = w * s2;
+    double r;
+    if (idx < 0) r = xx + -(xx * (s1 + s2));
+    else r = hi[idx] + -(((xx * (s1 + s2)) + -lo[idx]) + -xx);
+    return neg ? -r : r;
+}
+
 // draw streams of the counter mode (mirrored in qhg4_b200/csrc/qhg_rng.cuh)
 enum { STREAM_ACT0 = 0, STREAM_ACT1 = 1, STREAM_PAIR = 2, STREAM_BABY = 3 };
 // lanes of STREAM_ACT0 / STREAM_ACT1
@@ -313,7 +352,8 @@ struct qor_pop {
         case A_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
             if (a.life > 0) {
                 a.age = t - a.birth;
-                double p = 0.5 + atanScale * atan(atanSlope * (a.age - atanMaxAge)) / PI;
+                double x = atanSlope * (a.age - atanMaxAge);
+                double p = 0.5 + atanScale * (mode == QOR_MODE_WELL ? atan(x) : atan_portable(x)) / PI;
                 double r = u2d(draw(a.id, STREAM_ACT0, L0_DEATH));
                 if (r < p) registerDeath(i);
             }
@@ -701,7 +741,10 @@ int qor_get_birth_death_probs(qor_pop *p, double *b, double *d) {
 }
 
 int qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out) {
-    for (int i = 0; i < n; i++) out[i] = 0.5 + p->atanScale * atan(p->atanSlope * (age[i] - p->atanMaxAge)) / PI;
+    for (int i = 0; i < n; i++) {
+        double x = p->atanSlope * (age[i] - p->atanMaxAge);
+        out[i] = 0.5 + p->atanScale * (p->mode == QOR_MODE_WELL ? atan(x) : atan_portable(x)) / PI;
+    }
     return 0;
 }
 

@@ -1,0 +1,509 @@
+// qhg_kernels.cuh -- sm_100a kernels of the per-step agent update (device side only).
+//
+// Layout in HBM: agents are a structure of arrays kept BINNED BY CELL (cellStart[c]..cellStart[c+1]
+// is the contiguous segment of cell c), double buffered; one step reads the current buffer and
+// scatters survivors, movers and newborns into the other one (counting sort by destination cell).
+// Per-cell arrays (neighbours, counts, b/d probabilities, cumulated weights) are small (a few MB)
+// and stay L2 resident.  See DESIGN.md for the byte accounting of every kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "qhg_rng.cuh"
+
+namespace qhg {
+
+constexpr int MAXN = 6;            // core/SCell.h:4 MAX_NEIGH
+constexpr int WSTRIDE = MAXN + 1;  // weight row: own cell + 6 neighbours (actions/SingleEvaluator.cpp:216-243)
+constexpr int MAX_POLY = 16;
+constexpr int MAX_OPS = 16;
+
+// agent flag byte: gender and the FERTILE bit of the reference's life state (core/SPopulation.h:70-74)
+constexpr uint8_t F_MALE = 1, F_FERTILE = 2, F_BORN = 4;  // F_BORN only in the per-step decision byte
+
+enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN };
+
+struct AgentArrays {
+    int64_t *id;
+    float *birth;
+    float *lastBirth;
+    int32_t *cell;
+    uint8_t *flags;
+    float *age;  // only maintained when the action set does not refresh the age before it is read
+};
+
+struct DevStats {
+    int nAgents;   // live agents in the current buffer
+    int nNew;      // live agents after the running step
+    int nBirths, nDeaths, nMoves;
+    int overflow;
+    unsigned step;  // counter word of the random streams; +1 per finalizeStep
+    int pad;
+    long long nextID;
+};
+
+struct ActParams {
+    int nOps;
+    uint8_t ops[MAX_OPS];
+    float t;
+    int storeAge;
+    // ATanDeath (actions/ATanDeath.cpp:49-59,66-90)
+    double atanMaxAge, atanSlope, atanScale, atanXlo, atanXhi;
+    // OldAgeDeath (actions/OldAgeDeath.cpp:48-67)
+    double oadMaxAge, oadLo, oadHi;
+    // WeightedMove (actions/WeightedMove.cpp:45-106)
+    double moveProb;
+    // Fertility (actions/Fertility.cpp:49-74)
+    float fertMinAge, fertMaxAge, fertInterbirth;
+    RngKey key;
+};
+
+struct PolyLineDev {  // utils/PolyLine.cpp:60-89
+    int nseg;  // 0 => identity
+    double x[MAX_POLY], v[MAX_POLY], a[MAX_POLY];
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// counter[key] += (number of lanes with this key); returns this lane's rank inside the cell.
+// Agents are binned by cell, so a warp usually touches 1-3 distinct keys: one atomic per key, not per lane.
+__device__ __forceinline__ int warp_agg_inc(int *counter, int key, bool active) {
+    unsigned act = __ballot_sync(0xffffffffu, active);
+    int r = 0;
+    if (active) {
+        unsigned peers = __match_any_sync(act, key);
+        int leader = __ffs(peers) - 1;
+        int base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&counter[key], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        r = base + __popc(peers & lanemask_lt());
+    }
+    return r;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-cell: Verhulst birth and death probabilities from last step's counts
+// (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and reset of the step's counters
+__global__ void k_cell_init(int nCells, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
+                            double b0, double d0, double theta, double K, int doVerhulst,
+                            int *__restrict__ newCount, int *__restrict__ birthCount, int *__restrict__ nFert) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        if (doVerhulst) {
+            double q = __ddiv_rn((double)count[c], K);
+            B[c] = __dadd_rn(b0, __dmul_rn(__dadd_rn(theta, -b0), q));
+            D[c] = __dadd_rn(d0, __dmul_rn(__dadd_rn(theta, -d0), q));
+        }
+        newCount[c] = 0;
+        birthCount[c] = 0;
+        nFert[2 * c] = 0;
+        nFert[2 * c + 1] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell weights: SingleEvaluator::calcValues (actions/SingleEvaluator.cpp:174-207) ...
+__device__ __forceinline__ double polyline_val(const PolyLineDev &pl, double fx) {
+    if (pl.nseg == 0) return fx;
+    if (fx >= pl.x[pl.nseg]) return pl.v[pl.nseg];
+    int i = 0;
+    while (i <= pl.nseg && fx > pl.x[i]) i++;
+    if (i == 0) return pl.v[0];
+    if (i <= pl.nseg) return __dadd_rn(pl.v[i - 1], __dmul_rn(pl.a[i - 1], __dadd_rn(fx, -pl.x[i - 1])));
+    return pl.v[pl.nseg];
+}
+
+__global__ void k_weights_own(int nCells, const double *__restrict__ in, const uint8_t *__restrict__ ice,
+                              PolyLineDev pl, int usePoly, double *__restrict__ W) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        double v = 0;
+        if (!ice || !ice[c]) {
+            double dv = usePoly ? polyline_val(pl, (double)(float)in[c]) : in[c];  // the (float) cast is the reference's, :185
+            v = (dv > 0) ? dv : 0;
+        }
+        W[(size_t)c * WSTRIDE] = v;
+    }
+}
+
+// ... and exchangeAndCumulate (:216-243): row c = running sum over [own, n1..n6], missing neighbours count 0
+__global__ void k_weights_cumulate(int nCells, const int *__restrict__ nbr, double *__restrict__ W, int cumulate) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        double w = W[(size_t)c * WSTRIDE];
+#pragma unroll
+        for (int k = 0; k < MAXN; k++) {
+            int n = nbr[(size_t)c * MAXN + k];
+            double cw = (n >= 0) ? W[(size_t)n * WSTRIDE] : 0.0;
+            cw = (cw > 0) ? cw : 0;
+            w = cumulate ? __dadd_rn(w, cw) : cw;
+            W[(size_t)c * WSTRIDE + k + 1] = w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pairing (RandomPair::initialize/findMates, actions/RandomPair.cpp:107-128,146-279), counter-mode law:
+// inside a cell the fertile females and the fertile males are ranked by (random key, id); equal ranks mate.
+__global__ void k_pair_keys(const DevStats *__restrict__ st, AgentArrays a, RngKey key, uint32_t *__restrict__ pkey,
+                            int *__restrict__ mate, int *__restrict__ nFert) {
+    const int n = st->nAgents;
+    const unsigned step = st->step;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        int i = i0 + threadIdx.x;
+        bool fert = false;
+        int slot = 0;
+        if (i < n) {
+            uint8_t f = a.flags[i];
+            mate[i] = -3;
+            fert = (f & F_FERTILE) != 0;
+            if (fert) {
+                pkey[i] = agent_draws(a.id[i], step, STREAM_PAIR, key).x;
+                slot = 2 * a.cell[i] + (f & F_MALE);
+            }
+        }
+        warp_agg_inc(nFert, slot, fert);
+    }
+}
+
+__global__ void k_pair_rank(const DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ cellStart,
+                            const uint32_t *__restrict__ pkey, int *__restrict__ prank, int *__restrict__ ranked) {
+    const int n = st->nAgents;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint8_t f = a.flags[i];
+        if (!(f & F_FERTILE)) continue;
+        int c = a.cell[i];
+        int s = cellStart[c], e = cellStart[c + 1];
+        uint32_t k = pkey[i];
+        int64_t id = a.id[i];
+        int r = 0;
+        for (int j = s; j < e; j++) {
+            uint8_t fj = a.flags[j];
+            if ((fj & (F_FERTILE | F_MALE)) != (f & (F_FERTILE | F_MALE))) continue;
+            uint32_t kj = pkey[j];
+            if (kj < k || (kj == k && a.id[j] < id)) r++;
+        }
+        prank[i] = r;
+        if (f & F_MALE) ranked[e - 1 - r] = i; else ranked[s + r] = i;
+    }
+}
+
+__global__ void k_pair_match(const DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ cellStart,
+                             const int *__restrict__ nFert, const int *__restrict__ prank, const int *__restrict__ ranked,
+                             int *__restrict__ mate) {
+    const int n = st->nAgents;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint8_t f = a.flags[i];
+        if (!(f & F_FERTILE)) continue;
+        int c = a.cell[i];
+        int np = min(nFert[2 * c], nFert[2 * c + 1]);
+        int r = prank[i];
+        if (r < np) mate[i] = (f & F_MALE) ? ranked[cellStart[c] + r] : ranked[cellStart[c + 1] - 1 - r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused per-agent pass: every enabled action in priority order (core/SPopulation.cpp:554-577 runs them as
+// separate passes; an action only touches its own agent, so one pass in the same order is equivalent).
+// Output per agent: destination cell (-1 = dead), rank inside the destination cell, new flag byte.
+__global__ void __launch_bounds__(256)
+k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate, ActParams P,
+          const int *__restrict__ nbr, const uint8_t *__restrict__ nNbr, const uint8_t *__restrict__ ice,
+          const double *__restrict__ alt, const double *__restrict__ W, const double *__restrict__ B,
+          const double *__restrict__ D, int *__restrict__ newCount, int *__restrict__ birthCount,
+          int *__restrict__ dest, int *__restrict__ rank, uint8_t *__restrict__ oflags) {
+    const int n = st->nAgents;
+    const unsigned step = st->step;
+    int nDead = 0, nMove = 0, nBorn = 0;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        bool alive = valid, born = false;
+        int c = 0, to = 0;
+        uint8_t f = 0;
+        if (valid) {
+            const int64_t id = a.id[i];
+            const float birth = a.birth[i];
+            c = a.cell[i];
+            f = a.flags[i];
+            to = c;
+            float age = P.storeAge ? a.age[i] : 0.0f;
+            bool moving = false;
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+            bool have0 = false, have1 = false;
+#pragma unroll 1
+            for (int k = 0; k < P.nOps; k++) {
+                if (!alive) break;
+                switch (P.ops[k]) {
+                case OP_GETOLD:  // actions/GetOld.cpp:37-48
+                    age = __fsub_rn(P.t, birth);
+                    break;
+                case OP_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
+                    age = __fsub_rn(P.t, birth);
+                    double x = __dmul_rn(P.atanSlope, __dadd_rn((double)age, -P.atanMaxAge));
+                    if (x > P.atanXlo) {  // below Xlo the probability is negative: nobody dies, no draw needed
+                        if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+                        bool dies = true;  // above Xhi the probability exceeds 1
+                        if (x < P.atanXhi) {
+                            double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(x)), 3.141592653589793));
+                            dies = u2d(r0.x) < p;
+                        }
+                        if (dies) alive = false;
+                    }
+                    break;
+                }
+                case OP_OLDAGEDEATH: {  // actions/OldAgeDeath.cpp:48-67
+                    age = __fsub_rn(P.t, birth);
+                    if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                    double r = u2range(r1.w, P.oadLo, P.oadHi);
+                    if ((double)age > __dadd_rn(P.oadMaxAge, r)) alive = false;
+                    break;
+                }
+                case OP_WEIGHTEDMOVE: {  // actions/WeightedMove.cpp:45-106
+                    if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+                    if (u2d(r0.y) < P.moveProb) {
+                        if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                        const int nreal = nNbr[c];
+                        const double *row = W + (size_t)c * WSTRIDE;
+                        int pick = -1;
+                        const double wmax = row[nreal];
+                        if (row[0] == wmax) {
+                            pick = (int)u2int(r1.x, 0, nreal + 1);
+                        } else {
+                            double r2 = __dmul_rn(u2d(r1.x), wmax);
+                            for (int q = 0; q < nreal + 1; q++) {
+                                if (r2 < row[q]) { pick = q; break; }
+                            }
+                        }
+                        if (pick > 0) {
+                            int dst = nbr[(size_t)c * MAXN + pick - 1];
+                            if (dst >= 0 && !(ice && ice[dst])) { to = dst; moving = true; }
+                        }
+                    }
+                    break;
+                }
+                case OP_FERTILITY: {  // actions/Fertility.cpp:49-74
+                    bool fert;
+                    if (!(f & F_MALE)) {
+                        fert = (age > P.fertMinAge) && (age < P.fertMaxAge) && (__fsub_rn(P.t, a.lastBirth[i]) > P.fertInterbirth);
+                    } else {
+                        fert = age > P.fertMinAge;
+                    }
+                    f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
+                    break;
+                }
+                case OP_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
+                    if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+                    const double b = B[c];
+                    if (b > 0) {
+                        if (!(f & F_MALE) && mate[i] >= 0) {
+                            if (u2d(r0.z) < b) born = true;
+                        }
+                    } else if (b < 0) {
+                        if (u2d(r0.z) < -b) alive = false;
+                    }
+                    if (alive && u2d(r0.w) < D[c]) alive = false;
+                    break;
+                }
+                case OP_DROWN:  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
+                    if (alt[c] < 0 || (ice && ice[c])) alive = false;
+                    break;
+                }
+            }
+            if (P.storeAge && alive) a.age[i] = age;  // moved with the agent by k_scatter
+            if (moving) nMove++;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
+            if (!alive) nDead++;
+            if (born) nBorn++;
+        }
+        int r = warp_agg_inc(newCount, to, alive);
+        warp_agg_inc(birthCount, c, born);
+        if (valid) {
+            dest[i] = alive ? to : -1;
+            rank[i] = r;
+            oflags[i] = (uint8_t)(f | (born ? F_BORN : 0));
+        }
+    }
+    nDead = warp_sum(nDead); nMove = warp_sum(nMove); nBorn = warp_sum(nBorn);
+    if ((threadIdx.x & 31) == 0) {
+        if (nDead) atomicAdd(&st->nDeaths, nDead);
+        if (nMove) atomicAdd(&st->nMoves, nMove);
+        if (nBorn) atomicAdd(&st->nBirths, nBorn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan over cells of (survivors + births) -> newStart, of births -> birthBase.
+// Two kernels: per-tile sums, then every tile adds the sums of the tiles before it.
+constexpr int SCAN_TILE = 2048;  // cells per block (256 threads x 8)
+
+__global__ void __launch_bounds__(256)
+k_scan_tiles(int nCells, const int *__restrict__ newCount, const int *__restrict__ birthCount, int2 *__restrict__ tileSums) {
+    __shared__ int sa[8], sb[8];
+    int base = blockIdx.x * SCAN_TILE;
+    int sumA = 0, sumB = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
+        int c = base + k;
+        if (c < nCells) { int b = birthCount[c]; sumA += newCount[c] + b; sumB += b; }
+    }
+    sumA = warp_sum(sumA); sumB = warp_sum(sumB);
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = sumA; sb[threadIdx.x >> 5] = sumB; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int A = 0, Bq = 0;
+        for (int w = 0; w < 8; w++) { A += sa[w]; Bq += sb[w]; }
+        tileSums[blockIdx.x] = make_int2(A, Bq);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_scan_apply(int nCells, int nTiles, const int *__restrict__ newCount, const int *__restrict__ birthCount,
+             const int2 *__restrict__ tileSums, int *__restrict__ newStart, int *__restrict__ birthBase,
+             int *__restrict__ count, DevStats *__restrict__ st, int capacity) {
+    __shared__ int sa[8], sb[8];
+    __shared__ int baseA, baseB;
+    // sum of the tiles before this one
+    int pa = 0, pb = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) { int2 v = tileSums[k]; pa += v.x; pb += v.y; }
+    pa = warp_sum(pa); pb = warp_sum(pb);
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = pa; sb[threadIdx.x >> 5] = pb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int A = 0, Bq = 0;
+        for (int w = 0; w < 8; w++) { A += sa[w]; Bq += sb[w]; }
+        baseA = A; baseB = Bq;
+    }
+    __syncthreads();
+    // each thread owns 8 consecutive cells
+    int c0 = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    int va[8], vb[8];
+    int ta = 0, tb = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int c = c0 + k;
+        int b = (c < nCells) ? birthCount[c] : 0;
+        int v = (c < nCells) ? newCount[c] + b : 0;
+        va[k] = ta; vb[k] = tb;
+        ta += v; tb += b;
+    }
+    // block exclusive scan of (ta, tb)
+    int ia = ta, ib = tb;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += xa; ib += xb; }
+    }
+    __syncthreads();
+    if (lane == 31) { sa[wid] = ia; sb[wid] = ib; }
+    __syncthreads();
+    int wa = 0, wb = 0;
+    for (int w = 0; w < wid; w++) { wa += sa[w]; wb += sb[w]; }
+    int exA = baseA + wa + ia - ta, exB = baseB + wb + ib - tb;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int c = c0 + k;
+        if (c < nCells) {
+            newStart[c] = exA + va[k];
+            birthBase[c] = exB + vb[k];
+            count[c] = newCount[c] + birthCount[c];
+        }
+    }
+    if (blockIdx.x == nTiles - 1 && threadIdx.x == 255) {
+        int total = exA + ta;
+        newStart[nCells] = total;
+        st->nNew = total;
+        if (total > capacity) st->overflow = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// counting-sort scatter of the survivors + creation of the newborns
+// (performMoves core/SPopulation.cpp:1058-1092; makeOffspring / createAgentAtIndex :823-847,880-918;
+//  makePopSpecificOffspring populations/tut_EnvironAltPop.cpp:141-149)
+__global__ void __launch_bounds__(256)
+k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const int *__restrict__ cellStart,
+          const int *__restrict__ dest, const int *__restrict__ rank, const uint8_t *__restrict__ oflags,
+          const int *__restrict__ newStart, const int *__restrict__ newCount, const int *__restrict__ birthBase,
+          float t, int storeAge, RngKey key) {
+    if (st->overflow) return;
+    const int n = st->nAgents;
+    const unsigned step = st->step;
+    const long long nextID = st->nextID;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int d = dest[i];
+        const uint8_t f = oflags[i];
+        int64_t id = 0;
+        if (d >= 0 || (f & F_BORN)) id = a.id[i];
+        if (d >= 0) {
+            int pos = newStart[d] + rank[i];
+            o.id[pos] = id;
+            o.birth[pos] = a.birth[i];
+            o.lastBirth[pos] = a.lastBirth[i];
+            o.cell[pos] = d;
+            o.flags[pos] = (uint8_t)(f & (F_MALE | F_FERTILE));
+            if (storeAge) o.age[pos] = a.age[i];
+        }
+        if (f & F_BORN) {
+            // newborn id = nextID + rank of (cell, mother id) among this step's births
+            const int c = a.cell[i];
+            const int s = cellStart[c], e = cellStart[c + 1];
+            int r = 0;
+            for (int j = s; j < e; j++) {
+                if ((oflags[j] & F_BORN) && a.id[j] < id) r++;
+            }
+            const int64_t cid = nextID + birthBase[c] + r;
+            const uint32_t g = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
+            const int pos = newStart[c] + newCount[c] + r;
+            o.id[pos] = cid;
+            o.birth[pos] = t;
+            o.lastBirth[pos] = 0.0f;
+            o.cell[pos] = c;
+            o.flags[pos] = (uint8_t)(g ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
+            if (storeAge) o.age[pos] = 0.0f;
+        }
+    }
+}
+
+__global__ void k_step_end(DevStats *st, int advanceStep) {
+    if (st->overflow) return;
+    st->nAgents = st->nNew;
+    st->nextID += st->nBirths;
+    if (advanceStep) st->step++;
+}
+
+__global__ void k_step_begin(DevStats *st) {
+    st->nBirths = 0;
+    st->nDeaths = 0;
+    st->nMoves = 0;
+    st->nNew = 0;
+}
+
+__global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {
+    const int n = st->nAgents;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) age[i] = __fsub_rn(t, birth[i]);
+}
+
+__global__ void k_atan_prob(int n, const float *__restrict__ age, double *__restrict__ out, double maxAge, double slope, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double x = __dmul_rn(slope, __dadd_rn((double)age[i], -maxAge));
+        out[i] = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(scale, atan_rn(x)), 3.141592653589793));
+    }
+}
+
+__global__ void k_gather_mate_id(const DevStats *__restrict__ st, const int64_t *__restrict__ id, const int *__restrict__ mate,
+                                 int64_t *__restrict__ out) {
+    const int n = st->nAgents;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int m = mate[i];
+        out[i] = (m >= 0) ? id[m] : (int64_t)m;
+    }
+}
+
+}  // namespace qhg

@@ -1,0 +1,908 @@
+// qhg_pop.cu -- host side of the C ABI declared in include/qhg_b200.h.
+//
+// A qhgb_pop owns the device-resident population (structure of arrays, binned by cell, double buffered),
+// the per-cell arrays and one CUDA stream.  The host object mirrors what SPopulation<T> + Prioritizer<T> +
+// the Action<T> objects hold on the host in the reference (core/SPopulation.h:86-344,
+// core/Prioritizer.h:19-78): named actions with priorities and enable flags, named attributes, per-step
+// totals.  No CPU fallback exists: every entry point that computes launches kernels from qhg_kernels.cuh.
+#include "../../include/qhg_b200.h"
+#include "qhg_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace qhg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST };
+
+struct HostAction {
+    std::string name;
+    ActKind kind;
+    int prio = -1;  // no <prio> entry: the action exists but is never run (core/Prioritizer.cpp:19-30)
+    bool enabled = true;
+};
+
+struct KernelTime {
+    std::string name;
+    double ms = 0;
+    int64_t calls = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct qhgb_pop {
+    std::string popClass;
+    int device = 0;
+    int nCells = 0, maxNeigh = 6;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+
+    std::vector<HostAction> actions;
+    std::map<std::string, double> attr;
+    std::map<std::string, std::string> attrStr;
+    PolyLineDev poly{};
+    bool havePoly = false;
+    uint32_t state16[16] = {0};
+    RngKey key{0, 0};
+
+    // grid / env
+    DevBuf<int> nbr, gid, count, cellStart[2], newCount, birthCount, birthBase, nFert;
+    DevBuf<uint8_t> nNbr, ice;
+    DevBuf<double> alt, W, B, D;
+    DevBuf<int2> tileSums;
+    std::map<std::string, DevBuf<double>> envExtra;
+    bool haveCells = false, haveAlt = false, haveIce = false;
+    std::vector<int32_t> hGid;
+
+    // agents
+    int64_t capacity = 0;
+    DevBuf<int64_t> id[2];
+    DevBuf<float> birth[2], lastBirth[2], age[2];
+    DevBuf<int> cell[2], mate, prank, ranked, dest, rank;
+    DevBuf<uint8_t> flags[2], oflags;
+    DevBuf<uint32_t> pkey;
+    int cur = 0;
+    DevBuf<DevStats> dstats;
+    DevStats *hstats = nullptr;  // pinned
+    // m_fAge: either the device array holds it (ageValid) or, when the action set refreshes the age from the birth
+    // time before anything reads it, it is implied: age = lastAgeTime - birth (see programNeedsStoredAge)
+    bool ageValid = true;
+    float lastAgeTime = 0;
+
+    // step state
+    bool preLooped = false, inStep = false, pairingValid = false;
+    bool evalFirst = true, evalNeedUpdate = false;
+    float curTime = -1;
+    std::vector<unsigned> levels;
+    int64_t nAgents = 0, maxID = 0, stepsDone = 0;
+    int64_t lastBirths = 0, lastDeaths = 0, lastMoves = 0, nextID = 0;
+    int64_t launches = 0;
+
+    bool timing = false;
+    cudaEvent_t userEv[8] = {nullptr};
+    std::vector<KernelTime> ktimes;
+
+    AgentArrays arrays(int b) { return AgentArrays{id[b].p, birth[b].p, lastBirth[b].p, cell[b].p, flags[b].p, age[b].p}; }
+    HostAction *find(const std::string &n) {
+        for (auto &a : actions) if (a.name == n) return &a;
+        return nullptr;
+    }
+    double A(const char *n, double def = 0) const {
+        auto it = attr.find(n);
+        return it == attr.end() ? def : it->second;
+    }
+    int gridFor(int64_t n, int block = 256, int perSM = 8) const {
+        int64_t need = (n + block - 1) / block;
+        int64_t cap = (int64_t)numSMs * perSM;
+        return (int)std::max<int64_t>(1, std::min(need, cap));
+    }
+    KernelTime &kt(const char *name) {
+        for (auto &k : ktimes) if (k.name == name) return k;
+        ktimes.push_back(KernelTime{name});
+        return ktimes.back();
+    }
+};
+
+#define LAUNCH(p, name, kern, grid, block, ...)                                \
+    do {                                                                       \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                              \
+        if ((p)->timing) {                                                     \
+            cudaEventCreate(&e0_);                                             \
+            cudaEventCreate(&e1_);                                             \
+            cudaEventRecord(e0_, (p)->stream);                                 \
+        }                                                                      \
+        kern<<<(grid), (block), 0, (p)->stream>>>(__VA_ARGS__);                \
+        (p)->launches++;                                                       \
+        if ((p)->timing) {                                                     \
+            cudaEventRecord(e1_, (p)->stream);                                 \
+            (p)->kt(name).pending.push_back({e0_, e1_});                       \
+        }                                                                      \
+    } while (0)
+
+namespace {
+
+int allocAgents(qhgb_pop *p, int64_t cap) {
+    // grow (or create) the agent buffers, keeping the live prefix of the current buffer
+    if (cap > (int64_t)2000000000) return fail("capacity %lld exceeds 32-bit agent indices", (long long)cap);
+    qhgb_pop &q = *p;
+    for (int b = 0; b < 2; b++) {
+        int64_t keep = (b == q.cur) ? q.nAgents : 0;
+        auto regrow = [&](auto &buf) -> cudaError_t {
+            using T = std::remove_pointer_t<decltype(buf.p)>;
+            T *np = nullptr;
+            cudaError_t e = cudaMalloc(&np, cap * sizeof(T));
+            if (e != cudaSuccess) return e;
+            if (keep > 0 && buf.p) e = cudaMemcpyAsync(np, buf.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, q.stream);
+            cudaStreamSynchronize(q.stream);
+            if (buf.p) cudaFree(buf.p);
+            buf.p = np;
+            buf.n = cap;
+            return e;
+        };
+        CK(regrow(q.id[b]));
+        CK(regrow(q.birth[b]));
+        CK(regrow(q.lastBirth[b]));
+        CK(regrow(q.age[b]));
+        CK(regrow(q.cell[b]));
+        CK(regrow(q.flags[b]));
+    }
+    CK(q.mate.alloc(cap));
+    CK(q.prank.alloc(cap));
+    CK(q.ranked.alloc(cap));
+    CK(q.dest.alloc(cap));
+    CK(q.rank.alloc(cap));
+    CK(q.oflags.alloc(cap));
+    CK(q.pkey.alloc(cap));
+    q.capacity = cap;
+    q.pairingValid = false;
+    return 0;
+}
+
+int ensureCapacity(qhgb_pop *p, int64_t need) {
+    if (need <= p->capacity) return 0;
+    int64_t cap = std::max<int64_t>(need + need / 4, 1024);
+    return allocAgents(p, cap);
+}
+
+int pushStats(qhgb_pop *p) {
+    DevStats s{};
+    s.nAgents = (int)p->nAgents;
+    s.nextID = p->nextID;
+    s.step = (unsigned)p->stepsDone;
+    CK(cudaMemcpyAsync(p->dstats.p, &s, sizeof(s), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int pullStats(qhgb_pop *p) {
+    CK(cudaMemcpyAsync(p->hstats, p->dstats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// derive the fused action program from the host-side action table: priority ascending, same priority in
+// name order (core/SPopulation.cpp:249-257 iterates a std::map<string,int>), only the requested levels
+ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t) {
+    ActParams P{};
+    std::vector<const HostAction *> v;
+    for (auto &a : p->actions) {
+        if (a.prio < 0 || !a.enabled) continue;
+        if (levels && std::find(levels->begin(), levels->end(), (unsigned)a.prio) == levels->end()) continue;
+        v.push_back(&a);
+    }
+    std::stable_sort(v.begin(), v.end(), [](const HostAction *x, const HostAction *y) {
+        if (x->prio != y->prio) return x->prio < y->prio;
+        return x->name < y->name;
+    });
+    for (const HostAction *a : v) {
+        uint8_t op = 0;
+        switch (a->kind) {
+        case A_GETOLD: op = OP_GETOLD; break;
+        case A_ATANDEATH: op = OP_ATANDEATH; break;
+        case A_OLDAGEDEATH: op = OP_OLDAGEDEATH; break;
+        case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
+        case A_FERTILITY: op = OP_FERTILITY; break;
+        case A_VERHULST: op = OP_VERHULST; break;
+        default: break;  // evaluators and pairing have no per-agent execute()
+        }
+        if (op && P.nOps < MAX_OPS) P.ops[P.nOps++] = op;
+    }
+    P.t = t;
+    P.storeAge = 1;
+    P.key = p->key;
+    // ATanDeath::preLoop, actions/ATanDeath.cpp:49-59 (EPS = 0.001, actions/ATanDeath.h:14)
+    P.atanMaxAge = p->A("ATanDeath_max_age");
+    P.atanSlope = p->A("ATanDeath_slope");
+    double range = p->A("ATanDeath_range");
+    P.atanScale = (M_PI / 2 - 0.001) / atan(P.atanSlope * range);
+    // outside [Xlo, Xhi] the probability is < 0 resp. > 1 whatever the draw: skip the atan there
+    P.atanXlo = -INFINITY;
+    P.atanXhi = INFINITY;
+    if (P.atanScale > 1.0 + 1e-9 && std::isfinite(P.atanScale)) {
+        double th = tan(M_PI / (2 * P.atanScale));
+        P.atanXhi = th * (1 + 1e-6) + 1e-9;
+        P.atanXlo = -P.atanXhi;
+    }
+    P.oadMaxAge = p->A("OAD_max_age");
+    double unc = p->A("OAD_uncertainty");
+    P.oadLo = 1 - unc * P.oadMaxAge;
+    P.oadHi = 1 + unc * P.oadMaxAge;
+    P.moveProb = p->A("WeightedMove_prob");
+    P.fertMinAge = (float)p->A("Fertility_min_age");
+    P.fertMaxAge = (float)p->A("Fertility_max_age");
+    P.fertInterbirth = (float)p->A("Fertility_interbirth");
+    return P;
+}
+
+// does the program refresh m_fAge from the birth time before anything reads it?  Then the age never has to be
+// stored or moved: it is (time of the last refresh - birth time), also for the records handed back to the host.
+bool programNeedsStoredAge(const ActParams &P) {
+    for (int k = 0; k < P.nOps; k++) {
+        switch (P.ops[k]) {
+        case OP_GETOLD: case OP_ATANDEATH: case OP_OLDAGEDEATH: return false;
+        case OP_FERTILITY: return true;
+        default: break;
+        }
+    }
+    return true;  // nothing touches the age: keep what is stored
+}
+
+int materializeAges(qhgb_pop *p) {
+    if (p->ageValid) return 0;
+    if (p->nAgents > 0) {
+        LAUNCH(p, "k_fill_age", k_fill_age, p->gridFor(p->nAgents), 256, p->dstats.p, p->birth[p->cur].p, p->age[p->cur].p, p->lastAgeTime);
+        CK(cudaGetLastError());
+    }
+    p->ageValid = true;
+    return 0;
+}
+
+int computeWeights(qhgb_pop *p) {
+    if (!p->haveAlt) return fail("SingleEvaluator[Alt]: no array with name [Altitude]");
+    int g = p->gridFor(p->nCells);
+    LAUNCH(p, "k_weights_own", k_weights_own, g, 256, p->nCells, p->alt.p, p->haveIce ? p->ice.p : nullptr, p->poly,
+           p->havePoly ? 1 : 0, p->W.p);
+    LAUNCH(p, "k_weights_cumulate", k_weights_cumulate, g, 256, p->nCells, p->nbr.p, p->W.p, 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// decide -> scan -> scatter with the given program; used by finalizeStep, by the GEO event and (with an empty
+// program) to bin freshly uploaded agents by cell
+int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool isBirthStep) {
+    qhgb_pop &q = *p;
+    const int n = (int)q.nAgents;
+    const int ga = q.gridFor(n), gc = q.gridFor(q.nCells);
+    const int nTiles = (q.nCells + SCAN_TILE - 1) / SCAN_TILE;
+    AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
+    LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, q.nbr.p, q.nNbr.p,
+           q.haveIce ? q.ice.p : nullptr, q.alt.p, q.W.p, q.B.p, q.D.p, q.newCount.p, q.birthCount.p, q.dest.p,
+           q.rank.p, q.oflags.p);
+    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, q.nCells, q.newCount.p, q.birthCount.p, q.tileSums.p);
+    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, q.nCells, nTiles, q.newCount.p, q.birthCount.p, q.tileSums.p,
+           q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count.p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
+    LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
+           q.cellStart[q.cur ^ 1].p, q.newCount.p, q.birthBase.p, P.t, P.storeAge, q.key);
+    LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0);
+    (void)gc; (void)isBirthStep;
+    CK(cudaGetLastError());
+    if (pullStats(p) != 0) return -1;
+    if (q.hstats->overflow) return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
+    q.cur ^= 1;
+    q.nAgents = q.hstats->nAgents;
+    q.nextID = q.hstats->nextID;
+    q.lastBirths = q.hstats->nBirths;
+    q.lastDeaths = q.hstats->nDeaths;
+    q.lastMoves = q.hstats->nMoves;
+    q.pairingValid = false;
+    return 0;
+}
+
+int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
+    qhgb_pop &q = *p;
+    LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
+    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.nCells), 256, q.nCells, q.count.p, q.B.p, q.D.p, q.A("Verhulst_b0"),
+           q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), doVerhulst ? 1 : 0, q.newCount.p, q.birthCount.p,
+           q.nFert.p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *qhgb_last_error(void) { return g_err.c_str(); }
+const char *qhgb_version(void) { return "qhg4_b200 0.1 (sm_100a)"; }
+
+int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, int64_t capacity_hint, qhgb_pop **out) {
+    if (!out) return fail("qhgb_create: out is NULL");
+    *out = nullptr;
+    if (max_neigh != MAXN) return fail("qhgb_create: connectivity %d not supported (the cell struct holds %d neighbours)", max_neigh, MAXN);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("qhgb_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("qhgb_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    qhgb_pop *p = new qhgb_pop;
+    p->popClass = pop_class;
+    p->device = device;
+    p->nCells = n_cells;
+    p->maxNeigh = max_neigh;
+    if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else {
+        delete p;
+        return fail("qhgb_create: unknown population class [%s]", pop_class);
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    p->numSMs = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    size_t nc = (size_t)n_cells;
+    CK(p->nbr.alloc(nc * MAXN));
+    CK(p->gid.alloc(nc));
+    CK(p->nNbr.alloc(nc));
+    CK(p->ice.alloc(nc));
+    CK(p->alt.alloc(nc));
+    CK(p->count.alloc(nc));
+    CK(p->cellStart[0].alloc(nc + 1));
+    CK(p->cellStart[1].alloc(nc + 1));
+    CK(p->newCount.alloc(nc));
+    CK(p->birthCount.alloc(nc));
+    CK(p->birthBase.alloc(nc));
+    CK(p->nFert.alloc(2 * nc));
+    CK(p->W.alloc(nc * WSTRIDE));
+    CK(p->B.alloc(nc));
+    CK(p->D.alloc(nc));
+    CK(p->tileSums.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
+    CK(p->dstats.alloc(1));
+    CK(cudaMemsetAsync(p->count.p, 0, nc * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->cellStart[0].p, 0, (nc + 1) * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->cellStart[1].p, 0, (nc + 1) * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->W.p, 0, nc * WSTRIDE * sizeof(double), p->stream));
+    CK(cudaMemsetAsync(p->B.p, 0, nc * sizeof(double), p->stream));
+    CK(cudaMemsetAsync(p->D.p, 0, nc * sizeof(double), p->stream));
+    CK(cudaMemsetAsync(p->alt.p, 0, nc * sizeof(double), p->stream));
+    CK(cudaMemsetAsync(p->ice.p, 0, nc, p->stream));
+    CK(cudaMemsetAsync(p->dstats.p, 0, sizeof(DevStats), p->stream));
+    CK(cudaMallocHost(&p->hstats, sizeof(DevStats)));
+    memset(p->hstats, 0, sizeof(DevStats));
+    if (capacity_hint > 0 && allocAgents(p, capacity_hint) != 0) { qhgb_destroy(p); return -1; }
+    CK(cudaStreamSynchronize(p->stream));
+    *out = p;
+    return 0;
+}
+
+int qhgb_destroy(qhgb_pop *p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (auto &k : p->ktimes) for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    p->nbr.release(); p->gid.release(); p->count.release(); p->cellStart[0].release(); p->cellStart[1].release();
+    p->newCount.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
+    p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
+    for (auto &kv : p->envExtra) kv.second.release();
+    for (int b = 0; b < 2; b++) {
+        p->id[b].release(); p->birth[b].release(); p->lastBirth[b].release(); p->age[b].release();
+        p->cell[b].release(); p->flags[b].release();
+    }
+    p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
+    p->oflags.release(); p->pkey.release(); p->dstats.release();
+    for (auto &e : p->userEv) if (e) cudaEventDestroy(e);
+    if (p->hstats) cudaFreeHost(p->hstats);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
+    if (!p || !nbr) return fail("qhgb_set_cells: NULL argument");
+    CK(cudaSetDevice(p->device));
+    size_t nc = (size_t)p->nCells;
+    std::vector<uint8_t> nn(nc);
+    p->hGid.resize(nc);
+    for (size_t c = 0; c < nc; c++) {
+        int k = 0;
+        for (int j = 0; j < MAXN; j++) {
+            int v = nbr[c * MAXN + j];
+            if (v >= p->nCells) return fail("qhgb_set_cells: cell %zu has neighbour index %d >= %d", c, v, p->nCells);
+            // real neighbours come first, -1 pads the tail (core/SCellGrid.cpp:58-62); m_iNumNeighbors = their number
+            if (v >= 0) { if (k != j) return fail("qhgb_set_cells: cell %zu has a -1 before a neighbour", c); k++; }
+        }
+        nn[c] = (uint8_t)k;
+        p->hGid[c] = global_id ? global_id[c] : (int32_t)c;
+    }
+    CK(cudaMemcpyAsync(p->nbr.p, nbr, nc * MAXN * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->nNbr.p, nn.data(), nc, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->gid.p, p->hGid.data(), nc * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->haveCells = true;
+    return 0;
+}
+
+int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n) {
+    if (!p || !name || !values) return fail("qhgb_set_env_array: NULL argument");
+    if (n != p->nCells) return fail("qhgb_set_env_array: [%s] has %lld values, grid has %d cells", name, (long long)n, p->nCells);
+    CK(cudaSetDevice(p->device));
+    std::string s(name);
+    if (s == "Altitude") {
+        CK(cudaMemcpyAsync(p->alt.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        p->haveAlt = true;
+    } else if (s == "Ice") {
+        std::vector<uint8_t> b(n);
+        bool any = false;
+        for (int64_t i = 0; i < n; i++) { b[i] = values[i] != 0; any |= b[i] != 0; }
+        CK(cudaMemcpyAsync(p->ice.p, b.data(), n, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        p->haveIce = true;
+        (void)any;
+    } else {
+        DevBuf<double> &d = p->envExtra[s];
+        if (d.n != (size_t)n) CK(d.alloc(n));
+        CK(cudaMemcpyAsync(d.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+static const char *const kNumericAttrs[] = {
+    "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob",
+    "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
+    "Verhulst_K"};
+
+int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
+    if (!p || !name) return fail("qhgb_set_attribute: NULL argument");
+    for (const char *k : kNumericAttrs) {
+        if (strcmp(k, name) == 0) { p->attr[name] = value; return 0; }
+    }
+    return fail("qhgb_set_attribute: no action of [%s] has an attribute [%s]", p->popClass.c_str(), name);
+}
+
+int qhgb_set_attribute_str(qhgb_pop *p, const char *name, const char *value) {
+    if (!p || !name || !value) return fail("qhgb_set_attribute_str: NULL argument");
+    if (strcmp(name, "AltCapPref") == 0) {  // PolyLine::readFromString, utils/PolyLine.cpp:92-127
+        std::vector<double> d;
+        const char *s = value;
+        char *e;
+        while (true) {
+            while (*s == ' ' || *s == '\t') s++;
+            if (!*s) break;
+            double v = strtod(s, &e);
+            if (e == s) return fail("Bad Function def (number format) : [%s]", value);
+            d.push_back(v);
+            s = e;
+        }
+        if (d.size() < 4 || d.size() % 2) return fail("[PolyLine::readFromString] Expected non-zero even number of arguments : [%s]", value);
+        size_t np = d.size() / 2;
+        if (np > (size_t)MAX_POLY) return fail("poly-line [%s] has more than %d points", name, MAX_POLY);
+        PolyLineDev pl{};
+        pl.nseg = (int)np - 1;
+        for (size_t i = 0; i < np; i++) {
+            pl.x[i] = d[2 * i];
+            pl.v[i] = d[2 * i + 1];
+            if (i > 0) pl.a[i - 1] = (pl.v[i] - pl.v[i - 1]) / (pl.x[i] - pl.x[i - 1]);  // utils/PolyLine.h:24-30
+        }
+        p->poly = pl;
+        p->havePoly = true;
+        p->attrStr[name] = value;
+        p->evalNeedUpdate = true;
+        return 0;
+    }
+    char *e;
+    double v = strtod(value, &e);
+    if (e == value) return fail("qhgb_set_attribute_str: [%s] = [%s] is not a number", name, value);
+    return qhgb_set_attribute(p, name, v);
+}
+
+int qhgb_set_prio(qhgb_pop *p, const char *action_name, int prio) {
+    if (!p || !action_name) return fail("qhgb_set_prio: NULL argument");
+    HostAction *a = p->find(action_name);
+    if (!a) return fail("[Prioritizer::setPrio] tried to add non-existing action '%s'", action_name);
+    if (prio < 0) return fail("qhgb_set_prio: negative priority for '%s'", action_name);
+    a->prio = prio;
+    return 0;
+}
+
+int qhgb_enable_action(qhgb_pop *p, const char *action_name, int enabled) {
+    if (!p || !action_name) return fail("qhgb_enable_action: NULL argument");
+    HostAction *a = p->find(action_name);
+    if (!a) return fail("qhgb_enable_action: no action '%s'", action_name);
+    a->enabled = enabled != 0;
+    return 0;
+}
+
+int qhgb_set_seed(qhgb_pop *p, const uint32_t *st) {
+    if (!p || !st) return fail("qhgb_set_seed: NULL argument");
+    memcpy(p->state16, st, sizeof(p->state16));
+    p->key.k0 = p->key.k1 = 0;
+    for (int j = 0; j < 16; j += 2) { p->key.k0 ^= st[j]; p->key.k1 ^= st[j + 1]; }
+    return 0;
+}
+
+int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
+                    const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life_state) {
+    if (!p || !cell || !id || !birth_time || !gender) return fail("qhgb_add_agents: NULL argument");
+    if (p->inStep) return fail("qhgb_add_agents: called inside a step");
+    CK(cudaSetDevice(p->device));
+    // pack the live ones (readAgentDataQDF drops nothing, but dead records carry no agent: core/SPopulation.cpp:1689-1741)
+    std::vector<int32_t> hc; std::vector<int64_t> hi; std::vector<float> hb, hl, ha; std::vector<uint8_t> hf;
+    hc.reserve(n); hi.reserve(n); hb.reserve(n); hl.reserve(n); ha.reserve(n); hf.reserve(n);
+    for (int64_t j = 0; j < n; j++) {
+        uint32_t life = life_state ? life_state[j] : QHGB_LIFE_STATE_ALIVE;
+        if (life == QHGB_LIFE_STATE_DEAD) continue;
+        if (cell[j] < 0 || cell[j] >= p->nCells) return fail("[addAgent] agent %lld has cellindex %d", (long long)id[j], cell[j]);
+        if (gender[j] > 1) return fail("[addAgent] agent %lld has gender %d", (long long)id[j], (int)gender[j]);
+        hc.push_back(cell[j]);
+        hi.push_back(id[j]);
+        hb.push_back(birth_time[j]);
+        hl.push_back(last_birth ? last_birth[j] : 0.0f);
+        ha.push_back(age ? age[j] : 0.0f);
+        hf.push_back((uint8_t)((gender[j] ? F_MALE : 0) | (((life & ~8u) == QHGB_LIFE_STATE_FERTILE) ? F_FERTILE : 0)));
+        if (id[j] > p->maxID) p->maxID = id[j];
+    }
+    int64_t m = (int64_t)hc.size();
+    if (m == 0) return 0;
+    if (materializeAges(p) != 0) return -1;
+    int64_t total = p->nAgents + m;
+    if (ensureCapacity(p, total + total / 2 + 1024) != 0) return -1;
+    int b = p->cur;
+    int64_t off = p->nAgents;
+    CK(cudaMemcpyAsync(p->cell[b].p + off, hc.data(), m * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->id[b].p + off, hi.data(), m * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->birth[b].p + off, hb.data(), m * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->lastBirth[b].p + off, hl.data(), m * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->age[b].p + off, ha.data(), m * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->flags[b].p + off, hf.data(), m, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->nAgents = total;
+    if (p->preLooped) {  // late additions are binned at once
+        p->nextID = std::max(p->nextID, p->maxID + 1);
+        ActParams P = buildProgram(p, nullptr, p->curTime);
+        P.nOps = 0;
+        int rc = pushStats(p);
+        if (rc == 0) rc = resetCellCounters(p, false);
+        if (rc == 0) rc = runPipeline(p, P, false, false);
+        return rc;
+    }
+    return 0;
+}
+
+int qhgb_pre_loop(qhgb_pop *p) {
+    if (!p) return fail("qhgb_pre_loop: NULL population");
+    if (!p->haveCells) return fail("qhgb_pre_loop: no cells (qhgb_set_cells)");
+    CK(cudaSetDevice(p->device));
+    if (p->capacity == 0 && ensureCapacity(p, 1024) != 0) return -1;
+    p->nextID = p->maxID + 1;  // IDGen base, app/Simulator.cpp:94-111
+    p->stepsDone = 0;
+    if (pushStats(p) != 0) return -1;
+    // bin the uploaded agents by cell and count them (updateTotal + updateNumAgentsPerCell, core/SPopulation.cpp:287-288):
+    // the step pipeline with an empty action list; ages are carried along
+    ActParams P = buildProgram(p, nullptr, 0);
+    P.nOps = 0;
+    if (resetCellCounters(p, false) != 0) return -1;
+    if (runPipeline(p, P, false, false) != 0) return -1;
+    p->preLooped = true;
+    p->evalFirst = true;
+    return 0;
+}
+
+int qhgb_initialize_step(qhgb_pop *p, float t) {
+    if (!p) return fail("qhgb_initialize_step: NULL population");
+    if (!p->preLooped) return fail("qhgb_initialize_step: preLoop has not run");
+    CK(cudaSetDevice(p->device));
+    qhgb_pop &q = *p;
+    q.curTime = t;
+    q.levels.clear();
+    q.inStep = true;
+    // births need room: at most one baby per paired female (grown here, before the pairing scratch is filled)
+    if (ensureCapacity(p, q.nAgents + q.nAgents / 2 + 1024) != 0) return -1;
+    // initialize() of every action that has a priority, in order (core/SPopulation.cpp:394-417)
+    HostAction *ver = q.find("Verhulst"), *pair = q.find("RandomPair"), *ev = q.find("SingleEvaluator[Alt]");
+    bool doVer = ver && ver->prio >= 0 && ver->enabled;
+    if (doVer && !(q.A("Verhulst_K", 0) != 0)) return fail("Verhulst: Verhulst_K is not set");
+    if (resetCellCounters(p, doVer) != 0) return -1;
+    const int ga = q.gridFor(q.nAgents);
+    AgentArrays a = q.arrays(q.cur);
+    if (pair && pair->prio >= 0 && pair->enabled) {
+        LAUNCH(p, "k_pair_keys", k_pair_keys, ga, 256, q.dstats.p, a, q.key, q.pkey.p, q.mate.p, q.nFert.p);
+        LAUNCH(p, "k_pair_rank", k_pair_rank, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.pkey.p, q.prank.p, q.ranked.p);
+        LAUNCH(p, "k_pair_match", k_pair_match, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.nFert.p, q.prank.p, q.ranked.p, q.mate.p);
+        q.pairingValid = true;
+    } else if (!q.pairingValid) {
+        CK(cudaMemsetAsync(q.mate.p, 0xFF, (size_t)q.nAgents * sizeof(int), q.stream));  // -1: nobody is paired
+    }
+    if (ev && ev->prio >= 0 && ev->enabled && (q.evalNeedUpdate || q.evalFirst)) {
+        q.evalFirst = false;
+        if (computeWeights(p) != 0) return -1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int qhgb_do_actions(qhgb_pop *p, unsigned prio, float t) {
+    if (!p) return fail("qhgb_do_actions: NULL population");
+    if (!p->inStep) return fail("qhgb_do_actions: initializeStep has not run");
+    (void)t;
+    p->levels.push_back(prio);
+    return 0;
+}
+
+int qhgb_finalize_step(qhgb_pop *p) {
+    if (!p) return fail("qhgb_finalize_step: NULL population");
+    if (!p->inStep) return fail("qhgb_finalize_step: initializeStep has not run");
+    CK(cudaSetDevice(p->device));
+    qhgb_pop &q = *p;
+    ActParams P = buildProgram(p, &q.levels, q.curTime);
+    const bool needAge = programNeedsStoredAge(P);
+    if (needAge && materializeAges(p) != 0) return -1;
+    P.storeAge = needAge ? 1 : 0;
+    if (q.nAgents + q.nAgents / 2 + 1024 > q.capacity) return fail("qhgb_finalize_step: agent buffers too small");
+    HostAction *ev = q.find("SingleEvaluator[Alt]");
+    if (ev && ev->prio >= 0 && ev->enabled) q.evalNeedUpdate = false;  // SingleEvaluator::finalize, :125-130
+    int rc = runPipeline(p, P, true, true);
+    q.inStep = false;
+    if (rc != 0) return rc;
+    q.stepsDone++;
+    if (!needAge) { q.ageValid = false; q.lastAgeTime = q.curTime; }
+    return 0;
+}
+
+int qhgb_step(qhgb_pop *p, float t) {
+    if (!p) return fail("qhgb_step: NULL population");
+    int rc = qhgb_initialize_step(p, t);
+    if (rc != 0) return rc;
+    std::vector<unsigned> lv;
+    for (auto &a : p->actions) if (a.prio >= 0) lv.push_back((unsigned)a.prio);
+    std::sort(lv.begin(), lv.end());
+    lv.erase(std::unique(lv.begin(), lv.end()), lv.end());
+    for (unsigned l : lv) rc += qhgb_do_actions(p, l, t);
+    rc += qhgb_finalize_step(p);
+    return rc;
+}
+
+int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
+    int rc = 0;
+    for (int k = 0; k < n_steps && rc == 0; k++) rc = qhgb_step(p, t0 + k);
+    return rc;
+}
+
+int qhgb_synchronize(qhgb_pop *p) {
+    if (!p) return fail("qhgb_synchronize: NULL population");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
+    if (!p) return fail("qhgb_update_event: NULL population");
+    if (!p->preLooped) return fail("qhgb_update_event: preLoop has not run");
+    CK(cudaSetDevice(p->device));
+    if (event_id == QHGB_EVENT_ID_GEO) {  // populations/tut_EnvironAltPop.cpp:100-127
+        ActParams P = buildProgram(p, nullptr, t);
+        P.nOps = 1;
+        P.ops[0] = OP_DROWN;
+        P.storeAge = p->ageValid ? 1 : 0;
+        if (resetCellCounters(p, false) != 0) return -1;
+        int rc = runPipeline(p, P, false, false);
+        if (rc != 0) return rc;
+        p->evalNeedUpdate = true;  // SingleEvaluator::notify, actions/SingleEvaluator.cpp:332-346
+    }
+    return 0;
+}
+
+int qhgb_flush_events(qhgb_pop *p, float t) {
+    (void)t;
+    if (!p) return fail("qhgb_flush_events: NULL population");
+    return 0;  // EVENT_ID_FLUSH: the evaluator recomputes at the next initialize (actions/SingleEvaluator.cpp:335-337)
+}
+
+int64_t qhgb_get_num_agents_effective(qhgb_pop *p) { return p ? p->nAgents : -1; }
+
+int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
+    if (!p || !out) return fail("qhgb_get_num_agents_array: NULL argument");
+    CK(cudaSetDevice(p->device));
+    std::vector<int> h(p->nCells);
+    CK(cudaMemcpyAsync(h.data(), p->count.p, (size_t)p->nCells * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int c = 0; c < p->nCells; c++) out[c] = (uint64_t)h[c];
+    return 0;
+}
+
+int qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out) {
+    if (!p || !out) return fail("qhgb_get_step_stats: NULL argument");
+    out->num_agents = p->nAgents;
+    out->births = p->lastBirths;
+    out->deaths = p->lastDeaths;
+    out->moves = p->lastMoves;
+    out->next_id = p->nextID;
+    out->steps_done = p->stepsDone;
+    return 0;
+}
+
+int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
+                        uint8_t *gender, float *age, float *last_birth, uint32_t *life_state, int64_t *mate_id) {
+    if (!p) { fail("qhgb_get_agents: NULL population"); return -1; }
+    if (cudaSetDevice(p->device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1; }
+    int64_t n = p->nAgents, m = std::min(n, cap);
+    if (m <= 0) return n;
+    int b = p->cur;
+    cudaStream_t s = p->stream;
+    std::vector<int32_t> hc;
+    std::vector<float> hb;
+    std::vector<uint8_t> hf;
+    bool err = false;
+    auto D2H = [&](void *dst, const void *src, size_t bytes) { err |= cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess; };
+    if (cell || cell_id) { hc.resize(m); D2H(hc.data(), p->cell[b].p, m * sizeof(int)); }
+    if (id) D2H(id, p->id[b].p, m * sizeof(int64_t));
+    if (birth_time || (age && (!p->ageValid))) { hb.resize(m); D2H(hb.data(), p->birth[b].p, m * sizeof(float)); }
+    if (gender || life_state) { hf.resize(m); D2H(hf.data(), p->flags[b].p, m); }
+    if (age && !(!p->ageValid)) D2H(age, p->age[b].p, m * sizeof(float));
+    if (last_birth) D2H(last_birth, p->lastBirth[b].p, m * sizeof(float));
+    if (mate_id) {
+        if (p->pairingValid) {
+            int64_t *tmp = nullptr;
+            err |= cudaMalloc(&tmp, m * sizeof(int64_t)) != cudaSuccess;
+            if (!err) {
+                LAUNCH(p, "k_gather_mate_id", k_gather_mate_id, p->gridFor(m), 256, p->dstats.p, p->id[b].p, p->mate.p, tmp);
+                D2H(mate_id, tmp, m * sizeof(int64_t));
+                cudaStreamSynchronize(s);
+                cudaFree(tmp);
+            }
+        } else {
+            for (int64_t i = 0; i < m; i++) mate_id[i] = -3;
+        }
+    }
+    err |= cudaStreamSynchronize(s) != cudaSuccess;
+    if (err) { fail("qhgb_get_agents: device to host copy failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    for (int64_t i = 0; i < m; i++) {
+        if (cell) cell[i] = hc[i];
+        if (cell_id) cell_id[i] = p->hGid.empty() ? hc[i] : p->hGid[hc[i]];
+        if (birth_time) birth_time[i] = hb[i];
+        if (gender) gender[i] = hf[i] & F_MALE;
+        if (life_state) life_state[i] = (hf[i] & F_FERTILE) ? QHGB_LIFE_STATE_FERTILE : QHGB_LIFE_STATE_ALIVE;
+        if (age && (!p->ageValid)) age[i] = p->lastAgeTime - hb[i];
+    }
+    return n;
+}
+
+int qhgb_get_env_weights(qhgb_pop *p, double *out) {
+    if (!p || !out) return fail("qhgb_get_env_weights: NULL argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(out, p->W.p, (size_t)p->nCells * WSTRIDE * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d) {
+    if (!p || !b || !d) return fail("qhgb_get_birth_death_probs: NULL argument");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(b, p->B.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(d, p->D.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_atan_death_prob(qhgb_pop *p, int n, const float *age, double *out) {
+    if (!p || !age || !out) return fail("qhgb_atan_death_prob: NULL argument");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(p->device));
+    ActParams P = buildProgram(p, nullptr, 0);
+    float *da = nullptr;
+    double *dp = nullptr;
+    CK(cudaMalloc(&da, n * sizeof(float)));
+    CK(cudaMalloc(&dp, n * sizeof(double)));
+    CK(cudaMemcpyAsync(da, age, n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    LAUNCH(p, "k_atan_prob", k_atan_prob, (n + 255) / 256, 256, n, da, dp, P.atanMaxAge, P.atanSlope, P.atanScale);
+    CK(cudaMemcpyAsync(out, dp, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(da);
+    cudaFree(dp);
+    return 0;
+}
+
+int qhgb_event_record(qhgb_pop *p, int slot) {
+    if (!p || slot < 0 || slot >= 8) return fail("qhgb_event_record: bad argument");
+    CK(cudaSetDevice(p->device));
+    if (!p->userEv[slot]) CK(cudaEventCreate(&p->userEv[slot]));
+    CK(cudaEventRecord(p->userEv[slot], p->stream));
+    return 0;
+}
+
+double qhgb_event_elapsed_ms(qhgb_pop *p, int a, int b) {
+    if (!p || a < 0 || a >= 8 || b < 0 || b >= 8 || !p->userEv[a] || !p->userEv[b]) { fail("qhgb_event_elapsed_ms: bad argument"); return -1; }
+    cudaSetDevice(p->device);
+    if (cudaEventSynchronize(p->userEv[b]) != cudaSuccess) { fail("cudaEventSynchronize failed"); return -1; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->userEv[a], p->userEv[b]) != cudaSuccess) { fail("cudaEventElapsedTime failed"); return -1; }
+    return ms;
+}
+
+int64_t qhgb_get_launch_count(qhgb_pop *p) { return p ? p->launches : -1; }
+void *qhgb_get_stream(qhgb_pop *p) { return p ? (void *)p->stream : nullptr; }
+
+int qhgb_reset_kernel_times(qhgb_pop *p, int enable) {
+    if (!p) return fail("qhgb_reset_kernel_times: NULL population");
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    for (auto &k : p->ktimes) {
+        for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+        k.pending.clear();
+        k.ms = 0;
+        k.calls = 0;
+    }
+    p->timing = enable != 0;
+    return 0;
+}
+
+int qhgb_get_kernel_times(qhgb_pop *p, int cap, const char **names, double *ms, int64_t *calls) {
+    if (!p) return fail("qhgb_get_kernel_times: NULL population");
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    for (auto &k : p->ktimes) {
+        for (auto &ev : k.pending) {
+            float f = 0;
+            if (cudaEventElapsedTime(&f, ev.first, ev.second) == cudaSuccess) { k.ms += f; k.calls++; }
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        k.pending.clear();
+    }
+    int n = (int)p->ktimes.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (names) names[i] = p->ktimes[i].name.c_str();
+        if (ms) ms[i] = p->ktimes[i].ms;
+        if (calls) calls[i] = p->ktimes[i].calls;
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -130,8 +130,9 @@ def synthetic_population(n_agents: int, altitude: np.ndarray, seed: int = 1, t0:
     """
     rng = np.random.default_rng(seed)
     land = np.flatnonzero(altitude > 0) if cells is None else np.asarray(cells)
-    cell = np.sort(land[rng.integers(0, len(land), size=n_agents)]).astype(np.int32)
-    age = rng.uniform(0, max_age, size=n_agents).astype(np.float32)
+    per_cell = rng.multinomial(n_agents, np.full(len(land), 1.0 / len(land)))  # uniform over the cells, already binned
+    cell = np.repeat(land.astype(np.int32), per_cell)
+    age = (rng.random(n_agents, dtype=np.float32) * np.float32(max_age)).astype(np.float32)
     birth = (np.float32(t0) - age).astype(np.float32)
     return dict(
         cell=cell,

@@ -1,0 +1,196 @@
+"""`GpuPopulation`: the host-side mirror of the reference's population interface over the C ABI.
+
+Method names and call order are the reference's `PopBase` / `PopLooper` ones
+(core/PopBase.h:16-121, core/PopLooper.cpp:166-202): `read_species_data` (XML parameters and
+priorities), `add_agents`, `pre_loop`, then per step `initialize_step(t)`, `do_actions(prio, t)` for
+every priority level, `finalize_step()`; `update_event` / `flush_events` on environment events.
+Every method goes through `include/qhg_b200.h`; errors raise `QhgError` carrying the text of
+`qhgb_last_error()` (the C calls themselves return the reference's 0 / -1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import QhgError, StepStats, check
+from .params import DEFAULT_STATE, PopParams
+
+EVENT_ID_GEO, EVENT_ID_CLIMATE, EVENT_ID_VEG, EVENT_ID_NAV, EVENT_ID_FLUSH = 2, 3, 4, 5, 20
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GpuPopulation:
+    def __init__(self, pop_class: str, nbr, device: int = 0, capacity_hint: int = 0, global_id=None):
+        self.L = capi.load()
+        nbr = np.ascontiguousarray(nbr, np.int32)
+        self.ncells, self.max_neigh = nbr.shape
+        h = C.c_void_p()
+        check(self.L.qhgb_create(pop_class.encode(), device, self.ncells, self.max_neigh, int(capacity_hint), C.byref(h)),
+              "qhgb_create")
+        self.h = h
+        gid = None if global_id is None else np.ascontiguousarray(global_id, np.int32)
+        check(self.L.qhgb_set_cells(self.h, _p(nbr), _p(gid)), "qhgb_set_cells")
+        self.prios = {}
+        self.set_seed(DEFAULT_STATE)
+
+    # ---- construction helpers ---------------------------------------------------------------
+    @classmethod
+    def from_params(cls, params: PopParams, nbr, altitude, ice=None, state16=None, device=0, capacity_hint=0):
+        pop = cls(params.class_name, nbr, device=device, capacity_hint=capacity_hint)
+        pop.set_env("Altitude", altitude)
+        if ice is not None:
+            pop.set_env("Ice", ice)
+        pop.read_species_data(params)
+        if state16 is not None:
+            pop.set_seed(state16)
+        return pop
+
+    def set_env(self, name: str, values):
+        v = np.ascontiguousarray(values, np.float64)
+        check(self.L.qhgb_set_env_array(self.h, name.encode(), _p(v), len(v)), f"qhgb_set_env_array({name})")
+
+    def read_species_data(self, params: PopParams):
+        """SPopulation::readSpeciesData (core/SPopulation.cpp:1108-1142): priorities, then action attributes."""
+        for name, pr in params.prios.items():
+            check(self.L.qhgb_set_prio(self.h, name.encode(), int(pr)), f"qhgb_set_prio({name})")
+            self.prios[name] = int(pr)
+        for mod, pars in params.modules.items():
+            for k, v in pars.items():
+                check(self.L.qhgb_set_attribute_str(self.h, k.encode(), str(v).encode()), f"qhgb_set_attribute_str({k})")
+
+    def modify_attributes(self, name: str, value: float):
+        check(self.L.qhgb_set_attribute(self.h, name.encode(), float(value)), f"qhgb_set_attribute({name})")
+
+    def set_prio(self, action: str, prio: int):
+        check(self.L.qhgb_set_prio(self.h, action.encode(), int(prio)), f"qhgb_set_prio({action})")
+        self.prios[action] = int(prio)
+
+    def enable_action(self, action: str, on: bool = True):
+        check(self.L.qhgb_enable_action(self.h, action.encode(), int(on)), f"qhgb_enable_action({action})")
+
+    def disable_action(self, action: str):
+        self.enable_action(action, False)
+
+    def set_seed(self, state16):
+        st = np.ascontiguousarray(state16, np.uint32)
+        assert st.shape == (16,)
+        check(self.L.qhgb_set_seed(self.h, _p(st)), "qhgb_set_seed")
+
+    def add_agents(self, pop: dict):
+        n = len(pop["cell"])
+        arrs = [np.ascontiguousarray(pop["cell"], np.int32), np.ascontiguousarray(pop["id"], np.int64),
+                np.ascontiguousarray(pop["birth"], np.float32), np.ascontiguousarray(pop["gender"], np.uint8),
+                np.ascontiguousarray(pop["age"], np.float32), np.ascontiguousarray(pop["last_birth"], np.float32),
+                np.ascontiguousarray(pop["life"], np.uint32)]
+        check(self.L.qhgb_add_agents(self.h, n, *[_p(a) for a in arrs]), "qhgb_add_agents")
+
+    # ---- the loop ---------------------------------------------------------------------------
+    def pre_loop(self):
+        check(self.L.qhgb_pre_loop(self.h), "qhgb_pre_loop")
+
+    start = pre_loop
+
+    def initialize_step(self, t: float):
+        check(self.L.qhgb_initialize_step(self.h, float(t)), "qhgb_initialize_step")
+
+    def do_actions(self, prio: int, t: float):
+        check(self.L.qhgb_do_actions(self.h, int(prio), float(t)), "qhgb_do_actions")
+
+    def finalize_step(self):
+        check(self.L.qhgb_finalize_step(self.h), "qhgb_finalize_step")
+
+    def step(self, t: float):
+        check(self.L.qhgb_step(self.h, float(t)), "qhgb_step")
+
+    def run(self, t0: float, nsteps: int):
+        check(self.L.qhgb_run(self.h, float(t0), int(nsteps)), "qhgb_run")
+
+    def synchronize(self):
+        check(self.L.qhgb_synchronize(self.h), "qhgb_synchronize")
+
+    def update_event(self, event_id: int, t: float = 0.0):
+        check(self.L.qhgb_update_event(self.h, int(event_id), float(t)), "qhgb_update_event")
+
+    def flush_events(self, t: float = 0.0):
+        check(self.L.qhgb_flush_events(self.h, float(t)), "qhgb_flush_events")
+
+    # ---- read back --------------------------------------------------------------------------
+    def num_agents(self) -> int:
+        return int(self.L.qhgb_get_num_agents_effective(self.h))
+
+    def counts(self, out=None):
+        out = np.zeros(self.ncells, np.uint64) if out is None else out
+        check(self.L.qhgb_get_num_agents_array(self.h, _p(out)), "qhgb_get_num_agents_array")
+        return out
+
+    def step_stats(self) -> StepStats:
+        s = StepStats()
+        check(self.L.qhgb_get_step_stats(self.h, C.byref(s)), "qhgb_get_step_stats")
+        return s
+
+    def agents(self) -> dict:
+        n = self.num_agents()
+        out = dict(cell=np.zeros(n, np.int32), cell_id=np.zeros(n, np.int32), id=np.zeros(n, np.int64),
+                   birth=np.zeros(n, np.float32), gender=np.zeros(n, np.uint8), age=np.zeros(n, np.float32),
+                   last_birth=np.zeros(n, np.float32), life=np.zeros(n, np.uint32), mate_id=np.zeros(n, np.int64))
+        k = self.L.qhgb_get_agents(self.h, n, *[_p(out[f]) for f in
+                                                ("cell", "cell_id", "id", "birth", "gender", "age", "last_birth", "life", "mate_id")])
+        if k != n:
+            raise QhgError(f"qhgb_get_agents -> {k}: {self.L.qhgb_last_error().decode()}")
+        return out
+
+    def weights(self):
+        out = np.zeros((self.ncells, self.max_neigh + 1))
+        check(self.L.qhgb_get_env_weights(self.h, _p(out)), "qhgb_get_env_weights")
+        return out
+
+    def bd(self):
+        b, d = np.zeros(self.ncells), np.zeros(self.ncells)
+        check(self.L.qhgb_get_birth_death_probs(self.h, _p(b), _p(d)), "qhgb_get_birth_death_probs")
+        return b, d
+
+    def atan_prob(self, age):
+        age = np.ascontiguousarray(age, np.float32)
+        p = np.zeros(len(age))
+        check(self.L.qhgb_atan_death_prob(self.h, len(age), _p(age), _p(p)), "qhgb_atan_death_prob")
+        return p
+
+    # ---- measurement ------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.L.qhgb_get_launch_count(self.h))
+
+    def reset_kernel_times(self, enable=True):
+        check(self.L.qhgb_reset_kernel_times(self.h, int(enable)), "qhgb_reset_kernel_times")
+
+    def kernel_times(self) -> dict:
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        calls = (C.c_int64 * cap)()
+        n = self.L.qhgb_get_kernel_times(self.h, cap, names, ms, calls)
+        return {names[i].decode(): (ms[i], calls[i]) for i in range(min(n, cap))}
+
+    def event_record(self, slot: int):
+        check(self.L.qhgb_event_record(self.h, int(slot)), "qhgb_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = float(self.L.qhgb_event_elapsed_ms(self.h, int(a), int(b)))
+        if ms < 0:
+            raise QhgError(self.L.qhgb_last_error().decode())
+        return ms
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.qhgb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

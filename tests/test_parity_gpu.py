@@ -1,0 +1,201 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference.
+
+* deterministic sub-steps (per-cell counts, Verhulst b/d, cell weights, ATanDeath probability):
+  bit-exact against the oracle, within 1e-6 relative of the reference's own arrays (oracle/_ref);
+* whole trajectories: bit-exact against the oracle's counter mode (same random streams), compared
+  as sets of agents because the order inside a cell is not part of the result.
+"""
+import numpy as np
+import pytest
+
+from conftest import sort_agents
+from qhg4_b200.icogrid import make_ico_grid, make_torus_grid, synthetic_altitude, synthetic_population
+from qhg4_b200.params import seed_state, tut_environ_alt
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("cell", "id", "birth", "gender", "age", "last_birth", "life")
+
+
+def make_pair(params, nbr, alt, pop, ice=None, seed=0):
+    from oracle import port
+    from qhg4_b200.population import GpuPopulation
+    st = seed_state(seed)
+    g = GpuPopulation.from_params(params, nbr, alt, ice=ice, state16=st)
+    o = port.OraclePop(params, nbr, alt, ice=ice, mode=port.MODE_COUNTER, state16=st)
+    g.add_agents(pop)
+    o.add_agents(pop)
+    g.pre_loop()
+    o.start()
+    return g, o
+
+
+def assert_same_population(g, o, step):
+    assert g.num_agents() == o.num_agents(), f"step {step}: {g.num_agents()} vs {o.num_agents()}"
+    ga, oa = sort_agents(g.agents()), sort_agents(o.agents())
+    for f in FIELDS:
+        assert np.array_equal(ga[f], oa[f]), f"step {step}: field {f} differs"
+    assert np.array_equal(g.counts(), o.counts()), f"step {step}: per-cell counts differ"
+
+
+def test_trajectory_bit_exact_vs_oracle(small_world):
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(40000, alt, seed=5)
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=11)
+    assert_same_population(g, o, -1)
+    for k in range(25):
+        g.step(float(k))
+        o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        gb, gd = g.bd()
+        ob, od = o.bd()
+        assert np.array_equal(gb, ob) and np.array_equal(gd, od)
+    assert np.array_equal(g.weights(), o.weights())
+
+
+def test_mates_match_oracle(small_world):
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(30000, alt, seed=6)
+    pop["life"][:] = 5  # everybody fertile from the start so that step 0 already pairs
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=2)
+    for k in range(3):
+        g.initialize_step(float(k))
+        o.initialize_step(float(k))
+        ga, oa = sort_agents(g.agents()), sort_agents(o.agents())
+        assert np.array_equal(ga["mate_id"], oa["mate_id"])
+        if k == 0:
+            assert (ga["mate_id"] >= 0).sum() > 1000
+        for lvl in sorted(set(g.prios.values())):
+            g.do_actions(lvl, float(k))
+            o.do_actions(lvl, float(k))
+        g.finalize_step()
+        o.finalize_step()
+        assert_same_population(g, o, k)
+
+
+def test_deterministic_substeps_vs_reference(small_world):
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(40000, alt, seed=7)
+    par = tut_environ_alt(20.0)
+    from qhg4_b200.population import GpuPopulation
+    g = GpuPopulation.from_params(par, nbr, alt)
+    g.add_agents(pop)
+    g.pre_loop()
+    r = refsim.RefSim(par, nbr, alt, threads=2)
+    r.add_agents(pop)
+    r.start()
+    assert np.array_equal(g.counts(), r.counts())            # per-cell counts: bit-exact
+    g.initialize_step(0.0)
+    r.step(0.0)                                               # the reference computes b, d, weights in its initialize
+    gb, gd = g.bd()
+    rb, rd = r.bd()
+    np.testing.assert_allclose(gb, rb, rtol=1e-6, atol=0)     # north-star tolerance: 1e-6 relative
+    np.testing.assert_allclose(gd, rd, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(g.weights(), r.weights(), rtol=1e-6, atol=0)
+    ages = np.linspace(0, 90, 2001).astype(np.float32)
+    np.testing.assert_allclose(g.atan_prob(ages), r.atan_prob(ages), rtol=1e-6, atol=1e-12)
+    r.close()
+
+
+def test_rebinning_keeps_every_agent(small_world):
+    """compaction + re-binning: with no births and deaths the agent set is preserved bit for bit and sorted by cell."""
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(50000, alt, seed=8)
+    par = tut_environ_alt(20.0)
+    for name in ("ATanDeath", "Verhulst", "Fertility", "RandomPair"):
+        del par.prios[name]
+    par.modules["WeightedMove"]["WeightedMove_prob"] = "0.9"
+    g, o = make_pair(par, nbr, alt, pop, seed=4)
+    for k in range(5):
+        g.step(float(k))
+        o.step(float(k))
+        a = g.agents()
+        assert np.all(np.diff(a["cell"]) >= 0), "agents are not binned by cell"
+        assert np.array_equal(np.sort(a["id"]), np.arange(50000))
+        assert_same_population(g, o, k)
+        assert g.step_stats().moves > 30000
+
+
+def test_geo_event_kills_drowned(small_world):
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(30000, alt, seed=9)
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=3)
+    for k in range(3):
+        g.step(float(k)); o.step(float(k))
+    alt2 = alt - 400.0  # sea level rises
+    ice = (xyz[:, 2] > 0.8).astype(np.float64)
+    g.set_env("Altitude", alt2); g.set_env("Ice", ice)
+    o.set_env("Altitude", alt2); o.set_env("Ice", ice)
+    g.update_event(2, 3.0); g.flush_events(3.0)
+    o.update_event(2, 3.0)
+    assert_same_population(g, o, "event")
+    a = g.agents()
+    assert np.all(alt2[a["cell"]] >= 0) and np.all(ice[a["cell"]] == 0)
+    for k in range(3, 8):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+    assert np.array_equal(g.weights(), o.weights())
+
+
+def test_pentagon_and_ocean_cells():
+    """edge cases: 5-neighbour cells, cells whose whole neighbourhood has weight 0 (uniform pick), empty cells."""
+    nbr, xyz = make_ico_grid(3)
+    alt = np.full(len(nbr), -100.0)      # everything below sea level: all weights 0
+    alt[:40] = 500.0
+    pop = synthetic_population(5000, alt, seed=1, cells=np.arange(len(nbr)))
+    g, o = make_pair(tut_environ_alt(30.0), nbr, alt, pop, seed=5)
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+
+
+def test_empty_population_and_late_agents(small_world):
+    nbr, xyz, alt = small_world
+    from qhg4_b200.population import GpuPopulation
+    g = GpuPopulation.from_params(tut_environ_alt(20.0), nbr, alt)
+    g.pre_loop()
+    g.step(0.0)
+    assert g.num_agents() == 0 and g.counts().sum() == 0
+    pop = synthetic_population(1000, alt, seed=2)
+    g.add_agents(pop)
+    assert g.num_agents() == 1000 and g.counts().sum() == 1000
+    g.step(1.0)
+    assert 800 < g.num_agents() <= 1000
+
+
+def test_statistical_equivalence_vs_reference():
+    """stochastic sub-steps: per-cell population and age distributions over 32 seeds, two-sample KS, p > 0.01."""
+    from scipy import stats
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    from qhg4_b200.population import GpuPopulation
+    nbr = make_torus_grid(24, 24)
+    alt = np.full(len(nbr), 800.0)
+    alt[::7] = 1400.0
+    par = tut_environ_alt(20.0)
+    nseeds, nsteps = 32, 40
+    tot_g, tot_r, age_g, age_r, occ_g, occ_r = [], [], [], [], [], []
+    for s in range(nseeds):
+        pop = synthetic_population(6000, alt, seed=100 + s)
+        st = seed_state(1000 + s)
+        g = GpuPopulation.from_params(par, nbr, alt, state16=st)
+        g.add_agents(pop); g.pre_loop()
+        r = refsim.RefSim(par, nbr, alt, threads=2, state16=st)
+        r.add_agents(pop); r.start()
+        for k in range(nsteps):
+            g.step(float(k)); r.step(float(k))
+        ga, ra = g.agents(), r.agents()
+        tot_g.append(g.num_agents()); tot_r.append(r.num_agents())
+        age_g.append(ga["age"]); age_r.append(ra["age"])
+        occ_g.append(g.counts()); occ_r.append(r.counts())
+        r.close(); g.close()
+    p_tot = stats.ks_2samp(tot_g, tot_r).pvalue
+    p_age = stats.ks_2samp(np.concatenate(age_g)[::7], np.concatenate(age_r)[::7]).pvalue
+    p_occ = stats.ks_2samp(np.concatenate(occ_g)[::3], np.concatenate(occ_r)[::3]).pvalue
+    assert p_tot > 0.01 and p_age > 0.01 and p_occ > 0.01, (p_tot, p_age, p_occ)
