@@ -37,7 +37,7 @@ struct DevStats {
     int nBirths, nDeaths, nMoves;
     int overflow;
     unsigned step;  // counter word of the random streams; +1 per finalizeStep
-    int pad;
+    int oversize;   // a tile did not fit the shared-memory path: the host reruns the step on the generic path
     long long nextID;
 };
 
@@ -95,14 +95,17 @@ __device__ __forceinline__ int warp_sum(int v) {
 // (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and reset of the step's counters
 __global__ void k_cell_init(int nCells, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
                             double b0, double d0, double theta, double K, int doVerhulst,
-                            int *__restrict__ newCount, int *__restrict__ birthCount, int *__restrict__ nFert) {
+                            int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
+                            int *__restrict__ birthCount, int *__restrict__ nFert) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
         if (doVerhulst) {
             double q = __ddiv_rn((double)count[c], K);
             B[c] = __dadd_rn(b0, __dmul_rn(__dadd_rn(theta, -b0), q));
             D[c] = __dadd_rn(d0, __dmul_rn(__dadd_rn(theta, -d0), q));
         }
-        newCount[c] = 0;
+        stay[c] = 0;
+        arrive[c] = 0;
+        cursor[c] = 0;
         birthCount[c] = 0;
         nFert[2 * c] = 0;
         nFert[2 * c + 1] = 0;
@@ -209,14 +212,122 @@ __global__ void k_pair_match(const DevStats *__restrict__ st, AgentArrays a, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// the fused per-agent pass: every enabled action in priority order (core/SPopulation.cpp:554-577 runs them as
-// separate passes; an action only touches its own agent, so one pass in the same order is equivalent).
-// Output per agent: destination cell (-1 = dead), rank inside the destination cell, new flag byte.
+// per-cell read-only data the actions touch (L2 resident)
+struct CellEnv {
+    const int *nbr;
+    const uint8_t *nNbr;
+    const uint8_t *ice;   // may be NULL
+    const double *alt;
+    const double *W;
+    const double *B;
+    const double *D;
+};
+
+struct Decision {
+    bool alive, born, moving;
+    int pick;    // 0: stays, 1..6: moves to neighbour slot pick-1
+    int to;      // destination cell
+    uint8_t f;   // new flag byte (gender | fertile)
+    float age;
+};
+
+// every enabled action in priority order for ONE agent (core/SPopulation.cpp:554-577 runs them as separate passes
+// over all agents; an action only touches its own agent and queues births/deaths/moves, so running them back to
+// back per agent in the same order is equivalent).  A dead agent skips the remaining actions (:568).
+__device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEnv &E, unsigned step, int64_t id, float birth,
+                                                float ageIn, int c, uint8_t f, bool hasMate, const float *lastBirthPtr) {
+    Decision d;
+    d.alive = true; d.born = false; d.moving = false; d.pick = 0; d.to = c; d.f = f; d.age = ageIn;
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    bool have0 = false, have1 = false;
+#pragma unroll 1
+    for (int k = 0; k < P.nOps; k++) {
+        if (!d.alive) break;
+        switch (P.ops[k]) {
+        case OP_GETOLD:  // actions/GetOld.cpp:37-48
+            d.age = __fsub_rn(P.t, birth);
+            break;
+        case OP_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
+            d.age = __fsub_rn(P.t, birth);
+            double x = __dmul_rn(P.atanSlope, __dadd_rn((double)d.age, -P.atanMaxAge));
+            if (x > P.atanXlo) {  // below Xlo the probability is negative: nobody dies, no draw needed
+                if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+                bool dies = true;  // above Xhi the probability exceeds 1
+                if (x < P.atanXhi) {
+                    double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(x)), 3.141592653589793));
+                    dies = u2d(r0.x) < p;
+                }
+                if (dies) d.alive = false;
+            }
+            break;
+        }
+        case OP_OLDAGEDEATH: {  // actions/OldAgeDeath.cpp:48-67
+            d.age = __fsub_rn(P.t, birth);
+            if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+            double r = u2range(r1.w, P.oadLo, P.oadHi);
+            if ((double)d.age > __dadd_rn(P.oadMaxAge, r)) d.alive = false;
+            break;
+        }
+        case OP_WEIGHTEDMOVE: {  // actions/WeightedMove.cpp:45-106
+            if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+            if (u2d(r0.y) < P.moveProb) {
+                if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                const int nreal = E.nNbr[c];
+                const double *row = E.W + (size_t)c * WSTRIDE;
+                int pick = -1;
+                const double wmax = row[nreal];
+                if (row[0] == wmax) {
+                    pick = (int)u2int(r1.x, 0, nreal + 1);
+                } else {
+                    double r2 = __dmul_rn(u2d(r1.x), wmax);
+                    for (int q = 0; q < nreal + 1; q++) {
+                        if (r2 < row[q]) { pick = q; break; }
+                    }
+                }
+                if (pick > 0) {
+                    int dst = E.nbr[(size_t)c * MAXN + pick - 1];
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; }
+                }
+            }
+            break;
+        }
+        case OP_FERTILITY: {  // actions/Fertility.cpp:49-74
+            bool fert;
+            if (!(d.f & F_MALE)) {
+                fert = (d.age > P.fertMinAge) && (d.age < P.fertMaxAge) && (__fsub_rn(P.t, *lastBirthPtr) > P.fertInterbirth);
+            } else {
+                fert = d.age > P.fertMinAge;
+            }
+            d.f = (uint8_t)((d.f & F_MALE) | (fert ? F_FERTILE : 0));
+            break;
+        }
+        case OP_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
+            if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+            const double b = E.B[c];
+            if (b > 0) {
+                if (!(d.f & F_MALE) && hasMate) {
+                    if (u2d(r0.z) < b) d.born = true;
+                }
+            } else if (b < 0) {
+                if (u2d(r0.z) < -b) d.alive = false;
+            }
+            if (d.alive && u2d(r0.w) < E.D[c]) d.alive = false;
+            break;
+        }
+        case OP_DROWN:  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
+            if (E.alt[c] < 0 || (E.ice && E.ice[c])) d.alive = false;
+            break;
+        }
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic path, pass 1: one thread per agent, pairing read from `mate`.  Output per agent: destination cell
+// (-1 = dead), rank inside the destination cell, new flag byte.  Used for cells too large for the tiled path.
 __global__ void __launch_bounds__(256)
-k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate, ActParams P,
-          const int *__restrict__ nbr, const uint8_t *__restrict__ nNbr, const uint8_t *__restrict__ ice,
-          const double *__restrict__ alt, const double *__restrict__ W, const double *__restrict__ B,
-          const double *__restrict__ D, int *__restrict__ newCount, int *__restrict__ birthCount,
+k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate, ActParams P, CellEnv E,
+          int *__restrict__ arrive, int *__restrict__ birthCount,
           int *__restrict__ dest, int *__restrict__ rank, uint8_t *__restrict__ oflags) {
     const int n = st->nAgents;
     const unsigned step = st->step;
@@ -224,109 +335,27 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + threadIdx.x;
         const bool valid = i < n;
-        bool alive = valid, born = false;
-        int c = 0, to = 0;
-        uint8_t f = 0;
+        Decision d;
+        d.alive = false; d.born = false; d.moving = false; d.to = 0; d.f = 0;
+        int c = 0;
         if (valid) {
-            const int64_t id = a.id[i];
-            const float birth = a.birth[i];
             c = a.cell[i];
-            f = a.flags[i];
-            to = c;
-            float age = P.storeAge ? a.age[i] : 0.0f;
-            bool moving = false;
-            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-            bool have0 = false, have1 = false;
-#pragma unroll 1
-            for (int k = 0; k < P.nOps; k++) {
-                if (!alive) break;
-                switch (P.ops[k]) {
-                case OP_GETOLD:  // actions/GetOld.cpp:37-48
-                    age = __fsub_rn(P.t, birth);
-                    break;
-                case OP_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
-                    age = __fsub_rn(P.t, birth);
-                    double x = __dmul_rn(P.atanSlope, __dadd_rn((double)age, -P.atanMaxAge));
-                    if (x > P.atanXlo) {  // below Xlo the probability is negative: nobody dies, no draw needed
-                        if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
-                        bool dies = true;  // above Xhi the probability exceeds 1
-                        if (x < P.atanXhi) {
-                            double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(x)), 3.141592653589793));
-                            dies = u2d(r0.x) < p;
-                        }
-                        if (dies) alive = false;
-                    }
-                    break;
-                }
-                case OP_OLDAGEDEATH: {  // actions/OldAgeDeath.cpp:48-67
-                    age = __fsub_rn(P.t, birth);
-                    if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
-                    double r = u2range(r1.w, P.oadLo, P.oadHi);
-                    if ((double)age > __dadd_rn(P.oadMaxAge, r)) alive = false;
-                    break;
-                }
-                case OP_WEIGHTEDMOVE: {  // actions/WeightedMove.cpp:45-106
-                    if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
-                    if (u2d(r0.y) < P.moveProb) {
-                        if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
-                        const int nreal = nNbr[c];
-                        const double *row = W + (size_t)c * WSTRIDE;
-                        int pick = -1;
-                        const double wmax = row[nreal];
-                        if (row[0] == wmax) {
-                            pick = (int)u2int(r1.x, 0, nreal + 1);
-                        } else {
-                            double r2 = __dmul_rn(u2d(r1.x), wmax);
-                            for (int q = 0; q < nreal + 1; q++) {
-                                if (r2 < row[q]) { pick = q; break; }
-                            }
-                        }
-                        if (pick > 0) {
-                            int dst = nbr[(size_t)c * MAXN + pick - 1];
-                            if (dst >= 0 && !(ice && ice[dst])) { to = dst; moving = true; }
-                        }
-                    }
-                    break;
-                }
-                case OP_FERTILITY: {  // actions/Fertility.cpp:49-74
-                    bool fert;
-                    if (!(f & F_MALE)) {
-                        fert = (age > P.fertMinAge) && (age < P.fertMaxAge) && (__fsub_rn(P.t, a.lastBirth[i]) > P.fertInterbirth);
-                    } else {
-                        fert = age > P.fertMinAge;
-                    }
-                    f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
-                    break;
-                }
-                case OP_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
-                    if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
-                    const double b = B[c];
-                    if (b > 0) {
-                        if (!(f & F_MALE) && mate[i] >= 0) {
-                            if (u2d(r0.z) < b) born = true;
-                        }
-                    } else if (b < 0) {
-                        if (u2d(r0.z) < -b) alive = false;
-                    }
-                    if (alive && u2d(r0.w) < D[c]) alive = false;
-                    break;
-                }
-                case OP_DROWN:  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
-                    if (alt[c] < 0 || (ice && ice[c])) alive = false;
-                    break;
-                }
-            }
-            if (P.storeAge && alive) a.age[i] = age;  // moved with the agent by k_scatter
-            if (moving) nMove++;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
-            if (!alive) nDead++;
-            if (born) nBorn++;
+            bool needMate = false;
+            for (int k = 0; k < P.nOps; k++) needMate |= (P.ops[k] == OP_VERHULST);
+            const uint8_t f = a.flags[i];
+            const bool hasMate = needMate && !(f & F_MALE) && mate[i] >= 0;
+            d = run_actions(P, E, step, a.id[i], a.birth[i], P.storeAge ? a.age[i] : 0.0f, c, f, hasMate, a.lastBirth + i);
+            if (P.storeAge && d.alive) a.age[i] = d.age;  // moved with the agent by k_scatter
+            if (d.moving) nMove++;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
+            if (!d.alive) nDead++;
+            if (d.born) nBorn++;
         }
-        int r = warp_agg_inc(newCount, to, alive);
-        warp_agg_inc(birthCount, c, born);
+        int r = warp_agg_inc(arrive, d.to, d.alive);
+        warp_agg_inc(birthCount, c, d.born);
         if (valid) {
-            dest[i] = alive ? to : -1;
+            dest[i] = d.alive ? d.to : -1;
             rank[i] = r;
-            oflags[i] = (uint8_t)(f | (born ? F_BORN : 0));
+            oflags[i] = (uint8_t)(d.f | (d.born ? F_BORN : 0));
         }
     }
     nDead = warp_sum(nDead); nMove = warp_sum(nMove); nBorn = warp_sum(nBorn);
@@ -343,13 +372,14 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
 constexpr int SCAN_TILE = 2048;  // cells per block (256 threads x 8)
 
 __global__ void __launch_bounds__(256)
-k_scan_tiles(int nCells, const int *__restrict__ newCount, const int *__restrict__ birthCount, int2 *__restrict__ tileSums) {
+k_scan_tiles(int nCells, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
+             int2 *__restrict__ tileSums) {
     __shared__ int sa[8], sb[8];
     int base = blockIdx.x * SCAN_TILE;
     int sumA = 0, sumB = 0;
     for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
         int c = base + k;
-        if (c < nCells) { int b = birthCount[c]; sumA += newCount[c] + b; sumB += b; }
+        if (c < nCells) { int b = birthCount[c]; sumA += stay[c] + arrive[c] + b; sumB += b; }
     }
     sumA = warp_sum(sumA); sumB = warp_sum(sumB);
     if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = sumA; sb[threadIdx.x >> 5] = sumB; }
@@ -362,7 +392,7 @@ k_scan_tiles(int nCells, const int *__restrict__ newCount, const int *__restrict
 }
 
 __global__ void __launch_bounds__(256)
-k_scan_apply(int nCells, int nTiles, const int *__restrict__ newCount, const int *__restrict__ birthCount,
+k_scan_apply(int nCells, int nTiles, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
              const int2 *__restrict__ tileSums, int *__restrict__ newStart, int *__restrict__ birthBase,
              int *__restrict__ count, DevStats *__restrict__ st, int capacity) {
     __shared__ int sa[8], sb[8];
@@ -387,7 +417,7 @@ k_scan_apply(int nCells, int nTiles, const int *__restrict__ newCount, const int
     for (int k = 0; k < 8; k++) {
         int c = c0 + k;
         int b = (c < nCells) ? birthCount[c] : 0;
-        int v = (c < nCells) ? newCount[c] + b : 0;
+        int v = (c < nCells) ? stay[c] + arrive[c] + b : 0;
         va[k] = ta; vb[k] = tb;
         ta += v; tb += b;
     }
@@ -411,7 +441,7 @@ k_scan_apply(int nCells, int nTiles, const int *__restrict__ newCount, const int
         if (c < nCells) {
             newStart[c] = exA + va[k];
             birthBase[c] = exB + vb[k];
-            count[c] = newCount[c] + birthCount[c];
+            count[c] = stay[c] + arrive[c] + birthCount[c];
         }
     }
     if (blockIdx.x == nTiles - 1 && threadIdx.x == 255) {
@@ -429,8 +459,8 @@ k_scan_apply(int nCells, int nTiles, const int *__restrict__ newCount, const int
 __global__ void __launch_bounds__(256)
 k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const int *__restrict__ cellStart,
           const int *__restrict__ dest, const int *__restrict__ rank, const uint8_t *__restrict__ oflags,
-          const int *__restrict__ newStart, const int *__restrict__ newCount, const int *__restrict__ birthBase,
-          float t, int storeAge, RngKey key) {
+          const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ arrive,
+          const int *__restrict__ birthBase, float t, int storeAge, RngKey key) {
     if (st->overflow) return;
     const int n = st->nAgents;
     const unsigned step = st->step;
@@ -441,7 +471,7 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
         int64_t id = 0;
         if (d >= 0 || (f & F_BORN)) id = a.id[i];
         if (d >= 0) {
-            int pos = newStart[d] + rank[i];
+            int pos = newStart[d] + stay[d] + rank[i];
             o.id[pos] = id;
             o.birth[pos] = a.birth[i];
             o.lastBirth[pos] = a.lastBirth[i];
@@ -459,7 +489,7 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
             }
             const int64_t cid = nextID + birthBase[c] + r;
             const uint32_t g = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
-            const int pos = newStart[c] + newCount[c] + r;
+            const int pos = newStart[c] + stay[c] + arrive[c] + r;
             o.id[pos] = cid;
             o.birth[pos] = t;
             o.lastBirth[pos] = 0.0f;
@@ -471,7 +501,7 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
 }
 
 __global__ void k_step_end(DevStats *st, int advanceStep) {
-    if (st->overflow) return;
+    if (st->overflow || st->oversize) return;
     st->nAgents = st->nNew;
     st->nextID += st->nBirths;
     if (advanceStep) st->step++;
@@ -482,6 +512,7 @@ __global__ void k_step_begin(DevStats *st) {
     st->nDeaths = 0;
     st->nMoves = 0;
     st->nNew = 0;
+    st->oversize = 0;
 }
 
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {

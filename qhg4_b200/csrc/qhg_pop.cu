@@ -6,7 +6,7 @@
 // core/Prioritizer.h:19-78): named actions with priorities and enable flags, named attributes, per-step
 // totals.  No CPU fallback exists: every entry point that computes launches kernels from qhg_kernels.cuh.
 #include "../../include/qhg_b200.h"
-#include "qhg_kernels.cuh"
+#include "qhg_tiles.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -92,7 +92,7 @@ struct qhgb_pop {
     RngKey key{0, 0};
 
     // grid / env
-    DevBuf<int> nbr, gid, count, cellStart[2], newCount, birthCount, birthBase, nFert;
+    DevBuf<int> nbr, gid, count[2], cellStart[2], stay, arrive, cursor, birthCount, birthBase, nFert;
     DevBuf<uint8_t> nNbr, ice;
     DevBuf<double> alt, W, B, D;
     DevBuf<int2> tileSums;
@@ -105,7 +105,7 @@ struct qhgb_pop {
     DevBuf<int64_t> id[2];
     DevBuf<float> birth[2], lastBirth[2], age[2];
     DevBuf<int> cell[2], mate, prank, ranked, dest, rank;
-    DevBuf<uint8_t> flags[2], oflags;
+    DevBuf<uint8_t> flags[2], oflags, dec;
     DevBuf<uint32_t> pkey;
     int cur = 0;
     DevBuf<DevStats> dstats;
@@ -116,7 +116,9 @@ struct qhgb_pop {
     float lastAgeTime = 0;
 
     // step state
-    bool preLooped = false, inStep = false, pairingValid = false;
+    bool preLooped = false, inStep = false, pairingValid = false, needPair = false, doVerhulst = false;
+    bool forceGeneric = false;
+    int64_t genericSteps = 0, tiledSteps = 0;
     bool evalFirst = true, evalNeedUpdate = false;
     float curTime = -1;
     std::vector<unsigned> levels;
@@ -165,6 +167,22 @@ struct qhgb_pop {
         }                                                                      \
     } while (0)
 
+#define LAUNCH_SMEM(p, name, kern, grid, block, smem, ...)                     \
+    do {                                                                       \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                              \
+        if ((p)->timing) {                                                     \
+            cudaEventCreate(&e0_);                                             \
+            cudaEventCreate(&e1_);                                             \
+            cudaEventRecord(e0_, (p)->stream);                                 \
+        }                                                                      \
+        kern<<<(grid), (block), (smem), (p)->stream>>>(__VA_ARGS__);           \
+        (p)->launches++;                                                       \
+        if ((p)->timing) {                                                     \
+            cudaEventRecord(e1_, (p)->stream);                                 \
+            (p)->kt(name).pending.push_back({e0_, e1_});                       \
+        }                                                                      \
+    } while (0)
+
 namespace {
 
 int allocAgents(qhgb_pop *p, int64_t cap) {
@@ -198,6 +216,7 @@ int allocAgents(qhgb_pop *p, int64_t cap) {
     CK(q.dest.alloc(cap));
     CK(q.rank.alloc(cap));
     CK(q.oflags.alloc(cap));
+    CK(q.dec.alloc(cap));
     CK(q.pkey.alloc(cap));
     q.capacity = cap;
     q.pairingValid = false;
@@ -313,26 +332,86 @@ int computeWeights(qhgb_pop *p) {
     return 0;
 }
 
+CellEnv cellEnv(qhgb_pop *p) {
+    return CellEnv{p->nbr.p, p->nNbr.p, p->haveIce ? p->ice.p : nullptr, p->alt.p, p->W.p, p->B.p, p->D.p};
+}
+
+int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
+    qhgb_pop &q = *p;
+    LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
+    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.nCells), 256, q.nCells, q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
+           q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
+           q.birthCount.p, q.nFert.p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// stand-alone pairing (generic path, and whenever the host asks for the mates between initializeStep and finalizeStep)
+int ensurePairing(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    if (q.pairingValid) return 0;
+    const int ga = q.gridFor(q.nAgents);
+    AgentArrays a = q.arrays(q.cur);
+    if (q.needPair) {
+        LAUNCH(p, "k_pair_keys", k_pair_keys, ga, 256, q.dstats.p, a, q.key, q.pkey.p, q.mate.p, q.nFert.p);
+        LAUNCH(p, "k_pair_rank", k_pair_rank, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.pkey.p, q.prank.p, q.ranked.p);
+        LAUNCH(p, "k_pair_match", k_pair_match, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.nFert.p, q.prank.p, q.ranked.p, q.mate.p);
+    } else if (q.nAgents > 0) {
+        CK(cudaMemsetAsync(q.mate.p, 0xFF, (size_t)q.nAgents * sizeof(int), q.stream));  // -1: nobody is paired
+    }
+    CK(cudaGetLastError());
+    q.pairingValid = true;
+    return 0;
+}
+
+int launchScan(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    const int nTiles = (q.nCells + SCAN_TILE - 1) / SCAN_TILE;
+    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, q.nCells, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p);
+    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, q.nCells, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p,
+           q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count[q.cur ^ 1].p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
+    return 0;
+}
+
 // decide -> scan -> scatter with the given program; used by finalizeStep, by the GEO event and (with an empty
-// program) to bin freshly uploaded agents by cell
-int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool isBirthStep) {
+// program, generic path) to bin freshly uploaded agents by cell.
+//   tiled   = the fast path (qhg_tiles.cuh): needs the current buffer binned by cell
+//   generic = one thread per agent, global atomics; any order of the input, any cell size
+int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, bool doPair) {
     qhgb_pop &q = *p;
     const int n = (int)q.nAgents;
-    const int ga = q.gridFor(n), gc = q.gridFor(q.nCells);
-    const int nTiles = (q.nCells + SCAN_TILE - 1) / SCAN_TILE;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
-    LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, q.nbr.p, q.nNbr.p,
-           q.haveIce ? q.ice.p : nullptr, q.alt.p, q.W.p, q.B.p, q.D.p, q.newCount.p, q.birthCount.p, q.dest.p,
-           q.rank.p, q.oflags.p);
-    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, q.nCells, q.newCount.p, q.birthCount.p, q.tileSums.p);
-    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, q.nCells, nTiles, q.newCount.p, q.birthCount.p, q.tileSums.p,
-           q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count.p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
-    LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
-           q.cellStart[q.cur ^ 1].p, q.newCount.p, q.birthBase.p, P.t, P.storeAge, q.key);
-    LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0);
-    (void)gc; (void)isBirthStep;
-    CK(cudaGetLastError());
-    if (pullStats(p) != 0) return -1;
+    bool tiled = binned && !q.forceGeneric && n > 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (tiled) {
+            const int nT = (n + TILE_T - 1) / TILE_T;
+            const size_t sm = sizeof(TileSmem);
+            LAUNCH_SMEM(p, "k_tile_decide", k_tile_decide, nT, TB, sm, q.dstats.p, a, P, cellEnv(p), q.cellStart[q.cur].p,
+                        doPair ? 1 : 0, 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, (int *)nullptr);
+            launchScan(p);
+            LAUNCH_SMEM(p, "k_tile_scatter", k_tile_scatter, nT, TB, sm, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dec.p, q.nbr.p,
+                        q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key);
+        } else {
+            const int ga = q.gridFor(n);
+            q.needPair = doPair;
+            if (ensurePairing(p) != 0) return -1;
+            LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, cellEnv(p), q.arrive.p, q.birthCount.p,
+                   q.dest.p, q.rank.p, q.oflags.p);
+            launchScan(p);
+            LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
+                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key);
+        }
+        LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0);
+        CK(cudaGetLastError());
+        if (pullStats(p) != 0) return -1;
+        if (tiled && q.hstats->oversize) {  // a cell larger than a tile: redo the step on the generic path
+            tiled = false;
+            if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
+            continue;
+        }
+        (tiled ? q.tiledSteps : q.genericSteps)++;
+        break;
+    }
     if (q.hstats->overflow) return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
     q.cur ^= 1;
     q.nAgents = q.hstats->nAgents;
@@ -341,16 +420,6 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool isBirthS
     q.lastDeaths = q.hstats->nDeaths;
     q.lastMoves = q.hstats->nMoves;
     q.pairingValid = false;
-    return 0;
-}
-
-int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
-    qhgb_pop &q = *p;
-    LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
-    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.nCells), 256, q.nCells, q.count.p, q.B.p, q.D.p, q.A("Verhulst_b0"),
-           q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), doVerhulst ? 1 : 0, q.newCount.p, q.birthCount.p,
-           q.nFert.p);
-    CK(cudaGetLastError());
     return 0;
 }
 
@@ -387,16 +456,25 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(cudaGetDeviceProperties(&prop, device));
     p->numSMs = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(k_tile_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    {
+        const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
+        p->forceGeneric = e && strcmp(e, "generic") == 0;
+    }
     size_t nc = (size_t)n_cells;
     CK(p->nbr.alloc(nc * MAXN));
     CK(p->gid.alloc(nc));
     CK(p->nNbr.alloc(nc));
     CK(p->ice.alloc(nc));
     CK(p->alt.alloc(nc));
-    CK(p->count.alloc(nc));
+    CK(p->count[0].alloc(nc));
+    CK(p->count[1].alloc(nc));
     CK(p->cellStart[0].alloc(nc + 1));
     CK(p->cellStart[1].alloc(nc + 1));
-    CK(p->newCount.alloc(nc));
+    CK(p->stay.alloc(nc));
+    CK(p->arrive.alloc(nc));
+    CK(p->cursor.alloc(nc));
     CK(p->birthCount.alloc(nc));
     CK(p->birthBase.alloc(nc));
     CK(p->nFert.alloc(2 * nc));
@@ -405,7 +483,8 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(p->D.alloc(nc));
     CK(p->tileSums.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
     CK(p->dstats.alloc(1));
-    CK(cudaMemsetAsync(p->count.p, 0, nc * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->count[0].p, 0, nc * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->count[1].p, 0, nc * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->cellStart[0].p, 0, (nc + 1) * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->cellStart[1].p, 0, (nc + 1) * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->W.p, 0, nc * WSTRIDE * sizeof(double), p->stream));
@@ -427,8 +506,8 @@ int qhgb_destroy(qhgb_pop *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (auto &k : p->ktimes) for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    p->nbr.release(); p->gid.release(); p->count.release(); p->cellStart[0].release(); p->cellStart[1].release();
-    p->newCount.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
+    p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release();
+    p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
     for (int b = 0; b < 2; b++) {
@@ -436,7 +515,7 @@ int qhgb_destroy(qhgb_pop *p) {
         p->cell[b].release(); p->flags[b].release();
     }
     p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
-    p->oflags.release(); p->pkey.release(); p->dstats.release();
+    p->oflags.release(); p->dec.release(); p->pkey.release(); p->dstats.release();
     for (auto &e : p->userEv) if (e) cudaEventDestroy(e);
     if (p->hstats) cudaFreeHost(p->hstats);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -610,7 +689,7 @@ int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *
         P.nOps = 0;
         int rc = pushStats(p);
         if (rc == 0) rc = resetCellCounters(p, false);
-        if (rc == 0) rc = runPipeline(p, P, false, false);
+        if (rc == 0) rc = runPipeline(p, P, false, false, false);
         return rc;
     }
     return 0;
@@ -629,7 +708,8 @@ int qhgb_pre_loop(qhgb_pop *p) {
     ActParams P = buildProgram(p, nullptr, 0);
     P.nOps = 0;
     if (resetCellCounters(p, false) != 0) return -1;
-    if (runPipeline(p, P, false, false) != 0) return -1;
+    p->doVerhulst = false;
+    if (runPipeline(p, P, false, false, false) != 0) return -1;
     p->preLooped = true;
     p->evalFirst = true;
     return 0;
@@ -650,16 +730,11 @@ int qhgb_initialize_step(qhgb_pop *p, float t) {
     bool doVer = ver && ver->prio >= 0 && ver->enabled;
     if (doVer && !(q.A("Verhulst_K", 0) != 0)) return fail("Verhulst: Verhulst_K is not set");
     if (resetCellCounters(p, doVer) != 0) return -1;
-    const int ga = q.gridFor(q.nAgents);
-    AgentArrays a = q.arrays(q.cur);
-    if (pair && pair->prio >= 0 && pair->enabled) {
-        LAUNCH(p, "k_pair_keys", k_pair_keys, ga, 256, q.dstats.p, a, q.key, q.pkey.p, q.mate.p, q.nFert.p);
-        LAUNCH(p, "k_pair_rank", k_pair_rank, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.pkey.p, q.prank.p, q.ranked.p);
-        LAUNCH(p, "k_pair_match", k_pair_match, ga, 256, q.dstats.p, a, q.cellStart[q.cur].p, q.nFert.p, q.prank.p, q.ranked.p, q.mate.p);
-        q.pairingValid = true;
-    } else if (!q.pairingValid) {
-        CK(cudaMemsetAsync(q.mate.p, 0xFF, (size_t)q.nAgents * sizeof(int), q.stream));  // -1: nobody is paired
-    }
+    // pairing (RandomPair::initialize) is fused into the decide pass of finalizeStep; ensurePairing() runs it
+    // stand-alone if the host looks at the mates before that
+    q.needPair = pair && pair->prio >= 0 && pair->enabled;
+    q.doVerhulst = doVer;
+    q.pairingValid = false;
     if (ev && ev->prio >= 0 && ev->enabled && (q.evalNeedUpdate || q.evalFirst)) {
         q.evalFirst = false;
         if (computeWeights(p) != 0) return -1;
@@ -688,7 +763,7 @@ int qhgb_finalize_step(qhgb_pop *p) {
     if (q.nAgents + q.nAgents / 2 + 1024 > q.capacity) return fail("qhgb_finalize_step: agent buffers too small");
     HostAction *ev = q.find("SingleEvaluator[Alt]");
     if (ev && ev->prio >= 0 && ev->enabled) q.evalNeedUpdate = false;  // SingleEvaluator::finalize, :125-130
-    int rc = runPipeline(p, P, true, true);
+    int rc = runPipeline(p, P, true, true, q.needPair);
     q.inStep = false;
     if (rc != 0) return rc;
     q.stepsDone++;
@@ -732,7 +807,8 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
         P.ops[0] = OP_DROWN;
         P.storeAge = p->ageValid ? 1 : 0;
         if (resetCellCounters(p, false) != 0) return -1;
-        int rc = runPipeline(p, P, false, false);
+        p->doVerhulst = false;
+        int rc = runPipeline(p, P, false, true, false);
         if (rc != 0) return rc;
         p->evalNeedUpdate = true;  // SingleEvaluator::notify, actions/SingleEvaluator.cpp:332-346
     }
@@ -751,7 +827,7 @@ int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     if (!p || !out) return fail("qhgb_get_num_agents_array: NULL argument");
     CK(cudaSetDevice(p->device));
     std::vector<int> h(p->nCells);
-    CK(cudaMemcpyAsync(h.data(), p->count.p, (size_t)p->nCells * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(h.data(), p->count[p->cur].p, (size_t)p->nCells * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     for (int c = 0; c < p->nCells; c++) out[c] = (uint64_t)h[c];
     return 0;
@@ -788,7 +864,7 @@ int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_i
     if (age && !(!p->ageValid)) D2H(age, p->age[b].p, m * sizeof(float));
     if (last_birth) D2H(last_birth, p->lastBirth[b].p, m * sizeof(float));
     if (mate_id) {
-        if (p->pairingValid) {
+        if (p->inStep && ensurePairing(p) == 0) {
             int64_t *tmp = nullptr;
             err |= cudaMalloc(&tmp, m * sizeof(int64_t)) != cudaSuccess;
             if (!err) {

@@ -38,7 +38,14 @@ def assert_same_population(g, o, step):
     assert np.array_equal(g.counts(), o.counts()), f"step {step}: per-cell counts differ"
 
 
-def test_trajectory_bit_exact_vs_oracle(small_world):
+@pytest.fixture(params=["tiled", "generic"])
+def path(request, monkeypatch):
+    """both device paths: the tiled shared-memory one and the one-thread-per-agent one"""
+    monkeypatch.setenv("QHG_B200_PATH", request.param)
+    return request.param
+
+
+def test_trajectory_bit_exact_vs_oracle(small_world, path):
     nbr, xyz, alt = small_world
     pop = synthetic_population(40000, alt, seed=5)
     g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=11)
@@ -55,7 +62,7 @@ def test_trajectory_bit_exact_vs_oracle(small_world):
     assert np.array_equal(g.weights(), o.weights())
 
 
-def test_mates_match_oracle(small_world):
+def test_mates_match_oracle(small_world, path):
     nbr, xyz, alt = small_world
     pop = synthetic_population(30000, alt, seed=6)
     pop["life"][:] = 5  # everybody fertile from the start so that step 0 already pairs
@@ -121,7 +128,7 @@ def test_rebinning_keeps_every_agent(small_world):
         assert g.step_stats().moves > 30000
 
 
-def test_geo_event_kills_drowned(small_world):
+def test_geo_event_kills_drowned(small_world, path):
     nbr, xyz, alt = small_world
     pop = synthetic_population(30000, alt, seed=9)
     g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=3)
@@ -142,7 +149,7 @@ def test_geo_event_kills_drowned(small_world):
     assert np.array_equal(g.weights(), o.weights())
 
 
-def test_pentagon_and_ocean_cells():
+def test_pentagon_and_ocean_cells(path):
     """edge cases: 5-neighbour cells, cells whose whole neighbourhood has weight 0 (uniform pick), empty cells."""
     nbr, xyz = make_ico_grid(3)
     alt = np.full(len(nbr), -100.0)      # everything below sea level: all weights 0
@@ -150,6 +157,34 @@ def test_pentagon_and_ocean_cells():
     pop = synthetic_population(5000, alt, seed=1, cells=np.arange(len(nbr)))
     g, o = make_pair(tut_environ_alt(30.0), nbr, alt, pop, seed=5)
     for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+
+
+def test_crowded_cells_fall_back_to_generic_path():
+    """cells with more agents than a tile holds (2048): the step is redone on the generic path, same result"""
+    nbr, xyz = make_ico_grid(3)
+    alt = np.full(len(nbr), 800.0)
+    pop = synthetic_population(60000, alt, seed=3, cells=np.array([5, 6, 7, 40, 41, 100]))
+    g, o = make_pair(tut_environ_alt(9000.0), nbr, alt, pop, seed=8)
+    for k in range(4):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+
+
+def test_dense_and_sparse_cells_mix():
+    """tile boundaries: dense cells next to long runs of empty cells, tiles of very different cell counts"""
+    nbr, xyz = make_ico_grid(31)
+    alt = synthetic_altitude(xyz, seed=2)
+    land = np.flatnonzero(alt > 0)
+    rng = np.random.default_rng(0)
+    hot = rng.choice(land, 40, replace=False)
+    pop_a = synthetic_population(30000, alt, seed=4, cells=hot)            # ~750 per cell
+    pop_b = synthetic_population(20000, alt, seed=5)                       # ~3 per land cell
+    pop = {k: np.concatenate([pop_a[k], pop_b[k]]) for k in pop_a}
+    pop["id"] = np.arange(len(pop["id"]), dtype=np.int64)
+    g, o = make_pair(tut_environ_alt(600.0), nbr, alt, pop, seed=9)
+    for k in range(8):
         g.step(float(k)); o.step(float(k))
         assert_same_population(g, o, k)
 
