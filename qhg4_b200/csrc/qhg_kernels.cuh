@@ -43,7 +43,7 @@ struct DevStats {
 
 struct ActParams {
     int nOps;
-    uint8_t ops[MAX_OPS];
+    unsigned long long prog;  // the action program: 4 bits per op, first op in the low nibble
     float t;
     int storeAge;
     // ATanDeath (actions/ATanDeath.cpp:49-59,66-90)
@@ -56,6 +56,8 @@ struct ActParams {
     float fertMinAge, fertMaxAge, fertInterbirth;
     RngKey key;
 };
+
+__host__ __device__ __forceinline__ int prog_op(const ActParams &P, int k) { return (int)((P.prog >> (4 * k)) & 15ull); }
 
 struct PolyLineDev {  // utils/PolyLine.cpp:60-89
     int nseg;  // 0 => identity
@@ -243,7 +245,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
 #pragma unroll 1
     for (int k = 0; k < P.nOps; k++) {
         if (!d.alive) break;
-        switch (P.ops[k]) {
+        switch (prog_op(P, k)) {
         case OP_GETOLD:  // actions/GetOld.cpp:37-48
             d.age = __fsub_rn(P.t, birth);
             break;
@@ -341,7 +343,7 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
         if (valid) {
             c = a.cell[i];
             bool needMate = false;
-            for (int k = 0; k < P.nOps; k++) needMate |= (P.ops[k] == OP_VERHULST);
+            for (int k = 0; k < P.nOps; k++) needMate |= (prog_op(P, k) == OP_VERHULST);
             const uint8_t f = a.flags[i];
             const bool hasMate = needMate && !(f & F_MALE) && mate[i] >= 0;
             d = run_actions(P, E, step, a.id[i], a.birth[i], P.storeAge ? a.age[i] : 0.0f, c, f, hasMate, a.lastBirth + i);

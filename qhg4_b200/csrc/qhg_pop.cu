@@ -6,7 +6,7 @@
 // core/Prioritizer.h:19-78): named actions with priorities and enable flags, named attributes, per-step
 // totals.  No CPU fallback exists: every entry point that computes launches kernels from qhg_kernels.cuh.
 #include "../../include/qhg_b200.h"
-#include "qhg_tiles.cuh"
+#include "qhg_cells.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -270,7 +270,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_VERHULST: op = OP_VERHULST; break;
         default: break;  // evaluators and pairing have no per-agent execute()
         }
-        if (op && P.nOps < MAX_OPS) P.ops[P.nOps++] = op;
+        if (op && P.nOps < MAX_OPS) { P.prog |= (unsigned long long)op << (4 * P.nOps); P.nOps++; }
     }
     P.t = t;
     P.storeAge = 1;
@@ -303,7 +303,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
 // stored or moved: it is (time of the last refresh - birth time), also for the records handed back to the host.
 bool programNeedsStoredAge(const ActParams &P) {
     for (int k = 0; k < P.nOps; k++) {
-        switch (P.ops[k]) {
+        switch (prog_op(P, k)) {
         case OP_GETOLD: case OP_ATANDEATH: case OP_OLDAGEDEATH: return false;
         case OP_FERTILITY: return true;
         default: break;
@@ -375,7 +375,7 @@ int launchScan(qhgb_pop *p) {
 
 // decide -> scan -> scatter with the given program; used by finalizeStep, by the GEO event and (with an empty
 // program, generic path) to bin freshly uploaded agents by cell.
-//   tiled   = the fast path (qhg_tiles.cuh): needs the current buffer binned by cell
+//   tiled   = the fast path (qhg_cells.cuh, one warp per cell): needs the current buffer binned by cell
 //   generic = one thread per agent, global atomics; any order of the input, any cell size
 int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, bool doPair) {
     qhgb_pop &q = *p;
@@ -384,13 +384,12 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     bool tiled = binned && !q.forceGeneric && n > 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
-            const int nT = (n + TILE_T - 1) / TILE_T;
-            const size_t sm = sizeof(TileSmem);
-            LAUNCH_SMEM(p, "k_tile_decide", k_tile_decide, nT, TB, sm, q.dstats.p, a, P, cellEnv(p), q.cellStart[q.cur].p,
-                        doPair ? 1 : 0, 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, (int *)nullptr);
+            const int gridC = q.numSMs * 4;  // persistent: 4 CTAs of 8 warps per SM, one warp per cell at a time
+            LAUNCH(p, "k_cell_decide", k_cell_decide, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells, q.cellStart[q.cur].p,
+                   doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
             launchScan(p);
-            LAUNCH_SMEM(p, "k_tile_scatter", k_tile_scatter, nT, TB, sm, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dec.p, q.nbr.p,
-                        q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key);
+            LAUNCH(p, "k_cell_scatter", k_cell_scatter, gridC, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
+                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key);
         } else {
             const int ga = q.gridFor(n);
             q.needPair = doPair;
@@ -404,7 +403,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0);
         CK(cudaGetLastError());
         if (pullStats(p) != 0) return -1;
-        if (tiled && q.hstats->oversize) {  // a cell larger than a tile: redo the step on the generic path
+        if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
             tiled = false;
             if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
             continue;
@@ -456,8 +455,6 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(cudaGetDeviceProperties(&prop, device));
     p->numSMs = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(k_tile_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    CK(cudaFuncSetAttribute(k_tile_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     {
         const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
         p->forceGeneric = e && strcmp(e, "generic") == 0;
@@ -687,6 +684,7 @@ int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *
         p->nextID = std::max(p->nextID, p->maxID + 1);
         ActParams P = buildProgram(p, nullptr, p->curTime);
         P.nOps = 0;
+        P.prog = 0;
         int rc = pushStats(p);
         if (rc == 0) rc = resetCellCounters(p, false);
         if (rc == 0) rc = runPipeline(p, P, false, false, false);
@@ -707,6 +705,7 @@ int qhgb_pre_loop(qhgb_pop *p) {
     // the step pipeline with an empty action list; ages are carried along
     ActParams P = buildProgram(p, nullptr, 0);
     P.nOps = 0;
+        P.prog = 0;
     if (resetCellCounters(p, false) != 0) return -1;
     p->doVerhulst = false;
     if (runPipeline(p, P, false, false, false) != 0) return -1;
@@ -804,7 +803,7 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
     if (event_id == QHGB_EVENT_ID_GEO) {  // populations/tut_EnvironAltPop.cpp:100-127
         ActParams P = buildProgram(p, nullptr, t);
         P.nOps = 1;
-        P.ops[0] = OP_DROWN;
+        P.prog = OP_DROWN;
         P.storeAge = p->ageValid ? 1 : 0;
         if (resetCellCounters(p, false) != 0) return -1;
         p->doVerhulst = false;
