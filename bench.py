@@ -93,7 +93,7 @@ def build_world(subdiv, n_agents, seed=1):
     alt = synthetic_altitude(xyz, seed=1)
     n_land = int((alt > 0).sum())
     K = max(1.0, round(n_agents / n_land / 0.7))  # N/K ~ 0.7 on land cells
-    pop = synthetic_population(n_agents, alt, seed=seed)
+    pop = synthetic_population(n_agents, alt, seed=seed, fertile=True)  # pairing and births active from the first step
     return nbr, alt, pop, tut_environ_alt(K), K
 
 

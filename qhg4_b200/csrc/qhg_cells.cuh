@@ -26,39 +26,51 @@
 
 namespace qhg {
 
-constexpr int CW = 8;            // warps per CTA
+constexpr int CW = 4;            // warps per CTA
 constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles; larger ones -> generic path
 constexpr int MAXF = 512;        // most fertile females of one cell that can be ranked in shared memory
 constexpr int QCAP = 64;         // work-queue entries per warp
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
+constexpr int DU = 2;            // agents per lane and chunk in the decide pass
 
 // decision byte handed from pass 1 to pass 2: bit0 male, bit1 fertile (the agent's new flags), bit2 gave birth,
 // bits 3-5 move code: 0 stays, 1..6 neighbour slot + 1, 7 dead
 constexpr int DEC_MOVE_SHIFT = 3;
 constexpr uint8_t DEC_DEAD = 7;
-// transient bits while a cell is being worked on
-constexpr uint8_t T_HASMATE = 4, T_ATANDIES = 0x40, T_DEADNOW = 0x80;
+// transient bits while a cell is being worked on (bit2 = birth candidate until the pairing is settled)
+constexpr uint8_t T_ATANDIES = 0x40, T_DEADNOW = 0x80;
 
 struct WarpSmem {
-    double qaX[QCAP];          // ATanDeath queue: argument of the atan
+    double row[8];             // the cell's cumulated weight row (7 used)
+    long long qmId[QCAP];      // WeightedMove queue: agent id
+    float qaAge[QCAP];         // ATanDeath queue: the agent's age
     uint32_t qaU[QCAP];        //                  the agent's death draw
     uint32_t keys[MAXF];       // pairing keys of the cell's fertile females
-    uint16_t keyJ[MAXF];       //   and their position in the cell
+    uint16_t ffJ[MAXF];        //   and their position in the cell
     uint16_t qaJ[QCAP];
     uint16_t qmJ[QCAP];        // WeightedMove queue: position in the cell
-    uint8_t dec[WCAP];         // flags -> provisional decision of every agent of the cell
+    uint16_t candQ[MAXF];      // birth candidates among the fertile females (index into keys / ffJ)
+    int outC[8];               // movers of the cell per direction
+    int nbrC[8];               // the cell's neighbours (6 used)
+    uint8_t dec[WCAP];         // provisional decision of every agent of the cell
 };
+
+// the action program the fast path is specialised for at compile time: the tutorial populations' order
+// GetOld, ATanDeath, WeightedMove, Fertility, Verhulst (tutorial_data/xmldat/tut_EnvironAlt.xml priorities)
+constexpr unsigned long long PROG_TUT5 = (unsigned long long)OP_GETOLD | ((unsigned long long)OP_ATANDEATH << 4) |
+                                         ((unsigned long long)OP_WEIGHTEDMOVE << 8) | ((unsigned long long)OP_FERTILITY << 12) |
+                                         ((unsigned long long)OP_VERHULST << 16);
 
 struct ProgramInfo {  // warp-uniform facts about the action program
     bool needAct0, hasFert, hasVerhulst;
     bool moveAfterAtan, bornAfterAtan;
 };
 
-__device__ __forceinline__ ProgramInfo program_info(const ActParams &P) {
+__device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int nOps) {
     ProgramInfo I{false, false, false, false, false};
     int ka = -1;
-    for (int k = 0; k < P.nOps; k++) {
-        int op = prog_op(P, k);
+    for (int k = 0; k < nOps; k++) {
+        int op = (int)((prog >> (4 * k)) & 15ull);
         if (op == OP_ATANDEATH) { ka = k; I.needAct0 = true; }
         if (op == OP_WEIGHTEDMOVE) { I.needAct0 = true; if (ka >= 0) I.moveAfterAtan = true; }
         if (op == OP_VERHULST) { I.needAct0 = true; I.hasVerhulst = true; if (ka >= 0) I.bornAfterAtan = true; }
@@ -68,19 +80,34 @@ __device__ __forceinline__ ProgramInfo program_info(const ActParams &P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1
-__global__ void __launch_bounds__(CW * 32)
+// pass 1.  SPEC = true: the program is PROG_TUT5, known at compile time (straight-line code);
+//          SPEC = false: any program, interpreted from P.prog.
+#ifndef QHG_DECIDE_MINB
+#define QHG_DECIDE_MINB 6
+#endif
+template <bool SPEC>
+__global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
 k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int nCells, const int *__restrict__ cellStart,
               int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec) {
     __shared__ WarpSmem smem[CW];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmem &S = smem[wid];
+    uint8_t *const sdec = S.dec;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
-    const ProgramInfo I = program_info(P);
+    const unsigned long long prog = SPEC ? PROG_TUT5 : P.prog;
+    const int nOps = SPEC ? 5 : P.nOps;
+    const ProgramInfo I = program_info(prog, nOps);
     const int gw = blockIdx.x * CW + wid, nW = gridDim.x * CW;
     int nDead = 0, nMove = 0, nBorn = 0;  // warp-uniform tallies
+    // loop invariants in registers
+    const float tNow = P.t, fertMin = P.fertMinAge, fertMax = P.fertMaxAge, fertInter = P.fertInterbirth;
+    const float atanAgeLo = P.atanAgeLo, atanAgeHi = P.atanAgeHi;
+    const unsigned long long tMove = prob_threshold(P.moveProb);
+    const RngKey key = P.key;
+    const RoundKeys RK = round_keys(key);
+    const bool storeAge = P.storeAge != 0;
 
     for (int c = gw; c < nCells; c += nW) {
         const int s = cellStart[c], n = cellStart[c + 1] - s;
@@ -89,66 +116,23 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             if (lane == 0) atomicExch(&st->oversize, 1);
             continue;
         }
-        // ---- fertile counts; flags go to shared memory ----------------------------------------------------------
-        int nF = 0, nM = 0;
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            uint8_t f = (j < n) ? a.flags[s + j] : 0;
-            if (j < n) S.dec[j] = f;
-            nF += __popc(__ballot_sync(FULL, (f & (F_FERTILE | F_MALE)) == F_FERTILE));
-            nM += __popc(__ballot_sync(FULL, (f & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE)));
+        if (lane < 8) {
+            S.outC[lane] = 0;
+            S.row[lane] = (lane < WSTRIDE) ? E.W[(size_t)c * WSTRIDE + lane] : 0.0;
+            S.nbrC[lane] = (lane < MAXN) ? E.nbr[(size_t)c * MAXN + lane] : -1;
         }
-        // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ----------
-        // fertile females and fertile males are ranked by (random key, id); equal ranks mate.  Only "does this
-        // female have a mate" matters to the actions: with nF <= nM every fertile female has one, otherwise the nM
-        // females with the smallest keys.
-        bool allPaired = false;
-        if (doPair && nF > 0 && nM > 0) {
-            if (nF <= nM) {
-                allPaired = true;
-            } else if (nF > MAXF) {
-                if (lane == 0) atomicExch(&st->oversize, 1);
-                continue;
-            } else {
-                int nf = 0;
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    const bool ff = (j < n) && ((S.dec[j] & (F_FERTILE | F_MALE)) == F_FERTILE);
-                    const unsigned m = __ballot_sync(FULL, ff);
-                    if (ff) {
-                        const int pos = nf + __popc(m & lt);
-                        S.keys[pos] = agent_draws(a.id[s + j], step, STREAM_PAIR, P.key).x;
-                        S.keyJ[pos] = (uint16_t)j;
-                    }
-                    nf += __popc(m);
-                }
-                __syncwarp();
-                for (int q0 = 0; q0 < nF; q0 += 32) {
-                    const int q = q0 + lane;
-                    if (q < nF) {
-                        const uint32_t k = S.keys[q];
-                        int r = 0;
-                        for (int e = 0; e < nF; e++) {
-                            const uint32_t ke = S.keys[e];
-                            if (ke < k) r++;
-                            else if (ke == k && e != q && a.id[s + S.keyJ[e]] < a.id[s + S.keyJ[q]]) r++;
-                        }
-                        if (r < nM) S.dec[S.keyJ[q]] |= T_HASMATE;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- actions, provisional decisions ------------------------------------------------------------------------
-        int nqa = 0, nqm = 0;
+        int nF = 0, nM = 0, nqa = 0, nqm = 0;
+        bool tooMany = false;
         const int nreal = E.nNbr[c];
-        const double *row = E.W + (size_t)c * WSTRIDE;
+        const double *row = S.row;
         const double bC = I.hasVerhulst ? E.B[c] : 0.0, dC = I.hasVerhulst ? E.D[c] : 0.0;
+        // the probability tests of LinearBirth / LinearDeath as exact integer thresholds on the 32-bit draws
+        const unsigned long long tBirth = prob_threshold(bC), tBirthNeg = prob_threshold(-bC), tDeath = prob_threshold(dC);
         auto flush_atan = [&]() {  // ATanDeath::execute, actions/ATanDeath.cpp:75-83, for the queued agents
             for (int e = lane; e < nqa; e += 32) {
-                double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(S.qaX[e])), 3.141592653589793));
-                if (u2d(S.qaU[e]) < p) S.dec[S.qaJ[e]] |= T_ATANDIES;
+                const double x = __dmul_rn(P.atanSlope, __dadd_rn((double)S.qaAge[e], -P.atanMaxAge));
+                const double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(x)), 3.141592653589793));
+                if (u2d(S.qaU[e]) < p) sdec[S.qaJ[e]] |= T_ATANDIES;
             }
             nqa = 0;
             __syncwarp();
@@ -156,7 +140,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         auto flush_move = [&]() {  // WeightedMove::execute, actions/WeightedMove.cpp:56-98, for the queued agents
             for (int e = lane; e < nqm; e += 32) {
                 const int j = S.qmJ[e];
-                const uint32_t u = agent_draws(a.id[s + j], step, STREAM_ACT1, P.key).x;
+                const uint32_t u = agent_draws_rk(S.qmId[e], step, STREAM_ACT1, RK).x;
                 int pick = -1;
                 const double wmax = row[nreal];
                 if (row[0] == wmax) {
@@ -168,124 +152,190 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                     }
                 }
                 if (pick > 0) {
-                    const int dst = E.nbr[(size_t)c * MAXN + pick - 1];
-                    if (dst >= 0 && !(E.ice && E.ice[dst])) S.dec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    const int dst = S.nbrC[pick - 1];
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
                 }
             }
             nqm = 0;
             __syncwarp();
         };
 
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            const bool valid = j < n;
-            bool needAtan = false, needMove = false;
-            double x = 0;
-            uint32_t uDeath = 0;
-            if (valid) {
-                const int g = s + j;
-                const uint8_t f0 = S.dec[j];
-                uint8_t f = f0 & (F_MALE | F_FERTILE);
-                const bool hasMate = allPaired ? (f == F_FERTILE) : ((f0 & T_HASMATE) != 0);
-                const int64_t id = a.id[g];
-                const float birth = a.birth[g];
-                float age = P.storeAge ? a.age[g] : 0.0f;
-                const float lastBirth = I.hasFert ? a.lastBirth[g] : 0.0f;
-                uint4 r0 = make_uint4(0, 0, 0, 0);
-                if (I.needAct0) r0 = agent_draws(id, step, STREAM_ACT0, P.key);
-                bool alive = true, born = false;
-#pragma unroll 1
-                for (int k = 0; k < P.nOps && alive; k++) {
-                    switch (prog_op(P, k)) {
-                    case OP_GETOLD:  // actions/GetOld.cpp:37-48
-                        age = __fsub_rn(P.t, birth);
-                        break;
-                    case OP_ATANDEATH: {  // actions/ATanDeath.cpp:66-90
-                        age = __fsub_rn(P.t, birth);
-                        x = __dmul_rn(P.atanSlope, __dadd_rn((double)age, -P.atanMaxAge));
-                        if (x > P.atanXlo) {          // below: probability < 0, nobody dies
-                            if (x < P.atanXhi) { needAtan = true; uDeath = r0.x; }  // decided when the queue is flushed
-                            else alive = false;       // above: probability > 1
-                        }
-                        break;
-                    }
-                    case OP_OLDAGEDEATH: {  // actions/OldAgeDeath.cpp:48-67
-                        age = __fsub_rn(P.t, birth);
-                        const uint32_t u = agent_draws(id, step, STREAM_ACT1, P.key).w;
-                        if ((double)age > __dadd_rn(P.oadMaxAge, u2range(u, P.oadLo, P.oadHi))) alive = false;
-                        break;
-                    }
-                    case OP_WEIGHTEDMOVE:  // actions/WeightedMove.cpp:45-106; the neighbour is chosen at the flush
-                        if (u2d(r0.y) < P.moveProb) needMove = true;
-                        break;
-                    case OP_FERTILITY: {  // actions/Fertility.cpp:49-74
-                        bool fert;
-                        if (!(f & F_MALE)) fert = (age > P.fertMinAge) && (age < P.fertMaxAge) && (__fsub_rn(P.t, lastBirth) > P.fertInterbirth);
-                        else fert = age > P.fertMinAge;
-                        f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
-                        break;
-                    }
-                    case OP_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
-                        if (bC > 0) {
-                            if (!(f & F_MALE) && hasMate && u2d(r0.z) < bC) born = true;
-                        } else if (bC < 0) {
-                            if (u2d(r0.z) < -bC) alive = false;
-                        }
-                        if (alive && u2d(r0.w) < dC) alive = false;
-                        break;
-                    }
-                    case OP_DROWN:  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
-                        if (E.alt[c] < 0 || (E.ice && E.ice[c])) alive = false;
-                        break;
-                    }
-                }
-                if (P.storeAge) a.age[g] = age;
-                S.dec[j] = (uint8_t)(f | (born ? F_BORN : 0) | (alive ? 0 : T_DEADNOW));
+        // ---- one pass over the cell: fertile census + all actions, provisional decisions --------------------------
+        // software pipeline: the next chunk's loads are in flight while this chunk is evaluated; every lane carries
+        // DU agents per chunk so that their (independent) Philox chains overlap
+        int64_t idN[DU]; float birthN[DU], lastN[DU], ageN[DU]; uint8_t fN[DU];
+#pragma unroll
+        for (int u = 0; u < DU; u++) {
+            const int j = u * 32 + lane;
+            idN[u] = 0; birthN[u] = 0; lastN[u] = 0; ageN[u] = 0; fN[u] = 0;
+            if (j < n) {
+                idN[u] = a.id[s + j]; birthN[u] = a.birth[s + j]; fN[u] = a.flags[s + j];
+                if (I.hasFert) lastN[u] = a.lastBirth[s + j];
+                if (storeAge) ageN[u] = a.age[s + j];
             }
-            // queue the rare expensive work
-            unsigned ma = __ballot_sync(FULL, needAtan), mm = __ballot_sync(FULL, needMove);
-            if (nqa + __popc(ma) > QCAP) flush_atan();
-            if (nqm + __popc(mm) > QCAP) flush_move();
-            if (needAtan) { const int e = nqa + __popc(ma & lt); S.qaX[e] = x; S.qaU[e] = uDeath; S.qaJ[e] = (uint16_t)j; }
-            if (needMove) { const int e = nqm + __popc(mm & lt); S.qmJ[e] = (uint16_t)j; }
-            nqa += __popc(ma);
-            nqm += __popc(mm);
+        }
+        for (int j0 = 0; j0 < n; j0 += 32 * DU) {
+            int64_t id[DU]; float birth[DU], lastBirth[DU], age[DU]; uint8_t f0[DU];
+            uint4 r0[DU];
+#pragma unroll
+            for (int u = 0; u < DU; u++) {
+                id[u] = idN[u]; birth[u] = birthN[u]; lastBirth[u] = lastN[u]; age[u] = ageN[u]; f0[u] = fN[u];
+                const int j2 = j0 + 32 * DU + u * 32 + lane;
+                if (j2 < n) {
+                    idN[u] = a.id[s + j2]; birthN[u] = a.birth[s + j2]; fN[u] = a.flags[s + j2];
+                    if (I.hasFert) lastN[u] = a.lastBirth[s + j2];
+                    if (storeAge) ageN[u] = a.age[s + j2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < DU; u++) r0[u] = I.needAct0 ? agent_draws_rk(id[u], step, STREAM_ACT0, RK) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < DU; u++) {
+                const int j = j0 + u * 32 + lane;
+                const bool valid = j < n;
+                // fertile census (for the pairing): positions of the fertile females, number of fertile males
+                const bool fertF = valid && ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE);
+                const unsigned mF = __ballot_sync(FULL, fertF);
+                nM += __popc(__ballot_sync(FULL, valid && ((f0[u] & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE))));
+                if (nF + __popc(mF) > MAXF) tooMany = true;
+                else if (fertF) S.ffJ[nF + __popc(mF & lt)] = (uint16_t)j;
+                nF += __popc(mF);
+
+                bool needAtan = false, needMove = false;
+                float ag = age[u];
+                if (valid) {
+                    uint8_t f = f0[u] & (F_MALE | F_FERTILE);
+                    bool alive = true, cand = false;
+#pragma unroll
+                    for (int k = 0; k < (SPEC ? 5 : MAX_OPS); k++) {
+                        if (!SPEC && k >= nOps) break;
+                        if (!alive) break;
+                        const int op = (int)((prog >> (4 * k)) & 15ull);
+                        if (op == OP_GETOLD) {  // actions/GetOld.cpp:37-48
+                            ag = __fsub_rn(tNow, birth[u]);
+                        } else if (op == OP_ATANDEATH) {  // actions/ATanDeath.cpp:66-90
+                            ag = __fsub_rn(tNow, birth[u]);
+                            if (ag >= atanAgeLo) {        // below the window the probability is < 0: nobody dies
+                                if (ag <= atanAgeHi) needAtan = true;  // inside: decided exactly when the queue is flushed
+                                else alive = false;       // above the window the probability is > 1
+                            }
+                        } else if (op == OP_OLDAGEDEATH) {  // actions/OldAgeDeath.cpp:48-67
+                            ag = __fsub_rn(tNow, birth[u]);
+                            const uint32_t uo = agent_draws(id[u], step, STREAM_ACT1, key).w;
+                            if ((double)ag > __dadd_rn(P.oadMaxAge, u2range(uo, P.oadLo, P.oadHi))) alive = false;
+                        } else if (op == OP_WEIGHTEDMOVE) {  // actions/WeightedMove.cpp:45-106; the neighbour is chosen at the flush
+                            if ((unsigned long long)r0[u].y < tMove) needMove = true;
+                        } else if (op == OP_FERTILITY) {  // actions/Fertility.cpp:49-74
+                            bool fert;
+                            if (!(f & F_MALE)) fert = (ag > fertMin) && (ag < fertMax) && (__fsub_rn(tNow, lastBirth[u]) > fertInter);
+                            else fert = ag > fertMin;
+                            f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
+                        } else if (op == OP_VERHULST) {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
+                            if (bC > 0) {
+                                // a birth needs a mate (LinearBirth.cpp:142); whether this fertile female got one is settled
+                                // once the whole cell has been seen: she is a candidate until then
+                                if ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE && (unsigned long long)r0[u].z < tBirth) cand = true;
+                            } else if (bC < 0) {
+                                if ((unsigned long long)r0[u].z < tBirthNeg) alive = false;
+                            }
+                            if (alive && (unsigned long long)r0[u].w < tDeath) alive = false;
+                        } else if (op == OP_DROWN) {  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
+                            if (E.alt[c] < 0 || (E.ice && E.ice[c])) alive = false;
+                        }
+                    }
+                    if (storeAge) a.age[s + j] = ag;
+                    sdec[j] = (uint8_t)(f | (cand ? F_BORN : 0) | (alive ? 0 : T_DEADNOW));
+                }
+                // queue the rare expensive work
+                const unsigned ma = __ballot_sync(FULL, needAtan), mm = __ballot_sync(FULL, needMove);
+                if (nqa + __popc(ma) > QCAP) flush_atan();
+                if (nqm + __popc(mm) > QCAP) flush_move();
+                if (needAtan) { const int e = nqa + __popc(ma & lt); S.qaAge[e] = ag; S.qaU[e] = r0[u].x; S.qaJ[e] = (uint16_t)j; }
+                if (needMove) { const int e = nqm + __popc(mm & lt); S.qmJ[e] = (uint16_t)j; S.qmId[e] = id[u]; }
+                nqa += __popc(ma);
+                nqm += __popc(mm);
+            }
             __syncwarp();
         }
         flush_atan();
         flush_move();
 
+        // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------
+        // fertile females and fertile males are ranked by (random key, id); equal ranks mate.  Only "does this female
+        // have a mate" matters to the actions: with nF <= nM every fertile female has one, otherwise the nM females
+        // with the smallest keys -- and only the birth candidates need to know.
+        bool mates = doPair && nF > 0 && nM > 0;
+        if (mates && nF > nM) {
+            if (tooMany) {
+                if (lane == 0) atomicExch(&st->oversize, 1);
+                continue;
+            }
+            for (int q = lane; q < nF; q += 32) S.keys[q] = agent_draws_rk(a.id[s + S.ffJ[q]], step, STREAM_PAIR, RK).x;
+            __syncwarp();
+            // the candidates, compacted, so that every lane of the ranking loop has work
+            int nCand = 0;
+            for (int q0 = 0; q0 < nF; q0 += 32) {
+                const int q = q0 + lane;
+                const bool isCand = (q < nF) && (sdec[S.ffJ[q]] & F_BORN);
+                const unsigned mc = __ballot_sync(FULL, isCand);
+                if (isCand) S.candQ[nCand + __popc(mc & lt)] = (uint16_t)q;
+                nCand += __popc(mc);
+            }
+            __syncwarp();
+            for (int i = lane; i < nCand; i += 32) {
+                const int q = S.candQ[i];
+                const uint32_t k = S.keys[q];
+                int r = 0;
+                bool tie = false;
+                for (int e = 0; e < nF; e++) {
+                    const uint32_t ke = S.keys[e];
+                    r += (ke < k) ? 1 : 0;
+                    tie |= (ke == k) && (e != q);
+                }
+                if (tie) {  // equal keys (about one pair in 10^8): the id decides
+                    const int64_t myId = a.id[s + S.ffJ[q]];
+                    for (int e = 0; e < nF; e++) {
+                        if (e != q && S.keys[e] == k && a.id[s + S.ffJ[e]] < myId) r++;
+                    }
+                }
+                if (r >= nM) sdec[S.ffJ[q]] &= (uint8_t)~F_BORN;  // no mate: no birth
+            }
+            __syncwarp();
+        }
+
         // ---- commit: final decision bytes, per-cell counts ---------------------------------------------------------
-        int stayC = 0, bornC = 0;
-        int outC[MAXN] = {0, 0, 0, 0, 0, 0};
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            const bool valid = j < n;
-            const uint8_t v = valid ? S.dec[j] : (uint8_t)T_DEADNOW;
-            const bool atanDies = (v & T_ATANDIES) != 0;
-            const bool dead = atanDies || (v & T_DEADNOW);
-            int code = (v >> DEC_MOVE_SHIFT) & 7;
-            const bool born = (v & F_BORN) && !(atanDies && I.bornAfterAtan);
-            const bool moveRegistered = valid && code != 0 && !(atanDies && I.moveAfterAtan);
-            if (valid) dec[s + j] = (uint8_t)((v & (F_MALE | F_FERTILE)) | (born ? F_BORN : 0) | ((dead ? DEC_DEAD : code) << DEC_MOVE_SHIFT));
-            if (dead) code = 0;
-            stayC += __popc(__ballot_sync(FULL, valid && !dead && code == 0));
-            bornC += __popc(__ballot_sync(FULL, valid && born));
-            nDead += __popc(__ballot_sync(FULL, valid && dead));
-            nMove += __popc(__ballot_sync(FULL, moveRegistered));
-            const unsigned mv = __ballot_sync(FULL, valid && !dead && code != 0);
-            if (mv) {
+        // every lane takes 4 consecutive agents per round and tallies in registers; one warp reduction per cell
+        int stayL = 0, bornL = 0, moveL = 0, outL = 0;
+        for (int j0 = 4 * lane; j0 < n; j0 += 128) {
 #pragma unroll
-                for (int q = 0; q < MAXN; q++) outC[q] += __popc(__ballot_sync(FULL, valid && !dead && code == q + 1));
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q;
+                if (j < n) {
+                    const uint8_t v = sdec[j];
+                    const bool atanDies = (v & T_ATANDIES) != 0;
+                    const bool dead = atanDies || (v & T_DEADNOW);
+                    const int code = (v >> DEC_MOVE_SHIFT) & 7;
+                    const bool born = mates && (v & F_BORN) && !(atanDies && I.bornAfterAtan);
+                    dec[s + j] = (uint8_t)((v & (F_MALE | F_FERTILE)) | (born ? F_BORN : 0) | ((dead ? DEC_DEAD : code) << DEC_MOVE_SHIFT));
+                    bornL += born ? 1 : 0;
+                    moveL += (code != 0 && !(atanDies && I.moveAfterAtan)) ? 1 : 0;  // registered moves (core/SPopulation.cpp:1067)
+                    if (!dead) {
+                        if (code == 0) stayL++;
+                        else { outL++; atomicAdd(&S.outC[code - 1], 1); }
+                    }
+                }
             }
         }
+        const int stayC = __reduce_add_sync(FULL, stayL), bornC = __reduce_add_sync(FULL, bornL);
+        const int outC = __reduce_add_sync(FULL, outL);
+        nMove += __reduce_add_sync(FULL, moveL);
+        nDead += n - stayC - outC;
         nBorn += bornC;
+        __syncwarp();
         if (bornC > MAXMOTHERS && lane == 0) atomicExch(&st->oversize, 1);
         if (lane == 0) { stay[c] = stayC; birthCount[c] = bornC; }  // a cell belongs to exactly one warp: plain stores
         if (lane < MAXN) {
-            int cnt = 0;
-#pragma unroll
-            for (int q = 0; q < MAXN; q++) if (lane == q) cnt = outC[q];
+            const int cnt = S.outC[lane];
             if (cnt) atomicAdd(&arrive[E.nbr[(size_t)c * MAXN + lane]], cnt);
         }
         __syncwarp();
@@ -323,17 +373,27 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
         if (n == 0) continue;
         const int ns = newStart[c];
         int stayBase = 0, nMothers = 0;
+        // software pipeline: the next chunk's loads are in flight while this chunk is written
+        uint8_t vN = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
+        int64_t idN = 0; float birthN = 0, lastN = 0, ageN = 0;
+        if (lane < n) {
+            vN = dec[s + lane]; idN = a.id[s + lane]; birthN = a.birth[s + lane]; lastN = a.lastBirth[s + lane];
+            if (storeAge) ageN = a.age[s + lane];
+        }
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
-            const bool valid = j < n;
-            const int g = s + j;
-            const uint8_t v = valid ? dec[g] : (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
+            const uint8_t v = vN;
+            const int64_t id = idN; const float birth = birthN, lastBirth = lastN, age = ageN;
+            vN = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
+            if (j + 32 < n) {
+                const int g2 = s + j + 32;
+                vN = dec[g2]; idN = a.id[g2]; birthN = a.birth[g2]; lastN = a.lastBirth[g2];
+                if (storeAge) ageN = a.age[g2];
+            }
             const int code = v >> DEC_MOVE_SHIFT;
             const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
             const unsigned ms = __ballot_sync(FULL, alive && code == 0);
             const unsigned mb = __ballot_sync(FULL, born);
-            int64_t id = 0;
-            if (alive || born) id = a.id[g];
             if (alive) {
                 int d = c, pos;
                 if (code == 0) {
@@ -343,11 +403,11 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
                     pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
                 }
                 o.id[pos] = id;
-                o.birth[pos] = a.birth[g];
-                o.lastBirth[pos] = a.lastBirth[g];
+                o.birth[pos] = birth;
+                o.lastBirth[pos] = lastBirth;
                 o.cell[pos] = d;
                 o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
-                if (storeAge) o.age[pos] = a.age[g];
+                if (storeAge) o.age[pos] = age;
             }
             if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
             stayBase += __popc(ms);

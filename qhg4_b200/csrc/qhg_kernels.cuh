@@ -48,6 +48,7 @@ struct ActParams {
     int storeAge;
     // ATanDeath (actions/ATanDeath.cpp:49-59,66-90)
     double atanMaxAge, atanSlope, atanScale, atanXlo, atanXhi;
+    float atanAgeLo, atanAgeHi;  // float ages strictly outside [lo, hi] are outside [Xlo, Xhi] (fast path pre-test)
     // OldAgeDeath (actions/OldAgeDeath.cpp:48-67)
     double oadMaxAge, oadLo, oadHi;
     // WeightedMove (actions/WeightedMove.cpp:45-106)

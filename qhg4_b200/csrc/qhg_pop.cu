@@ -288,6 +288,15 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         P.atanXhi = th * (1 + 1e-6) + 1e-9;
         P.atanXlo = -P.atanXhi;
     }
+    // the same window on the float age, widened by a safety margin, for the fast path's cheap pre-test
+    P.atanAgeLo = -INFINITY;
+    P.atanAgeHi = INFINITY;
+    if (std::isfinite(P.atanXhi) && P.atanSlope > 0) {
+        double lo = P.atanMaxAge + P.atanXlo / P.atanSlope, hi = P.atanMaxAge + P.atanXhi / P.atanSlope;
+        double m = 1e-3 * (fabs(lo) + fabs(hi) + 1.0);
+        P.atanAgeLo = nextafterf((float)(lo - m), -INFINITY);
+        P.atanAgeHi = nextafterf((float)(hi + m), INFINITY);
+    }
     P.oadMaxAge = p->A("OAD_max_age");
     double unc = p->A("OAD_uncertainty");
     P.oadLo = 1 - unc * P.oadMaxAge;
@@ -384,9 +393,14 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     bool tiled = binned && !q.forceGeneric && n > 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
-            const int gridC = q.numSMs * 4;  // persistent: 4 CTAs of 8 warps per SM, one warp per cell at a time
-            LAUNCH(p, "k_cell_decide", k_cell_decide, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells, q.cellStart[q.cur].p,
-                   doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
+            const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
+            if (P.prog == PROG_TUT5 && P.nOps == 5) {  // the tutorial action order: compile-time specialised kernel
+                LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells,
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
+            } else {
+                LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells,
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
+            }
             launchScan(p);
             LAUNCH(p, "k_cell_scatter", k_cell_scatter, gridC, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key);

@@ -40,6 +40,35 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
     return make_uint4(c0, c1, c2, c3);
 }
 
+// the same function with the ten round keys (warp-uniform) computed once per kernel, and the two 32x32->64
+// products of a round written so that each becomes one IMAD.WIDE
+struct RoundKeys { uint32_t a[10], b[10]; };
+__device__ __forceinline__ RoundKeys round_keys(RngKey key) {
+    RoundKeys K;
+#pragma unroll
+    for (int r = 0; r < 10; r++) { K.a[r] = key.k0 + (uint32_t)r * 0x9E3779B9u; K.b[r] = key.k1 + (uint32_t)r * 0xBB67AE85u; }
+    return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.a[r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.b[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 agent_draws_rk(int64_t id, uint32_t step, uint32_t stream, const RoundKeys &K) {
+    return philox4x32_10_rk((uint32_t)((uint64_t)id & 0xffffffffu), (uint32_t)((uint64_t)id >> 32), step, stream, K);
+}
+
+// u2d(u) < p  <=>  u < ceil(p * 2^32): the double comparison of the reference as an exact integer threshold
+// (p * 2^32 is exact; p <= 0 or NaN gives 0 = never, p >= 1 gives >= 2^32 = always)
+__device__ __forceinline__ unsigned long long prob_threshold(double p) {
+    return (p > 0.0) ? __double2ull_ru(__dmul_rn(p, 4294967296.0)) : 0ull;
+}
+
 __device__ __forceinline__ uint4 agent_draws(int64_t id, uint32_t step, uint32_t stream, RngKey key) {
     return philox4x32_10((uint32_t)((uint64_t)id & 0xffffffffu), (uint32_t)((uint64_t)id >> 32), step, stream, key);
 }

@@ -122,7 +122,7 @@ def synthetic_altitude(xyz: np.ndarray, seed: int = 1) -> np.ndarray:
 
 
 def synthetic_population(n_agents: int, altitude: np.ndarray, seed: int = 1, t0: float = 0.0,
-                         max_age: float = 60.0, cells: np.ndarray | None = None):
+                         max_age: float = 60.0, cells: np.ndarray | None = None, fertile: bool = False):
     """Agents uniform over land cells, ages U(0,max_age), gender Bernoulli(0.5).
 
     Returns a dict of SoA numpy arrays in the reference's field order
@@ -134,12 +134,16 @@ def synthetic_population(n_agents: int, altitude: np.ndarray, seed: int = 1, t0:
     cell = np.repeat(land.astype(np.int32), per_cell)
     age = (rng.random(n_agents, dtype=np.float32) * np.float32(max_age)).astype(np.float32)
     birth = (np.float32(t0) - age).astype(np.float32)
+    gender = rng.integers(0, 2, size=n_agents).astype(np.uint8)
+    life = np.ones(n_agents, dtype=np.uint32)
+    if fertile:  # the state Fertility::execute (actions/Fertility.cpp:49-74, tutorial parameters) leaves behind
+        life[(age > 15) & ((gender == 1) | (age < 50))] = 5
     return dict(
         cell=cell,
         id=np.arange(n_agents, dtype=np.int64),
         birth=birth,
-        gender=rng.integers(0, 2, size=n_agents).astype(np.uint8),
+        gender=gender,
         age=age,
-        last_birth=np.full(n_agents, -1.0, dtype=np.float32),
-        life=np.ones(n_agents, dtype=np.uint32),
+        last_birth=np.full(n_agents, -10.0 if fertile else -1.0, dtype=np.float32),
+        life=life,
     )
