@@ -196,6 +196,7 @@ struct qor_pop {
 
     // evaluator state (actions/SingleEvaluator.cpp:138-167,332-346)
     bool evalFirst = true, evalNeedUpdate = false;
+    bool evaluatorObserves = false;  // does the population addObserver() its evaluator?
 
     // storage: slots with holes, lowest-free-index allocation (utils/LBController.cpp:249-269 + utils/L2List.cpp:355-370:
     // the PASSIVE list is kept in index order, so getFreeIndex returns the lowest free slot)
@@ -560,7 +561,11 @@ struct qor_pop {
             recycleDeadSpace();
             updateNumAgentsPerCell();
             birthList.clear(); deathList.clear(); moveList.clear();
-            evalNeedUpdate = true;  // actions/SingleEvaluator.cpp:332-346, trigger id EVENT_ID_GEO
+            // notifyObservers(EVENT_ID_GEO) follows (populations/tut_EnvironAltPop.cpp:120), but tut_EnvironAltPop never
+            // registers its evaluator as an observer (no addObserver in populations/tut_EnvironAltPop.cpp:24-53, unlike
+            // populations/OoANavGenPop.cpp:59), so SingleEvaluator::notify (actions/SingleEvaluator.cpp:332-346) is never
+            // reached: the weights computed at the first step stay in force.  Replicated as is.
+            if (evaluatorObserves) evalNeedUpdate = true;
         }
         return 0;
     }

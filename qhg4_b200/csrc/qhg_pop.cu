@@ -120,6 +120,7 @@ struct qhgb_pop {
     bool forceGeneric = false;
     int64_t genericSteps = 0, tiledSteps = 0;
     bool evalFirst = true, evalNeedUpdate = false;
+    bool evaluatorObserves = false;  // does the population class addObserver() its evaluator?
     float curTime = -1;
     std::vector<unsigned> levels;
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
@@ -823,7 +824,11 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
         p->doVerhulst = false;
         int rc = runPipeline(p, P, false, true, false);
         if (rc != 0) return rc;
-        p->evalNeedUpdate = true;  // SingleEvaluator::notify, actions/SingleEvaluator.cpp:332-346
+        // notifyObservers(EVENT_ID_GEO): tut_EnvironAltPop never registers its evaluator as an observer (no addObserver in
+        // populations/tut_EnvironAltPop.cpp:24-53, unlike populations/OoANavGenPop.cpp:59), so in the reference
+        // SingleEvaluator::notify (actions/SingleEvaluator.cpp:332-346) is never reached and the weights of the first
+        // step stay in force.  Replicated as is.
+        if (p->evaluatorObserves) p->evalNeedUpdate = true;
     }
     return 0;
 }

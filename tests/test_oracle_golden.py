@@ -1,0 +1,94 @@
+"""The CPU oracle (oracle/qhg_oracle.cpp) against golden vectors generated from the reference itself
+(tests/make_golden.py -> tests/golden/*.npz) and against published known-answer vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port
+from qhg4_b200.params import tut_environ_alt
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_well512_sequences():
+    g = np.load(os.path.join(GOLD, "well512.npz"))
+    assert np.array_equal(port.well_sequence(g["state"], 256), g["seq"])
+    assert np.array_equal(port.well_sequence(g["state_thread0"], 256), g["seq_thread0"])
+    # SURVEY.md §9.2 known answers
+    assert [hex(x) for x in g["seq"][:4]] == ["0x846f945a", "0xf7691ff", "0x7880c84b", "0x8c1a003d"]
+    assert [hex(x) for x in g["seq_thread0"][:4]] == ["0x5c4b0026", "0x9a92fa79", "0xf28c9caf", "0x967286a"]
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert [hex(x) for x in port.philox([0, 0, 0, 0], [0, 0])] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in port.philox([0xffffffff] * 4, [0xffffffff] * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in port.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_polyline():
+    g = np.load(os.path.join(GOLD, "polyline.npz"))
+    d = str(g["definition"])
+    assert np.array_equal(port.polyline_eval(d, g["x"], True), g["y_float_cast"])
+    assert np.array_equal(port.polyline_eval(d, g["x"], False), g["y_double"])
+    with pytest.raises(ValueError):
+        port.polyline_eval("1 2 3", [0.0])
+
+
+def _load_case():
+    g = np.load(os.path.join(GOLD, "tut_environ_alt_ico3.npz"))
+    pop = {k[4:]: g[k] for k in g.files if k.startswith("pop_")}
+    return g, pop
+
+
+def test_deterministic_substeps_bit_exact():
+    g, pop = _load_case()
+    o = port.OraclePop(tut_environ_alt(float(g["K"])), g["nbr"], g["alt"], ice=g["ice"].astype(float), mode=port.MODE_WELL)
+    o.add_agents(pop)
+    o.start()
+    assert np.array_equal(o.counts(), g["counts0"])
+    assert np.array_equal(o.atan_prob(g["ages"]), g["p_atan"])
+    o.step(0.0)
+    b, d = o.bd()
+    assert np.array_equal(b, g["b_step0"]) and np.array_equal(d, g["d_step0"])
+    assert np.array_equal(o.weights(), g["weights"])
+    # Verhulst b0 0.8, d0 0.001, theta 0.1, K 20
+    n = g["counts0"].astype(float)
+    assert np.allclose(b, 0.8 + (0.1 - 0.8) * n / 20.0, rtol=0, atol=1e-15)
+
+
+def test_trajectory_bit_exact_one_thread():
+    """WELL mode = the reference with one OpenMP thread: same agents in the same slots after 12 steps."""
+    g, pop = _load_case()
+    o = port.OraclePop(tut_environ_alt(float(g["K"])), g["nbr"], g["alt"], ice=g["ice"].astype(float), mode=port.MODE_WELL)
+    o.add_agents(pop)
+    o.start()
+    tot = []
+    for k in range(12):
+        o.step(float(k))
+        tot.append(o.num_agents())
+    assert tot == list(g["totals"])
+    a = o.agents()
+    for f in ("cell", "id", "birth", "gender", "age", "last_birth", "life", "slot"):
+        assert np.array_equal(a[f], g["fin_" + f]), f
+    assert np.array_equal(o.counts(), g["counts_final"])
+
+
+def test_counter_mode_is_order_invariant():
+    """counter mode must not depend on the order in which agents are stored"""
+    g, pop = _load_case()
+    perm = np.random.default_rng(0).permutation(len(pop["id"]))
+    res = []
+    for p in (pop, {k: v[perm] for k, v in pop.items()}):
+        o = port.OraclePop(tut_environ_alt(float(g["K"])), g["nbr"], g["alt"], mode=port.MODE_COUNTER)
+        o.add_agents(p)
+        o.start()
+        for k in range(10):
+            o.step(float(k))
+        a = o.agents()
+        s = np.argsort(a["id"])
+        res.append({f: a[f][s] for f in ("cell", "id", "birth", "gender", "life")})
+    for f in res[0]:
+        assert np.array_equal(res[0][f], res[1][f]), f
