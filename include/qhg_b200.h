@@ -132,6 +132,20 @@ int  qhgb_get_env_weights(qhgb_pop *p, double *out);
 int  qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d);
 int  qhgb_atan_death_prob(qhgb_pop *p, int n, const float *age, double *out);
 
+/* ---- several GPUs: the grid sharded by contiguous cell ranges --------------------------------------
+ * One process per GPU, each with its own qhgb_pop holding the agents of its cell range [cell_begin[rank],
+ * cell_begin[rank+1]); environment arrays are replicated.  Per step the ranks exchange (NCCL over NVLink) the
+ * arrivals per cell, the births per rank (newborn ids are global ranks) and the packed records of the agents that
+ * crossed a range boundary.  Results are identical to the single-GPU run.  The reference has no counterpart (its only
+ * message-passing code is the tiling experiment tools_ico/MPIMulti.cpp:301-370); the simulator's note at
+ * app/Simulator.cpp:89-101 names what a distributed run needs: the global max id and the births of the preceding nodes.
+ *   qhgb_comm_get_unique_id  rank 0 creates the 128-byte NCCL id; the host distributes it (any transport)
+ *   qhgb_comm_init           before qhgb_add_agents; afterwards qhgb_add_agents keeps only the agents of the own range
+ *   qhgb_comm_get_traffic    agents sent / received in the last step */
+int  qhgb_comm_get_unique_id(void *out, int nbytes);
+int  qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin);
+int  qhgb_comm_get_traffic(qhgb_pop *p, int64_t *sent, int64_t *received);
+
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * number of kernels launched by this population since creation, and the CUDA stream they run on */
 int64_t qhgb_get_launch_count(qhgb_pop *p);

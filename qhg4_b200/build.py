@@ -15,7 +15,7 @@ SOURCES = ["qhg_pop.cu"]
 HEADERS = ["qhg_kernels.cuh", "qhg_cells.cuh", "qhg_rng.cuh", os.path.join("..", "..", "include", "qhg_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++", "-I/usr/include", "-ldl"]
 
 
 def stale() -> bool:

@@ -354,11 +354,83 @@ struct WarpSmemB {
     int64_t motherId[MAXMOTHERS];
 };
 
+// ---- multi-GPU: the grid is sharded by contiguous cell ranges, one range per rank ------------------
+// An agent that moves into a cell of another rank is not written to the local buffer but packed into the send
+// buffer of the owning rank; the receiver places it with k_place_migrants.  Environment arrays are replicated.
+struct Migrant {  // 32 bytes
+    long long id;
+    float birth, lastBirth, age;
+    int cell;
+    unsigned flags;
+    unsigned pad;
+};
+
+struct ShardArgs {
+    int on;                 // 0: single GPU
+    int rank, nranks;
+    int c0, c1;             // owned cells [c0, c1)
+    const int *cellBegin;   // nranks+1 range boundaries (device)
+    Migrant *sendBuf;       // packed by destination rank: sendOff[q] .. sendOff[q+1]
+    const int *sendOff;
+    int *sendCursor;        // nranks counters
+    long long birthOffset;  // births of the lower ranks this step (newborn ids are global ranks)
+};
+
+__device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
+    int q = 0;
+    while (q + 1 < H.nranks && c >= H.cellBegin[q + 1]) q++;
+    return q;
+}
+
+// arrivals this rank sends to every other rank = sum of its arrive[] over the other rank's cells; block q handles rank q
+__global__ void __launch_bounds__(256)
+k_shard_counts(const int *__restrict__ arrive, const int *__restrict__ cellBegin, int rank, int nranks,
+               const DevStats *__restrict__ st, int *__restrict__ info) {
+    __shared__ int sa[8];
+    const int q = blockIdx.x;
+    int sum = 0;
+    if (q != rank) {
+        for (int c = cellBegin[q] + threadIdx.x; c < cellBegin[q + 1]; c += 256) sum += arrive[c];
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) sa[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += sa[w];
+        info[q] = t;
+        if (q == 0) info[nranks] = st->nBirths;
+    }
+}
+
+// after the all-reduce of arrive[]: cells of other ranks take no agents here
+__global__ void k_shard_mask(int nCells, int c0, int c1, int *__restrict__ arrive) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        if (c < c0 || c >= c1) arrive[c] = 0;
+    }
+}
+
+__global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant *__restrict__ in, int n, AgentArrays o,
+                                 const int *__restrict__ newStart, const int *__restrict__ stay, int *__restrict__ cursor,
+                                 int storeAge) {
+    if (st->overflow || st->oversize) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Migrant m = in[i];
+        const int pos = newStart[m.cell] + stay[m.cell] + atomicAdd(&cursor[m.cell], 1);
+        o.id[pos] = m.id;
+        o.birth[pos] = m.birth;
+        o.lastBirth[pos] = m.lastBirth;
+        o.cell[pos] = m.cell;
+        o.flags[pos] = (uint8_t)m.flags;
+        if (storeAge) o.age[pos] = m.age;
+    }
+}
+
 __global__ void __launch_bounds__(CW * 32)
 k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCells, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, int *__restrict__ cursor,
-               const int *__restrict__ birthBase, float t, int storeAge, RngKey key) {
+               const int *__restrict__ birthBase, float t, int storeAge, RngKey key, ShardArgs H) {
     __shared__ WarpSmemB smem[CW];
     if (st->overflow || st->oversize) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -400,14 +472,25 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
                     pos = ns + stayBase + __popc(ms & lt);
                 } else {
                     d = nbr[(size_t)c * MAXN + code - 1];
-                    pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
+                    if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
+                        const int qo = shard_owner(H, d);
+                        Migrant m;
+                        m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
+                        m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
+                        H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                        pos = -1;
+                    } else {
+                        pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
+                    }
                 }
+                if (pos >= 0) {
                 o.id[pos] = id;
                 o.birth[pos] = birth;
                 o.lastBirth[pos] = lastBirth;
                 o.cell[pos] = d;
                 o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
                 if (storeAge) o.age[pos] = age;
+                }
             }
             if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
             stayBase += __popc(ms);
@@ -420,7 +503,7 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
             const int64_t mid = S.motherId[m];
             int r = 0;
             for (int e = 0; e < nMothers; e++) r += (S.motherId[e] < mid) ? 1 : 0;
-            const int64_t cid = nextID + birthBase[c] + r;
+            const int64_t cid = nextID + H.birthOffset + birthBase[c] + r;
             const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
             const int pos = babyBase + r;
             o.id[pos] = cid;

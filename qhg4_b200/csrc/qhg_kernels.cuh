@@ -503,10 +503,10 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
     }
 }
 
-__global__ void k_step_end(DevStats *st, int advanceStep) {
+__global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) {
     if (st->overflow || st->oversize) return;
     st->nAgents = st->nNew;
-    st->nextID += st->nBirths;
+    st->nextID += (globalBirths >= 0) ? globalBirths : (long long)st->nBirths;
     if (advanceStep) st->step++;
 }
 

@@ -8,6 +8,9 @@
 #include "../../include/qhg_b200.h"
 #include "qhg_cells.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -38,6 +41,57 @@ int fail(const char *fmt, ...) {
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// NCCL is bound at run time (dlopen) so that the library also loads on hosts without it; the communicator is only
+// needed when a population is sharded over several GPUs (qhgb_comm_init).
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+};
+NcclApi g_nccl;
+
+int loadNccl() {
+    if (g_nccl.handle) return 0;
+    const char *names[] = {getenv("QHG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail("NCCL library not found (set QHG_NCCL_LIB): %s", dlerror());
+#define QHG_SYM(field, name)                                                                 \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                              \
+    if (!g_nccl.field) return fail("NCCL symbol %s missing", name)
+    QHG_SYM(GetUniqueId, "ncclGetUniqueId");
+    QHG_SYM(CommInitRank, "ncclCommInitRank");
+    QHG_SYM(CommDestroy, "ncclCommDestroy");
+    QHG_SYM(GetErrorString, "ncclGetErrorString");
+    QHG_SYM(AllReduce, "ncclAllReduce");
+    QHG_SYM(AllGather, "ncclAllGather");
+    QHG_SYM(Send, "ncclSend");
+    QHG_SYM(Recv, "ncclRecv");
+    QHG_SYM(GroupStart, "ncclGroupStart");
+    QHG_SYM(GroupEnd, "ncclGroupEnd");
+#undef QHG_SYM
+    g_nccl.handle = h;
+    return 0;
+}
+
+#define NK(call)                                                                                           \
+    do {                                                                                                   \
+        ncclResult_t r_ = (call);                                                                          \
+        if (r_ != ncclSuccess) return fail("%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST };
@@ -126,6 +180,16 @@ struct qhgb_pop {
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
     int64_t lastBirths = 0, lastDeaths = 0, lastMoves = 0, nextID = 0;
     int64_t launches = 0;
+
+    // multi-GPU sharding (qhgb_comm_init): contiguous cell ranges, one per rank
+    bool sharded = false;
+    int shRank = 0, shRanks = 1;
+    std::vector<int> cellBegin;
+    ncclComm_t comm = nullptr;
+    DevBuf<int> dCellBegin, dInfo, dAllInfo, dSendOff, dSendCursor;
+    DevBuf<Migrant> sendBuf, recvBuf;
+    int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
+    int64_t lastSent = 0, lastReceived = 0;
 
     bool timing = false;
     cudaEvent_t userEv[8] = {nullptr};
@@ -391,7 +455,9 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     qhgb_pop &q = *p;
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
-    bool tiled = binned && !q.forceGeneric && n > 0;
+    bool tiled = binned && !q.forceGeneric && (n > 0 || q.sharded);
+    if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
+    long long stepEndBirths = -1;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
             const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
@@ -402,9 +468,62 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells,
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
             }
+            ShardArgs H{};
+            long long globalBirths = -1;
+            int nRecv = 0;
+            std::vector<int> sendCnt, recvCnt;
+            if (q.sharded) {
+                // (1) what this rank sends to every other rank, (2) arrivals per cell summed over all ranks,
+                // (3) everybody learns every count (and the births per rank: newborn ids are global ranks)
+                const int R = q.shRanks;
+                LAUNCH(p, "k_shard_counts", k_shard_counts, R, 256, q.arrive.p, q.dCellBegin.p, q.shRank, R, q.dstats.p, q.dInfo.p);
+                NK(g_nccl.AllReduce(q.arrive.p, q.arrive.p, (size_t)q.nCells, ncclInt32, ncclSum, q.comm, q.stream));
+                NK(g_nccl.AllGather(q.dInfo.p, q.dAllInfo.p, (size_t)(R + 1), ncclInt32, q.comm, q.stream));
+                CK(cudaMemcpyAsync(q.hAllInfo, q.dAllInfo.p, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
+                LAUNCH(p, "k_shard_mask", k_shard_mask, q.gridFor(q.nCells), 256, q.nCells, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1], q.arrive.p);
+                CK(cudaStreamSynchronize(q.stream));
+                sendCnt.assign(R, 0); recvCnt.assign(R, 0);
+                std::vector<int> sendOff(R + 1, 0);
+                long long below = 0, total = 0;
+                for (int r = 0; r < R; r++) {
+                    sendCnt[r] = q.hAllInfo[q.shRank * (R + 1) + r];
+                    recvCnt[r] = q.hAllInfo[r * (R + 1) + q.shRank];
+                    sendOff[r + 1] = sendOff[r] + sendCnt[r];
+                    nRecv += recvCnt[r];
+                    if (r < q.shRank) below += q.hAllInfo[r * (R + 1) + R];
+                    total += q.hAllInfo[r * (R + 1) + R];
+                }
+                globalBirths = total;
+                if ((size_t)sendOff[R] > q.sendBuf.n) CK(q.sendBuf.alloc((size_t)sendOff[R] * 2 + 1024));
+                if ((size_t)nRecv > q.recvBuf.n) CK(q.recvBuf.alloc((size_t)nRecv * 2 + 1024));
+                CK(cudaMemcpyAsync(q.dSendOff.p, sendOff.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, q.stream));
+                CK(cudaMemsetAsync(q.dSendCursor.p, 0, sizeof(int) * R, q.stream));
+                H.on = 1; H.rank = q.shRank; H.nranks = R; H.c0 = q.cellBegin[q.shRank]; H.c1 = q.cellBegin[q.shRank + 1];
+                H.cellBegin = q.dCellBegin.p; H.sendBuf = q.sendBuf.p; H.sendOff = q.dSendOff.p; H.sendCursor = q.dSendCursor.p;
+                H.birthOffset = below;
+                q.lastSent = sendOff[R];
+                q.lastReceived = nRecv;
+            }
             launchScan(p);
             LAUNCH(p, "k_cell_scatter", k_cell_scatter, gridC, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
-                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key);
+                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
+            if (q.sharded) {  // agent migration: packed records straight between the GPUs (NCCL over NVLink)
+                const int R = q.shRanks;
+                int so = 0, ro = 0;
+                NK(g_nccl.GroupStart());
+                for (int r = 0; r < R; r++) {
+                    if (sendCnt[r] > 0) NK(g_nccl.Send(q.sendBuf.p + so, (size_t)sendCnt[r] * sizeof(Migrant), ncclUint8, r, q.comm, q.stream));
+                    if (recvCnt[r] > 0) NK(g_nccl.Recv(q.recvBuf.p + ro, (size_t)recvCnt[r] * sizeof(Migrant), ncclUint8, r, q.comm, q.stream));
+                    so += sendCnt[r];
+                    ro += recvCnt[r];
+                }
+                NK(g_nccl.GroupEnd());
+                if (nRecv > 0) {
+                    LAUNCH(p, "k_place_migrants", k_place_migrants, q.gridFor(nRecv), 256, q.dstats.p, q.recvBuf.p, nRecv, o,
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
+                }
+            }
+            stepEndBirths = globalBirths;
         } else {
             const int ga = q.gridFor(n);
             q.needPair = doPair;
@@ -415,10 +534,11 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key);
         }
-        LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0);
+        LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
         CK(cudaGetLastError());
         if (pullStats(p) != 0) return -1;
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
+            if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
             tiled = false;
             if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
             continue;
@@ -528,6 +648,10 @@ int qhgb_destroy(qhgb_pop *p) {
     }
     p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
     p->oflags.release(); p->dec.release(); p->pkey.release(); p->dstats.release();
+    if (p->comm) g_nccl.CommDestroy(p->comm);
+    if (p->hAllInfo) cudaFreeHost(p->hAllInfo);
+    p->dCellBegin.release(); p->dInfo.release(); p->dAllInfo.release(); p->dSendOff.release(); p->dSendCursor.release();
+    p->sendBuf.release(); p->recvBuf.release();
     for (auto &e : p->userEv) if (e) cudaEventDestroy(e);
     if (p->hstats) cudaFreeHost(p->hstats);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -672,13 +796,14 @@ int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *
         if (life == QHGB_LIFE_STATE_DEAD) continue;
         if (cell[j] < 0 || cell[j] >= p->nCells) return fail("[addAgent] agent %lld has cellindex %d", (long long)id[j], cell[j]);
         if (gender[j] > 1) return fail("[addAgent] agent %lld has gender %d", (long long)id[j], (int)gender[j]);
+        if (id[j] > p->maxID) p->maxID = id[j];
+        if (p->sharded && (cell[j] < p->cellBegin[p->shRank] || cell[j] >= p->cellBegin[p->shRank + 1])) continue;  // another rank's cell
         hc.push_back(cell[j]);
         hi.push_back(id[j]);
         hb.push_back(birth_time[j]);
         hl.push_back(last_birth ? last_birth[j] : 0.0f);
         ha.push_back(age ? age[j] : 0.0f);
         hf.push_back((uint8_t)((gender[j] ? F_MALE : 0) | (((life & ~8u) == QHGB_LIFE_STATE_FERTILE) ? F_FERTILE : 0)));
-        if (id[j] > p->maxID) p->maxID = id[j];
     }
     int64_t m = (int64_t)hc.size();
     if (m == 0) return 0;
@@ -713,6 +838,17 @@ int qhgb_pre_loop(qhgb_pop *p) {
     if (!p->haveCells) return fail("qhgb_pre_loop: no cells (qhgb_set_cells)");
     CK(cudaSetDevice(p->device));
     if (p->capacity == 0 && ensureCapacity(p, 1024) != 0) return -1;
+    if (p->sharded) {  // the id base is the maximum over all ranks
+        long long *d = nullptr;
+        long long h = p->maxID;
+        CK(cudaMalloc(&d, sizeof(long long)));
+        CK(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, p->stream));
+        NK(g_nccl.AllReduce(d, d, 1, ncclInt64, ncclMax, p->comm, p->stream));
+        CK(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        cudaFree(d);
+        p->maxID = h;
+    }
     p->nextID = p->maxID + 1;  // IDGen base, app/Simulator.cpp:94-111
     p->stepsDone = 0;
     if (pushStats(p) != 0) return -1;
@@ -958,6 +1094,48 @@ double qhgb_event_elapsed_ms(qhgb_pop *p, int a, int b) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, p->userEv[a], p->userEv[b]) != cudaSuccess) { fail("cudaEventElapsedTime failed"); return -1; }
     return ms;
+}
+
+int qhgb_comm_get_unique_id(void *out, int nbytes) {
+    if (!out || nbytes < (int)sizeof(ncclUniqueId)) return fail("qhgb_comm_get_unique_id: need a %d byte buffer", (int)sizeof(ncclUniqueId));
+    if (loadNccl() != 0) return -1;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin) {
+    if (!p || !unique_id || !cell_begin) return fail("qhgb_comm_init: NULL argument");
+    if (p->nAgents > 0 || p->preLooped) return fail("qhgb_comm_init: must be called before agents are added");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("qhgb_comm_init: rank %d of %d", rank, nranks);
+    if (cell_begin[0] != 0 || cell_begin[nranks] != p->nCells) return fail("qhgb_comm_init: cell ranges must cover [0, %d)", p->nCells);
+    for (int r = 0; r < nranks; r++) if (cell_begin[r + 1] < cell_begin[r]) return fail("qhgb_comm_init: cell ranges must be ascending");
+    if (loadNccl() != 0) return -1;
+    CK(cudaSetDevice(p->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    NK(g_nccl.CommInitRank(&p->comm, nranks, id, rank));
+    p->shRank = rank;
+    p->shRanks = nranks;
+    p->cellBegin.assign(cell_begin, cell_begin + nranks + 1);
+    CK(p->dCellBegin.alloc(nranks + 1));
+    CK(p->dInfo.alloc(nranks + 1));
+    CK(p->dAllInfo.alloc((size_t)nranks * (nranks + 1)));
+    CK(p->dSendOff.alloc(nranks + 1));
+    CK(p->dSendCursor.alloc(nranks));
+    CK(cudaMallocHost(&p->hAllInfo, sizeof(int) * nranks * (nranks + 1)));
+    CK(cudaMemcpyAsync(p->dCellBegin.p, p->cellBegin.data(), sizeof(int) * (nranks + 1), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->sharded = nranks > 1;
+    return 0;
+}
+
+int qhgb_comm_get_traffic(qhgb_pop *p, int64_t *sent, int64_t *received) {
+    if (!p) return fail("qhgb_comm_get_traffic: NULL population");
+    if (sent) *sent = p->lastSent;
+    if (received) *received = p->lastReceived;
+    return 0;
 }
 
 int64_t qhgb_get_launch_count(qhgb_pop *p) { return p ? p->launches : -1; }

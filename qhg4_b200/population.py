@@ -160,6 +160,18 @@ class GpuPopulation:
         check(self.L.qhgb_atan_death_prob(self.h, len(age), _p(age), _p(p)), "qhgb_atan_death_prob")
         return p
 
+    # ---- several GPUs ------------------------------------------------------------------------
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes, cell_begin):
+        cb = np.ascontiguousarray(cell_begin, np.int32)
+        assert len(cb) == nranks + 1 and len(unique_id) == 128
+        uid = C.create_string_buffer(unique_id, 128)
+        check(self.L.qhgb_comm_init(self.h, int(rank), int(nranks), uid, _p(cb)), "qhgb_comm_init")
+
+    def comm_traffic(self):
+        s, r = C.c_int64(0), C.c_int64(0)
+        check(self.L.qhgb_comm_get_traffic(self.h, C.byref(s), C.byref(r)), "qhgb_comm_get_traffic")
+        return s.value, r.value
+
     # ---- measurement ------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.L.qhgb_get_launch_count(self.h))
