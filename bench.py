@@ -43,6 +43,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_per_step(agents):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, scaled to this run's agents."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            d = json.load(f)["k_cell_decide"]
+        return d["dram_bytes_per_launch"] / d["agents"] * agents
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -55,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -130,49 +140,81 @@ def run_reference(args):
 
 
 def run_ours(args, rank, world):
+    from qhg4_b200 import sharding
     from qhg4_b200.population import GpuPopulation
     device = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
     if world > 1:
-        raise SystemExit("multi-GPU sharding is not wired into bench.py yet")
+        import torch.distributed as dist  # host-side plumbing only (128-byte NCCL id, scalar reductions); the data
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # path is NCCL inside the C library
     t_setup = time.time()
     nbr, alt, pop, par, K = build_world(args.subdiv, args.agents)
     ncell = len(nbr)
-    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int(args.agents * 1.6))
+    begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=ncell), world)
+    lo, hi = np.searchsorted(pop["cell"], [begin[rank], begin[rank + 1]])  # the population is generated binned by cell
+    pop = {k: v[lo:hi] for k, v in pop.items()}
+    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096)
+    if world > 1:
+        sharding.connect(g, begin, rank, world)
     t0 = time.time()
     g.add_agents(pop)
     g.pre_loop()
     g.synchronize()
     upload_s = time.time() - t0
     del pop
+    sampler = ClockSampler(device)  # sampled from the warm-up on: the timed region alone can be shorter than one sample
+    sampler.start()
     t = 0.0
     for _ in range(args.warmup):
         g.step(t); t += 1.0
     g.synchronize()
 
+    def allsum(x):
+        if dist is None:
+            return x
+        import torch
+        v = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v)
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        v = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v)
+
+    def barrier():
+        g.synchronize()
+        if dist is not None:
+            dist.barrier()
+
     # ---- timed region 1: device-resident loop --------------------------------------------------------------
-    sampler = ClockSampler(device)
-    sampler.start()
     g.reset_kernel_times(True)
     launches0 = g.launch_count()
-    agent_steps = 0
-    g.synchronize()
+    agent_steps, migrated = 0, 0
+    barrier()
     g.event_record(0)
     for _ in range(args.steps):
         agent_steps += g.num_agents()
         g.step(t); t += 1.0
+        migrated += g.comm_traffic()[0]
     g.event_record(1)
-    g.synchronize()
-    ms = g.event_elapsed_ms(0, 1)
+    barrier()
+    ms = allmax(g.event_elapsed_ms(0, 1))  # device time of the K steps, max over ranks
     clocks = sampler.stop()
     launches = g.launch_count() - launches0
     ktimes = g.kernel_times()
     g.reset_kernel_times(False)
+    agent_steps = allsum(agent_steps)
+    migrated = allsum(migrated)
     value = agent_steps / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the C ABI with host buffers --------------------------------------
     counts = np.zeros(ncell, np.uint64)
     e2e_steps = 0
-    g.synchronize()
+    barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_steps += g.num_agents()
@@ -183,23 +225,25 @@ def run_ours(args, rank, world):
         st = g.step_stats()          # totals of the step (D2H inside finalize_step)
         g.counts(counts)             # per-cell counts into host memory, as PopBase::getNumAgents exposes them
         t += 1.0
-    g.synchronize()
-    e2e_sec = time.perf_counter() - w0
-    e2e_val = e2e_steps / e2e_sec
+    barrier()
+    e2e_sec = allmax(time.perf_counter() - w0)
+    e2e_val = allsum(e2e_steps) / e2e_sec
     t1 = time.time()
     final = g.agents()
     download_s = time.time() - t1
-    n_final = len(final["id"])
+    n_final = int(allsum(len(final["id"])))
     del final
 
     # ---- roofline: whole-step algorithmic bytes over the summed kernel time ------------------------------------
     peak, peak_src = measured_peak_gbs()
-    kern_ms = sum(v[0] for v in ktimes.values())
+    kern_ms = allmax(sum(v[0] for v in ktimes.values()))  # slowest rank
+    peak *= world
     alg_bytes = ALG_BYTES_PER_AGENT * agent_steps + ALG_BYTES_PER_CELL * ncell * args.steps
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     top = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
     roof = {"bound": "hbm", "kernel": "whole step (all kernels of one doStep, summed device time)", "achieved": achieved,
-            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_step(agent_steps / args.steps),
+            "peak_source": peak_src,
             "alg_bytes_per_step": alg_bytes / args.steps, "dominant_kernel": top,
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}}
 
@@ -211,13 +255,17 @@ def run_ours(args, rank, world):
                                    if args.subdiv == 255 else f"tut_EnvironAltPop action set, {args.agents} agents on eq:{args.subdiv}",
                        "cells": ncell, "agents_start": args.agents, "agents_end": n_final, "verhulst_K": K,
                        "l2": "agent state per step (>2 GB at 1e8 agents) exceeds the 126 MB L2; no explicit flush",
-                       "upload_s": round(upload_s, 2), "download_s": round(download_s, 2), "setup_s": round(t0 - t_setup, 2)},
+                       "upload_s": round(upload_s, 2), "download_s": round(download_s, 2), "setup_s": round(t0 - t_setup, 2),
+                       "parallelism": f"cell-range shards x{world}, NCCL migration" if world > 1 else "single GPU",
+                       "migrations_per_step": migrated / args.steps},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 4 * ncell + 48,
                     "what": "initializeStep + doActions per level + finalizeStep through the C ABI, then totals and the per-cell count "
                             "array copied to host memory every step"},
             "roofline": roof}
     g.close()
+    if dist is not None:
+        dist.barrier()
     return line
 
 

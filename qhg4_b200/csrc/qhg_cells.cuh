@@ -382,15 +382,17 @@ __device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
     return q;
 }
 
-// arrivals this rank sends to every other rank = sum of its arrive[] over the other rank's cells; block q handles rank q
+// arrivals this rank sends to every other rank = sum of its arrive[] over the other rank's cells;
+// SHARD_SPLIT blocks per destination rank, info[] zeroed before
+constexpr int SHARD_SPLIT = 32;
 __global__ void __launch_bounds__(256)
 k_shard_counts(const int *__restrict__ arrive, const int *__restrict__ cellBegin, int rank, int nranks,
                const DevStats *__restrict__ st, int *__restrict__ info) {
     __shared__ int sa[8];
-    const int q = blockIdx.x;
+    const int q = blockIdx.x / SHARD_SPLIT, part = blockIdx.x % SHARD_SPLIT;
     int sum = 0;
     if (q != rank) {
-        for (int c = cellBegin[q] + threadIdx.x; c < cellBegin[q + 1]; c += 256) sum += arrive[c];
+        for (int c = cellBegin[q] + part * 256 + threadIdx.x; c < cellBegin[q + 1]; c += 256 * SHARD_SPLIT) sum += arrive[c];
     }
     sum = warp_sum(sum);
     if ((threadIdx.x & 31) == 0) sa[threadIdx.x >> 5] = sum;
@@ -398,8 +400,8 @@ k_shard_counts(const int *__restrict__ arrive, const int *__restrict__ cellBegin
     if (threadIdx.x == 0) {
         int t = 0;
         for (int w = 0; w < 8; w++) t += sa[w];
-        info[q] = t;
-        if (q == 0) info[nranks] = st->nBirths;
+        if (t) atomicAdd(&info[q], t);
+        if (blockIdx.x == 0) info[nranks] = st->nBirths;
     }
 }
 

@@ -476,7 +476,8 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 // (1) what this rank sends to every other rank, (2) arrivals per cell summed over all ranks,
                 // (3) everybody learns every count (and the births per rank: newborn ids are global ranks)
                 const int R = q.shRanks;
-                LAUNCH(p, "k_shard_counts", k_shard_counts, R, 256, q.arrive.p, q.dCellBegin.p, q.shRank, R, q.dstats.p, q.dInfo.p);
+                CK(cudaMemsetAsync(q.dInfo.p, 0, sizeof(int) * (R + 1), q.stream));
+                LAUNCH(p, "k_shard_counts", k_shard_counts, R * SHARD_SPLIT, 256, q.arrive.p, q.dCellBegin.p, q.shRank, R, q.dstats.p, q.dInfo.p);
                 NK(g_nccl.AllReduce(q.arrive.p, q.arrive.p, (size_t)q.nCells, ncclInt32, ncclSum, q.comm, q.stream));
                 NK(g_nccl.AllGather(q.dInfo.p, q.dAllInfo.p, (size_t)(R + 1), ncclInt32, q.comm, q.stream));
                 CK(cudaMemcpyAsync(q.hAllInfo, q.dAllInfo.p, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
