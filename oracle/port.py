@@ -57,6 +57,15 @@ def lib():
         L.qor_get_birth_death_probs.argtypes = [vp, vp, vp]
         L.qor_atan_death_prob.argtypes = [vp, i32, vp, vp]
         L.qor_get_step_stats.argtypes = [vp, vp, vp, vp]
+        L.qor_get_pending_births.restype = i64
+        L.qor_get_pending_births.argtypes = [vp]
+        L.qor_set_birth_id_offset.argtypes = [vp, i64, i64]
+        L.qor_extract_foreign.restype = i64
+        L.qor_extract_foreign.argtypes = [vp, i32, i32, i64] + [vp] * 7
+        L.qor_recount.argtypes = [vp]
+        L.qor_get_max_id.restype = i64
+        L.qor_get_max_id.argtypes = [vp]
+        L.qor_set_max_id.argtypes = [vp, i64]
         L.qor_philox4x32_10.argtypes = [vp, vp, vp]
         L.qor_well_sequence.argtypes = [vp, i32, vp]
         L.qor_polyline_eval.argtypes = [C.c_char_p, i32, vp, vp, i32]
@@ -190,6 +199,31 @@ class OraclePop:
         b, d, m = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         lib().qor_get_step_stats(self.h, C.byref(b), C.byref(d), C.byref(m))
         return b.value, d.value, m.value
+
+    # ---- sharded runs ---------------------------------------------------------------------
+    def pending_births(self):
+        return int(lib().qor_get_pending_births(self.h))
+
+    def set_birth_id_offset(self, offset, total):
+        lib().qor_set_birth_id_offset(self.h, int(offset), int(total))
+
+    def extract_foreign(self, c0, c1):
+        cap = self.num_agents()
+        out = dict(cell=np.zeros(cap, np.int32), id=np.zeros(cap, np.int64), birth=np.zeros(cap, np.float32),
+                   gender=np.zeros(cap, np.uint8), age=np.zeros(cap, np.float32), last_birth=np.zeros(cap, np.float32),
+                   life=np.zeros(cap, np.uint32))
+        k = lib().qor_extract_foreign(self.h, int(c0), int(c1), cap, *[_p(out[f]) for f in
+                                                                          ("cell", "id", "birth", "gender", "age", "last_birth", "life")])
+        return {f: v[:k] for f, v in out.items()}
+
+    def recount(self):
+        lib().qor_recount(self.h)
+
+    def max_id(self):
+        return int(lib().qor_get_max_id(self.h))
+
+    def set_max_id(self, v):
+        lib().qor_set_max_id(self.h, int(v))
 
     def close(self):
         if self.h:

@@ -206,6 +206,7 @@ struct qor_pop {
     std::vector<int> prevDead, deathList, birthList, moveList;  // core/SPopulation.cpp:160-181 queues (one thread)
     int64_t numUsed = 0;       // LBController::m_iNumUsed
     int64_t maxID = 0, nextID = 0;
+    int64_t birthIdOffset = 0, birthIdTotal = -1;  // sharded runs: births of the lower ranks / of all ranks this step
     std::vector<uint64_t> counts;
     std::vector<double> B, D, W;
     float curTime = -1;
@@ -495,8 +496,9 @@ struct qor_pop {
                 if (cx != cy) return cx < cy;
                 return slots[birthList[3 * x + 1]].id < slots[birthList[3 * y + 1]].id;
             });
-            for (size_t r = 0; r < nBirths; r++) babyId[ord[r]] = nextID + (int64_t)r;
-            nextID += (int64_t)nBirths;
+            for (size_t r = 0; r < nBirths; r++) babyId[ord[r]] = nextID + birthIdOffset + (int64_t)r;
+            nextID += (birthIdTotal >= 0) ? birthIdTotal : (int64_t)nBirths;
+            birthIdOffset = 0; birthIdTotal = -1;
         }
         size_t nReuse = std::min(prevDead.size(), nBirths);
         auto born = [&](int slot, size_t k) {
@@ -752,6 +754,40 @@ int qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out) {
     }
     return 0;
 }
+
+// ---- sharded runs (the protocol of the CUDA path's multi-GPU mode, counter mode only) --------------------------
+int64_t qor_get_pending_births(qor_pop *p) { return (int64_t)(p->birthList.size() / 3); }
+
+int qor_set_birth_id_offset(qor_pop *p, int64_t offset, int64_t total) {
+    p->birthIdOffset = offset;
+    p->birthIdTotal = total;
+    return 0;
+}
+
+// remove the live agents whose cell lies outside [c0, c1) and hand their records out
+int64_t qor_extract_foreign(qor_pop *p, int c0, int c1, int64_t cap, int32_t *cell, int64_t *id, float *birth, uint8_t *gender,
+                            float *age, float *last_birth, uint32_t *life) {
+    int64_t k = 0;
+    for (int i = 0; i < p->hi(); i++) {
+        if (!p->active[i] || p->slots[i].life == LIFE_DEAD) continue;
+        Agent &a = p->slots[i];
+        if (a.cell >= c0 && a.cell < c1) continue;
+        if (k < cap) {
+            cell[k] = a.cell; id[k] = a.id; birth[k] = a.birth; gender[k] = a.gender; age[k] = a.age;
+            last_birth[k] = a.lastBirth; life[k] = a.life;
+            a.life = LIFE_DEAD;
+            p->freeSlot(i);
+        }
+        k++;
+    }
+    p->updateNumAgentsPerCell();
+    return k;
+}
+
+int qor_recount(qor_pop *p) { p->updateNumAgentsPerCell(); return 0; }
+
+int64_t qor_get_max_id(qor_pop *p) { return p->maxID; }
+int qor_set_max_id(qor_pop *p, int64_t v) { p->maxID = v; return 0; }
 
 int qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves) {
     if (births) *births = p->stepBirths;

@@ -55,6 +55,15 @@ int      qor_get_birth_death_probs(qor_pop *p, double *b, double *d);
 int      qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out);
 int      qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves);
 
+/* sharded runs: the protocol of the CUDA path's multi-GPU mode (counter mode) */
+int64_t  qor_get_pending_births(qor_pop *p);
+int      qor_set_birth_id_offset(qor_pop *p, int64_t offset, int64_t total);
+int64_t  qor_extract_foreign(qor_pop *p, int c0, int c1, int64_t cap, int32_t *cell, int64_t *id, float *birth, uint8_t *gender,
+                             float *age, float *last_birth, uint32_t *life);
+int      qor_recount(qor_pop *p);
+int64_t  qor_get_max_id(qor_pop *p);
+int      qor_set_max_id(qor_pop *p, int64_t v);
+
 /* stand-alone pieces */
 void     qor_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int      qor_well_sequence(const uint32_t *state16, int n, uint32_t *out);

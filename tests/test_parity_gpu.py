@@ -234,3 +234,17 @@ def test_statistical_equivalence_vs_reference():
     p_age = stats.ks_2samp(np.concatenate(age_g)[::7], np.concatenate(age_r)[::7]).pvalue
     p_occ = stats.ks_2samp(np.concatenate(occ_g)[::3], np.concatenate(occ_r)[::3]).pvalue
     assert p_tot > 0.01 and p_age > 0.01 and p_occ > 0.01, (p_tot, p_age, p_occ)
+
+
+def test_two_gpu_shards_equal_unsharded_oracle():
+    """cell-range sharding + NCCL migration on 2 GPUs: bit-identical to the unsharded oracle (tests/mgpu_check.py)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tests/mgpu_check.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,115 @@
+"""The multi-GPU protocol on CPU: world_size-2 gloo processes, each running the oracle (counter mode) on its cell
+range and exchanging arrivals / births / migrants exactly like the CUDA path does over NCCL.
+The sharded run must equal the unsharded one bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = ("cell", "id", "birth", "gender", "age", "last_birth", "life")
+
+
+def test_partition_cells_balances_agents():
+    from qhg4_b200.sharding import owner_of, partition_cells
+    rng = np.random.default_rng(0)
+    cnt = rng.poisson(20, 5000) * (rng.random(5000) > 0.3)
+    for n in (1, 2, 4, 8):
+        b = partition_cells(cnt, n)
+        assert b[0] == 0 and b[-1] == 5000 and np.all(np.diff(b) >= 0) and len(b) == n + 1
+        per = [cnt[b[r]:b[r + 1]].sum() for r in range(n)]
+        assert max(per) - min(per) <= 2 * cnt.max() + 1, per
+        cells = rng.integers(0, 5000, 100)
+        own = owner_of(cells, b)
+        assert np.all((cells >= b[own]) & (cells < b[own + 1]))
+    assert list(partition_cells(np.zeros(10), 2)) == [0, 5, 10]
+
+
+def _worker(rank, world, port_no, nsteps, out_q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import port
+    from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_population
+    from qhg4_b200.params import seed_state, tut_environ_alt
+    from qhg4_b200.sharding import owner_of, partition_cells
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=2)
+    pop = synthetic_population(20000, alt, seed=3, fertile=True)
+    par, st = tut_environ_alt(40.0), seed_state(5)
+    begin = partition_cells(np.bincount(pop["cell"], minlength=len(nbr)), world)
+    c0, c1 = int(begin[rank]), int(begin[rank + 1])
+    mine = (pop["cell"] >= c0) & (pop["cell"] < c1)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st)
+    o.add_agents({k: v[mine] for k, v in pop.items()})
+    mx = torch.tensor([int(pop["id"].max())])          # global id base (the CUDA path all-reduces the local maxima)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    o.set_max_id(int(mx))
+    o.start()
+    levels = sorted(set(par.prios.values()))
+    for k in range(nsteps):
+        t = float(k)
+        o.initialize_step(t)
+        for lv in levels:
+            o.do_actions(lv, t)
+        births = [None] * world                          # births per rank: newborn ids are global ranks
+        dist.all_gather_object(births, o.pending_births())
+        o.set_birth_id_offset(sum(births[:rank]), sum(births))
+        o.finalize_step()
+        gone = o.extract_foreign(c0, c1)                 # agents that moved into another rank's cells
+        dest = owner_of(gone["cell"], begin)
+        outbox = [{f: v[dest == r] for f, v in gone.items()} for r in range(world)]
+        inbox = [None] * world
+        dist.all_to_all_object_list(inbox, outbox) if hasattr(dist, "all_to_all_object_list") else None
+        if inbox[0] is None:                             # portable fallback: gather everything everywhere
+            allbox = [None] * world
+            dist.all_gather_object(allbox, outbox)
+            inbox = [allbox[r][rank] for r in range(world)]
+        for r in range(world):
+            if r != rank and len(inbox[r]["id"]):
+                o.add_agents(inbox[r])
+        o.recount()
+    a = o.agents()
+    res = [None] * world
+    dist.gather_object({f: a[f] for f in FIELDS} | {"counts": o.counts()}, res if rank == 0 else None, dst=0)
+    if rank == 0:
+        out_q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_oracle_equals_unsharded():
+    from oracle import port
+    from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_population
+    from qhg4_b200.params import seed_state, tut_environ_alt
+    nsteps, world = 10, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=2)
+    pop = synthetic_population(20000, alt, seed=3, fertile=True)
+    o = port.OraclePop(tut_environ_alt(40.0), nbr, alt, mode=port.MODE_COUNTER, state16=seed_state(5))
+    o.add_agents(pop)
+    o.start()
+    for k in range(nsteps):
+        o.step(float(k))
+    ref = o.agents()
+    got = {f: np.concatenate([r[f] for r in res]) for f in FIELDS}
+    assert len(got["id"]) == o.num_agents()
+    og, orf = np.argsort(got["id"]), np.argsort(ref["id"])
+    for f in FIELDS:
+        assert np.array_equal(got[f][og], ref[f][orf]), f
+    assert np.array_equal(sum(r["counts"] for r in res), o.counts())
