@@ -32,6 +32,7 @@ constexpr int MAXF = 512;        // most fertile females of one cell that can be
 constexpr int QCAP = 64;         // work-queue entries per warp
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
 constexpr int DU = 2;            // agents per lane and chunk in the decide pass
+constexpr int SU = 2;            // the same in the scatter pass
 
 // decision byte handed from pass 1 to pass 2: bit0 male, bit1 fertile (the agent's new flags), bit2 gave birth,
 // bits 3-5 move code: 0 stays, 1..6 neighbour slot + 1, 7 dead
@@ -412,6 +413,18 @@ __global__ void k_shard_mask(int nCells, int c0, int c1, int *__restrict__ arriv
     }
 }
 
+// the per-agent cell index is implied by cellStart on the fast path; this writes it out when somebody needs it
+// (generic path, records handed back to the host)
+__global__ void __launch_bounds__(256)
+k_fill_cells(int nCells, const int *__restrict__ cellStart, int *__restrict__ cell) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
+    for (int c = gw; c < nCells; c += nW) {
+        const int s = cellStart[c], e = cellStart[c + 1];
+        for (int i = s + lane; i < e; i += 32) cell[i] = c;
+    }
+}
+
 __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant *__restrict__ in, int n, AgentArrays o,
                                  const int *__restrict__ newStart, const int *__restrict__ stay, int *__restrict__ cursor,
                                  int storeAge) {
@@ -422,7 +435,6 @@ __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant 
         o.id[pos] = m.id;
         o.birth[pos] = m.birth;
         o.lastBirth[pos] = m.lastBirth;
-        o.cell[pos] = m.cell;
         o.flags[pos] = (uint8_t)m.flags;
         if (storeAge) o.age[pos] = m.age;
     }
@@ -447,56 +459,66 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
         if (n == 0) continue;
         const int ns = newStart[c];
         int stayBase = 0, nMothers = 0;
-        // software pipeline: the next chunk's loads are in flight while this chunk is written
-        uint8_t vN = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
-        int64_t idN = 0; float birthN = 0, lastN = 0, ageN = 0;
-        if (lane < n) {
-            vN = dec[s + lane]; idN = a.id[s + lane]; birthN = a.birth[s + lane]; lastN = a.lastBirth[s + lane];
-            if (storeAge) ageN = a.age[s + lane];
-        }
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            const uint8_t v = vN;
-            const int64_t id = idN; const float birth = birthN, lastBirth = lastN, age = ageN;
-            vN = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
-            if (j + 32 < n) {
-                const int g2 = s + j + 32;
-                vN = dec[g2]; idN = a.id[g2]; birthN = a.birth[g2]; lastN = a.lastBirth[g2];
-                if (storeAge) ageN = a.age[g2];
+        // software pipeline: the next chunk's loads are in flight while this chunk is written; SU chunks of 32 per round
+        uint8_t vN[SU]; int64_t idN[SU]; float birthN[SU], lastN[SU], ageN[SU];
+#pragma unroll
+        for (int u = 0; u < SU; u++) {
+            const int j = u * 32 + lane;
+            vN[u] = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT); idN[u] = 0; birthN[u] = 0; lastN[u] = 0; ageN[u] = 0;
+            if (j < n) {
+                vN[u] = dec[s + j]; idN[u] = a.id[s + j]; birthN[u] = a.birth[s + j]; lastN[u] = a.lastBirth[s + j];
+                if (storeAge) ageN[u] = a.age[s + j];
             }
-            const int code = v >> DEC_MOVE_SHIFT;
-            const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
-            const unsigned ms = __ballot_sync(FULL, alive && code == 0);
-            const unsigned mb = __ballot_sync(FULL, born);
-            if (alive) {
-                int d = c, pos;
-                if (code == 0) {
-                    pos = ns + stayBase + __popc(ms & lt);
-                } else {
-                    d = nbr[(size_t)c * MAXN + code - 1];
-                    if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
-                        const int qo = shard_owner(H, d);
-                        Migrant m;
-                        m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
-                        m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
-                        H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
-                        pos = -1;
+        }
+        for (int j0 = 0; j0 < n; j0 += 32 * SU) {
+            uint8_t vv[SU]; int64_t idv[SU]; float birthv[SU], lastv[SU], agev[SU];
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                vv[u] = vN[u]; idv[u] = idN[u]; birthv[u] = birthN[u]; lastv[u] = lastN[u]; agev[u] = ageN[u];
+                vN[u] = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
+                const int j2 = j0 + 32 * SU + u * 32 + lane;
+                if (j2 < n) {
+                    vN[u] = dec[s + j2]; idN[u] = a.id[s + j2]; birthN[u] = a.birth[s + j2]; lastN[u] = a.lastBirth[s + j2];
+                    if (storeAge) ageN[u] = a.age[s + j2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const uint8_t v = vv[u];
+                const int64_t id = idv[u];
+                const int code = v >> DEC_MOVE_SHIFT;
+                const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
+                const unsigned ms = __ballot_sync(FULL, alive && code == 0);
+                const unsigned mb = __ballot_sync(FULL, born);
+                if (alive) {
+                    int pos;
+                    if (code == 0) {
+                        pos = ns + stayBase + __popc(ms & lt);
                     } else {
-                        pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
+                        const int d = nbr[(size_t)c * MAXN + code - 1];
+                        if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
+                            const int qo = shard_owner(H, d);
+                            Migrant m;
+                            m.id = id; m.birth = birthv[u]; m.lastBirth = lastv[u]; m.age = agev[u]; m.cell = d;
+                            m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
+                            H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                            pos = -1;
+                        } else {
+                            pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
+                        }
+                    }
+                    if (pos >= 0) {
+                        o.id[pos] = id;
+                        o.birth[pos] = birthv[u];
+                        o.lastBirth[pos] = lastv[u];
+                        o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
+                        if (storeAge) o.age[pos] = agev[u];
                     }
                 }
-                if (pos >= 0) {
-                o.id[pos] = id;
-                o.birth[pos] = birth;
-                o.lastBirth[pos] = lastBirth;
-                o.cell[pos] = d;
-                o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
-                if (storeAge) o.age[pos] = age;
-                }
+                if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
+                stayBase += __popc(ms);
+                nMothers += __popc(mb);
             }
-            if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
-            stayBase += __popc(ms);
-            nMothers += __popc(mb);
         }
         __syncwarp();
         // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
@@ -511,7 +533,6 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
             o.id[pos] = cid;
             o.birth[pos] = t;
             o.lastBirth[pos] = 0.0f;
-            o.cell[pos] = c;
             o.flags[pos] = (uint8_t)(gnd ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
             if (storeAge) o.age[pos] = 0.0f;
         }

@@ -172,6 +172,7 @@ struct qhgb_pop {
     // step state
     bool preLooped = false, inStep = false, pairingValid = false, needPair = false, doVerhulst = false;
     bool forceGeneric = false;
+    bool cellValid = true;  // does cell[cur] hold the per-agent cell index? (the fast path leaves it implied by cellStart)
     int64_t genericSteps = 0, tiledSteps = 0;
     bool evalFirst = true, evalNeedUpdate = false;
     bool evaluatorObserves = false;  // does the population class addObserver() its evaluator?
@@ -420,10 +421,21 @@ int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
     return 0;
 }
 
+int ensureCells(qhgb_pop *p) {
+    if (p->cellValid) return 0;
+    if (p->nAgents > 0) {
+        LAUNCH(p, "k_fill_cells", k_fill_cells, p->gridFor((int64_t)p->nCells * 32), 256, p->nCells, p->cellStart[p->cur].p, p->cell[p->cur].p);
+        CK(cudaGetLastError());
+    }
+    p->cellValid = true;
+    return 0;
+}
+
 // stand-alone pairing (generic path, and whenever the host asks for the mates between initializeStep and finalizeStep)
 int ensurePairing(qhgb_pop *p) {
     qhgb_pop &q = *p;
     if (q.pairingValid) return 0;
+    if (ensureCells(p) != 0) return -1;
     const int ga = q.gridFor(q.nAgents);
     AgentArrays a = q.arrays(q.cur);
     if (q.needPair) {
@@ -506,7 +518,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
-            LAUNCH(p, "k_cell_scatter", k_cell_scatter, gridC, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
+            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * 16, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
             if (q.sharded) {  // agent migration: packed records straight between the GPUs (NCCL over NVLink)
                 const int R = q.shRanks;
@@ -527,6 +539,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             stepEndBirths = globalBirths;
         } else {
             const int ga = q.gridFor(n);
+            if (binned && ensureCells(p) != 0) return -1;
             q.needPair = doPair;
             if (ensurePairing(p) != 0) return -1;
             LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, cellEnv(p), q.arrive.p, q.birthCount.p,
@@ -545,6 +558,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             continue;
         }
         (tiled ? q.tiledSteps : q.genericSteps)++;
+        q.cellValid = !tiled;
         break;
     }
     if (q.hstats->overflow) return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
@@ -808,7 +822,7 @@ int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *
     }
     int64_t m = (int64_t)hc.size();
     if (m == 0) return 0;
-    if (materializeAges(p) != 0) return -1;
+    if (materializeAges(p) != 0 || ensureCells(p) != 0) return -1;
     int64_t total = p->nAgents + m;
     if (ensureCapacity(p, total + total / 2 + 1024) != 0) return -1;
     int b = p->cur;
@@ -1005,6 +1019,7 @@ int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_i
     if (cudaSetDevice(p->device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1; }
     int64_t n = p->nAgents, m = std::min(n, cap);
     if (m <= 0) return n;
+    if ((cell || cell_id) && ensureCells(p) != 0) return -1;
     int b = p->cur;
     cudaStream_t s = p->stream;
     std::vector<int32_t> hc;
