@@ -31,6 +31,7 @@ constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles;
 constexpr int MAXF = 512;        // most fertile females of one cell that can be ranked in shared memory
 constexpr int QCAP = 64;         // work-queue entries per warp
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
+constexpr int CELL_BATCH = 8;    // consecutive cells a warp takes per grab of the work counter
 constexpr int DU = 2;            // agents per lane and chunk in the decide pass
 constexpr int SU = 2;            // the same in the scatter pass
 
@@ -53,7 +54,7 @@ struct WarpSmem {
     uint16_t candQ[MAXF];      // birth candidates among the fertile females (index into keys / ffJ)
     int outC[8];               // movers of the cell per direction
     int nbrC[8];               // the cell's neighbours (6 used)
-    uint8_t dec[WCAP];         // provisional decision of every agent of the cell
+    alignas(4) uint8_t dec[WCAP + 4];  // provisional decision of every agent of the cell, shifted by (cell start & 3)
 };
 
 // the action program the fast path is specialised for at compile time: the tutorial populations' order
@@ -93,14 +94,12 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     __shared__ WarpSmem smem[CW];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmem &S = smem[wid];
-    uint8_t *const sdec = S.dec;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
     const unsigned long long prog = SPEC ? PROG_TUT5 : P.prog;
     const int nOps = SPEC ? 5 : P.nOps;
     const ProgramInfo I = program_info(prog, nOps);
-    const int gw = blockIdx.x * CW + wid, nW = gridDim.x * CW;
     int nDead = 0, nMove = 0, nBorn = 0;  // warp-uniform tallies
     // loop invariants in registers
     const float tNow = P.t, fertMin = P.fertMinAge, fertMax = P.fertMaxAge, fertInter = P.fertInterbirth;
@@ -110,13 +109,23 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     const RoundKeys RK = round_keys(key);
     const bool storeAge = P.storeAge != 0;
 
-    for (int c = gw; c < nCells; c += nW) {
+    // cells are handed out dynamically in batches of CELL_BATCH consecutive cells (sea cells are empty, land cells are
+    // not: a static split leaves a long tail)
+    for (;;) {
+    int cBase = 0;
+    if (lane == 0) cBase = atomicAdd(&st->workDecide, CELL_BATCH);
+    cBase = __shfl_sync(FULL, cBase, 0);
+    if (cBase >= nCells) break;
+    for (int c = cBase; c < min(cBase + CELL_BATCH, nCells); c++) {
         const int s = cellStart[c], n = cellStart[c + 1] - s;
         if (n == 0) continue;
         if (n > WCAP) {
             if (lane == 0) atomicExch(&st->oversize, 1);
             continue;
         }
+        // the cell's bytes sit at dec[gOff + j]: shared-memory word k then is the aligned global word of dec[] it is stored to
+        const int gOff = s & 3;
+        uint8_t *const sdec = S.dec + gOff;
         if (lane < 8) {
             S.outC[lane] = 0;
             S.row[lane] = (lane < WSTRIDE) ? E.W[(size_t)c * WSTRIDE + lane] : 0.0;
@@ -305,25 +314,44 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         }
 
         // ---- commit: final decision bytes, per-cell counts ---------------------------------------------------------
-        // every lane takes 4 consecutive agents per round and tallies in registers; one warp reduction per cell
+        // four agents (one 32-bit word of decision bytes) per lane and round, all byte lanes in parallel; tallies in
+        // registers, one warp reduction per cell
         int stayL = 0, bornL = 0, moveL = 0, outL = 0;
-        for (int j0 = 4 * lane; j0 < n; j0 += 128) {
+        {
+            const uint32_t ONES = 0x01010101u;
+            const uint32_t matesM = mates ? ONES : 0u, bornVoid = I.bornAfterAtan ? ONES : 0u, moveVoid = I.moveAfterAtan ? ONES : 0u;
+            const int nWords = (gOff + n + 3) >> 2;
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(S.dec);
+            uint32_t *gw32 = reinterpret_cast<uint32_t *>(dec + (s - gOff));
+            for (int k = lane; k < nWords; k += 32) {
+                const uint32_t w = sw[k];
+                uint32_t vm = ONES;  // valid bytes of this word
+                if (4 * k < gOff || 4 * k + 4 > gOff + n) {
+                    vm = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int j = j0 + q;
-                if (j < n) {
-                    const uint8_t v = sdec[j];
-                    const bool atanDies = (v & T_ATANDIES) != 0;
-                    const bool dead = atanDies || (v & T_DEADNOW);
-                    const int code = (v >> DEC_MOVE_SHIFT) & 7;
-                    const bool born = mates && (v & F_BORN) && !(atanDies && I.bornAfterAtan);
-                    dec[s + j] = (uint8_t)((v & (F_MALE | F_FERTILE)) | (born ? F_BORN : 0) | ((dead ? DEC_DEAD : code) << DEC_MOVE_SHIFT));
-                    bornL += born ? 1 : 0;
-                    moveL += (code != 0 && !(atanDies && I.moveAfterAtan)) ? 1 : 0;  // registered moves (core/SPopulation.cpp:1067)
-                    if (!dead) {
-                        if (code == 0) stayL++;
-                        else { outL++; atomicAdd(&S.outC[code - 1], 1); }
-                    }
+                    for (int b = 0; b < 4; b++) if (4 * k + b >= gOff && 4 * k + b < gOff + n) vm |= 1u << (8 * b);
+                }
+                const uint32_t at = (w >> 6) & ONES, dn = (w >> 7) & ONES, dead = at | dn;
+                const uint32_t code = (w >> DEC_MOVE_SHIFT) & 0x07070707u;
+                const uint32_t nz = ((code + 0x07070707u) >> 3) & ONES;       // move code != 0
+                const uint32_t born = (w >> 2) & matesM & ~(at & bornVoid) & ONES;
+                const uint32_t alive = ~dead & vm;
+                const uint32_t out = alive & nz;
+                const uint32_t d7 = (dead << 3) - dead;                        // 7 in every dead byte
+                const uint32_t fin = (w & 0x03030303u) | (born << 2) | ((code | d7) << DEC_MOVE_SHIFT);
+                stayL += __popc(alive & ~nz);
+                bornL += __popc(born & vm);
+                moveL += __popc(nz & ~(at & moveVoid) & vm);                   // registered moves (core/SPopulation.cpp:1067)
+                outL += __popc(out);
+                if (vm == ONES) {
+                    gw32[k] = fin;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) if (vm & (1u << (8 * b))) dec[s - gOff + 4 * k + b] = (uint8_t)(fin >> (8 * b));
+                }
+                if (out) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) if (out & (1u << (8 * b))) atomicAdd(&S.outC[((code >> (8 * b)) & 7) - 1], 1);
                 }
             }
         }
@@ -341,6 +369,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         }
         __syncwarp();
     }
+    }
     if (lane == 0) {
         if (nDead) atomicAdd(&st->nDeaths, nDead);
         if (nMove) atomicAdd(&st->nMoves, nMove);
@@ -353,6 +382,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
 // (makeOffspring / createAgentAtIndex :823-847,880-918; makePopSpecificOffspring populations/tut_EnvironAltPop.cpp:141-149)
 struct WarpSmemB {
     int64_t motherId[MAXMOTHERS];
+    uint16_t mvJ[QCAP];  // movers of the cell, worked off together (their atomics and gathers overlap)
 };
 
 // ---- multi-GPU: the grid is sharded by contiguous cell ranges, one range per rank ------------------
@@ -441,7 +471,7 @@ __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant 
 }
 
 __global__ void __launch_bounds__(CW * 32)
-k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCells, const int *__restrict__ cellStart,
+k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCells, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, int *__restrict__ cursor,
                const int *__restrict__ birthBase, float t, int storeAge, RngKey key, ShardArgs H) {
@@ -453,12 +483,44 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
     const long long nextID = st->nextID;
-    const int gw = blockIdx.x * CW + wid, nW = gridDim.x * CW;
-    for (int c = gw; c < nCells; c += nW) {
+    for (;;) {
+    int cBase = 0;
+    if (lane == 0) cBase = atomicAdd(&st->workScatter, CELL_BATCH);
+    cBase = __shfl_sync(FULL, cBase, 0);
+    if (cBase >= nCells) break;
+    for (int c = cBase; c < min(cBase + CELL_BATCH, nCells); c++) {
         const int s = cellStart[c], n = cellStart[c + 1] - s;
         if (n == 0) continue;
         const int ns = newStart[c];
         int stayBase = 0, nMothers = 0;
+        int nmv = 0;
+        auto flush_movers = [&]() {
+            __syncwarp();
+            for (int e = lane; e < nmv; e += 32) {
+                const int g = s + S.mvJ[e];
+                const uint8_t v = dec[g];
+                const int d = nbr[(size_t)c * MAXN + (v >> DEC_MOVE_SHIFT) - 1];
+                const int64_t id = a.id[g];
+                const float birth = a.birth[g], lastBirth = a.lastBirth[g];
+                const float age = storeAge ? a.age[g] : 0.0f;
+                if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
+                    const int qo = shard_owner(H, d);
+                    Migrant m;
+                    m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
+                    m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
+                    H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                } else {
+                    const int pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
+                    o.id[pos] = id;
+                    o.birth[pos] = birth;
+                    o.lastBirth[pos] = lastBirth;
+                    o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
+                    if (storeAge) o.age[pos] = age;
+                }
+            }
+            nmv = 0;
+            __syncwarp();
+        };
         // software pipeline: the next chunk's loads are in flight while this chunk is written; SU chunks of 32 per round
         uint8_t vN[SU]; int64_t idN[SU]; float birthN[SU], lastN[SU], ageN[SU];
 #pragma unroll
@@ -490,37 +552,25 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
                 const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
                 const unsigned ms = __ballot_sync(FULL, alive && code == 0);
                 const unsigned mb = __ballot_sync(FULL, born);
-                if (alive) {
-                    int pos;
-                    if (code == 0) {
-                        pos = ns + stayBase + __popc(ms & lt);
-                    } else {
-                        const int d = nbr[(size_t)c * MAXN + code - 1];
-                        if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
-                            const int qo = shard_owner(H, d);
-                            Migrant m;
-                            m.id = id; m.birth = birthv[u]; m.lastBirth = lastv[u]; m.age = agev[u]; m.cell = d;
-                            m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
-                            H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
-                            pos = -1;
-                        } else {
-                            pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
-                        }
-                    }
-                    if (pos >= 0) {
-                        o.id[pos] = id;
-                        o.birth[pos] = birthv[u];
-                        o.lastBirth[pos] = lastv[u];
-                        o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
-                        if (storeAge) o.age[pos] = agev[u];
-                    }
+                const bool mover = alive && code != 0;
+                const unsigned mm = __ballot_sync(FULL, mover);
+                if (nmv + __popc(mm) > QCAP) flush_movers();
+                if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)(j0 + u * 32 + lane);
+                nmv += __popc(mm);
+                if (alive && code == 0) {
+                    const int pos = ns + stayBase + __popc(ms & lt);
+                    o.id[pos] = id;
+                    o.birth[pos] = birthv[u];
+                    o.lastBirth[pos] = lastv[u];
+                    o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
+                    if (storeAge) o.age[pos] = agev[u];
                 }
                 if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
                 stayBase += __popc(ms);
                 nMothers += __popc(mb);
             }
         }
-        __syncwarp();
+        flush_movers();
         // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
         const int babyBase = ns + stayBase + arrive[c];
         for (int m = lane; m < nMothers; m += 32) {
@@ -537,6 +587,7 @@ k_cell_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, in
             if (storeAge) o.age[pos] = 0.0f;
         }
         __syncwarp();
+    }
     }
 }
 

@@ -37,7 +37,8 @@ struct DevStats {
     int nBirths, nDeaths, nMoves;
     int overflow;
     unsigned step;  // counter word of the random streams; +1 per finalizeStep
-    int oversize;   // a tile did not fit the shared-memory path: the host reruns the step on the generic path
+    int oversize;   // a cell did not fit the fast path: the host reruns the step on the generic path
+    int workDecide, workScatter;  // dynamic work counters of the two fast-path passes
     long long nextID;
 };
 
@@ -516,6 +517,8 @@ __global__ void k_step_begin(DevStats *st) {
     st->nMoves = 0;
     st->nNew = 0;
     st->oversize = 0;
+    st->workDecide = 0;
+    st->workScatter = 0;
 }
 
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {
