@@ -1,8 +1,7 @@
 #!/bin/bash
-# run the small profile workload with every library variant under build/libs (A/B of compile-time knobs)
+# A/B of compile-time knobs: run the bench with every library variant under build/libs
 for f in build/libs/*.so; do
   cp "$f" qhg4_b200/libqhg_b200.so
   echo "== $f"
-  python -m pytest tests -m gpu -q -x 2>&1 | tail -1
-  python profiles/prof_small.py 2>&1 | tail -1 | python -c "import sys,ast; d=ast.literal_eval(sys.stdin.read()); print(d['frac'], d['kernels_ms_per_step'])"
+  python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernels_ms_per_step'])"
 done

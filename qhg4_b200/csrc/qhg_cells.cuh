@@ -29,9 +29,13 @@ namespace qhg {
 constexpr int CW = 4;            // warps per CTA
 constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles; larger ones -> generic path
 constexpr int MAXF = 512;        // most fertile females of one cell that can be ranked in shared memory
-constexpr int QCAP = 64;         // work-queue entries per warp
+constexpr int QCAP = 128;        // work-queue entries per warp (flushed when more than half full)
+constexpr int MVCAP = 64;        // movers queued per warp in the scatter pass
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
-constexpr int CELL_BATCH = 8;    // consecutive cells a warp takes per grab of the work counter
+#ifndef QHG_CELL_BATCH
+#define QHG_CELL_BATCH 4
+#endif
+constexpr int CELL_BATCH = QHG_CELL_BATCH;    // consecutive cells a warp takes per grab of the work counter
 constexpr int DU = 2;            // agents per lane and chunk in the decide pass
 constexpr int SU = 2;            // the same in the scatter pass
 
@@ -258,17 +262,17 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 }
                 // queue the rare expensive work
                 const unsigned ma = __ballot_sync(FULL, needAtan), mm = __ballot_sync(FULL, needMove);
-                if (nqa + __popc(ma) > QCAP) flush_atan();
-                if (nqm + __popc(mm) > QCAP) flush_move();
                 if (needAtan) { const int e = nqa + __popc(ma & lt); S.qaAge[e] = ag; S.qaU[e] = r0[u].x; S.qaJ[e] = (uint16_t)j; }
                 if (needMove) { const int e = nqm + __popc(mm & lt); S.qmJ[e] = (uint16_t)j; S.qmId[e] = id[u]; }
                 nqa += __popc(ma);
                 nqm += __popc(mm);
             }
             __syncwarp();
+            // one call site each (code size): flush when a queue could overflow in the next round, and at the end of the cell
+            const bool last = j0 + 32 * DU >= n;
+            if (nqa > QCAP - 32 * DU || (last && nqa > 0)) flush_atan();
+            if (nqm > QCAP - 32 * DU || (last && nqm > 0)) flush_move();
         }
-        flush_atan();
-        flush_move();
 
         // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------
         // fertile females and fertile males are ranked by (random key, id); equal ranks mate.  Only "does this female
@@ -382,7 +386,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
 // (makeOffspring / createAgentAtIndex :823-847,880-918; makePopSpecificOffspring populations/tut_EnvironAltPop.cpp:141-149)
 struct WarpSmemB {
     int64_t motherId[MAXMOTHERS];
-    uint16_t mvJ[QCAP];  // movers of the cell, worked off together (their atomics and gathers overlap)
+    uint16_t mvJ[MVCAP];  // movers of the cell, worked off together (their atomics and gathers overlap)
 };
 
 // ---- multi-GPU: the grid is sharded by contiguous cell ranges, one range per rank ------------------
@@ -554,7 +558,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCel
                 const unsigned mb = __ballot_sync(FULL, born);
                 const bool mover = alive && code != 0;
                 const unsigned mm = __ballot_sync(FULL, mover);
-                if (nmv + __popc(mm) > QCAP) flush_movers();
+                if (nmv + __popc(mm) > MVCAP) flush_movers();
                 if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)(j0 + u * 32 + lane);
                 nmv += __popc(mm);
                 if (alive && code == 0) {
