@@ -131,6 +131,8 @@ int     qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out);
 int  qhgb_get_env_weights(qhgb_pop *p, double *out);
 int  qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d);
 int  qhgb_atan_death_prob(qhgb_pop *p, int n, const float *age, double *out);
+/* the carrying capacities NPPCapacity keeps in m_adCapacities (actions/NPPCapacity.cpp:138-217), one double per cell */
+int  qhgb_get_capacities(qhgb_pop *p, double *out);
 
 /* ---- several GPUs: the grid sharded by contiguous cell ranges --------------------------------------
  * One process per GPU, each with its own qhgb_pop holding the agents of its cell range [cell_begin[rank],

@@ -56,6 +56,7 @@ def lib():
         L.qor_get_env_weights.argtypes = [vp, vp]
         L.qor_get_birth_death_probs.argtypes = [vp, vp, vp]
         L.qor_atan_death_prob.argtypes = [vp, i32, vp, vp]
+        L.qor_get_capacities.argtypes = [vp, vp]
         L.qor_get_step_stats.argtypes = [vp, vp, vp, vp]
         L.qor_get_pending_births.restype = i64
         L.qor_get_pending_births.argtypes = [vp]
@@ -103,7 +104,7 @@ def polyline_eval(defn, x, float_cast=True):
 class OraclePop:
     """Same call sequence as the product's `GpuPopulation` (and the reference's PopBase)."""
 
-    def __init__(self, params, nbr, altitude, ice=None, mode=MODE_COUNTER, state16=None):
+    def __init__(self, params, nbr, altitude, ice=None, mode=MODE_COUNTER, state16=None, env=None):
         from qhg4_b200.params import DEFAULT_STATE
         L = lib()
         nbr = np.ascontiguousarray(nbr, np.int32)
@@ -115,6 +116,8 @@ class OraclePop:
         self.set_env("Altitude", altitude)
         if ice is not None:
             self.set_env("Ice", ice)
+        for k, v in (env or {}).items():
+            self.set_env(k, v)
         for mod, pars in params.modules.items():
             for k, v in pars.items():
                 if L.qor_set_attribute_str(self.h, k.encode(), str(v).encode()) != 0:
@@ -154,6 +157,14 @@ class OraclePop:
 
     def update_event(self, ev, t=0.0):
         return lib().qor_update_event(self.h, int(ev), float(t))
+
+    def flush_events(self, t=0.0):
+        return lib().qor_flush_events(self.h, float(t))
+
+    def capacities(self):
+        out = np.zeros(self.ncells)
+        assert lib().qor_get_capacities(self.h, _p(out)) == 0
+        return out
 
     def enable_action(self, name, on=True):
         return lib().qor_enable_action(self.h, name.encode(), int(on))

@@ -112,6 +112,26 @@ inline double atan_portable(double x) {
     return neg ? -r : r;
 }
 
+// exp used by the counter mode (Miami NPP model), same scheme: reduction by ln2 in two pieces + degree-5 polynomial
+// in r^2, operation order identical to qhg_rng.cuh::exp_rn.  Arguments outside [-700, 700] do not occur here.
+inline double exp_portable(double x) {
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+    const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (std::fabs(x) < 3.725290298461914e-9) return 1.0 + x;  // 2^-28
+    const int k = (int)(invln2 * x + (x < 0 ? -0.5 : 0.5));
+    const double t = (double)k;
+    const double hi = x + -(t * ln2HI), lo = t * ln2LO;
+    const double r = hi + -lo;
+    const double tt = r * r;
+    double pp = P5;
+    pp = P4 + tt * pp; pp = P3 + tt * pp; pp = P2 + tt * pp; pp = P1 + tt * pp;
+    const double c = r + -(tt * pp);
+    if (k == 0) return 1.0 + -(((r * c) / (c + -2.0)) + -r);
+    const double y = 1.0 + -((lo + -((r * c) / (2.0 + -c))) + -hi);
+    return std::ldexp(y, k);
+}
+
 // draw streams of the counter mode (mirrored in qhg4_b200/csrc/qhg_rng.cuh)
 enum { STREAM_ACT0 = 0, STREAM_ACT1 = 1, STREAM_PAIR = 2, STREAM_BABY = 3 };
 // lanes of STREAM_ACT0 / STREAM_ACT1
@@ -166,7 +186,17 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
     int32_t mate = -3;
 };
 
-enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH };
+enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP };
+
+// one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
+struct SubEval {
+    std::string input;      // environment array it evaluates ("Altitude") or "" for the capacities array
+    std::string weightName; // name of its combination weight attribute
+    bool usePoly = false;
+    bool first = true, needUpdate = false;
+    double weight = 0;
+};
 
 struct Action {
     std::string name;
@@ -193,6 +223,12 @@ struct qor_pop {
     double vB0 = -1024, vD0 = -1024, vTheta = -1024, vK = -1024;
     PolyLine altPref;
     bool havePoly = false;
+    // NPPCapacity (actions/NPPCapacity.cpp) + MultiEvaluator (actions/MultiEvaluator.cpp) of tut_EnvironCapAltPop
+    double nppWater = 0, nppCoastal = 0, nppCoastMinLat = 0, nppCoastMaxLat = 0, nppMin = 0, nppMax = 0, nppKMax = 0, nppKMin = 0, nppEff = 1;
+    bool nppNeedUpdate = true;
+    std::vector<double> cap;      // m_adCapacities
+    std::vector<SubEval> subs;    // evaluators of the MultiEvaluator, in construction order
+    bool multiFirst = true;
 
     // evaluator state (actions/SingleEvaluator.cpp:138-167,332-346)
     bool evalFirst = true, evalNeedUpdate = false;
@@ -270,6 +306,96 @@ struct qor_pop {
             B[c] = vB0 + (vTheta - vB0) * ((double)counts[c] / vK);
             D[c] = vD0 + (vTheta - vD0) * ((double)counts[c] / vK);
         }
+    }
+    // actions/VerhulstVarK.cpp:69-87 -> LinearBirth.cpp:97-112 / LinearDeath.cpp:101-119 with a per-cell K
+    void verhulstVarKInit() {
+        for (int c = 0; c < nCells; c++) {
+            if (cap[c] <= 0) { B[c] = 0; D[c] = 1; }
+            else {
+                B[c] = vB0 + (vTheta - vB0) * ((double)counts[c] / cap[c]);
+                D[c] = vD0 + (vTheta - vD0) * ((double)counts[c] / cap[c]);
+            }
+        }
+    }
+    // actions/NPPCapacity.cpp:138-217 (recalculate) + core/NPPCalcMiami.cpp:28-42 (calcNPP)
+    void nppRecalculate() {
+        if (!nppNeedUpdate) return;
+        const std::vector<double> &T = env["AnnualMeanTemp"], &P = env["AnnualRainfall"], &Wt = env["Water"], &npp = env["BaseNPP"],
+                                  &alt = env["Altitude"], &lon = env["Longitude"], &lat = env["Latitude"], &coast = env["Coastal"];
+        for (int i = 0; i < nCells; i++) {
+            const double eT = (mode == QOR_MODE_WELL) ? exp(1.315 - 0.119 * T[i]) : exp_portable(1.315 - 0.119 * T[i]);
+            const double eP = (mode == QOR_MODE_WELL) ? exp(-0.000664 * P[i]) : exp_portable(-0.000664 * P[i]);
+            const double nppT = 3000.0 / (1 + eT);
+            const double nppP = 3000.0 * (1 - eP);
+            cap[i] = 0.000475 * ((nppT < nppP) ? nppT : nppP);  // GDM_TO_KGC, core/NPPCalcMiami.cpp:12
+        }
+        for (int i = 0; i < nCells; i++) {
+            double tc = -1;
+            if (alt[i] > 0) {
+                const float A0 = 1500, A1 = 2500;
+                double af = (alt[i] < A0) ? 1 : ((A1 - alt[i]) / (A1 - A0));
+                if (af < 0) af = 0;
+                double tn = npp[i];
+                if (lon[i] > 115.0 && lat[i] > -12.0 && lon[i] < 150.0 && lat[i] < 1.0) {  // Oceania box, actions/NPPCapacity.cpp:22-25
+                    if (npp[i] < nppMin) tn = cap[i];
+                }
+                tn *= af;
+                if (tn < nppMin) tc = nppKMin;
+                else if (tn > nppMax) tc = nppKMax;
+                else tc = nppKMin + tn * nppKMax / (nppMax - nppMin);
+                if (coast[i] != 0 && lat[i] > nppCoastMinLat && lat[i] < nppCoastMaxLat) tc += nppCoastal * nppKMax;
+                tc += Wt[i] * nppWater * nppKMax;
+                if (tc > nppKMax) tc = nppKMax;
+            } else {
+                tc = 0;
+            }
+            cap[i] = tc * nppEff;
+        }
+        nppNeedUpdate = false;
+    }
+    // SingleEvaluator::calcValues + exchangeAndCumulate (bCumulate = true) into a scratch array
+    void subEvalCompute(const SubEval &e, std::vector<double> &out) {
+        const int stride = maxNeigh + 1;
+        const std::vector<double> &in = e.input.empty() ? cap : env[e.input];
+        const std::vector<double> *ice = env.count("Ice") ? &env["Ice"] : nullptr;
+        for (int c = 0; c < nCells; c++) {
+            double v = 0;
+            if (!ice || (*ice)[c] == 0) {
+                double dv = e.usePoly ? altPref.val((float)in[c]) : in[c];
+                v = (dv > 0) ? dv : 0;
+            }
+            out[(size_t)c * stride] = v;
+        }
+        for (int c = 0; c < nCells; c++) {
+            double w = out[(size_t)c * stride];
+            for (int k = 0; k < maxNeigh; k++) {
+                int n = nbr[(size_t)c * maxNeigh + k];
+                double cw = (n >= 0) ? out[(size_t)n * stride] : 0;
+                cw = (cw > 0) ? cw : 0;
+                w = w + cw;
+                out[(size_t)c * stride + k + 1] = w;
+            }
+        }
+    }
+    // MultiEvaluator::initialize + addSingleWeights (actions/MultiEvaluator.cpp:142-182,221-253), MODE_ADD_SIMPLE
+    void multiEvalInit() {
+        bool need = false;
+        for (auto &e : subs) need |= e.needUpdate;
+        if (!(need || multiFirst)) return;
+        multiFirst = false;
+        std::fill(W.begin(), W.end(), 0.0);
+        std::vector<double> scratch(W.size());
+        const int stride = maxNeigh + 1;
+        for (auto &e : subs) {
+            std::fill(scratch.begin(), scratch.end(), 0.0);
+            if (e.needUpdate || e.first) {  // an evaluator that needs no update contributes zeros (the reference's behaviour)
+                e.first = false;
+                subEvalCompute(e, scratch);
+            }
+            for (size_t i = 0; i < W.size(); i++) W[i] += scratch[i] * e.weight;
+        }
+        for (int c = 0; c < nCells; c++)
+            for (int k = 1; k < stride; k++) W[(size_t)c * stride + k] += W[(size_t)c * stride + k - 1];
     }
     // actions/SingleEvaluator.cpp:174-207 (calcValues) and :216-243 (exchangeAndCumulate), bCumulate = true
     void evaluatorCompute() {
@@ -405,6 +531,7 @@ struct qor_pop {
             }
             break;
         }
+        case A_VERHULSTVARK:  // actions/VerhulstVarK.cpp:96-112: the same two executes
         case A_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168 then LinearDeath.cpp:131-153
             if (a.life > 0) {
                 int c = a.cell;
@@ -425,6 +552,8 @@ struct qor_pop {
             break;
         }
         case A_SINGLEEVAL:
+        case A_MULTIEVAL:
+        case A_NPPCAP:
         case A_RANDOMPAIR:
             break;  // execute() is empty for these (actions/Action.h:36 default)
         }
@@ -450,6 +579,8 @@ struct qor_pop {
             if (!a->enabled) continue;
             switch (a->kind) {
             case A_VERHULST: verhulstInit(); break;
+            case A_VERHULSTVARK: verhulstVarKInit(); break;
+            case A_MULTIEVAL: multiEvalInit(); break;
             case A_RANDOMPAIR: randomPairInit(); break;
             case A_SINGLEEVAL: evaluatorInit(); break;
             default: break;
@@ -534,6 +665,7 @@ struct qor_pop {
     int finalizeStep() {  // core/SPopulation.cpp:439-477
         for (const Action *a : ordered()) {
             if (a->enabled && a->kind == A_SINGLEEVAL) evalNeedUpdate = false;  // actions/SingleEvaluator.cpp:125-130
+            if (a->enabled && a->kind == A_MULTIEVAL) for (auto &e : subs) e.needUpdate = false;  // actions/MultiEvaluator.cpp:189-195
         }
         recycleDeadSpace();
         performMoves();
@@ -569,6 +701,9 @@ struct qor_pop {
             // reached: the weights computed at the first step stay in force.  Replicated as is.
             if (evaluatorObserves) evalNeedUpdate = true;
         }
+        // NPPCapacity registers itself as an observer (actions/NPPCapacity.cpp:69) and reacts to GEO, CLIMATE and VEG (:121-131);
+        // the MultiEvaluator of tut_EnvironCapAltPop is never registered, so its weights stay as first computed
+        if (ev == 2 || ev == 3 || ev == 4) nppNeedUpdate = true;
         return 0;
     }
 };
@@ -589,6 +724,16 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
+                      {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"NPPCapacity", A_NPPCAP}};
+        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true;
+        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false;
+        p->subs = {ea, en};
+        p->cap.assign(n_cells, 0.0);
+        for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
+            p->env[nm].assign(n_cells, 0.0);
     } else {
         delete p;
         return nullptr;
@@ -635,12 +780,22 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "Verhulst_d0") p->vD0 = v;
     else if (s == "Verhulst_theta") p->vTheta = v;
     else if (s == "Verhulst_K") p->vK = v;
+    else if (s == "NPPCap_water_factor") p->nppWater = v;
+    else if (s == "NPPCap_coastal_factor") p->nppCoastal = v;
+    else if (s == "NPPCap_coastal_min_latitude") p->nppCoastMinLat = v;
+    else if (s == "NPPCap_coastal_max_latitude") p->nppCoastMaxLat = v;
+    else if (s == "NPPCap_NPP_min") p->nppMin = v;
+    else if (s == "NPPCap_NPP_max") p->nppMax = v;
+    else if (s == "NPPCap_K_max") p->nppKMax = v;
+    else if (s == "NPPCap_K_min") p->nppKMin = v;
+    else if (s == "NPPCap_efficiency") p->nppEff = v;
+    else if (s == "Multi_weight_alt" || s == "Multi_weight_npp") { for (auto &e : p->subs) if (e.weightName == s) e.weight = v; }
     else return -1;
     return 0;
 }
 
 int qor_set_attribute_str(qor_pop *p, const char *name, const char *v) {
-    if (std::string(name) == "AltCapPref") {
+    if (std::string(name) == "AltCapPref" || std::string(name) == "AltPref") {
         p->havePoly = p->altPref.parse(v);
         return p->havePoly ? 0 : -1;
     }
@@ -697,6 +852,7 @@ int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDe
     p->atanScale = (PI / 2 - ATAN_EPS) / atan(p->atanSlope * p->atanRange);
     p->nextID = p->maxID + 1;
     p->updateNumAgentsPerCell();
+    if (p->find("NPPCapacity")) p->nppRecalculate();  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     return 0;
 }
 
@@ -705,7 +861,10 @@ int qor_do_actions(qor_pop *p, unsigned prio, float t) { return p->doActions(pri
 int qor_finalize_step(qor_pop *p) { return p->finalizeStep(); }
 int qor_step(qor_pop *p, float t) { return p->step(t); }
 int qor_update_event(qor_pop *p, int ev, float t) { return p->updateEvent(ev, t); }
-int qor_flush_events(qor_pop *, float) { return 0; }
+int qor_flush_events(qor_pop *p, float) {  // EVENT_ID_FLUSH: NPPCapacity::notify -> recalculate (actions/NPPCapacity.cpp:127-130)
+    if (p->find("NPPCapacity")) p->nppRecalculate();
+    return 0;
+}
 
 int64_t qor_get_num_agents_effective(qor_pop *p) { return p->numUsed - (int64_t)p->prevDead.size(); }  // core/SPopulation.h:148
 
@@ -744,6 +903,12 @@ int qor_get_env_weights(qor_pop *p, double *out) {
 int qor_get_birth_death_probs(qor_pop *p, double *b, double *d) {
     memcpy(b, p->B.data(), sizeof(double) * p->nCells);
     memcpy(d, p->D.data(), sizeof(double) * p->nCells);
+    return 0;
+}
+
+int qor_get_capacities(qor_pop *p, double *out) {
+    if (p->cap.empty()) return -1;
+    memcpy(out, p->cap.data(), sizeof(double) * p->nCells);
     return 0;
 }
 

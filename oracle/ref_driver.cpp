@@ -33,7 +33,10 @@
 #include "ParamProvider2.h"
 #include "ArrayShare.h"
 #include "EventConsts.h"
+#include "Climate.h"
+#include "Vegetation.h"
 #include "tut_EnvironAltPop.h"
+#include "tut_EnvironCapAltPop.h"
 
 namespace {
 
@@ -55,18 +58,80 @@ struct Quiet {  // the reference prints several lines per step; send them to /de
     }
 };
 
+struct AgentRec {  // the fields every supported population's agent struct has
+    int cell; int64_t id; float birth; uint8_t gender; float age; float lastBirth; uint32_t life; int mate; int slot;
+};
+
+// what the C API needs from a population, whatever its concrete class
+struct PopAccess {
+    virtual ~PopAccess() {}
+    virtual PopBase *base() = 0;
+    virtual int reserve(int n) = 0;
+    virtual void put(int slot, const AgentRec &r, gridtype cellID) = 0;
+    virtual bool get(int slot, AgentRec &r) = 0;
+    virtual int first() = 0;
+    virtual int last() = 0;
+    virtual idtype &maxID() = 0;
+    virtual double *envWeights() = 0;
+    virtual double *capacities() = 0;
+    virtual int bd(double *&b, double *&d) = 0;
+    virtual void atanParams(double &scale, double &slope, double &maxAge) = 0;
+};
+
+template <class PopT, class AgentT>
+struct PopAccessT : PopAccess {
+    PopT *pop;
+    explicit PopAccessT(PopT *p) : pop(p) {}
+    PopBase *base() override { return pop; }
+    int reserve(int n) override { return pop->reserveAgentSpace(n); }
+    void put(int slot, const AgentRec &r, gridtype cellID) override {
+        AgentT &a = pop->m_aAgents[slot];
+        a.m_iLifeState = r.life; a.m_iCellIndex = r.cell; a.m_ulID = r.id; a.m_ulCellID = cellID;
+        a.m_fBirthTime = r.birth; a.m_iGender = r.gender; a.m_fAge = r.age; a.m_fLastBirth = r.lastBirth; a.m_iMateIndex = -3;
+    }
+    bool get(int slot, AgentRec &r) override {
+        AgentT &a = pop->m_aAgents[slot];
+        if (a.m_iLifeState == LIFE_STATE_DEAD) return false;
+        r.cell = a.m_iCellIndex; r.id = a.m_ulID; r.birth = a.m_fBirthTime; r.gender = a.m_iGender; r.age = a.m_fAge;
+        r.lastBirth = a.m_fLastBirth; r.life = a.m_iLifeState; r.mate = a.m_iMateIndex; r.slot = slot;
+        return true;
+    }
+    int first() override { return pop->getFirstAgentIndex(); }
+    int last() override { return pop->getLastAgentIndex(); }
+    idtype &maxID() override { return pop->m_iMaxID; }
+    double *envWeights() override { return pop->m_adEnvWeights; }
+    double *capacities() override { return pop->m_adCapacities; }
+    int bd(double *&b, double *&d) override;
+    void atanParams(double &scale, double &slope, double &maxAge) override {
+        scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge;
+    }
+};
+template <>
+int PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>::bd(double *&b, double *&d) {
+    if (pop->m_pVerhulst->m_pLB == NULL || pop->m_pVerhulst->m_pLD == NULL) return -1;
+    b = pop->m_pVerhulst->m_pLB->m_adB; d = pop->m_pVerhulst->m_pLD->m_adD;
+    return 0;
+}
+template <>
+int PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>::bd(double *&b, double *&d) {
+    if (pop->m_pVerVarK->m_pLB == NULL || pop->m_pVerVarK->m_pLD == NULL) return -1;
+    b = pop->m_pVerVarK->m_pLB->m_adB; d = pop->m_pVerVarK->m_pLD->m_adD;
+    return 0;
+}
+
 struct RefSim {
     int nCells = 0;
     int nThreads = 1;
     bool quiet = true;
     SCellGrid *cg = nullptr;
     Geography *geo = nullptr;
+    Climate *cli = nullptr;
+    Vegetation *veg = nullptr;
     PopLooper *looper = nullptr;
     IDGen **idg = nullptr;
-    tut_EnvironAltPop *pop = nullptr;
+    PopAccess *pa = nullptr;
     uint32_t state[16];
     uint seeds[8];
-    double tInit = 0, tActions = 0, tFinal = 0;
 };
 
 }  // namespace
@@ -130,12 +195,27 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
     s->looper->dTimeActions = 0;
     s->looper->dTimeFinalize = 0;
 
-    s->pop = new tut_EnvironAltPop(s->cg, s->looper, layerSize > 0 ? layerSize : 65536, s->idg, s->state, s->seeds);
+    // climate and vegetation groups (needed by NPPCapacity, actions/NPPCapacity.cpp:92-115)
+    s->cli = new Climate(s->cg, (uint)nCells, 1);
+    s->cg->setClimate(s->cli);
+    s->veg = new Vegetation(s->cg, (uint)nCells, 1);
+    s->cg->setVegetation(s->veg);
+    for (int c = 0; c < nCells; c++) { s->cli->m_adAnnualMeanTemp[c] = 0; s->cli->m_adAnnualRainfall[c] = 0; s->geo->m_adWater[c] = 0; }
+
+    const int ls = layerSize > 0 ? layerSize : 65536;
+    if (std::string(class_name) == "tut_EnvironAltPop") {
+        s->pa = new PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>(new tut_EnvironAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
+        s->pa = new PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else {
+        fprintf(stderr, "[qref_create] unknown population class [%s]\n", class_name);
+        return NULL;
+    }
     ParamProvider2 *pp = ParamProvider2::createInstance(xml_path);
     int rc = -1;
     if (pp != NULL) {
         rc = pp->selectClass(class_name);
-        if (rc == 0) rc = s->pop->readSpeciesData(pp);
+        if (rc == 0) rc = s->pa->base()->readSpeciesData(pp);
         delete pp;
     }
     if (rc != 0) {
@@ -152,23 +232,17 @@ int qref_add_agents(void *h, long n, const int *cell, const int64_t *id, const f
     long done = 0;
     while (done < n) {  // reserveAgentSpace takes int
         int chunk = (int)((n - done > (1 << 30)) ? (1 << 30) : (n - done));
-        int start = s->pop->reserveAgentSpace(chunk);
+        int start = s->pa->reserve(chunk);
 #pragma omp parallel for
         for (int i = 0; i < chunk; i++) {
-            tut_EnvironAltAgent &a = s->pop->m_aAgents[start + i];
             long j = done + i;
-            a.m_iLifeState = life ? life[j] : LIFE_STATE_ALIVE;
-            a.m_iCellIndex = cell[j];
-            a.m_ulID = id[j];
-            a.m_ulCellID = s->cg->m_aCells[cell[j]].m_iGlobalID;
-            a.m_fBirthTime = birth[j];
-            a.m_iGender = gender[j];
-            a.m_fAge = age[j];
-            a.m_fLastBirth = lastBirth[j];
-            a.m_iMateIndex = -3;
+            AgentRec r;
+            r.life = life ? life[j] : LIFE_STATE_ALIVE; r.cell = cell[j]; r.id = id[j]; r.birth = birth[j];
+            r.gender = gender[j]; r.age = age[j]; r.lastBirth = lastBirth[j];
+            s->pa->put(start + i, r, s->cg->m_aCells[cell[j]].m_iGlobalID);
         }
         for (int i = 0; i < chunk; i++) {
-            if (id[done + i] > s->pop->m_iMaxID) s->pop->m_iMaxID = id[done + i];
+            if (id[done + i] > s->pa->maxID()) s->pa->maxID() = id[done + i];
         }
         done += chunk;
     }
@@ -178,7 +252,7 @@ int qref_add_agents(void *h, long n, const int *cell, const int64_t *id, const f
 int qref_start(void *h) {
     RefSim *s = (RefSim *)h;
     Quiet q(s->quiet);
-    int rc = s->looper->addPop(s->pop);
+    int rc = s->looper->addPop(s->pa->base());
     idtype maxID = s->looper->getMaxID();
     for (int t = 0; t < s->nThreads; t++) s->idg[t]->setData(maxID + 1, t, s->nThreads);
     rc += s->looper->preLoop();
@@ -198,7 +272,7 @@ double qref_run(void *h, float t0, int nSteps, int64_t *agentSteps) {
     int64_t as = 0;
     double w0 = omp_get_wtime();
     for (int i = 0; i < nSteps; i++) {
-        as += (int64_t)s->pop->getNumAgentsEffective();
+        as += (int64_t)s->pa->base()->getNumAgentsEffective();
         s->looper->doStep(t0 + i);
     }
     double w1 = omp_get_wtime();
@@ -206,28 +280,28 @@ double qref_run(void *h, float t0, int nSteps, int64_t *agentSteps) {
     return w1 - w0;
 }
 
-long qref_num_agents(void *h) { return (long)((RefSim *)h)->pop->getNumAgentsEffective(); }
+long qref_num_agents(void *h) { return (long)((RefSim *)h)->pa->base()->getNumAgentsEffective(); }
 
 // live agents in slot order; returns number written (or needed if cap too small)
 long qref_get_agents(void *h, long cap, int *cell, int64_t *id, float *birth, uint8_t *gender, float *age,
                      float *lastBirth, uint32_t *life, int *mate, int *slot) {
     RefSim *s = (RefSim *)h;
-    int first = s->pop->getFirstAgentIndex();
+    int first = s->pa->first();
     if (first < 0) return 0;
-    int last = s->pop->getLastAgentIndex();
+    int last = s->pa->last();
     long k = 0;
     for (int i = first; i <= last; i++) {
-        tut_EnvironAltAgent &a = s->pop->m_aAgents[i];
-        if (a.m_iLifeState == LIFE_STATE_DEAD) continue;
+        AgentRec a;
+        if (!s->pa->get(i, a)) continue;
         if (k < cap) {
-            if (cell) cell[k] = a.m_iCellIndex;
-            if (id) id[k] = a.m_ulID;
-            if (birth) birth[k] = a.m_fBirthTime;
-            if (gender) gender[k] = a.m_iGender;
-            if (age) age[k] = a.m_fAge;
-            if (lastBirth) lastBirth[k] = a.m_fLastBirth;
-            if (life) life[k] = a.m_iLifeState;
-            if (mate) mate[k] = a.m_iMateIndex;
+            if (cell) cell[k] = a.cell;
+            if (id) id[k] = a.id;
+            if (birth) birth[k] = a.birth;
+            if (gender) gender[k] = a.gender;
+            if (age) age[k] = a.age;
+            if (lastBirth) lastBirth[k] = a.lastBirth;
+            if (life) life[k] = a.life;
+            if (mate) mate[k] = a.mate;
             if (slot) slot[k] = i;
         }
         k++;
@@ -237,30 +311,69 @@ long qref_get_agents(void *h, long cap, int *cell, int64_t *id, float *birth, ui
 
 int qref_get_counts(void *h, uint64_t *out) {
     RefSim *s = (RefSim *)h;
-    for (int c = 0; c < s->nCells; c++) out[c] = s->pop->getNumAgents(c);
+    for (int c = 0; c < s->nCells; c++) out[c] = s->pa->base()->getNumAgents(c);
     return 0;
 }
 
 int qref_get_weights(void *h, double *out) {  // nCells*7, actions/SingleEvaluator.cpp:174-243
     RefSim *s = (RefSim *)h;
-    memcpy(out, s->pop->m_adEnvWeights, sizeof(double) * (size_t)s->nCells * 7);
+    memcpy(out, s->pa->envWeights(), sizeof(double) * (size_t)s->nCells * 7);
     return 0;
 }
 
 int qref_get_bd(void *h, double *b, double *d) {  // actions/LinearBirth.cpp:97-112, LinearDeath.cpp:101-119
     RefSim *s = (RefSim *)h;
-    if (s->pop->m_pVerhulst->m_pLB == NULL || s->pop->m_pVerhulst->m_pLD == NULL) return -1;
-    memcpy(b, s->pop->m_pVerhulst->m_pLB->m_adB, sizeof(double) * s->nCells);
-    memcpy(d, s->pop->m_pVerhulst->m_pLD->m_adD, sizeof(double) * s->nCells);
+    double *pb = NULL, *pd = NULL;
+    if (s->pa->bd(pb, pd) != 0) return -1;
+    memcpy(b, pb, sizeof(double) * s->nCells);
+    memcpy(d, pd, sizeof(double) * s->nCells);
     return 0;
+}
+
+// carrying capacities of NPPCapacity (actions/NPPCapacity.cpp:138-217); NULL array for populations without one
+int qref_get_capacities(void *h, double *out) {
+    RefSim *s = (RefSim *)h;
+    double *k = s->pa->capacities();
+    if (k == NULL) return -1;
+    memcpy(out, k, sizeof(double) * s->nCells);
+    return 0;
+}
+
+// any per-cell environment array the supported populations read (core/Geography.h:31-39, core/Climate.h, core/Vegetation.h)
+int qref_set_env(void *h, const char *name, const double *v) {
+    RefSim *s = (RefSim *)h;
+    std::string n(name);
+    for (int c = 0; c < s->nCells; c++) {
+        if (n == "Altitude") s->geo->m_adAltitude[c] = v[c];
+        else if (n == "Ice") s->geo->m_abIce[c] = v[c] != 0;
+        else if (n == "Water") s->geo->m_adWater[c] = v[c];
+        else if (n == "Coastal") s->geo->m_abCoastal[c] = v[c] != 0;
+        else if (n == "Latitude") s->geo->m_adLatitude[c] = v[c];
+        else if (n == "Longitude") s->geo->m_adLongitude[c] = v[c];
+        else if (n == "AnnualMeanTemp") s->cli->m_adAnnualMeanTemp[c] = v[c];
+        else if (n == "AnnualRainfall") s->cli->m_adAnnualRainfall[c] = v[c];
+        else if (n == "BaseNPP") s->veg->m_adBaseANPP[c] = v[c];
+        else return -1;
+    }
+    return 0;
+}
+
+// deliver an event the way app/Simulator.cpp:728-735,372-374 does: updateEvent for the id(s), then flushEvents
+int qref_event(void *h, int event_id, float t, int flush) {
+    RefSim *s = (RefSim *)h;
+    Quiet q(s->quiet);
+    int rc = s->pa->base()->updateEvent(event_id, NULL, t);
+    if (flush) s->pa->base()->flushEvents(t);
+    return rc;
 }
 
 // ATanDeath probability exactly as actions/ATanDeath.cpp:49-59,75 computes it (fAge is the agent's float age)
 int qref_atan_prob(void *h, int n, const float *age, double *p) {
     RefSim *s = (RefSim *)h;
-    ATanDeath<tut_EnvironAltAgent> *ad = s->pop->m_pAD;
+    double scale, slope, maxAge;
+    s->pa->atanParams(scale, slope, maxAge);
     for (int i = 0; i < n; i++) {
-        p[i] = 0.5 + ad->m_dScale * atan(ad->m_dSlope * (age[i] - ad->m_dMaxAge)) / Q_PI;
+        p[i] = 0.5 + scale * atan(slope * (age[i] - maxAge)) / Q_PI;
     }
     return 0;
 }
@@ -273,8 +386,8 @@ int qref_geo_event(void *h, const double *altitude, const uint8_t *ice, float t)
         if (altitude) s->geo->m_adAltitude[c] = altitude[c];
         if (ice) s->geo->m_abIce[c] = ice[c] != 0;
     }
-    int rc = s->pop->updateEvent(EVENT_ID_GEO, NULL, t);
-    s->pop->flushEvents(t);
+    int rc = s->pa->base()->updateEvent(EVENT_ID_GEO, NULL, t);
+    s->pa->base()->flushEvents(t);
     return rc;
 }
 
@@ -294,7 +407,10 @@ void qref_destroy(void *h) {
     delete s->looper;  // deletes the pops (core/PopLooper.cpp:25-34)
     for (int t = 0; t < s->nThreads; t++) delete s->idg[t];
     delete[] s->idg;
+    delete s->pa;
     s->cg->delGeography();
+    s->cg->delClimate();
+    s->cg->delVegetation();
     delete s->cg;
     delete s;
 }

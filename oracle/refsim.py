@@ -43,6 +43,9 @@ def lib():
         L.qref_atan_prob.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.qref_geo_event.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.qref_timers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qref_get_capacities.argtypes = [C.c_void_p, C.c_void_p]
+        L.qref_set_env.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.qref_event.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.qref_destroy.argtypes = [C.c_void_p]
         L.qref_well_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.qref_polyline_eval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -73,7 +76,7 @@ def polyline_eval(defn: str, x, float_cast=True):
 class RefSim:
     """One `tut_EnvironAltPop` on a given grid, driven through PopLooper::doStep."""
 
-    def __init__(self, params, nbr, altitude, ice=None, threads=1, state16=None, quiet=True, layer_size=65536):
+    def __init__(self, params, nbr, altitude, ice=None, threads=1, state16=None, quiet=True, layer_size=65536, env=None):
         from qhg4_b200.params import DEFAULT_STATE
         self.ncells = len(nbr)
         self._nbr = np.ascontiguousarray(nbr, dtype=np.int32)
@@ -91,6 +94,21 @@ class RefSim:
         if not self.h:
             raise RuntimeError("qref_create failed")
         self.threads = threads
+        for k, v in (env or {}).items():
+            self.set_env(k, v)
+
+    def set_env(self, name, v):
+        v = np.ascontiguousarray(v, np.float64)
+        assert len(v) == self.ncells
+        assert lib().qref_set_env(self.h, name.encode(), _p(v)) == 0, name
+
+    def event(self, event_id, t=0.0, flush=True):
+        return lib().qref_event(self.h, int(event_id), float(t), int(flush))
+
+    def capacities(self):
+        out = np.zeros(self.ncells)
+        assert lib().qref_get_capacities(self.h, _p(out)) == 0
+        return out
 
     def add_agents(self, pop: dict):
         n = len(pop["cell"])

@@ -26,3 +26,6 @@ int   qdf_writePolyLine(hid_t, PolyLine *, const std::string) { return -1; }
 int   qdf_compareDataTypes(hid_t, hid_t) { return -1; }
 int   dumpWELL(WELL512 **, int, const std::string, hid_t) { return -1; }
 int   restoreWELL(WELL512 **, int, const std::string, hid_t) { return -1; }
+int   qdf_readArray(hid_t, const std::string, const uint, void *, const hid_t) { return -1; }
+int   qdf_writeArray(hid_t, const std::string, const uint, void *, const hid_t) { return -1; }
+int   qdf_replaceArray(hid_t, const std::string, const uint, void *, const hid_t) { return -1; }

@@ -98,14 +98,20 @@ __device__ __forceinline__ int warp_sum(int v) {
 // per-cell: Verhulst birth and death probabilities from last step's counts
 // (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and reset of the step's counters
 __global__ void k_cell_init(int nCells, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
-                            double b0, double d0, double theta, double K, int doVerhulst,
+                            double b0, double d0, double theta, double K, const double *__restrict__ Kcell, int doVerhulst,
                             int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
                             int *__restrict__ birthCount, int *__restrict__ nFert) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
         if (doVerhulst) {
-            double q = __ddiv_rn((double)count[c], K);
-            B[c] = __dadd_rn(b0, __dmul_rn(__dadd_rn(theta, -b0), q));
-            D[c] = __dadd_rn(d0, __dmul_rn(__dadd_rn(theta, -d0), q));
+            const double Kc = Kcell ? Kcell[c] : K;  // VerhulstVarK: the carrying capacity of the cell (actions/VerhulstVarK.cpp)
+            if (Kcell && Kc <= 0) {               // LinearBirth.cpp:104-105, LinearDeath.cpp:113-114
+                B[c] = 0;
+                D[c] = 1;
+            } else {
+                double q = __ddiv_rn((double)count[c], Kc);
+                B[c] = __dadd_rn(b0, __dmul_rn(__dadd_rn(theta, -b0), q));
+                D[c] = __dadd_rn(d0, __dmul_rn(__dadd_rn(theta, -d0), q));
+            }
         }
         stay[c] = 0;
         arrive[c] = 0;
@@ -152,6 +158,58 @@ __global__ void k_weights_cumulate(int nCells, const int *__restrict__ nbr, doub
             w = cumulate ? __dadd_rn(w, cw) : cw;
             W[(size_t)c * WSTRIDE + k + 1] = w;
         }
+    }
+}
+
+// MultiEvaluator::addSingleWeights (actions/MultiEvaluator.cpp:221-253): out += single * weight for every evaluator ...
+__global__ void k_multi_accumulate(size_t n, const double *__restrict__ single, double weight, double *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __dadd_rn(out[i], __dmul_rn(single[i], weight));
+}
+// ... then the rows are cumulated (again: the evaluators inside were built cumulating, docs/DoubleCumulateArtifactsBug.odt)
+__global__ void k_rows_cumulate(int nCells, double *__restrict__ W) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        double w = W[(size_t)c * WSTRIDE];
+#pragma unroll
+        for (int k = 1; k < WSTRIDE; k++) {
+            w = __dadd_rn(W[(size_t)c * WSTRIDE + k], w);
+            W[(size_t)c * WSTRIDE + k] = w;
+        }
+    }
+}
+
+// NPPCapacity::recalculate (actions/NPPCapacity.cpp:138-217) with NPPCalcMiami::calcNPP (core/NPPCalcMiami.cpp:28-42)
+struct NppParams {
+    double waterFactor, coastalFactor, coastMinLat, coastMaxLat, nppMin, nppMax, kMax, kMin, efficiency;
+};
+__global__ void k_npp_capacity(int nCells, NppParams Q, const double *__restrict__ T, const double *__restrict__ Pr,
+                               const double *__restrict__ water, const double *__restrict__ npp, const double *__restrict__ alt,
+                               const double *__restrict__ lon, const double *__restrict__ lat, const double *__restrict__ coastal,
+                               double *__restrict__ cap) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nCells; i += gridDim.x * blockDim.x) {
+        const double nppT = __ddiv_rn(3000.0, __dadd_rn(1.0, exp_rn(__dadd_rn(1.315, -__dmul_rn(0.119, T[i])))));
+        const double nppP = __dmul_rn(3000.0, __dadd_rn(1.0, -exp_rn(__dmul_rn(-0.000664, Pr[i]))));
+        const double miami = __dmul_rn(0.000475, (nppT < nppP) ? nppT : nppP);  // GDM_TO_KGC
+        double tc;
+        const double a = alt[i];
+        if (a > 0) {
+            double af = (a < 1500.0) ? 1.0 : __ddiv_rn(__dadd_rn(2500.0, -a), 1000.0);
+            if (af < 0) af = 0;
+            double tn = npp[i];
+            if (lon[i] > 115.0 && lat[i] > -12.0 && lon[i] < 150.0 && lat[i] < 1.0) {  // Oceania box (:22-25)
+                if (npp[i] < Q.nppMin) tn = miami;
+            }
+            tn = __dmul_rn(tn, af);
+            if (tn < Q.nppMin) tc = Q.kMin;
+            else if (tn > Q.nppMax) tc = Q.kMax;
+            else tc = __dadd_rn(Q.kMin, __ddiv_rn(__dmul_rn(tn, Q.kMax), __dadd_rn(Q.nppMax, -Q.nppMin)));
+            if (coastal[i] != 0 && lat[i] > Q.coastMinLat && lat[i] < Q.coastMaxLat) tc = __dadd_rn(tc, __dmul_rn(Q.coastalFactor, Q.kMax));
+            tc = __dadd_rn(tc, __dmul_rn(__dmul_rn(water[i], Q.waterFactor), Q.kMax));
+            if (tc > Q.kMax) tc = Q.kMax;
+        } else {
+            tc = 0;
+        }
+        cap[i] = __dmul_rn(tc, Q.efficiency);
     }
 }
 

@@ -94,7 +94,16 @@ int loadNccl() {
         if (r_ != ncclSuccess) return fail("%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
-enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST };
+enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP };
+
+// one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
+struct SubEval {
+    std::string input;       // environment array it evaluates, "" = the capacities array of NPPCapacity
+    std::string weightName;  // attribute holding its combination weight
+    bool usePoly = false;
+    bool first = true, needUpdate = false;
+};
 
 struct HostAction {
     std::string name;
@@ -176,6 +185,10 @@ struct qhgb_pop {
     int64_t genericSteps = 0, tiledSteps = 0;
     bool evalFirst = true, evalNeedUpdate = false;
     bool evaluatorObserves = false;  // does the population class addObserver() its evaluator?
+    // tut_EnvironCapAltPop: NPPCapacity + MultiEvaluator[NPP+Alt] + VerhulstVarK (populations/tut_EnvironCapAltPop.cpp:27-72)
+    std::vector<SubEval> subs;
+    bool multiFirst = true, nppNeedUpdate = true;
+    DevBuf<double> cap, Wtmp;
     float curTime = -1;
     std::vector<unsigned> levels;
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
@@ -197,6 +210,14 @@ struct qhgb_pop {
     std::vector<KernelTime> ktimes;
 
     AgentArrays arrays(int b) { return AgentArrays{id[b].p, birth[b].p, lastBirth[b].p, cell[b].p, flags[b].p, age[b].p}; }
+    HostAction *findKind(ActKind k) {
+        for (auto &a : actions) if (a.kind == k) return &a;
+        return nullptr;
+    }
+    bool active(ActKind k) {
+        HostAction *a = findKind(k);
+        return a && a->prio >= 0 && a->enabled;
+    }
     HostAction *find(const std::string &n) {
         for (auto &a : actions) if (a.name == n) return &a;
         return nullptr;
@@ -334,6 +355,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
         case A_FERTILITY: op = OP_FERTILITY; break;
         case A_VERHULST: op = OP_VERHULST; break;
+        case A_VERHULSTVARK: op = OP_VERHULST; break;  // the same two executes with a per-cell K (actions/VerhulstVarK.cpp:96-112)
         default: break;  // evaluators and pairing have no per-agent execute()
         }
         if (op && P.nOps < MAX_OPS) { P.prog |= (unsigned long long)op << (4 * P.nOps); P.nOps++; }
@@ -397,6 +419,53 @@ int materializeAges(qhgb_pop *p) {
     return 0;
 }
 
+// NPPCapacity::recalculate on the device (actions/NPPCapacity.cpp:138-217)
+int recalcCapacities(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    if (!q.nppNeedUpdate) return 0;
+    const char *need[] = {"AnnualMeanTemp", "AnnualRainfall", "Water", "BaseNPP", "Longitude", "Latitude", "Coastal"};
+    for (const char *n : need) {
+        if (!q.envExtra.count(n)) {  // an array that was never set is all zero (Geography::init memsets them)
+            CK(q.envExtra[n].alloc(q.nCells));
+            CK(cudaMemsetAsync(q.envExtra[n].p, 0, sizeof(double) * q.nCells, q.stream));
+        }
+    }
+    if (!q.haveAlt) return fail("[NPPCapacity] no geography (Altitude)");
+    NppParams Q{q.A("NPPCap_water_factor"), q.A("NPPCap_coastal_factor"), q.A("NPPCap_coastal_min_latitude"), q.A("NPPCap_coastal_max_latitude"),
+                q.A("NPPCap_NPP_min"), q.A("NPPCap_NPP_max"), q.A("NPPCap_K_max"), q.A("NPPCap_K_min"), q.A("NPPCap_efficiency", 1.0)};
+    LAUNCH(p, "k_npp_capacity", k_npp_capacity, q.gridFor(q.nCells), 256, q.nCells, Q, q.envExtra["AnnualMeanTemp"].p, q.envExtra["AnnualRainfall"].p,
+           q.envExtra["Water"].p, q.envExtra["BaseNPP"].p, q.alt.p, q.envExtra["Longitude"].p, q.envExtra["Latitude"].p, q.envExtra["Coastal"].p, q.cap.p);
+    CK(cudaGetLastError());
+    q.nppNeedUpdate = false;
+    return 0;
+}
+
+// MultiEvaluator::initialize + addSingleWeights, MODE_ADD_SIMPLE (actions/MultiEvaluator.cpp:142-182,221-253)
+int computeMultiWeights(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    bool need = false;
+    for (auto &e : q.subs) need |= e.needUpdate;
+    if (!(need || q.multiFirst)) return 0;
+    q.multiFirst = false;
+    const size_t nW = (size_t)q.nCells * WSTRIDE;
+    const int g = q.gridFor(q.nCells);
+    CK(cudaMemsetAsync(q.W.p, 0, nW * sizeof(double), q.stream));
+    for (auto &e : q.subs) {
+        CK(cudaMemsetAsync(q.Wtmp.p, 0, nW * sizeof(double), q.stream));
+        if (e.needUpdate || e.first) {  // an evaluator that needs no update contributes zeros (the reference's behaviour)
+            e.first = false;
+            const double *in = e.input.empty() ? q.cap.p : (e.input == "Altitude" ? q.alt.p : q.envExtra[e.input].p);
+            if (!in) return fail("No array with name [%s] found", e.input.c_str());
+            LAUNCH(p, "k_weights_own", k_weights_own, g, 256, q.nCells, in, q.haveIce ? q.ice.p : nullptr, q.poly, (e.usePoly && q.havePoly) ? 1 : 0, q.Wtmp.p);
+            LAUNCH(p, "k_weights_cumulate", k_weights_cumulate, g, 256, q.nCells, q.nbr.p, q.Wtmp.p, 1);
+        }
+        LAUNCH(p, "k_multi_accumulate", k_multi_accumulate, q.gridFor((int64_t)nW), 256, nW, q.Wtmp.p, q.A(e.weightName.c_str()), q.W.p);
+    }
+    LAUNCH(p, "k_rows_cumulate", k_rows_cumulate, g, 256, q.nCells, q.W.p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int computeWeights(qhgb_pop *p) {
     if (!p->haveAlt) return fail("SingleEvaluator[Alt]: no array with name [Altitude]");
     int g = p->gridFor(p->nCells);
@@ -415,7 +484,7 @@ int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
     qhgb_pop &q = *p;
     LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
     LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.nCells), 256, q.nCells, q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
-           q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
+           q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), q.findKind(A_VERHULSTVARK) ? q.cap.p : nullptr, doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
            q.birthCount.p, q.nFert.p);
     CK(cudaGetLastError());
     return 0;
@@ -597,6 +666,13 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
+                      {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"NPPCapacity", A_NPPCAP}};
+        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true;
+        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false;
+        p->subs = {ea, en};
     } else {
         delete p;
         return fail("qhgb_create: unknown population class [%s]", pop_class);
@@ -629,6 +705,11 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(p->B.alloc(nc));
     CK(p->D.alloc(nc));
     CK(p->tileSums.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
+    if (!p->subs.empty()) {
+        CK(p->cap.alloc(nc));
+        CK(p->Wtmp.alloc(nc * WSTRIDE));
+        CK(cudaMemsetAsync(p->cap.p, 0, nc * sizeof(double), p->stream));
+    }
     CK(p->dstats.alloc(1));
     CK(cudaMemsetAsync(p->count[0].p, 0, nc * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->count[1].p, 0, nc * sizeof(int), p->stream));
@@ -657,6 +738,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
+    p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) {
         p->id[b].release(); p->birth[b].release(); p->lastBirth[b].release(); p->age[b].release();
         p->cell[b].release(); p->flags[b].release();
@@ -727,7 +809,8 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
 static const char *const kNumericAttrs[] = {
     "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
-    "Verhulst_K"};
+    "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
+    "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp"};
 
 int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
     if (!p || !name) return fail("qhgb_set_attribute: NULL argument");
@@ -739,7 +822,7 @@ int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
 
 int qhgb_set_attribute_str(qhgb_pop *p, const char *name, const char *value) {
     if (!p || !name || !value) return fail("qhgb_set_attribute_str: NULL argument");
-    if (strcmp(name, "AltCapPref") == 0) {  // PolyLine::readFromString, utils/PolyLine.cpp:92-127
+    if (strcmp(name, "AltCapPref") == 0 || strcmp(name, "AltPref") == 0) {  // PolyLine::readFromString, utils/PolyLine.cpp:92-127
         std::vector<double> d;
         const char *s = value;
         char *e;
@@ -875,6 +958,7 @@ int qhgb_pre_loop(qhgb_pop *p) {
     if (resetCellCounters(p, false) != 0) return -1;
     p->doVerhulst = false;
     if (runPipeline(p, P, false, false, false) != 0) return -1;
+    if (p->findKind(A_NPPCAP) && recalcCapacities(p) != 0) return -1;  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     p->preLooped = true;
     p->evalFirst = true;
     return 0;
@@ -891,9 +975,9 @@ int qhgb_initialize_step(qhgb_pop *p, float t) {
     // births need room: at most one baby per paired female (grown here, before the pairing scratch is filled)
     if (ensureCapacity(p, q.nAgents + q.nAgents / 2 + 1024) != 0) return -1;
     // initialize() of every action that has a priority, in order (core/SPopulation.cpp:394-417)
-    HostAction *ver = q.find("Verhulst"), *pair = q.find("RandomPair"), *ev = q.find("SingleEvaluator[Alt]");
-    bool doVer = ver && ver->prio >= 0 && ver->enabled;
-    if (doVer && !(q.A("Verhulst_K", 0) != 0)) return fail("Verhulst: Verhulst_K is not set");
+    HostAction *pair = q.find("RandomPair"), *ev = q.find("SingleEvaluator[Alt]");
+    bool doVer = q.active(A_VERHULST) || q.active(A_VERHULSTVARK);
+    if (q.active(A_VERHULST) && !(q.A("Verhulst_K", 0) != 0)) return fail("Verhulst: Verhulst_K is not set");
     if (resetCellCounters(p, doVer) != 0) return -1;
     // pairing (RandomPair::initialize) is fused into the decide pass of finalizeStep; ensurePairing() runs it
     // stand-alone if the host looks at the mates before that
@@ -904,6 +988,7 @@ int qhgb_initialize_step(qhgb_pop *p, float t) {
         q.evalFirst = false;
         if (computeWeights(p) != 0) return -1;
     }
+    if (q.active(A_MULTIEVAL) && computeMultiWeights(p) != 0) return -1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -928,6 +1013,7 @@ int qhgb_finalize_step(qhgb_pop *p) {
     if (q.nAgents + q.nAgents / 2 + 1024 > q.capacity) return fail("qhgb_finalize_step: agent buffers too small");
     HostAction *ev = q.find("SingleEvaluator[Alt]");
     if (ev && ev->prio >= 0 && ev->enabled) q.evalNeedUpdate = false;  // SingleEvaluator::finalize, :125-130
+    if (q.active(A_MULTIEVAL)) for (auto &e : q.subs) e.needUpdate = false;  // MultiEvaluator::finalize, actions/MultiEvaluator.cpp:189-195
     int rc = runPipeline(p, P, true, true, q.needPair);
     q.inStep = false;
     if (rc != 0) return rc;
@@ -981,13 +1067,22 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
         // step stay in force.  Replicated as is.
         if (p->evaluatorObserves) p->evalNeedUpdate = true;
     }
+    // NPPCapacity registers itself as an observer (actions/NPPCapacity.cpp:69) and reacts to GEO, CLIMATE and VEG (:121-131);
+    // the MultiEvaluator of tut_EnvironCapAltPop is never registered, so its weights stay as first computed
+    if (event_id == QHGB_EVENT_ID_GEO || event_id == QHGB_EVENT_ID_CLIMATE || event_id == QHGB_EVENT_ID_VEG) p->nppNeedUpdate = true;
     return 0;
 }
 
 int qhgb_flush_events(qhgb_pop *p, float t) {
     (void)t;
     if (!p) return fail("qhgb_flush_events: NULL population");
-    return 0;  // EVENT_ID_FLUSH: the evaluator recomputes at the next initialize (actions/SingleEvaluator.cpp:335-337)
+    // EVENT_ID_FLUSH: NPPCapacity recalculates now (actions/NPPCapacity.cpp:127-130); evaluators recompute at the next
+    // initialize (actions/SingleEvaluator.cpp:335-337)
+    if (p->findKind(A_NPPCAP)) {
+        CK(cudaSetDevice(p->device));
+        if (recalcCapacities(p) != 0) return -1;
+    }
+    return 0;
 }
 
 int64_t qhgb_get_num_agents_effective(qhgb_pop *p) { return p ? p->nAgents : -1; }
@@ -1073,6 +1168,15 @@ int qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d) {
     CK(cudaSetDevice(p->device));
     CK(cudaMemcpyAsync(b, p->B.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaMemcpyAsync(d, p->D.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_capacities(qhgb_pop *p, double *out) {
+    if (!p || !out) return fail("qhgb_get_capacities: NULL argument");
+    if (!p->cap.p) return fail("qhgb_get_capacities: population [%s] has no NPPCapacity", p->popClass.c_str());
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(out, p->cap.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }

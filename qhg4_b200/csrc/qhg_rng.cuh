@@ -139,4 +139,28 @@ __device__ __forceinline__ double atan_rn(double x) {
     return neg ? -r : r;
 }
 
+// exp in double for the Miami NPP model (core/NPPCalcMiami.cpp:28-42): reduction by ln2 in two pieces + degree-5
+// polynomial in r^2 (fdlibm scheme), explicitly rounded, identical operation order in oracle/qhg_oracle.cpp::exp_portable.
+// Valid for |x| < 700 (the model's arguments stay within [-100, 100]).
+__device__ __forceinline__ double exp_rn(double x) {
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+    const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (fabs(x) < 3.725290298461914e-9) return __dadd_rn(1.0, x);  // 2^-28
+    const int k = (int)__dadd_rn(__dmul_rn(invln2, x), (x < 0 ? -0.5 : 0.5));  // truncation toward zero, as the C cast
+    const double t = (double)k;
+    const double hi = __dadd_rn(x, -__dmul_rn(t, ln2HI)), lo = __dmul_rn(t, ln2LO);
+    const double rr = __dadd_rn(hi, -lo);
+    const double tt = __dmul_rn(rr, rr);
+    double pp = P5;
+    pp = __dadd_rn(P4, __dmul_rn(tt, pp));
+    pp = __dadd_rn(P3, __dmul_rn(tt, pp));
+    pp = __dadd_rn(P2, __dmul_rn(tt, pp));
+    pp = __dadd_rn(P1, __dmul_rn(tt, pp));
+    const double c = __dadd_rn(rr, -__dmul_rn(tt, pp));
+    if (k == 0) return __dadd_rn(1.0, -__dadd_rn(__ddiv_rn(__dmul_rn(rr, c), __dadd_rn(c, -2.0)), -rr));
+    const double y = __dadd_rn(1.0, -__dadd_rn(__dadd_rn(lo, -__ddiv_rn(__dmul_rn(rr, c), __dadd_rn(2.0, -c))), -hi));
+    return ldexp(y, k);
+}
+
 }  // namespace qhg

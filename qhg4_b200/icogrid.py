@@ -147,3 +147,22 @@ def synthetic_population(n_agents: int, altitude: np.ndarray, seed: int = 1, t0:
         last_birth=np.full(n_agents, -10.0 if fertile else -1.0, dtype=np.float32),
         life=life,
     )
+
+
+def synthetic_climate(xyz: np.ndarray, altitude: np.ndarray, seed: int = 1) -> dict:
+    """Smooth synthetic fields for the arrays NPPCapacity reads (actions/NPPCapacity.cpp:138-217): latitude and
+    longitude in degrees, annual mean temperature (deg C), annual rainfall (mm), base NPP (kgC/m2/y), river water and
+    a coastal flag (land cell with a sea neighbour is approximated by low altitude)."""
+    rng = np.random.default_rng(seed)
+    lat = np.degrees(np.arcsin(np.clip(xyz[:, 2], -1, 1)))
+    lon = np.degrees(np.arctan2(xyz[:, 1], xyz[:, 0]))
+    d = rng.normal(size=3); d /= np.linalg.norm(d)
+    wave = np.cos(3 * np.pi * (xyz @ d))
+    temp = 28.0 - 0.45 * np.abs(lat) - 0.0065 * np.maximum(altitude, 0) + 2.0 * wave
+    rain = np.maximum(0.0, 1800.0 * np.cos(np.radians(lat)) ** 2 + 500.0 * wave)
+    npp = np.maximum(0.0, 0.9 * np.cos(np.radians(lat)) ** 1.5 + 0.25 * wave) * (altitude > 0)
+    npp[(lon > 115) & (lon < 150) & (lat > -12) & (lat < 1)] *= 0.0   # the Oceania box falls back to the Miami model
+    water = (rng.random(len(xyz)) < 0.05) * rng.random(len(xyz)) * (altitude > 0)
+    coastal = ((altitude > 0) & (altitude < 60)).astype(np.float64)
+    return {"Latitude": lat, "Longitude": lon, "AnnualMeanTemp": temp, "AnnualRainfall": rain, "BaseNPP": npp,
+            "Water": water, "Coastal": coastal}

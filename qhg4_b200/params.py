@@ -17,6 +17,10 @@ import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 
 
+def base_is_multi(name: str) -> bool:
+    return name.startswith("MultiEvaluator")
+
+
 @dataclass
 class PopParams:
     class_name: str
@@ -34,7 +38,16 @@ class PopParams:
             else:
                 out.append(f'  <module name="{name}">')
             for k, v in pars.items():
+                if base_is_multi(name) and k == "AltPref":
+                    continue
                 out.append(f'    <param name="{k}" value="{v}"/>')
+            if base_is_multi(name):  # tutorial_data/xmldat/tut_EnvironCapAlt.xml: the evaluators are sub-modules
+                out.append('    <module name="SingleEvaluator" id="Alt">')
+                if "AltPref" in pars:
+                    out.append(f'      <param name="AltPref" value="{pars["AltPref"]}"/>')
+                out.append("    </module>")
+                out.append('    <module name="SingleEvaluator" id="NPP">')
+                out.append("    </module>")
             out.append("  </module>")
         out.append("  <priorities>")
         for name, p in self.prios.items():
@@ -59,7 +72,7 @@ class PopParams:
                     name = m.get("name")
                     if m.get("id"):
                         name = f'{name}[{m.get("id")}]'
-                    pp.modules[name] = {p.get("name"): p.get("value") for p in m.findall("param")}
+                    pp.modules[name] = {p.get("name"): p.get("value") for p in m.iter("param")}
                 pr = c.find("priorities")
                 if pr is not None:
                     for p in pr.findall("prio"):
@@ -85,6 +98,26 @@ def tut_environ_alt(K: float = 20.0) -> PopParams:
         },
         prios={"GetOld": 1, "ATanDeath": 2, "WeightedMove": 3, "SingleEvaluator[Alt]": 4,
                "Fertility": 5, "RandomPair": 6, "Verhulst": 7},
+    )
+
+
+def tut_environ_cap_alt() -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_EnvironCapAlt.xml` (values restated)."""
+    return PopParams(
+        "tut_EnvironCapAltPop",
+        modules={
+            "ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"},
+            "WeightedMove": {"WeightedMove_prob": "0.07"},
+            "Fertility": {"Fertility_interbirth": "2.0", "Fertility_max_age": "50.0", "Fertility_min_age": "15.0"},
+            "NPPCapacity": {"NPPCap_K_max": "38.4716796875", "NPPCap_K_min": "0.0", "NPPCap_NPP_max": "1.0576171875",
+                            "NPPCap_NPP_min": "0.0", "NPPCap_coastal_factor": "0.4", "NPPCap_coastal_max_latitude": "66.0",
+                            "NPPCap_coastal_min_latitude": "50.0", "NPPCap_water_factor": "0.5349609375", "NPPCap_efficiency": "1"},
+            "MultiEvaluator[NPP+Alt]": {"Multi_weight_alt": "0.2", "Multi_weight_npp": "0.8",
+                                        "AltPref": "-0.1 0 0.1 0.01 1500 1.0 2000 1 3000 -9999"},
+            "VerhulstVarK": {"Verhulst_b0": "0.8", "Verhulst_d0": "0.001", "Verhulst_theta": "0.1"},
+        },
+        prios={"NPPCapacity": 1, "GetOld": 2, "ATanDeath": 3, "WeightedMove": 4, "MultiEvaluator[NPP+Alt]": 5,
+               "Fertility": 6, "RandomPair": 7, "VerhulstVarK": 8},
     )
 
 

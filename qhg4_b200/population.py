@@ -40,11 +40,13 @@ class GpuPopulation:
 
     # ---- construction helpers ---------------------------------------------------------------
     @classmethod
-    def from_params(cls, params: PopParams, nbr, altitude, ice=None, state16=None, device=0, capacity_hint=0):
+    def from_params(cls, params: PopParams, nbr, altitude, ice=None, state16=None, device=0, capacity_hint=0, env=None):
         pop = cls(params.class_name, nbr, device=device, capacity_hint=capacity_hint)
         pop.set_env("Altitude", altitude)
         if ice is not None:
             pop.set_env("Ice", ice)
+        for k, v in (env or {}).items():
+            pop.set_env(k, v)
         pop.read_species_data(params)
         if state16 is not None:
             pop.set_seed(state16)
@@ -153,6 +155,11 @@ class GpuPopulation:
         b, d = np.zeros(self.ncells), np.zeros(self.ncells)
         check(self.L.qhgb_get_birth_death_probs(self.h, _p(b), _p(d)), "qhgb_get_birth_death_probs")
         return b, d
+
+    def capacities(self):
+        out = np.zeros(self.ncells)
+        check(self.L.qhgb_get_capacities(self.h, _p(out)), "qhgb_get_capacities")
+        return out
 
     def atan_prob(self, age):
         age = np.ascontiguousarray(age, np.float32)

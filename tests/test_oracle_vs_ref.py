@@ -88,3 +88,42 @@ def test_counter_mode_statistically_equivalent_to_reference():
     assert stats.ks_2samp(tot_o, tot_r).pvalue > 0.01
     assert stats.ks_2samp(np.concatenate(age_o)[::5], np.concatenate(age_r)[::5]).pvalue > 0.01
     assert stats.ks_2samp(np.concatenate(occ_o), np.concatenate(occ_r)).pvalue > 0.01
+
+
+def _cap_world(seed=2):
+    from qhg4_b200.icogrid import synthetic_climate
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=seed)
+    return nbr, xyz, alt, synthetic_climate(xyz, alt, seed=seed + 1)
+
+
+def test_cap_alt_population_equals_reference():
+    """tut_EnvironCapAltPop: NPPCapacity (Miami NPP, ramps, bonuses), MultiEvaluator[NPP+Alt] (double cumulation),
+    VerhulstVarK -- WELL mode against the reference with one thread, incl. a climate event + flush."""
+    from qhg4_b200.params import tut_environ_cap_alt
+    nbr, xyz, alt, env = _cap_world()
+    pop = synthetic_population(9000, alt, seed=4, fertile=True)
+    par = tut_environ_cap_alt()
+    r = refsim.RefSim(par, nbr, alt, threads=1, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, env=env)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    assert np.array_equal(r.capacities(), o.capacities()) and r.capacities().max() > 10
+    for k in range(8):
+        r.step(float(k)); o.step(float(k))
+    assert np.array_equal(r.weights(), o.weights())
+    # the climate gets colder and drier: capacities change on the flush, weights do not (the evaluator is not an observer)
+    env2 = dict(env, AnnualMeanTemp=env["AnnualMeanTemp"] - 6.0, AnnualRainfall=env["AnnualRainfall"] * 0.6, BaseNPP=env["BaseNPP"] * 0.7)
+    for name in ("AnnualMeanTemp", "AnnualRainfall", "BaseNPP"):
+        r.set_env(name, env2[name]); o.set_env(name, env2[name])
+    r.event(3, 8.0, flush=False); r.event(4, 8.0, flush=True)
+    o.update_event(3, 8.0); o.update_event(4, 8.0); o.flush_events(8.0)
+    assert np.array_equal(r.capacities(), o.capacities())
+    for k in range(8, 16):
+        r.step(float(k)); o.step(float(k))
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+    rb, rd = r.bd(); ob, od = o.bd()
+    assert np.array_equal(rb, ob) and np.array_equal(rd, od) and np.array_equal(r.weights(), o.weights())
+    r.close()

@@ -248,3 +248,56 @@ def test_two_gpu_shards_equal_unsharded_oracle():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _cap_world(S=15, seed=2):
+    from qhg4_b200.icogrid import synthetic_climate
+    nbr, xyz = make_ico_grid(S)
+    alt = synthetic_altitude(xyz, seed=seed)
+    return nbr, xyz, alt, synthetic_climate(xyz, alt, seed=seed + 1)
+
+
+def test_cap_alt_population_vs_oracle_and_reference(path):
+    """tut_EnvironCapAltPop (NPPCapacity, MultiEvaluator[NPP+Alt], VerhulstVarK): capacities / weights / b,d bit-exact
+    against the oracle and within 1e-6 of the reference; trajectory bit-exact against the oracle, incl. climate events."""
+    from oracle import port, refsim
+    from qhg4_b200.params import tut_environ_cap_alt
+    from qhg4_b200.population import GpuPopulation
+    nbr, xyz, alt, env = _cap_world()
+    pop = synthetic_population(40000, alt, seed=4, fertile=True)
+    par, st = tut_environ_cap_alt(), seed_state(17)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    g.add_agents(pop); o.add_agents(pop)
+    g.pre_loop(); o.start()
+    assert np.array_equal(g.capacities(), o.capacities())
+    if refsim.available():
+        r = refsim.RefSim(par, nbr, alt, threads=2, env=env)
+        r.add_agents(pop); r.start()
+        np.testing.assert_allclose(g.capacities(), r.capacities(), rtol=1e-6, atol=1e-12)
+        g.initialize_step(0.0); r.step(0.0)
+        np.testing.assert_allclose(g.weights(), r.weights(), rtol=1e-6, atol=1e-12)
+        gb, gd = g.bd(); rb, rd = r.bd()
+        np.testing.assert_allclose(gb, rb, rtol=1e-6); np.testing.assert_allclose(gd, rd, rtol=1e-6)
+        for lvl in sorted(set(g.prios.values())):
+            g.do_actions(lvl, 0.0)
+        g.finalize_step(); o.step(0.0)
+        r.close()
+    else:
+        g.step(0.0); o.step(0.0)
+    assert_same_population(g, o, 0)
+    for k in range(1, 10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+    env2 = dict(env, AnnualMeanTemp=env["AnnualMeanTemp"] - 6.0, AnnualRainfall=env["AnnualRainfall"] * 0.6, BaseNPP=env["BaseNPP"] * 0.7)
+    for name in ("AnnualMeanTemp", "AnnualRainfall", "BaseNPP"):
+        g.set_env(name, env2[name]); o.set_env(name, env2[name])
+    g.update_event(3, 10.0); g.update_event(4, 10.0); g.flush_events(10.0)
+    o.update_event(3, 10.0); o.update_event(4, 10.0); o.flush_events(10.0)
+    assert np.array_equal(g.capacities(), o.capacities())
+    for k in range(10, 18):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+    assert np.array_equal(g.weights(), o.weights())
+    gb, gd = g.bd(); ob, od = o.bd()
+    assert np.array_equal(gb, ob) and np.array_equal(gd, od)
