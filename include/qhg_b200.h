@@ -95,6 +95,15 @@ int     qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64
 int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
                         uint8_t *gender, float *age, float *last_birth, uint32_t *life_state, int64_t *mate_id);
 
+/* genomes of populations with Genetics<.., BitGeneUtils> (actions/Genetics.cpp:196-267,285-337; genes/BitGeneUtils.cpp):
+ * 2 strands x ceil(Genetics_genome_size/64) 64-bit words per agent, 1 bit per nucleotide.
+ * qhgb_set_genomes = what readAgentDataQDF + SequenceIOUtils load beside the agents (actions/Genetics.cpp "readAdditionalDataQDF"):
+ *                    one row per agent added so far, in the order of qhgb_add_agents; before qhgb_pre_loop; rows never set are zero.
+ * qhgb_get_genomes = what writeAdditionalDataQDF writes: one row per live agent in the order of qhgb_get_agents, plus
+ *                    m_iNumBabies (populations/OoANavGenPop.h:21-27).  Returns the number of live agents, or -1. */
+int     qhgb_set_genomes(qhgb_pop *p, int64_t n, const uint64_t *genomes);
+int64_t qhgb_get_genomes(qhgb_pop *p, int64_t cap, uint64_t *genomes, int32_t *num_babies);
+
 /* ---- the step (PopBase virtuals called by PopLooper::doStep, core/PopLooper.cpp:166-202) -----------
  * qhgb_pre_loop        = PopBase::preLoop (core/SPopulation.cpp:273-292): uploads are sealed, agents are binned
  *                        per cell, per-cell counts and derived parameters are computed.

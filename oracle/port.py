@@ -57,6 +57,9 @@ def lib():
         L.qor_get_birth_death_probs.argtypes = [vp, vp, vp]
         L.qor_atan_death_prob.argtypes = [vp, i32, vp, vp]
         L.qor_get_capacities.argtypes = [vp, vp]
+        L.qor_set_genomes.argtypes = [vp, i64, vp]
+        L.qor_get_genomes.restype = i64
+        L.qor_get_genomes.argtypes = [vp, i64, vp, vp]
         L.qor_get_step_stats.argtypes = [vp, vp, vp, vp]
         L.qor_get_pending_births.restype = i64
         L.qor_get_pending_births.argtypes = [vp]
@@ -165,6 +168,17 @@ class OraclePop:
         out = np.zeros(self.ncells)
         assert lib().qor_get_capacities(self.h, _p(out)) == 0
         return out
+
+    def set_genomes(self, genomes):
+        g = np.ascontiguousarray(genomes, np.uint64)
+        assert lib().qor_set_genomes(self.h, g.shape[0], _p(g)) == 0
+
+    def genomes(self, row_words):
+        n = self.num_agents()
+        g = np.zeros((n, row_words), np.uint64)
+        nb = np.zeros(n, np.int32)
+        assert lib().qor_get_genomes(self.h, n, _p(g), _p(nb)) == n
+        return g, nb
 
     def enable_action(self, name, on=True):
         return lib().qor_enable_action(self.h, name.encode(), int(on))

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <numbers>
 #include <queue>
 #include <string>
@@ -175,6 +176,123 @@ struct PolyLine {
 };
 
 // ---------------------------------------------------------------------------------------------
+// genome primitives for 1-bit nucleotides (genes/BitGeneUtils.cpp), generic over the source of 32-bit draws so that
+// WELL mode (draws = consecutive words of one WELL512, the reference's call order) and counter mode share them.
+typedef std::function<uint32_t()> NextU32;
+
+// genes/BitGeneUtils.cpp:86-106.  The break list is used in the order given (the reference never sorts it,
+// SURVEY.md §7 "crossover break lists per block are not sorted although makeMultiMask assumes sorted").
+inline uint64_t makeMultiMask(const std::vector<uint32_t> &br) {
+    uint32_t k = 1 - (uint32_t)(br.size() % 2);
+    uint64_t out = 0;
+    int i = (int)br.size() - 1;
+    for (uint32_t j = 0; j < 64; j++) {
+        if (i >= 0 && j == 64 - br[i]) { i--; k = 1 - k; }
+        out = (out << 1) + k;
+    }
+    return out;
+}
+
+// genes/BitGeneUtils.cpp:116-186: out (2 strands x nBlocks) = in with its two strands crossed over at nCross random bits
+inline void bitCrossOver(uint64_t *out, const uint64_t *in, int G, int nCross, const NextU32 &next) {
+    const uint32_t nBlocks = (uint32_t)((G + 63) / 64), nBits = nBlocks * 64;
+    std::map<uint32_t, std::vector<uint32_t>> blockBreaks;
+    for (int i = 0; i < nCross; i++) {
+        uint32_t pos = u2int(next(), 0, nBits);  // wrandi(0, nBits, BITSINNUC = 1)
+        blockBreaks[pos / 64].push_back(pos % 64);
+    }
+    uint32_t last = 0, S = 0;
+    int cur = 0;
+    for (auto &kv : blockBreaks) {
+        const uint32_t b = kv.first;
+        cur = S % 2;
+        for (uint32_t q = last; q < b; q++) { out[q] = in[cur * nBlocks + q]; out[nBlocks + q] = in[(1 - cur) * nBlocks + q]; }
+        const uint64_t L = makeMultiMask(kv.second), R = ~L;
+        out[b] = (L & in[cur * nBlocks + b]) | (R & in[(1 - cur) * nBlocks + b]);
+        out[b + nBlocks] = (L & in[(1 - cur) * nBlocks + b]) | (R & in[cur * nBlocks + b]);
+        S += (uint32_t)kv.second.size();
+        last = b + 1;
+    }
+    if (nBlocks > last) {
+        cur = S % 2;
+        for (uint32_t q = last; q < nBlocks; q++) { out[q] = in[cur * nBlocks + q]; out[nBlocks + q] = in[(1 - cur) * nBlocks + q]; }
+    }
+}
+
+// genes/BitGeneUtils.cpp:190-220: every block gets an independent random 64-bit mask (two 32-bit draws, high word first)
+inline void bitFreeReco(uint64_t *out, const uint64_t *in, int nBlocks, const NextU32 &next) {
+    for (int b = 0; b < nBlocks; b++) {
+        const uint64_t hi = next(), lo = next();
+        const uint64_t L = (hi << 32) + lo, R = ~L;
+        out[b] = (L & in[b]) | (R & in[nBlocks + b]);
+        out[b + nBlocks] = (L & in[nBlocks + b]) | (R & in[b]);
+    }
+}
+
+// genes/BitGeneUtils.cpp:57-75: flip nMut random bits of the first nBits bits
+inline void bitMutate(uint64_t *g, int nBits, int nMut, const NextU32 &next) {
+    for (int i = 0; i < nMut; i++) {
+        uint32_t pos = u2int(next(), 0, (uint32_t)nBits);
+        g[pos / 64] ^= (uint64_t)1 << (pos % 64);
+    }
+}
+
+// utils/bino_tools.cpp (the classic log-gamma series and continued fraction of the incomplete beta function)
+inline double gammaln_(double xx) {
+    static const double co[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5};
+    double ser = 1.000000000190015, x = xx, y = xx + 1, tmp = x + 5.5;
+    tmp -= (x + 0.5) * log(tmp);
+    for (int k = 0; k <= 5; k++) { ser += co[k] / y; y++; }
+    return -tmp + log(2.5066282746310005 * ser / x);
+}
+inline double betacf_(double a, double b, double x) {
+    const double EPSB = 3.0e-7; const float FMIN = 1.0e-30f;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0, c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < FMIN) d = FMIN;
+    d = 1.0 / d;
+    double h = d;
+    int m;
+    for (m = 1; m <= 100; m++) {
+        int m2 = 2 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < FMIN) d = FMIN;
+        c = 1.0 + aa / c; if (fabs(c) < FMIN) c = FMIN;
+        d = 1.0 / d; h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < FMIN) d = FMIN;
+        c = 1.0 + aa / c; if (fabs(c) < FMIN) c = FMIN;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < EPSB) break;
+    }
+    if (m > 100) h = -1;
+    return h;
+}
+inline double ibeta_(double a, double b, double x) {
+    if (x < 0.0 || x > 1.0) return -1;
+    double bt = (x == 0.0 || x == 1.0) ? 0.0 : exp(gammaln_(a + b) - gammaln_(a) - gammaln_(b) + a * log(x) + b * log(1.0 - x));
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf_(a, b, x) / a;
+    return 1.0 - bt * betacf_(b, a, 1.0 - x) / b;
+}
+// utils/BinomialDist.cpp:61-87: table[k] = 1 - I_p(k+1, n-k) until the tail drops below eps; getN(r) = first k with r <= table[k]
+inline std::vector<double> binomialTable(double prob, int n, double eps) {
+    std::vector<double> v;
+    int k = 1;
+    double d2 = ibeta_(k, n - k + 1, prob);
+    while (d2 > eps && k < n) { v.push_back(d2); k++; d2 = ibeta_(k, n - k + 1, prob); }
+    v.push_back(d2);
+    for (auto &x : v) x = 1 - x;
+    return v;
+}
+inline int binomialGetN(const std::vector<double> &t, double r) {  // utils/BinomialDist.cpp:92-103
+    if (!(r >= 0)) return -1;
+    size_t i = 0;
+    while (i < t.size() && r > t[i]) i++;
+    return (int)i;
+}
+
+// ---------------------------------------------------------------------------------------------
 struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16-21
     uint32_t life = 0;
     int32_t cell = -1;
@@ -184,16 +302,21 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
     float age = 0;
     float lastBirth = 0;
     int32_t mate = -3;
+    int32_t numBabies = 0;          // populations/OoANavGenPop.h:21-27
+    std::vector<uint64_t> genome;   // 2 strands x nBlocks (actions/Genetics.cpp keeps them in a LayerArrBuf beside the agents)
 };
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
     std::string input;      // environment array it evaluates ("Altitude") or "" for the capacities array
     std::string weightName; // name of its combination weight attribute
     bool usePoly = false;
+    int trigger = 0;        // event id that makes it recompute (EVENT_ID_GEO / EVENT_ID_VEG)
+    PolyLine poly;
+    std::string polyName;
     bool first = true, needUpdate = false;
     double weight = 0;
 };
@@ -228,7 +351,11 @@ struct qor_pop {
     bool nppNeedUpdate = true;
     std::vector<double> cap;      // m_adCapacities
     std::vector<SubEval> subs;    // evaluators of the MultiEvaluator, in construction order
-    bool multiFirst = true;
+    bool multiFirst = true, multiObserves = false;
+    // Genetics<.., BitGeneUtils> (actions/Genetics.cpp)
+    int genomeSize = 0, numCrossOvers = 0, nBlocks = 0;
+    double mutationRate = 0;
+    std::vector<double> binoTable;
 
     // evaluator state (actions/SingleEvaluator.cpp:138-167,332-346)
     bool evalFirst = true, evalNeedUpdate = false;
@@ -361,7 +488,7 @@ struct qor_pop {
         for (int c = 0; c < nCells; c++) {
             double v = 0;
             if (!ice || (*ice)[c] == 0) {
-                double dv = e.usePoly ? altPref.val((float)in[c]) : in[c];
+                double dv = e.usePoly ? (e.polyName.empty() ? altPref : e.poly).val((float)in[c]) : in[c];
                 v = (dv > 0) ? dv : 0;
             }
             out[(size_t)c * stride] = v;
@@ -554,6 +681,8 @@ struct qor_pop {
         case A_SINGLEEVAL:
         case A_MULTIEVAL:
         case A_NPPCAP:
+        case A_GENETICS:
+        case A_NAVIGATE:
         case A_RANDOMPAIR:
             break;  // execute() is empty for these (actions/Action.h:36 default)
         }
@@ -610,6 +739,43 @@ struct qor_pop {
         b.age = 0.0f;
         b.lastBirth = 0.0f;
         b.mate = -3;
+        b.numBabies = 0;
+    }
+
+    // Genetics::makeOffspring (actions/Genetics.cpp:285-337) under the counter-mode law: every draw is a word of
+    // Philox(child id, step, stream) -- stream 4: strand choices and mutation count; 0x01000000|parent<<20|block/2: free
+    // recombination masks; 0x02000000|parent<<20|i/4: crossover breaks; 0x03000000|i/4: mutation positions
+    void makeGenome(int babySlot, int64_t cid, int mother, int father) {
+        const int nb = nBlocks;
+        std::vector<uint64_t> out(2 * nb, 0), t1(2 * nb), t2(2 * nb);
+        uint32_t g0[4];
+        draw4(cid, 4, g0);
+        const int i1 = (int)(2 * 1.0 * u2d(g0[0])), i2 = (int)(2 * 1.0 * u2d(g0[1]));
+        const std::vector<uint64_t> &gm = slots[mother].genome, &gf = slots[father].genome;
+        auto words = [&](uint32_t base) {
+            auto state = std::make_shared<std::pair<uint32_t, std::vector<uint32_t>>>(0u, std::vector<uint32_t>());
+            return NextU32([this, cid, base, state]() {
+                uint32_t i = state->first++;
+                uint32_t o[4];
+                draw4(cid, base | (i / 4), o);
+                return o[i % 4];
+            });
+        };
+        if (numCrossOvers > 0) {
+            bitCrossOver(t1.data(), gm.data(), genomeSize, numCrossOvers, words(0x02000000u | (0u << 20)));
+            bitCrossOver(t2.data(), gf.data(), genomeSize, numCrossOvers, words(0x02000000u | (1u << 20)));
+        } else if (numCrossOvers == -1) {
+            bitFreeReco(t1.data(), gm.data(), nb, words(0x01000000u | (0u << 20)));
+            bitFreeReco(t2.data(), gf.data(), nb, words(0x01000000u | (1u << 20)));
+        } else {
+            t1 = gm; t2 = gf;
+        }
+        for (int q = 0; q < nb; q++) { out[q] = t1[i1 * nb + q]; out[nb + q] = t2[i2 * nb + q]; }
+        if (mutationRate > 0) {
+            int nMut = binomialGetN(binoTable, u2d(g0[2]));
+            if (nMut > 0) bitMutate(out.data(), 2 * genomeSize, nMut, words(0x03000000u));
+        }
+        slots[babySlot].genome = out;
     }
 
     // core/SPopulation.cpp:596-724 recycleDeadSpaceNew (+ performBirths :778-815, performDeaths :974-989)
@@ -645,6 +811,10 @@ struct qor_pop {
                 g = o[0];
             }
             makeBaby(slot, birthList[3 * k], id, g);
+            if (find("Genetics")) {  // populations/OoANavGenPop.cpp:231-245 makePopSpecificOffspring
+                makeGenome(slot, id, birthList[3 * k + 1], birthList[3 * k + 2]);
+                slots[birthList[3 * k + 1]].numBabies++;
+            }
         };
         for (size_t k = 0; k < nReuse; k++) born(prevDead[k], k);          // babies into last step's dead slots
         for (size_t k = nReuse; k < nBirths; k++) born(allocSlot(), k);     // remaining births: lowest free index
@@ -704,6 +874,9 @@ struct qor_pop {
         // NPPCapacity registers itself as an observer (actions/NPPCapacity.cpp:69) and reacts to GEO, CLIMATE and VEG (:121-131);
         // the MultiEvaluator of tut_EnvironCapAltPop is never registered, so its weights stay as first computed
         if (ev == 2 || ev == 3 || ev == 4) nppNeedUpdate = true;
+        // OoANavGenPop registers its MultiEvaluator (populations/OoANavGenPop.cpp:59), which forwards the event to its
+        // evaluators (actions/MultiEvaluator.cpp:203-214): each one reacts to its own trigger id
+        if (multiObserves) for (auto &e : subs) if (e.trigger == ev) e.needUpdate = true;
         return 0;
     }
 };
@@ -731,6 +904,18 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false;
         p->subs = {ea, en};
+        p->cap.assign(n_cells, 0.0);
+        for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
+            p->env[nm].assign(n_cells, 0.0);
+    } else if (p->popClass == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97 (Navigate is registered but unsupported)
+        if (mode != QOR_MODE_COUNTER) { delete p; return nullptr; }  // the genome draws only exist under the counter-mode law
+        p->actions = {{"MultiEvaluator[Alt+NPP]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}, {"VerhulstVarK", A_VERHULSTVARK},
+                      {"RandomPair", A_RANDOMPAIR}, {"GetOld", A_GETOLD}, {"OldAgeDeath", A_OLDAGEDEATH}, {"Fertility", A_FERTILITY},
+                      {"NPPCapacity", A_NPPCAP}, {"Genetics", A_GENETICS}, {"Navigate", A_NAVIGATE}};
+        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltCapPref"; ea.trigger = EVENT_ID_GEO;
+        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = true; en.polyName = "NPPPref"; en.trigger = 4;
+        p->subs = {ea, en};
+        p->multiObserves = true;  // addObserver(m_pME), populations/OoANavGenPop.cpp:59
         p->cap.assign(n_cells, 0.0);
         for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
             p->env[nm].assign(n_cells, 0.0);
@@ -789,12 +974,20 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "NPPCap_K_max") p->nppKMax = v;
     else if (s == "NPPCap_K_min") p->nppKMin = v;
     else if (s == "NPPCap_efficiency") p->nppEff = v;
+    else if (s == "Genetics_genome_size") { p->genomeSize = (int)v; p->nBlocks = ((int)v + 63) / 64; }
+    else if (s == "Genetics_num_crossover") p->numCrossOvers = (int)v;
+    else if (s == "Genetics_mutation_rate") p->mutationRate = v;
+    else if (s == "Genetics_create_new_genome" || s == "Genetics_bits_per_nuc") { if (s == "Genetics_bits_per_nuc" && (int)v != 1) return -1; }
     else if (s == "Multi_weight_alt" || s == "Multi_weight_npp") { for (auto &e : p->subs) if (e.weightName == s) e.weight = v; }
     else return -1;
     return 0;
 }
 
 int qor_set_attribute_str(qor_pop *p, const char *name, const char *v) {
+    for (auto &e : p->subs) {
+        if (!e.polyName.empty() && e.polyName == name) return e.poly.parse(v) ? 0 : -1;
+    }
+    if (std::string(name) == "Genetics_initial_muts") return 0;  // genomes are supplied by the host (qor_set_genomes)
     if (std::string(name) == "AltCapPref" || std::string(name) == "AltPref") {
         p->havePoly = p->altPref.parse(v);
         return p->havePoly ? 0 : -1;
@@ -852,6 +1045,11 @@ int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDe
     p->atanScale = (PI / 2 - ATAN_EPS) / atan(p->atanSlope * p->atanRange);
     p->nextID = p->maxID + 1;
     p->updateNumAgentsPerCell();
+    if (p->find("Genetics")) {  // Genetics::init, actions/Genetics.cpp:196-267
+        if (p->genomeSize <= 0) return -1;
+        if (p->mutationRate > 0) p->binoTable = binomialTable(p->mutationRate, 2 * p->genomeSize, 1e-6);
+        for (auto &a : p->slots) if (a.genome.empty()) a.genome.assign(2 * p->nBlocks, 0);
+    }
     if (p->find("NPPCapacity")) p->nppRecalculate();  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     return 0;
 }
@@ -905,6 +1103,52 @@ int qor_get_birth_death_probs(qor_pop *p, double *b, double *d) {
     memcpy(d, p->D.data(), sizeof(double) * p->nCells);
     return 0;
 }
+
+// genomes of the agents added so far, in add order (2*nBlocks words each); call after qor_add_agents
+int qor_set_genomes(qor_pop *p, int64_t n, const uint64_t *g) {
+    if (p->nBlocks <= 0 || n != (int64_t)p->slots.size()) return -1;
+    const size_t row = 2 * (size_t)p->nBlocks;
+    for (int64_t i = 0; i < n; i++) p->slots[i].genome.assign(g + i * row, g + (i + 1) * row);
+    return 0;
+}
+
+// genomes and NumBabies of the live agents in the order of qor_get_agents
+int64_t qor_get_genomes(qor_pop *p, int64_t cap, uint64_t *g, int32_t *num_babies) {
+    const size_t row = 2 * (size_t)p->nBlocks;
+    int64_t k = 0;
+    for (int i = 0; i < p->hi(); i++) {
+        if (!p->active[i] || p->slots[i].life == LIFE_DEAD) continue;
+        if (k < cap) {
+            if (g && p->slots[i].genome.size() == row) memcpy(g + k * row, p->slots[i].genome.data(), row * sizeof(uint64_t));
+            if (num_babies) num_babies[k] = p->slots[i].numBabies;
+        }
+        k++;
+    }
+    return k;
+}
+
+// ---- genome primitives with the reference's own draw order from ONE WELL512 (pins them against genes/BitGeneUtils.cpp) ----
+int qor_bit_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out) {
+    Well512 w; w.seed(state16);
+    bitCrossOver(out, in, genome_size, n_cross, [&w]() { return w.next(); });
+    return 0;
+}
+int qor_bit_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out) {
+    Well512 w; w.seed(state16);
+    bitFreeReco(out, in, n_blocks, [&w]() { return w.next(); });
+    return 0;
+}
+int qor_bit_mutate(const uint32_t *state16, uint64_t *genome, int n_bits, int n_mut) {
+    Well512 w; w.seed(state16);
+    bitMutate(genome, n_bits, n_mut, [&w]() { return w.next(); });
+    return 0;
+}
+int qor_binomial_table(double prob, int n, double eps, int cap, double *out) {
+    std::vector<double> t = binomialTable(prob, n, eps);
+    for (size_t i = 0; i < t.size() && (int)i < cap; i++) out[i] = t[i];
+    return (int)t.size();
+}
+int qor_binomial_get_n(double prob, int n, double eps, double r) { return binomialGetN(binomialTable(prob, n, eps), r); }
 
 int qor_get_capacities(qor_pop *p, double *out) {
     if (p->cap.empty()) return -1;

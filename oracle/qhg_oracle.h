@@ -56,6 +56,15 @@ int      qor_get_capacities(qor_pop *p, double *out);
 int      qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out);
 int      qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves);
 
+/* genomes (actions/Genetics.cpp, genes/BitGeneUtils.cpp) */
+int      qor_set_genomes(qor_pop *p, int64_t n, const uint64_t *g);
+int64_t  qor_get_genomes(qor_pop *p, int64_t cap, uint64_t *g, int32_t *num_babies);
+int      qor_bit_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out);
+int      qor_bit_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out);
+int      qor_bit_mutate(const uint32_t *state16, uint64_t *genome, int n_bits, int n_mut);
+int      qor_binomial_table(double prob, int n, double eps, int cap, double *out);
+int      qor_binomial_get_n(double prob, int n, double eps, double r);
+
 /* sharded runs: the protocol of the CUDA path's multi-GPU mode (counter mode) */
 int64_t  qor_get_pending_births(qor_pop *p);
 int      qor_set_birth_id_offset(qor_pop *p, int64_t offset, int64_t total);

@@ -33,6 +33,8 @@
 #include "ParamProvider2.h"
 #include "ArrayShare.h"
 #include "EventConsts.h"
+#include "BitGeneUtils.h"
+#include "BinomialDist.h"
 #include "Climate.h"
 #include "Vegetation.h"
 #include "tut_EnvironAltPop.h"
@@ -153,6 +155,41 @@ int qref_polyline_eval(const char *def, int n, const double *x, double *out, int
     for (int i = 0; i < n; i++) out[i] = float_cast ? pl->getVal((float)x[i]) : pl->getVal(x[i]);
     delete pl;
     return 0;
+}
+
+// ---- genome primitives (genes/BitGeneUtils.cpp:57-75,116-186,190-220; utils/BinomialDist.cpp:61-103) ----
+int qref_bit_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    BitGeneUtils::crossOver((ulong *)out, (const ulong *)in, genome_size, n_cross, &w);
+    return 0;
+}
+int qref_bit_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    BitGeneUtils::freeReco((ulong *)out, (ulong *)in, n_blocks, &w);
+    return 0;
+}
+int qref_bit_mutate(const uint32_t *state16, uint64_t *genome, int n_bits, int n_mut) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    BitGeneUtils::mutateNucs((ulong *)genome, n_bits, n_mut, &w);
+    return 0;
+}
+int qref_binomial_table(double prob, int n, double eps, int cap, double *out) {
+    BinomialDist *b = BinomialDist::create(prob, n, eps);
+    if (b == NULL) return -1;
+    int nb = (int)b->m_iNumBins;
+    for (int i = 0; i < nb && i < cap; i++) out[i] = b->m_adLookUp[i];
+    delete b;
+    return nb;
+}
+int qref_binomial_get_n(double prob, int n, double eps, double r) {
+    BinomialDist *b = BinomialDist::create(prob, n, eps);
+    if (b == NULL) return -2;
+    int k = b->getN(r);
+    delete b;
+    return k;
 }
 
 // ---- simulation ----

@@ -34,6 +34,8 @@ SYMBOLS = {
     "qhgb_set_seed": (i32, [vp, vp]),
     "qhgb_add_agents": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "qhgb_get_agents": (i64, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "qhgb_set_genomes": (i32, [vp, i64, vp]),
+    "qhgb_get_genomes": (i64, [vp, i64, vp, vp]),
     "qhgb_pre_loop": (i32, [vp]),
     "qhgb_initialize_step": (i32, [vp, f32]),
     "qhgb_do_actions": (i32, [vp, u32, f32]),

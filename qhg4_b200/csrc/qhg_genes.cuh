@@ -1,0 +1,155 @@
+// qhg_genes.cuh -- genomes on the device: Genetics<.., BitGeneUtils> (actions/Genetics.cpp, genes/BitGeneUtils.cpp).
+//
+// A genome is 2 strands x nBlocks 64-bit words of 1-bit nucleotides.  Genomes live in a pool of fixed-size rows and are
+// NOT moved when the agents are re-binned: an agent carries a 4-byte handle (row index).  Births take rows from a free
+// stack (rows of last step's dead) or from the never-used tail; deaths push their rows after all births of the step
+// have read their parents.
+//
+// Offspring law (counter mode, mirrored by oracle/qhg_oracle.cpp::makeGenome): every draw is a word of
+// Philox(child id, step, stream) -- stream 4: strand choices (x, y) and mutation count (z); 0x01000000|parent<<20|block/2:
+// free-recombination masks; 0x02000000|parent<<20|i/4: crossover break i; 0x03000000|i/4: position of mutation i.
+#pragma once
+#include "qhg_kernels.cuh"
+
+namespace qhg {
+
+constexpr int MAX_BINO = 64;    // entries of the mutation-count table (utils/BinomialDist.cpp:61-87)
+constexpr int MAX_CROSS = 32;   // crossover breaks per parent handled by one warp
+
+struct GeneParams {
+    int genomeSize, nBlocks, numCrossOvers, nBino;
+    double mutationRate;
+    double bino[MAX_BINO];
+};
+
+// genes/BitGeneUtils.cpp:86-106 with the break list in draw order (never sorted in the reference)
+__device__ __forceinline__ unsigned long long make_multi_mask(const unsigned *br, int nbr) {
+    unsigned k = 1u - (unsigned)(nbr & 1);
+    unsigned long long out = 0;
+    int i = nbr - 1;
+    for (unsigned j = 0; j < 64; j++) {
+        if (i >= 0 && j == 64u - br[i]) { i--; k = 1u - k; }
+        out = (out << 1) + k;
+    }
+    return out;
+}
+
+// one warp per birth: Genetics::makeOffspring (actions/Genetics.cpp:285-337)
+__global__ void __launch_bounds__(128)
+k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, const BirthEntry *__restrict__ births, GeneParams G,
+                 RngKey key, const int *__restrict__ oldSlot, int *__restrict__ newSlot, unsigned long long *__restrict__ pool,
+                 const int *__restrict__ freeStack) {
+    __shared__ unsigned sbr[4][2][MAX_CROSS];
+    if (st->overflow) return;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
+    const int nb = G.nBlocks, row = 2 * nb;
+    const unsigned step = st->step;
+    const unsigned FULL = 0xffffffffu;
+    for (int e = w; e < ctl->nBirths; e += nW) {
+        const BirthEntry be = births[e];
+        int slot = 0;
+        if (lane == 0) {  // a row for the baby
+            int idx = atomicSub(&ctl->nFree, 1) - 1;
+            slot = (idx >= 0) ? freeStack[idx] : atomicAdd(&ctl->hwm, 1);
+            newSlot[be.babyPos] = slot;
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        const unsigned long long *gm = pool + (size_t)oldSlot[be.mother] * row;
+        const unsigned long long *gf = pool + (size_t)oldSlot[be.father] * row;
+        unsigned long long *gb = pool + (size_t)slot * row;
+        const uint4 g0 = agent_draws(be.cid, step, 4u, key);
+        const int i1 = (int)(g0.x >> 31), i2 = (int)(g0.y >> 31);  // (int)(2 * wrandd())
+        // crossover breaks of both parents: lane i holds break i
+        unsigned brM = 0, brF = 0;
+        const int nc = G.numCrossOvers;
+        if (nc > 0 && lane < nc) {
+            const unsigned nBits = (unsigned)nb * 64u;
+            const uint4 dm = agent_draws(be.cid, step, 0x02000000u | (0u << 20) | (unsigned)(lane / 4), key);
+            const uint4 df = agent_draws(be.cid, step, 0x02000000u | (1u << 20) | (unsigned)(lane / 4), key);
+            const unsigned wm = (lane & 3) == 0 ? dm.x : (lane & 3) == 1 ? dm.y : (lane & 3) == 2 ? dm.z : dm.w;
+            const unsigned wf = (lane & 3) == 0 ? df.x : (lane & 3) == 1 ? df.y : (lane & 3) == 2 ? df.z : df.w;
+            brM = u2int(wm, 0, nBits);
+            brF = u2int(wf, 0, nBits);
+            sbr[wl][0][lane] = brM;
+            sbr[wl][1][lane] = brF;
+        }
+        __syncwarp();
+        // mutations: count from the binomial table, lane i holds position i
+        int nMut = 0;
+        if (G.mutationRate > 0) {
+            const double r = u2d(g0.z);
+            while (nMut < G.nBino && r > G.bino[nMut]) nMut++;
+        }
+        for (int q = lane; q < row; q += 32) {
+            const int parent = (q < nb) ? 0 : 1;
+            const int b = q - parent * nb;
+            const unsigned long long *P = parent ? gf : gm;
+            const int pick = parent ? i2 : i1;
+            const unsigned long long p0 = P[b], p1 = P[nb + b];
+            unsigned long long t0 = p0, t1 = p1;
+            if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
+                const uint4 d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(b / 2), key);
+                const unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
+                t0 = (L & p0) | (~L & p1);
+                t1 = (L & p1) | (~L & p0);
+            } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
+                unsigned mine[MAX_CROSS];
+                int cnt = 0, below = 0;
+                for (int i = 0; i < nc; i++) {
+                    const unsigned pos = sbr[wl][parent][i];
+                    const int pb = (int)(pos >> 6);
+                    if (pb < b) below++;
+                    else if (pb == b) mine[cnt++] = pos & 63u;
+                }
+                const int cur = below & 1;
+                const unsigned long long c0 = cur ? p1 : p0, c1 = cur ? p0 : p1;
+                if (cnt == 0) { t0 = c0; t1 = c1; }
+                else {
+                    const unsigned long long L = make_multi_mask(mine, cnt);
+                    t0 = (L & c0) | (~L & c1);
+                    t1 = (L & c1) | (~L & c0);
+                }
+            }
+            gb[q] = pick ? t1 : t0;
+        }
+        __syncwarp();
+        // mutateNucs (genes/BitGeneUtils.cpp:57-75): flips commute, one atomic XOR per mutation
+        for (int m = lane; m < nMut; m += 32) {
+            const uint4 d = agent_draws(be.cid, step, 0x03000000u | (unsigned)(m / 4), key);
+            const unsigned wv = (m & 3) == 0 ? d.x : (m & 3) == 1 ? d.y : (m & 3) == 2 ? d.z : d.w;
+            const unsigned pos = u2int(wv, 0, 2u * (unsigned)G.genomeSize);
+            atomicXor(&gb[pos >> 6], 1ull << (pos & 63u));
+        }
+        __syncwarp();
+    }
+}
+
+// rows of the agents that died this step go back to the free stack (after the births have read their parents)
+__global__ void k_free_genomes(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, const int *__restrict__ dest,
+                               const int *__restrict__ oldSlot, int *__restrict__ freeStack) {
+    if (st->overflow) return;
+    const int n = st->nAgents;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (dest[i] < 0) {
+            freeStack[atomicAdd(&ctl->nFree, 1)] = oldSlot[i];
+        }
+    }
+}
+
+// the births may have popped more rows than the stack held (the rest came from the unused tail): clamp, reset the list
+__global__ void k_genome_ctl_reset(GenomeCtl *ctl, int clampFree, int resetBirths) {
+    if (clampFree && ctl->nFree < 0) ctl->nFree = 0;
+    if (resetBirths) ctl->nBirths = 0;
+}
+
+__global__ void k_gather_genomes(const DevStats *__restrict__ st, int row, const int *__restrict__ slot,
+                                 const unsigned long long *__restrict__ pool, unsigned long long *__restrict__ out) {
+    const int n = st->nAgents;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * row; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t a = i / row, k = i % row;
+        out[i] = pool[(size_t)slot[a] * row + k];
+    }
+}
+
+}  // namespace qhg

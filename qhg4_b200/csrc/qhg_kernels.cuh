@@ -29,7 +29,30 @@ struct AgentArrays {
     int32_t *cell;
     uint8_t *flags;
     float *age;  // only maintained when the action set does not refresh the age before it is read
+    int32_t *gslot;    // genome row of the agent (populations with Genetics), else NULL
+    int32_t *nbabies;  // m_iNumBabies (populations/OoANavGenPop.h:21-27), else NULL
 };
+
+struct BirthEntry {
+    int babyPos;   // position of the newborn in the new buffer
+    int mother;    // positions of the parents in the old buffer
+    int father;
+    int pad;
+    long long cid; // id of the newborn
+};
+
+struct GenomeCtl {
+    int nFree;     // genome rows on the free stack
+    int hwm;       // rows ever used
+    int nBirths;   // entries of the birth list this step
+    int pad;
+};
+
+__device__ __forceinline__ void record_birth(BirthEntry *births, GenomeCtl *ctl, int babyPos, int mother, int father, long long cid) {
+    BirthEntry e;
+    e.babyPos = babyPos; e.mother = mother; e.father = father; e.pad = 0; e.cid = cid;
+    births[atomicAdd(&ctl->nBirths, 1)] = e;
+}
 
 struct DevStats {
     int nAgents;   // live agents in the current buffer
@@ -522,7 +545,8 @@ __global__ void __launch_bounds__(256)
 k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const int *__restrict__ cellStart,
           const int *__restrict__ dest, const int *__restrict__ rank, const uint8_t *__restrict__ oflags,
           const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ arrive,
-          const int *__restrict__ birthBase, float t, int storeAge, RngKey key) {
+          const int *__restrict__ birthBase, float t, int storeAge, RngKey key,
+          const int *__restrict__ mate, BirthEntry *__restrict__ births, GenomeCtl *__restrict__ gctl) {
     if (st->overflow) return;
     const int n = st->nAgents;
     const unsigned step = st->step;
@@ -540,6 +564,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
             o.cell[pos] = d;
             o.flags[pos] = (uint8_t)(f & (F_MALE | F_FERTILE));
             if (storeAge) o.age[pos] = a.age[i];
+            if (a.gslot) o.gslot[pos] = a.gslot[i];
+            if (a.nbabies) o.nbabies[pos] = a.nbabies[i] + ((f & F_BORN) ? 1 : 0);  // populations/OoANavGenPop.cpp:243
         }
         if (f & F_BORN) {
             // newborn id = nextID + rank of (cell, mother id) among this step's births
@@ -558,6 +584,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
             o.cell[pos] = c;
             o.flags[pos] = (uint8_t)(g ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
             if (storeAge) o.age[pos] = 0.0f;
+            if (o.nbabies) o.nbabies[pos] = 0;
+            if (births) record_birth(births, gctl, pos, i, mate[i], cid);  // the genome is made by k_make_offspring
         }
     }
 }

@@ -7,6 +7,7 @@
 // totals.  No CPU fallback exists: every entry point that computes launches kernels from qhg_kernels.cuh.
 #include "../../include/qhg_b200.h"
 #include "qhg_cells.cuh"
+#include "qhg_genes.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -95,13 +96,15 @@ int loadNccl() {
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
     std::string input;       // environment array it evaluates, "" = the capacities array of NPPCapacity
     std::string weightName;  // attribute holding its combination weight
     bool usePoly = false;
+    std::string polyName;    // attribute holding its poly-line
+    int trigger = 0;         // event id that makes it recompute
     bool first = true, needUpdate = false;
 };
 
@@ -187,8 +190,17 @@ struct qhgb_pop {
     bool evaluatorObserves = false;  // does the population class addObserver() its evaluator?
     // tut_EnvironCapAltPop: NPPCapacity + MultiEvaluator[NPP+Alt] + VerhulstVarK (populations/tut_EnvironCapAltPop.cpp:27-72)
     std::vector<SubEval> subs;
-    bool multiFirst = true, nppNeedUpdate = true;
+    bool multiFirst = true, nppNeedUpdate = true, multiObserves = false;
     DevBuf<double> cap, Wtmp;
+    std::map<std::string, PolyLineDev> polys;
+    // Genetics<.., BitGeneUtils>: genome pool (rows are not moved by the re-binning), free stack, birth list
+    bool genetic = false;
+    GeneParams gp{};
+    DevBuf<int> gslot[2], nbabies[2], gfree;
+    DevBuf<unsigned long long> gpool;
+    DevBuf<BirthEntry> births;
+    DevBuf<GenomeCtl> gctl;
+    int64_t poolRows = 0;
     float curTime = -1;
     std::vector<unsigned> levels;
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
@@ -209,7 +221,10 @@ struct qhgb_pop {
     cudaEvent_t userEv[8] = {nullptr};
     std::vector<KernelTime> ktimes;
 
-    AgentArrays arrays(int b) { return AgentArrays{id[b].p, birth[b].p, lastBirth[b].p, cell[b].p, flags[b].p, age[b].p}; }
+    AgentArrays arrays(int b) {
+        return AgentArrays{id[b].p, birth[b].p, lastBirth[b].p, cell[b].p, flags[b].p, age[b].p, genetic ? gslot[b].p : nullptr,
+                           genetic ? nbabies[b].p : nullptr};
+    }
     HostAction *findKind(ActKind k) {
         for (auto &a : actions) if (a.kind == k) return &a;
         return nullptr;
@@ -296,6 +311,26 @@ int allocAgents(qhgb_pop *p, int64_t cap) {
         CK(regrow(q.age[b]));
         CK(regrow(q.cell[b]));
         CK(regrow(q.flags[b]));
+        if (q.genetic) {
+            CK(regrow(q.gslot[b]));
+            CK(regrow(q.nbabies[b]));
+        }
+    }
+    if (q.genetic) {  // the pool keeps its rows; the free stack its entries
+        const size_t row = 2 * (size_t)q.gp.nBlocks;
+        unsigned long long *np = nullptr;
+        CK(cudaMalloc(&np, (size_t)cap * row * sizeof(unsigned long long)));
+        if (q.gpool.p && q.poolRows > 0) CK(cudaMemcpyAsync(np, q.gpool.p, (size_t)q.poolRows * row * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, q.stream));
+        int *nf = nullptr;
+        CK(cudaMalloc(&nf, (size_t)cap * sizeof(int)));
+        if (q.gfree.p && q.poolRows > 0) CK(cudaMemcpyAsync(nf, q.gfree.p, (size_t)q.poolRows * sizeof(int), cudaMemcpyDeviceToDevice, q.stream));
+        CK(cudaStreamSynchronize(q.stream));
+        if (q.gpool.p) cudaFree(q.gpool.p);
+        if (q.gfree.p) cudaFree(q.gfree.p);
+        q.gpool.p = np; q.gpool.n = (size_t)cap * row;
+        q.gfree.p = nf; q.gfree.n = cap;
+        q.poolRows = cap;
+        CK(q.births.alloc(cap / 2 + 1024));
     }
     CK(q.mate.alloc(cap));
     CK(q.prank.alloc(cap));
@@ -456,7 +491,8 @@ int computeMultiWeights(qhgb_pop *p) {
             e.first = false;
             const double *in = e.input.empty() ? q.cap.p : (e.input == "Altitude" ? q.alt.p : q.envExtra[e.input].p);
             if (!in) return fail("No array with name [%s] found", e.input.c_str());
-            LAUNCH(p, "k_weights_own", k_weights_own, g, 256, q.nCells, in, q.haveIce ? q.ice.p : nullptr, q.poly, (e.usePoly && q.havePoly) ? 1 : 0, q.Wtmp.p);
+            const bool havePl = e.usePoly && q.polys.count(e.polyName);
+            LAUNCH(p, "k_weights_own", k_weights_own, g, 256, q.nCells, in, q.haveIce ? q.ice.p : nullptr, havePl ? q.polys[e.polyName] : q.poly, havePl ? 1 : 0, q.Wtmp.p);
             LAUNCH(p, "k_weights_cumulate", k_weights_cumulate, g, 256, q.nCells, q.nbr.p, q.Wtmp.p, 1);
         }
         LAUNCH(p, "k_multi_accumulate", k_multi_accumulate, q.gridFor((int64_t)nW), 256, nW, q.Wtmp.p, q.A(e.weightName.c_str()), q.W.p);
@@ -464,6 +500,54 @@ int computeMultiWeights(qhgb_pop *p) {
     LAUNCH(p, "k_rows_cumulate", k_rows_cumulate, g, 256, q.nCells, q.W.p);
     CK(cudaGetLastError());
     return 0;
+}
+
+// mutation-count table of Genetics (utils/BinomialDist.cpp:61-87): table[k] = 1 - I_p(k+1, n-k) until the tail is below eps;
+// the incomplete beta function by the classic log-gamma series + continued fraction (utils/bino_tools.cpp)
+double gammaLn(double xx) {
+    static const double co[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5};
+    double ser = 1.000000000190015, x = xx, y = xx + 1, tmp = x + 5.5;
+    tmp -= (x + 0.5) * log(tmp);
+    for (int k = 0; k <= 5; k++) { ser += co[k] / y; y++; }
+    return -tmp + log(2.5066282746310005 * ser / x);
+}
+double betaCf(double a, double b, double x) {
+    const double eps = 3.0e-7; const float fmin_ = 1.0e-30f;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0, c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < fmin_) d = fmin_;
+    d = 1.0 / d;
+    double h = d;
+    int m;
+    for (m = 1; m <= 100; m++) {
+        int m2 = 2 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < fmin_) d = fmin_;
+        c = 1.0 + aa / c; if (fabs(c) < fmin_) c = fmin_;
+        d = 1.0 / d; h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < fmin_) d = fmin_;
+        c = 1.0 + aa / c; if (fabs(c) < fmin_) c = fmin_;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return (m > 100) ? -1 : h;
+}
+double incBeta(double a, double b, double x) {
+    if (x < 0.0 || x > 1.0) return -1;
+    double bt = (x == 0.0 || x == 1.0) ? 0.0 : exp(gammaLn(a + b) - gammaLn(a) - gammaLn(b) + a * log(x) + b * log(1.0 - x));
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * betaCf(a, b, x) / a;
+    return 1.0 - bt * betaCf(b, a, 1.0 - x) / b;
+}
+std::vector<double> binomialTable(double prob, int n, double eps) {
+    std::vector<double> v;
+    int k = 1;
+    double d2 = incBeta(k, n - k + 1, prob);
+    while (d2 > eps && k < n) { v.push_back(d2); k++; d2 = incBeta(k, n - k + 1, prob); }
+    v.push_back(d2);
+    for (auto &x : v) x = 1 - x;
+    return v;
 }
 
 int computeWeights(qhgb_pop *p) {
@@ -611,11 +695,19 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             if (binned && ensureCells(p) != 0) return -1;
             q.needPair = doPair;
             if (ensurePairing(p) != 0) return -1;
+            if (q.genetic) LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
             LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, cellEnv(p), q.arrive.p, q.birthCount.p,
                    q.dest.p, q.rank.p, q.oflags.p);
             launchScan(p);
             LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
-                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key);
+                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key, q.mate.p,
+                   q.genetic ? q.births.p : nullptr, q.gctl.p);
+            if (q.genetic) {  // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
+                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 8, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
+                       q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
+                LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0);
+                LAUNCH(p, "k_free_genomes", k_free_genomes, ga, 256, q.dstats.p, q.gctl.p, q.dest.p, q.gslot[q.cur].p, q.gfree.p);
+            }
         }
         LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
         CK(cudaGetLastError());
@@ -670,9 +762,19 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"NPPCapacity", A_NPPCAP}};
-        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true;
-        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false;
+        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltPref"; ea.trigger = QHGB_EVENT_ID_GEO;
+        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false; en.trigger = QHGB_EVENT_ID_VEG;
         p->subs = {ea, en};
+    } else if (p->popClass == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97
+        p->actions = {{"MultiEvaluator[Alt+NPP]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}, {"VerhulstVarK", A_VERHULSTVARK},
+                      {"RandomPair", A_RANDOMPAIR}, {"GetOld", A_GETOLD}, {"OldAgeDeath", A_OLDAGEDEATH}, {"Fertility", A_FERTILITY},
+                      {"NPPCapacity", A_NPPCAP}, {"Genetics", A_GENETICS}, {"Navigate", A_NAVIGATE}};
+        SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltCapPref"; ea.trigger = QHGB_EVENT_ID_GEO;
+        SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = true; en.polyName = "NPPPref"; en.trigger = QHGB_EVENT_ID_VEG;
+        p->subs = {ea, en};
+        p->multiObserves = true;  // addObserver(m_pME), populations/OoANavGenPop.cpp:59
+        p->genetic = true;
+        p->forceGeneric = true;   // births need the identity of the father: the generic path keeps the full pairing
     } else {
         delete p;
         return fail("qhgb_create: unknown population class [%s]", pop_class);
@@ -683,7 +785,7 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
         const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
-        p->forceGeneric = e && strcmp(e, "generic") == 0;
+        p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);
     }
     size_t nc = (size_t)n_cells;
     CK(p->nbr.alloc(nc * MAXN));
@@ -711,6 +813,8 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         CK(cudaMemsetAsync(p->cap.p, 0, nc * sizeof(double), p->stream));
     }
     CK(p->dstats.alloc(1));
+    CK(p->gctl.alloc(1));
+    CK(cudaMemsetAsync(p->gctl.p, 0, sizeof(GenomeCtl), p->stream));
     CK(cudaMemsetAsync(p->count[0].p, 0, nc * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->count[1].p, 0, nc * sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->cellStart[0].p, 0, (nc + 1) * sizeof(int), p->stream));
@@ -739,6 +843,8 @@ int qhgb_destroy(qhgb_pop *p) {
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
     p->cap.release(); p->Wtmp.release();
+    for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
+    p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release();
     for (int b = 0; b < 2; b++) {
         p->id[b].release(); p->birth[b].release(); p->lastBirth[b].release(); p->age[b].release();
         p->cell[b].release(); p->flags[b].release();
@@ -810,19 +916,31 @@ static const char *const kNumericAttrs[] = {
     "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
-    "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp"};
+    "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
+    "Genetics_genome_size", "Genetics_num_crossover", "Genetics_mutation_rate", "Genetics_create_new_genome", "Genetics_bits_per_nuc"};
 
 int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
     if (!p || !name) return fail("qhgb_set_attribute: NULL argument");
     for (const char *k : kNumericAttrs) {
-        if (strcmp(k, name) == 0) { p->attr[name] = value; return 0; }
+        if (strcmp(k, name) == 0) {
+            if (strcmp(name, "Genetics_bits_per_nuc") == 0 && (int)value != 1)
+                return fail("[Genetics] This module expects 1 bit nucleotides, but the attribute specifies %d bit nucleotides", (int)value);
+            if (strcmp(name, "Genetics_genome_size") == 0) {
+                if (p->capacity > 0 && p->genetic) return fail("Genetics_genome_size must be set before agents are added");
+                p->gp.genomeSize = (int)value;
+                p->gp.nBlocks = ((int)value + 63) / 64;
+            }
+            p->attr[name] = value;
+            return 0;
+        }
     }
     return fail("qhgb_set_attribute: no action of [%s] has an attribute [%s]", p->popClass.c_str(), name);
 }
 
 int qhgb_set_attribute_str(qhgb_pop *p, const char *name, const char *value) {
     if (!p || !name || !value) return fail("qhgb_set_attribute_str: NULL argument");
-    if (strcmp(name, "AltCapPref") == 0 || strcmp(name, "AltPref") == 0) {  // PolyLine::readFromString, utils/PolyLine.cpp:92-127
+    if (strcmp(name, "Genetics_initial_muts") == 0) { p->attrStr[name] = value; return 0; }  // genomes come from the host (qhgb_set_genomes)
+    if (strcmp(name, "AltCapPref") == 0 || strcmp(name, "AltPref") == 0 || strcmp(name, "NPPPref") == 0) {  // PolyLine::readFromString, utils/PolyLine.cpp:92-127
         std::vector<double> d;
         const char *s = value;
         char *e;
@@ -844,8 +962,8 @@ int qhgb_set_attribute_str(qhgb_pop *p, const char *name, const char *value) {
             pl.v[i] = d[2 * i + 1];
             if (i > 0) pl.a[i - 1] = (pl.v[i] - pl.v[i - 1]) / (pl.x[i] - pl.x[i - 1]);  // utils/PolyLine.h:24-30
         }
-        p->poly = pl;
-        p->havePoly = true;
+        p->polys[name] = pl;
+        if (strcmp(name, "NPPPref") != 0) { p->poly = pl; p->havePoly = true; }
         p->attrStr[name] = value;
         p->evalNeedUpdate = true;
         return 0;
@@ -884,6 +1002,8 @@ int qhgb_set_seed(qhgb_pop *p, const uint32_t *st) {
 int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
                     const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life_state) {
     if (!p || !cell || !id || !birth_time || !gender) return fail("qhgb_add_agents: NULL argument");
+    if (p->genetic && p->gp.nBlocks <= 0) return fail("[Genetics] Genetics_genome_size must be set before agents are added");
+    if (p->genetic && p->preLooped) return fail("[Genetics] adding agents after preLoop is not supported for populations with genomes");
     if (p->inStep) return fail("qhgb_add_agents: called inside a step");
     CK(cudaSetDevice(p->device));
     // pack the live ones (readAgentDataQDF drops nothing, but dead records carry no agent: core/SPopulation.cpp:1689-1741)
@@ -916,6 +1036,13 @@ int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *
     CK(cudaMemcpyAsync(p->lastBirth[b].p + off, hl.data(), m * sizeof(float), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->age[b].p + off, ha.data(), m * sizeof(float), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->flags[b].p + off, hf.data(), m, cudaMemcpyHostToDevice, p->stream));
+    if (p->genetic) {  // genome rows in upload order; qhgb_set_genomes fills them
+        std::vector<int> hs(m);
+        for (int64_t j = 0; j < m; j++) hs[j] = (int)(off + j);
+        CK(cudaMemcpyAsync(p->gslot[b].p + off, hs.data(), m * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaMemsetAsync(p->nbabies[b].p + off, 0, m * sizeof(int), p->stream));
+        CK(cudaMemsetAsync(p->gpool.p + (size_t)off * 2 * p->gp.nBlocks, 0, (size_t)m * 2 * p->gp.nBlocks * sizeof(unsigned long long), p->stream));
+    }
     CK(cudaStreamSynchronize(p->stream));
     p->nAgents = total;
     if (p->preLooped) {  // late additions are binned at once
@@ -958,6 +1085,22 @@ int qhgb_pre_loop(qhgb_pop *p) {
     if (resetCellCounters(p, false) != 0) return -1;
     p->doVerhulst = false;
     if (runPipeline(p, P, false, false, false) != 0) return -1;
+    if (p->genetic) {  // Genetics::init (actions/Genetics.cpp:196-267): mutation-count table, genome bookkeeping
+        if (p->findKind(A_NAVIGATE) && p->findKind(A_NAVIGATE)->prio >= 0) return fail("Navigate is not supported on the device yet");
+        p->gp.numCrossOvers = (int)p->A("Genetics_num_crossover");
+        p->gp.mutationRate = p->A("Genetics_mutation_rate");
+        if (p->gp.numCrossOvers > MAX_CROSS) return fail("[Genetics] more than %d crossovers", MAX_CROSS);
+        p->gp.nBino = 0;
+        if (p->gp.mutationRate > 0) {
+            std::vector<double> t = binomialTable(p->gp.mutationRate, 2 * p->gp.genomeSize, 1e-6);
+            if (t.size() > (size_t)MAX_BINO) return fail("[Genetics] mutation-count table has %zu entries (> %d)", t.size(), MAX_BINO);
+            p->gp.nBino = (int)t.size();
+            for (size_t i = 0; i < t.size(); i++) p->gp.bino[i] = t[i];
+        }
+        GenomeCtl ctl{0, (int)p->nAgents, 0, 0};
+        CK(cudaMemcpyAsync(p->gctl.p, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
     if (p->findKind(A_NPPCAP) && recalcCapacities(p) != 0) return -1;  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     p->preLooped = true;
     p->evalFirst = true;
@@ -1070,6 +1213,9 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
     // NPPCapacity registers itself as an observer (actions/NPPCapacity.cpp:69) and reacts to GEO, CLIMATE and VEG (:121-131);
     // the MultiEvaluator of tut_EnvironCapAltPop is never registered, so its weights stay as first computed
     if (event_id == QHGB_EVENT_ID_GEO || event_id == QHGB_EVENT_ID_CLIMATE || event_id == QHGB_EVENT_ID_VEG) p->nppNeedUpdate = true;
+    // OoANavGenPop registers its MultiEvaluator (populations/OoANavGenPop.cpp:59), which forwards the event to its evaluators
+    // (actions/MultiEvaluator.cpp:203-214): each one reacts to its own trigger id
+    if (p->multiObserves) for (auto &e : p->subs) if (e.trigger == event_id) e.needUpdate = true;
     return 0;
 }
 
@@ -1170,6 +1316,40 @@ int qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d) {
     CK(cudaMemcpyAsync(d, p->D.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
+}
+
+int qhgb_set_genomes(qhgb_pop *p, int64_t n, const uint64_t *genomes) {
+    if (!p || !genomes) return fail("qhgb_set_genomes: NULL argument");
+    if (!p->genetic) return fail("qhgb_set_genomes: population [%s] has no Genetics", p->popClass.c_str());
+    if (p->preLooped) return fail("qhgb_set_genomes: must be called before preLoop");
+    if (n != p->nAgents) return fail("qhgb_set_genomes: %lld genomes for %lld agents", (long long)n, (long long)p->nAgents);
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->gpool.p, genomes, (size_t)n * 2 * p->gp.nBlocks * sizeof(unsigned long long), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int64_t qhgb_get_genomes(qhgb_pop *p, int64_t cap, uint64_t *genomes, int32_t *num_babies) {
+    if (!p) { fail("qhgb_get_genomes: NULL population"); return -1; }
+    if (!p->genetic) { fail("qhgb_get_genomes: population [%s] has no Genetics", p->popClass.c_str()); return -1; }
+    if (cudaSetDevice(p->device) != cudaSuccess) return -1;
+    const int64_t n = p->nAgents, m = std::min(n, cap);
+    if (m <= 0) return n;
+    const int row = 2 * p->gp.nBlocks;
+    if (genomes) {
+        unsigned long long *tmp = nullptr;
+        if (cudaMalloc(&tmp, (size_t)n * row * sizeof(unsigned long long)) != cudaSuccess) { fail("qhgb_get_genomes: out of device memory"); return -1; }
+        LAUNCH(p, "k_gather_genomes", k_gather_genomes, p->gridFor(n * row), 256, p->dstats.p, row, p->gslot[p->cur].p, p->gpool.p, tmp);
+        cudaMemcpyAsync(genomes, tmp, (size_t)m * row * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream);
+        cudaStreamSynchronize(p->stream);
+        cudaFree(tmp);
+    }
+    if (num_babies) {
+        cudaMemcpyAsync(num_babies, p->nbabies[p->cur].p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, p->stream);
+        cudaStreamSynchronize(p->stream);
+    }
+    if (cudaGetLastError() != cudaSuccess) { fail("qhgb_get_genomes: device error"); return -1; }
+    return n;
 }
 
 int qhgb_get_capacities(qhgb_pop *p, double *out) {

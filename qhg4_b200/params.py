@@ -121,6 +121,24 @@ def tut_environ_cap_alt() -> PopParams:
     )
 
 
+def ooa_nav_gen(genome_size: int = 4096, num_crossover: int = -1, mutation_rate: float = 1e-5) -> PopParams:
+    """`OoANavGenPop` (populations/OoANavGenPop.cpp:33-97) without Navigate: the genetic population of config C3.
+    The reference ships no parameter file for it; ecological values follow tut_EnvironCapAlt.xml, the Genetics values are
+    the ones SURVEY.md §8d declares (4096 one-bit sites, free recombination, mutation rate 1e-5)."""
+    base = tut_environ_cap_alt()
+    mods = {k: dict(v) for k, v in base.modules.items() if k not in ("ATanDeath", "MultiEvaluator[NPP+Alt]")}
+    mods["OldAgeDeath"] = {"OAD_max_age": "60.0", "OAD_uncertainty": "0.1"}
+    mods["MultiEvaluator[Alt+NPP]"] = {"Multi_weight_alt": "0.2", "Multi_weight_npp": "0.8",
+                                       "AltCapPref": "-0.1 0 0.1 0.01 1500 1.0 2000 1 3000 -9999",
+                                       "NPPPref": "0 0 5 0.2 38.5 1.0"}
+    mods["Genetics"] = {"Genetics_genome_size": str(int(genome_size)), "Genetics_num_crossover": str(int(num_crossover)),
+                        "Genetics_mutation_rate": repr(float(mutation_rate)), "Genetics_create_new_genome": "0",
+                        "Genetics_bits_per_nuc": "1", "Genetics_initial_muts": "none"}
+    return PopParams("OoANavGenPop", modules=mods,
+                     prios={"NPPCapacity": 1, "GetOld": 2, "OldAgeDeath": 3, "WeightedMove": 4, "MultiEvaluator[Alt+NPP]": 5,
+                            "Fertility": 6, "RandomPair": 7, "VerhulstVarK": 8, "Genetics": 9})
+
+
 # default WELL512 state of the reference (app/SimParams.cpp:82-87): 16 words of seed material
 DEFAULT_STATE = (
     0x2ef76080, 0x1bf121c5, 0xb222a768, 0x6c5d388b, 0xab99166e, 0x326c9f12, 0x3354197a, 0x7036b9a5,

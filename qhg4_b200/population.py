@@ -61,7 +61,7 @@ class GpuPopulation:
         for name, pr in params.prios.items():
             check(self.L.qhgb_set_prio(self.h, name.encode(), int(pr)), f"qhgb_set_prio({name})")
             self.prios[name] = int(pr)
-        for mod, pars in params.modules.items():
+        for mod, pars in sorted(params.modules.items(), key=lambda kv: kv[0] != "Genetics"):  # genome size first
             for k, v in pars.items():
                 check(self.L.qhgb_set_attribute_str(self.h, k.encode(), str(v).encode()), f"qhgb_set_attribute_str({k})")
 
@@ -90,6 +90,19 @@ class GpuPopulation:
                 np.ascontiguousarray(pop["age"], np.float32), np.ascontiguousarray(pop["last_birth"], np.float32),
                 np.ascontiguousarray(pop["life"], np.uint32)]
         check(self.L.qhgb_add_agents(self.h, n, *[_p(a) for a in arrs]), "qhgb_add_agents")
+
+    def set_genomes(self, genomes):
+        g = np.ascontiguousarray(genomes, np.uint64)
+        check(self.L.qhgb_set_genomes(self.h, g.shape[0], _p(g)), "qhgb_set_genomes")
+
+    def genomes(self, row_words: int):
+        n = self.num_agents()
+        g = np.zeros((n, row_words), np.uint64)
+        nb = np.zeros(n, np.int32)
+        k = self.L.qhgb_get_genomes(self.h, n, _p(g), _p(nb))
+        if k != n:
+            raise QhgError(f"qhgb_get_genomes -> {k}: {self.L.qhgb_last_error().decode()}")
+        return g, nb
 
     # ---- the loop ---------------------------------------------------------------------------
     def pre_loop(self):

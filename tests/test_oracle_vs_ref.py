@@ -127,3 +127,73 @@ def test_cap_alt_population_equals_reference():
     rb, rd = r.bd(); ob, od = o.bd()
     assert np.array_equal(rb, ob) and np.array_equal(rd, od) and np.array_equal(r.weights(), o.weights())
     r.close()
+
+
+def test_genome_primitives_equal_reference():
+    """genes/BitGeneUtils.cpp crossOver (incl. its unsorted break lists), freeReco, mutateNucs and the mutation-count
+    table of utils/BinomialDist.cpp: the oracle's restatement against the reference functions, same WELL512 stream."""
+    import ctypes as C
+    R, O = refsim.lib(), port.lib()
+    for L, pre in ((R, "qref"), (O, "qor")):
+        getattr(L, pre + "_binomial_table").argtypes = [C.c_double, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        getattr(L, pre + "_binomial_get_n").argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        G = int(rng.choice([64, 128, 200, 1000, 4096]))
+        nb = (G + 63) // 64
+        gin = rng.integers(0, 2 ** 63, size=2 * nb, dtype=np.int64).astype(np.uint64)
+        st = seed_state(trial + 1)
+        for nc in (1, 2, 3, 7, 20):
+            a, b = np.zeros(2 * nb, np.uint64), np.zeros(2 * nb, np.uint64)
+            R.qref_bit_crossover(p(st), p(gin), G, nc, p(a)); O.qor_bit_crossover(p(st), p(gin), G, nc, p(b))
+            assert np.array_equal(a, b), (trial, nc)
+        a, b = np.zeros(2 * nb, np.uint64), np.zeros(2 * nb, np.uint64)
+        R.qref_bit_freereco(p(st), p(gin), nb, p(a)); O.qor_bit_freereco(p(st), p(gin), nb, p(b))
+        assert np.array_equal(a, b)
+        a, b = gin.copy(), gin.copy()
+        R.qref_bit_mutate(p(st), p(a), 2 * G, 6); O.qor_bit_mutate(p(st), p(b), 2 * G, 6)
+        assert np.array_equal(a, b) and not np.array_equal(a, gin)
+    for pr, n in ((1e-5, 8192), (1e-3, 8192), (0.01, 256), (1e-4, 128)):
+        ta, tb = np.zeros(128), np.zeros(128)
+        na = R.qref_binomial_table(pr, n, 1e-6, 128, p(ta)); nb_ = O.qor_binomial_table(pr, n, 1e-6, 128, p(tb))
+        assert na == nb_ and np.array_equal(ta, tb)
+        for r in (0.0, 0.5, 0.93, 0.999, 0.9999999):
+            assert R.qref_binomial_get_n(pr, n, 1e-6, r) == O.qor_binomial_get_n(pr, n, 1e-6, r)
+    # SURVEY.md §9.2: BinomialDist::create(1e-5, 8192, 1e-6)
+    t = np.zeros(16)
+    assert O.qor_binomial_table(1e-5, 8192, 1e-6, 16, p(t)) == 5 and abs(t[0] - 0.9213453) < 1e-6
+    assert [O.qor_binomial_get_n(1e-5, 8192, 1e-6, r) for r in (0.5, 0.93, 0.999, 0.9999999)] == [0, 1, 2, 4]
+
+
+def test_genetic_population_counter_mode_properties():
+    """OoANavGenPop in the oracle: order invariance with genomes, inheritance (every newborn strand is made of parental
+    alleles when there is no mutation)."""
+    from qhg4_b200.params import ooa_nav_gen
+    nbr, xyz, alt, env = _cap_world()
+    pop = synthetic_population(6000, alt, seed=4, fertile=True)
+    G, row = 128, 4
+    gen0 = np.random.default_rng(3).integers(0, 2 ** 63, size=(6000, row), dtype=np.int64).astype(np.uint64)
+    res = []
+    for perm in (np.arange(6000), np.random.default_rng(1).permutation(6000)):
+        o = port.OraclePop(ooa_nav_gen(G, -1, 0.0), nbr, alt, mode=port.MODE_COUNTER, state16=seed_state(9), env=env)
+        o.add_agents({k: v[perm] for k, v in pop.items()})
+        o.set_genomes(gen0[perm])
+        o.start()
+        for k in range(8):
+            o.step(float(k))
+        a = o.agents(); g, nbab = o.genomes(row)
+        s = np.argsort(a["id"])
+        res.append((a["id"][s], a["cell"][s], g[s], nbab[s]))
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+    ids, _, g, nbab = res[0]
+    assert nbab.sum() > 500 and (ids >= 6000).sum() > 500
+    # with all founders carrying allele 0 at bit 0 of both strands, no descendant can carry allele 1 there
+    gz = gen0.copy(); gz[:, 0] &= ~np.uint64(1); gz[:, 2] &= ~np.uint64(1)
+    o = port.OraclePop(ooa_nav_gen(G, 2, 0.0), nbr, alt, mode=port.MODE_COUNTER, state16=seed_state(9), env=env)
+    o.add_agents(pop); o.set_genomes(gz); o.start()
+    for k in range(8):
+        o.step(float(k))
+    g, _ = o.genomes(row)
+    assert np.all((g[:, 0] & np.uint64(1)) == 0) and np.all((g[:, 2] & np.uint64(1)) == 0)

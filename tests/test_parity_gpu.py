@@ -301,3 +301,41 @@ def test_cap_alt_population_vs_oracle_and_reference(path):
     assert np.array_equal(g.weights(), o.weights())
     gb, gd = g.bd(); ob, od = o.bd()
     assert np.array_equal(gb, ob) and np.array_equal(gd, od)
+
+
+@pytest.mark.parametrize("ncross,mut", [(-1, 1e-3), (0, 0.0), (2, 1e-3), (7, 5e-3)])
+def test_genetic_population_bit_exact_vs_oracle(ncross, mut):
+    """OoANavGenPop without Navigate (config C3): OldAgeDeath, VerhulstVarK, NPPCapacity, MultiEvaluator[Alt+NPP] and
+    Genetics<BitGeneUtils> -- agents AND genomes bit-exact against the oracle's counter mode, for free recombination,
+    no recombination and crossovers, with mutations."""
+    from oracle import port
+    from qhg4_b200.params import ooa_nav_gen
+    from qhg4_b200.population import GpuPopulation
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    G = 200 if ncross == 7 else 256
+    par, st = ooa_nav_gen(G, ncross, mut), seed_state(31)
+    row = 2 * ((G + 63) // 64)
+    gen0 = np.random.default_rng(1).integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    g.add_agents(pop); o.add_agents(pop)
+    g.set_genomes(gen0); o.set_genomes(gen0)
+    g.pre_loop(); o.start()
+    births = 0
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        births += g.step_stats().births
+        ga, oa = g.agents(), o.agents()
+        gg, gnb = g.genomes(row)
+        og, onb = o.genomes(row)
+        si, so = np.argsort(ga["id"]), np.argsort(oa["id"])
+        assert np.array_equal(gg[si], og[so]), f"step {k}: genomes differ"
+        assert np.array_equal(gnb[si], onb[so]), f"step {k}: NumBabies differ"
+    assert births > 1500
+    # founders keep their genomes; newborn genomes are built from existing alleles (plus rare mutations)
+    ga = g.agents()
+    gg, _ = g.genomes(row)
+    founders = ga["id"] < len(pop["id"])
+    assert np.array_equal(gg[founders], gen0[ga["id"][founders]])
