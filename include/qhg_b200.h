@@ -66,6 +66,13 @@ int  qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id);
  * (app/Simulator.cpp:668-753). */
 int  qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n);
 
+/* the Navigation group (sea-ways) that Navigate reads through SCellGrid::m_pNavigation (core/Navigation.h:13-37,
+ * io/NavGroupReader.cpp:98-160): n_ports origin cells; port p jumps to dest_cell[port_ptr[p] .. port_ptr[p+1]) over
+ * the distances dist[] (same indexing); bridges = n_bridges pairs of cells.  Navigate builds its jump tables from it
+ * at preLoop and again after EVENT_ID_NAV / EVENT_ID_GEO + flush (actions/Navigate.cpp:79-144). */
+int  qhgb_set_navigation(qhgb_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+                         const double *dist, int n_bridges, const int32_t *bridges);
+
 /* ---- parameters --------------------------------------------------------------------------------
  * Attribute names are the reference's XML / QDF attribute names, e.g. "ATanDeath_max_age",
  * "Verhulst_K", "WeightedMove_prob" (actions/ATanDeath.h:9-12, actions/Verhulst.h:9-13, ...).

@@ -57,6 +57,7 @@ def lib():
         L.qor_get_birth_death_probs.argtypes = [vp, vp, vp]
         L.qor_atan_death_prob.argtypes = [vp, i32, vp, vp]
         L.qor_get_capacities.argtypes = [vp, vp]
+        L.qor_set_navigation.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
         L.qor_set_genomes.argtypes = [vp, i64, vp]
         L.qor_get_genomes.restype = i64
         L.qor_get_genomes.argtypes = [vp, i64, vp, vp]
@@ -168,6 +169,12 @@ class OraclePop:
         out = np.zeros(self.ncells)
         assert lib().qor_get_capacities(self.h, _p(out)) == 0
         return out
+
+    def set_navigation(self, port_cell, port_ptr, dest_cell, dist, bridges=()):
+        pc, pp = np.ascontiguousarray(port_cell, np.int32), np.ascontiguousarray(port_ptr, np.int32)
+        dc, dd = np.ascontiguousarray(dest_cell, np.int32), np.ascontiguousarray(dist, np.float64)
+        br = np.ascontiguousarray(np.asarray(bridges, np.int32).reshape(-1, 2))
+        assert lib().qor_set_navigation(self.h, len(pc), _p(pc), _p(pp), _p(dc), _p(dd), len(br), _p(br) if len(br) else None) == 0
 
     def set_genomes(self, genomes):
         g = np.ascontiguousarray(genomes, np.uint64)

@@ -356,6 +356,12 @@ struct qor_pop {
     int genomeSize = 0, numCrossOvers = 0, nBlocks = 0;
     double mutationRate = 0;
     std::vector<double> binoTable;
+    // Navigate (actions/Navigate.cpp) over the Navigation group (core/Navigation.h:13-37)
+    std::map<int, std::map<int, double>> navDest;          // port cell -> (destination cell -> distance)
+    std::vector<std::pair<int, int>> navBridges, curBridges;
+    std::map<int, std::pair<int, std::vector<std::pair<int, double>>>> jumpProbs;  // port -> (n, [(dest, cumulated prob)])
+    double navDecay = 0, navDist0 = 0, navProb0 = 0, navBridgeProb = 0;
+    bool navNeedUpdate = true;
 
     // evaluator state (actions/SingleEvaluator.cpp:138-167,332-346)
     bool evalFirst = true, evalNeedUpdate = false;
@@ -551,6 +557,32 @@ struct qor_pop {
     void evaluatorInit() {
         if (evalNeedUpdate || evalFirst) { evalFirst = false; evaluatorCompute(); }
     }
+    // actions/Navigate.cpp:94-144
+    int navRecalculate() {
+        if (!navNeedUpdate) return 0;
+        const double A = navProb0 / exp(navDecay * navDist0);
+        jumpProbs.clear();
+        curBridges.clear();
+        for (auto &pt : navDest) {
+            std::vector<std::pair<int, double>> tp(pt.second.size() + 1);
+            double sum = 0;
+            int i = 1;
+            for (auto &dd : pt.second) {
+                double pr = A * exp(navDecay * dd.second);
+                sum += pr;
+                tp[i++] = {dd.first, pr};
+            }
+            if (!(sum < 1)) return -1;
+            tp[0] = {-1, 1 - sum};
+            for (size_t j = 1; j < tp.size(); j++) tp[j].second += tp[j - 1].second;
+            jumpProbs[pt.first] = {(int)pt.second.size(), tp};
+        }
+        const std::vector<double> &alt = env["Altitude"];
+        for (auto &b : navBridges) if (alt[b.first] > 0 && alt[b.second] > 0) curBridges.push_back(b);
+        navNeedUpdate = false;
+        return 0;
+    }
+
     // actions/RandomPair.cpp:107-128 (initialize) and :146-279 (findMates)
     void randomPairInit() {
         for (int i = 0; i < hi(); i++) if (active[i]) slots[i].mate = -3;
@@ -678,11 +710,38 @@ struct qor_pop {
             }
             break;
         }
+        case A_NAVIGATE: {  // actions/Navigate.cpp:181-250
+            if (a.life > 0 && (a.life & LIFE_MOVING) == 0) {
+                const int c = a.cell;
+                auto it = jumpProbs.find(c);
+                if (it != jumpProbs.end()) {
+                    // the reference bounds the search by the map key = the port's cell index (:194); the table has n+1 entries
+                    const int nd = it->second.first, lim = (it->first < nd) ? it->first : nd;
+                    const double r = u2d(draw(a.id, STREAM_ACT1, L1_NAV));
+                    int i = 0;
+                    while (i < lim && r > it->second.second[i].second) i++;
+                    if (i > 0) {
+                        const int to = it->second.second[i].first;
+                        const bool iced = env.count("Ice") && env["Ice"][to] != 0;
+                        if (!iced) registerMove(c, (int)(&a - slots.data()), to);
+                    }
+                }
+                for (size_t b = 0; b < curBridges.size(); b++) {
+                    const int to = (curBridges[b].first == c) ? curBridges[b].second : ((curBridges[b].second == c) ? curBridges[b].first : -1);
+                    if (to >= 0) {
+                        uint32_t w;
+                        if (mode == QOR_MODE_WELL) w = well.next();
+                        else { uint32_t o[4]; draw4(a.id, 0x04000000u | (uint32_t)(b / 4), o); w = o[b % 4]; }
+                        if (u2d(w) < navBridgeProb) registerMove(c, (int)(&a - slots.data()), to);
+                    }
+                }
+            }
+            break;
+        }
         case A_SINGLEEVAL:
         case A_MULTIEVAL:
         case A_NPPCAP:
         case A_GENETICS:
-        case A_NAVIGATE:
         case A_RANDOMPAIR:
             break;  // execute() is empty for these (actions/Action.h:36 default)
         }
@@ -877,6 +936,7 @@ struct qor_pop {
         // OoANavGenPop registers its MultiEvaluator (populations/OoANavGenPop.cpp:59), which forwards the event to its
         // evaluators (actions/MultiEvaluator.cpp:203-214): each one reacts to its own trigger id
         if (multiObserves) for (auto &e : subs) if (e.trigger == ev) e.needUpdate = true;
+        if (ev == 2 || ev == 5) navNeedUpdate = true;  // Navigate::notify, actions/Navigate.cpp:79-87
         return 0;
     }
 };
@@ -974,6 +1034,11 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "NPPCap_K_max") p->nppKMax = v;
     else if (s == "NPPCap_K_min") p->nppKMin = v;
     else if (s == "NPPCap_efficiency") p->nppEff = v;
+    else if (s == "Navigate_decay") p->navDecay = v;
+    else if (s == "Navigate_dist0") p->navDist0 = v;
+    else if (s == "Navigate_prob0") p->navProb0 = v;
+    else if (s == "Navigate_min_dens") {}
+    else if (s == "Navigate_bridge_prob") p->navBridgeProb = v;
     else if (s == "Genetics_genome_size") { p->genomeSize = (int)v; p->nBlocks = ((int)v + 63) / 64; }
     else if (s == "Genetics_num_crossover") p->numCrossOvers = (int)v;
     else if (s == "Genetics_mutation_rate") p->mutationRate = v;
@@ -1050,6 +1115,7 @@ int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDe
         if (p->mutationRate > 0) p->binoTable = binomialTable(p->mutationRate, 2 * p->genomeSize, 1e-6);
         for (auto &a : p->slots) if (a.genome.empty()) a.genome.assign(2 * p->nBlocks, 0);
     }
+    { Action *nv = p->find("Navigate"); if (nv && nv->prio >= 0 && p->navRecalculate() != 0) return -1; }  // Navigate::preLoop
     if (p->find("NPPCapacity")) p->nppRecalculate();  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     return 0;
 }
@@ -1061,6 +1127,7 @@ int qor_step(qor_pop *p, float t) { return p->step(t); }
 int qor_update_event(qor_pop *p, int ev, float t) { return p->updateEvent(ev, t); }
 int qor_flush_events(qor_pop *p, float) {  // EVENT_ID_FLUSH: NPPCapacity::notify -> recalculate (actions/NPPCapacity.cpp:127-130)
     if (p->find("NPPCapacity")) p->nppRecalculate();
+    { Action *nv = p->find("Navigate"); if (nv && nv->prio >= 0) p->navRecalculate(); }
     return 0;
 }
 
@@ -1101,6 +1168,17 @@ int qor_get_env_weights(qor_pop *p, double *out) {
 int qor_get_birth_death_probs(qor_pop *p, double *b, double *d) {
     memcpy(b, p->B.data(), sizeof(double) * p->nCells);
     memcpy(d, p->D.data(), sizeof(double) * p->nCells);
+    return 0;
+}
+
+int qor_set_navigation(qor_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+                       const double *dist, int n_bridges, const int32_t *bridges) {
+    p->navDest.clear();
+    p->navBridges.clear();
+    for (int pt = 0; pt < n_ports; pt++)
+        for (int k = port_ptr[pt]; k < port_ptr[pt + 1]; k++) p->navDest[port_cell[pt]][dest_cell[k]] = dist[k];
+    for (int b = 0; b < n_bridges; b++) p->navBridges.push_back({bridges[2 * b], bridges[2 * b + 1]});
+    p->navNeedUpdate = true;
     return 0;
 }
 

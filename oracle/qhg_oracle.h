@@ -56,6 +56,9 @@ int      qor_get_capacities(qor_pop *p, double *out);
 int      qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out);
 int      qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves);
 
+int      qor_set_navigation(qor_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+                            const double *dist, int n_bridges, const int32_t *bridges);
+
 /* genomes (actions/Genetics.cpp, genes/BitGeneUtils.cpp) */
 int      qor_set_genomes(qor_pop *p, int64_t n, const uint64_t *g);
 int64_t  qor_get_genomes(qor_pop *p, int64_t cap, uint64_t *g, int32_t *num_babies);

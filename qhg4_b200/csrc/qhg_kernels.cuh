@@ -20,7 +20,7 @@ constexpr int MAX_OPS = 16;
 // agent flag byte: gender and the FERTILE bit of the reference's life state (core/SPopulation.h:70-74)
 constexpr uint8_t F_MALE = 1, F_FERTILE = 2, F_BORN = 4;  // F_BORN only in the per-step decision byte
 
-enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN };
+enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE };
 
 struct AgentArrays {
     int64_t *id;
@@ -306,10 +306,20 @@ struct CellEnv {
     const double *W;
     const double *B;
     const double *D;
+    // Navigate (actions/Navigate.cpp): ports as CSR (every port has n+1 entries: 0 = stay at home), current bridges
+    const int *navRow;       // per cell: port index or -1; NULL if the population does not navigate
+    const int *navPtr;       // first entry of port p
+    const int *navDest;      // destination cell of every entry (-1 for entry 0)
+    const double *navCum;    // cumulated jump probability of every entry
+    const int2 *bridges;
+    int nBridges;
+    double bridgeProb;
 };
 
 struct Decision {
     bool alive, born, moving;
+    bool movingBit;  // LIFE_STATE_MOVING as later actions see it (Fertility overwrites the whole life state)
+    int nMoves;      // registered moves (every registerMove counts, the last one wins: core/SPopulation.cpp:1058-1092)
     int pick;    // 0: stays, 1..6: moves to neighbour slot pick-1
     int to;      // destination cell
     uint8_t f;   // new flag byte (gender | fertile)
@@ -322,7 +332,7 @@ struct Decision {
 __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEnv &E, unsigned step, int64_t id, float birth,
                                                 float ageIn, int c, uint8_t f, bool hasMate, const float *lastBirthPtr) {
     Decision d;
-    d.alive = true; d.born = false; d.moving = false; d.pick = 0; d.to = c; d.f = f; d.age = ageIn;
+    d.alive = true; d.born = false; d.moving = false; d.movingBit = false; d.nMoves = 0; d.pick = 0; d.to = c; d.f = f; d.age = ageIn;
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     bool have0 = false, have1 = false;
 #pragma unroll 1
@@ -371,7 +381,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 }
                 if (pick > 0) {
                     int dst = E.nbr[(size_t)c * MAXN + pick - 1];
-                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; }
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
                 }
             }
             break;
@@ -384,6 +394,33 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 fert = d.age > P.fertMinAge;
             }
             d.f = (uint8_t)((d.f & F_MALE) | (fert ? F_FERTILE : 0));
+            d.movingBit = false;  // the life state is overwritten, MOVING bit included (actions/Fertility.cpp:56-68)
+            break;
+        }
+        case OP_NAVIGATE: {  // actions/Navigate.cpp:181-250
+            if (d.movingBit || !E.navRow) break;
+            const int port = E.navRow[c];
+            if (port >= 0) {
+                if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                const int p0 = E.navPtr[port], nd = E.navPtr[port + 1] - p0 - 1;
+                const int lim = (c < nd) ? c : nd;  // the reference bounds the search by the port's cell index (:194); entries end at nd
+                const double r = u2d(r1.y);
+                int i = 0;
+                while (i < lim && r > E.navCum[p0 + i]) i++;
+                if (i > 0) {
+                    const int dst = E.navDest[p0 + i];
+                    if (!(E.ice && E.ice[dst])) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; }
+                }
+            }
+            for (int b = 0; b < E.nBridges; b++) {  // manual bridges: one draw per incident bridge (:228-247)
+                const int2 br = E.bridges[b];
+                const int dst = (br.x == c) ? br.y : ((br.y == c) ? br.x : -1);
+                if (dst >= 0) {
+                    const uint4 db = agent_draws(id, step, 0x04000000u | (unsigned)(b / 4), P.key);
+                    const unsigned wv = (b & 3) == 0 ? db.x : (b & 3) == 1 ? db.y : (b & 3) == 2 ? db.z : db.w;
+                    if (u2d(wv) < E.bridgeProb) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; }
+                }
+            }
             break;
         }
         case OP_VERHULST: {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
@@ -431,7 +468,7 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
             const bool hasMate = needMate && !(f & F_MALE) && mate[i] >= 0;
             d = run_actions(P, E, step, a.id[i], a.birth[i], P.storeAge ? a.age[i] : 0.0f, c, f, hasMate, a.lastBirth + i);
             if (P.storeAge && d.alive) a.age[i] = d.age;  // moved with the agent by k_scatter
-            if (d.moving) nMove++;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
+            nMove += d.nMoves;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
             if (!d.alive) nDead++;
             if (d.born) nBorn++;
         }

@@ -201,6 +201,15 @@ struct qhgb_pop {
     DevBuf<BirthEntry> births;
     DevBuf<GenomeCtl> gctl;
     int64_t poolRows = 0;
+    // Navigate: the Navigation group as the host handed it over, and the jump tables built from it
+    std::vector<int> hPortCell, hPortPtr, hDestCell, hBridges;
+    std::vector<double> hDist;
+    bool navNeedUpdate = true, navReady = false;
+    int nCurBridges = 0;
+    DevBuf<int> navRow, navPtr, navDest;
+    DevBuf<double> navCum;
+    DevBuf<int2> navBridges;
+    std::vector<double> hAlt;  // host copy of the altitude (bridges need both ends above sea level)
     float curTime = -1;
     std::vector<unsigned> levels;
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
@@ -390,7 +399,8 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
         case A_FERTILITY: op = OP_FERTILITY; break;
         case A_VERHULST: op = OP_VERHULST; break;
-        case A_VERHULSTVARK: op = OP_VERHULST; break;  // the same two executes with a per-cell K (actions/VerhulstVarK.cpp:96-112)
+        case A_VERHULSTVARK: op = OP_VERHULST; break;
+        case A_NAVIGATE: op = OP_NAVIGATE; break;  // the same two executes with a per-cell K (actions/VerhulstVarK.cpp:96-112)
         default: break;  // evaluators and pairing have no per-agent execute()
         }
         if (op && P.nOps < MAX_OPS) { P.prog |= (unsigned long long)op << (4 * P.nOps); P.nOps++; }
@@ -550,6 +560,53 @@ std::vector<double> binomialTable(double prob, int n, double eps) {
     return v;
 }
 
+// Navigate::recalculate (actions/Navigate.cpp:94-144): per port the cumulated jump probabilities
+// [stay, d1, d1+d2, ...] with p_i = prob0/exp(decay*dist0) * exp(decay*dist_i); bridges with both ends on land.
+// A small host-side table build (ports << cells), like the reference does it at event time.
+int recalcNavigation(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    if (!q.navNeedUpdate) return 0;
+    const int nPorts = (int)q.hPortCell.size();
+    const double decay = q.A("Navigate_decay"), A = q.A("Navigate_prob0") / exp(decay * q.A("Navigate_dist0"));
+    std::vector<int> row(q.nCells, -1), ptr(nPorts + 1, 0), dest;
+    std::vector<double> cum;
+    for (int pt = 0; pt < nPorts; pt++) {
+        const int b = q.hPortPtr[pt], e = q.hPortPtr[pt + 1];
+        ptr[pt] = (int)dest.size();
+        row[q.hPortCell[pt]] = pt;
+        double sum = 0;
+        for (int k = b; k < e; k++) sum += A * exp(decay * q.hDist[k]);
+        if (!(sum < 1)) return fail("[Navigate] probabilities for port [%d] add up to %f", q.hPortCell[pt], sum);
+        dest.push_back(-1);
+        cum.push_back(1 - sum);
+        for (int k = b; k < e; k++) {
+            dest.push_back(q.hDestCell[k]);
+            cum.push_back(cum.back() + A * exp(decay * q.hDist[k]));
+        }
+    }
+    ptr[nPorts] = (int)dest.size();
+    std::vector<int2> br;
+    for (size_t k = 0; k + 1 < q.hBridges.size(); k += 2) {
+        const int a = q.hBridges[k], b = q.hBridges[k + 1];
+        if (!q.hAlt.empty() && q.hAlt[a] > 0 && q.hAlt[b] > 0) br.push_back(make_int2(a, b));
+    }
+    CK(q.navRow.alloc(q.nCells));
+    CK(q.navPtr.alloc(ptr.size()));
+    CK(q.navDest.alloc(std::max<size_t>(dest.size(), 1)));
+    CK(q.navCum.alloc(std::max<size_t>(cum.size(), 1)));
+    CK(q.navBridges.alloc(std::max<size_t>(br.size(), 1)));
+    CK(cudaMemcpyAsync(q.navRow.p, row.data(), row.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
+    CK(cudaMemcpyAsync(q.navPtr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
+    if (!dest.empty()) CK(cudaMemcpyAsync(q.navDest.p, dest.data(), dest.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
+    if (!cum.empty()) CK(cudaMemcpyAsync(q.navCum.p, cum.data(), cum.size() * sizeof(double), cudaMemcpyHostToDevice, q.stream));
+    if (!br.empty()) CK(cudaMemcpyAsync(q.navBridges.p, br.data(), br.size() * sizeof(int2), cudaMemcpyHostToDevice, q.stream));
+    CK(cudaStreamSynchronize(q.stream));
+    q.nCurBridges = (int)br.size();
+    q.navReady = true;
+    q.navNeedUpdate = false;
+    return 0;
+}
+
 int computeWeights(qhgb_pop *p) {
     if (!p->haveAlt) return fail("SingleEvaluator[Alt]: no array with name [Altitude]");
     int g = p->gridFor(p->nCells);
@@ -561,7 +618,13 @@ int computeWeights(qhgb_pop *p) {
 }
 
 CellEnv cellEnv(qhgb_pop *p) {
-    return CellEnv{p->nbr.p, p->nNbr.p, p->haveIce ? p->ice.p : nullptr, p->alt.p, p->W.p, p->B.p, p->D.p};
+    CellEnv E{};
+    E.nbr = p->nbr.p; E.nNbr = p->nNbr.p; E.ice = p->haveIce ? p->ice.p : nullptr; E.alt = p->alt.p; E.W = p->W.p; E.B = p->B.p; E.D = p->D.p;
+    if (p->navReady) {
+        E.navRow = p->navRow.p; E.navPtr = p->navPtr.p; E.navDest = p->navDest.p; E.navCum = p->navCum.p;
+        E.bridges = p->navBridges.p; E.nBridges = p->nCurBridges; E.bridgeProb = p->A("Navigate_bridge_prob");
+    }
+    return E;
 }
 
 int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
@@ -621,6 +684,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
     bool tiled = binned && !q.forceGeneric && (n > 0 || q.sharded);
+    for (int k = 0; k < P.nOps; k++) if (prog_op(P, k) == OP_NAVIGATE) tiled = false;  // far jumps: generic path only (for now)
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
     long long stepEndBirths = -1;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -845,6 +909,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release();
+    p->navRow.release(); p->navPtr.release(); p->navDest.release(); p->navCum.release(); p->navBridges.release();
     for (int b = 0; b < 2; b++) {
         p->id[b].release(); p->birth[b].release(); p->lastBirth[b].release(); p->age[b].release();
         p->cell[b].release(); p->flags[b].release();
@@ -895,6 +960,7 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
     if (s == "Altitude") {
         CK(cudaMemcpyAsync(p->alt.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         p->haveAlt = true;
+        p->hAlt.assign(values, values + n);
     } else if (s == "Ice") {
         std::vector<uint8_t> b(n);
         bool any = false;
@@ -917,6 +983,7 @@ static const char *const kNumericAttrs[] = {
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
     "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
+    "Navigate_decay", "Navigate_dist0", "Navigate_prob0", "Navigate_min_dens", "Navigate_bridge_prob",
     "Genetics_genome_size", "Genetics_num_crossover", "Genetics_mutation_rate", "Genetics_create_new_genome", "Genetics_bits_per_nuc"};
 
 int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
@@ -1086,7 +1153,6 @@ int qhgb_pre_loop(qhgb_pop *p) {
     p->doVerhulst = false;
     if (runPipeline(p, P, false, false, false) != 0) return -1;
     if (p->genetic) {  // Genetics::init (actions/Genetics.cpp:196-267): mutation-count table, genome bookkeeping
-        if (p->findKind(A_NAVIGATE) && p->findKind(A_NAVIGATE)->prio >= 0) return fail("Navigate is not supported on the device yet");
         p->gp.numCrossOvers = (int)p->A("Genetics_num_crossover");
         p->gp.mutationRate = p->A("Genetics_mutation_rate");
         if (p->gp.numCrossOvers > MAX_CROSS) return fail("[Genetics] more than %d crossovers", MAX_CROSS);
@@ -1100,6 +1166,10 @@ int qhgb_pre_loop(qhgb_pop *p) {
         GenomeCtl ctl{0, (int)p->nAgents, 0, 0};
         CK(cudaMemcpyAsync(p->gctl.p, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
+    }
+    if (p->findKind(A_NAVIGATE) && p->findKind(A_NAVIGATE)->prio >= 0) {  // Navigate::preLoop, actions/Navigate.cpp:151-174
+        if (p->hPortPtr.empty()) return fail("[Navigate] m_pNavigation is NULL! (qhgb_set_navigation)");
+        if (recalcNavigation(p) != 0) return -1;
     }
     if (p->findKind(A_NPPCAP) && recalcCapacities(p) != 0) return -1;  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     p->preLooped = true;
@@ -1216,6 +1286,7 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
     // OoANavGenPop registers its MultiEvaluator (populations/OoANavGenPop.cpp:59), which forwards the event to its evaluators
     // (actions/MultiEvaluator.cpp:203-214): each one reacts to its own trigger id
     if (p->multiObserves) for (auto &e : p->subs) if (e.trigger == event_id) e.needUpdate = true;
+    if (event_id == QHGB_EVENT_ID_GEO || event_id == QHGB_EVENT_ID_NAV) p->navNeedUpdate = true;  // Navigate::notify, actions/Navigate.cpp:79-87
     return 0;
 }
 
@@ -1227,6 +1298,10 @@ int qhgb_flush_events(qhgb_pop *p, float t) {
     if (p->findKind(A_NPPCAP)) {
         CK(cudaSetDevice(p->device));
         if (recalcCapacities(p) != 0) return -1;
+    }
+    if (p->findKind(A_NAVIGATE) && p->findKind(A_NAVIGATE)->prio >= 0 && !p->hPortPtr.empty()) {
+        CK(cudaSetDevice(p->device));
+        if (recalcNavigation(p) != 0) return -1;
     }
     return 0;
 }
@@ -1315,6 +1390,34 @@ int qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d) {
     CK(cudaMemcpyAsync(b, p->B.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaMemcpyAsync(d, p->D.p, (size_t)p->nCells * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_set_navigation(qhgb_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+                        const double *dist, int n_bridges, const int32_t *bridges) {
+    if (!p || (n_ports > 0 && (!port_cell || !port_ptr || !dest_cell || !dist)) || (n_bridges > 0 && !bridges))
+        return fail("qhgb_set_navigation: NULL argument");
+    if (!p->findKind(A_NAVIGATE)) return fail("qhgb_set_navigation: population [%s] has no Navigate action", p->popClass.c_str());
+    p->hPortCell.assign(port_cell, port_cell + n_ports);
+    p->hPortPtr.assign(port_ptr, port_ptr + n_ports + 1);
+    const int nd = n_ports > 0 ? port_ptr[n_ports] : 0;
+    // the reference keeps the destinations of a port in a std::map keyed by cell (core/Navigation.h:13-16): ascending order
+    p->hDestCell.clear(); p->hDist.clear();
+    for (int pt = 0; pt < n_ports; pt++) {
+        if (port_cell[pt] < 0 || port_cell[pt] >= p->nCells) return fail("qhgb_set_navigation: port cell %d", port_cell[pt]);
+        std::map<int, double> v;  // a destination given twice keeps the last distance, like the reference's map
+        for (int k = port_ptr[pt]; k < port_ptr[pt + 1]; k++) {
+            if (dest_cell[k] < 0 || dest_cell[k] >= p->nCells) return fail("qhgb_set_navigation: destination cell %d", dest_cell[k]);
+            v[dest_cell[k]] = dist[k];
+        }
+        p->hPortPtr[pt] = (int)p->hDestCell.size();
+        for (auto &x : v) { p->hDestCell.push_back(x.first); p->hDist.push_back(x.second); }
+    }
+    p->hPortPtr[n_ports] = (int)p->hDestCell.size();
+    (void)nd;
+    p->hBridges.assign(bridges, bridges + 2 * (size_t)n_bridges);
+    for (int b : p->hBridges) if (b < 0 || b >= p->nCells) return fail("qhgb_set_navigation: bridge cell %d", b);
+    p->navNeedUpdate = true;
     return 0;
 }
 

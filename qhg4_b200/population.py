@@ -91,6 +91,13 @@ class GpuPopulation:
                 np.ascontiguousarray(pop["life"], np.uint32)]
         check(self.L.qhgb_add_agents(self.h, n, *[_p(a) for a in arrs]), "qhgb_add_agents")
 
+    def set_navigation(self, port_cell, port_ptr, dest_cell, dist, bridges=()):
+        pc, pp = np.ascontiguousarray(port_cell, np.int32), np.ascontiguousarray(port_ptr, np.int32)
+        dc, dd = np.ascontiguousarray(dest_cell, np.int32), np.ascontiguousarray(dist, np.float64)
+        br = np.ascontiguousarray(np.asarray(bridges, np.int32).reshape(-1, 2))
+        check(self.L.qhgb_set_navigation(self.h, len(pc), _p(pc), _p(pp), _p(dc), _p(dd), len(br), _p(br) if len(br) else None),
+              "qhgb_set_navigation")
+
     def set_genomes(self, genomes):
         g = np.ascontiguousarray(genomes, np.uint64)
         check(self.L.qhgb_set_genomes(self.h, g.shape[0], _p(g)), "qhgb_set_genomes")
