@@ -37,7 +37,10 @@ constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast
 #endif
 constexpr int CELL_BATCH = QHG_CELL_BATCH;    // consecutive cells a warp takes per grab of the work counter
 constexpr int DU = 2;            // agents per lane and chunk in the decide pass
-constexpr int SU = 2;            // the same in the scatter pass
+#ifndef QHG_SU
+#define QHG_SU 2
+#endif
+constexpr int SU = QHG_SU;            // the same in the scatter pass
 
 // decision byte handed from pass 1 to pass 2: bit0 male, bit1 fertile (the agent's new flags), bit2 gave birth,
 // bits 3-5 move code: 0 stays, 1..6 neighbour slot + 1, 7 dead
@@ -51,7 +54,7 @@ struct WarpSmem {
     long long qmId[QCAP];      // WeightedMove queue: agent id
     float qaAge[QCAP];         // ATanDeath queue: the agent's age
     uint32_t qaU[QCAP];        //                  the agent's death draw
-    uint32_t keys[MAXF];       // pairing keys of the cell's fertile females
+    alignas(16) uint32_t keys[MAXF];  // pairing keys of the cell's fertile females
     uint16_t ffJ[MAXF];        //   and their position in the cell
     uint16_t qaJ[QCAP];
     uint16_t qmJ[QCAP];        // WeightedMove queue: position in the cell
@@ -89,7 +92,7 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 // pass 1.  SPEC = true: the program is PROG_TUT5, known at compile time (straight-line code);
 //          SPEC = false: any program, interpreted from P.prog.
 #ifndef QHG_DECIDE_MINB
-#define QHG_DECIDE_MINB 6
+#define QHG_DECIDE_MINB 7
 #endif
 template <bool SPEC>
 __global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
@@ -110,7 +113,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     const float atanAgeLo = P.atanAgeLo, atanAgeHi = P.atanAgeHi;
     const unsigned long long tMove = prob_threshold(P.moveProb);
     const RngKey key = P.key;
-    const RoundKeys RK = round_keys(key);
+    const RoundKeys &RK = P.rk;
     const bool storeAge = P.storeAge != 0;
 
     // cells are handed out dynamically in batches of CELL_BATCH consecutive cells (sea cells are empty, land cells are
@@ -299,13 +302,20 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             for (int i = lane; i < nCand; i += 32) {
                 const int q = S.candQ[i];
                 const uint32_t k = S.keys[q];
-                int r = 0;
-                bool tie = false;
-                for (int e = 0; e < nF; e++) {
+                // rank = number of smaller keys; four keys per shared-memory load; "<=" counts reveal ties (the key itself is one)
+                int r = 0, le = 0;
+                const int nF4 = nF & ~3;
+                for (int e = 0; e < nF4; e += 4) {
+                    const uint4 kk = *reinterpret_cast<const uint4 *>(&S.keys[e]);
+                    r += (kk.x < k) + (kk.y < k) + (kk.z < k) + (kk.w < k);
+                    le += (kk.x <= k) + (kk.y <= k) + (kk.z <= k) + (kk.w <= k);
+                }
+                for (int e = nF4; e < nF; e++) {
                     const uint32_t ke = S.keys[e];
                     r += (ke < k) ? 1 : 0;
-                    tie |= (ke == k) && (e != q);
+                    le += (ke <= k) ? 1 : 0;
                 }
+                const bool tie = (le - r) > 1;
                 if (tie) {  // equal keys (about one pair in 10^8): the id decides
                     const int64_t myId = a.id[s + S.ffJ[q]];
                     for (int e = 0; e < nF; e++) {
@@ -474,7 +484,10 @@ __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant 
     }
 }
 
-__global__ void __launch_bounds__(CW * 32)
+#ifndef QHG_SCATTER_MINB
+#define QHG_SCATTER_MINB 9
+#endif
+__global__ void __launch_bounds__(CW * 32, QHG_SCATTER_MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCells, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, int *__restrict__ cursor,

@@ -80,6 +80,7 @@ struct ActParams {
     // Fertility (actions/Fertility.cpp:49-74)
     float fertMinAge, fertMaxAge, fertInterbirth;
     RngKey key;
+    RoundKeys rk;  // the ten Philox round keys of `key` (read straight from the constant bank by the fast path)
 };
 
 __host__ __device__ __forceinline__ int prog_op(const ActParams &P, int k) { return (int)((P.prog >> (4 * k)) & 15ull); }

@@ -408,6 +408,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     P.t = t;
     P.storeAge = 1;
     P.key = p->key;
+    for (int r = 0; r < 10; r++) { P.rk.a[r] = p->key.k0 + (uint32_t)r * 0x9E3779B9u; P.rk.b[r] = p->key.k1 + (uint32_t)r * 0xBB67AE85u; }
     // ATanDeath::preLoop, actions/ATanDeath.cpp:49-59 (EPS = 0.001, actions/ATanDeath.h:14)
     P.atanMaxAge = p->A("ATanDeath_max_age");
     P.atanSlope = p->A("ATanDeath_slope");
