@@ -96,7 +96,7 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 #endif
 template <bool SPEC>
 __global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
-k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int nCells, const int *__restrict__ cellStart,
+k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
               int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec) {
     __shared__ WarpSmem smem[CW];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -120,10 +120,10 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     // not: a static split leaves a long tail)
     for (;;) {
     int cBase = 0;
-    if (lane == 0) cBase = atomicAdd(&st->workDecide, CELL_BATCH);
+    if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, CELL_BATCH);
     cBase = __shfl_sync(FULL, cBase, 0);
-    if (cBase >= nCells) break;
-    for (int c = cBase; c < min(cBase + CELL_BATCH, nCells); c++) {
+    if (cBase >= cHi) break;
+    for (int c = cBase; c < min(cBase + CELL_BATCH, cHi); c++) {
         const int s = cellStart[c], n = cellStart[c + 1] - s;
         if (n == 0) continue;
         if (n > WCAP) {
@@ -208,6 +208,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             for (int u = 0; u < DU; u++) r0[u] = I.needAct0 ? agent_draws_rk(id[u], step, STREAM_ACT0, RK) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int u = 0; u < DU; u++) {
+                if (u > 0 && j0 + u * 32 >= n) break;  // warp-uniform: the cell's tail leaves this sub-chunk empty
                 const int j = j0 + u * 32 + lane;
                 const bool valid = j < n;
                 // fertile census (for the pairing): positions of the fertile females, number of fertile males
@@ -427,33 +428,44 @@ __device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
     return q;
 }
 
-// arrivals this rank sends to every other rank = sum of its arrive[] over the other rank's cells;
-// SHARD_SPLIT blocks per destination rank, info[] zeroed before
-constexpr int SHARD_SPLIT = 32;
+// Arrivals cross a shard boundary only in the halo: the cells with a neighbour owned by another rank (the list is the
+// same on every rank, built in qhgb_comm_init).  Their arrival counts travel as one compact array that is summed over
+// the ranks; this kernel fills it, counts what this rank sends to every other rank (info[q]) and clears the foreign
+// cells' local counters.  info[] is zeroed before the launch.
+constexpr int MAX_RANKS_SMEM = 64;
 __global__ void __launch_bounds__(256)
-k_shard_counts(const int *__restrict__ arrive, const int *__restrict__ cellBegin, int rank, int nranks,
-               const DevStats *__restrict__ st, int *__restrict__ info) {
-    __shared__ int sa[8];
-    const int q = blockIdx.x / SHARD_SPLIT, part = blockIdx.x % SHARD_SPLIT;
-    int sum = 0;
-    if (q != rank) {
-        for (int c = cellBegin[q] + part * 256 + threadIdx.x; c < cellBegin[q + 1]; c += 256 * SHARD_SPLIT) sum += arrive[c];
+k_halo_gather(int nHalo, const int *__restrict__ halo, const int *__restrict__ cellBegin, int rank, int nranks,
+              int *__restrict__ arrive, int *__restrict__ buf, const DevStats *__restrict__ st, int *__restrict__ info) {
+    __shared__ int sInfo[MAX_RANKS_SMEM];
+    const bool useSmem = nranks <= MAX_RANKS_SMEM;
+    if (useSmem) {
+        for (int q = threadIdx.x; q < nranks; q += blockDim.x) sInfo[q] = 0;
+        __syncthreads();
     }
-    sum = warp_sum(sum);
-    if ((threadIdx.x & 31) == 0) sa[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < 8; w++) t += sa[w];
-        if (t) atomicAdd(&info[q], t);
-        if (blockIdx.x == 0) info[nranks] = st->nBirths;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
+        const int c = halo[i];
+        const int v = arrive[c];
+        buf[i] = v;
+        int q = 0;
+        while (q + 1 < nranks && c >= cellBegin[q + 1]) q++;
+        if (q != rank) {
+            if (v) atomicAdd(useSmem ? &sInfo[q] : &info[q], v);
+            arrive[c] = 0;
+        }
     }
+    if (useSmem) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < nranks; q += blockDim.x) if (sInfo[q]) atomicAdd(&info[q], sInfo[q]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) info[nranks] = st->nBirths;
 }
 
-// after the all-reduce of arrive[]: cells of other ranks take no agents here
-__global__ void k_shard_mask(int nCells, int c0, int c1, int *__restrict__ arrive) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
-        if (c < c0 || c >= c1) arrive[c] = 0;
+// after the all-reduce of the halo array: the owned halo cells take the sum over all ranks
+__global__ void k_halo_apply(int nHalo, const int *__restrict__ halo, int c0, int c1, const int *__restrict__ buf,
+                             int *__restrict__ arrive) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
+        const int c = halo[i];
+        if (c >= c0 && c < c1) arrive[c] = buf[i];
     }
 }
 
@@ -488,7 +500,7 @@ __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant 
 #define QHG_SCATTER_MINB 9
 #endif
 __global__ void __launch_bounds__(CW * 32, QHG_SCATTER_MINB)
-k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCells, const int *__restrict__ cellStart,
+k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, int *__restrict__ cursor,
                const int *__restrict__ birthBase, float t, int storeAge, RngKey key, ShardArgs H) {
@@ -502,10 +514,10 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int nCel
     const long long nextID = st->nextID;
     for (;;) {
     int cBase = 0;
-    if (lane == 0) cBase = atomicAdd(&st->workScatter, CELL_BATCH);
+    if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, CELL_BATCH);
     cBase = __shfl_sync(FULL, cBase, 0);
-    if (cBase >= nCells) break;
-    for (int c = cBase; c < min(cBase + CELL_BATCH, nCells); c++) {
+    if (cBase >= cHi) break;
+    for (int c = cBase; c < min(cBase + CELL_BATCH, cHi); c++) {
         const int s = cellStart[c], n = cellStart[c + 1] - s;
         if (n == 0) continue;
         const int ns = newStart[c];

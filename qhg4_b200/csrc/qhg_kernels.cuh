@@ -121,11 +121,11 @@ __device__ __forceinline__ int warp_sum(int v) {
 // ---------------------------------------------------------------------------------------------
 // per-cell: Verhulst birth and death probabilities from last step's counts
 // (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and reset of the step's counters
-__global__ void k_cell_init(int nCells, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
+__global__ void k_cell_init(int cLo, int cHi, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
                             double b0, double d0, double theta, double K, const double *__restrict__ Kcell, int doVerhulst,
                             int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
                             int *__restrict__ birthCount, int *__restrict__ nFert) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+    for (int c = cLo + blockIdx.x * blockDim.x + threadIdx.x; c < cHi; c += gridDim.x * blockDim.x) {  // the cells this GPU owns
         if (doVerhulst) {
             const double Kc = Kcell ? Kcell[c] : K;  // VerhulstVarK: the carrying capacity of the cell (actions/VerhulstVarK.cpp)
             if (Kcell && Kc <= 0) {               // LinearBirth.cpp:104-105, LinearDeath.cpp:113-114

@@ -131,7 +131,9 @@ struct DevBuf {
         p = nullptr;
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaMemset(p, 0, count * sizeof(T));  // per-cell counters of cells another rank owns are never touched again
     }
     void release() {
         if (p) cudaFree(p);
@@ -220,10 +222,16 @@ struct qhgb_pop {
     bool sharded = false;
     int shRank = 0, shRanks = 1;
     std::vector<int> cellBegin;
+    std::vector<int> hNbr;  // host copy of the neighbour table (halo construction)
     ncclComm_t comm = nullptr;
     DevBuf<int> dCellBegin, dInfo, dAllInfo, dSendOff, dSendCursor;
+    DevBuf<int> dHalo, dHaloBuf;  // cells with a neighbour on another rank (same list on all ranks) and their exchanged arrival counts
+    int nHalo = 0;
+    int cLo() const { return sharded ? cellBegin[shRank] : 0; }
+    int cHi() const { return sharded ? cellBegin[shRank + 1] : nCells; }
     DevBuf<Migrant> sendBuf, recvBuf;
     int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
+    int *hCount = nullptr;    // pinned: per-cell counts on their way to the host
     int64_t lastSent = 0, lastReceived = 0;
 
     bool timing = false;
@@ -288,6 +296,22 @@ struct qhgb_pop {
         }                                                                      \
         kern<<<(grid), (block), (smem), (p)->stream>>>(__VA_ARGS__);           \
         (p)->launches++;                                                       \
+        if ((p)->timing) {                                                     \
+            cudaEventRecord(e1_, (p)->stream);                                 \
+            (p)->kt(name).pending.push_back({e0_, e1_});                       \
+        }                                                                      \
+    } while (0)
+
+// any stream-ordered statement (NCCL calls, copies) under the same optional event timing as the kernels
+#define TIMED(p, name, ...)                                                    \
+    do {                                                                       \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                              \
+        if ((p)->timing) {                                                     \
+            cudaEventCreate(&e0_);                                             \
+            cudaEventCreate(&e1_);                                             \
+            cudaEventRecord(e0_, (p)->stream);                                 \
+        }                                                                      \
+        __VA_ARGS__;                                                           \
         if ((p)->timing) {                                                     \
             cudaEventRecord(e1_, (p)->stream);                                 \
             (p)->kt(name).pending.push_back({e0_, e1_});                       \
@@ -631,7 +655,7 @@ CellEnv cellEnv(qhgb_pop *p) {
 int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
     qhgb_pop &q = *p;
     LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
-    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.nCells), 256, q.nCells, q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
+    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.cHi() - q.cLo()), 256, q.cLo(), q.cHi(), q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
            q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), q.findKind(A_VERHULSTVARK) ? q.cap.p : nullptr, doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
            q.birthCount.p, q.nFert.p);
     CK(cudaGetLastError());
@@ -688,14 +712,16 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     for (int k = 0; k < P.nOps; k++) if (prog_op(P, k) == OP_NAVIGATE) tiled = false;  // far jumps: generic path only (for now)
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
     long long stepEndBirths = -1;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;  // device time of the whole pipeline, gaps between the launches included
+    if (q.timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, q.stream); }
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
             const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
             if (P.prog == PROG_TUT5 && P.nOps == 5) {  // the tutorial action order: compile-time specialised kernel
-                LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells,
+                LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
             } else {
-                LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.nCells,
+                LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
             }
             ShardArgs H{};
@@ -703,15 +729,17 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             int nRecv = 0;
             std::vector<int> sendCnt, recvCnt;
             if (q.sharded) {
-                // (1) what this rank sends to every other rank, (2) arrivals per cell summed over all ranks,
+                // (1) what this rank sends to every other rank, (2) arrivals per halo cell summed over all ranks,
                 // (3) everybody learns every count (and the births per rank: newborn ids are global ranks)
                 const int R = q.shRanks;
                 CK(cudaMemsetAsync(q.dInfo.p, 0, sizeof(int) * (R + 1), q.stream));
-                LAUNCH(p, "k_shard_counts", k_shard_counts, R * SHARD_SPLIT, 256, q.arrive.p, q.dCellBegin.p, q.shRank, R, q.dstats.p, q.dInfo.p);
-                NK(g_nccl.AllReduce(q.arrive.p, q.arrive.p, (size_t)q.nCells, ncclInt32, ncclSum, q.comm, q.stream));
-                NK(g_nccl.AllGather(q.dInfo.p, q.dAllInfo.p, (size_t)(R + 1), ncclInt32, q.comm, q.stream));
+                LAUNCH(p, "k_halo_gather", k_halo_gather, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.arrive.p,
+                       q.dHaloBuf.p, q.dstats.p, q.dInfo.p);
+                if (q.nHalo > 0) TIMED(p, "nccl_allreduce_halo", NK(g_nccl.AllReduce(q.dHaloBuf.p, q.dHaloBuf.p, (size_t)q.nHalo, ncclInt32, ncclSum, q.comm, q.stream)));
+                TIMED(p, "nccl_allgather_info", NK(g_nccl.AllGather(q.dInfo.p, q.dAllInfo.p, (size_t)(R + 1), ncclInt32, q.comm, q.stream)));
                 CK(cudaMemcpyAsync(q.hAllInfo, q.dAllInfo.p, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
-                LAUNCH(p, "k_shard_mask", k_shard_mask, q.gridFor(q.nCells), 256, q.nCells, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1], q.arrive.p);
+                LAUNCH(p, "k_halo_apply", k_halo_apply, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
+                       q.dHaloBuf.p, q.arrive.p);
                 CK(cudaStreamSynchronize(q.stream));
                 sendCnt.assign(R, 0); recvCnt.assign(R, 0);
                 std::vector<int> sendOff(R + 1, 0);
@@ -736,11 +764,13 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
-            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * 16, CW * 32, q.dstats.p, a, o, q.nCells, q.cellStart[q.cur].p, q.dec.p,
+            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * 16, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
             if (q.sharded) {  // agent migration: packed records straight between the GPUs (NCCL over NVLink)
                 const int R = q.shRanks;
                 int so = 0, ro = 0;
+                cudaEvent_t g0 = nullptr, g1 = nullptr;
+                if (q.timing) { cudaEventCreate(&g0); cudaEventCreate(&g1); cudaEventRecord(g0, q.stream); }
                 NK(g_nccl.GroupStart());
                 for (int r = 0; r < R; r++) {
                     if (sendCnt[r] > 0) NK(g_nccl.Send(q.sendBuf.p + so, (size_t)sendCnt[r] * sizeof(Migrant), ncclUint8, r, q.comm, q.stream));
@@ -749,6 +779,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                     ro += recvCnt[r];
                 }
                 NK(g_nccl.GroupEnd());
+                if (q.timing) { cudaEventRecord(g1, q.stream); q.kt("nccl_sendrecv_migrants").pending.push_back({g0, g1}); }
                 if (nRecv > 0) {
                     LAUNCH(p, "k_place_migrants", k_place_migrants, q.gridFor(nRecv), 256, q.dstats.p, q.recvBuf.p, nRecv, o,
                            q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
@@ -776,6 +807,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         }
         LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
         CK(cudaGetLastError());
+        if (q.timing && attempt == 0) { cudaEventRecord(t1, q.stream); q.kt("pipeline_total").pending.push_back({t0, t1}); }
         if (pullStats(p) != 0) return -1;
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
             if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
@@ -918,6 +950,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
     p->oflags.release(); p->dec.release(); p->pkey.release(); p->dstats.release();
     if (p->comm) g_nccl.CommDestroy(p->comm);
+    if (p->hCount) cudaFreeHost(p->hCount);
     if (p->hAllInfo) cudaFreeHost(p->hAllInfo);
     p->dCellBegin.release(); p->dInfo.release(); p->dAllInfo.release(); p->dSendOff.release(); p->dSendCursor.release();
     p->sendBuf.release(); p->recvBuf.release();
@@ -945,10 +978,12 @@ int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
         nn[c] = (uint8_t)k;
         p->hGid[c] = global_id ? global_id[c] : (int32_t)c;
     }
+    p->hNbr.assign(nbr, nbr + nc * MAXN);
     CK(cudaMemcpyAsync(p->nbr.p, nbr, nc * MAXN * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->nNbr.p, nn.data(), nc, cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->gid.p, p->hGid.data(), nc * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if (!p->hCount) CK(cudaMallocHost(&p->hCount, sizeof(int) * nc));  // pinned staging buffer of qhgb_get_num_agents_array
     p->haveCells = true;
     return 0;
 }
@@ -1311,11 +1346,14 @@ int64_t qhgb_get_num_agents_effective(qhgb_pop *p) { return p ? p->nAgents : -1;
 
 int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     if (!p || !out) return fail("qhgb_get_num_agents_array: NULL argument");
+    if (!p->hCount) return fail("qhgb_get_num_agents_array: call qhgb_set_cells first");
     CK(cudaSetDevice(p->device));
-    std::vector<int> h(p->nCells);
-    CK(cudaMemcpyAsync(h.data(), p->count[p->cur].p, (size_t)p->nCells * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    const int c0 = p->cLo(), c1 = p->cHi();  // a shard holds agents in its own cells only
+    if (c1 > c0) CK(cudaMemcpyAsync(p->hCount + c0, p->count[p->cur].p + c0, (size_t)(c1 - c0) * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    for (int c = 0; c < p->nCells; c++) out[c] = (uint64_t)h[c];
+    if (c0 > 0) memset(out, 0, sizeof(uint64_t) * (size_t)c0);
+    for (int c = c0; c < c1; c++) out[c] = (uint64_t)p->hCount[c];
+    if (c1 < p->nCells) memset(out + c1, 0, sizeof(uint64_t) * (size_t)(p->nCells - c1));
     return 0;
 }
 
@@ -1513,6 +1551,7 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
     if (!p || !unique_id || !cell_begin) return fail("qhgb_comm_init: NULL argument");
     if (p->nAgents > 0 || p->preLooped) return fail("qhgb_comm_init: must be called before agents are added");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("qhgb_comm_init: rank %d of %d", rank, nranks);
+    if (!p->haveCells) return fail("qhgb_comm_init: call qhgb_set_cells first");
     if (cell_begin[0] != 0 || cell_begin[nranks] != p->nCells) return fail("qhgb_comm_init: cell ranges must cover [0, %d)", p->nCells);
     for (int r = 0; r < nranks; r++) if (cell_begin[r + 1] < cell_begin[r]) return fail("qhgb_comm_init: cell ranges must be ascending");
     if (loadNccl() != 0) return -1;
@@ -1530,7 +1569,25 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
     CK(p->dSendCursor.alloc(nranks));
     CK(cudaMallocHost(&p->hAllInfo, sizeof(int) * nranks * (nranks + 1)));
     CK(cudaMemcpyAsync(p->dCellBegin.p, p->cellBegin.data(), sizeof(int) * (nranks + 1), cudaMemcpyHostToDevice, p->stream));
-    CK(cudaStreamSynchronize(p->stream));
+    // the halo: every cell with a neighbour owned by another rank (tools_ico/EQTileLinks.h:20-24 keeps the same sets per tile)
+    {
+        auto owner = [&](int c) { return (int)(std::upper_bound(p->cellBegin.begin() + 1, p->cellBegin.end(), c) - (p->cellBegin.begin() + 1)); };
+        std::vector<uint8_t> mark(p->nCells, 0);
+        for (int c = 0; c < p->nCells; c++) {
+            const int oc = owner(c);
+            for (int j = 0; j < MAXN; j++) {
+                const int d = p->hNbr[(size_t)c * MAXN + j];
+                if (d >= 0 && owner(d) != oc) { mark[c] = 1; mark[d] = 1; }
+            }
+        }
+        std::vector<int> halo;
+        for (int c = 0; c < p->nCells; c++) if (mark[c]) halo.push_back(c);
+        p->nHalo = (int)halo.size();
+        CK(p->dHalo.alloc(halo.size() + 1));
+        CK(p->dHaloBuf.alloc(halo.size() + 1));
+        if (!halo.empty()) CK(cudaMemcpyAsync(p->dHalo.p, halo.data(), sizeof(int) * halo.size(), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
     p->sharded = nranks > 1;
     return 0;
 }
