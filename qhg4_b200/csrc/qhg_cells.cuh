@@ -472,10 +472,10 @@ __global__ void k_halo_apply(int nHalo, const int *__restrict__ halo, int c0, in
 // the per-agent cell index is implied by cellStart on the fast path; this writes it out when somebody needs it
 // (generic path, records handed back to the host)
 __global__ void __launch_bounds__(256)
-k_fill_cells(int nCells, const int *__restrict__ cellStart, int *__restrict__ cell) {
+k_fill_cells(int cLo, int cHi, const int *__restrict__ cellStart, int *__restrict__ cell) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
-    for (int c = gw; c < nCells; c += nW) {
+    for (int c = cLo + gw; c < cHi; c += nW) {  // a shard holds agents in its own cells only
         const int s = cellStart[c], e = cellStart[c + 1];
         for (int i = s + lane; i < e; i += 32) cell[i] = c;
     }

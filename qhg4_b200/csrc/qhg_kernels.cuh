@@ -121,10 +121,19 @@ __device__ __forceinline__ int warp_sum(int v) {
 // ---------------------------------------------------------------------------------------------
 // per-cell: Verhulst birth and death probabilities from last step's counts
 // (actions/LinearBirth.cpp:97-112, actions/LinearDeath.cpp:101-119), and reset of the step's counters
-__global__ void k_cell_init(int cLo, int cHi, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
+__global__ void k_cell_init(DevStats *__restrict__ st, int cLo, int cHi, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
                             double b0, double d0, double theta, double K, const double *__restrict__ Kcell, int doVerhulst,
                             int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
                             int *__restrict__ birthCount, int *__restrict__ nFert) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the step's tallies and work counters start from zero
+        st->nBirths = 0;
+        st->nDeaths = 0;
+        st->nMoves = 0;
+        st->nNew = 0;
+        st->oversize = 0;
+        st->workDecide = 0;
+        st->workScatter = 0;
+    }
     for (int c = cLo + blockIdx.x * blockDim.x + threadIdx.x; c < cHi; c += gridDim.x * blockDim.x) {  // the cells this GPU owns
         if (doVerhulst) {
             const double Kc = Kcell ? Kcell[c] : K;  // VerhulstVarK: the carrying capacity of the cell (actions/VerhulstVarK.cpp)
@@ -494,16 +503,37 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
 // Two kernels: per-tile sums, then every tile adds the sums of the tiles before it.
 constexpr int SCAN_TILE = 2048;  // cells per block (256 threads x 8)
 
+// The scan runs over the cells [cA, cHi): the rank's own range, its start rounded down to a multiple of 8 (the counters
+// of cells owned by other ranks are zero), so that every thread's 8 cells are two aligned 128-bit words.
+__device__ __forceinline__ void load8(const int *__restrict__ p, int c0, int cHi, int v[8]) {
+    if (c0 + 8 <= cHi) {
+        const int4 x = *reinterpret_cast<const int4 *>(p + c0), y = *reinterpret_cast<const int4 *>(p + c0 + 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (c0 + k < cHi) ? p[c0 + k] : 0;
+    }
+}
+__device__ __forceinline__ void store8(int *__restrict__ p, int c0, int cHi, const int v[8]) {
+    if (c0 + 8 <= cHi) {
+        *reinterpret_cast<int4 *>(p + c0) = make_int4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<int4 *>(p + c0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (c0 + k < cHi) p[c0 + k] = v[k];
+    }
+}
+
 __global__ void __launch_bounds__(256)
-k_scan_tiles(int nCells, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
+k_scan_tiles(int cA, int cHi, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
              int2 *__restrict__ tileSums) {
     __shared__ int sa[8], sb[8];
-    int base = blockIdx.x * SCAN_TILE;
+    const int c0 = cA + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    int s8[8], a8[8], b8[8];
+    load8(stay, c0, cHi, s8); load8(arrive, c0, cHi, a8); load8(birthCount, c0, cHi, b8);
     int sumA = 0, sumB = 0;
-    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) {
-        int c = base + k;
-        if (c < nCells) { int b = birthCount[c]; sumA += stay[c] + arrive[c] + b; sumB += b; }
-    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { sumA += s8[k] + a8[k] + b8[k]; sumB += b8[k]; }
     sumA = warp_sum(sumA); sumB = warp_sum(sumB);
     if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = sumA; sb[threadIdx.x >> 5] = sumB; }
     __syncthreads();
@@ -515,7 +545,7 @@ k_scan_tiles(int nCells, const int *__restrict__ stay, const int *__restrict__ a
 }
 
 __global__ void __launch_bounds__(256)
-k_scan_apply(int nCells, int nTiles, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
+k_scan_apply(int cA, int cHi, int nTiles, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
              const int2 *__restrict__ tileSums, int *__restrict__ newStart, int *__restrict__ birthBase,
              int *__restrict__ count, DevStats *__restrict__ st, int capacity) {
     __shared__ int sa[8], sb[8];
@@ -533,16 +563,15 @@ k_scan_apply(int nCells, int nTiles, const int *__restrict__ stay, const int *__
     }
     __syncthreads();
     // each thread owns 8 consecutive cells
-    int c0 = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
-    int va[8], vb[8];
+    const int c0 = cA + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    int s8[8], a8[8], b8[8], va[8], vb[8], vc[8];
+    load8(stay, c0, cHi, s8); load8(arrive, c0, cHi, a8); load8(birthCount, c0, cHi, b8);
     int ta = 0, tb = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        int c = c0 + k;
-        int b = (c < nCells) ? birthCount[c] : 0;
-        int v = (c < nCells) ? stay[c] + arrive[c] + b : 0;
+        vc[k] = s8[k] + a8[k] + b8[k];
         va[k] = ta; vb[k] = tb;
-        ta += v; tb += b;
+        ta += vc[k]; tb += b8[k];
     }
     // block exclusive scan of (ta, tb)
     int ia = ta, ib = tb;
@@ -557,19 +586,15 @@ k_scan_apply(int nCells, int nTiles, const int *__restrict__ stay, const int *__
     __syncthreads();
     int wa = 0, wb = 0;
     for (int w = 0; w < wid; w++) { wa += sa[w]; wb += sb[w]; }
-    int exA = baseA + wa + ia - ta, exB = baseB + wb + ib - tb;
+    const int exA = baseA + wa + ia - ta, exB = baseB + wb + ib - tb;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int c = c0 + k;
-        if (c < nCells) {
-            newStart[c] = exA + va[k];
-            birthBase[c] = exB + vb[k];
-            count[c] = stay[c] + arrive[c] + birthCount[c];
-        }
-    }
+    for (int k = 0; k < 8; k++) { va[k] += exA; vb[k] += exB; }
+    store8(newStart, c0, cHi, va);
+    store8(birthBase, c0, cHi, vb);
+    store8(count, c0, cHi, vc);
     if (blockIdx.x == nTiles - 1 && threadIdx.x == 255) {
-        int total = exA + ta;
-        newStart[nCells] = total;
+        const int total = exA + ta;
+        newStart[cHi] = total;
         st->nNew = total;
         if (total > capacity) st->overflow = 1;
     }
@@ -633,16 +658,6 @@ __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths
     st->nAgents = st->nNew;
     st->nextID += (globalBirths >= 0) ? globalBirths : (long long)st->nBirths;
     if (advanceStep) st->step++;
-}
-
-__global__ void k_step_begin(DevStats *st) {
-    st->nBirths = 0;
-    st->nDeaths = 0;
-    st->nMoves = 0;
-    st->nNew = 0;
-    st->oversize = 0;
-    st->workDecide = 0;
-    st->workScatter = 0;
 }
 
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {

@@ -654,8 +654,7 @@ CellEnv cellEnv(qhgb_pop *p) {
 
 int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
     qhgb_pop &q = *p;
-    LAUNCH(p, "k_step_begin", k_step_begin, 1, 1, q.dstats.p);
-    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.cHi() - q.cLo()), 256, q.cLo(), q.cHi(), q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
+    LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.cHi() - q.cLo()), 256, q.dstats.p, q.cLo(), q.cHi(), q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
            q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), q.findKind(A_VERHULSTVARK) ? q.cap.p : nullptr, doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
            q.birthCount.p, q.nFert.p);
     CK(cudaGetLastError());
@@ -665,7 +664,7 @@ int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
 int ensureCells(qhgb_pop *p) {
     if (p->cellValid) return 0;
     if (p->nAgents > 0) {
-        LAUNCH(p, "k_fill_cells", k_fill_cells, p->gridFor((int64_t)p->nCells * 32), 256, p->nCells, p->cellStart[p->cur].p, p->cell[p->cur].p);
+        LAUNCH(p, "k_fill_cells", k_fill_cells, p->gridFor((int64_t)(p->cHi() - p->cLo()) * 32), 256, p->cLo(), p->cHi(), p->cellStart[p->cur].p, p->cell[p->cur].p);
         CK(cudaGetLastError());
     }
     p->cellValid = true;
@@ -693,9 +692,10 @@ int ensurePairing(qhgb_pop *p) {
 
 int launchScan(qhgb_pop *p) {
     qhgb_pop &q = *p;
-    const int nTiles = (q.nCells + SCAN_TILE - 1) / SCAN_TILE;
-    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, q.nCells, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p);
-    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, q.nCells, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p,
+    const int cA = q.cLo() & ~7, cHi = q.cHi();  // own cells; the start rounded down for aligned 128-bit accesses
+    const int nTiles = std::max(1, (cHi - cA + SCAN_TILE - 1) / SCAN_TILE);
+    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, cA, cHi, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p);
+    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, cA, cHi, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p,
            q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count[q.cur ^ 1].p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
     return 0;
 }
@@ -732,12 +732,14 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 // (1) what this rank sends to every other rank, (2) arrivals per halo cell summed over all ranks,
                 // (3) everybody learns every count (and the births per rank: newborn ids are global ranks)
                 const int R = q.shRanks;
-                CK(cudaMemsetAsync(q.dInfo.p, 0, sizeof(int) * (R + 1), q.stream));
+                // the exchange buffer: nHalo arrival counts, then one row of R+1 ints per rank (everybody fills its own row,
+                // the sum over the ranks is the gathered table)
+                int *const infoAll = q.dHaloBuf.p + q.nHalo;
+                CK(cudaMemsetAsync(infoAll, 0, sizeof(int) * R * (R + 1), q.stream));
                 LAUNCH(p, "k_halo_gather", k_halo_gather, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.arrive.p,
-                       q.dHaloBuf.p, q.dstats.p, q.dInfo.p);
-                if (q.nHalo > 0) TIMED(p, "nccl_allreduce_halo", NK(g_nccl.AllReduce(q.dHaloBuf.p, q.dHaloBuf.p, (size_t)q.nHalo, ncclInt32, ncclSum, q.comm, q.stream)));
-                TIMED(p, "nccl_allgather_info", NK(g_nccl.AllGather(q.dInfo.p, q.dAllInfo.p, (size_t)(R + 1), ncclInt32, q.comm, q.stream)));
-                CK(cudaMemcpyAsync(q.hAllInfo, q.dAllInfo.p, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
+                       q.dHaloBuf.p, q.dstats.p, infoAll + q.shRank * (R + 1));
+                TIMED(p, "nccl_allreduce_halo", NK(g_nccl.AllReduce(q.dHaloBuf.p, q.dHaloBuf.p, (size_t)q.nHalo + (size_t)R * (R + 1), ncclInt32, ncclSum, q.comm, q.stream)));
+                CK(cudaMemcpyAsync(q.hAllInfo, infoAll, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
                 LAUNCH(p, "k_halo_apply", k_halo_apply, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
                        q.dHaloBuf.p, q.arrive.p);
                 CK(cudaStreamSynchronize(q.stream));
@@ -1584,7 +1586,7 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
         for (int c = 0; c < p->nCells; c++) if (mark[c]) halo.push_back(c);
         p->nHalo = (int)halo.size();
         CK(p->dHalo.alloc(halo.size() + 1));
-        CK(p->dHaloBuf.alloc(halo.size() + 1));
+        CK(p->dHaloBuf.alloc(halo.size() + (size_t)nranks * (nranks + 1)));
         if (!halo.empty()) CK(cudaMemcpyAsync(p->dHalo.p, halo.data(), sizeof(int) * halo.size(), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
     }
