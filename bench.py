@@ -96,9 +96,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-SETTLE_STEPS = 150
-
-
 def build_world(subdiv, n_agents, seed=1):
     from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_population
     from qhg4_b200.params import tut_environ_alt
@@ -171,13 +168,6 @@ def run_ours(args, rank, world):
     for _ in range(args.warmup):
         g.step(t); t += 1.0
     g.synchronize()
-    # settle: the first steps after start-up run measurably slower (clocks and power state still ramping); keep stepping,
-    # untimed, for a fixed number of steps (the same on every rank) so that the timed region sees a warm device
-    settle = SETTLE_STEPS
-    for _ in range(settle):
-        g.step(t); t += 1.0
-    g.synchronize()
-
     def allsum(x):
         if dist is None:
             return x
@@ -268,7 +258,7 @@ def run_ours(args, rank, world):
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}}
 
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "settle_steps": settle, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C4: tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove+SingleEvaluator[Alt], Fertility, "
                                    f"RandomPair, Verhulst), {args.agents} agents on the subdivision-256 icosahedral grid"

@@ -3,5 +3,5 @@
 for f in build/libs/*.so; do
   cp "$f" qhg4_b200/libqhg_b200.so
   echo "== $f"
-  python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernels_ms_per_step'])"
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernels_ms_per_step'])"
 done

@@ -31,16 +31,14 @@ constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles;
 constexpr int MAXF = 512;        // most fertile females of one cell that can be ranked in shared memory
 constexpr int QCAP = 128;        // work-queue entries per warp (flushed when more than half full)
 constexpr int MVCAP = 64;        // movers queued per warp in the scatter pass
+constexpr int MOVE_STRIDE = 8;    // ints per cell in moveBase[] (one 32-byte sector)
+constexpr int AGENT_SLACK = 64;  // elements allocated past the capacity of every per-agent array (aligned bulk reads)
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
 #ifndef QHG_CELL_BATCH
 #define QHG_CELL_BATCH 4
 #endif
 constexpr int CELL_BATCH = QHG_CELL_BATCH;    // consecutive cells a warp takes per grab of the work counter
 constexpr int DU = 2;            // agents per lane and chunk in the decide pass
-#ifndef QHG_SU
-#define QHG_SU 2
-#endif
-constexpr int SU = QHG_SU;            // the same in the scatter pass
 
 // decision byte handed from pass 1 to pass 2: bit0 male, bit1 fertile (the agent's new flags), bit2 gave birth,
 // bits 3-5 move code: 0 stays, 1..6 neighbour slot + 1, 7 dead
@@ -97,7 +95,8 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 template <bool SPEC>
 __global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
 k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
-              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec) {
+              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
+              int *__restrict__ moveBase) {
     __shared__ WarpSmem smem[CW];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmem &S = smem[wid];
@@ -108,6 +107,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     const int nOps = SPEC ? 5 : P.nOps;
     const ProgramInfo I = program_info(prog, nOps);
     int nDead = 0, nMove = 0, nBorn = 0;  // warp-uniform tallies
+    int pendCell = -1, pendBase = 0;      // slot reservation of the previous cell, stored one cell later (atomic latency)
     // loop invariants in registers
     const float tNow = P.t, fertMin = P.fertMinAge, fertMax = P.fertMaxAge, fertInter = P.fertInterbirth;
     const float atanAgeLo = P.atanAgeLo, atanAgeHi = P.atanAgeHi;
@@ -378,13 +378,18 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         __syncwarp();
         if (bornC > MAXMOTHERS && lane == 0) atomicExch(&st->oversize, 1);
         if (lane == 0) { stay[c] = stayC; birthCount[c] = bornC; }  // a cell belongs to exactly one warp: plain stores
+        // the movers towards neighbour k take the slots [base, base+cnt) of that cell's arrivals: pass 2 places them
+        // without atomics
         if (lane < MAXN) {
+            if (pendCell >= 0) moveBase[(size_t)pendCell * MOVE_STRIDE + lane] = pendBase;
             const int cnt = S.outC[lane];
-            if (cnt) atomicAdd(&arrive[E.nbr[(size_t)c * MAXN + lane]], cnt);
+            pendBase = cnt ? atomicAdd(&arrive[S.nbrC[lane]], cnt) : 0;
         }
+        pendCell = c;
         __syncwarp();
     }
     }
+    if (lane < MAXN && pendCell >= 0) moveBase[(size_t)pendCell * MOVE_STRIDE + lane] = pendBase;
     if (lane == 0) {
         if (nDead) atomicAdd(&st->nDeaths, nDead);
         if (nMove) atomicAdd(&st->nMoves, nMove);
@@ -395,10 +400,6 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
 // ---------------------------------------------------------------------------------------------
 // pass 2: counting-sort scatter (performMoves core/SPopulation.cpp:1058-1092) + newborns
 // (makeOffspring / createAgentAtIndex :823-847,880-918; makePopSpecificOffspring populations/tut_EnvironAltPop.cpp:141-149)
-struct WarpSmemB {
-    int64_t motherId[MAXMOTHERS];
-    uint16_t mvJ[MVCAP];  // movers of the cell, worked off together (their atomics and gathers overlap)
-};
 
 // ---- multi-GPU: the grid is sharded by contiguous cell ranges, one range per rank ------------------
 // An agent that moves into a cell of another rank is not written to the local buffer but packed into the send
@@ -435,7 +436,8 @@ __device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
 constexpr int MAX_RANKS_SMEM = 64;
 __global__ void __launch_bounds__(256)
 k_halo_gather(int nHalo, const int *__restrict__ halo, const int *__restrict__ cellBegin, int rank, int nranks,
-              int *__restrict__ arrive, int *__restrict__ buf, const DevStats *__restrict__ st, int *__restrict__ info) {
+              int *__restrict__ arrive, int *__restrict__ cursor, int *__restrict__ buf, const DevStats *__restrict__ st,
+              int *__restrict__ info) {
     __shared__ int sInfo[MAX_RANKS_SMEM];
     const bool useSmem = nranks <= MAX_RANKS_SMEM;
     if (useSmem) {
@@ -451,6 +453,8 @@ k_halo_gather(int nHalo, const int *__restrict__ halo, const int *__restrict__ c
         if (q != rank) {
             if (v) atomicAdd(useSmem ? &sInfo[q] : &info[q], v);
             arrive[c] = 0;
+        } else {
+            cursor[c] = v;  // the local movers hold the slots [0, v) of the cell's arrivals; migrants follow
         }
     }
     if (useSmem) {
@@ -496,127 +500,230 @@ __global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant 
     }
 }
 
-#ifndef QHG_SCATTER_MINB
-#define QHG_SCATTER_MINB 9
+// ---- pass 2 with bulk-copy staging -------------------------------------------------------------------------------
+// The agents of a batch of consecutive cells are one contiguous range of every array.  The warp walks it in windows
+// of SCH agents; lane 0 brings each window into shared memory with four 1-D bulk copies (cp.async.bulk, completion on
+// an mbarrier), SNST windows ahead, so the bytes in flight do not depend on registers or occupancy.  Windows start
+// on a multiple of 16 agents: every source address and size is a multiple of 16 bytes.
+#ifndef QHG_SCH
+#define QHG_SCH 384
 #endif
-__global__ void __launch_bounds__(CW * 32, QHG_SCATTER_MINB)
+#ifndef QHG_SNST
+#define QHG_SNST 1
+#endif
+constexpr int SCH = QHG_SCH;
+constexpr int SNST = QHG_SNST;
+
+struct alignas(128) StagedAgents {
+    int64_t id[SCH];
+    float birth[SCH];
+    float lastBirth[SCH];
+    uint8_t dec[SCH];
+};
+struct alignas(128) WarpSmemS {
+    StagedAgents win[SNST];
+    int64_t motherId[MAXMOTHERS];
+    uint16_t mvJ[MVCAP];
+    unsigned long long bar[SNST];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#ifndef QHG_SCATTER_S_MINB
+#define QHG_SCATTER_S_MINB 6
+#endif
+constexpr int SCATTER_CTAS_PER_SM = QHG_SCATTER_S_MINB;  // persistent grid: this many CTAs per SM
+__global__ void __launch_bounds__(CW * 32, QHG_SCATTER_S_MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
-               const int *__restrict__ stay, const int *__restrict__ arrive, int *__restrict__ cursor,
+               const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
                const int *__restrict__ birthBase, float t, int storeAge, RngKey key, ShardArgs H) {
-    __shared__ WarpSmemB smem[CW];
+    static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
+    __shared__ WarpSmemS smem[CW];
     if (st->overflow || st->oversize) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmemB &S = smem[wid];
+    WarpSmemS &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
     const long long nextID = st->nextID;
-    for (;;) {
-    int cBase = 0;
-    if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, CELL_BATCH);
-    cBase = __shfl_sync(FULL, cBase, 0);
-    if (cBase >= cHi) break;
-    for (int c = cBase; c < min(cBase + CELL_BATCH, cHi); c++) {
-        const int s = cellStart[c], n = cellStart[c + 1] - s;
-        if (n == 0) continue;
-        const int ns = newStart[c];
-        int stayBase = 0, nMothers = 0;
-        int nmv = 0;
-        auto flush_movers = [&]() {
-            __syncwarp();
-            for (int e = lane; e < nmv; e += 32) {
-                const int g = s + S.mvJ[e];
-                const uint8_t v = dec[g];
-                const int d = nbr[(size_t)c * MAXN + (v >> DEC_MOVE_SHIFT) - 1];
-                const int64_t id = a.id[g];
-                const float birth = a.birth[g], lastBirth = a.lastBirth[g];
-                const float age = storeAge ? a.age[g] : 0.0f;
-                if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
-                    const int qo = shard_owner(H, d);
-                    Migrant m;
-                    m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
-                    m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
-                    H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
-                } else {
-                    const int pos = newStart[d] + stay[d] + atomicAdd(&cursor[d], 1);
-                    o.id[pos] = id;
-                    o.birth[pos] = birth;
-                    o.lastBirth[pos] = lastBirth;
-                    o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
-                    if (storeAge) o.age[pos] = age;
-                }
-            }
-            nmv = 0;
-            __syncwarp();
-        };
-        // software pipeline: the next chunk's loads are in flight while this chunk is written; SU chunks of 32 per round
-        uint8_t vN[SU]; int64_t idN[SU]; float birthN[SU], lastN[SU], ageN[SU];
-#pragma unroll
-        for (int u = 0; u < SU; u++) {
-            const int j = u * 32 + lane;
-            vN[u] = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT); idN[u] = 0; birthN[u] = 0; lastN[u] = 0; ageN[u] = 0;
-            if (j < n) {
-                vN[u] = dec[s + j]; idN[u] = a.id[s + j]; birthN[u] = a.birth[s + j]; lastN[u] = a.lastBirth[s + j];
-                if (storeAge) ageN[u] = a.age[s + j];
-            }
-        }
-        for (int j0 = 0; j0 < n; j0 += 32 * SU) {
-            uint8_t vv[SU]; int64_t idv[SU]; float birthv[SU], lastv[SU], agev[SU];
-#pragma unroll
-            for (int u = 0; u < SU; u++) {
-                vv[u] = vN[u]; idv[u] = idN[u]; birthv[u] = birthN[u]; lastv[u] = lastN[u]; agev[u] = ageN[u];
-                vN[u] = (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
-                const int j2 = j0 + 32 * SU + u * 32 + lane;
-                if (j2 < n) {
-                    vN[u] = dec[s + j2]; idN[u] = a.id[s + j2]; birthN[u] = a.birth[s + j2]; lastN[u] = a.lastBirth[s + j2];
-                    if (storeAge) ageN[u] = a.age[s + j2];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SU; u++) {
-                const uint8_t v = vv[u];
-                const int64_t id = idv[u];
-                const int code = v >> DEC_MOVE_SHIFT;
-                const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
-                const unsigned ms = __ballot_sync(FULL, alive && code == 0);
-                const unsigned mb = __ballot_sync(FULL, born);
-                const bool mover = alive && code != 0;
-                const unsigned mm = __ballot_sync(FULL, mover);
-                if (nmv + __popc(mm) > MVCAP) flush_movers();
-                if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)(j0 + u * 32 + lane);
-                nmv += __popc(mm);
-                if (alive && code == 0) {
-                    const int pos = ns + stayBase + __popc(ms & lt);
-                    o.id[pos] = id;
-                    o.birth[pos] = birthv[u];
-                    o.lastBirth[pos] = lastv[u];
-                    o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
-                    if (storeAge) o.age[pos] = agev[u];
-                }
-                if (born) S.motherId[nMothers + __popc(mb & lt)] = id;
-                stayBase += __popc(ms);
-                nMothers += __popc(mb);
-            }
-        }
-        flush_movers();
-        // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
-        const int babyBase = ns + stayBase + arrive[c];
-        for (int m = lane; m < nMothers; m += 32) {
-            const int64_t mid = S.motherId[m];
-            int r = 0;
-            for (int e = 0; e < nMothers; e++) r += (S.motherId[e] < mid) ? 1 : 0;
-            const int64_t cid = nextID + H.birthOffset + birthBase[c] + r;
-            const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
-            const int pos = babyBase + r;
-            o.id[pos] = cid;
-            o.birth[pos] = t;
-            o.lastBirth[pos] = 0.0f;
-            o.flags[pos] = (uint8_t)(gnd ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
-            if (storeAge) o.age[pos] = 0.0f;
-        }
-        __syncwarp();
+    if (lane == 0) {
+        for (int k = 0; k < SNST; k++) mbar_init(&S.bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    __syncwarp();
+    unsigned phase = 0;  // parity of the next completion of every stage's barrier
+    for (;;) {
+        int cBase = 0;
+        if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, CELL_BATCH);
+        cBase = __shfl_sync(FULL, cBase, 0);
+        if (cBase >= cHi) break;
+        const int cEnd = min(cBase + CELL_BATCH, cHi);
+        // lane l keeps the numbers of cell cBase+l (lane CELL_BATCH-or-less: the end of the batch)
+        int csL = 0, nsL = 0, arL = 0, bbL = 0, nbL = -1;
+        if (cBase + lane <= cEnd) csL = cellStart[cBase + lane];
+        if (cBase + lane / MAXN < cEnd && lane < CELL_BATCH * MAXN) nbL = nbr[(size_t)cBase * MAXN + lane];  // lane = cell*MAXN + direction
+        if (cBase + lane < cEnd) { nsL = newStart[cBase + lane]; arL = arrive[cBase + lane]; bbL = birthBase[cBase + lane]; }
+        const int gs = __shfl_sync(FULL, csL, 0), ge = __shfl_sync(FULL, csL, cEnd - cBase);
+        if (ge == gs) continue;
+        const int g0 = gs & ~15;
+        const int nWin = (ge - g0 + SCH - 1) / SCH;
+        auto issue = [&](int k) {  // lane 0: start the copies of window k
+            const int w0 = g0 + k * SCH;
+            const int cnt = min(SCH, (ge - w0 + 15) & ~15);
+            StagedAgents &W = S.win[k % SNST];
+            unsigned long long *bar = &S.bar[k % SNST];
+            mbar_expect_tx(bar, (uint32_t)cnt * 17u);
+            bulk_g2s(W.id, a.id + w0, (uint32_t)cnt * 8u, bar);
+            bulk_g2s(W.birth, a.birth + w0, (uint32_t)cnt * 4u, bar);
+            bulk_g2s(W.lastBirth, a.lastBirth + w0, (uint32_t)cnt * 4u, bar);
+            bulk_g2s(W.dec, dec + w0, (uint32_t)cnt, bar);
+        };
+        if (lane == 0) for (int k = 0; k < min(nWin, SNST); k++) issue(k);
+
+        int ci = 0;  // cell of the batch the walk is in
+        int s = gs, e = __shfl_sync(FULL, csL, 1);
+        while (ci < cEnd - cBase && e == s) { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); }
+        int ns = 0, stayBase = 0, nMothers = 0, nmv = 0;
+        // lane k < MAXN: where the movers of this cell towards neighbour k go.  The three loads are issued when the
+        // cell begins and first used when its movers are flushed.
+        int dirCell = -1, dirA = 0, dirB = 0, dirC = 0, dirOff = 0;
+        auto begin_cell = [&]() {
+            ns = __shfl_sync(FULL, nsL, ci);
+            stayBase = 0; nMothers = 0;
+            const int d = __shfl_sync(FULL, nbL, min(ci * MAXN + lane, 31));
+            dirCell = -1; dirA = 0; dirB = 0; dirC = 0; dirOff = 0;
+            if (lane < MAXN && d >= 0) {
+                dirCell = d;
+                if (!(H.on && (d < H.c0 || d >= H.c1))) {
+                    dirA = newStart[d]; dirB = stay[d]; dirC = moveBase[(size_t)(cBase + ci) * MOVE_STRIDE + lane];
+                }
+            }
+        };
+        begin_cell();
+        for (int k = 0; k < nWin; k++) {
+            const int w0 = g0 + k * SCH, w1 = min(w0 + SCH, ge);
+            const StagedAgents &W = S.win[k % SNST];
+            mbar_wait(&S.bar[k % SNST], (phase >> (k % SNST)) & 1u);
+            phase ^= 1u << (k % SNST);
+            auto flush_movers = [&]() {  // the queued movers of cell cBase+ci; their records are in this window
+                __syncwarp();
+                for (int q0 = 0; q0 < nmv; q0 += 32) {
+                    const int q = q0 + lane;
+                    const bool act = q < nmv;
+                    const int x = act ? S.mvJ[q] : 0;
+                    const uint8_t v = act ? W.dec[x] : (uint8_t)0;
+                    const int dir = act ? (v >> DEC_MOVE_SHIFT) - 1 : -1;
+                    // rank among the movers of the same direction: slots were reserved per (cell, direction) in pass 1
+                    unsigned mine = 0;
+                    int cntL = 0;
+#pragma unroll
+                    for (int L = 0; L < MAXN; L++) {
+                        const unsigned b = __ballot_sync(FULL, dir == L);
+                        if (dir == L) mine = b;
+                        if (lane == L) cntL = __popc(b);
+                    }
+                    const int base = dirA + dirB + dirC + dirOff;
+                    const int pos = __shfl_sync(FULL, base, max(dir, 0)) + __popc(mine & lt);
+                    const int d = __shfl_sync(FULL, dirCell, max(dir, 0));
+                    dirOff += cntL;
+                    if (act) {
+                        const int64_t id = W.id[x];
+                        const float birth = W.birth[x], lastBirth = W.lastBirth[x];
+                        const float age = storeAge ? a.age[w0 + x] : 0.0f;
+                        if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
+                            const int qo = shard_owner(H, d);
+                            Migrant m;
+                            m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
+                            m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
+                            H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                        } else {
+                            o.id[pos] = id;
+                            o.birth[pos] = birth;
+                            o.lastBirth[pos] = lastBirth;
+                            o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
+                            if (storeAge) o.age[pos] = age;
+                        }
+                    }
+                }
+                nmv = 0;
+                __syncwarp();
+            };
+            while (ci < cEnd - cBase) {
+                const int lo = max(s, w0), hi = min(e, w1);
+                for (int j0 = lo; j0 < hi; j0 += 32) {
+                    const int j = j0 + lane, x = j - w0;
+                    const bool valid = j < hi;
+                    const uint8_t v = valid ? W.dec[x] : (uint8_t)(DEC_DEAD << DEC_MOVE_SHIFT);
+                    const int code = v >> DEC_MOVE_SHIFT;
+                    const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
+                    const bool stays = alive && code == 0, mover = alive && code != 0;
+                    const unsigned ms = __ballot_sync(FULL, stays), mb = __ballot_sync(FULL, born), mm = __ballot_sync(FULL, mover);
+                    if (nmv + __popc(mm) > MVCAP) flush_movers();
+                    if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)x;
+                    nmv += __popc(mm);
+                    if (stays) {
+                        const int pos = ns + stayBase + __popc(ms & lt);
+                        o.id[pos] = W.id[x];
+                        o.birth[pos] = W.birth[x];
+                        o.lastBirth[pos] = W.lastBirth[x];
+                        o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
+                        if (storeAge) o.age[pos] = a.age[j];
+                    }
+                    if (born) S.motherId[nMothers + __popc(mb & lt)] = W.id[x];
+                    stayBase += __popc(ms);
+                    nMothers += __popc(mb);
+                }
+                if (e > w1) break;  // the cell goes on in the next window
+                // ---- the cell is complete ----
+                if (nmv > 0) flush_movers(); else __syncwarp();
+                // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
+                const int babyBase = ns + stayBase + __shfl_sync(FULL, arL, ci);
+                const int bb = __shfl_sync(FULL, bbL, ci);
+                for (int m = lane; m < nMothers; m += 32) {
+                    const int64_t mid = S.motherId[m];
+                    int r = 0;
+                    for (int q = 0; q < nMothers; q++) r += (S.motherId[q] < mid) ? 1 : 0;
+                    const int64_t cid = nextID + H.birthOffset + bb + r;
+                    const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
+                    const int pos = babyBase + r;
+                    o.id[pos] = cid;
+                    o.birth[pos] = t;
+                    o.lastBirth[pos] = 0.0f;
+                    o.flags[pos] = (uint8_t)(gnd ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
+                    if (storeAge) o.age[pos] = 0.0f;
+                }
+                __syncwarp();
+                do { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); } while (ci < cEnd - cBase && e == s);
+                if (ci < cEnd - cBase) begin_cell();
+            }
+            if (nmv > 0) flush_movers(); else __syncwarp();  // the window is about to be overwritten
+            if (lane == 0 && k + SNST < nWin) issue(k + SNST);
+        }
     }
 }
 

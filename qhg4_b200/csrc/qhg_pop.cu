@@ -161,6 +161,7 @@ struct qhgb_pop {
 
     // grid / env
     DevBuf<int> nbr, gid, count[2], cellStart[2], stay, arrive, cursor, birthCount, birthBase, nFert;
+    DevBuf<int> moveBase;  // fast path: first arrival slot of the movers of (cell, direction), MOVE_STRIDE ints per cell
     DevBuf<uint8_t> nNbr, ice;
     DevBuf<double> alt, W, B, D;
     DevBuf<int2> tileSums;
@@ -329,7 +330,7 @@ int allocAgents(qhgb_pop *p, int64_t cap) {
         auto regrow = [&](auto &buf) -> cudaError_t {
             using T = std::remove_pointer_t<decltype(buf.p)>;
             T *np = nullptr;
-            cudaError_t e = cudaMalloc(&np, cap * sizeof(T));
+            cudaError_t e = cudaMalloc(&np, (cap + AGENT_SLACK) * sizeof(T));  // bulk copies read whole 16-agent groups
             if (e != cudaSuccess) return e;
             if (keep > 0 && buf.p) e = cudaMemcpyAsync(np, buf.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, q.stream);
             cudaStreamSynchronize(q.stream);
@@ -371,7 +372,7 @@ int allocAgents(qhgb_pop *p, int64_t cap) {
     CK(q.dest.alloc(cap));
     CK(q.rank.alloc(cap));
     CK(q.oflags.alloc(cap));
-    CK(q.dec.alloc(cap));
+    CK(q.dec.alloc(cap + AGENT_SLACK));
     CK(q.pkey.alloc(cap));
     q.capacity = cap;
     q.pairingValid = false;
@@ -719,10 +720,10 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
             if (P.prog == PROG_TUT5 && P.nOps == 5) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             } else {
                 LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p);
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             }
             ShardArgs H{};
             long long globalBirths = -1;
@@ -737,7 +738,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 int *const infoAll = q.dHaloBuf.p + q.nHalo;
                 CK(cudaMemsetAsync(infoAll, 0, sizeof(int) * R * (R + 1), q.stream));
                 LAUNCH(p, "k_halo_gather", k_halo_gather, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.arrive.p,
-                       q.dHaloBuf.p, q.dstats.p, infoAll + q.shRank * (R + 1));
+                       q.cursor.p, q.dHaloBuf.p, q.dstats.p, infoAll + q.shRank * (R + 1));
                 TIMED(p, "nccl_allreduce_halo", NK(g_nccl.AllReduce(q.dHaloBuf.p, q.dHaloBuf.p, (size_t)q.nHalo + (size_t)R * (R + 1), ncclInt32, ncclSum, q.comm, q.stream)));
                 CK(cudaMemcpyAsync(q.hAllInfo, infoAll, sizeof(int) * R * (R + 1), cudaMemcpyDeviceToHost, q.stream));
                 LAUNCH(p, "k_halo_apply", k_halo_apply, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
@@ -766,8 +767,8 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
-            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * 16, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
-                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.cursor.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
+            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
+                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
             if (q.sharded) {  // agent migration: packed records straight between the GPUs (NCCL over NVLink)
                 const int R = q.shRanks;
                 int so = 0, ro = 0;
@@ -894,6 +895,7 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(p->alt.alloc(nc));
     CK(p->count[0].alloc(nc));
     CK(p->count[1].alloc(nc));
+    CK(p->moveBase.alloc(nc * MOVE_STRIDE));
     CK(p->cellStart[0].alloc(nc + 1));
     CK(p->cellStart[1].alloc(nc + 1));
     CK(p->stay.alloc(nc));
@@ -937,7 +939,7 @@ int qhgb_destroy(qhgb_pop *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (auto &k : p->ktimes) for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release();
+    p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release(); p->moveBase.release();
     p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
