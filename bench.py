@@ -221,7 +221,7 @@ def run_ours(args, rank, world):
     pipeline_ms = ktimes.pop("pipeline_total", (0.0, 0))[0]  # device time of the steps, gaps between launches included
 
     # ---- timed region 2: end to end through the C ABI with host buffers --------------------------------------
-    counts = np.zeros(ncell, np.uint64)
+    counts = g.host_array(ncell, np.uint64)  # page-locked: the per-step result is one DMA into host memory
     e2e_steps = 0
     barrier()
     w0 = time.perf_counter()
@@ -269,9 +269,9 @@ def run_ours(args, rank, world):
                        "parallelism": f"cell-range shards x{world}, NCCL migration" if world > 1 else "single GPU",
                        "migrations_per_step": migrated / args.steps},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 4 * ncell + 48,
+            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * ncell + 48,
                     "what": "initializeStep + doActions per level + finalizeStep through the C ABI, then totals and the per-cell count "
-                            "array copied to host memory every step"},
+                            "array (ulong per cell, as PopBase::getNumAgentsArray) copied into page-locked host memory every step"},
             "roofline": roof}
     g.close()
     if dist is not None:

@@ -15,6 +15,7 @@
  */
 #ifndef QHG_B200_H
 #define QHG_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -163,6 +164,13 @@ int  qhgb_get_capacities(qhgb_pop *p, double *out);
 int  qhgb_comm_get_unique_id(void *out, int nbytes);
 int  qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin);
 int  qhgb_comm_get_traffic(qhgb_pop *p, int64_t *sent, int64_t *received);
+
+/* ---- page-locked host arrays ------------------------------------------------------------------------
+ * The reference hands its per-cell arrays to the host as plain new[] memory (core/SPopulation.cpp:236-247).  An array
+ * the host reads every step (qhgb_get_num_agents_array) is copied by one DMA when it is page-locked; these two calls
+ * allocate and free such memory.  Every qhgb_get_* call also accepts ordinary pageable memory. */
+void *qhgb_host_alloc(size_t bytes);
+int   qhgb_host_free(void *ptr);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * number of kernels launched by this population since creation, and the CUDA stream they run on */

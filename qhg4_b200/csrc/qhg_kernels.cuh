@@ -660,6 +660,12 @@ __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths
     if (advanceStep) st->step++;
 }
 
+// PopBase::getNumAgentsArray hands out ulong counts (core/SPopulation.h); a shard reports 0 for the cells of other ranks
+__global__ void k_counts_u64(int nCells, int cLo, int cHi, const int *__restrict__ count, unsigned long long *__restrict__ out) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x)
+        out[c] = (c >= cLo && c < cHi) ? (unsigned long long)count[c] : 0ull;
+}
+
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {
     const int n = st->nAgents;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) age[i] = __fsub_rn(t, birth[i]);

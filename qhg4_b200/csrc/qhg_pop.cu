@@ -161,6 +161,7 @@ struct qhgb_pop {
 
     // grid / env
     DevBuf<int> nbr, gid, count[2], cellStart[2], stay, arrive, cursor, birthCount, birthBase, nFert;
+    DevBuf<unsigned long long> count64;  // per-cell counts widened for qhgb_get_num_agents_array
     DevBuf<int> moveBase;  // fast path: first arrival slot of the movers of (cell, direction), MOVE_STRIDE ints per cell
     DevBuf<uint8_t> nNbr, ice;
     DevBuf<double> alt, W, B, D;
@@ -232,7 +233,6 @@ struct qhgb_pop {
     int cHi() const { return sharded ? cellBegin[shRank + 1] : nCells; }
     DevBuf<Migrant> sendBuf, recvBuf;
     int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
-    int *hCount = nullptr;    // pinned: per-cell counts on their way to the host
     int64_t lastSent = 0, lastReceived = 0;
 
     bool timing = false;
@@ -939,7 +939,7 @@ int qhgb_destroy(qhgb_pop *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (auto &k : p->ktimes) for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release(); p->moveBase.release();
+    p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release(); p->moveBase.release(); p->count64.release();
     p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
@@ -954,7 +954,6 @@ int qhgb_destroy(qhgb_pop *p) {
     p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
     p->oflags.release(); p->dec.release(); p->pkey.release(); p->dstats.release();
     if (p->comm) g_nccl.CommDestroy(p->comm);
-    if (p->hCount) cudaFreeHost(p->hCount);
     if (p->hAllInfo) cudaFreeHost(p->hAllInfo);
     p->dCellBegin.release(); p->dInfo.release(); p->dAllInfo.release(); p->dSendOff.release(); p->dSendCursor.release();
     p->sendBuf.release(); p->recvBuf.release();
@@ -987,7 +986,6 @@ int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
     CK(cudaMemcpyAsync(p->nNbr.p, nn.data(), nc, cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->gid.p, p->hGid.data(), nc * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    if (!p->hCount) CK(cudaMallocHost(&p->hCount, sizeof(int) * nc));  // pinned staging buffer of qhgb_get_num_agents_array
     p->haveCells = true;
     return 0;
 }
@@ -1350,14 +1348,25 @@ int64_t qhgb_get_num_agents_effective(qhgb_pop *p) { return p ? p->nAgents : -1;
 
 int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     if (!p || !out) return fail("qhgb_get_num_agents_array: NULL argument");
-    if (!p->hCount) return fail("qhgb_get_num_agents_array: call qhgb_set_cells first");
+    if (!p->haveCells) return fail("qhgb_get_num_agents_array: call qhgb_set_cells first");
     CK(cudaSetDevice(p->device));
-    const int c0 = p->cLo(), c1 = p->cHi();  // a shard holds agents in its own cells only
-    if (c1 > c0) CK(cudaMemcpyAsync(p->hCount + c0, p->count[p->cur].p + c0, (size_t)(c1 - c0) * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    // widened to the reference's ulong on the device (cells of other ranks: 0), then one copy into the caller's array --
+    // a single DMA when that array is page-locked (qhgb_host_alloc)
+    if (!p->count64.p) CK(p->count64.alloc((size_t)p->nCells));
+    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
+    CK(cudaMemcpyAsync(out, p->count64.p, sizeof(uint64_t) * (size_t)p->nCells, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    if (c0 > 0) memset(out, 0, sizeof(uint64_t) * (size_t)c0);
-    for (int c = c0; c < c1; c++) out[c] = (uint64_t)p->hCount[c];
-    if (c1 < p->nCells) memset(out + c1, 0, sizeof(uint64_t) * (size_t)(p->nCells - c1));
+    return 0;
+}
+
+void *qhgb_host_alloc(size_t bytes) {
+    void *ptr = nullptr;
+    if (cudaMallocHost(&ptr, bytes ? bytes : 1) != cudaSuccess) { fail("qhgb_host_alloc: %zu bytes of page-locked memory not available", bytes); return nullptr; }
+    return ptr;
+}
+
+int qhgb_host_free(void *ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
     return 0;
 }
 

@@ -27,6 +27,7 @@ def _p(a):
 class GpuPopulation:
     def __init__(self, pop_class: str, nbr, device: int = 0, capacity_hint: int = 0, global_id=None):
         self.L = capi.load()
+        self._host_blocks = []
         nbr = np.ascontiguousarray(nbr, np.int32)
         self.ncells, self.max_neigh = nbr.shape
         h = C.c_void_p()
@@ -203,6 +204,17 @@ class GpuPopulation:
     def launch_count(self) -> int:
         return int(self.L.qhgb_get_launch_count(self.h))
 
+    def host_array(self, n: int, dtype=np.uint64):
+        """numpy array over page-locked host memory (qhgb_host_alloc): the per-step result arrays copy into it by one DMA"""
+        dt = np.dtype(dtype)
+        ptr = self.L.qhgb_host_alloc(int(n) * dt.itemsize)
+        if not ptr:
+            raise QhgError(self.L.qhgb_last_error().decode())
+        buf = (C.c_char * (int(n) * dt.itemsize)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dt, count=int(n))
+        self._host_blocks.append(ptr)
+        return arr
+
     def reset_kernel_times(self, enable=True):
         check(self.L.qhgb_reset_kernel_times(self.h, int(enable)), "qhgb_reset_kernel_times")
 
@@ -227,6 +239,9 @@ class GpuPopulation:
         if getattr(self, "h", None):
             self.L.qhgb_destroy(self.h)
             self.h = None
+            for ptr in self._host_blocks:  # arrays from host_array() must not be used after close()
+                self.L.qhgb_host_free(ptr)
+            self._host_blocks = []
 
     def __del__(self):
         try:
