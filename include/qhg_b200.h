@@ -164,6 +164,15 @@ int  qhgb_get_capacities(qhgb_pop *p, double *out);
 int  qhgb_comm_get_unique_id(void *out, int nbytes);
 int  qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin);
 int  qhgb_comm_get_traffic(qhgb_pop *p, int64_t *sent, int64_t *received);
+/* Exchange over peer memory instead of NCCL calls (same results): every rank exports two device allocations (its
+ * remote arrival counters and its receive buffer) as CUDA IPC handles, the host gathers the 128 bytes of every rank
+ * (any transport) and hands the table to each rank.  From then on a step has no host round trip: arrival counts go
+ * to the owning GPU by remote atomics, migrant records by direct NVLink stores from the scatter kernel, ordered by
+ * two device-side cross-GPU barriers.
+ *   qhgb_comm_p2p_handle   after qhgb_comm_init: writes 128 bytes (two cudaIpcMemHandle_t)
+ *   qhgb_comm_p2p_connect  all_handles = nranks x 128 bytes in rank order */
+int  qhgb_comm_p2p_handle(qhgb_pop *p, void *out, int nbytes);
+int  qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles);
 
 /* ---- page-locked host arrays ------------------------------------------------------------------------
  * The reference hands its per-cell arrays to the host as plain new[] memory (core/SPopulation.cpp:236-247).  An array

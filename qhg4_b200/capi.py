@@ -56,6 +56,8 @@ SYMBOLS = {
     "qhgb_comm_get_unique_id": (i32, [vp, i32]),
     "qhgb_comm_init": (i32, [vp, i32, i32, vp, vp]),
     "qhgb_comm_get_traffic": (i32, [vp, vp, vp]),
+    "qhgb_comm_p2p_handle": (i32, [vp, vp, i32]),
+    "qhgb_comm_p2p_connect": (i32, [vp, vp]),
     "qhgb_host_alloc": (vp, [C.c_size_t]),
     "qhgb_host_free": (i32, [vp]),
     "qhgb_get_launch_count": (i64, [vp]),

@@ -412,16 +412,40 @@ struct Migrant {  // 32 bytes
     unsigned pad;
 };
 
+// Exchange over peer memory (NVLink): every rank owns one XchgBlock and one double-buffered array of remote arrival
+// counts, both mapped into every other rank's address space (cudaIpc).  Per step: each rank adds its arrivals into the
+// owners' counters (atomicAdd_system returns the first slot), announces its births, and after a cross-GPU barrier
+// writes the records of the agents that leave straight into the owner's receive buffer.  No host round trip.
+constexpr int MAXR = 16;
+struct XchgBlock {
+    unsigned flagA[MAXR];   // stamp of rank r: its arrival counts and births of this step are in
+    unsigned flagB[MAXR];   // stamp of rank r: its migrant records of this step are in
+    long long births[MAXR];
+    int recvCount;          // migrant records reserved in recv[] this step
+    int pad[31];
+};
+static_assert(sizeof(XchgBlock) % 32 == 0, "the migrant records follow the header");
+struct PeerTable {
+    int *arriveRemote[MAXR];  // [2][nCells] per rank
+    XchgBlock *x[MAXR];
+};
+
 struct ShardArgs {
     int on;                 // 0: single GPU
     int rank, nranks;
     int c0, c1;             // owned cells [c0, c1)
     const int *cellBegin;   // nranks+1 range boundaries (device)
-    Migrant *sendBuf;       // packed by destination rank: sendOff[q] .. sendOff[q+1]
+    Migrant *sendBuf;       // NCCL mode: packed by destination rank, sendOff[q] .. sendOff[q+1]
     const int *sendOff;
     int *sendCursor;        // nranks counters
-    long long birthOffset;  // births of the lower ranks this step (newborn ids are global ranks)
+    long long birthOffset;  // births of the lower ranks this step (newborn ids are global ranks); p2p: in DevStats
+    int p2p;                // 1: records go straight into the owner's receive buffer
+    int recvCap;            // records per receive buffer
+    const int *remoteBase;  // per foreign halo cell: first arrival slot of this rank's movers in the owner's cell
+    const PeerTable *peers; // device copy
 };
+
+__device__ __forceinline__ Migrant *xchg_recv(XchgBlock *x) { return reinterpret_cast<Migrant *>(x + 1); }
 
 __device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
     int q = 0;
@@ -470,6 +494,98 @@ __global__ void k_halo_apply(int nHalo, const int *__restrict__ halo, int c0, in
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
         const int c = halo[i];
         if (c >= c0 && c < c1) arrive[c] = buf[i];
+    }
+}
+
+// ---- exchange over peer memory ----------------------------------------------------------------------------
+// (1) arrivals into the cells of other ranks: one remote atomicAdd per halo cell, the returned slot is kept for pass 2;
+//     own halo cells: the counters the peers will use in the NEXT step are cleared.  Births are announced to every rank.
+__global__ void __launch_bounds__(256)
+k_halo_push(int nHalo, const int *__restrict__ halo, const int *__restrict__ cellBegin, int rank, int nranks, int nCells,
+            int parity, int *__restrict__ arrive, int *__restrict__ remoteBase, const PeerTable *__restrict__ T,
+            DevStats *__restrict__ st) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
+        const int c = halo[i];
+        int q = 0;
+        while (q + 1 < nranks && c >= cellBegin[q + 1]) q++;
+        if (q != rank) {
+            const int v = arrive[c];
+            if (v) {
+                remoteBase[c] = atomicAdd_system(T->arriveRemote[q] + (size_t)parity * nCells + c, v);
+                arrive[c] = 0;
+            }
+        } else {
+            T->arriveRemote[rank][(size_t)(parity ^ 1) * nCells + c] = 0;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < nranks) {
+        T->x[threadIdx.x]->births[rank] = (long long)st->nBirths;
+        if (threadIdx.x == 0) T->x[rank]->recvCount = 0;  // nobody reserves records before the barrier that follows
+    }
+}
+
+// (2) cross-GPU barrier: one warp; lane r tells rank r "I am at `stamp`" and waits for rank r's word.  A rank that
+//     does not show up within ~4 s of GPU clock raises commError (the host fails the step) instead of hanging.
+__global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, const PeerTable *__restrict__ T, DevStats *__restrict__ st) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        __threadfence_system();
+        volatile unsigned *theirs = which ? &T->x[r]->flagB[rank] : &T->x[r]->flagA[rank];
+        *theirs = stamp;
+        volatile unsigned *mine = which ? &T->x[rank]->flagB[r] : &T->x[rank]->flagA[r];
+        const long long t0 = clock64();
+        while ((int)(*mine - stamp) < 0) {
+            if (clock64() - t0 > 8000000000ll) { st->commError = 1; break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (which == 0 && r == 0) {  // everybody's births are in: id offset of this rank, total of the step
+        long long below = 0, total = 0;
+        for (int q = 0; q < nranks; q++) {
+            const long long b = ((volatile long long *)T->x[rank]->births)[q];
+            if (q < rank) below += b;
+            total += b;
+        }
+        st->birthOffset = below;
+        st->globalBirths = total;
+    }
+}
+
+// (3) after barrier A: the owned halo cells take the arrivals of the other ranks; the local movers hold the first
+//     slots of a cell's arrivals, the migrants follow
+__global__ void k_halo_merge(int nHalo, const int *__restrict__ halo, int c0, int c1, int nCells, int parity,
+                             const PeerTable *__restrict__ T, int rank, int *__restrict__ arrive, int *__restrict__ cursor) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
+        const int c = halo[i];
+        if (c >= c0 && c < c1) {
+            const int local = arrive[c];
+            cursor[c] = local;
+            arrive[c] = local + T->arriveRemote[rank][(size_t)parity * nCells + c];
+        }
+    }
+}
+
+// (4) after barrier B: the records the other ranks wrote into this rank's receive buffer go to their slots
+__global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable *__restrict__ T, int rank, int recvCap, AgentArrays o,
+                                     const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ cursor,
+                                     int storeAge) {
+    if (st->overflow || st->oversize) return;
+    const int n = T->x[rank]->recvCount;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->nRecv = n;
+        if (n > recvCap) st->commError = 2;
+    }
+    const Migrant *in = xchg_recv(T->x[rank]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < min(n, recvCap); i += gridDim.x * blockDim.x) {
+        const Migrant m = in[i];
+        const int pos = newStart[m.cell] + stay[m.cell] + cursor[m.cell] + (int)m.pad;
+        o.id[pos] = m.id;
+        o.birth[pos] = m.birth;
+        o.lastBirth[pos] = m.lastBirth;
+        o.flags[pos] = (uint8_t)m.flags;
+        if (storeAge) o.age[pos] = m.age;
     }
 }
 
@@ -570,6 +686,8 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
     const long long nextID = st->nextID;
+    const long long birthOffset = H.p2p ? st->birthOffset : H.birthOffset;
+    int nSentL = 0;
     if (lane == 0) {
         for (int k = 0; k < SNST; k++) mbar_init(&S.bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -621,6 +739,8 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                 dirCell = d;
                 if (!(H.on && (d < H.c0 || d >= H.c1))) {
                     dirA = newStart[d]; dirB = stay[d]; dirC = moveBase[(size_t)(cBase + ci) * MOVE_STRIDE + lane];
+                } else if (H.p2p) {  // slot among the arrivals of the owner's cell (k_halo_push)
+                    dirA = H.remoteBase[d]; dirC = moveBase[(size_t)(cBase + ci) * MOVE_STRIDE + lane];
                 }
             }
         };
@@ -660,7 +780,15 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                             Migrant m;
                             m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
                             m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
-                            H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                            if (H.p2p) {  // straight into the owner's receive buffer over NVLink
+                                XchgBlock *X = H.peers->x[qo];
+                                const int slot = atomicAdd_system(&X->recvCount, 1);
+                                m.pad = (unsigned)pos;
+                                if (slot < H.recvCap) xchg_recv(X)[slot] = m;
+                                nSentL++;
+                            } else {
+                                H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                            }
                         } else {
                             o.id[pos] = id;
                             o.birth[pos] = birth;
@@ -708,7 +836,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     const int64_t mid = S.motherId[m];
                     int r = 0;
                     for (int q = 0; q < nMothers; q++) r += (S.motherId[q] < mid) ? 1 : 0;
-                    const int64_t cid = nextID + H.birthOffset + bb + r;
+                    const int64_t cid = nextID + birthOffset + bb + r;
                     const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
                     const int pos = babyBase + r;
                     o.id[pos] = cid;
@@ -724,6 +852,10 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
             if (nmv > 0) flush_movers(); else __syncwarp();  // the window is about to be overwritten
             if (lane == 0 && k + SNST < nWin) issue(k + SNST);
         }
+    }
+    if (H.p2p) {
+        nSentL = __reduce_add_sync(FULL, nSentL);
+        if (lane == 0 && nSentL) atomicAdd(&st->nSent, nSentL);
     }
 }
 

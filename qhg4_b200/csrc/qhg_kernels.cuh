@@ -63,6 +63,11 @@ struct DevStats {
     int oversize;   // a cell did not fit the fast path: the host reruns the step on the generic path
     int workDecide, workScatter;  // dynamic work counters of the two fast-path passes
     long long nextID;
+    // sharded runs over peer memory (qhgb_comm_p2p_connect)
+    int commError;                // a peer did not reach a cross-GPU barrier in time, or the migrant buffer overflowed
+    int nSent, nRecv;             // agents that left for / arrived from other ranks in the running step
+    long long birthOffset;        // births of the lower ranks this step (newborn ids are global ranks)
+    long long globalBirths;       // births of all ranks this step
 };
 
 struct ActParams {
@@ -133,6 +138,9 @@ __global__ void k_cell_init(DevStats *__restrict__ st, int cLo, int cHi, const i
         st->oversize = 0;
         st->workDecide = 0;
         st->workScatter = 0;
+        st->nSent = 0;
+        st->nRecv = 0;
+        st->birthOffset = 0;
     }
     for (int c = cLo + blockIdx.x * blockDim.x + threadIdx.x; c < cHi; c += gridDim.x * blockDim.x) {  // the cells this GPU owns
         if (doVerhulst) {
@@ -656,7 +664,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
 __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) {
     if (st->overflow || st->oversize) return;
     st->nAgents = st->nNew;
-    st->nextID += (globalBirths >= 0) ? globalBirths : (long long)st->nBirths;
+    // globalBirths: -1 single GPU, -2 the sum the ranks exchanged on the device (st->globalBirths), else the sum from the host
+    st->nextID += (globalBirths >= 0) ? globalBirths : (globalBirths == -2 ? st->globalBirths : (long long)st->nBirths);
     if (advanceStep) st->step++;
 }
 

@@ -234,6 +234,15 @@ struct qhgb_pop {
     DevBuf<Migrant> sendBuf, recvBuf;
     int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
     int64_t lastSent = 0, lastReceived = 0;
+    // exchange over peer memory (qhgb_comm_p2p_handle / qhgb_comm_p2p_connect)
+    bool p2p = false;
+    int *arriveRemote = nullptr;     // [2][nCells], written by the peers
+    XchgBlock *xchg = nullptr;       // header + receive buffer, written by the peers
+    int recvCap = 0;
+    unsigned xStep = 0;              // exchanges done so far (the same on every rank): parity and barrier stamp
+    DevBuf<int> remoteBase;
+    DevBuf<PeerTable> dPeers;
+    std::vector<void *> ipcOpened;
 
     bool timing = false;
     cudaEvent_t userEv[8] = {nullptr};
@@ -729,7 +738,18 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             long long globalBirths = -1;
             int nRecv = 0;
             std::vector<int> sendCnt, recvCnt;
-            if (q.sharded) {
+            if (q.sharded && q.p2p) {
+                // exchange over peer memory: remote adds of the arrival counts, births announced, cross-GPU barrier; no host sync
+                const int R = q.shRanks, parity = (int)(q.xStep & 1u);
+                LAUNCH(p, "k_halo_push", k_halo_push, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.nCells, parity,
+                       q.arrive.p, q.remoteBase.p, q.dPeers.p, q.dstats.p);
+                LAUNCH(p, "k_xbarrier_counts", k_xbarrier, 1, 32, q.shRank, R, 0, q.xStep + 1, q.dPeers.p, q.dstats.p);
+                LAUNCH(p, "k_halo_merge", k_halo_merge, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
+                       q.nCells, parity, q.dPeers.p, q.shRank, q.arrive.p, q.cursor.p);
+                H.on = 1; H.rank = q.shRank; H.nranks = R; H.c0 = q.cellBegin[q.shRank]; H.c1 = q.cellBegin[q.shRank + 1];
+                H.cellBegin = q.dCellBegin.p; H.p2p = 1; H.recvCap = q.recvCap; H.remoteBase = q.remoteBase.p; H.peers = q.dPeers.p;
+                globalBirths = -2;
+            } else if (q.sharded) {
                 // (1) what this rank sends to every other rank, (2) arrivals per halo cell summed over all ranks,
                 // (3) everybody learns every count (and the births per rank: newborn ids are global ranks)
                 const int R = q.shRanks;
@@ -769,7 +789,12 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             launchScan(p);
             LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
-            if (q.sharded) {  // agent migration: packed records straight between the GPUs (NCCL over NVLink)
+            if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
+                LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p);
+                LAUNCH(p, "k_place_migrants", k_place_migrants_p2p, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
+                       q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
+                q.xStep++;
+            } else if (q.sharded) {  // agent migration: packed records between the GPUs (NCCL over NVLink)
                 const int R = q.shRanks;
                 int so = 0, ro = 0;
                 cudaEvent_t g0 = nullptr, g1 = nullptr;
@@ -812,6 +837,9 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         CK(cudaGetLastError());
         if (q.timing && attempt == 0) { cudaEventRecord(t1, q.stream); q.kt("pipeline_total").pending.push_back({t0, t1}); }
         if (pullStats(p) != 0) return -1;
+        if (q.hstats->commError == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
+        if (q.hstats->commError == 2) return fail("receive buffer too small for the migrants of one step (%d > %d)", q.hstats->nRecv, q.recvCap);
+        if (tiled && q.sharded && q.p2p) { q.lastSent = q.hstats->nSent; q.lastReceived = q.hstats->nRecv; }
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
             if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
             tiled = false;
@@ -896,6 +924,7 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(p->count[0].alloc(nc));
     CK(p->count[1].alloc(nc));
     CK(p->moveBase.alloc(nc * MOVE_STRIDE));
+    CK(p->count64.alloc(nc));
     CK(p->cellStart[0].alloc(nc + 1));
     CK(p->cellStart[1].alloc(nc + 1));
     CK(p->stay.alloc(nc));
@@ -953,6 +982,9 @@ int qhgb_destroy(qhgb_pop *p) {
     }
     p->mate.release(); p->prank.release(); p->ranked.release(); p->dest.release(); p->rank.release();
     p->oflags.release(); p->dec.release(); p->pkey.release(); p->dstats.release();
+    for (void *m : p->ipcOpened) cudaIpcCloseMemHandle(m);
+    if (p->arriveRemote) cudaFree(p->arriveRemote);
+    if (p->xchg) cudaFree(p->xchg);
     if (p->comm) g_nccl.CommDestroy(p->comm);
     if (p->hAllInfo) cudaFreeHost(p->hAllInfo);
     p->dCellBegin.release(); p->dInfo.release(); p->dAllInfo.release(); p->dSendOff.release(); p->dSendCursor.release();
@@ -1352,7 +1384,6 @@ int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     CK(cudaSetDevice(p->device));
     // widened to the reference's ulong on the device (cells of other ranks: 0), then one copy into the caller's array --
     // a single DMA when that array is page-locked (qhgb_host_alloc)
-    if (!p->count64.p) CK(p->count64.alloc((size_t)p->nCells));
     LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
     CK(cudaMemcpyAsync(out, p->count64.p, sizeof(uint64_t) * (size_t)p->nCells, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -1602,6 +1633,58 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
         CK(cudaStreamSynchronize(p->stream));
     }
     p->sharded = nranks > 1;
+    return 0;
+}
+
+int qhgb_comm_p2p_handle(qhgb_pop *p, void *out, int nbytes) {
+    if (!p || !out) return fail("qhgb_comm_p2p_handle: NULL argument");
+    if (nbytes < 2 * (int)sizeof(cudaIpcMemHandle_t)) return fail("qhgb_comm_p2p_handle: %d bytes needed", 2 * (int)sizeof(cudaIpcMemHandle_t));
+    if (p->shRanks < 1 || p->cellBegin.empty()) return fail("qhgb_comm_p2p_handle: call qhgb_comm_init first");
+    if (p->shRanks > MAXR) return fail("qhgb_comm_p2p_handle: at most %d ranks", MAXR);
+    CK(cudaSetDevice(p->device));
+    if (!p->xchg) {
+        p->recvCap = (int)std::max<int64_t>(1 << 16, p->capacity / 8);
+        const size_t xb = sizeof(XchgBlock) + (size_t)p->recvCap * sizeof(Migrant);
+        CK(cudaMalloc(&p->arriveRemote, sizeof(int) * 2 * (size_t)p->nCells));
+        CK(cudaMemset(p->arriveRemote, 0, sizeof(int) * 2 * (size_t)p->nCells));
+        CK(cudaMalloc(&p->xchg, xb));
+        CK(cudaMemset(p->xchg, 0, xb));
+        CK(p->remoteBase.alloc((size_t)p->nCells));
+    }
+    cudaIpcMemHandle_t h[2];
+    CK(cudaIpcGetMemHandle(&h[0], p->arriveRemote));
+    CK(cudaIpcGetMemHandle(&h[1], p->xchg));
+    memcpy(out, h, sizeof(h));
+    return 0;
+}
+
+int qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles) {
+    if (!p || !all_handles) return fail("qhgb_comm_p2p_connect: NULL argument");
+    if (!p->xchg) return fail("qhgb_comm_p2p_connect: call qhgb_comm_p2p_handle first");
+    CK(cudaSetDevice(p->device));
+    PeerTable T{};
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < p->shRanks; r++) {
+        if (r == p->shRank) {
+            T.arriveRemote[r] = p->arriveRemote;
+            T.x[r] = p->xchg;
+            continue;
+        }
+        void *a = nullptr, *x = nullptr;
+        cudaIpcMemHandle_t ha, hx;
+        memcpy(&ha, &h[2 * r], sizeof(ha));
+        memcpy(&hx, &h[2 * r + 1], sizeof(hx));
+        CK(cudaIpcOpenMemHandle(&a, ha, cudaIpcMemLazyEnablePeerAccess));
+        p->ipcOpened.push_back(a);
+        CK(cudaIpcOpenMemHandle(&x, hx, cudaIpcMemLazyEnablePeerAccess));
+        p->ipcOpened.push_back(x);
+        T.arriveRemote[r] = (int *)a;
+        T.x[r] = (XchgBlock *)x;
+    }
+    CK(p->dPeers.alloc(1));
+    CK(cudaMemcpyAsync(p->dPeers.p, &T, sizeof(T), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->p2p = p->shRanks > 1;
     return 0;
 }
 

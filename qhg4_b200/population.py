@@ -195,6 +195,15 @@ class GpuPopulation:
         uid = C.create_string_buffer(unique_id, 128)
         check(self.L.qhgb_comm_init(self.h, int(rank), int(nranks), uid, _p(cb)), "qhgb_comm_init")
 
+    def comm_p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(self.L.qhgb_comm_p2p_handle(self.h, buf, 128), "qhgb_comm_p2p_handle")
+        return buf.raw
+
+    def comm_p2p_connect(self, all_handles: bytes):
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        check(self.L.qhgb_comm_p2p_connect(self.h, buf), "qhgb_comm_p2p_connect")
+
     def comm_traffic(self):
         s, r = C.c_int64(0), C.c_int64(0)
         check(self.L.qhgb_comm_get_traffic(self.h, C.byref(s), C.byref(r)), "qhgb_comm_get_traffic")

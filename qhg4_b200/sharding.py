@@ -33,8 +33,13 @@ def owner_of(cells, begin) -> np.ndarray:
     return (np.searchsorted(np.asarray(begin), np.asarray(cells), side="right") - 1).astype(np.int32)
 
 
-def connect(pop, begin, rank: int, nranks: int):
-    """Create the NCCL communicator of `pop` (a GpuPopulation); call before add_agents."""
+def connect(pop, begin, rank: int, nranks: int, p2p: bool | None = None):
+    """Join `pop` (a GpuPopulation) to the sharded run; call before add_agents.
+
+    The host side only carries small tables between the ranks (torch.distributed, any backend): the 128-byte NCCL id
+    and, for the exchange over peer memory (default; QHG_P2P=0 or p2p=False keeps the NCCL calls), the CUDA IPC
+    handles of every rank's exchange buffers."""
+    import os
     import torch
     import torch.distributed as dist
     buf = (C.c_char * 128)()
@@ -46,3 +51,10 @@ def connect(pop, begin, rank: int, nranks: int):
         dist.broadcast(t, src=0)
     uid = bytes(t.tolist())
     pop.comm_init(rank, nranks, uid, begin)
+    if p2p is None:
+        p2p = os.environ.get("QHG_P2P", "1") != "0"
+    if p2p and nranks > 1:
+        mine = torch.tensor(list(pop.comm_p2p_handle()), dtype=torch.uint8)
+        table = [torch.zeros_like(mine) for _ in range(nranks)]
+        dist.all_gather(table, mine)
+        pop.comm_p2p_connect(b"".join(bytes(x.tolist()) for x in table))

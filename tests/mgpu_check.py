@@ -60,7 +60,8 @@ def main():
     tot = torch.tensor([moved])
     dist.all_reduce(tot)
     if rank == 0:
-        print(f"mgpu_check ok: {world} ranks, {nsteps} steps, {o.num_agents()} agents, {int(tot)} cross-rank migrations, "
+        how = "peer-memory" if os.environ.get("QHG_P2P", "1") != "0" else "nccl"
+        print(f"mgpu_check ok: {world} ranks, {nsteps} steps, {o.num_agents()} agents, {int(tot)} cross-rank migrations ({how} exchange), "
               f"bit-exact vs the unsharded oracle")
     dist.barrier()
     dist.destroy_process_group()

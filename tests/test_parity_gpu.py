@@ -236,8 +236,10 @@ def test_statistical_equivalence_vs_reference():
     assert p_tot > 0.01 and p_age > 0.01 and p_occ > 0.01, (p_tot, p_age, p_occ)
 
 
-def test_two_gpu_shards_equal_unsharded_oracle():
-    """cell-range sharding + NCCL migration on 2 GPUs: bit-identical to the unsharded oracle (tests/mgpu_check.py)"""
+@pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
+def test_two_gpu_shards_equal_unsharded_oracle(exchange):
+    """cell-range sharding on 2 GPUs, migration over peer memory (default) and over NCCL calls: bit-identical to the
+    unsharded oracle (tests/mgpu_check.py)"""
     import os
     import subprocess
     import sys
@@ -245,9 +247,11 @@ def test_two_gpu_shards_equal_unsharded_oracle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run tests/mgpu_check.py under torchrun on a multi-GPU box)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QHG_P2P="1" if exchange == "peer-memory" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+                        "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "mgpu_check ok" in r.stdout and exchange in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def _cap_world(S=15, seed=2):
