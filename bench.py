@@ -44,11 +44,13 @@ def measured_peak_gbs():
 
 
 def traffic_per_step(agents):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, scaled to this run's agents."""
+    """DRAM bytes per step of the two fast-path kernels (everything else is per-cell and tiny) from the committed
+    ncu --set full capture, scaled to this run's agents."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            d = json.load(f)["k_cell_decide"]
-        return d["dram_bytes_per_launch"] / d["agents"] * agents
+            d = json.load(f)
+        per_agent = (d["k_cell_decide"]["dram_bytes_per_launch"] + d["k_cell_scatter"]["dram_bytes_per_launch"]) / d["agents"]
+        return per_agent * agents
     except Exception:
         return None
 
@@ -60,8 +62,9 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device = device
-        self.lines = []
+        self.lines = []   # (arrival time, line)
         self.proc = None
+        self.t_begin = 0.0
 
     def start(self):
         try:
@@ -73,15 +76,22 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def begin(self):
+        """samples from here on count (nvidia-smi is started early: it needs a moment before its first line)"""
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.perf_counter() + 0.03  # one more sampling interval: the line for the last steps
+        time.sleep(0.05)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ta, ln in self.lines:
+            if ta < self.t_begin or ta > t_end:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -148,6 +158,8 @@ def run_ours(args, rank, world):
         import torch.distributed as dist  # host-side plumbing only (128-byte NCCL id, scalar reductions); the data
         dist.init_process_group("gloo", rank=rank, world_size=world)  # path is NCCL inside the C library
     t_setup = time.time()
+    sampler = ClockSampler(device)
+    sampler.start()
     nbr, alt, pop, par, K = build_world(args.subdiv, args.agents)
     ncell = len(nbr)
     begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=ncell), world)
@@ -162,8 +174,7 @@ def run_ours(args, rank, world):
     g.synchronize()
     upload_s = time.time() - t0
     del pop
-    sampler = ClockSampler(device)  # sampled from the warm-up on: the timed region alone can be shorter than one sample
-    sampler.start()
+    sampler.begin()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
     t = 0.0
     for _ in range(args.warmup):
         g.step(t); t += 1.0

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_$R.log 2>&1
 # the two hot kernels, full set, full-size workload (third step)
-ncu --set full --clock-control none --import-source on -k regex:k_cell_ -s 4 -c 2 -o gpurun_out/prof_$R \
+ncu --set full --clock-control none --import-source on -k 'regex:k_cell_(decide|scatter)' -s 4 -c 2 -o gpurun_out/prof_$R \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_full_$R.log 2>&1
 # clocks while a plain run is going on
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks_$R.csv &

@@ -811,7 +811,6 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
                     const bool stays = alive && code == 0, mover = alive && code != 0;
                     const unsigned ms = __ballot_sync(FULL, stays), mb = __ballot_sync(FULL, born), mm = __ballot_sync(FULL, mover);
-                    if (nmv + __popc(mm) > MVCAP) flush_movers();
                     if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)x;
                     nmv += __popc(mm);
                     if (stays) {
@@ -825,10 +824,13 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     if (born) S.motherId[nMothers + __popc(mb & lt)] = W.id[x];
                     stayBase += __popc(ms);
                     nMothers += __popc(mb);
+                    // one call site (code size): the queue could overflow in the next round, or this is the last round of
+                    // the range -- the cell is complete (its slot bases end here) or the window is about to be recycled
+                    if (nmv > MVCAP - 32 || (j0 + 32 >= hi && nmv > 0)) flush_movers();
                 }
+                __syncwarp();
                 if (e > w1) break;  // the cell goes on in the next window
                 // ---- the cell is complete ----
-                if (nmv > 0) flush_movers(); else __syncwarp();
                 // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
                 const int babyBase = ns + stayBase + __shfl_sync(FULL, arL, ci);
                 const int bb = __shfl_sync(FULL, bbL, ci);
@@ -849,7 +851,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                 do { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); } while (ci < cEnd - cBase && e == s);
                 if (ci < cEnd - cBase) begin_cell();
             }
-            if (nmv > 0) flush_movers(); else __syncwarp();  // the window is about to be overwritten
+            __syncwarp();  // every lane is done with the window: it can be overwritten
             if (lane == 0 && k + SNST < nWin) issue(k + SNST);
         }
     }
