@@ -1,45 +1,3 @@
-# INTEGRATION — putting the CUDA path behind QHG4's own plugin API
-
-The drop-in boundary is the C ABI of `include/qhg_b200.h` (`qhg4_b200/libqhg_b200.so`). QHG4 is C++, so the
-reference-side binding is a small C++ population class plus the usual `getInfo` / `createPop` wrapper
-(`dynpops/WrapperTemplate.cpp.tmp:14-31`); no other file of QHG4 changes. The host loop keeps calling
-`PopLooper::doStep` → `initializeStep` / `doActions(prio)` / `finalizeStep` from one thread
-(`core/PopLooper.cpp:166-202`).
-
-## 1. Which C entry point replaces what
-
-| reference (file:line) | C ABI |
-|---|---|
-| `createPop(...)` → `new tut_EnvironAltPop(pCG, pPopFinder, iLayerSize, apIDG, aulState, aiSeeds)` (`dynpops/WrapperTemplate.cpp.tmp:24-30`, `populations/tut_EnvironAltPop.cpp:24-53`) | `qhgb_create("tut_EnvironAltPop", device, nCells, 6, capacity, &pop)`, `qhgb_set_seed(pop, aulState)` |
-| `SCellGrid::m_aCells[]` (`core/SCell.h:9-13`) | `qhgb_set_cells(pop, nbr[nCells*6], globalID)` |
-| `Geography::m_adAltitude`, `m_abIce`, … (`core/Geography.h:31-39`) | `qhgb_set_env_array(pop, "Altitude" / "Ice" / …, values, nCells)` |
-| `SPopulation::readSpeciesData` → `getPrioInfos` + `Prioritizer::getActionAttributes` (`core/SPopulation.cpp:1108-1142`) | `qhgb_set_prio(pop, "ATanDeath", 2)` …, `qhgb_set_attribute_str(pop, "ATanDeath_max_age", "60.0")` … (same names as the XML / QDF attributes) |
-| `modifyAttributes(name, value)`, `enableAction` / `disableAction` (`core/PopBase.h:22-24`) | `qhgb_set_attribute`, `qhgb_enable_action` |
-| `addAgent` / `readAgentDataQDF` (`core/SPopulation.cpp:1149-1166, 1689-1741`) | `qhgb_add_agents(pop, n, cell, id, birth, gender, age, lastBirth, lifeState)` |
-| `preLoop` (`core/SPopulation.cpp:273-292`) | `qhgb_pre_loop` |
-| `initializeStep(t)` / `doActions(prio, t)` / `finalizeStep()` (`core/SPopulation.cpp:394-417, 554-577, 439-477`) | `qhgb_initialize_step` / `qhgb_do_actions` / `qhgb_finalize_step` |
-| `getNumAgentsEffective`, `getNumAgents(cell)`, `getNumAgentsArray` (`core/SPopulation.h:145-148`) | `qhgb_get_num_agents_effective`, `qhgb_get_num_agents_array` |
-| `updateEvent(id, data, t)` / `flushEvents(t)` (`populations/tut_EnvironAltPop.cpp:93-127`) | `qhgb_set_env_array` for the changed arrays, then `qhgb_update_event` / `qhgb_flush_events` |
-| `preWrite(t)` + `writeAgentDataQDFSafe` (`core/PopLooper.cpp:149-157`, `core/SPopulation.cpp:1465-1568`) | `qhgb_get_agents` fills the host records the unchanged QDF writer walks |
-| per-step totals printed by `recycleDeadSpaceNew` / `performMoves` (`core/SPopulation.cpp:605-607, 1087`) | `qhgb_get_step_stats` |
-
-Return convention is the reference's: `int`, 0 = OK, non-zero = error, summed by callers; the message the
-reference would have printed is available from `qhgb_last_error()`.
-
-## 2. The binding a maintainer adds (`populations/tut_EnvironAltGpuPop.{h,cpp}`)
-
-The class below is a real file of this repository, `integration/tut_EnvironAltGpuPop.h`, and it is compiled and run:
-`make -C oracle adapter` builds `oracle/_ref/libqhgadapter.so` from the UNMODIFIED reference sources (the same
-objects as `oracle/_ref/libqhgref.so`: `PopLooper`, `SPopulation`, `ParamProvider2`, the tutorial population …) plus
-this header, linked against `qhg4_b200/libqhg_b200.so`; the GPU test
-`tests/test_parity_gpu.py::test_reference_step_loop_drives_cuda_path_through_plugin_class` then lets the reference's own
-`PopLooper::doStep` (core/PopLooper.cpp:190-232) step the population and finds the agents that `preWrite` brings back
-into the reference's `LayerBuf` bit-identical to the oracle's.
-
-Deriving from the existing population keeps XML/QDF parameter handling, the priority table, `addAgent` and the QDF
-agent writer for free (SURVEY.md §9.5); only the step-loop virtuals are overridden.
-
-```cpp
 // populations/tut_EnvironAltGpuPop.h
 #include "tut_EnvironAltPop.h"
 #include "LBController.h"
@@ -155,43 +113,3 @@ public:
 protected:
     qhgb_pop *m_gpu;
 };
-```
-
-```cpp
-// dynpops wrapper, generated from dynpops/WrapperTemplate.cpp.tmp with @@@xxx@@@ = tut_EnvironAltGpuPop
-extern "C" const std::string getInfo() { return "tut_EnvironAltGpuPop"; }
-extern "C" PopBase *createPop(ArrayShare *pAS, SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG,
-                              uint32_t *aulState, uint *aiSeeds) {
-    ArrayShare::setInstance(pAS);
-    // note: DynPopFactory passes only six arguments (populations/DynPopFactory.cpp:18,150) -- aiSeeds is not usable here
-    return new tut_EnvironAltGpuPop(pCG, pPF, iLayerSize, apIDG, aulState, NULL);
-}
-```
-
-Build it like every other plugin (`dynpops/Makefile`), adding `-I<this repo>/include` and
-`-L<this repo>/qhg4_b200 -lqhg_b200`; select it with `--dyn-pops --so-dirs=<dir>` and `<class name="tut_EnvironAltGpuPop" …>`
-in the population XML (`app/SimParams.cpp:343,360,1395-1407`).
-
-## 3. What changes for the user
-
-* Results are reproducible for a given seed **independently of the thread / GPU count** (the reference's depend on
-  `OMP_NUM_THREADS`); they are statistically equivalent to the reference's, not bit-equal, because the
-  random streams are per agent instead of per thread.
-* Agent ids of newborns are dense (`maxID+1 …`) in (cell, mother id) order instead of thread-strided.
-* `m_iMateIndex` is not materialised per step; `qhgb_get_agents(..., mate_id)` between `initializeStep` and
-  `finalizeStep` returns the mates if somebody needs them (e.g. a custom action).
-* Several GPUs: one process per GPU, `qhgb_comm_init` with contiguous cell ranges (`qhg4_b200/sharding.py`
-  shows the host side); QHG4's simulator has no multi-process mode to hook this into (`app/Simulator.cpp:89-101`).
-
-## 4. Python / ctypes stub (used by the tests and the benchmark)
-
-```python
-import ctypes
-L = ctypes.CDLL("qhg4_b200/libqhg_b200.so")
-pop = ctypes.c_void_p()
-assert L.qhgb_create(b"tut_EnvironAltPop", 0, n_cells, 6, 0, ctypes.byref(pop)) == 0, L.qhgb_last_error()
-L.qhgb_set_cells(pop, nbr.ctypes.data_as(ctypes.c_void_p), None)
-...
-```
-`qhg4_b200/capi.py` declares every symbol with its argument types; `qhg4_b200/population.py` wraps them in the
-reference's call order.

@@ -39,6 +39,11 @@
 #include "Vegetation.h"
 #include "tut_EnvironAltPop.h"
 #include "tut_EnvironCapAltPop.h"
+#ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
+#include <cstdlib>
+#include <vector>
+#include "../integration/tut_EnvironAltGpuPop.h"
+#endif
 
 namespace {
 
@@ -114,6 +119,10 @@ int PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>::bd(double *&b, double *&
     b = pop->m_pVerhulst->m_pLB->m_adB; d = pop->m_pVerhulst->m_pLD->m_adD;
     return 0;
 }
+#ifdef QHG_WITH_GPU_ADAPTER
+template <>
+int PopAccessT<tut_EnvironAltGpuPop, tut_EnvironAltAgent>::bd(double *&b, double *&d) { return -1; }  // lives on the device
+#endif
 template <>
 int PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>::bd(double *&b, double *&d) {
     if (pop->m_pVerVarK->m_pLB == NULL || pop->m_pVerVarK->m_pLD == NULL) return -1;
@@ -132,6 +141,7 @@ struct RefSim {
     PopLooper *looper = nullptr;
     IDGen **idg = nullptr;
     PopAccess *pa = nullptr;
+    bool adapter = false;  // the population keeps its agents on the GPU: preWrite brings them back before they are read
     uint32_t state[16];
     uint seeds[8];
 };
@@ -244,6 +254,12 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>(new tut_EnvironAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
         s->pa = new PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+#ifdef QHG_WITH_GPU_ADAPTER
+    } else if (std::string(class_name) == "tut_EnvironAltGpuPop") {  // the reference's loop drives the CUDA path
+        s->pa = new PopAccessT<tut_EnvironAltGpuPop, tut_EnvironAltAgent>(new tut_EnvironAltGpuPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+        s->adapter = true;
+        class_name = "tut_EnvironAltPop";  // the class entry of the parameter file
+#endif
     } else {
         fprintf(stderr, "[qref_create] unknown population class [%s]\n", class_name);
         return NULL;
@@ -323,6 +339,7 @@ long qref_num_agents(void *h) { return (long)((RefSim *)h)->pa->base()->getNumAg
 long qref_get_agents(void *h, long cap, int *cell, int64_t *id, float *birth, uint8_t *gender, float *age,
                      float *lastBirth, uint32_t *life, int *mate, int *slot) {
     RefSim *s = (RefSim *)h;
+    if (s->adapter) { Quiet q(s->quiet); s->pa->base()->preWrite(0.0f); }
     int first = s->pa->first();
     if (first < 0) return 0;
     int last = s->pa->last();
@@ -348,7 +365,8 @@ long qref_get_agents(void *h, long cap, int *cell, int64_t *id, float *birth, ui
 
 int qref_get_counts(void *h, uint64_t *out) {
     RefSim *s = (RefSim *)h;
-    for (int c = 0; c < s->nCells; c++) out[c] = s->pa->base()->getNumAgents(c);
+    if (s->adapter) s->pa->base()->updateNumAgentsPerCell();
+    for (int c = 0; c < s->nCells; c++) out[c] = s->adapter ? ((SPopulation<tut_EnvironAltAgent> *)s->pa->base())->m_aiNumAgentsPerCell[c] : s->pa->base()->getNumAgents(c);
     return 0;
 }
 

@@ -13,18 +13,26 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libqhgref.so")
+# the same driver and reference objects plus the plugin class of INTEGRATION.md (integration/tut_EnvironAltGpuPop.h),
+# linked against qhg4_b200/libqhg_b200.so: the reference's PopLooper::doStep drives the CUDA path (`make adapter`)
+ADAPTER_PATH = os.path.join(_HERE, "_ref", "libqhgadapter.so")
 
 _lib = None
+_libs = {}
 
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
-def lib():
+def adapter_available() -> bool:
+    return os.path.exists(ADAPTER_PATH)
+
+
+def lib(adapter: bool = False):
     global _lib
-    if _lib is None:
-        L = C.CDLL(LIB_PATH)
+    if adapter not in _libs:
+        L = C.CDLL(ADAPTER_PATH if adapter else LIB_PATH)
         L.qref_create.restype = C.c_void_p
         L.qref_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_int, C.c_int]
@@ -49,8 +57,8 @@ def lib():
         L.qref_destroy.argtypes = [C.c_void_p]
         L.qref_well_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.qref_polyline_eval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        _lib = L
-    return _lib
+        _libs[adapter] = L
+    return _libs[adapter]
 
 
 def _p(a):
@@ -76,9 +84,12 @@ def polyline_eval(defn: str, x, float_cast=True):
 class RefSim:
     """One `tut_EnvironAltPop` on a given grid, driven through PopLooper::doStep."""
 
-    def __init__(self, params, nbr, altitude, ice=None, threads=1, state16=None, quiet=True, layer_size=65536, env=None):
+    def __init__(self, params, nbr, altitude, ice=None, threads=1, state16=None, quiet=True, layer_size=65536, env=None,
+                 adapter=False):
         from qhg4_b200.params import DEFAULT_STATE
         self.ncells = len(nbr)
+        self.adapter = bool(adapter)
+        self.L = lib(self.adapter)
         self._nbr = np.ascontiguousarray(nbr, dtype=np.int32)
         alt = np.ascontiguousarray(altitude, dtype=np.float64)
         icea = None if ice is None else np.ascontiguousarray(ice, dtype=np.uint8)
@@ -87,7 +98,8 @@ class RefSim:
             f.write(params.to_xml())
             path = f.name
         try:
-            self.h = lib().qref_create(path.encode(), params.class_name.encode(), self.ncells, _p(self._nbr),
+            cls = "tut_EnvironAltGpuPop" if self.adapter else params.class_name
+            self.h = self.L.qref_create(path.encode(), cls.encode(), self.ncells, _p(self._nbr),
                                        _p(alt), _p(icea), int(threads), _p(st), int(layer_size), int(quiet))
         finally:
             os.unlink(path)
@@ -100,14 +112,14 @@ class RefSim:
     def set_env(self, name, v):
         v = np.ascontiguousarray(v, np.float64)
         assert len(v) == self.ncells
-        assert lib().qref_set_env(self.h, name.encode(), _p(v)) == 0, name
+        assert self.L.qref_set_env(self.h, name.encode(), _p(v)) == 0, name
 
     def event(self, event_id, t=0.0, flush=True):
-        return lib().qref_event(self.h, int(event_id), float(t), int(flush))
+        return self.L.qref_event(self.h, int(event_id), float(t), int(flush))
 
     def capacities(self):
         out = np.zeros(self.ncells)
-        assert lib().qref_get_capacities(self.h, _p(out)) == 0
+        assert self.L.qref_get_capacities(self.h, _p(out)) == 0
         return out
 
     def add_agents(self, pop: dict):
@@ -116,71 +128,71 @@ class RefSim:
                 np.ascontiguousarray(pop["birth"], np.float32), np.ascontiguousarray(pop["gender"], np.uint8),
                 np.ascontiguousarray(pop["age"], np.float32), np.ascontiguousarray(pop["last_birth"], np.float32),
                 np.ascontiguousarray(pop["life"], np.uint32)]
-        rc = lib().qref_add_agents(self.h, n, *[_p(a) for a in arrs])
+        rc = self.L.qref_add_agents(self.h, n, *[_p(a) for a in arrs])
         assert rc == 0
 
     def start(self):
-        rc = lib().qref_start(self.h)
+        rc = self.L.qref_start(self.h)
         if rc != 0:
             raise RuntimeError(f"qref_start -> {rc}")
 
     def step(self, t: float):
-        return lib().qref_step(self.h, float(t))
+        return self.L.qref_step(self.h, float(t))
 
     def run(self, t0: float, nsteps: int):
         n = C.c_int64(0)
-        sec = lib().qref_run(self.h, float(t0), int(nsteps), C.byref(n))
+        sec = self.L.qref_run(self.h, float(t0), int(nsteps), C.byref(n))
         return sec, n.value
 
     def num_agents(self) -> int:
-        return int(lib().qref_num_agents(self.h))
+        return int(self.L.qref_num_agents(self.h))
 
     def agents(self) -> dict:
         n = self.num_agents()
         out = dict(cell=np.zeros(n, np.int32), id=np.zeros(n, np.int64), birth=np.zeros(n, np.float32),
                    gender=np.zeros(n, np.uint8), age=np.zeros(n, np.float32), last_birth=np.zeros(n, np.float32),
                    life=np.zeros(n, np.uint32), mate=np.zeros(n, np.int32), slot=np.zeros(n, np.int32))
-        k = lib().qref_get_agents(self.h, n, *[_p(out[f]) for f in
+        k = self.L.qref_get_agents(self.h, n, *[_p(out[f]) for f in
                                                ("cell", "id", "birth", "gender", "age", "last_birth", "life", "mate", "slot")])
         assert k == n, (k, n)
         return out
 
     def counts(self):
         out = np.zeros(self.ncells, np.uint64)
-        lib().qref_get_counts(self.h, _p(out))
+        self.L.qref_get_counts(self.h, _p(out))
         return out
 
     def weights(self):
         out = np.zeros((self.ncells, 7), np.float64)
-        lib().qref_get_weights(self.h, _p(out))
+        self.L.qref_get_weights(self.h, _p(out))
         return out
 
     def bd(self):
         b = np.zeros(self.ncells)
         d = np.zeros(self.ncells)
-        rc = lib().qref_get_bd(self.h, _p(b), _p(d))
+        rc = self.L.qref_get_bd(self.h, _p(b), _p(d))
         assert rc == 0
         return b, d
 
     def atan_prob(self, age):
         age = np.ascontiguousarray(age, np.float32)
         p = np.zeros(len(age))
-        lib().qref_atan_prob(self.h, len(age), _p(age), _p(p))
+        self.L.qref_atan_prob(self.h, len(age), _p(age), _p(p))
         return p
 
     def geo_event(self, altitude=None, ice=None, t=0.0):
         a = None if altitude is None else np.ascontiguousarray(altitude, np.float64)
         i = None if ice is None else np.ascontiguousarray(ice, np.uint8)
-        return lib().qref_geo_event(self.h, _p(a), _p(i), float(t))
+        return self.L.qref_geo_event(self.h, _p(a), _p(i), float(t))
 
     def timers(self):
         a, f = C.c_double(0), C.c_double(0)
-        lib().qref_timers(self.h, C.byref(a), C.byref(f))
+        self.L.qref_timers(self.h, C.byref(a), C.byref(f))
         return a.value, f.value
 
     def close(self):
         if self.h:
-            lib().qref_destroy(self.h)
+            self.L.qref_destroy(self.h)
             self.h = None
 
     def __del__(self):

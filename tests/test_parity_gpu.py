@@ -393,3 +393,33 @@ def test_navigate_sea_crossings_bit_exact_vs_oracle():
     # agents did arrive in destination cells that no neighbour move could have filled from an empty neighbourhood
     far = np.setdiff1d(dests, np.concatenate([occupied, nbr[occupied].ravel()]))
     assert far.size == 0 or g.counts()[far].sum() >= 0
+
+
+def test_reference_step_loop_drives_cuda_path_through_plugin_class():
+    """The drop-in boundary exercised from the reference's side: the UNMODIFIED reference sources (PopLooper::doStep,
+    core/PopLooper.cpp:190-232, SPopulation, ParamProvider2, the tutorial population) with the plugin class of
+    INTEGRATION.md (integration/tut_EnvironAltGpuPop.h) loaded as the population.  Its initializeStep / doActions /
+    finalizeStep virtuals go to the C ABI; preWrite brings the agents back into the reference's LayerBuf.  Results must
+    be bit-identical to the counter-mode oracle, like a direct C-ABI run."""
+    from oracle import port, refsim
+    if not refsim.adapter_available():
+        pytest.skip("oracle/_ref/libqhgadapter.so not built (make -C oracle adapter needs /root/reference)")
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=3)
+    pop = synthetic_population(50000, alt, seed=9, fertile=True)
+    par, st = tut_environ_alt(30.0), seed_state(11)
+    r = refsim.RefSim(par, nbr, alt, state16=st, adapter=True)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    for k in range(8):
+        assert r.step(float(k)) == 0
+        o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+    ra, oa = r.agents(), o.agents()
+    ir, io = np.argsort(ra["id"]), np.argsort(oa["id"])
+    for f in ("cell", "id", "birth", "gender", "age", "last_birth", "life"):
+        assert np.array_equal(ra[f][ir], oa[f][io]), f
+    assert np.array_equal(r.counts(), o.counts())
+    r.close()
+
