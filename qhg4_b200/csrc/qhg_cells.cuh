@@ -28,8 +28,14 @@ namespace qhg {
 
 constexpr int CW = 4;            // warps per CTA
 constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles; larger ones -> generic path
-constexpr int MAXF = 512;        // most fertile females of one cell that can be ranked in shared memory
-constexpr int QCAP = 128;        // work-queue entries per warp (flushed when more than half full)
+#ifndef QHG_MAXF
+#define QHG_MAXF 512
+#endif
+#ifndef QHG_QCAP
+#define QHG_QCAP 64
+#endif
+constexpr int MAXF = QHG_MAXF;   // most fertile females of one cell that can be ranked in shared memory
+constexpr int QCAP = QHG_QCAP;   // work-queue entries per warp (flushed when the next round could overflow them)
 constexpr int MVCAP = 64;        // movers queued per warp in the scatter pass
 constexpr int MOVE_STRIDE = 8;    // ints per cell in moveBase[] (one 32-byte sector)
 constexpr int AGENT_SLACK = 64;  // elements allocated past the capacity of every per-agent array (aligned bulk reads)
@@ -38,7 +44,10 @@ constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast
 #define QHG_CELL_BATCH 4
 #endif
 constexpr int CELL_BATCH = QHG_CELL_BATCH;    // consecutive cells a warp takes per grab of the work counter
-constexpr int DU = 2;            // agents per lane and chunk in the decide pass
+#ifndef QHG_DU
+#define QHG_DU 1
+#endif
+constexpr int DU = QHG_DU;       // agents per lane and chunk in the decide pass
 
 // decision byte handed from pass 1 to pass 2: bit0 male, bit1 fertile (the agent's new flags), bit2 gave birth,
 // bits 3-5 move code: 0 stays, 1..6 neighbour slot + 1, 7 dead
@@ -89,8 +98,11 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 // ---------------------------------------------------------------------------------------------
 // pass 1.  SPEC = true: the program is PROG_TUT5, known at compile time (straight-line code);
 //          SPEC = false: any program, interpreted from P.prog.
+#ifndef QHG_PF2
+#define QHG_PF2 0
+#endif
 #ifndef QHG_DECIDE_MINB
-#define QHG_DECIDE_MINB 7
+#define QHG_DECIDE_MINB 8
 #endif
 template <bool SPEC>
 __global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
@@ -191,18 +203,41 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 if (storeAge) ageN[u] = a.age[s + j];
             }
         }
+#if QHG_PF2  // second prefetch stage: two chunks ahead
+        int64_t idM[DU]; float birthM[DU], lastM[DU], ageM[DU]; uint8_t fM[DU];
+#pragma unroll
+        for (int u = 0; u < DU; u++) {
+            const int j = 32 * DU + u * 32 + lane;
+            idM[u] = 0; birthM[u] = 0; lastM[u] = 0; ageM[u] = 0; fM[u] = 0;
+            if (j < n) {
+                idM[u] = a.id[s + j]; birthM[u] = a.birth[s + j]; fM[u] = a.flags[s + j];
+                if (I.hasFert) lastM[u] = a.lastBirth[s + j];
+                if (storeAge) ageM[u] = a.age[s + j];
+            }
+        }
+#endif
         for (int j0 = 0; j0 < n; j0 += 32 * DU) {
             int64_t id[DU]; float birth[DU], lastBirth[DU], age[DU]; uint8_t f0[DU];
             uint4 r0[DU];
 #pragma unroll
             for (int u = 0; u < DU; u++) {
                 id[u] = idN[u]; birth[u] = birthN[u]; lastBirth[u] = lastN[u]; age[u] = ageN[u]; f0[u] = fN[u];
+#if QHG_PF2
+                idN[u] = idM[u]; birthN[u] = birthM[u]; lastN[u] = lastM[u]; ageN[u] = ageM[u]; fN[u] = fM[u];
+                const int j2 = j0 + 2 * 32 * DU + u * 32 + lane;
+                if (j2 < n) {
+                    idM[u] = a.id[s + j2]; birthM[u] = a.birth[s + j2]; fM[u] = a.flags[s + j2];
+                    if (I.hasFert) lastM[u] = a.lastBirth[s + j2];
+                    if (storeAge) ageM[u] = a.age[s + j2];
+                }
+#else
                 const int j2 = j0 + 32 * DU + u * 32 + lane;
                 if (j2 < n) {
                     idN[u] = a.id[s + j2]; birthN[u] = a.birth[s + j2]; fN[u] = a.flags[s + j2];
                     if (I.hasFert) lastN[u] = a.lastBirth[s + j2];
                     if (storeAge) ageN[u] = a.age[s + j2];
                 }
+#endif
             }
 #pragma unroll
             for (int u = 0; u < DU; u++) r0[u] = I.needAct0 ? agent_draws_rk(id[u], step, STREAM_ACT0, RK) : make_uint4(0, 0, 0, 0);
