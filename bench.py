@@ -243,7 +243,10 @@ def run_ours(args, rank, world):
             g.do_actions(lvl, t)
         g.finalize_step()
         st = g.step_stats()          # totals of the step (D2H inside finalize_step)
-        g.counts(counts)             # per-cell counts into host memory, as PopBase::getNumAgents exposes them
+        if world > 1:                # a shard reads back the counts of its own cell range
+            g.counts_range(begin[rank], begin[rank + 1], counts)
+        else:
+            g.counts(counts)         # per-cell counts into host memory, as PopBase::getNumAgentsArray exposes them
         t += 1.0
     barrier()
     e2e_sec = allmax(time.perf_counter() - w0)
@@ -261,11 +264,20 @@ def run_ours(args, rank, world):
     alg_bytes = ALG_BYTES_PER_AGENT * prof_agent_steps + ALG_BYTES_PER_CELL * ncell * args.steps
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     top = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
+    # the two hot kernels against their own algorithmic bytes: pass 1 reads 17 B and writes 1 B per agent,
+    # pass 2 reads 18 B per agent and writes 17 B per agent that is alive afterwards (~ the same number)
+    per_kernel = {}
+    for kname, bpa in (("k_cell_decide", 18.0), ("k_cell_scatter", 35.0)):
+        if kname in ktimes and ktimes[kname][0] > 0:
+            kms = allmax(ktimes[kname][0])
+            gbs = bpa * prof_agent_steps / (kms * 1e-3) / 1e9
+            per_kernel[kname] = {"alg_bytes_per_agent": bpa, "ms_per_step": round(kms / args.steps, 4), "achieved": round(gbs, 1),
+                                 "frac": round(gbs / peak, 4)}
     roof = {"bound": "hbm", "kernel": "whole step (all kernels of one doStep, summed device time)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_step(agent_steps / args.steps),
             "peak_source": peak_src,
             "alg_bytes_per_step": alg_bytes / args.steps, "dominant_kernel": top,
-            "pipeline_ms_per_step": round(pipeline_ms / args.steps, 4),
+            "pipeline_ms_per_step": round(pipeline_ms / args.steps, 4), "per_kernel": per_kernel,
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}}
 
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
@@ -280,9 +292,10 @@ def run_ours(args, rank, world):
                        "parallelism": f"cell-range shards x{world}, NCCL migration" if world > 1 else "single GPU",
                        "migrations_per_step": migrated / args.steps},
             "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * ncell + 48,
+            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * int(begin[rank + 1] - begin[rank]) + 48,
                     "what": "initializeStep + doActions per level + finalizeStep through the C ABI, then totals and the per-cell count "
-                            "array (ulong per cell, as PopBase::getNumAgentsArray) copied into page-locked host memory every step"},
+                            "array (ulong per cell, as PopBase::getNumAgentsArray; sharded: every rank its own cell range) copied into "
+                            "page-locked host memory every step"},
             "roofline": roof}
     g.close()
     if dist is not None:

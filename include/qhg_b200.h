@@ -140,6 +140,9 @@ int  qhgb_flush_events(qhgb_pop *p, float t);
  * (:145-146; one ulong per cell). */
 int64_t qhgb_get_num_agents_effective(qhgb_pop *p);
 int     qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out);
+/* the same for the cells [cell_begin, cell_end) only, out[0] = cell_begin's count: what a rank of a sharded run reads
+ * back every step (its own cell range; the other cells are some other rank's and 0 here) */
+int     qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end, uint64_t *out);
 int     qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out);
 /* parity probes for the deterministic sub-steps: the arrays the reference keeps in
  * m_adEnvWeights (n_cells*(max_neigh+1) doubles, actions/SingleEvaluator.cpp:174-243), LinearBirth::m_adB /

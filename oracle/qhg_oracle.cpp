@@ -307,7 +307,7 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
 };
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE};
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -342,6 +342,7 @@ struct qor_pop {
     double atanMaxAge = 0, atanRange = 0, atanSlope = 0, atanScale = 0;
     double oadMaxAge = 0, oadUncertainty = 0;
     double moveProb = 0;
+    double randMoveProb = 0;  // RandomMove_prob (actions/RandomMove.cpp)
     float fertMinAge = 0, fertMaxAge = 0, fertInterbirth = 0;
     double vB0 = -1024, vD0 = -1024, vTheta = -1024, vK = -1024;
     PolyLine altPref;
@@ -680,6 +681,21 @@ struct qor_pop {
             }
             break;
         }
+        case A_RANDOMMOVE: {  // actions/RandomMove.cpp:65-100: no weights, no ice test; direction 0 = stay
+            if (a.life > 0) {
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_MOVE));
+                if (r < randMoveProb) {
+                    int c = a.cell;
+                    double r2 = u2d(draw(a.id, STREAM_ACT1, L1_MOVE2));
+                    int pick = (int)(r2 * (nNbr[c] + 1));
+                    if (pick > 0) {
+                        int to = nbr[(size_t)c * maxNeigh + pick - 1];
+                        if (to >= 0) registerMove(c, i, to);
+                    }
+                }
+            }
+            break;
+        }
         case A_FERTILITY: {  // actions/Fertility.cpp:49-74 (overwrites the whole life state, incl. the MOVING bit)
             if (a.life > 0) {
                 if (a.gender == 0) {
@@ -957,6 +973,13 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_SexualPop") {  // populations/tut_SexualPop.cpp:24-44
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Fertility", A_FERTILITY},
+                      {"Verhulst", A_VERHULST}, {"RandomPair", A_RANDOMPAIR}};
+    } else if (p->popClass == "tut_MovePop") {  // populations/tut_MovePop.cpp:19-31
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}};
+    } else if (p->popClass == "tut_OldAgeDiePop") {  // populations/tut_OldAgeDiePop.cpp:17-26
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}};
     } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
@@ -1018,6 +1041,7 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "OAD_max_age") p->oadMaxAge = v;
     else if (s == "OAD_uncertainty") p->oadUncertainty = v;
     else if (s == "WeightedMove_prob") p->moveProb = v;
+    else if (s == "RandomMove_prob") p->randMoveProb = v;
     else if (s == "Fertility_min_age") p->fertMinAge = (float)v;
     else if (s == "Fertility_max_age") p->fertMaxAge = (float)v;
     else if (s == "Fertility_interbirth") p->fertInterbirth = (float)v;

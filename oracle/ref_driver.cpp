@@ -39,6 +39,9 @@
 #include "Vegetation.h"
 #include "tut_EnvironAltPop.h"
 #include "tut_EnvironCapAltPop.h"
+#include "tut_SexualPop.h"
+#include "tut_MovePop.h"
+#include "tut_OldAgeDiePop.h"
 #ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
 #include <cstdlib>
 #include <vector>
@@ -94,42 +97,44 @@ struct PopAccessT : PopAccess {
     void put(int slot, const AgentRec &r, gridtype cellID) override {
         AgentT &a = pop->m_aAgents[slot];
         a.m_iLifeState = r.life; a.m_iCellIndex = r.cell; a.m_ulID = r.id; a.m_ulCellID = cellID;
-        a.m_fBirthTime = r.birth; a.m_iGender = r.gender; a.m_fAge = r.age; a.m_fLastBirth = r.lastBirth; a.m_iMateIndex = -3;
+        a.m_fBirthTime = r.birth; a.m_iGender = r.gender; a.m_fAge = r.age;
+        if constexpr (requires { a.m_fLastBirth; }) { a.m_fLastBirth = r.lastBirth; a.m_iMateIndex = -3; }  // the smaller tutorial agents have no such fields
     }
     bool get(int slot, AgentRec &r) override {
         AgentT &a = pop->m_aAgents[slot];
         if (a.m_iLifeState == LIFE_STATE_DEAD) return false;
         r.cell = a.m_iCellIndex; r.id = a.m_ulID; r.birth = a.m_fBirthTime; r.gender = a.m_iGender; r.age = a.m_fAge;
-        r.lastBirth = a.m_fLastBirth; r.life = a.m_iLifeState; r.mate = a.m_iMateIndex; r.slot = slot;
+        r.lastBirth = 0; r.mate = -3;
+        if constexpr (requires { a.m_fLastBirth; }) { r.lastBirth = a.m_fLastBirth; r.mate = a.m_iMateIndex; }
+        r.life = a.m_iLifeState; r.slot = slot;
         return true;
     }
     int first() override { return pop->getFirstAgentIndex(); }
     int last() override { return pop->getLastAgentIndex(); }
     idtype &maxID() override { return pop->m_iMaxID; }
-    double *envWeights() override { return pop->m_adEnvWeights; }
-    double *capacities() override { return pop->m_adCapacities; }
-    int bd(double *&b, double *&d) override;
+    double *envWeights() override {
+        if constexpr (requires { pop->m_adEnvWeights; }) return pop->m_adEnvWeights; else return nullptr;
+    }
+    double *capacities() override {
+        if constexpr (requires { pop->m_adCapacities; }) return pop->m_adCapacities; else return nullptr;
+    }
+    int bd(double *&b, double *&d) override {  // the arrays of LinearBirth / LinearDeath inside Verhulst resp. VerhulstVarK
+        if constexpr (requires { pop->m_pVerhulst; }) {
+            if (pop->m_pVerhulst->m_pLB == NULL || pop->m_pVerhulst->m_pLD == NULL) return -1;
+            b = pop->m_pVerhulst->m_pLB->m_adB; d = pop->m_pVerhulst->m_pLD->m_adD;
+            return 0;
+        } else if constexpr (requires { pop->m_pVerVarK; }) {
+            if (pop->m_pVerVarK->m_pLB == NULL || pop->m_pVerVarK->m_pLD == NULL) return -1;
+            b = pop->m_pVerVarK->m_pLB->m_adB; d = pop->m_pVerVarK->m_pLD->m_adD;
+            return 0;
+        } else {
+            return -1;
+        }
+    }
     void atanParams(double &scale, double &slope, double &maxAge) override {
         scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge;
     }
 };
-template <>
-int PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>::bd(double *&b, double *&d) {
-    if (pop->m_pVerhulst->m_pLB == NULL || pop->m_pVerhulst->m_pLD == NULL) return -1;
-    b = pop->m_pVerhulst->m_pLB->m_adB; d = pop->m_pVerhulst->m_pLD->m_adD;
-    return 0;
-}
-#ifdef QHG_WITH_GPU_ADAPTER
-template <>
-int PopAccessT<tut_EnvironAltGpuPop, tut_EnvironAltAgent>::bd(double *&b, double *&d) { return -1; }  // lives on the device
-#endif
-template <>
-int PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>::bd(double *&b, double *&d) {
-    if (pop->m_pVerVarK->m_pLB == NULL || pop->m_pVerVarK->m_pLD == NULL) return -1;
-    b = pop->m_pVerVarK->m_pLB->m_adB; d = pop->m_pVerVarK->m_pLD->m_adD;
-    return 0;
-}
-
 struct RefSim {
     int nCells = 0;
     int nThreads = 1;
@@ -252,6 +257,12 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
     const int ls = layerSize > 0 ? layerSize : 65536;
     if (std::string(class_name) == "tut_EnvironAltPop") {
         s->pa = new PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>(new tut_EnvironAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_SexualPop") {
+        s->pa = new PopAccessT<tut_SexualPop, tut_SexualAgent>(new tut_SexualPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_MovePop") {
+        s->pa = new PopAccessT<tut_MovePop, tut_MoveAgent>(new tut_MovePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_OldAgeDiePop") {
+        s->pa = new PopAccessT<tut_OldAgeDiePop, tut_OldAgeDieAgent>(new tut_OldAgeDiePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
         s->pa = new PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
 #ifdef QHG_WITH_GPU_ADAPTER

@@ -80,15 +80,16 @@ constexpr unsigned long long PROG_TUT5 = (unsigned long long)OP_GETOLD | ((unsig
 struct ProgramInfo {  // warp-uniform facts about the action program
     bool needAct0, hasFert, hasVerhulst;
     bool moveAfterAtan, bornAfterAtan;
+    bool randomMove;  // the move action is RandomMove (uniform direction, no ice test) instead of WeightedMove
 };
 
 __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int nOps) {
-    ProgramInfo I{false, false, false, false, false};
+    ProgramInfo I{false, false, false, false, false, false};
     int ka = -1;
     for (int k = 0; k < nOps; k++) {
         int op = (int)((prog >> (4 * k)) & 15ull);
         if (op == OP_ATANDEATH) { ka = k; I.needAct0 = true; }
-        if (op == OP_WEIGHTEDMOVE) { I.needAct0 = true; if (ka >= 0) I.moveAfterAtan = true; }
+        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) { I.needAct0 = true; I.randomMove = (op == OP_RANDOMMOVE); if (ka >= 0) I.moveAfterAtan = true; }
         if (op == OP_VERHULST) { I.needAct0 = true; I.hasVerhulst = true; if (ka >= 0) I.bornAfterAtan = true; }
         if (op == OP_FERTILITY) I.hasFert = true;
     }
@@ -171,6 +172,11 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 const int j = S.qmJ[e];
                 const uint32_t u = agent_draws_rk(S.qmId[e], step, STREAM_ACT1, RK).x;
                 int pick = -1;
+                if (!SPEC && I.randomMove) {  // RandomMove: uniform over "stay" and the neighbours, no ice test
+                    pick = (int)__dmul_rn(u2d(u), (double)(nreal + 1));
+                    if (pick > 0 && S.nbrC[pick - 1] >= 0) sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    continue;
+                }
                 const double wmax = row[nreal];
                 if (row[0] == wmax) {
                     pick = (int)u2int(u, 0, nreal + 1);
@@ -276,7 +282,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                             ag = __fsub_rn(tNow, birth[u]);
                             const uint32_t uo = agent_draws(id[u], step, STREAM_ACT1, key).w;
                             if ((double)ag > __dadd_rn(P.oadMaxAge, u2range(uo, P.oadLo, P.oadHi))) alive = false;
-                        } else if (op == OP_WEIGHTEDMOVE) {  // actions/WeightedMove.cpp:45-106; the neighbour is chosen at the flush
+                        } else if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) {  // actions/WeightedMove.cpp:45-106, RandomMove.cpp:65-100; the neighbour is chosen at the flush
                             if ((unsigned long long)r0[u].y < tMove) needMove = true;
                         } else if (op == OP_FERTILITY) {  // actions/Fertility.cpp:49-74
                             bool fert;

@@ -20,7 +20,7 @@ constexpr int MAX_OPS = 16;
 // agent flag byte: gender and the FERTILE bit of the reference's life state (core/SPopulation.h:70-74)
 constexpr uint8_t F_MALE = 1, F_FERTILE = 2, F_BORN = 4;  // F_BORN only in the per-step decision byte
 
-enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE };
+enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE, OP_RANDOMMOVE };
 
 struct AgentArrays {
     int64_t *id;
@@ -400,6 +400,18 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 if (pick > 0) {
                     int dst = E.nbr[(size_t)c * MAXN + pick - 1];
                     if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
+                }
+            }
+            break;
+        }
+        case OP_RANDOMMOVE: {  // actions/RandomMove.cpp:65-100: direction = (int)(r2 * (neighbours + 1)), 0 = stay; no ice test
+            if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+            if (u2d(r0.y) < P.moveProb) {
+                if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                const int pick = (int)__dmul_rn(u2d(r1.x), (double)(E.nNbr[c] + 1));
+                if (pick > 0) {
+                    int dst = E.nbr[(size_t)c * MAXN + pick - 1];
+                    if (dst >= 0) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
                 }
             }
             break;

@@ -96,7 +96,7 @@ int loadNccl() {
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -431,6 +431,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_ATANDEATH: op = OP_ATANDEATH; break;
         case A_OLDAGEDEATH: op = OP_OLDAGEDEATH; break;
         case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
+        case A_RANDOMMOVE: op = OP_RANDOMMOVE; break;
         case A_FERTILITY: op = OP_FERTILITY; break;
         case A_VERHULST: op = OP_VERHULST; break;
         case A_VERHULSTVARK: op = OP_VERHULST; break;
@@ -469,7 +470,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     double unc = p->A("OAD_uncertainty");
     P.oadLo = 1 - unc * P.oadMaxAge;
     P.oadHi = 1 + unc * P.oadMaxAge;
-    P.moveProb = p->A("WeightedMove_prob");
+    P.moveProb = p->findKind(A_RANDOMMOVE) ? p->A("RandomMove_prob") : p->A("WeightedMove_prob");  // a population has one move action
     P.fertMinAge = (float)p->A("Fertility_min_age");
     P.fertMaxAge = (float)p->A("Fertility_max_age");
     P.fertInterbirth = (float)p->A("Fertility_interbirth");
@@ -886,6 +887,13 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_SexualPop") {  // populations/tut_SexualPop.cpp:24-44
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Fertility", A_FERTILITY},
+                      {"Verhulst", A_VERHULST}, {"RandomPair", A_RANDOMPAIR}};
+    } else if (p->popClass == "tut_MovePop") {  // populations/tut_MovePop.cpp:19-31
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}};
+    } else if (p->popClass == "tut_OldAgeDiePop") {  // populations/tut_OldAgeDiePop.cpp:17-26
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}};
     } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
@@ -1049,7 +1057,7 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
 }
 
 static const char *const kNumericAttrs[] = {
-    "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob",
+    "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob", "RandomMove_prob",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
     "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
@@ -1386,6 +1394,18 @@ int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     // a single DMA when that array is page-locked (qhgb_host_alloc)
     LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
     CK(cudaMemcpyAsync(out, p->count64.p, sizeof(uint64_t) * (size_t)p->nCells, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end, uint64_t *out) {
+    if (!p || !out) return fail("qhgb_get_num_agents_range: NULL argument");
+    if (!p->haveCells) return fail("qhgb_get_num_agents_range: call qhgb_set_cells first");
+    if (cell_begin < 0 || cell_end > p->nCells || cell_begin > cell_end) return fail("qhgb_get_num_agents_range: [%d, %d) is not inside [0, %d)", cell_begin, cell_end, p->nCells);
+    if (cell_begin == cell_end) return 0;
+    CK(cudaSetDevice(p->device));
+    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
+    CK(cudaMemcpyAsync(out, p->count64.p + cell_begin, sizeof(uint64_t) * (size_t)(cell_end - cell_begin), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }

@@ -121,6 +121,42 @@ def tut_environ_cap_alt() -> PopParams:
     )
 
 
+def tut_sexual(K: float = 30.0, move_prob: float = 0.05) -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_Sexual.xml` (values restated): RandomMove instead of WeightedMove, and
+    the ageing / death actions AFTER pairing, births and the move."""
+    return PopParams(
+        "tut_SexualPop",
+        modules={
+            "ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"},
+            "RandomMove": {"RandomMove_prob": repr(float(move_prob))},
+            "Fertility": {"Fertility_interbirth": "2.0", "Fertility_max_age": "50.0", "Fertility_min_age": "14.0"},
+            "Verhulst": {"Verhulst_b0": "0.8", "Verhulst_d0": "0.001", "Verhulst_theta": "0.1", "Verhulst_K": repr(float(K))},
+        },
+        prios={"GetOld": 8, "ATanDeath": 10, "RandomMove": 7, "Fertility": 2, "RandomPair": 3, "Verhulst": 6},
+    )
+
+
+def tut_move(move_prob: float = 0.1) -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_Move.xml` (values restated): ageing, ATanDeath, RandomMove; no births."""
+    return PopParams(
+        "tut_MovePop",
+        modules={
+            "ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"},
+            "RandomMove": {"RandomMove_prob": repr(float(move_prob))},
+        },
+        prios={"GetOld": 8, "ATanDeath": 10, "RandomMove": 9},
+    )
+
+
+def tut_old_age_die() -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_OldAgeDie.xml` (values restated): ageing and ATanDeath only."""
+    return PopParams(
+        "tut_OldAgeDiePop",
+        modules={"ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"}},
+        prios={"GetOld": 8, "ATanDeath": 10},
+    )
+
+
 def ooa_nav_gen(genome_size: int = 4096, num_crossover: int = -1, mutation_rate: float = 1e-5) -> PopParams:
     """`OoANavGenPop` (populations/OoANavGenPop.cpp:33-97) without Navigate: the genetic population of config C3.
     The reference ships no parameter file for it; ecological values follow tut_EnvironCapAlt.xml, the Genetics values are

@@ -151,6 +151,12 @@ class GpuPopulation:
         check(self.L.qhgb_get_num_agents_array(self.h, _p(out)), "qhgb_get_num_agents_array")
         return out
 
+    def counts_range(self, c0: int, c1: int, out=None):
+        """per-cell counts of the cells [c0, c1) only (a shard reads back its own range)"""
+        out = np.zeros(c1 - c0, np.uint64) if out is None else out
+        check(self.L.qhgb_get_num_agents_range(self.h, int(c0), int(c1), _p(out)), "qhgb_get_num_agents_range")
+        return out
+
     def step_stats(self) -> StepStats:
         s = StepStats()
         check(self.L.qhgb_get_step_stats(self.h, C.byref(s)), "qhgb_get_step_stats")

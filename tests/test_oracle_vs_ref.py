@@ -40,6 +40,33 @@ def test_well_mode_equals_reference_one_thread(seed, K, grid):
     r.close()
 
 
+@pytest.mark.parametrize("which", ["tut_SexualPop", "tut_MovePop", "tut_OldAgeDiePop"])
+def test_small_tutorial_populations_equal_reference(which):
+    """RandomMove (actions/RandomMove.cpp:65-100) and the other action orders of the tutorial ladder
+    (tut_Sexual.xml: Fertility 2, RandomPair 3, Verhulst 6, RandomMove 7, GetOld 8, ATanDeath 10): the oracle's WELL
+    mode reproduces the reference slot for slot."""
+    from qhg4_b200.params import tut_move, tut_old_age_die, tut_sexual
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=4)
+    pop = synthetic_population(9000, alt, seed=8, fertile=True)
+    par = {"tut_SexualPop": tut_sexual(25.0, 0.2), "tut_MovePop": tut_move(0.3), "tut_OldAgeDiePop": tut_old_age_die()}[which]
+    st = seed_state(13)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    fields = FIELDS if which == "tut_SexualPop" else tuple(f for f in FIELDS if f != "last_birth")
+    for k in range(15):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in fields:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+    assert r.num_agents() != len(pop["id"])  # something happened
+    r.close()
+
+
 def test_geo_event_equals_reference():
     nbr, xyz = make_ico_grid(7)
     alt = synthetic_altitude(xyz, seed=5)

@@ -395,6 +395,30 @@ def test_navigate_sea_crossings_bit_exact_vs_oracle():
     assert far.size == 0 or g.counts()[far].sum() >= 0
 
 
+@pytest.mark.parametrize("which", ["tut_SexualPop", "tut_MovePop", "tut_OldAgeDiePop"])
+def test_small_tutorial_populations_bit_exact_vs_oracle(which, path):
+    """The rest of the reference's tutorial ladder: RandomMove (actions/RandomMove.cpp:65-100) and the action order of
+    tut_Sexual.xml (Fertility, RandomPair, Verhulst, RandomMove, then GetOld and ATanDeath: the age the earlier actions
+    see is last step's, so it is stored) -- on both device paths, bit-exact against the oracle's counter mode.  The
+    oracle's WELL mode is pinned against the reference for the same classes in tests/test_oracle_vs_ref.py."""
+    from qhg4_b200.params import tut_move, tut_old_age_die, tut_sexual
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=3)
+    pop = synthetic_population(40000, alt, seed=12, fertile=True)
+    par = {"tut_SexualPop": tut_sexual(30.0, 0.2), "tut_MovePop": tut_move(0.3), "tut_OldAgeDiePop": tut_old_age_die()}[which]
+    g, o = make_pair(par, nbr, alt, pop, seed=23)
+    moves = 0
+    for k in range(14):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        moves += s.moves
+    assert (moves > 0) == (which != "tut_OldAgeDiePop")
+    if which == "tut_SexualPop":
+        assert g.num_agents() > 0 and g.step_stats().births > 0
+
+
 def test_reference_step_loop_drives_cuda_path_through_plugin_class():
     """The drop-in boundary exercised from the reference's side: the UNMODIFIED reference sources (PopLooper::doStep,
     core/PopLooper.cpp:190-232, SPopulation, ParamProvider2, the tutorial population) with the plugin class of
