@@ -154,6 +154,16 @@ int  qhgb_atan_death_prob(qhgb_pop *p, int n, const float *age, double *out);
 /* the carrying capacities NPPCapacity keeps in m_adCapacities (actions/NPPCapacity.cpp:138-217), one double per cell */
 int  qhgb_get_capacities(qhgb_pop *p, double *out);
 
+/* ---- dump / restore (core/SPopulation.cpp:2024-2570: dumpSpecies..., restoreSpecies...; app/Simulator.cpp dump events) ----
+ * qhgb_dump_state writes the whole dynamic state of the population between two steps into one file (agents, genomes,
+ * id base, the step counter that is the state of the counter-based random streams, weights/capacities and the observers'
+ * flags); qhgb_restore_state loads it into a population that was created and configured like the dumped one (cells,
+ * environment arrays as of the dump, attributes, priorities, navigation) but holds no agents, and replaces
+ * qhgb_add_agents + qhgb_pre_loop.  The continued run is bit-identical to the uninterrupted one.  The file format is
+ * this library's own (HDF5, which the reference's QDF dumps use, is outside the path). */
+int  qhgb_dump_state(qhgb_pop *p, const char *path);
+int  qhgb_restore_state(qhgb_pop *p, const char *path);
+
 /* ---- several GPUs: the grid sharded by contiguous cell ranges --------------------------------------
  * One process per GPU, each with its own qhgb_pop holding the agents of its cell range [cell_begin[rank],
  * cell_begin[rank+1]); environment arrays are replicated.  Per step the ranks exchange (NCCL over NVLink) the

@@ -54,6 +54,8 @@ SYMBOLS = {
     "qhgb_get_birth_death_probs": (i32, [vp, vp, vp]),
     "qhgb_atan_death_prob": (i32, [vp, i32, vp, vp]),
     "qhgb_get_capacities": (i32, [vp, vp]),
+    "qhgb_dump_state": (i32, [vp, cp]),
+    "qhgb_restore_state": (i32, [vp, cp]),
     "qhgb_comm_get_unique_id": (i32, [vp, i32]),
     "qhgb_comm_init": (i32, [vp, i32, i32, vp, vp]),
     "qhgb_comm_get_traffic": (i32, [vp, vp, vp]),

@@ -864,6 +864,25 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
 
 }  // namespace
 
+// header and array helpers of qhgb_dump_state / qhgb_restore_state
+namespace {
+struct DumpHeader {
+    char magic[8];          // "QHGB200D"
+    uint32_t version;
+    char popClass[64];
+    int32_t nCells, maxNeigh;
+    int64_t nAgents, nextID, stepsDone;
+    float curTime;
+    uint32_t key[2];
+    int32_t genetic, rowWords;
+    int32_t evalFirst, evalNeedUpdate, multiFirst, nppNeedUpdate, navNeedUpdate, haveCap, nSubs;
+    int32_t subFirst[8], subNeedUpdate[8];
+    int64_t lastBirths, lastDeaths, lastMoves;
+};
+template <class T> bool wr(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
+template <class T> bool rd(FILE *f, std::vector<T> &v) { return v.empty() || fread(v.data(), sizeof(T), v.size(), f) == v.size(); }
+}  // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -1653,6 +1672,101 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
         CK(cudaStreamSynchronize(p->stream));
     }
     p->sharded = nranks > 1;
+    return 0;
+}
+
+// ---- dump / restore of the device state -------------------------------------------------------
+// The reference dumps a population with SPopulation::dump* / restore* (core/SPopulation.cpp:2024-2570): agent layers,
+// the WELL512 states of every thread, the IDGen states.  Here the random streams are counter based (seed, agent id,
+// step), so the whole generator state is the step counter; agents are written as the records qhgb_get_agents returns
+// (their order inside a cell carries no information).  File: one fixed header, then flat little-endian arrays.
+
+int qhgb_dump_state(qhgb_pop *p, const char *path) {
+    if (!p || !path) return fail("qhgb_dump_state: NULL argument");
+    if (!p->preLooped || p->inStep) return fail("qhgb_dump_state: only between steps (after preLoop / finalizeStep)");
+    if (p->subs.size() > 8) return fail("qhgb_dump_state: more than 8 sub-evaluators");
+    CK(cudaSetDevice(p->device));
+    const int64_t n = p->nAgents;
+    std::vector<int32_t> cell(n), cid(n);
+    std::vector<int64_t> id(n);
+    std::vector<float> birth(n), age(n), last(n);
+    std::vector<uint8_t> gender(n);
+    std::vector<uint32_t> life(n);
+    if (n > 0 && qhgb_get_agents(p, n, cell.data(), cid.data(), id.data(), birth.data(), gender.data(), age.data(), last.data(), life.data(), nullptr) != n) return -1;
+    DumpHeader h{};
+    memcpy(h.magic, "QHGB200D", 8);
+    h.version = 1;
+    snprintf(h.popClass, sizeof(h.popClass), "%s", p->popClass.c_str());
+    h.nCells = p->nCells; h.maxNeigh = p->maxNeigh; h.nAgents = n; h.nextID = p->nextID; h.stepsDone = p->stepsDone;
+    h.curTime = p->curTime; h.key[0] = p->key.k0; h.key[1] = p->key.k1;
+    h.genetic = p->genetic ? 1 : 0; h.rowWords = p->genetic ? 2 * p->gp.nBlocks : 0;
+    h.evalFirst = p->evalFirst; h.evalNeedUpdate = p->evalNeedUpdate; h.multiFirst = p->multiFirst; h.nppNeedUpdate = p->nppNeedUpdate;
+    h.navNeedUpdate = p->navNeedUpdate; h.haveCap = p->cap.p ? 1 : 0; h.nSubs = (int)p->subs.size();
+    for (size_t i = 0; i < p->subs.size(); i++) { h.subFirst[i] = p->subs[i].first; h.subNeedUpdate[i] = p->subs[i].needUpdate; }
+    h.lastBirths = p->lastBirths; h.lastDeaths = p->lastDeaths; h.lastMoves = p->lastMoves;
+    std::vector<uint64_t> genomes((size_t)n * h.rowWords);
+    std::vector<int32_t> nbab(p->genetic ? n : 0);
+    if (p->genetic && n > 0 && qhgb_get_genomes(p, n, genomes.data(), nbab.data()) != n) return -1;
+    std::vector<double> W((size_t)p->nCells * WSTRIDE), cap(h.haveCap ? p->nCells : 0);
+    CK(cudaMemcpyAsync(W.data(), p->W.p, W.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (h.haveCap) CK(cudaMemcpyAsync(cap.data(), p->cap.p, cap.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail("qhgb_dump_state: cannot open [%s]", path);
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && wr(f, cell) && wr(f, id) && wr(f, birth) && wr(f, gender) && wr(f, age) && wr(f, last) && wr(f, life) &&
+              wr(f, genomes) && wr(f, nbab) && wr(f, W) && wr(f, cap);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail("qhgb_dump_state: short write to [%s]", path);
+    return 0;
+}
+
+int qhgb_restore_state(qhgb_pop *p, const char *path) {
+    if (!p || !path) return fail("qhgb_restore_state: NULL argument");
+    if (p->preLooped || p->nAgents > 0) return fail("qhgb_restore_state: the population must be configured (cells, environment, attributes, priorities) but empty");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail("qhgb_restore_state: cannot open [%s]", path);
+    DumpHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QHGB200D", 8) != 0 || h.version != 1) { fclose(f); return fail("qhgb_restore_state: [%s] is not a qhg4_b200 dump", path); }
+    if (p->popClass != h.popClass || h.nCells != p->nCells || h.maxNeigh != p->maxNeigh || (h.genetic != 0) != p->genetic ||
+        (p->genetic && h.rowWords != 2 * p->gp.nBlocks) || h.nSubs != (int)p->subs.size()) {
+        fclose(f);
+        return fail("qhgb_restore_state: the dump is of [%s], %d cells, %d genome words -- not this population", h.popClass, h.nCells, h.rowWords);
+    }
+    const int64_t n = h.nAgents;
+    std::vector<int32_t> cell(n);
+    std::vector<int64_t> id(n);
+    std::vector<float> birth(n), age(n), last(n);
+    std::vector<uint8_t> gender(n);
+    std::vector<uint32_t> life(n);
+    std::vector<uint64_t> genomes((size_t)n * h.rowWords);
+    std::vector<int32_t> nbab(h.genetic ? n : 0);
+    std::vector<double> W((size_t)h.nCells * WSTRIDE), cap(h.haveCap ? h.nCells : 0);
+    bool ok = rd(f, cell) && rd(f, id) && rd(f, birth) && rd(f, gender) && rd(f, age) && rd(f, last) && rd(f, life) && rd(f, genomes) && rd(f, nbab) &&
+              rd(f, W) && rd(f, cap);
+    fclose(f);
+    if (!ok) return fail("qhgb_restore_state: [%s] is truncated", path);
+    CK(cudaSetDevice(p->device));
+    p->key.k0 = h.key[0]; p->key.k1 = h.key[1];
+    if (n > 0 && qhgb_add_agents(p, n, cell.data(), id.data(), birth.data(), gender.data(), age.data(), last.data(), life.data()) != 0) return -1;
+    if (p->genetic && n > 0) {
+        if (qhgb_set_genomes(p, n, genomes.data()) != 0) return -1;
+        CK(cudaMemcpyAsync(p->nbabies[p->cur].p, nbab.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    if (qhgb_pre_loop(p) != 0) return -1;
+    // what a fresh start does not know: the generator's step counter, the id base, the weights and capacities as they
+    // were (they may lag behind the environment, DESIGN.md §2 "reference quirks"), the observers' flags
+    p->stepsDone = h.stepsDone;
+    p->nextID = h.nextID;
+    p->curTime = h.curTime;
+    p->lastBirths = h.lastBirths; p->lastDeaths = h.lastDeaths; p->lastMoves = h.lastMoves;
+    if (pushStats(p) != 0) return -1;
+    CK(cudaMemcpyAsync(p->W.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (h.haveCap && p->cap.p) CK(cudaMemcpyAsync(p->cap.p, cap.data(), cap.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->evalFirst = h.evalFirst != 0; p->evalNeedUpdate = h.evalNeedUpdate != 0; p->multiFirst = h.multiFirst != 0;
+    p->nppNeedUpdate = h.nppNeedUpdate != 0; p->navNeedUpdate = h.navNeedUpdate != 0;
+    for (size_t i = 0; i < p->subs.size(); i++) { p->subs[i].first = h.subFirst[i] != 0; p->subs[i].needUpdate = h.subNeedUpdate[i] != 0; }
     return 0;
 }
 

@@ -201,6 +201,13 @@ class GpuPopulation:
         uid = C.create_string_buffer(unique_id, 128)
         check(self.L.qhgb_comm_init(self.h, int(rank), int(nranks), uid, _p(cb)), "qhgb_comm_init")
 
+    def dump_state(self, path: str):
+        check(self.L.qhgb_dump_state(self.h, str(path).encode()), "qhgb_dump_state")
+
+    def restore_state(self, path: str):
+        """instead of add_agents + pre_loop, on a population configured like the dumped one"""
+        check(self.L.qhgb_restore_state(self.h, str(path).encode()), "qhgb_restore_state")
+
     def comm_p2p_handle(self) -> bytes:
         buf = C.create_string_buffer(128)
         check(self.L.qhgb_comm_p2p_handle(self.h, buf, 128), "qhgb_comm_p2p_handle")

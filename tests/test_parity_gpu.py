@@ -419,6 +419,65 @@ def test_small_tutorial_populations_bit_exact_vs_oracle(which, path):
         assert g.num_agents() > 0 and g.step_stats().births > 0
 
 
+@pytest.mark.parametrize("which", ["tut_EnvironAltPop", "OoANavGenPop"])
+def test_dump_restore_resumes_bit_identically(which, tmp_path):
+    """SURVEY.md §8f-2 (reference: dump*/restore*, core/SPopulation.cpp:2024-2570): a run that is dumped after some steps,
+    restored into a NEW population object and continued equals the uninterrupted run AND the oracle, bit for bit --
+    agents, genomes, ids of later newborns (the id base), later random draws (the step counter), and the weights that a
+    GEO event left stale in tut_EnvironAltPop (its evaluator observes nothing, populations/tut_EnvironAltPop.cpp:24-53)."""
+    from oracle import port
+    from qhg4_b200.params import ooa_nav_gen
+    from qhg4_b200.population import GpuPopulation
+    st = seed_state(77)
+    if which == "tut_EnvironAltPop":
+        nbr, xyz = make_ico_grid(15)
+        alt = synthetic_altitude(xyz, seed=3)
+        env, par, row, gen0 = None, tut_environ_alt(25.0), 0, None
+        pop = synthetic_population(30000, alt, seed=4, fertile=True)
+    else:
+        nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+        par, row = ooa_nav_gen(256, 2, 1e-3), 8
+        pop = synthetic_population(12000, alt, seed=6, fertile=True)
+        gen0 = np.random.default_rng(1).integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+
+    def fresh():
+        return GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+
+    g = fresh()
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    for q in (g, o):
+        q.add_agents(pop)
+        if gen0 is not None:
+            q.set_genomes(gen0)
+    g.pre_loop(); o.start()
+    alt2 = alt - 120.0
+    for k in range(6):
+        g.step(float(k)); o.step(float(k))
+        if k == 2:  # sea level rises: the drowned die at once; tut_EnvironAltPop keeps its old weights
+            for q in (g, o):
+                q.set_env("Altitude", alt2)
+                q.update_event(2, 3.0); q.flush_events(3.0)
+    path = str(tmp_path / "state.qhgb")
+    g.dump_state(path)
+    r = GpuPopulation.from_params(par, nbr, alt2, state16=st, env=env)  # the environment as of the dump
+    r.restore_state(path)
+    assert r.num_agents() == g.num_agents() == o.num_agents()
+    for k in range(6, 14):
+        g.step(float(k)); r.step(float(k)); o.step(float(k))
+        assert_same_population(r, o, k)
+        assert_same_population(g, o, k)
+        assert r.step_stats().births == g.step_stats().births
+    assert np.array_equal(r.weights(), g.weights())
+    if row:
+        ra, oa = r.agents(), o.agents()
+        rg, rnb = r.genomes(row)
+        og, onb = o.genomes(row)
+        ir, io = np.argsort(ra["id"]), np.argsort(oa["id"])
+        assert np.array_equal(rg[ir], og[io]) and np.array_equal(rnb[ir], onb[io])
+    with pytest.raises(Exception):
+        g.restore_state(path)  # only into an empty, configured population
+
+
 def test_reference_step_loop_drives_cuda_path_through_plugin_class():
     """The drop-in boundary exercised from the reference's side: the UNMODIFIED reference sources (PopLooper::doStep,
     core/PopLooper.cpp:190-232, SPopulation, ParamProvider2, the tutorial population) with the plugin class of
