@@ -117,6 +117,13 @@ def build_world(subdiv, n_agents, seed=1):
     return nbr, alt, pop, tut_environ_alt(K), K
 
 
+def workload_name(args):
+    if args.subdiv == 255:
+        return (f"C4: tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove+SingleEvaluator[Alt], Fertility, "
+                f"RandomPair, Verhulst), {args.agents} agents on the subdivision-256 icosahedral grid")
+    return f"tut_EnvironAltPop action set, {args.agents} agents on eq:{args.subdiv}"
+
+
 def run_reference(args):
     """The reference's own OpenMP step loop (oracle/_ref) on the host cores, bounded sample of the workload."""
     from oracle import refsim
@@ -141,7 +148,7 @@ def run_reference(args):
     line = {"metric": "agent-steps/sec", "value": val, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.ref_steps,
             "warmup": args.ref_warmup, "ms_per_step": 1e3 * sec / args.ref_steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"C4 sample: tut_EnvironAltPop action set, {n} agents on eq:{sub} ({ncell} cells)"},
+            "config": {"workload": workload_name(args), "sample": f"bounded sample of it: {n} agents on eq:{sub} ({ncell} cells), same density and K"},
             "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -283,13 +290,12 @@ def run_ours(args, rank, world):
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4: tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove+SingleEvaluator[Alt], Fertility, "
-                                   f"RandomPair, Verhulst), {args.agents} agents on the subdivision-256 icosahedral grid"
-                                   if args.subdiv == 255 else f"tut_EnvironAltPop action set, {args.agents} agents on eq:{args.subdiv}",
+            "config": {"workload": workload_name(args),
                        "cells": ncell, "agents_start": args.agents, "agents_end": n_final, "verhulst_K": K,
                        "l2": "agent state per step (>2 GB at 1e8 agents) exceeds the 126 MB L2; no explicit flush",
                        "upload_s": round(upload_s, 2), "download_s": round(download_s, 2), "setup_s": round(t0 - t_setup, 2),
-                       "parallelism": f"cell-range shards x{world}, NCCL migration" if world > 1 else "single GPU",
+                       "parallelism": (f"cell-range shards x{world}, migration over " + ("peer memory (NVLink stores from the scatter kernel)"
+                                       if os.environ.get("QHG_P2P", "1") != "0" else "NCCL send/recv")) if world > 1 else "single GPU",
                        "migrations_per_step": migrated / args.steps},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * int(begin[rank + 1] - begin[rank]) + 48,
