@@ -136,8 +136,25 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, CELL_BATCH);
     cBase = __shfl_sync(FULL, cBase, 0);
     if (cBase >= cHi) break;
-    for (int c = cBase; c < min(cBase + CELL_BATCH, cHi); c++) {
-        const int s = cellStart[c], n = cellStart[c + 1] - s;
+    // everything per cell of the batch is fetched at once, one lane per item (lane = 8 * cell + k for the rows): one
+    // memory round trip per batch instead of two dependent ones per cell
+    static_assert(CELL_BATCH * 8 <= 32 && WSTRIDE <= 8 && MAXN <= 8, "one lane per (cell of the batch, row entry)");
+    const int nB = min(CELL_BATCH, cHi - cBase);
+    const int bc = lane >> 3, bk = lane & 7;
+    int csL = 0, nnL = 0, nbL = -1;
+    double wL = 0.0, bL = 0.0, dL = 0.0;
+    if (lane <= nB) csL = cellStart[cBase + lane];
+    if (lane < nB) {
+        nnL = E.nNbr[cBase + lane];
+        if (I.hasVerhulst) { bL = E.B[cBase + lane]; dL = E.D[cBase + lane]; }
+    }
+    if (bc < nB) {
+        if (bk < WSTRIDE) wL = E.W[(size_t)(cBase + bc) * WSTRIDE + bk];
+        if (bk < MAXN) nbL = E.nbr[(size_t)(cBase + bc) * MAXN + bk];
+    }
+    for (int ci = 0; ci < nB; ci++) {
+        const int c = cBase + ci;
+        const int s = __shfl_sync(FULL, csL, ci), n = __shfl_sync(FULL, csL, ci + 1) - s;
         if (n == 0) continue;
         if (n > WCAP) {
             if (lane == 0) atomicExch(&st->oversize, 1);
@@ -146,16 +163,20 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         // the cell's bytes sit at dec[gOff + j]: shared-memory word k then is the aligned global word of dec[] it is stored to
         const int gOff = s & 3;
         uint8_t *const sdec = S.dec + gOff;
-        if (lane < 8) {
-            S.outC[lane] = 0;
-            S.row[lane] = (lane < WSTRIDE) ? E.W[(size_t)c * WSTRIDE + lane] : 0.0;
-            S.nbrC[lane] = (lane < MAXN) ? E.nbr[(size_t)c * MAXN + lane] : -1;
+        {
+            const double rv = __shfl_sync(FULL, wL, ci * 8 + bk);
+            const int nv = __shfl_sync(FULL, nbL, ci * 8 + bk);
+            if (lane < 8) {
+                S.outC[lane] = 0;
+                S.row[lane] = rv;
+                S.nbrC[lane] = nv;
+            }
         }
         int nF = 0, nM = 0, nqa = 0, nqm = 0;
         bool tooMany = false;
-        const int nreal = E.nNbr[c];
+        const int nreal = __shfl_sync(FULL, nnL, ci);
         const double *row = S.row;
-        const double bC = I.hasVerhulst ? E.B[c] : 0.0, dC = I.hasVerhulst ? E.D[c] : 0.0;
+        const double bC = __shfl_sync(FULL, bL, ci), dC = __shfl_sync(FULL, dL, ci);
         // the probability tests of LinearBirth / LinearDeath as exact integer thresholds on the 32-bit draws
         const unsigned long long tBirth = prob_threshold(bC), tBirthNeg = prob_threshold(-bC), tDeath = prob_threshold(dC);
         auto flush_atan = [&]() {  // ATanDeath::execute, actions/ATanDeath.cpp:75-83, for the queued agents
