@@ -183,7 +183,8 @@ int  qhgb_comm_get_traffic(qhgb_pop *p, int64_t *sent, int64_t *received);
  * to the owning GPU by remote atomics, migrant records by direct NVLink stores from the scatter kernel, ordered by
  * two device-side cross-GPU barriers.
  *   qhgb_comm_p2p_handle   after qhgb_comm_init: writes 128 bytes (two cudaIpcMemHandle_t)
- *   qhgb_comm_p2p_connect  all_handles = nranks x 128 bytes in rank order */
+ *   qhgb_comm_p2p_connect  all_handles = nranks x 128 bytes in rank order; NULL switches back to the NCCL exchange
+ *                          (every rank must use the same exchange) */
 int  qhgb_comm_p2p_handle(qhgb_pop *p, void *out, int nbytes);
 int  qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles);
 

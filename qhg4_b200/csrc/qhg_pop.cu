@@ -1793,7 +1793,11 @@ int qhgb_comm_p2p_handle(qhgb_pop *p, void *out, int nbytes) {
 }
 
 int qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles) {
-    if (!p || !all_handles) return fail("qhgb_comm_p2p_connect: NULL argument");
+    if (!p) return fail("qhgb_comm_p2p_connect: NULL population");
+    if (!all_handles) {  // back to the NCCL exchange (e.g. another rank could not map the peers)
+        p->p2p = false;
+        return 0;
+    }
     if (!p->xchg) return fail("qhgb_comm_p2p_connect: call qhgb_comm_p2p_handle first");
     CK(cudaSetDevice(p->device));
     PeerTable T{};

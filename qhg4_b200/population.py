@@ -213,8 +213,9 @@ class GpuPopulation:
         check(self.L.qhgb_comm_p2p_handle(self.h, buf, 128), "qhgb_comm_p2p_handle")
         return buf.raw
 
-    def comm_p2p_connect(self, all_handles: bytes):
-        buf = C.create_string_buffer(all_handles, len(all_handles))
+    def comm_p2p_connect(self, all_handles):
+        """all_handles: the 128 bytes of every rank in rank order; None switches back to the NCCL exchange"""
+        buf = None if all_handles is None else C.create_string_buffer(all_handles, len(all_handles))
         check(self.L.qhgb_comm_p2p_connect(self.h, buf), "qhgb_comm_p2p_connect")
 
     def comm_traffic(self):

@@ -7,6 +7,7 @@ NCCL id through the C ABI, `torch.distributed` (any backend; gloo is enough) onl
 from __future__ import annotations
 
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -54,7 +55,25 @@ def connect(pop, begin, rank: int, nranks: int, p2p: bool | None = None):
     if p2p is None:
         p2p = os.environ.get("QHG_P2P", "1") != "0"
     if p2p and nranks > 1:
-        mine = torch.tensor(list(pop.comm_p2p_handle()), dtype=torch.uint8)
+        # every rank must end up with the same exchange: if one cannot export or map the buffers (no peer access, IPC
+        # not permitted in the container), all of them keep the NCCL calls
+        ok = 1
+        try:
+            mine = torch.tensor(list(pop.comm_p2p_handle()), dtype=torch.uint8)
+        except Exception as e:  # noqa: BLE001
+            print(f"[qhg4_b200] rank {rank}: no peer-memory exchange ({e}); using NCCL", file=sys.stderr)
+            mine, ok = torch.zeros(128, dtype=torch.uint8), 0
         table = [torch.zeros_like(mine) for _ in range(nranks)]
         dist.all_gather(table, mine)
-        pop.comm_p2p_connect(b"".join(bytes(x.tolist()) for x in table))
+        flag = torch.tensor([ok])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            try:
+                pop.comm_p2p_connect(b"".join(bytes(x.tolist()) for x in table))
+            except Exception as e:  # noqa: BLE001
+                print(f"[qhg4_b200] rank {rank}: could not map the peers' buffers ({e}); using NCCL", file=sys.stderr)
+                ok = 0
+        flag = torch.tensor([ok])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            pop.comm_p2p_connect(None)
