@@ -42,6 +42,8 @@
 #include "tut_SexualPop.h"
 #include "tut_MovePop.h"
 #include "tut_OldAgeDiePop.h"
+#include "Navigation.h"
+#include "Navigate.cpp"  // the reference's action template, instantiated below for the tutorial agent
 #ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
 #include <cstdlib>
 #include <vector>
@@ -135,6 +137,20 @@ struct PopAccessT : PopAccess {
         scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge;
     }
 };
+// Probe class for pinning Navigate (actions/Navigate.cpp): the reference ships it only inside the large OoA*
+// populations (Genetics, QDF sequence I/O).  Here the reference's own Navigate<T> is added to the reference's own
+// tut_EnvironAltPop; nothing of the action is restated.
+class NavProbePop : public tut_EnvironAltPop {
+public:
+    NavProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        m_pNav = new Navigate<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL);
+        m_prio.addAction(m_pNav);
+    }
+    virtual ~NavProbePop() { delete m_pNav; }
+    Navigate<tut_EnvironAltAgent> *m_pNav;
+};
+
 struct RefSim {
     int nCells = 0;
     int nThreads = 1;
@@ -254,9 +270,12 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
     s->cg->setVegetation(s->veg);
     for (int c = 0; c < nCells; c++) { s->cli->m_adAnnualMeanTemp[c] = 0; s->cli->m_adAnnualRainfall[c] = 0; s->geo->m_adWater[c] = 0; }
 
+    s->cg->setNavigation(new Navigation(s->cg));  // filled by qref_set_navigation; Navigate keeps the pointer (actions/Navigate.cpp:40)
     const int ls = layerSize > 0 ? layerSize : 65536;
     if (std::string(class_name) == "tut_EnvironAltPop") {
         s->pa = new PopAccessT<tut_EnvironAltPop, tut_EnvironAltAgent>(new tut_EnvironAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironAltNavPop") {
+        s->pa = new PopAccessT<NavProbePop, tut_EnvironAltAgent>(new NavProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_SexualPop") {
         s->pa = new PopAccessT<tut_SexualPop, tut_SexualAgent>(new tut_SexualPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_MovePop") {
@@ -310,6 +329,24 @@ int qref_add_agents(void *h, long n, const int *cell, const int64_t *id, const f
         }
         done += chunk;
     }
+    return 0;
+}
+
+// the Navigation group (core/Navigation.h:22-39) as io/NavGroupReader would fill it: ports with their destination cells
+// and distances (CSR), manual bridges; call before qref_start
+int qref_set_navigation(void *h, int nPorts, const int *portCell, const int *portPtr, const int *destCell, const double *dist,
+                        int nBridges, const int *bridges) {
+    RefSim *s = (RefSim *)h;
+    distancemap dm;
+    for (int i = 0; i < nPorts; i++) {
+        distlist dl;
+        for (int k = portPtr[i]; k < portPtr[i + 1]; k++) dl[destCell[k]] = dist[k];
+        dm[portCell[i]] = dl;
+    }
+    bridgelist bl;
+    for (int b = 0; b < nBridges; b++) bl.push_back(bridgedef(bridges[2 * b], bridges[2 * b + 1]));
+    s->cg->m_pNavigation->setData(dm, 1.0);
+    s->cg->m_pNavigation->setBridges(bl);
     return 0;
 }
 

@@ -37,6 +37,7 @@ def lib(adapter: bool = False):
         L.qref_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.qref_add_agents.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 7
+        L.qref_set_navigation.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.qref_start.argtypes = [C.c_void_p]
         L.qref_step.argtypes = [C.c_void_p, C.c_float]
         L.qref_run.restype = C.c_double
@@ -113,6 +114,12 @@ class RefSim:
         v = np.ascontiguousarray(v, np.float64)
         assert len(v) == self.ncells
         assert self.L.qref_set_env(self.h, name.encode(), _p(v)) == 0, name
+
+    def set_navigation(self, port_cell, port_ptr, dest_cell, dist, bridges=()):
+        pc, pp = np.ascontiguousarray(port_cell, np.int32), np.ascontiguousarray(port_ptr, np.int32)
+        dc, dd = np.ascontiguousarray(dest_cell, np.int32), np.ascontiguousarray(dist, np.float64)
+        br = np.ascontiguousarray(np.asarray(bridges, np.int32).reshape(-1, 2))
+        assert self.L.qref_set_navigation(self.h, len(pc), _p(pc), _p(pp), _p(dc), _p(dd), len(br), _p(br) if len(br) else None) == 0
 
     def event(self, event_id, t=0.0, flush=True):
         return self.L.qref_event(self.h, int(event_id), float(t), int(flush))

@@ -67,6 +67,53 @@ def test_small_tutorial_populations_equal_reference(which):
     r.close()
 
 
+def test_navigate_equals_reference():
+    """Navigate (actions/Navigate.cpp:94-250) pinned against the reference's own action: the reference's Navigate<T> is
+    added to the reference's tut_EnvironAltPop (NavProbePop in oracle/ref_driver.cpp; the shipped populations that carry
+    Navigate also need Genetics and QDF sequence I/O), the oracle runs the same action list.  Sea crossings with
+    distance-dependent probabilities, the search bound `iNumDests = map key` (port cells with a small index), manual
+    bridges, a GEO event that drowns a bridge end and rebuilds the tables on the flush -- slot for slot."""
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    rng = np.random.default_rng(3)
+    land = np.flatnonzero(alt > 0)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    occupied = np.unique(pop["cell"])
+    ports = np.concatenate([occupied[:3], rng.choice(occupied[occupied > 8], 50, replace=False)]).astype(np.int32)  # incl. tiny indices
+    ptr = np.arange(0, 4 * len(ports) + 1, 4, dtype=np.int32)
+    dests = np.concatenate([rng.choice(land, 4, replace=False) for _ in ports]).astype(np.int32)
+    dist = rng.uniform(100, 700, len(dests))
+    bridges = rng.choice(occupied, (6, 2), replace=False).astype(np.int32)
+    par = tut_environ_alt(20.0)
+    par.class_name = "tut_EnvironAltNavPop"
+    par.modules["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1",
+                               "Navigate_min_dens": "0.0", "Navigate_bridge_prob": "0.3"}
+    par.prios["Navigate"] = 8
+    st = seed_state(9)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
+    for q in (r, o):
+        q.set_navigation(ports, ptr, dests, dist, bridges)
+        q.add_agents(pop)
+    r.start(); o.start()
+    moves_seen = 0
+    for k in range(12):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+        moves_seen += o.step_stats()[2]
+        if k == 5:  # sea level rises: the drowned die, bridges with an end under water close (rebuilt on the flush)
+            alt2 = alt - 150.0
+            r.geo_event(alt2, None, 6.0)
+            o.set_env("Altitude", alt2); o.update_event(2, 6.0); o.flush_events(6.0)
+    far = np.setdiff1d(dests, np.concatenate([occupied, nbr[occupied].ravel()]))
+    assert moves_seen > 0 and (far.size == 0 or o.counts()[far].sum() > 0)  # somebody did cross
+    r.close()
+
+
 def test_geo_event_equals_reference():
     nbr, xyz = make_ico_grid(7)
     alt = synthetic_altitude(xyz, seed=5)
