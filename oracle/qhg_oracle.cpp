@@ -974,11 +974,11 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
     } else if (p->popClass == "tut_EnvironAltNavPop") {
-        // probe class (no such class ships): tut_EnvironAltPop with a Navigate action added, the way NavProbePop in
+        // probe class (no such class ships): tut_EnvironAltPop with Navigate and OldAgeDeath added, the way NavProbePop in
         // oracle/ref_driver.cpp adds the reference's Navigate<T> to the reference's tut_EnvironAltPop -- pins Navigate
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
-                      {"Navigate", A_NAVIGATE}};
+                      {"Navigate", A_NAVIGATE}, {"OldAgeDeath", A_OLDAGEDEATH}};
     } else if (p->popClass == "tut_SexualPop") {  // populations/tut_SexualPop.cpp:24-44
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Fertility", A_FERTILITY},
                       {"Verhulst", A_VERHULST}, {"RandomPair", A_RANDOMPAIR}};

@@ -43,7 +43,8 @@
 #include "tut_MovePop.h"
 #include "tut_OldAgeDiePop.h"
 #include "Navigation.h"
-#include "Navigate.cpp"  // the reference's action template, instantiated below for the tutorial agent
+#include "Navigate.cpp"  // the reference's action templates, instantiated below for the tutorial agent
+#include "OldAgeDeath.cpp"
 #ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
 #include <cstdlib>
 #include <vector>
@@ -137,7 +138,7 @@ struct PopAccessT : PopAccess {
         scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge;
     }
 };
-// Probe class for pinning Navigate (actions/Navigate.cpp): the reference ships it only inside the large OoA*
+// Probe class for pinning Navigate and OldAgeDeath (actions/Navigate.cpp, OldAgeDeath.cpp): the reference ships them only inside the large OoA*
 // populations (Genetics, QDF sequence I/O).  Here the reference's own Navigate<T> is added to the reference's own
 // tut_EnvironAltPop; nothing of the action is restated.
 class NavProbePop : public tut_EnvironAltPop {
@@ -146,9 +147,12 @@ public:
         : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
         m_pNav = new Navigate<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL);
         m_prio.addAction(m_pNav);
+        m_pOAD = new OldAgeDeath<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL);  // the other action only the OoA* populations carry
+        m_prio.addAction(m_pOAD);
     }
-    virtual ~NavProbePop() { delete m_pNav; }
+    virtual ~NavProbePop() { delete m_pNav; delete m_pOAD; }
     Navigate<tut_EnvironAltAgent> *m_pNav;
+    OldAgeDeath<tut_EnvironAltAgent> *m_pOAD;
 };
 
 struct RefSim {

@@ -89,6 +89,7 @@ def test_navigate_equals_reference():
     par.modules["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1",
                                "Navigate_min_dens": "0.0", "Navigate_bridge_prob": "0.3"}
     par.prios["Navigate"] = 8
+    par.modules["OldAgeDeath"] = {"OAD_max_age": "60.0", "OAD_uncertainty": "0.1"}  # registered in the probe class, no <prio>: never runs
     st = seed_state(9)
     r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
     o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
@@ -111,6 +112,36 @@ def test_navigate_equals_reference():
             o.set_env("Altitude", alt2); o.update_event(2, 6.0); o.flush_events(6.0)
     far = np.setdiff1d(dests, np.concatenate([occupied, nbr[occupied].ravel()]))
     assert moves_seen > 0 and (far.size == 0 or o.counts()[far].sum() > 0)  # somebody did cross
+    r.close()
+
+
+def test_old_age_death_equals_reference():
+    """OldAgeDeath (actions/OldAgeDeath.cpp:48-67, `wrandr` draw) pinned the same way: the probe population runs it
+    INSTEAD of ATanDeath (an action without a <prio> entry never runs, core/Prioritizer.cpp:19-30)."""
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=2)
+    pop = synthetic_population(9000, alt, seed=3, fertile=True, max_age=75.0)
+    par = tut_environ_alt(20.0)
+    par.class_name = "tut_EnvironAltNavPop"
+    del par.prios["ATanDeath"]
+    par.modules["OldAgeDeath"] = {"OAD_max_age": "60.0", "OAD_uncertainty": "0.1"}
+    par.prios["OldAgeDeath"] = 2
+    par.modules["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1",
+                               "Navigate_min_dens": "0.0", "Navigate_bridge_prob": "0.3"}  # registered, no <prio>
+    st = seed_state(4)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
+    for q in (r, o):
+        q.add_agents(pop)
+    r.start(); o.start()
+    deaths = 0
+    for k in range(10):
+        r.step(float(k)); o.step(float(k))
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        deaths += o.step_stats()[1]
+    assert deaths > 500 and ra["age"].max() < 67.0  # nobody outlives max_age + 1 + 0.1 * max_age
     r.close()
 
 
