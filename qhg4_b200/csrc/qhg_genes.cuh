@@ -46,8 +46,15 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
     const int nb = G.nBlocks, row = 2 * nb;
     const unsigned step = st->step;
     const unsigned FULL = 0xffffffffu;
-    for (int e = w; e < ctl->nBirths; e += nW) {
-        const BirthEntry be = births[e];
+    // software pipeline: the next birth's record and its parents' row handles are fetched while this one is worked on
+    const int nBirths = ctl->nBirths;
+    BirthEntry beN{};
+    int smN = 0, sfN = 0;
+    if (w < nBirths) { beN = births[w]; smN = oldSlot[beN.mother]; sfN = oldSlot[beN.father]; }
+    for (int e = w; e < nBirths; e += nW) {
+        const BirthEntry be = beN;
+        const int sm = smN, sf = sfN;
+        if (e + nW < nBirths) { beN = births[e + nW]; smN = oldSlot[beN.mother]; sfN = oldSlot[beN.father]; }
         int slot = 0;
         if (lane == 0) {  // a row for the baby
             int idx = atomicSub(&ctl->nFree, 1) - 1;
@@ -55,8 +62,8 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
             newSlot[be.babyPos] = slot;
         }
         slot = __shfl_sync(FULL, slot, 0);
-        const unsigned long long *gm = pool + (size_t)oldSlot[be.mother] * row;
-        const unsigned long long *gf = pool + (size_t)oldSlot[be.father] * row;
+        const unsigned long long *gm = pool + (size_t)sm * row;
+        const unsigned long long *gf = pool + (size_t)sf * row;
         unsigned long long *gb = pool + (size_t)slot * row;
         const uint4 g0 = agent_draws(be.cid, step, 4u, key);
         const int i1 = (int)(g0.x >> 31), i2 = (int)(g0.y >> 31);  // (int)(2 * wrandd())

@@ -828,7 +828,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key, q.mate.p,
                    q.genetic ? q.births.p : nullptr, q.gctl.p);
             if (q.genetic) {  // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
-                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 8, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
+                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
                        q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0);
                 LAUNCH(p, "k_free_genomes", k_free_genomes, ga, 256, q.dstats.p, q.gctl.p, q.dest.p, q.gslot[q.cur].p, q.gfree.p);
