@@ -307,7 +307,7 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
 };
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE};
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE};
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -343,6 +343,13 @@ struct qor_pop {
     double oadMaxAge = 0, oadUncertainty = 0;
     double moveProb = 0;
     double randMoveProb = 0;  // RandomMove_prob (actions/RandomMove.cpp)
+    // ConfinedMove (actions/ConfinedMove.cpp): centre (lon, lat in degrees) and radius (km) of the region agents may enter
+    double confX = 0, confY = 0, confR = 0;
+    std::vector<uint8_t> confAllowed;
+    // tut_ParthenoPop: no pairing action; LinearBirth tests m_iMateIndex >= 0 (actions/LinearBirth.cpp:139-142), which holds for
+    // every agent there: newborns get their own index (populations/tut_ParthenoPop.cpp:107-119), agents that were read in keep
+    // the zero of LayerBuf's fresh memory.  All newborns are female, whatever the gender draw said (:116)
+    bool selfMate = false;
     float fertMinAge = 0, fertMaxAge = 0, fertInterbirth = 0;
     double vB0 = -1024, vD0 = -1024, vTheta = -1024, vK = -1024;
     PolyLine altPref;
@@ -759,6 +766,7 @@ struct qor_pop {
         case A_NPPCAP:
         case A_GENETICS:
         case A_RANDOMPAIR:
+        case A_CONFINEDMOVE:
             break;  // execute() is empty for these (actions/Action.h:36 default)
         }
     }
@@ -815,6 +823,7 @@ struct qor_pop {
         b.lastBirth = 0.0f;
         b.mate = -3;
         b.numBabies = 0;
+        if (selfMate) { b.gender = 0; b.mate = slot; }  // populations/tut_ParthenoPop.cpp:107-119 (the life state keeps what the draw gave)
     }
 
     // Genetics::makeOffspring (actions/Genetics.cpp:285-337) under the counter-mode law: every draw is a word of
@@ -907,10 +916,29 @@ struct qor_pop {
             a.life &= ~LIFE_MOVING;
         }
     }
+    // actions/ConfinedMove.cpp:44-78 (preLoop): the cells within m_dR km of (m_dX, m_dY); the grid built by the driver has no
+    // type (GRID_TYPE_NONE), which takes the icosahedral branch: great-circle distance (utils/geomutils.cpp:311-326)
+    void confinedPreLoop() {
+        const std::vector<double> &lon = env["Longitude"], &lat = env["Latitude"];
+        confAllowed.assign(nCells, 0);
+        const double conv = 3.14159 / 180.0;  // the reference's constant (actions/ConfinedMove.cpp:66)
+        for (int i = 0; i < nCells; i++) {
+            const double lo1 = lon[i] * conv, la1 = lat[i] * conv, lo2 = confX * conv, la2 = confY * conv;
+            const double x1 = cos(lo1) * cos(la1), y1 = sin(lo1) * cos(la1), z1 = sin(la1);
+            const double x2 = cos(lo2) * cos(la2), y2 = sin(lo2) * cos(la2), z2 = sin(la2);
+            double pr = x1 * x2 + y1 * y2 + z1 * z2;
+            if (pr > 1) pr = 1; else if (pr < -1) pr = -1;
+            if (6371.3 * acos(pr) < confR) confAllowed[i] = 1;  // RADIUS_EARTH_KM, utils/qhg_consts.h:54-55
+        }
+    }
     int finalizeStep() {  // core/SPopulation.cpp:439-477
         for (const Action *a : ordered()) {
             if (a->enabled && a->kind == A_SINGLEEVAL) evalNeedUpdate = false;  // actions/SingleEvaluator.cpp:125-130
             if (a->enabled && a->kind == A_MULTIEVAL) for (auto &e : subs) e.needUpdate = false;  // actions/MultiEvaluator.cpp:189-195
+            // ConfinedMove::finalize (actions/ConfinedMove.cpp:86-101): every registered move into a cell outside the
+            // region is turned into a move to the cell it starts from (it stays in the list and is counted)
+            if (a->enabled && a->kind == A_CONFINEDMOVE)
+                for (size_t k = 0; k < moveList.size(); k += 3) if (!confAllowed[moveList[k + 2]]) moveList[k + 2] = moveList[k];
         }
         recycleDeadSpace();
         performMoves();
@@ -979,6 +1007,17 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"Navigate", A_NAVIGATE}, {"OldAgeDeath", A_OLDAGEDEATH}};
+    } else if (p->popClass == "tut_EnvironAltConfPop") {
+        // probe class: tut_EnvironAltPop with ConfinedMove added (ConfProbePop in oracle/ref_driver.cpp) -- pins ConfinedMove
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"ConfinedMove", A_CONFINEDMOVE}};
+    } else if (p->popClass == "tut_ParthenoPop") {  // populations/tut_ParthenoPop.cpp:22-45
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Verhulst", A_VERHULST},
+                      {"Fertility", A_FERTILITY}};
+        p->selfMate = true;
+    } else if (p->popClass == "tut_StaticPop") {  // populations/tut_StaticPop.cpp:16-21: no actions at all
+        p->actions = {};
     } else if (p->popClass == "tut_SexualPop") {  // populations/tut_SexualPop.cpp:24-44
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Fertility", A_FERTILITY},
                       {"Verhulst", A_VERHULST}, {"RandomPair", A_RANDOMPAIR}};
@@ -1048,6 +1087,9 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "OAD_uncertainty") p->oadUncertainty = v;
     else if (s == "WeightedMove_prob") p->moveProb = v;
     else if (s == "RandomMove_prob") p->randMoveProb = v;
+    else if (s == "ConfinedMove_x") p->confX = v;
+    else if (s == "ConfinedMove_y") p->confY = v;
+    else if (s == "ConfinedMove_r") p->confR = v;
     else if (s == "Fertility_min_age") p->fertMinAge = (float)v;
     else if (s == "Fertility_max_age") p->fertMaxAge = (float)v;
     else if (s == "Fertility_interbirth") p->fertInterbirth = (float)v;
@@ -1130,7 +1172,7 @@ int qor_add_agents(qor_pop *p, int64_t n, const int32_t *cell, const int64_t *id
         a.gender = gender[j];
         a.age = age ? age[j] : 0.0f;
         a.lastBirth = last_birth ? last_birth[j] : 0.0f;
-        a.mate = -3;
+        a.mate = p->selfMate ? 0 : -3;
         if (a.id > p->maxID) p->maxID = a.id;
     }
     return 0;
@@ -1147,6 +1189,7 @@ int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDe
     }
     { Action *nv = p->find("Navigate"); if (nv && nv->prio >= 0 && p->navRecalculate() != 0) return -1; }  // Navigate::preLoop
     if (p->find("NPPCapacity")) p->nppRecalculate();  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
+    { Action *cm = p->find("ConfinedMove"); if (cm && cm->prio >= 0) { if (!p->env.count("Longitude") || !p->env.count("Latitude")) return -1; p->confinedPreLoop(); } }
     return 0;
 }
 

@@ -42,9 +42,12 @@
 #include "tut_SexualPop.h"
 #include "tut_MovePop.h"
 #include "tut_OldAgeDiePop.h"
+#include "tut_ParthenoPop.h"
+#include "tut_StaticPop.h"
 #include "Navigation.h"
 #include "Navigate.cpp"  // the reference's action templates, instantiated below for the tutorial agent
 #include "OldAgeDeath.cpp"
+#include "ConfinedMove.cpp"
 #ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
 #include <cstdlib>
 #include <vector>
@@ -100,13 +103,19 @@ struct PopAccessT : PopAccess {
     void put(int slot, const AgentRec &r, gridtype cellID) override {
         AgentT &a = pop->m_aAgents[slot];
         a.m_iLifeState = r.life; a.m_iCellIndex = r.cell; a.m_ulID = r.id; a.m_ulCellID = cellID;
-        a.m_fBirthTime = r.birth; a.m_iGender = r.gender; a.m_fAge = r.age;
+        a.m_fBirthTime = r.birth; a.m_iGender = r.gender;
+        if constexpr (requires { a.m_fAge; }) a.m_fAge = r.age;  // tut_StaticPop keeps the bare Agent
         if constexpr (requires { a.m_fLastBirth; }) { a.m_fLastBirth = r.lastBirth; a.m_iMateIndex = -3; }  // the smaller tutorial agents have no such fields
+        // tut_ParthenoPop never writes the mate index of an agent that was read in (populations/tut_ParthenoPop.cpp:76-89);
+        // LinearBirth tests it (actions/LinearBirth.cpp:139,142).  In the reference it is whatever LayerBuf's new T[] holds:
+        // zero in fresh pages, so the founders do give birth (the tutorial relies on it).  The driver writes that zero.
+        if constexpr (std::is_same_v<AgentT, tut_ParthenoAgent>) a.m_iMateIndex = 0;
     }
     bool get(int slot, AgentRec &r) override {
         AgentT &a = pop->m_aAgents[slot];
         if (a.m_iLifeState == LIFE_STATE_DEAD) return false;
-        r.cell = a.m_iCellIndex; r.id = a.m_ulID; r.birth = a.m_fBirthTime; r.gender = a.m_iGender; r.age = a.m_fAge;
+        r.cell = a.m_iCellIndex; r.id = a.m_ulID; r.birth = a.m_fBirthTime; r.gender = a.m_iGender; r.age = 0;
+        if constexpr (requires { a.m_fAge; }) r.age = a.m_fAge;
         r.lastBirth = 0; r.mate = -3;
         if constexpr (requires { a.m_fLastBirth; }) { r.lastBirth = a.m_fLastBirth; r.mate = a.m_iMateIndex; }
         r.life = a.m_iLifeState; r.slot = slot;
@@ -135,7 +144,8 @@ struct PopAccessT : PopAccess {
         }
     }
     void atanParams(double &scale, double &slope, double &maxAge) override {
-        scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge;
+        if constexpr (requires { pop->m_pAD; }) { scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge; }
+        else { scale = slope = maxAge = 0; }
     }
 };
 // Probe class for pinning Navigate and OldAgeDeath (actions/Navigate.cpp, OldAgeDeath.cpp): the reference ships them only inside the large OoA*
@@ -153,6 +163,19 @@ public:
     virtual ~NavProbePop() { delete m_pNav; delete m_pOAD; }
     Navigate<tut_EnvironAltAgent> *m_pNav;
     OldAgeDeath<tut_EnvironAltAgent> *m_pOAD;
+};
+
+// Probe class for pinning ConfinedMove (actions/ConfinedMove.cpp:44-101; carried by 21 of the shipped OoA* populations,
+// all of which also need Genetics / QDF sequence I/O): the reference's own ConfinedMove<T> added to tut_EnvironAltPop.
+class ConfProbePop : public tut_EnvironAltPop {
+public:
+    ConfProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        m_pCM = new ConfinedMove<tut_EnvironAltAgent>(this, m_pCG, "");
+        m_prio.addAction(m_pCM);
+    }
+    virtual ~ConfProbePop() { delete m_pCM; }
+    ConfinedMove<tut_EnvironAltAgent> *m_pCM;
 };
 
 struct RefSim {
@@ -286,6 +309,12 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_MovePop, tut_MoveAgent>(new tut_MovePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_OldAgeDiePop") {
         s->pa = new PopAccessT<tut_OldAgeDiePop, tut_OldAgeDieAgent>(new tut_OldAgeDiePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironAltConfPop") {
+        s->pa = new PopAccessT<ConfProbePop, tut_EnvironAltAgent>(new ConfProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_ParthenoPop") {
+        s->pa = new PopAccessT<tut_ParthenoPop, tut_ParthenoAgent>(new tut_ParthenoPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_StaticPop") {
+        s->pa = new PopAccessT<tut_StaticPop, Agent>(new tut_StaticPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
         s->pa = new PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
 #ifdef QHG_WITH_GPU_ADAPTER

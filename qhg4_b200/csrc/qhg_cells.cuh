@@ -128,6 +128,8 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     const RngKey key = P.key;
     const RoundKeys &RK = P.rk;
     const bool storeAge = P.storeAge != 0;
+    const bool selfMate = !SPEC && P.selfMate != 0;                    // tut_ParthenoPop: every female counts as mated
+    const bool confine = !SPEC && P.confine != 0 && E.allowed != nullptr;  // ConfinedMove filters the chosen destinations
 
     // cells are handed out dynamically in batches of CELL_BATCH consecutive cells (sea cells are empty, land cells are
     // not: a static split leaves a long tail)
@@ -173,6 +175,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             }
         }
         int nF = 0, nM = 0, nqa = 0, nqm = 0;
+        int confL = 0;  // moves of this lane that ConfinedMove turned back (they stay in the move list: counted, core/SPopulation.cpp:1067)
         bool tooMany = false;
         const int nreal = __shfl_sync(FULL, nnL, ci);
         const double *row = S.row;
@@ -195,7 +198,10 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 int pick = -1;
                 if (!SPEC && I.randomMove) {  // RandomMove: uniform over "stay" and the neighbours, no ice test
                     pick = (int)__dmul_rn(u2d(u), (double)(nreal + 1));
-                    if (pick > 0 && S.nbrC[pick - 1] >= 0) sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    if (pick > 0 && S.nbrC[pick - 1] >= 0) {
+                        if (confine && !E.allowed[S.nbrC[pick - 1]]) { if (!(I.moveAfterAtan && (sdec[j] & T_ATANDIES))) confL++; }
+                        else sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    }
                     continue;
                 }
                 const double wmax = row[nreal];
@@ -209,7 +215,12 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 }
                 if (pick > 0) {
                     const int dst = S.nbrC[pick - 1];
-                    if (dst >= 0 && !(E.ice && E.ice[dst])) sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) {
+                        // ConfinedMove (actions/ConfinedMove.cpp:86-101): the move is registered and counted, but leads back to
+                        // the cell it starts from -- unless ATanDeath (flushed before, see below) removed the agent before it moved
+                        if (confine && !E.allowed[dst]) { if (!(I.moveAfterAtan && (sdec[j] & T_ATANDIES))) confL++; }
+                        else sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    }
                 }
             }
             nqm = 0;
@@ -314,7 +325,8 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                             if (bC > 0) {
                                 // a birth needs a mate (LinearBirth.cpp:142); whether this fertile female got one is settled
                                 // once the whole cell has been seen: she is a candidate until then
-                                if ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE && (unsigned long long)r0[u].z < tBirth) cand = true;
+                                const bool mayBear = selfMate ? !(f0[u] & F_MALE) : ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE);
+                                if (mayBear && (unsigned long long)r0[u].z < tBirth) cand = true;
                             } else if (bC < 0) {
                                 if ((unsigned long long)r0[u].z < tBirthNeg) alive = false;
                             }
@@ -336,7 +348,8 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             __syncwarp();
             // one call site each (code size): flush when a queue could overflow in the next round, and at the end of the cell
             const bool last = j0 + 32 * DU >= n;
-            if (nqa > QCAP - 32 * DU || (last && nqa > 0)) flush_atan();
+            // with ConfinedMove the move flush reads the ATanDeath verdicts of its agents: the death queue goes first
+            if (nqa > QCAP - 32 * DU || (last && nqa > 0) || (confine && nqa > 0 && (nqm > QCAP - 32 * DU || (last && nqm > 0)))) flush_atan();
             if (nqm > QCAP - 32 * DU || (last && nqm > 0)) flush_move();
         }
 
@@ -344,8 +357,8 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         // fertile females and fertile males are ranked by (random key, id); equal ranks mate.  Only "does this female
         // have a mate" matters to the actions: with nF <= nM every fertile female has one, otherwise the nM females
         // with the smallest keys -- and only the birth candidates need to know.
-        bool mates = doPair && nF > 0 && nM > 0;
-        if (mates && nF > nM) {
+        bool mates = selfMate || (doPair && nF > 0 && nM > 0);
+        if (mates && !selfMate && nF > nM) {
             if (tooMany) {
                 if (lane == 0) atomicExch(&st->oversize, 1);
                 continue;
@@ -434,7 +447,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         }
         const int stayC = __reduce_add_sync(FULL, stayL), bornC = __reduce_add_sync(FULL, bornL);
         const int outC = __reduce_add_sync(FULL, outL);
-        nMove += __reduce_add_sync(FULL, moveL);
+        nMove += __reduce_add_sync(FULL, moveL + confL);
         nDead += n - stayC - outC;
         nBorn += bornC;
         __syncwarp();
@@ -738,7 +751,7 @@ __global__ void __launch_bounds__(CW * 32, QHG_SCATTER_S_MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
-               const int *__restrict__ birthBase, float t, int storeAge, RngKey key, ShardArgs H) {
+               const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
     __shared__ WarpSmemS smem[CW];
     if (st->overflow || st->oversize) return;
@@ -906,7 +919,8 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     o.id[pos] = cid;
                     o.birth[pos] = t;
                     o.lastBirth[pos] = 0.0f;
-                    o.flags[pos] = (uint8_t)(gnd ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
+                    // females are born FERTILE, core/SPopulation.cpp:895-898; tut_ParthenoPop turns the drawn males into females
+                    o.flags[pos] = (uint8_t)(gnd ? (femaleOnly ? 0 : F_MALE) : F_FERTILE);
                     if (storeAge) o.age[pos] = 0.0f;
                 }
                 __syncwarp();

@@ -86,6 +86,12 @@ struct ActParams {
     float fertMinAge, fertMaxAge, fertInterbirth;
     RngKey key;
     RoundKeys rk;  // the ten Philox round keys of `key` (read straight from the constant bank by the fast path)
+    // tut_ParthenoPop: no pairing action, every female counts as mated (actions/LinearBirth.cpp:139-142 only tests
+    // m_iMateIndex >= 0; populations/tut_ParthenoPop.cpp:107-119 gives every newborn its own index) and newborns are female
+    int selfMate;
+    // ConfinedMove is active (actions/ConfinedMove.cpp:86-101): a move into a cell outside the region becomes a move to the
+    // cell it starts from (still counted)
+    int confine;
 };
 
 __host__ __device__ __forceinline__ int prog_op(const ActParams &P, int k) { return (int)((P.prog >> (4 * k)) & 15ull); }
@@ -332,6 +338,7 @@ struct CellEnv {
     const int2 *bridges;
     int nBridges;
     double bridgeProb;
+    const uint8_t *allowed;  // ConfinedMove::m_bAllowed (actions/ConfinedMove.cpp:44-78), NULL without the action
 };
 
 struct Decision {
@@ -471,6 +478,9 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
             break;
         }
     }
+    // ConfinedMove::finalize runs in finalizeStep over the whole move list, whatever the action's priority
+    // (core/SPopulation.cpp:445-455, actions/ConfinedMove.cpp:86-101): the last registered move decides where the agent ends up
+    if (P.confine && d.moving && !E.allowed[d.to]) { d.to = c; d.pick = 0; }
     return d;
 }
 
@@ -495,7 +505,7 @@ k_actions(DevStats *__restrict__ st, AgentArrays a, const int *__restrict__ mate
             bool needMate = false;
             for (int k = 0; k < P.nOps; k++) needMate |= (prog_op(P, k) == OP_VERHULST);
             const uint8_t f = a.flags[i];
-            const bool hasMate = needMate && !(f & F_MALE) && mate[i] >= 0;
+            const bool hasMate = needMate && !(f & F_MALE) && (P.selfMate || mate[i] >= 0);
             d = run_actions(P, E, step, a.id[i], a.birth[i], P.storeAge ? a.age[i] : 0.0f, c, f, hasMate, a.lastBirth + i);
             if (P.storeAge && d.alive) a.age[i] = d.age;  // moved with the agent by k_scatter
             nMove += d.nMoves;  // registered moves count even if the agent dies later in the step (core/SPopulation.cpp:1067)
@@ -628,7 +638,7 @@ __global__ void __launch_bounds__(256)
 k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const int *__restrict__ cellStart,
           const int *__restrict__ dest, const int *__restrict__ rank, const uint8_t *__restrict__ oflags,
           const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ arrive,
-          const int *__restrict__ birthBase, float t, int storeAge, RngKey key,
+          const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key,
           const int *__restrict__ mate, BirthEntry *__restrict__ births, GenomeCtl *__restrict__ gctl) {
     if (st->overflow) return;
     const int n = st->nAgents;
@@ -665,7 +675,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
             o.birth[pos] = t;
             o.lastBirth[pos] = 0.0f;
             o.cell[pos] = c;
-            o.flags[pos] = (uint8_t)(g ? F_MALE : F_FERTILE);  // females are born FERTILE, core/SPopulation.cpp:895-898
+            // females are born FERTILE, core/SPopulation.cpp:895-898; tut_ParthenoPop turns the drawn males into (non-fertile) females
+            o.flags[pos] = (uint8_t)(g ? (femaleOnly ? 0 : F_MALE) : F_FERTILE);
             if (storeAge) o.age[pos] = 0.0f;
             if (o.nbabies) o.nbabies[pos] = 0;
             if (births) record_birth(births, gctl, pos, i, mate[i], cid);  // the genome is made by k_make_offspring

@@ -96,7 +96,7 @@ int loadNccl() {
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -214,6 +214,11 @@ struct qhgb_pop {
     DevBuf<double> navCum;
     DevBuf<int2> navBridges;
     std::vector<double> hAlt;  // host copy of the altitude (bridges need both ends above sea level)
+    // ConfinedMove: the cells inside the region (ConfinedMove::m_bAllowed, actions/ConfinedMove.cpp:44-78), built at preLoop
+    DevBuf<uint8_t> allowed;
+    bool confReady = false;
+    std::vector<double> hLon, hLat;  // host copies of Longitude / Latitude for it
+    bool selfMate = false;           // tut_ParthenoPop: every female counts as mated, newborns are female
     float curTime = -1;
     std::vector<unsigned> levels;
     int64_t nAgents = 0, maxID = 0, stepsDone = 0;
@@ -474,6 +479,8 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     P.fertMinAge = (float)p->A("Fertility_min_age");
     P.fertMaxAge = (float)p->A("Fertility_max_age");
     P.fertInterbirth = (float)p->A("Fertility_interbirth");
+    P.selfMate = p->selfMate ? 1 : 0;
+    P.confine = (p->active(A_CONFINEDMOVE) && p->confReady) ? 1 : 0;  // its finalize() runs in every finalizeStep, whatever the levels
     return P;
 }
 
@@ -643,6 +650,30 @@ int recalcNavigation(qhgb_pop *p) {
     return 0;
 }
 
+// ConfinedMove::preLoop (actions/ConfinedMove.cpp:44-78), icosahedral branch (the boundary carries no grid type; the flat-grid
+// branch compares squared lon/lat differences instead): the cells within ConfinedMove_r km (great circle,
+// utils/geomutils.cpp:311-326, RADIUS_EARTH_KM utils/qhg_consts.h:54-55) of (ConfinedMove_x, ConfinedMove_y).  Done once, on the
+// host like the reference does it, with the same expressions -- one byte per cell goes to the device.
+int recalcConfined(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    if (q.hLon.size() != (size_t)q.nCells || q.hLat.size() != (size_t)q.nCells) return fail("[ConfinedMove] no geography (Longitude / Latitude)");
+    const double conv = 3.14159 / 180.0, X = q.A("ConfinedMove_x"), Y = q.A("ConfinedMove_y"), R = q.A("ConfinedMove_r");
+    std::vector<uint8_t> ok(q.nCells, 0);
+    for (int i = 0; i < q.nCells; i++) {
+        const double lo1 = q.hLon[i] * conv, la1 = q.hLat[i] * conv, lo2 = X * conv, la2 = Y * conv;
+        const double x1 = cos(lo1) * cos(la1), y1 = sin(lo1) * cos(la1), z1 = sin(la1);
+        const double x2 = cos(lo2) * cos(la2), y2 = sin(lo2) * cos(la2), z2 = sin(la2);
+        double pr = x1 * x2 + y1 * y2 + z1 * z2;
+        if (pr > 1) pr = 1; else if (pr < -1) pr = -1;
+        if (6371.3 * acos(pr) < R) ok[i] = 1;
+    }
+    CK(q.allowed.alloc(q.nCells));
+    CK(cudaMemcpyAsync(q.allowed.p, ok.data(), ok.size(), cudaMemcpyHostToDevice, q.stream));
+    CK(cudaStreamSynchronize(q.stream));
+    q.confReady = true;
+    return 0;
+}
+
 int computeWeights(qhgb_pop *p) {
     if (!p->haveAlt) return fail("SingleEvaluator[Alt]: no array with name [Altitude]");
     int g = p->gridFor(p->nCells);
@@ -660,6 +691,7 @@ CellEnv cellEnv(qhgb_pop *p) {
         E.navRow = p->navRow.p; E.navPtr = p->navPtr.p; E.navDest = p->navDest.p; E.navCum = p->navCum.p;
         E.bridges = p->navBridges.p; E.nBridges = p->nCurBridges; E.bridgeProb = p->A("Navigate_bridge_prob");
     }
+    E.allowed = p->confReady ? p->allowed.p : nullptr;
     return E;
 }
 
@@ -728,7 +760,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
             const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
-            if (P.prog == PROG_TUT5 && P.nOps == 5) {  // the tutorial action order: compile-time specialised kernel
+            if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             } else {
@@ -789,7 +821,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             }
             launchScan(p);
             LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
-                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, q.key, H);
+                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H);
             if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
                 LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p);
                 LAUNCH(p, "k_place_migrants", k_place_migrants_p2p, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
@@ -825,7 +857,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                    q.dest.p, q.rank.p, q.oflags.p);
             launchScan(p);
             LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
-                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, q.key, q.mate.p,
+                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, q.mate.p,
                    q.genetic ? q.births.p : nullptr, q.gctl.p);
             if (q.genetic) {  // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
                 LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
@@ -906,6 +938,18 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_EnvironAltConfPop") {
+        // tut_EnvironAltPop with ConfinedMove added (actions/ConfinedMove.cpp; carried by 21 of the shipped OoA* classes): the class
+        // the reference driver builds to pin the action (ConfProbePop, oracle/ref_driver.cpp)
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"ConfinedMove", A_CONFINEDMOVE}};
+    } else if (p->popClass == "tut_ParthenoPop") {  // populations/tut_ParthenoPop.cpp:22-45
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Verhulst", A_VERHULST},
+                      {"Fertility", A_FERTILITY}};
+        p->selfMate = true;
+    } else if (p->popClass == "tut_StaticPop") {  // populations/tut_StaticPop.cpp:16-21: no actions
+        p->actions = {};
     } else if (p->popClass == "tut_SexualPop") {  // populations/tut_SexualPop.cpp:24-44
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Fertility", A_FERTILITY},
                       {"Verhulst", A_VERHULST}, {"RandomPair", A_RANDOMPAIR}};
@@ -1002,6 +1046,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release();
+    p->allowed.release();
     p->navRow.release(); p->navPtr.release(); p->navDest.release(); p->navCum.release(); p->navBridges.release();
     for (int b = 0; b < 2; b++) {
         p->id[b].release(); p->birth[b].release(); p->lastBirth[b].release(); p->age[b].release();
@@ -1067,6 +1112,8 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
         p->haveIce = true;
         (void)any;
     } else {
+        if (s == "Longitude") p->hLon.assign(values, values + n);
+        if (s == "Latitude") p->hLat.assign(values, values + n);
         DevBuf<double> &d = p->envExtra[s];
         if (d.n != (size_t)n) CK(d.alloc(n));
         CK(cudaMemcpyAsync(d.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
@@ -1077,6 +1124,7 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
 
 static const char *const kNumericAttrs[] = {
     "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob", "RandomMove_prob",
+    "ConfinedMove_x", "ConfinedMove_y", "ConfinedMove_r",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
     "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
@@ -1269,6 +1317,7 @@ int qhgb_pre_loop(qhgb_pop *p) {
         if (recalcNavigation(p) != 0) return -1;
     }
     if (p->findKind(A_NPPCAP) && recalcCapacities(p) != 0) return -1;  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
+    if (p->findKind(A_CONFINEDMOVE) && p->findKind(A_CONFINEDMOVE)->prio >= 0 && recalcConfined(p) != 0) return -1;  // ConfinedMove::preLoop
     p->preLooped = true;
     p->evalFirst = true;
     return 0;

@@ -157,6 +157,37 @@ def tut_old_age_die() -> PopParams:
     )
 
 
+def tut_partheno(K: float = 20.0, move_prob: float = 0.01) -> PopParams:
+    """Parameter set of `tutorial_data/xmldat/tut_Partheno.xml` (values restated): females only, no pairing action --
+    every agent counts as mated (populations/tut_ParthenoPop.cpp:107-119), all newborns are female."""
+    return PopParams(
+        "tut_ParthenoPop",
+        modules={
+            "ATanDeath": {"ATanDeath_max_age": "60.0", "ATanDeath_range": "6.0", "ATanDeath_slope": "1.0"},
+            "RandomMove": {"RandomMove_prob": repr(float(move_prob))},
+            "Fertility": {"Fertility_interbirth": "2.0", "Fertility_max_age": "50.0", "Fertility_min_age": "15.0"},
+            "Verhulst": {"Verhulst_b0": "0.8", "Verhulst_d0": "0.001", "Verhulst_theta": "0.1", "Verhulst_K": repr(float(K))},
+        },
+        prios={"GetOld": 8, "ATanDeath": 10, "RandomMove": 7, "Fertility": 2, "Verhulst": 6},
+    )
+
+
+def tut_static() -> PopParams:
+    """`tutorial_data/xmldat/tut_Static.xml`: a population without actions (populations/tut_StaticPop.cpp:16-21)."""
+    return PopParams("tut_StaticPop")
+
+
+def tut_environ_alt_confined(K: float, x: float, y: float, r_km: float, prio: int = 9) -> PopParams:
+    """tut_EnvironAltPop's parameter set plus ConfinedMove (actions/ConfinedMove.cpp; attributes ConfinedMove_x/_y in degrees,
+    ConfinedMove_r in km).  No shipped population of this size carries it (21 of the OoA* classes do): the class name is the
+    probe class `tut_EnvironAltConfPop` of oracle/ref_driver.cpp, the oracle and the CUDA library."""
+    par = tut_environ_alt(K)
+    par.class_name = "tut_EnvironAltConfPop"
+    par.modules["ConfinedMove"] = {"ConfinedMove_x": repr(float(x)), "ConfinedMove_y": repr(float(y)), "ConfinedMove_r": repr(float(r_km))}
+    par.prios["ConfinedMove"] = prio
+    return par
+
+
 def ooa_nav_gen(genome_size: int = 4096, num_crossover: int = -1, mutation_rate: float = 1e-5) -> PopParams:
     """`OoANavGenPop` (populations/OoANavGenPop.cpp:33-97) without Navigate: the genetic population of config C3.
     The reference ships no parameter file for it; ecological values follow tut_EnvironCapAlt.xml, the Genetics values are

@@ -67,6 +67,93 @@ def test_small_tutorial_populations_equal_reference(which):
     r.close()
 
 
+def _lonlat(xyz):
+    return np.degrees(np.arctan2(xyz[:, 1], xyz[:, 0])), np.degrees(np.arcsin(np.clip(xyz[:, 2], -1, 1)))
+
+
+def test_partheno_and_static_populations_equal_reference():
+    """The rest of the tutorial ladder.  tut_ParthenoPop (populations/tut_ParthenoPop.cpp): no pairing action, every female
+    counts as mated (LinearBirth only tests m_iMateIndex >= 0, actions/LinearBirth.cpp:139-142; the founders' index is the
+    zero of fresh memory, which oracle/ref_driver.cpp writes explicitly), newborns are forced female AFTER the gender draw
+    decided their life state (:107-119).  tut_StaticPop: no actions, nothing may change."""
+    from qhg4_b200.params import tut_partheno, tut_static
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=4)
+    pop = synthetic_population(7000, alt, seed=8, fertile=True)
+    pop["gender"][:] = 0
+    st = seed_state(21)
+    r = refsim.RefSim(tut_partheno(25.0, 0.2), nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(tut_partheno(25.0, 0.2), nbr, alt, mode=port.MODE_WELL, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    births = 0
+    for k in range(15):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+        births += o.step_stats()[0]
+    assert births > 1000 and not oa["gender"].any() and set(np.unique(oa["life"])) >= {1, 5}
+    r.close()
+    r = refsim.RefSim(tut_static(), nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(tut_static(), nbr, alt, mode=port.MODE_WELL, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    c0 = o.counts().copy()
+    for k in range(3):
+        r.step(float(k)); o.step(float(k))
+    ra, oa = r.agents(), o.agents()
+    for f in ("cell", "id", "birth", "gender", "life", "slot"):  # the bare Agent has no age / last birth
+        assert np.array_equal(ra[f], oa[f]), f
+    assert np.array_equal(r.counts(), c0) and np.array_equal(o.counts(), c0) and np.array_equal(oa["id"], pop["id"])
+    r.close()
+
+
+def test_confined_move_equals_reference():
+    """ConfinedMove (actions/ConfinedMove.cpp:44-101) pinned against the reference's own action added to tut_EnvironAltPop
+    (ConfProbePop in oracle/ref_driver.cpp): moves that would leave the disc around (x, y) are turned into moves to the
+    cell they start from -- still counted -- so nobody ever leaves, slot for slot."""
+    from qhg4_b200.params import tut_environ_alt_confined
+    nbr, xyz = make_ico_grid(7)
+    alt = np.minimum(np.abs(synthetic_altitude(xyz, seed=5)) + 50.0, 1400.0)  # all land: the disc's border is the only barrier
+    lon, lat = _lonlat(xyz)
+    env = {"Longitude": lon, "Latitude": lat}
+    par = tut_environ_alt_confined(150.0, 20.0, 10.0, 5000.0)
+    par.modules["WeightedMove"]["WeightedMove_prob"] = "0.4"
+    st = seed_state(5)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st, env=env)
+    # the population starts inside the disc (the action only filters moves, actions/ConfinedMove.cpp:86-101)
+    xc = np.array([np.cos(np.radians(20)) * np.cos(np.radians(10)), np.sin(np.radians(20)) * np.cos(np.radians(10)), np.sin(np.radians(10))])
+    inside = np.flatnonzero(6371.3 * np.arccos(np.clip(xyz @ xc, -1, 1)) < 4000.0)
+    pop = synthetic_population(9000, alt, seed=6, fertile=True, cells=inside)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    moves = 0
+    for k in range(12):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+        moves += o.step_stats()[2]
+    occ = np.flatnonzero(o.counts())
+    d = 6371.3 * np.arccos(np.clip(xyz[occ] @ xc, -1, 1))
+    assert moves > 10000 and 4000.0 < d.max() < 5000.0  # they reached the border and stayed inside
+    # the same run without the action spills over the border
+    par2 = par.copy(); del par2.prios["ConfinedMove"]
+    o2 = port.OraclePop(par2, nbr, alt, mode=port.MODE_WELL, state16=st, env=env)
+    o2.add_agents(pop); o2.start()
+    for k in range(12):
+        o2.step(float(k))
+    occ2 = np.flatnonzero(o2.counts())
+    assert (6371.3 * np.arccos(np.clip(xyz[occ2] @ xc, -1, 1))).max() > 5000.0
+    r.close()
+
+
 def test_navigate_equals_reference():
     """Navigate (actions/Navigate.cpp:94-250) pinned against the reference's own action: the reference's Navigate<T> is
     added to the reference's tut_EnvironAltPop (NavProbePop in oracle/ref_driver.cpp; the shipped populations that carry

@@ -17,12 +17,12 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("cell", "id", "birth", "gender", "age", "last_birth", "life")
 
 
-def make_pair(params, nbr, alt, pop, ice=None, seed=0):
+def make_pair(params, nbr, alt, pop, ice=None, seed=0, env=None):
     from oracle import port
     from qhg4_b200.population import GpuPopulation
     st = seed_state(seed)
-    g = GpuPopulation.from_params(params, nbr, alt, ice=ice, state16=st)
-    o = port.OraclePop(params, nbr, alt, ice=ice, mode=port.MODE_COUNTER, state16=st)
+    g = GpuPopulation.from_params(params, nbr, alt, ice=ice, state16=st, env=env)
+    o = port.OraclePop(params, nbr, alt, ice=ice, mode=port.MODE_COUNTER, state16=st, env=env)
     g.add_agents(pop)
     o.add_agents(pop)
     g.pre_loop()
@@ -417,6 +417,63 @@ def test_small_tutorial_populations_bit_exact_vs_oracle(which, path):
     assert (moves > 0) == (which != "tut_OldAgeDiePop")
     if which == "tut_SexualPop":
         assert g.num_agents() > 0 and g.step_stats().births > 0
+
+
+def test_partheno_and_static_populations_bit_exact_vs_oracle(path):
+    """tut_ParthenoPop (populations/tut_ParthenoPop.cpp: no pairing, every female counts as mated, newborns forced female
+    after the gender draw set their life state) and tut_StaticPop (no actions) on both device paths against the oracle's
+    counter mode; the oracle's WELL mode equals the reference for both (tests/test_oracle_vs_ref.py)."""
+    from qhg4_b200.params import tut_partheno, tut_static
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=3)
+    pop = synthetic_population(30000, alt, seed=12, fertile=True)
+    pop["gender"][:] = 0
+    g, o = make_pair(tut_partheno(30.0, 0.2), nbr, alt, pop, seed=29)
+    births = 0
+    for k in range(14):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        births += s.births
+    a = g.agents()
+    assert births > 5000 and not a["gender"].any() and set(np.unique(a["life"])) >= {1, 5}
+    g, o = make_pair(tut_static(), nbr, alt, pop, seed=29)
+    c0 = g.counts().copy()
+    for k in range(3):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+    s = g.step_stats()
+    assert (s.births, s.deaths, s.moves) == (0, 0, 0) and np.array_equal(g.counts(), c0) and g.num_agents() == 30000
+
+
+@pytest.mark.parametrize("move_first", [False, True])
+def test_confined_move_bit_exact_vs_oracle(move_first, path):
+    """ConfinedMove (actions/ConfinedMove.cpp:44-101; its finalize() filters the whole move list in finalizeStep): moves out
+    of the disc lead back to the cell they start from and are still counted.  Both device paths, with WeightedMove after
+    ATanDeath (a death decided earlier voids the move, also a turned-back one) and before it; the oracle's WELL mode is
+    pinned against the reference's own action (tests/test_oracle_vs_ref.py::test_confined_move_equals_reference)."""
+    from qhg4_b200.params import tut_environ_alt_confined
+    nbr, xyz = make_ico_grid(15)
+    alt = np.minimum(np.abs(synthetic_altitude(xyz, seed=5)) + 50.0, 1400.0)
+    env = {"Longitude": np.degrees(np.arctan2(xyz[:, 1], xyz[:, 0])), "Latitude": np.degrees(np.arcsin(np.clip(xyz[:, 2], -1, 1)))}
+    par = tut_environ_alt_confined(400.0, 20.0, 10.0, 3000.0)
+    par.modules["WeightedMove"]["WeightedMove_prob"] = "0.4"
+    if move_first:
+        par.prios.update({"WeightedMove": 1, "GetOld": 2, "ATanDeath": 3})
+    xc = np.array([np.cos(np.radians(20)) * np.cos(np.radians(10)), np.sin(np.radians(20)) * np.cos(np.radians(10)), np.sin(np.radians(10))])
+    dist = 6371.3 * np.arccos(np.clip(xyz @ xc, -1, 1))
+    pop = synthetic_population(40000, alt, seed=6, fertile=True, cells=np.flatnonzero(dist < 2600.0), max_age=70.0)
+    g, o = make_pair(par, nbr, alt, pop, seed=31, env=env)
+    moves = 0
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        moves += s.moves
+    occ = np.flatnonzero(g.counts())
+    assert moves > 50000 and 2700.0 < dist[occ].max() < 3000.0  # the border was reached, nobody crossed it
 
 
 @pytest.mark.parametrize("which", ["tut_EnvironAltPop", "OoANavGenPop"])
