@@ -67,6 +67,18 @@ int  qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id);
  * (app/Simulator.cpp:668-753). */
 int  qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n);
 
+/* Interpolated environment (core/AutoInterpolator.cpp:461-483, called from the simulator's loop app/Simulator.cpp:338-352,
+ * 356-367 between checkEvents and flushEvents): between two dated environment files every target array grows by a fixed
+ * per-step difference array.  qhgb_set_env_delta hands over the difference array of one target (m_mDiff[name]; NULL
+ * removes it) -- it stays on the device; qhgb_interpolate_env(steps) = AutoInterpolator::interpolate(iSteps): every target
+ * array += steps * its difference array, on the device, no host traffic.  The host then delivers the interpolator's events
+ * (qhgb_update_event for EVENT_ID_GEO / _CLIMATE / _VEG) and qhgb_flush_events exactly as after a reloaded array. */
+int  qhgb_set_env_delta(qhgb_pop *p, const char *name, const double *delta, int64_t n);
+int  qhgb_interpolate_env(qhgb_pop *p, int steps);
+/* the current values of an environment array on the device (after interpolation the host's Geography / Climate / Vegetation
+ * copy is stale; a host that writes them out -- e.g. the "write env" event, app/Simulator.cpp -- reads them back here) */
+int  qhgb_get_env_array(qhgb_pop *p, const char *name, double *out);
+
 /* the Navigation group (sea-ways) that Navigate reads through SCellGrid::m_pNavigation (core/Navigation.h:13-37,
  * io/NavGroupReader.cpp:98-160): n_ports origin cells; port p jumps to dest_cell[port_ptr[p] .. port_ptr[p+1]) over
  * the distances dist[] (same indexing); bridges = n_bridges pairs of cells.  Navigate builds its jump tables from it

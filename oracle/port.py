@@ -35,6 +35,9 @@ def lib():
         L.qor_destroy.argtypes = [vp]
         L.qor_set_cells.argtypes = [vp, vp, vp]
         L.qor_set_env_array.argtypes = [vp, C.c_char_p, vp, i64]
+        L.qor_set_env_delta.argtypes = [vp, C.c_char_p, vp, i64]
+        L.qor_interpolate_env.argtypes = [vp, i32]
+        L.qor_get_env_array.argtypes = [vp, C.c_char_p, vp]
         L.qor_set_attribute.argtypes = [vp, C.c_char_p, C.c_double]
         L.qor_set_attribute_str.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.qor_set_prio.argtypes = [vp, C.c_char_p, i32]
@@ -135,6 +138,18 @@ class OraclePop:
     def set_env(self, name, v):
         v = np.ascontiguousarray(v, np.float64)
         assert lib().qor_set_env_array(self.h, name.encode(), _p(v), len(v)) == 0
+
+    def set_env_delta(self, name, delta):
+        d = None if delta is None else np.ascontiguousarray(delta, np.float64)
+        assert lib().qor_set_env_delta(self.h, name.encode(), _p(d), 0 if d is None else len(d)) == 0, name
+
+    def interpolate_env(self, steps=1):
+        assert lib().qor_interpolate_env(self.h, int(steps)) == 0
+
+    def env_array(self, name):
+        out = np.zeros(self.ncells)
+        assert lib().qor_get_env_array(self.h, name.encode(), _p(out)) == 0, name
+        return out
 
     def add_agents(self, pop):
         n = len(pop["cell"])

@@ -336,6 +336,7 @@ struct qor_pop {
     std::vector<int32_t> nbr, gid;
     std::vector<uint8_t> nNbr;
     std::map<std::string, std::vector<double>> env;  // "Altitude", "Ice", ...
+    std::map<std::string, std::vector<double>> envDelta;  // AutoInterpolator::m_mDiff: per-step differences of the interpolated targets
     std::vector<Action> actions;
 
     // parameters (names as in the reference's XML / QDF attributes)
@@ -1075,6 +1076,30 @@ int qor_set_cells(qor_pop *p, const int32_t *nbr, const int32_t *global_id) {
 int qor_set_env_array(qor_pop *p, const char *name, const double *v, int64_t n) {
     if (n != p->nCells) return -1;
     p->env[name].assign(v, v + n);
+    return 0;
+}
+
+int qor_set_env_delta(qor_pop *p, const char *name, const double *delta, int64_t n) {
+    if (!delta) { p->envDelta.erase(name); return 0; }
+    if (n != p->nCells || !p->env.count(name)) return -1;
+    p->envDelta[name].assign(delta, delta + n);
+    return 0;
+}
+
+// AutoInterpolator::interpolate (core/AutoInterpolator.cpp:461-483): pTarget[i] += iSteps*pSource[i] (for iSteps == 1 the
+// reference writes += pSource[i], the same value)
+int qor_interpolate_env(qor_pop *p, int steps) {
+    for (auto &kv : p->envDelta) {
+        std::vector<double> &t = p->env[kv.first];
+        for (int i = 0; i < p->nCells; i++) t[i] += steps * kv.second[i];
+    }
+    return 0;
+}
+
+int qor_get_env_array(qor_pop *p, const char *name, double *out) {
+    auto it = p->env.find(name);
+    if (it == p->env.end()) return -1;
+    memcpy(out, it->second.data(), sizeof(double) * p->nCells);
     return 0;
 }
 

@@ -31,6 +31,9 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
 void     qor_destroy(qor_pop *p);
 int      qor_set_cells(qor_pop *p, const int32_t *nbr, const int32_t *global_id);
 int      qor_set_env_array(qor_pop *p, const char *name, const double *v, int64_t n);
+int      qor_set_env_delta(qor_pop *p, const char *name, const double *delta, int64_t n);  /* core/AutoInterpolator.cpp:461-483 */
+int      qor_interpolate_env(qor_pop *p, int steps);
+int      qor_get_env_array(qor_pop *p, const char *name, double *out);
 int      qor_set_attribute(qor_pop *p, const char *name, double v);
 int      qor_set_attribute_str(qor_pop *p, const char *name, const char *v);
 int      qor_set_prio(qor_pop *p, const char *action, int prio);

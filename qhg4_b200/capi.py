@@ -27,6 +27,9 @@ SYMBOLS = {
     "qhgb_version": (cp, []),
     "qhgb_set_cells": (i32, [vp, vp, vp]),
     "qhgb_set_env_array": (i32, [vp, cp, vp, i64]),
+    "qhgb_set_env_delta": (i32, [vp, cp, vp, i64]),
+    "qhgb_interpolate_env": (i32, [vp, i32]),
+    "qhgb_get_env_array": (i32, [vp, cp, vp]),
     "qhgb_set_navigation": (i32, [vp, i32, vp, vp, vp, vp, i32, vp]),
     "qhgb_set_attribute": (i32, [vp, cp, f64]),
     "qhgb_set_attribute_str": (i32, [vp, cp, cp]),

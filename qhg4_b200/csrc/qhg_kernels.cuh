@@ -225,6 +225,13 @@ __global__ void k_rows_cumulate(int nCells, double *__restrict__ W) {
     }
 }
 
+// AutoInterpolator::interpolate (core/AutoInterpolator.cpp:461-483): target += steps * diff, one multiply and one add per
+// cell, rounded separately like the reference's compiled loop (no fused multiply-add)
+__global__ void k_env_interpolate(int n, double steps, const double *__restrict__ diff, double *__restrict__ target) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        target[i] = __dadd_rn(target[i], __dmul_rn(steps, diff[i]));
+}
+
 // NPPCapacity::recalculate (actions/NPPCapacity.cpp:138-217) with NPPCalcMiami::calcNPP (core/NPPCalcMiami.cpp:28-42)
 struct NppParams {
     double waterFactor, coastalFactor, coastMinLat, coastMaxLat, nppMin, nppMax, kMax, kMin, efficiency;

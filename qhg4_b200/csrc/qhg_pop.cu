@@ -214,6 +214,8 @@ struct qhgb_pop {
     DevBuf<double> navCum;
     DevBuf<int2> navBridges;
     std::vector<double> hAlt;  // host copy of the altitude (bridges need both ends above sea level)
+    bool hAltStale = false;    // the device array was interpolated since the copy was taken
+    std::map<std::string, DevBuf<double>> envDelta;  // per-step difference arrays of the interpolated targets (AutoInterpolator::m_mDiff)
     // ConfinedMove: the cells inside the region (ConfinedMove::m_bAllowed, actions/ConfinedMove.cpp:44-78), built at preLoop
     DevBuf<uint8_t> allowed;
     bool confReady = false;
@@ -610,6 +612,12 @@ int recalcNavigation(qhgb_pop *p) {
     qhgb_pop &q = *p;
     if (!q.navNeedUpdate) return 0;
     const int nPorts = (int)q.hPortCell.size();
+    if (q.hAltStale && q.haveAlt) {  // the altitude was interpolated on the device: bring the copy up to date
+        q.hAlt.resize(q.nCells);
+        CK(cudaMemcpyAsync(q.hAlt.data(), q.alt.p, sizeof(double) * q.nCells, cudaMemcpyDeviceToHost, q.stream));
+        CK(cudaStreamSynchronize(q.stream));
+        q.hAltStale = false;
+    }
     const double decay = q.A("Navigate_decay"), A = q.A("Navigate_prob0") / exp(decay * q.A("Navigate_dist0"));
     std::vector<int> row(q.nCells, -1), ptr(nPorts + 1, 0), dest;
     std::vector<double> cum;
@@ -1043,6 +1051,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
+    for (auto &kv : p->envDelta) kv.second.release();
     p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release();
@@ -1103,6 +1112,7 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
         CK(cudaMemcpyAsync(p->alt.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         p->haveAlt = true;
         p->hAlt.assign(values, values + n);
+        p->hAltStale = false;
     } else if (s == "Ice") {
         std::vector<uint8_t> b(n);
         bool any = false;
@@ -1119,6 +1129,50 @@ int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int6
         CK(cudaMemcpyAsync(d.p, values, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     }
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_set_env_delta(qhgb_pop *p, const char *name, const double *delta, int64_t n) {
+    if (!p || !name) return fail("qhgb_set_env_delta: NULL argument");
+    std::string s(name);
+    if (!delta) {  // the target is no longer interpolated
+        auto it = p->envDelta.find(s);
+        if (it != p->envDelta.end()) { it->second.release(); p->envDelta.erase(it); }
+        return 0;
+    }
+    if (n != p->nCells) return fail("qhgb_set_env_delta: [%s] has %lld values, grid has %d cells", name, (long long)n, p->nCells);
+    if (s == "Ice") return fail("qhgb_set_env_delta: [Ice] is a flag array and cannot be interpolated");
+    if (s == "Altitude" ? !p->haveAlt : !p->envExtra.count(s)) return fail("No array with name [%s] found", name);  // the target must exist
+    CK(cudaSetDevice(p->device));
+    DevBuf<double> &d = p->envDelta[s];
+    if (d.n != (size_t)n) CK(d.alloc(n));
+    CK(cudaMemcpyAsync(d.p, delta, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_env_array(qhgb_pop *p, const char *name, double *out) {
+    if (!p || !name || !out) return fail("qhgb_get_env_array: NULL argument");
+    std::string s(name);
+    const double *src = nullptr;
+    if (s == "Altitude") src = p->haveAlt ? p->alt.p : nullptr;
+    else if (p->envExtra.count(s)) src = p->envExtra[s].p;
+    if (!src) return fail("No array with name [%s] found", name);
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(out, src, sizeof(double) * (size_t)p->nCells, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_interpolate_env(qhgb_pop *p, int steps) {
+    if (!p) return fail("qhgb_interpolate_env: NULL population");
+    CK(cudaSetDevice(p->device));
+    for (auto &kv : p->envDelta) {
+        double *target = (kv.first == "Altitude") ? p->alt.p : p->envExtra[kv.first].p;
+        LAUNCH(p, "k_env_interpolate", k_env_interpolate, p->gridFor(p->nCells), 256, p->nCells, (double)steps, kv.second.p, target);
+        if (kv.first == "Altitude") p->hAltStale = true;
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 

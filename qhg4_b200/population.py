@@ -57,6 +57,20 @@ class GpuPopulation:
         v = np.ascontiguousarray(values, np.float64)
         check(self.L.qhgb_set_env_array(self.h, name.encode(), _p(v), len(v)), f"qhgb_set_env_array({name})")
 
+    def set_env_delta(self, name: str, delta):
+        """AutoInterpolator's per-step difference array of one target (core/AutoInterpolator.cpp:461-483); None removes it."""
+        d = None if delta is None else np.ascontiguousarray(delta, np.float64)
+        check(self.L.qhgb_set_env_delta(self.h, name.encode(), _p(d), 0 if d is None else len(d)), f"qhgb_set_env_delta({name})")
+
+    def interpolate_env(self, steps: int = 1):
+        """AutoInterpolator::interpolate(iSteps) on the device: every target array += steps * its difference array."""
+        check(self.L.qhgb_interpolate_env(self.h, int(steps)), "qhgb_interpolate_env")
+
+    def env_array(self, name: str):
+        out = np.zeros(self.ncells, np.float64)
+        check(self.L.qhgb_get_env_array(self.h, name.encode(), _p(out)), f"qhgb_get_env_array({name})")
+        return out
+
     def read_species_data(self, params: PopParams):
         """SPopulation::readSpeciesData (core/SPopulation.cpp:1108-1142): priorities, then action attributes."""
         for name, pr in params.prios.items():

@@ -92,3 +92,45 @@ def test_counter_mode_is_order_invariant():
         res.append({f: a[f][s] for f in ("cell", "id", "birth", "gender", "life")})
     for f in res[0]:
         assert np.array_equal(res[0][f], res[1][f]), f
+
+
+def test_env_interpolation_restates_auto_interpolator():
+    """AutoInterpolator::interpolate (core/AutoInterpolator.cpp:461-483): target[i] += iSteps * diff[i] in double, product and
+    sum rounded separately.  The oracle against numpy's elementwise arithmetic, and a run whose climate is interpolated step
+    by step (events + flush as app/Simulator.cpp:338-374 delivers them) against the same run fed with re-uploaded arrays."""
+    from oracle import port
+    from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_climate, synthetic_population
+    from qhg4_b200.params import seed_state, tut_environ_cap_alt
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=2)
+    env = synthetic_climate(xyz, alt, seed=3)
+    pop = synthetic_population(6000, alt, seed=4, fertile=True)
+    rng = np.random.default_rng(1)
+    delta = {"AnnualMeanTemp": rng.normal(-0.3, 0.1, len(alt)), "AnnualRainfall": rng.normal(-15.0, 3.0, len(alt)),
+             "BaseNPP": rng.normal(-0.01, 0.003, len(alt)), "Altitude": rng.normal(-4.0, 1.0, len(alt))}
+    a = port.OraclePop(tut_environ_cap_alt(), nbr, alt, mode=port.MODE_COUNTER, state16=seed_state(3), env=env)
+    b = port.OraclePop(tut_environ_cap_alt(), nbr, alt, mode=port.MODE_COUNTER, state16=seed_state(3), env=env)
+    for q in (a, b):
+        q.add_agents(pop); q.start()
+    for name, d in delta.items():
+        a.set_env_delta(name, d)
+    cur = dict(env, Altitude=alt.copy())
+    for k in range(10):
+        a.step(float(k)); b.step(float(k))
+        steps = 1 if k % 3 else 2
+        a.interpolate_env(steps)
+        for name, d in delta.items():
+            cur[name] = cur[name] + steps * d          # numpy: one rounded product, one rounded sum per element
+            b.set_env(name, cur[name])
+            assert np.array_equal(a.env_array(name), cur[name]), (k, name)
+        for q in (a, b):
+            for ev in (2, 3, 4):
+                q.update_event(ev, float(k + 1))
+            q.flush_events(float(k + 1))
+        assert np.array_equal(a.capacities(), b.capacities()), k
+        assert a.num_agents() == b.num_agents(), k
+    assert not np.array_equal(a.env_array("Altitude"), alt) and a.num_agents() > 0
+    a.set_env_delta("Altitude", None)
+    before = a.env_array("Altitude").copy()
+    a.interpolate_env(5)
+    assert np.array_equal(a.env_array("Altitude"), before)

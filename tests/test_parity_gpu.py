@@ -447,6 +447,45 @@ def test_partheno_and_static_populations_bit_exact_vs_oracle(path):
     assert (s.births, s.deaths, s.moves) == (0, 0, 0) and np.array_equal(g.counts(), c0) and g.num_agents() == 30000
 
 
+def test_env_interpolation_on_device_bit_exact_vs_oracle(path):
+    """SURVEY.md §8f-4, AutoInterpolator::interpolate (core/AutoInterpolator.cpp:461-483) on the device: the per-step
+    difference arrays stay in HBM, every interpolation is one kernel per target (no host traffic), followed by the
+    interpolator's events and the flush (app/Simulator.cpp:338-374).  Arrays, capacities (NPPCapacity reacts on the flush),
+    the drowned of the GEO event and the whole trajectory equal the oracle's bit for bit."""
+    from qhg4_b200.params import tut_environ_cap_alt
+    nbr, xyz, alt, env = _cap_world()
+    pop = synthetic_population(30000, alt, seed=4, fertile=True)
+    rng = np.random.default_rng(1)
+    delta = {"AnnualMeanTemp": rng.normal(-0.3, 0.1, len(alt)), "AnnualRainfall": rng.normal(-15.0, 3.0, len(alt)),
+             "BaseNPP": rng.normal(-0.01, 0.003, len(alt)), "Altitude": rng.normal(-4.0, 1.0, len(alt))}
+    g, o = make_pair(tut_environ_cap_alt(), nbr, alt, pop, seed=3, env=env)
+    for name, d in delta.items():
+        g.set_env_delta(name, d); o.set_env_delta(name, d)
+    cur = dict(env, Altitude=alt.copy())
+    deaths0 = 0
+    for k in range(10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        steps = 1 if k % 3 else 2
+        g.interpolate_env(steps); o.interpolate_env(steps)
+        for name, d in delta.items():
+            cur[name] = cur[name] + steps * d
+            assert np.array_equal(g.env_array(name), cur[name]), (k, name)
+            assert np.array_equal(o.env_array(name), cur[name]), (k, name)
+        n0 = g.num_agents()
+        for ev in (2, 3, 4):
+            g.update_event(ev, float(k + 1)); o.update_event(ev, float(k + 1))
+        g.flush_events(float(k + 1)); o.flush_events(float(k + 1))
+        deaths0 += n0 - g.num_agents()
+        assert np.array_equal(g.capacities(), o.capacities()), k
+        assert_same_population(g, o, k)
+    assert deaths0 > 0 and g.num_agents() > 0  # the sinking coast drowned somebody
+    g.set_env_delta("Altitude", None)
+    before = g.env_array("Altitude")
+    g.interpolate_env(3)
+    assert np.array_equal(g.env_array("Altitude"), before)
+
+
 @pytest.mark.parametrize("move_first", [False, True])
 def test_confined_move_bit_exact_vs_oracle(move_first, path):
     """ConfinedMove (actions/ConfinedMove.cpp:44-101; its finalize() filters the whole move list in finalizeStep): moves out
