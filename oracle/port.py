@@ -65,6 +65,10 @@ def lib():
         L.qor_get_genomes.restype = i64
         L.qor_get_genomes.argtypes = [vp, i64, vp, vp]
         L.qor_get_step_stats.argtypes = [vp, vp, vp, vp]
+        L.qor_set_genetics_well.argtypes = [vp, vp, u32]
+        L.qor_gene2_crossover.argtypes = [vp, vp, i32, i32, vp]
+        L.qor_gene2_freereco.argtypes = [vp, vp, i32, vp]
+        L.qor_gene2_mutate.argtypes = [vp, vp, i32, i32]
         L.qor_get_pending_births.restype = i64
         L.qor_get_pending_births.argtypes = [vp]
         L.qor_set_birth_id_offset.argtypes = [vp, i64, i64]
@@ -190,6 +194,10 @@ class OraclePop:
         dc, dd = np.ascontiguousarray(dest_cell, np.int32), np.ascontiguousarray(dist, np.float64)
         br = np.ascontiguousarray(np.asarray(bridges, np.int32).reshape(-1, 2))
         assert lib().qor_set_navigation(self.h, len(pc), _p(pc), _p(pp), _p(dc), _p(dd), len(br), _p(br) if len(br) else None) == 0
+
+    def set_genetics_well(self, state16, index):
+        st = np.ascontiguousarray(state16, np.uint32)
+        assert lib().qor_set_genetics_well(self.h, _p(st), int(index)) == 0
 
     def set_genomes(self, genomes):
         g = np.ascontiguousarray(genomes, np.uint64)

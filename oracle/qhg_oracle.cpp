@@ -57,6 +57,11 @@ inline uint32_t u2int(uint32_t x, uint32_t a, uint32_t b) {  // wrandi(a,b) with
     uint32_t r = b - a;
     return a + (uint32_t)((1.0 * r * x) / 4294967296.0);
 }
+inline uint32_t u2int_s(uint32_t x, uint32_t a, uint32_t b, uint32_t s) {  // wrandi(a,b,s), utils/WELL512.h:39: multiples of s
+    uint32_t r = b - a;
+    r += (r % s);
+    return a + s * (uint32_t)((1.0 * r * x) / (s * 4294967296.0));
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011, public algorithm) -- the counter-based generator of the CUDA path
@@ -194,11 +199,12 @@ inline uint64_t makeMultiMask(const std::vector<uint32_t> &br) {
 }
 
 // genes/BitGeneUtils.cpp:116-186: out (2 strands x nBlocks) = in with its two strands crossed over at nCross random bits
-inline void bitCrossOver(uint64_t *out, const uint64_t *in, int G, int nCross, const NextU32 &next) {
-    const uint32_t nBlocks = (uint32_t)((G + 63) / 64), nBits = nBlocks * 64;
+// With bpn = 2 (genes/GeneUtils.cpp:184-245) the breaks fall on nucleotide boundaries: wrandi(0, nBits, 2).
+inline void bitCrossOver(uint64_t *out, const uint64_t *in, int G, int nCross, const NextU32 &next, int bpn = 1) {
+    const uint32_t nBlocks = (uint32_t)((G * bpn + 63) / 64), nBits = nBlocks * 64;
     std::map<uint32_t, std::vector<uint32_t>> blockBreaks;
     for (int i = 0; i < nCross; i++) {
-        uint32_t pos = u2int(next(), 0, nBits);  // wrandi(0, nBits, BITSINNUC = 1)
+        uint32_t pos = u2int_s(next(), 0, nBits, (uint32_t)bpn);  // wrandi(0, nBits, BITSINNUC)
         blockBreaks[pos / 64].push_back(pos % 64);
     }
     uint32_t last = 0, S = 0;
@@ -220,10 +226,13 @@ inline void bitCrossOver(uint64_t *out, const uint64_t *in, int G, int nCross, c
 }
 
 // genes/BitGeneUtils.cpp:190-220: every block gets an independent random 64-bit mask (two 32-bit draws, high word first)
-inline void bitFreeReco(uint64_t *out, const uint64_t *in, int nBlocks, const NextU32 &next) {
+// With bpn = 2 (genes/GeneUtils.cpp:322-362) every other bit of the mask is doubled, so that nucleotides stay whole.
+inline void bitFreeReco(uint64_t *out, const uint64_t *in, int nBlocks, const NextU32 &next, int bpn = 1) {
     for (int b = 0; b < nBlocks; b++) {
         const uint64_t hi = next(), lo = next();
-        const uint64_t L = (hi << 32) + lo, R = ~L;
+        uint64_t L = (hi << 32) + lo;
+        if (bpn == 2) { L &= 0x5555555555555555ull; L += L << 1; }
+        const uint64_t R = ~L;
         out[b] = (L & in[b]) | (R & in[nBlocks + b]);
         out[b + nBlocks] = (L & in[nBlocks + b]) | (R & in[b]);
     }
@@ -234,6 +243,15 @@ inline void bitMutate(uint64_t *g, int nBits, int nMut, const NextU32 &next) {
     for (int i = 0; i < nMut; i++) {
         uint32_t pos = u2int(next(), 0, (uint32_t)nBits);
         g[pos / 64] ^= (uint64_t)1 << (pos % 64);
+    }
+}
+// genes/GeneUtils.cpp:112-146: nMut times, a random nucleotide among the first nNucs is XORed with 01, 10 or 11
+inline void nucMutate(uint64_t *g, int nNucs, int nMut, const NextU32 &next) {
+    const uint32_t nBits = 2u * (uint32_t)nNucs;
+    for (int i = 0; i < nMut; i++) {
+        const uint32_t pos = u2int_s(next(), 0, nBits, 2);
+        const uint64_t mask = u2int(next(), 1, 4);
+        g[pos / 64] ^= mask << (pos % 64);
     }
 }
 
@@ -363,6 +381,9 @@ struct qor_pop {
     bool multiFirst = true, multiObserves = false;
     // Genetics<.., BitGeneUtils> (actions/Genetics.cpp)
     int genomeSize = 0, numCrossOvers = 0, nBlocks = 0;
+    int bitsPerNuc = 1;     // 1: Genetics<.., BitGeneUtils>, 2: Genetics<.., GeneUtils> (OoANavGen2bitPop ...)
+    Well512 genWell;        // WELL mode: the Genetics action's OWN generator (actions/Genetics.cpp:91-123), thread 0
+    bool haveGenWell = false;
     double mutationRate = 0;
     std::vector<double> binoTable;
     // Navigate (actions/Navigate.cpp) over the Navigation group (core/Navigation.h:13-37)
@@ -834,10 +855,13 @@ struct qor_pop {
         const int nb = nBlocks;
         std::vector<uint64_t> out(2 * nb, 0), t1(2 * nb), t2(2 * nb);
         uint32_t g0[4];
-        draw4(cid, 4, g0);
+        const bool seq = (mode == QOR_MODE_WELL);  // the reference's order of draws from Genetics' generator: strands, mother, father, count, positions
+        if (seq) { g0[0] = genWell.next(); g0[1] = genWell.next(); g0[2] = g0[3] = 0; }
+        else draw4(cid, 4, g0);
         const int i1 = (int)(2 * 1.0 * u2d(g0[0])), i2 = (int)(2 * 1.0 * u2d(g0[1]));
         const std::vector<uint64_t> &gm = slots[mother].genome, &gf = slots[father].genome;
         auto words = [&](uint32_t base) {
+            if (seq) return NextU32([this]() { return genWell.next(); });
             auto state = std::make_shared<std::pair<uint32_t, std::vector<uint32_t>>>(0u, std::vector<uint32_t>());
             return NextU32([this, cid, base, state]() {
                 uint32_t i = state->first++;
@@ -847,18 +871,22 @@ struct qor_pop {
             });
         };
         if (numCrossOvers > 0) {
-            bitCrossOver(t1.data(), gm.data(), genomeSize, numCrossOvers, words(0x02000000u | (0u << 20)));
-            bitCrossOver(t2.data(), gf.data(), genomeSize, numCrossOvers, words(0x02000000u | (1u << 20)));
+            bitCrossOver(t1.data(), gm.data(), genomeSize, numCrossOvers, words(0x02000000u | (0u << 20)), bitsPerNuc);
+            bitCrossOver(t2.data(), gf.data(), genomeSize, numCrossOvers, words(0x02000000u | (1u << 20)), bitsPerNuc);
         } else if (numCrossOvers == -1) {
-            bitFreeReco(t1.data(), gm.data(), nb, words(0x01000000u | (0u << 20)));
-            bitFreeReco(t2.data(), gf.data(), nb, words(0x01000000u | (1u << 20)));
+            bitFreeReco(t1.data(), gm.data(), nb, words(0x01000000u | (0u << 20)), bitsPerNuc);
+            bitFreeReco(t2.data(), gf.data(), nb, words(0x01000000u | (1u << 20)), bitsPerNuc);
         } else {
             t1 = gm; t2 = gf;
         }
         for (int q = 0; q < nb; q++) { out[q] = t1[i1 * nb + q]; out[nb + q] = t2[i2 * nb + q]; }
         if (mutationRate > 0) {
+            if (seq) g0[2] = genWell.next();
             int nMut = binomialGetN(binoTable, u2d(g0[2]));
-            if (nMut > 0) bitMutate(out.data(), 2 * genomeSize, nMut, words(0x03000000u));
+            if (nMut > 0) {  // U::mutateNucs(pBabyGenome, m_iNumParents*m_iGenomeSize, ...), actions/Genetics.cpp:332
+                if (bitsPerNuc == 2) nucMutate(out.data(), 2 * genomeSize, nMut, words(0x03000000u));
+                else bitMutate(out.data(), 2 * genomeSize, nMut, words(0x03000000u));
+            }
         }
         slots[babySlot].genome = out;
     }
@@ -1013,6 +1041,13 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"ConfinedMove", A_CONFINEDMOVE}};
+    } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
+        // probe classes: tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added and called from
+        // makePopSpecificOffspring (GenProbePop<U> in oracle/ref_driver.cpp) -- pin the Genetics action with 1- and 2-bit nucleotides
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"Genetics", A_GENETICS}};
+        p->bitsPerNuc = (p->popClass == "tut_EnvironAltGen2bitPop") ? 2 : 1;
     } else if (p->popClass == "tut_ParthenoPop") {  // populations/tut_ParthenoPop.cpp:22-45
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}, {"Verhulst", A_VERHULST},
                       {"Fertility", A_FERTILITY}};
@@ -1036,15 +1071,18 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->cap.assign(n_cells, 0.0);
         for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
             p->env[nm].assign(n_cells, 0.0);
-    } else if (p->popClass == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97 (Navigate is registered but unsupported)
-        if (mode != QOR_MODE_COUNTER) { delete p; return nullptr; }  // the genome draws only exist under the counter-mode law
+    } else if (p->popClass == "OoANavGenPop" || p->popClass == "OoANavGen2bitPop") {
+        // populations/OoANavGenPop.cpp:33-97; populations/OoANavGen2bitPop.cpp is the same class with Genetics<.., GeneUtils>
+        // (2-bit nucleotides) and WITHOUT addObserver(m_pME)
+        if (mode != QOR_MODE_COUNTER) { delete p; return nullptr; }  // these classes are not built in oracle/_ref (no WELL-mode partner)
+        p->bitsPerNuc = (p->popClass == "OoANavGen2bitPop") ? 2 : 1;
         p->actions = {{"MultiEvaluator[Alt+NPP]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"GetOld", A_GETOLD}, {"OldAgeDeath", A_OLDAGEDEATH}, {"Fertility", A_FERTILITY},
                       {"NPPCapacity", A_NPPCAP}, {"Genetics", A_GENETICS}, {"Navigate", A_NAVIGATE}};
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltCapPref"; ea.trigger = EVENT_ID_GEO;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = true; en.polyName = "NPPPref"; en.trigger = 4;
         p->subs = {ea, en};
-        p->multiObserves = true;  // addObserver(m_pME), populations/OoANavGenPop.cpp:59
+        p->multiObserves = (p->bitsPerNuc == 1);  // addObserver(m_pME), populations/OoANavGenPop.cpp:59; absent in OoANavGen2bitPop.cpp
         p->cap.assign(n_cells, 0.0);
         for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
             p->env[nm].assign(n_cells, 0.0);
@@ -1136,10 +1174,10 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "Navigate_prob0") p->navProb0 = v;
     else if (s == "Navigate_min_dens") {}
     else if (s == "Navigate_bridge_prob") p->navBridgeProb = v;
-    else if (s == "Genetics_genome_size") { p->genomeSize = (int)v; p->nBlocks = ((int)v + 63) / 64; }
+    else if (s == "Genetics_genome_size") { p->genomeSize = (int)v; p->nBlocks = ((int)v * p->bitsPerNuc + 63) / 64; }
     else if (s == "Genetics_num_crossover") p->numCrossOvers = (int)v;
     else if (s == "Genetics_mutation_rate") p->mutationRate = v;
-    else if (s == "Genetics_create_new_genome" || s == "Genetics_bits_per_nuc") { if (s == "Genetics_bits_per_nuc" && (int)v != 1) return -1; }
+    else if (s == "Genetics_create_new_genome" || s == "Genetics_bits_per_nuc") { if (s == "Genetics_bits_per_nuc" && (int)v != p->bitsPerNuc) return -1; }
     else if (s == "Multi_weight_alt" || s == "Multi_weight_npp") { for (auto &e : p->subs) if (e.weightName == s) e.weight = v; }
     else return -1;
     return 0;
@@ -1319,6 +1357,31 @@ int qor_bit_mutate(const uint32_t *state16, uint64_t *genome, int n_bits, int n_
     bitMutate(genome, n_bits, n_mut, [&w]() { return w.next(); });
     return 0;
 }
+// genes/GeneUtils.cpp (2-bit nucleotides): the same three primitives
+int qor_gene2_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out) {
+    Well512 w; w.seed(state16);
+    bitCrossOver(out, in, genome_size, n_cross, [&w]() { return w.next(); }, 2);
+    return 0;
+}
+int qor_gene2_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out) {
+    Well512 w; w.seed(state16);
+    bitFreeReco(out, in, n_blocks, [&w]() { return w.next(); }, 2);
+    return 0;
+}
+int qor_gene2_mutate(const uint32_t *state16, uint64_t *genome, int n_nucs, int n_mut) {
+    Well512 w; w.seed(state16);
+    nucMutate(genome, n_nucs, n_mut, [&w]() { return w.next(); });
+    return 0;
+}
+// WELL mode: state and index of the Genetics action's own generator (in the reference it is built from aiSeeds[1] through MD5
+// digests of seed phrases, utils/WELLUtils.cpp:127-148; the test reads it from the reference and hands it over)
+int qor_set_genetics_well(qor_pop *p, const uint32_t *state16, uint32_t index) {
+    p->genWell.seed(state16);
+    p->genWell.idx = index & 15u;
+    p->haveGenWell = true;
+    return 0;
+}
+
 int qor_binomial_table(double prob, int n, double eps, int cap, double *out) {
     std::vector<double> t = binomialTable(prob, n, eps);
     for (size_t i = 0; i < t.size() && (int)i < cap; i++) out[i] = t[i];

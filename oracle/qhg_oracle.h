@@ -68,6 +68,10 @@ int64_t  qor_get_genomes(qor_pop *p, int64_t cap, uint64_t *g, int32_t *num_babi
 int      qor_bit_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out);
 int      qor_bit_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out);
 int      qor_bit_mutate(const uint32_t *state16, uint64_t *genome, int n_bits, int n_mut);
+int      qor_gene2_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out);  /* genes/GeneUtils.cpp */
+int      qor_gene2_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out);
+int      qor_gene2_mutate(const uint32_t *state16, uint64_t *genome, int n_nucs, int n_mut);
+int      qor_set_genetics_well(qor_pop *p, const uint32_t *state16, uint32_t index);
 int      qor_binomial_table(double prob, int n, double eps, int cap, double *out);
 int      qor_binomial_get_n(double prob, int n, double eps, double r);
 

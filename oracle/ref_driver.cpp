@@ -48,6 +48,12 @@
 #include "Navigate.cpp"  // the reference's action templates, instantiated below for the tutorial agent
 #include "OldAgeDeath.cpp"
 #include "ConfinedMove.cpp"
+#include "GeneUtils.h"
+#include "LayerArrBuf.cpp"
+#include "SequenceIOUtils.cpp"
+#include "Genetics.cpp"
+#include "GenomeCreator.cpp"
+template class SequenceIOUtils<ulong>;  // io/SequenceIOUtils.cpp is an uninstantiated template
 #ifdef QHG_WITH_GPU_ADAPTER  // oracle/_ref/libqhgadapter.so: the same driver with the plugin class of INTEGRATION.md in it
 #include <cstdlib>
 #include <vector>
@@ -92,6 +98,11 @@ struct PopAccess {
     virtual double *capacities() = 0;
     virtual int bd(double *&b, double *&d) = 0;
     virtual void atanParams(double &scale, double &slope, double &maxAge) = 0;
+    // populations with Genetics: words per genome row (0: none), the row of a slot, the action's own generator (thread 0)
+    virtual int genomeWords() { return 0; }
+    virtual ulong *genomeRow(int slot) { return nullptr; }
+    virtual WELL512 *geneticsWell() { return nullptr; }
+    virtual int geneticsInit(int genomeSize, int numCrossOvers, double mutationRate) { return -1; }
 };
 
 template <class PopT, class AgentT>
@@ -143,6 +154,30 @@ struct PopAccessT : PopAccess {
             return -1;
         }
     }
+    int genomeWords() override {
+        if constexpr (requires { pop->m_pGenetics; }) return 2 * pop->m_pGenetics->m_iNumBlocks; else return 0;
+    }
+    ulong *genomeRow(int slot) override {
+        if constexpr (requires { pop->m_pGenetics; }) return pop->m_pGenetics->getGenome((uint)slot); else return nullptr;
+    }
+    // The seed-taking constructor of Genetics never registers its attribute names (actions/Genetics.cpp:91-123, unlike :52-85),
+    // so Action::checkAttributes rejects every Genetics attribute of an XML file as unknown: populations with Genetics can
+    // only be configured from a QDF (extractAttributesQDF, :440-500, which then calls init()).  Without HDF5 the driver sets
+    // the same members and calls the same init().
+    int geneticsInit(int genomeSize, int numCrossOvers, double mutationRate) override {
+        if constexpr (requires { pop->m_pGenetics; }) {
+            pop->m_pGenetics->m_iGenomeSize = genomeSize;
+            pop->m_pGenetics->m_iNumCrossOvers = numCrossOvers;
+            pop->m_pGenetics->m_dMutationRate = mutationRate;
+            pop->m_pGenetics->m_bCreateNewGenome = 0;
+            return pop->m_pGenetics->init();
+        } else {
+            return -1;
+        }
+    }
+    WELL512 *geneticsWell() override {
+        if constexpr (requires { pop->m_pGenetics; }) return pop->m_pGenetics->m_apWELL[0]; else return nullptr;
+    }
     void atanParams(double &scale, double &slope, double &maxAge) override {
         if constexpr (requires { pop->m_pAD; }) { scale = pop->m_pAD->m_dScale; slope = pop->m_pAD->m_dSlope; maxAge = pop->m_pAD->m_dMaxAge; }
         else { scale = slope = maxAge = 0; }
@@ -176,6 +211,31 @@ public:
     }
     virtual ~ConfProbePop() { delete m_pCM; }
     ConfinedMove<tut_EnvironAltAgent> *m_pCM;
+};
+
+// Probe class for pinning the Genetics action itself (actions/Genetics.cpp:285-337 makeOffspring: strand choice, crossover /
+// free recombination of both parents, mutation count and positions, all from the action's OWN generators seeded from
+// aiSeeds[1], :91-123) with 1-bit (genes/BitGeneUtils.cpp) and 2-bit (genes/GeneUtils.cpp) nucleotides.  The shipped classes
+// that carry it (OoANavGenPop, OoANavGen2bitPop ...) need Climate/Vegetation/Navigation files; here the reference's own
+// Genetics<T,U> is added to the reference's tut_EnvironAltPop and called from makePopSpecificOffspring exactly as
+// populations/OoANavGenPop.cpp:231-245 does.  Genetics::init() is what extractAttributesQDF calls after the attributes are
+// in (actions/Genetics.cpp:488-491); the XML path never calls it, the driver does.
+template <class U>
+class GenProbePop : public tut_EnvironAltPop {
+public:
+    GenProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        m_pGenetics = new Genetics<tut_EnvironAltAgent, U>(this, m_pCG, "", m_pAgentController, &m_vMergedDeadList, m_aiSeeds[1]);
+        m_prio.addAction(m_pGenetics);
+    }
+    virtual ~GenProbePop() { delete m_pGenetics; }
+    int makePopSpecificOffspring(int iAgent, int iMother, int iFather) {
+        m_pGenetics->initialize(m_fCurTime);
+        int iResult = m_pGenetics->makeOffspring(iAgent, iMother, iFather);
+        tut_EnvironAltPop::makePopSpecificOffspring(iAgent, iMother, iFather);
+        return iResult;
+    }
+    Genetics<tut_EnvironAltAgent, U> *m_pGenetics;
 };
 
 struct RefSim {
@@ -311,6 +371,10 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_OldAgeDiePop, tut_OldAgeDieAgent>(new tut_OldAgeDiePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltConfPop") {
         s->pa = new PopAccessT<ConfProbePop, tut_EnvironAltAgent>(new ConfProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironAltGenPop") {
+        s->pa = new PopAccessT<GenProbePop<BitGeneUtils>, tut_EnvironAltAgent>(new GenProbePop<BitGeneUtils>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironAltGen2bitPop") {
+        s->pa = new PopAccessT<GenProbePop<GeneUtils>, tut_EnvironAltAgent>(new GenProbePop<GeneUtils>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_ParthenoPop") {
         s->pa = new PopAccessT<tut_ParthenoPop, tut_ParthenoAgent>(new tut_ParthenoPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_StaticPop") {
@@ -442,6 +506,66 @@ long qref_get_agents(void *h, long cap, int *cell, int64_t *id, float *birth, ui
         k++;
     }
     return k;
+}
+
+// ---- genomes of the Genetics probe populations ----
+int qref_genetics_init(void *h, int genomeSize, int numCrossOvers, double mutationRate) {
+    RefSim *s = (RefSim *)h;
+    Quiet q(s->quiet);
+    return s->pa->geneticsInit(genomeSize, numCrossOvers, mutationRate);
+}
+// rows for the agents in slots [firstSlot, firstSlot + n): what readAdditionalDataQDF would load beside the agents
+int qref_set_genomes(void *h, int firstSlot, long n, const uint64_t *rows) {
+    RefSim *s = (RefSim *)h;
+    const int w = s->pa->genomeWords();
+    if (w <= 0) return -1;
+    for (long i = 0; i < n; i++) memcpy(s->pa->genomeRow(firstSlot + (int)i), rows + (size_t)i * w, sizeof(uint64_t) * w);
+    return w;
+}
+// rows of the live agents in slot order (the order of qref_get_agents); returns the words per row
+long qref_get_genomes(void *h, long cap, uint64_t *rows) {
+    RefSim *s = (RefSim *)h;
+    const int w = s->pa->genomeWords();
+    if (w <= 0) return -1;
+    int first = s->pa->first();
+    if (first < 0) return w;
+    long k = 0;
+    for (int i = first; i <= s->pa->last(); i++) {
+        AgentRec a;
+        if (!s->pa->get(i, a)) continue;
+        if (k < cap) memcpy(rows + (size_t)k * w, s->pa->genomeRow(i), sizeof(uint64_t) * w);
+        k++;
+    }
+    return w;
+}
+// state of the Genetics action's generator of thread 0 (built from aiSeeds[1] by WELLUtils::buildWELLs, MD5 of seed phrases)
+int qref_genetics_well(void *h, uint32_t *state16, uint32_t *index) {
+    RefSim *s = (RefSim *)h;
+    WELL512 *w = s->pa->geneticsWell();
+    if (w == NULL) return -1;
+    memcpy(state16, w->getState(), sizeof(uint32_t) * 16);
+    *index = w->getIndex();
+    return 0;
+}
+
+// ---- stand-alone 2-bit genome primitives (genes/GeneUtils.cpp:112-146,184-245,322-362) ----
+int qref_gene2_crossover(const uint32_t *state16, const uint64_t *in, int genome_size, int n_cross, uint64_t *out) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    GeneUtils::crossOver((ulong *)out, (const ulong *)in, genome_size, n_cross, &w);
+    return 0;
+}
+int qref_gene2_freereco(const uint32_t *state16, const uint64_t *in, int n_blocks, uint64_t *out) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    GeneUtils::freeReco((ulong *)out, (ulong *)in, n_blocks, &w);
+    return 0;
+}
+int qref_gene2_mutate(const uint32_t *state16, uint64_t *genome, int n_nucs, int n_mut) {
+    uint32_t tmp[16]; memcpy(tmp, state16, sizeof(tmp));
+    WELL512 w(tmp);
+    GeneUtils::mutateNucs((ulong *)genome, n_nucs, n_mut, &w);
+    return 0;
 }
 
 int qref_get_counts(void *h, uint64_t *out) {

@@ -55,6 +55,14 @@ def lib(adapter: bool = False):
         L.qref_get_capacities.argtypes = [C.c_void_p, C.c_void_p]
         L.qref_set_env.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.qref_event.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+        L.qref_set_genomes.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p]
+        L.qref_get_genomes.restype = C.c_long
+        L.qref_get_genomes.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        L.qref_genetics_well.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qref_genetics_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        for f in ("qref_gene2_crossover", "qref_gene2_freereco", "qref_gene2_mutate"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p] if f == "qref_gene2_crossover" else \
+                ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] if f == "qref_gene2_freereco" else [C.c_void_p, C.c_void_p, C.c_int, C.c_int])
         L.qref_destroy.argtypes = [C.c_void_p]
         L.qref_well_sequence.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.qref_polyline_eval.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -95,6 +103,10 @@ class RefSim:
         alt = np.ascontiguousarray(altitude, dtype=np.float64)
         icea = None if ice is None else np.ascontiguousarray(ice, dtype=np.uint8)
         st = np.ascontiguousarray(DEFAULT_STATE if state16 is None else state16, dtype=np.uint32)
+        gen = params.modules.get("Genetics")
+        if gen is not None:  # the reference cannot take Genetics attributes from XML (see geneticsInit in oracle/ref_driver.cpp)
+            params = params.copy()
+            del params.modules["Genetics"]
         with tempfile.NamedTemporaryFile("w", suffix=".xml", delete=False) as f:
             f.write(params.to_xml())
             path = f.name
@@ -107,6 +119,11 @@ class RefSim:
         if not self.h:
             raise RuntimeError("qref_create failed")
         self.threads = threads
+        if gen is not None:
+            rc = self.L.qref_genetics_init(self.h, int(gen["Genetics_genome_size"]), int(gen["Genetics_num_crossover"]),
+                                           float(gen["Genetics_mutation_rate"]))
+            if rc != 0:
+                raise RuntimeError("Genetics::init failed")
         for k, v in (env or {}).items():
             self.set_env(k, v)
 
@@ -137,6 +154,23 @@ class RefSim:
                 np.ascontiguousarray(pop["life"], np.uint32)]
         rc = self.L.qref_add_agents(self.h, n, *[_p(a) for a in arrs])
         assert rc == 0
+
+    def set_genomes(self, genomes, first_slot=0):
+        """genome rows of the agents in slots first_slot.. (Genetics probe populations; agents are added from slot 0 on)"""
+        g = np.ascontiguousarray(genomes, np.uint64)
+        w = self.L.qref_set_genomes(self.h, int(first_slot), len(g), _p(g))
+        assert w == g.shape[1], (w, g.shape)
+
+    def genomes(self, row_words):
+        n = self.num_agents()
+        g = np.zeros((n, row_words), np.uint64)
+        assert self.L.qref_get_genomes(self.h, n, _p(g)) == row_words
+        return g
+
+    def genetics_well(self):
+        st, idx = np.zeros(16, np.uint32), np.zeros(1, np.uint32)
+        assert self.L.qref_genetics_well(self.h, _p(st), _p(idx)) == 0
+        return st, int(idx[0])
 
     def start(self):
         rc = self.L.qref_start(self.h)

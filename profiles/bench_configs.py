@@ -92,6 +92,25 @@ def main():
                                 workload=f"OoANavGenPop with Navigate (2000 ports x 4 destinations), GEO+CLIMATE+VEG+NAV event every 10 steps "
                                          f"(arrays re-uploaded from the host inside the timed region), {n} agents")
     g.close()
+    # ---- C5'' : the same population, the environment interpolated on the device (AutoInterpolator::interpolate): the
+    # difference arrays are resident, an environment step is three small kernels + the events, no host array traffic
+    g = GpuPopulation.from_params(par5, nbr, alt, state16=seed_state(5), env=env)
+    g.set_navigation(ports, ptr, dests, dist, np.zeros((0, 2), np.int32))
+    g.add_agents(pop); g.set_genomes(gen0); g.pre_loop()
+    g.set_env_delta("Altitude", np.full(len(alt), -5.0))
+    g.set_env_delta("AnnualMeanTemp", np.full(len(alt), -0.5))
+    g.set_env_delta("BaseNPP", -0.02 * env["BaseNPP"])
+
+    def event_dev(t):
+        g.interpolate_env(1)
+        for ev in (2, 3, 4, 5):
+            g.update_event(ev, t)
+        g.flush_events(t)
+
+    out["C5_single_gpu_interpolated"] = dict(timed_steps(g, 20, 3, every=10, event=event_dev),
+                                             workload=f"as C5_single_gpu, the environment changed by qhgb_interpolate_env on the device "
+                                                      f"(resident difference arrays) instead of re-uploaded arrays, {n} agents")
+    g.close()
     print(json.dumps(out))
 
 

@@ -188,6 +188,19 @@ def tut_environ_alt_confined(K: float, x: float, y: float, r_km: float, prio: in
     return par
 
 
+def tut_environ_alt_genetic(K: float, genome_size: int, num_crossover: int, mutation_rate: float, bits_per_nuc: int = 1) -> PopParams:
+    """tut_EnvironAltPop's parameter set plus Genetics (actions/Genetics.cpp) with 1-bit (genes/BitGeneUtils.cpp) or 2-bit
+    (genes/GeneUtils.cpp) nucleotides: the probe classes `tut_EnvironAltGenPop` / `tut_EnvironAltGen2bitPop` of
+    oracle/ref_driver.cpp, the oracle and the CUDA library, which pin the Genetics action against the reference's own."""
+    par = tut_environ_alt(K)
+    par.class_name = "tut_EnvironAltGen2bitPop" if bits_per_nuc == 2 else "tut_EnvironAltGenPop"
+    par.modules["Genetics"] = {"Genetics_genome_size": str(int(genome_size)), "Genetics_num_crossover": str(int(num_crossover)),
+                               "Genetics_mutation_rate": repr(float(mutation_rate)), "Genetics_create_new_genome": "0",
+                               "Genetics_bits_per_nuc": str(int(bits_per_nuc)), "Genetics_initial_muts": "none"}
+    par.prios["Genetics"] = 9
+    return par
+
+
 def ooa_nav_gen(genome_size: int = 4096, num_crossover: int = -1, mutation_rate: float = 1e-5) -> PopParams:
     """`OoANavGenPop` (populations/OoANavGenPop.cpp:33-97) without Navigate: the genetic population of config C3.
     The reference ships no parameter file for it; ecological values follow tut_EnvironCapAlt.xml, the Genetics values are

@@ -358,6 +358,69 @@ def test_genome_primitives_equal_reference():
     assert [O.qor_binomial_get_n(1e-5, 8192, 1e-6, r) for r in (0.5, 0.93, 0.999, 0.9999999)] == [0, 1, 2, 4]
 
 
+@pytest.mark.parametrize("bits", [1, 2])
+@pytest.mark.parametrize("ncross,mut", [(-1, 1e-3), (3, 5e-3), (0, 0.0)])
+def test_genetics_action_equals_reference(bits, ncross, mut):
+    """The Genetics action itself (actions/Genetics.cpp:285-337: strand choice, crossover or free recombination of both
+    parents, mutation count from the binomial table, mutation positions -- all drawn from the action's OWN generator) with
+    1-bit (genes/BitGeneUtils.cpp) and 2-bit (genes/GeneUtils.cpp) nucleotides, pinned against the reference's own
+    Genetics<T,U> added to the reference's tut_EnvironAltPop (GenProbePop<U> in oracle/ref_driver.cpp, called from
+    makePopSpecificOffspring like populations/OoANavGenPop.cpp:231-245): every genome of every live agent, slot for slot."""
+    from qhg4_b200.params import tut_environ_alt_genetic
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    G = 200
+    row = 2 * ((G * bits + 63) // 64)
+    par = tut_environ_alt_genetic(20.0, G, ncross, mut, bits)
+    pop = synthetic_population(8000, alt, seed=6, fertile=True)
+    gen0 = np.random.default_rng(3).integers(0, 2 ** 63, size=(8000, row), dtype=np.int64).astype(np.uint64)
+    st = seed_state(9)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.set_genomes(gen0); o.set_genomes(gen0)
+    o.set_genetics_well(*r.genetics_well())  # built in the reference from aiSeeds[1] through MD5 digests (utils/WELLUtils.cpp:127-148)
+    r.start(); o.start()
+    for k in range(10):
+        r.step(float(k)); o.step(float(k))
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        og, _ = o.genomes(row)
+        assert np.array_equal(r.genomes(row), og), k
+    born = oa["id"] >= 8000
+    assert born.sum() > 1500
+    if ncross == 0 and mut == 0.0:  # whole parental strands are handed down: every strand of a newborn is a founder strand
+        nb = row // 2
+        founders = {bytes(x) for x in gen0.reshape(-1, nb)}
+        assert all(bytes(x) in founders for x in og[born].reshape(-1, nb))
+    r.close()
+
+
+def test_two_bit_genome_primitives_equal_reference():
+    """genes/GeneUtils.cpp crossOver (breaks on nucleotide boundaries), freeReco (doubled mask bits), mutateNucs (XOR with
+    01 / 10 / 11): the oracle's restatement against the reference functions on the same WELL512 stream."""
+    import ctypes as C
+    R, O = refsim.lib(), port.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(0)
+    for trial in range(100):
+        G = int(rng.choice([32, 64, 100, 500, 2048]))
+        nb = (2 * G + 63) // 64
+        gin = rng.integers(0, 2 ** 63, size=2 * nb, dtype=np.int64).astype(np.uint64)
+        st = seed_state(trial + 1)
+        for nc in (1, 2, 3, 7, 20):
+            a, b = np.zeros(2 * nb, np.uint64), np.zeros(2 * nb, np.uint64)
+            R.qref_gene2_crossover(p(st), p(gin), G, nc, p(a)); O.qor_gene2_crossover(p(st), p(gin), G, nc, p(b))
+            assert np.array_equal(a, b), (trial, nc)
+        a, b = np.zeros(2 * nb, np.uint64), np.zeros(2 * nb, np.uint64)
+        R.qref_gene2_freereco(p(st), p(gin), nb, p(a)); O.qor_gene2_freereco(p(st), p(gin), nb, p(b))
+        assert np.array_equal(a, b)
+        a, b = gin.copy(), gin.copy()
+        R.qref_gene2_mutate(p(st), p(a), 2 * G, 6); O.qor_gene2_mutate(p(st), p(b), 2 * G, 6)
+        assert np.array_equal(a, b) and not np.array_equal(a, gin)
+
+
 def test_genetic_population_counter_mode_properties():
     """OoANavGenPop in the oracle: order invariance with genomes, inheritance (every newborn strand is made of parental
     alleles when there is no mutation)."""
