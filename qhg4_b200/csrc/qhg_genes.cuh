@@ -1,6 +1,8 @@
-// qhg_genes.cuh -- genomes on the device: Genetics<.., BitGeneUtils> (actions/Genetics.cpp, genes/BitGeneUtils.cpp).
+// qhg_genes.cuh -- genomes on the device: Genetics<.., BitGeneUtils> and Genetics<.., GeneUtils> (actions/Genetics.cpp,
+// genes/BitGeneUtils.cpp, genes/GeneUtils.cpp).
 //
-// A genome is 2 strands x nBlocks 64-bit words of 1-bit nucleotides.  Genomes live in a pool of fixed-size rows and are
+// A genome is 2 strands x nBlocks 64-bit words of 1-bit or 2-bit nucleotides (GeneParams::bitsPerNuc; the 2-bit variant
+// keeps nucleotides whole: breaks on even bits, doubled mask bits in free recombination, XOR with 01/10/11 as mutation).  Genomes live in a pool of fixed-size rows and are
 // NOT moved when the agents are re-binned: an agent carries a 4-byte handle (row index).  Births take rows from a free
 // stack (rows of last step's dead) or from the never-used tail; deaths push their rows after all births of the step
 // have read their parents.
@@ -20,6 +22,7 @@ struct GeneParams {
     int genomeSize, nBlocks, numCrossOvers, nBino;
     double mutationRate;
     double bino[MAX_BINO];
+    int bitsPerNuc;  // 1: BitGeneUtils, 2: GeneUtils
 };
 
 // genes/BitGeneUtils.cpp:86-106 with the break list in draw order (never sorted in the reference)
@@ -76,8 +79,8 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
             const uint4 df = agent_draws(be.cid, step, 0x02000000u | (1u << 20) | (unsigned)(lane / 4), key);
             const unsigned wm = (lane & 3) == 0 ? dm.x : (lane & 3) == 1 ? dm.y : (lane & 3) == 2 ? dm.z : dm.w;
             const unsigned wf = (lane & 3) == 0 ? df.x : (lane & 3) == 1 ? df.y : (lane & 3) == 2 ? df.z : df.w;
-            brM = u2int(wm, 0, nBits);
-            brF = u2int(wf, 0, nBits);
+            brM = u2int_s(wm, 0, nBits, (unsigned)G.bitsPerNuc);  // wrandi(0, nBits, BITSINNUC), genes/GeneUtils.cpp:191
+            brF = u2int_s(wf, 0, nBits, (unsigned)G.bitsPerNuc);
             sbr[wl][0][lane] = brM;
             sbr[wl][1][lane] = brF;
         }
@@ -97,7 +100,8 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
             unsigned long long t0 = p0, t1 = p1;
             if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
                 const uint4 d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(b / 2), key);
-                const unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
+                unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
+                if (G.bitsPerNuc == 2) { L &= 0x5555555555555555ull; L += L << 1; }  // makeFreeMask, genes/GeneUtils.cpp:322-340
                 t0 = (L & p0) | (~L & p1);
                 t1 = (L & p1) | (~L & p0);
             } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
@@ -123,10 +127,17 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
         __syncwarp();
         // mutateNucs (genes/BitGeneUtils.cpp:57-75): flips commute, one atomic XOR per mutation
         for (int m = lane; m < nMut; m += 32) {
-            const uint4 d = agent_draws(be.cid, step, 0x03000000u | (unsigned)(m / 4), key);
-            const unsigned wv = (m & 3) == 0 ? d.x : (m & 3) == 1 ? d.y : (m & 3) == 2 ? d.z : d.w;
-            const unsigned pos = u2int(wv, 0, 2u * (unsigned)G.genomeSize);
-            atomicXor(&gb[pos >> 6], 1ull << (pos & 63u));
+            if (G.bitsPerNuc == 2) {  // genes/GeneUtils.cpp:112-146: two draws per mutation (position on an even bit, mask 1..3)
+                const uint4 d = agent_draws(be.cid, step, 0x03000000u | (unsigned)(m / 2), key);
+                const unsigned wp = (m & 1) ? d.z : d.x, wk = (m & 1) ? d.w : d.y;
+                const unsigned pos = u2int_s(wp, 0, 4u * (unsigned)G.genomeSize, 2u);
+                atomicXor(&gb[pos >> 6], (unsigned long long)u2int(wk, 1, 4) << (pos & 63u));
+            } else {
+                const uint4 d = agent_draws(be.cid, step, 0x03000000u | (unsigned)(m / 4), key);
+                const unsigned wv = (m & 3) == 0 ? d.x : (m & 3) == 1 ? d.y : (m & 3) == 2 ? d.z : d.w;
+                const unsigned pos = u2int(wv, 0, 2u * (unsigned)G.genomeSize);
+                atomicXor(&gb[pos >> 6], 1ull << (pos & 63u));
+            }
         }
         __syncwarp();
     }

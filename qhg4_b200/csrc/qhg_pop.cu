@@ -972,14 +972,26 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltPref"; ea.trigger = QHGB_EVENT_ID_GEO;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false; en.trigger = QHGB_EVENT_ID_VEG;
         p->subs = {ea, en};
-    } else if (p->popClass == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97
+    } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
+        // tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added: the classes the reference driver
+        // builds to pin the Genetics action (GenProbePop<U>, oracle/ref_driver.cpp)
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"Genetics", A_GENETICS}};
+        p->genetic = true;
+        p->forceGeneric = true;
+        p->gp.bitsPerNuc = (p->popClass == "tut_EnvironAltGen2bitPop") ? 2 : 1;
+    } else if (p->popClass == "OoANavGenPop" || p->popClass == "OoANavGen2bitPop") {
+        // populations/OoANavGenPop.cpp:33-97; populations/OoANavGen2bitPop.cpp is the same class with Genetics<.., GeneUtils>
+        // (2-bit nucleotides, genes/GeneUtils.cpp) and without addObserver(m_pME)
+        p->gp.bitsPerNuc = (p->popClass == "OoANavGen2bitPop") ? 2 : 1;
         p->actions = {{"MultiEvaluator[Alt+NPP]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"GetOld", A_GETOLD}, {"OldAgeDeath", A_OLDAGEDEATH}, {"Fertility", A_FERTILITY},
                       {"NPPCapacity", A_NPPCAP}, {"Genetics", A_GENETICS}, {"Navigate", A_NAVIGATE}};
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltCapPref"; ea.trigger = QHGB_EVENT_ID_GEO;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = true; en.polyName = "NPPPref"; en.trigger = QHGB_EVENT_ID_VEG;
         p->subs = {ea, en};
-        p->multiObserves = true;  // addObserver(m_pME), populations/OoANavGenPop.cpp:59
+        p->multiObserves = (p->gp.bitsPerNuc == 1);  // addObserver(m_pME), populations/OoANavGenPop.cpp:59; not in OoANavGen2bitPop.cpp
         p->genetic = true;
         p->forceGeneric = true;   // births need the identity of the father: the generic path keeps the full pairing
     } else {
@@ -1189,12 +1201,12 @@ int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
     if (!p || !name) return fail("qhgb_set_attribute: NULL argument");
     for (const char *k : kNumericAttrs) {
         if (strcmp(k, name) == 0) {
-            if (strcmp(name, "Genetics_bits_per_nuc") == 0 && (int)value != 1)
-                return fail("[Genetics] This module expects 1 bit nucleotides, but the attribute specifies %d bit nucleotides", (int)value);
+            if (strcmp(name, "Genetics_bits_per_nuc") == 0 && (int)value != std::max(1, p->gp.bitsPerNuc))
+                return fail("[Genetics] This module expects %d bit nucleotides, but the attribute specifies %d bit nucleotides", std::max(1, p->gp.bitsPerNuc), (int)value);
             if (strcmp(name, "Genetics_genome_size") == 0) {
                 if (p->capacity > 0 && p->genetic) return fail("Genetics_genome_size must be set before agents are added");
                 p->gp.genomeSize = (int)value;
-                p->gp.nBlocks = ((int)value + 63) / 64;
+                p->gp.nBlocks = ((int)value * std::max(1, p->gp.bitsPerNuc) + 63) / 64;  // numNucs2Blocks, genes/GeneUtils.h:36
             }
             p->attr[name] = value;
             return 0;

@@ -84,6 +84,14 @@ __device__ __forceinline__ uint32_t u2int(uint32_t x, uint32_t a, uint32_t b) {
     return a + (uint32_t)__dmul_rn(__dmul_rn((double)(b - a), (double)x), 2.3283064365386962890625e-10);
 }
 
+// wrandi(a,b,s): multiples of s, a + s*(uint)((1.0*r*x)/(s*2^32)) with r = b-a rounded up to a multiple of s (s = 1 or 2: the
+// divisor is a power of two, the division exact)
+__device__ __forceinline__ uint32_t u2int_s(uint32_t x, uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r = b - a;
+    r += r % s;
+    return a + s * (uint32_t)__dmul_rn(__dmul_rn((double)r, (double)x), (s == 2) ? 1.16415321826934814453125e-10 : 2.3283064365386962890625e-10);
+}
+
 // atan in double, argument reduction + odd polynomial (the classic fdlibm scheme), written with
 // explicitly rounded operations so that the oracle's counter mode (same operation order on the CPU)
 // gives the identical bits.  |error| < 1 ulp against libm (tests/test_kernels_gpu.py).

@@ -397,6 +397,67 @@ def test_genetics_action_equals_reference(bits, ncross, mut):
     r.close()
 
 
+def _genotype_samples(make_sim, nseeds, nsteps, G, bits, ncross, mut):
+    """per-site allele frequencies, per-agent heterozygosity and per-strand switch counts after nsteps, over nseeds runs"""
+    from qhg4_b200.params import tut_environ_alt_genetic
+    nbr = make_torus_grid(12, 12)
+    alt = np.full(len(nbr), 900.0)
+    par = tut_environ_alt_genetic(20.0, G, ncross, mut, bits)
+    nb = (G * bits + 63) // 64
+    freq, het, sw, tot = [], [], [], []
+    for s in range(nseeds):
+        pop = synthetic_population(2500, alt, seed=70 + s, fertile=True)
+        # founder strands are all-0 or all-1: every switch along a descendant's strand is a recombination break or a mutation
+        hap = np.random.default_rng(900 + s).integers(0, 2, size=(2500, 2), dtype=np.uint64) * np.uint64(0xFFFFFFFFFFFFFFFF)
+        gen0 = np.ascontiguousarray(np.repeat(hap, nb, axis=1))
+        g = make_sim(par, nbr, alt, seed_state(700 + s), pop, gen0)
+        for k in range(nsteps):
+            g.step(float(k))
+        rows = g.genomes(2 * nb)
+        rows = rows[0] if isinstance(rows, tuple) else rows
+        bitsarr = np.unpackbits(rows.view(np.uint8).reshape(len(rows), 2, nb * 8), axis=2, bitorder="little")[:, :, :G * bits]
+        freq.append([bitsarr.mean()])  # one value per run: with two founder haplotypes the sites of a run move together
+        het.append((bitsarr[:, 0, :] != bitsarr[:, 1, :]).sum(axis=1))
+        sw.append((bitsarr[:, :, 1:] != bitsarr[:, :, :-1]).sum(axis=2).ravel())
+        tot.append(len(rows))
+        if hasattr(g, "close"):
+            g.close()
+    return np.concatenate(freq), np.concatenate(het), np.concatenate(sw), np.array(tot)
+
+
+def _ref_sim(threads):
+    def make(par, nbr, alt, st, pop, gen0):
+        r = refsim.RefSim(par, nbr, alt, threads=threads, state16=st)
+        r.add_agents(pop); r.set_genomes(gen0); r.start()
+        return r
+    return make
+
+
+def _oracle_sim(par, nbr, alt, st, pop, gen0):
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st)
+    o.add_agents(pop); o.set_genomes(gen0); o.start()
+    return o
+
+
+@pytest.mark.parametrize("bits,ncross", [(1, -1), (2, 2)])
+def test_genotype_distributions_statistically_equivalent_to_reference(bits, ncross):
+    """Genotype side of the north-star's statistical gate: the counter-mode law (other random streams for strand choice,
+    recombination and mutation; key-rank pairing decides who the father is) against the reference's Genetics with two
+    threads -- the allele frequency of every run after 25 steps of drift, per-agent heterozygosity, and the number of switches along
+    a strand (founder strands are all-0 or all-1, so switches count recombination breaks and mutations), two-sample KS,
+    p > 0.01.  The switch statistic does tell laws apart: another crossover count or mutation rate fails it."""
+    from scipy import stats
+    G = 96
+    fo, ho, so, to = _genotype_samples(_oracle_sim, 12, 25, G, bits, ncross, 2e-3)
+    fr, hr, sr, tr = _genotype_samples(_ref_sim(2), 12, 25, G, bits, ncross, 2e-3)
+    ps = [stats.ks_2samp(fo, fr).pvalue, stats.ks_2samp(ho[::5], hr[::5]).pvalue, stats.ks_2samp(so[::11], sr[::11]).pvalue,
+          stats.ks_2samp(to, tr).pvalue]
+    assert min(ps) > 0.01, ps
+    assert fo.std() > 0.002 and so.mean() > 1.0  # drift and recombination happened
+    _, _, sx, _ = _genotype_samples(_oracle_sim, 12, 25, G, bits, ncross, 8e-3)  # four times the mutation rate: detected
+    assert stats.ks_2samp(sx[::11], sr[::11]).pvalue < 0.01
+
+
 def test_two_bit_genome_primitives_equal_reference():
     """genes/GeneUtils.cpp crossOver (breaks on nucleotide boundaries), freeReco (doubled mask bits), mutateNucs (XOR with
     01 / 10 / 11): the oracle's restatement against the reference functions on the same WELL512 stream."""

@@ -236,6 +236,33 @@ def test_statistical_equivalence_vs_reference():
     assert p_tot > 0.01 and p_age > 0.01 and p_occ > 0.01, (p_tot, p_age, p_occ)
 
 
+@pytest.mark.parametrize("bits,ncross", [(1, -1), (2, 2)])
+def test_genotype_distributions_statistically_equivalent_to_reference(bits, ncross):
+    """Genotype side of the statistical gate, device against the reference's own Genetics<T,U> (two threads) over 32 seeds:
+    allele frequency per run, per-agent heterozygosity, switches along a strand (recombination breaks + mutations; founder
+    strands are all-0 / all-1), population size -- two-sample KS, p > 0.01.  Same statistics as the CPU test of the oracle's
+    counter mode (tests/test_oracle_vs_ref.py), which also shows that a wrong mutation rate fails them."""
+    from scipy import stats
+    from oracle import refsim
+    if not refsim.available():
+        pytest.skip("oracle/_ref not built")
+    from test_oracle_vs_ref import _genotype_samples, _ref_sim
+    from qhg4_b200.population import GpuPopulation
+
+    def gpu_sim(par, nbr, alt, st, pop, gen0):
+        g = GpuPopulation.from_params(par, nbr, alt, state16=st)
+        g.add_agents(pop); g.set_genomes(gen0); g.pre_loop()
+        return g
+
+    G = 96
+    fg, hg, sg, tg = _genotype_samples(gpu_sim, 32, 25, G, bits, ncross, 2e-3)
+    fr, hr, sr, tr = _genotype_samples(_ref_sim(2), 32, 25, G, bits, ncross, 2e-3)
+    ps = [stats.ks_2samp(fg, fr).pvalue, stats.ks_2samp(hg[::13], hr[::13]).pvalue, stats.ks_2samp(sg[::29], sr[::29]).pvalue,
+          stats.ks_2samp(tg, tr).pvalue]
+    assert min(ps) > 0.01, ps
+    assert sg.mean() > 1.0
+
+
 @pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
 def test_two_gpu_shards_equal_unsharded_oracle(exchange):
     """cell-range sharding on 2 GPUs, migration over peer memory (default) and over NCCL calls: bit-identical to the
@@ -343,6 +370,47 @@ def test_genetic_population_bit_exact_vs_oracle(ncross, mut):
     gg, _ = g.genomes(row)
     founders = ga["id"] < len(pop["id"])
     assert np.array_equal(gg[founders], gen0[ga["id"][founders]])
+
+
+@pytest.mark.parametrize("cls,bits", [("OoANavGen2bitPop", 2), ("tut_EnvironAltGen2bitPop", 2), ("tut_EnvironAltGenPop", 1)])
+@pytest.mark.parametrize("ncross,mut", [(-1, 2e-3), (3, 5e-3)])
+def test_two_bit_genomes_and_genetics_probe_classes_bit_exact_vs_oracle(cls, bits, ncross, mut):
+    """Genetics<.., GeneUtils> (2-bit nucleotides, genes/GeneUtils.cpp: breaks on nucleotide boundaries, doubled mask bits,
+    mutation = XOR with 01/10/11) in OoANavGen2bitPop (populations/OoANavGen2bitPop.cpp) and in the probe classes
+    tut_EnvironAlt + Genetics, whose oracle WELL mode equals the reference's own Genetics<T,U> genome for genome
+    (tests/test_oracle_vs_ref.py::test_genetics_action_equals_reference): agents and genomes against the counter mode."""
+    from oracle import port
+    from qhg4_b200.params import ooa_nav_gen, tut_environ_alt_genetic
+    from qhg4_b200.population import GpuPopulation
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    G = 200
+    if cls == "OoANavGen2bitPop":
+        par = ooa_nav_gen(G, ncross, mut)
+        par.class_name = cls
+        par.modules["Genetics"]["Genetics_bits_per_nuc"] = "2"
+    else:
+        par, env = tut_environ_alt_genetic(20.0, G, ncross, mut, bits), None
+    st = seed_state(37)
+    row = 2 * ((G * bits + 63) // 64)
+    gen0 = np.random.default_rng(1).integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    g.add_agents(pop); o.add_agents(pop)
+    g.set_genomes(gen0); o.set_genomes(gen0)
+    g.pre_loop(); o.start()
+    births = 0
+    for k in range(10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        births += g.step_stats().births
+        ga, oa = g.agents(), o.agents()
+        gg, _ = g.genomes(row)
+        og, _ = o.genomes(row)
+        assert np.array_equal(gg[np.argsort(ga["id"])], og[np.argsort(oa["id"])]), f"step {k}: genomes differ"
+    assert births > 1500
+    with pytest.raises(Exception):  # the nucleotide width belongs to the class (actions/Genetics.cpp:204,259)
+        GpuPopulation.from_params(par, nbr, alt, state16=st, env=env).modify_attributes("Genetics_bits_per_nuc", 3 - bits)
 
 
 def test_navigate_sea_crossings_bit_exact_vs_oracle():
