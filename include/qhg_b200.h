@@ -141,6 +141,9 @@ int  qhgb_finalize_step(qhgb_pop *p);
 int  qhgb_step(qhgb_pop *p, float t);
 /* n steps at t0, t0+1, ... without returning to the host in between (the bench's device-resident loop) */
 int  qhgb_run(qhgb_pop *p, float t0, int n_steps);
+/* sums over all completed steps since preLoop: live agents at step start (the "agent-steps" of a throughput figure), agents
+ * sent to / received from other ranks; any pointer may be NULL */
+int  qhgb_get_run_totals(qhgb_pop *p, int64_t *agent_steps, int64_t *sent, int64_t *received);
 int  qhgb_synchronize(qhgb_pop *p);
 
 /* updateEvent(id, data, t) / flushEvents(t) (populations/tut_EnvironAltPop.cpp:93-127) */

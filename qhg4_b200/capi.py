@@ -46,6 +46,7 @@ SYMBOLS = {
     "qhgb_finalize_step": (i32, [vp]),
     "qhgb_step": (i32, [vp, f32]),
     "qhgb_run": (i32, [vp, f32, i32]),
+    "qhgb_get_run_totals": (i32, [vp, vp, vp, vp]),
     "qhgb_synchronize": (i32, [vp]),
     "qhgb_update_event": (i32, [vp, i32, f32]),
     "qhgb_flush_events": (i32, [vp, f32]),
@@ -85,6 +86,8 @@ def load():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m qhg4_b200.build` (or __graft_entry__.build())")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("QHG_AB_OLD_LIB") and not hasattr(L, name):
+                continue  # profiles/try_libs.sh only: A/B runs of the bench over libraries built from older commits
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

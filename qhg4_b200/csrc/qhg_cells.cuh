@@ -26,7 +26,14 @@
 
 namespace qhg {
 
-constexpr int CW = 4;            // warps per CTA
+constexpr int CW = 4;            // warps per CTA (scatter pass)
+#ifndef QHG_DCW
+#define QHG_DCW 4
+#endif
+constexpr int DCW = QHG_DCW;     // warps per CTA in the decide pass (1: the per-warp shared-memory slice has a compile-time address)
+#ifndef QHG_BATCH_FETCH
+#define QHG_BATCH_FETCH 0
+#endif
 constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles; larger ones -> generic path
 #ifndef QHG_MAXF
 #define QHG_MAXF 512
@@ -103,18 +110,20 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 #define QHG_PF2 0
 #endif
 #ifndef QHG_DECIDE_MINB
-#define QHG_DECIDE_MINB 8
+#define QHG_DECIDE_MINB (32 / QHG_DCW)
 #endif
+constexpr int DECIDE_CTAS_PER_SM = QHG_DECIDE_MINB;
 template <bool SPEC>
-__global__ void __launch_bounds__(CW * 32, QHG_DECIDE_MINB)
+__global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
               int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
               int *__restrict__ moveBase) {
-    __shared__ WarpSmem smem[CW];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ WarpSmem smem[DCW];
+    const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
     WarpSmem &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
+    if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it
     const unsigned step = st->step;
     const unsigned long long prog = SPEC ? PROG_TUT5 : P.prog;
     const int nOps = SPEC ? 5 : P.nOps;
@@ -145,6 +154,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
     const int bc = lane >> 3, bk = lane & 7;
     int csL = 0, nnL = 0, nbL = -1;
     double wL = 0.0, bL = 0.0, dL = 0.0;
+#if QHG_BATCH_FETCH
     if (lane <= nB) csL = cellStart[cBase + lane];
     if (lane < nB) {
         nnL = E.nNbr[cBase + lane];
@@ -154,9 +164,14 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         if (bk < WSTRIDE) wL = E.W[(size_t)(cBase + bc) * WSTRIDE + bk];
         if (bk < MAXN) nbL = E.nbr[(size_t)(cBase + bc) * MAXN + bk];
     }
+#endif
     for (int ci = 0; ci < nB; ci++) {
         const int c = cBase + ci;
+#if QHG_BATCH_FETCH
         const int s = __shfl_sync(FULL, csL, ci), n = __shfl_sync(FULL, csL, ci + 1) - s;
+#else
+        const int s = cellStart[c], n = cellStart[c + 1] - s;
+#endif
         if (n == 0) continue;
         if (n > WCAP) {
             if (lane == 0) atomicExch(&st->oversize, 1);
@@ -165,6 +180,7 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         // the cell's bytes sit at dec[gOff + j]: shared-memory word k then is the aligned global word of dec[] it is stored to
         const int gOff = s & 3;
         uint8_t *const sdec = S.dec + gOff;
+#if QHG_BATCH_FETCH
         {
             const double rv = __shfl_sync(FULL, wL, ci * 8 + bk);
             const int nv = __shfl_sync(FULL, nbL, ci * 8 + bk);
@@ -174,12 +190,24 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 S.nbrC[lane] = nv;
             }
         }
+#else
+        if (lane < 8) {
+            S.outC[lane] = 0;
+            S.row[lane] = (lane < WSTRIDE) ? E.W[(size_t)c * WSTRIDE + lane] : 0.0;
+            S.nbrC[lane] = (lane < MAXN) ? E.nbr[(size_t)c * MAXN + lane] : -1;
+        }
+#endif
         int nF = 0, nM = 0, nqa = 0, nqm = 0;
         int confL = 0;  // moves of this lane that ConfinedMove turned back (they stay in the move list: counted, core/SPopulation.cpp:1067)
         bool tooMany = false;
+#if QHG_BATCH_FETCH
         const int nreal = __shfl_sync(FULL, nnL, ci);
-        const double *row = S.row;
         const double bC = __shfl_sync(FULL, bL, ci), dC = __shfl_sync(FULL, dL, ci);
+#else
+        const int nreal = E.nNbr[c];
+        const double bC = I.hasVerhulst ? E.B[c] : 0.0, dC = I.hasVerhulst ? E.D[c] : 0.0;
+#endif
+        const double *row = S.row;
         // the probability tests of LinearBirth / LinearDeath as exact integer thresholds on the 32-bit draws
         const unsigned long long tBirth = prob_threshold(bC), tBirthNeg = prob_threshold(-bC), tDeath = prob_threshold(dC);
         auto flush_atan = [&]() {  // ATanDeath::execute, actions/ATanDeath.cpp:75-83, for the queued agents
@@ -646,7 +674,7 @@ __global__ void k_halo_merge(int nHalo, const int *__restrict__ halo, int c0, in
 __global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable *__restrict__ T, int rank, int recvCap, AgentArrays o,
                                      const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ cursor,
                                      int storeAge) {
-    if (st->overflow || st->oversize) return;
+    if (st->overflow || st->oversize || st->halt) return;
     const int n = T->x[rank]->recvCount;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->nRecv = n;
@@ -754,7 +782,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
     __shared__ WarpSmemS smem[CW];
-    if (st->overflow || st->oversize) return;
+    if (st->overflow || st->oversize || st->halt) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpSmemS &S = smem[wid];
     const unsigned FULL = 0xffffffffu;

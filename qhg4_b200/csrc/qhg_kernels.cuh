@@ -68,6 +68,13 @@ struct DevStats {
     int nSent, nRecv;             // agents that left for / arrived from other ranks in the running step
     long long birthOffset;        // births of the lower ranks this step (newborn ids are global ranks)
     long long globalBirths;       // births of all ranks this step
+    // several steps queued without a host round trip (qhgb_run): a step that cannot complete on the fast path (overflow,
+    // oversize cell) raises `halt`; every kernel of the later steps then does nothing, and the host, when it finally looks,
+    // finds the state as it was before that step (`step` tells which one) and redoes it the slow way
+    int halt;
+    int pad0;
+    long long agentSteps;         // sum over the completed steps of the live agents at step start
+    long long totSent, totRecv;   // agents sent to / received from other ranks, summed over the completed steps
 };
 
 struct ActParams {
@@ -136,6 +143,7 @@ __global__ void k_cell_init(DevStats *__restrict__ st, int cLo, int cHi, const i
                             double b0, double d0, double theta, double K, const double *__restrict__ Kcell, int doVerhulst,
                             int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
                             int *__restrict__ birthCount, int *__restrict__ nFert) {
+    if (st->halt) return;  // an earlier queued step failed: leave everything as it is
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the step's tallies and work counters start from zero
         st->nBirths = 0;
         st->nDeaths = 0;
@@ -587,6 +595,7 @@ k_scan_apply(int cA, int cHi, int nTiles, const int *__restrict__ stay, const in
              int *__restrict__ count, DevStats *__restrict__ st, int capacity) {
     __shared__ int sa[8], sb[8];
     __shared__ int baseA, baseB;
+    if (st->halt) return;  // an earlier queued step failed: the other buffer's cell starts are the valid ones, keep them
     // sum of the tiles before this one
     int pa = 0, pb = 0;
     for (int k = threadIdx.x; k < (int)blockIdx.x; k += 256) { int2 v = tileSums[k]; pa += v.x; pb += v.y; }
@@ -692,7 +701,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
 }
 
 __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) {
-    if (st->overflow || st->oversize) return;
+    if (st->overflow || st->oversize || st->halt) { st->halt = 1; return; }
+    if (advanceStep) { st->agentSteps += st->nAgents; st->totSent += st->nSent; st->totRecv += st->nRecv; }
     st->nAgents = st->nNew;
     // globalBirths: -1 single GPU, -2 the sum the ranks exchanged on the device (st->globalBirths), else the sum from the host
     st->nextID += (globalBirths >= 0) ? globalBirths : (globalBirths == -2 ? st->globalBirths : (long long)st->nBirths);
@@ -703,6 +713,13 @@ __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths
 __global__ void k_counts_u64(int nCells, int cLo, int cHi, const int *__restrict__ count, unsigned long long *__restrict__ out) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x)
         out[c] = (c >= cLo && c < cHi) ? (unsigned long long)count[c] : 0ull;
+}
+
+// the host has seen the failed step and is about to redo it (or to retry on the generic path)
+__global__ void k_clear_halt(DevStats *st) {
+    st->halt = 0;
+    st->overflow = 0;
+    st->oversize = 0;
 }
 
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {

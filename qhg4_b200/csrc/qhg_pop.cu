@@ -133,7 +133,11 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
         if (e != cudaSuccess) return e;
-        return cudaMemset(p, 0, count * sizeof(T));  // per-cell counters of cells another rank owns are never touched again
+        // per-cell counters of cells another rank owns are never touched again.  The zeroing runs on the default stream, which
+        // the populations' non-blocking streams do not wait for: it must have finished before anybody uses the buffer
+        e = cudaMemset(p, 0, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(0);
     }
     void release() {
         if (p) cudaFree(p);
@@ -241,6 +245,7 @@ struct qhgb_pop {
     DevBuf<Migrant> sendBuf, recvBuf;
     int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
     int64_t lastSent = 0, lastReceived = 0;
+    int64_t agentSteps = 0, totSent = 0, totRecv = 0;  // host mirrors of the device-side sums (DevStats)
     // exchange over peer memory (qhgb_comm_p2p_handle / qhgb_comm_p2p_connect)
     bool p2p = false;
     int *arriveRemote = nullptr;     // [2][nCells], written by the peers
@@ -406,6 +411,7 @@ int pushStats(qhgb_pop *p) {
     s.nAgents = (int)p->nAgents;
     s.nextID = p->nextID;
     s.step = (unsigned)p->stepsDone;
+    s.agentSteps = p->agentSteps; s.totSent = p->totSent; s.totRecv = p->totRecv;
     CK(cudaMemcpyAsync(p->dstats.p, &s, sizeof(s), cudaMemcpyHostToDevice, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
@@ -755,7 +761,7 @@ int launchScan(qhgb_pop *p) {
 // program, generic path) to bin freshly uploaded agents by cell.
 //   tiled   = the fast path (qhg_cells.cuh, one warp per cell): needs the current buffer binned by cell
 //   generic = one thread per agent, global atomics; any order of the input, any cell size
-int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, bool doPair) {
+int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, bool doPair, bool defer = false) {
     qhgb_pop &q = *p;
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
@@ -767,12 +773,12 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     if (q.timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, q.stream); }
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
-            const int gridC = q.numSMs * 8;  // persistent: 8 CTAs of 4 warps per SM, one warp per cell at a time
+            const int gridC = q.numSMs * DECIDE_CTAS_PER_SM;  // persistent: 32 warps per SM, one warp per cell at a time
             if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
-                LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             } else {
-                LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, CW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                LAUNCH(p, "k_cell_decide_generic", k_cell_decide<false>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             }
             ShardArgs H{};
@@ -877,6 +883,13 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
         CK(cudaGetLastError());
         if (q.timing && attempt == 0) { cudaEventRecord(t1, q.stream); q.kt("pipeline_total").pending.push_back({t0, t1}); }
+        if (defer && tiled) {  // qhgb_run: the host does not wait for the step; the device raises `halt` if it could not complete
+            q.tiledSteps++;
+            q.cellValid = false;
+            q.cur ^= 1;
+            q.pairingValid = false;
+            return 0;
+        }
         if (pullStats(p) != 0) return -1;
         if (q.hstats->commError == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
         if (q.hstats->commError == 2) return fail("receive buffer too small for the migrants of one step (%d > %d)", q.hstats->nRecv, q.recvCap);
@@ -884,6 +897,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
             if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
             tiled = false;
+            LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
             if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
             continue;
         }
@@ -891,10 +905,14 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         q.cellValid = !tiled;
         break;
     }
-    if (q.hstats->overflow) return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
+    if (q.hstats->overflow) {
+        LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);  // the step did not happen; the population is as it was
+        return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
+    }
     q.cur ^= 1;
     q.nAgents = q.hstats->nAgents;
     q.nextID = q.hstats->nextID;
+    q.agentSteps = q.hstats->agentSteps; q.totSent = q.hstats->totSent; q.totRecv = q.hstats->totRecv;
     q.lastBirths = q.hstats->nBirths;
     q.lastDeaths = q.hstats->nDeaths;
     q.lastMoves = q.hstats->nMoves;
@@ -1426,7 +1444,10 @@ int qhgb_do_actions(qhgb_pop *p, unsigned prio, float t) {
     return 0;
 }
 
-int qhgb_finalize_step(qhgb_pop *p) {
+static int finalizeStepImpl(qhgb_pop *p, bool defer);
+int qhgb_finalize_step(qhgb_pop *p) { return finalizeStepImpl(p, false); }
+
+static int finalizeStepImpl(qhgb_pop *p, bool defer) {
     if (!p) return fail("qhgb_finalize_step: NULL population");
     if (!p->inStep) return fail("qhgb_finalize_step: initializeStep has not run");
     CK(cudaSetDevice(p->device));
@@ -1439,7 +1460,7 @@ int qhgb_finalize_step(qhgb_pop *p) {
     HostAction *ev = q.find("SingleEvaluator[Alt]");
     if (ev && ev->prio >= 0 && ev->enabled) q.evalNeedUpdate = false;  // SingleEvaluator::finalize, :125-130
     if (q.active(A_MULTIEVAL)) for (auto &e : q.subs) e.needUpdate = false;  // MultiEvaluator::finalize, actions/MultiEvaluator.cpp:189-195
-    int rc = runPipeline(p, P, true, true, q.needPair);
+    int rc = runPipeline(p, P, true, true, q.needPair, defer);
     q.inStep = false;
     if (rc != 0) return rc;
     q.stepsDone++;
@@ -1447,7 +1468,10 @@ int qhgb_finalize_step(qhgb_pop *p) {
     return 0;
 }
 
-int qhgb_step(qhgb_pop *p, float t) {
+static int stepImpl(qhgb_pop *p, float t, bool defer);
+int qhgb_step(qhgb_pop *p, float t) { return stepImpl(p, t, false); }
+
+static int stepImpl(qhgb_pop *p, float t, bool defer) {
     if (!p) return fail("qhgb_step: NULL population");
     int rc = qhgb_initialize_step(p, t);
     if (rc != 0) return rc;
@@ -1456,14 +1480,89 @@ int qhgb_step(qhgb_pop *p, float t) {
     std::sort(lv.begin(), lv.end());
     lv.erase(std::unique(lv.begin(), lv.end()), lv.end());
     for (unsigned l : lv) rc += qhgb_do_actions(p, l, t);
-    rc += qhgb_finalize_step(p);
+    rc += finalizeStepImpl(p, defer);
     return rc;
 }
 
+// can the steps of a run be queued without waiting for each one?  Only the fast path (its grids do not depend on the
+// population size), and not the NCCL exchange (the host sizes its messages in every step)
+static bool canDefer(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    const char *e = getenv("QHG_RUN_SYNC");
+    if (e && *e && *e != '0') return false;
+    if (q.forceGeneric || q.genetic || q.nAgents <= 0 || !q.preLooped) return false;
+    if (q.sharded && !q.p2p) return false;
+    if (q.active(A_NAVIGATE)) return false;
+    return true;
+}
+
+// n steps at t0, t0+1, ...  The steps are queued on the stream in windows of up to 64 without a host round trip in between;
+// the host looks at the device's counters once per window.  A step the fast path cannot complete (a cell too large for it,
+// agent buffers too small) raises DevStats::halt on the device, the queued steps after it do nothing, and the host redoes that
+// step the way qhgb_step would have done it (generic path, larger buffers) and carries on.  The results are those of n
+// qhgb_step calls.
 int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
-    int rc = 0;
-    for (int k = 0; k < n_steps && rc == 0; k++) rc = qhgb_step(p, t0 + k);
+    if (!p) return fail("qhgb_run: NULL population");
+    CK(cudaSetDevice(p->device));
+    qhgb_pop &q = *p;
+    int k = 0, rc = 0;
+    while (k < n_steps && rc == 0) {
+        if (n_steps - k < 2 || !canDefer(p)) {
+            rc = qhgb_step(p, t0 + k);
+            k++;
+            continue;
+        }
+        const int W = std::min(n_steps - k, 64);
+        const int cur0 = q.cur;
+        const int64_t steps0 = q.stepsDone, tiled0 = q.tiledSteps;
+        const bool ageValid0 = q.ageValid, cellValid0 = q.cellValid;
+        const float lastAge0 = q.lastAgeTime;
+        const ActParams P0 = buildProgram(p, nullptr, 0);
+        const bool needAge = programNeedsStoredAge(P0);
+        int w = 0;
+        for (; w < W && rc == 0; w++) rc = stepImpl(p, t0 + k + w, true);
+        const int hostErr = rc;
+        if (pullStats(p) != 0) return -1;
+        if (q.hstats->commError == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
+        if (q.hstats->commError == 2) return fail("receive buffer too small for the migrants of one step (%d > %d)", q.hstats->nRecv, q.recvCap);
+        const int ok = (int)(q.hstats->step - (unsigned)steps0);  // steps of this window the device completed
+        q.nAgents = q.hstats->nAgents;
+        q.nextID = q.hstats->nextID;
+        q.agentSteps = q.hstats->agentSteps; q.totSent = q.hstats->totSent; q.totRecv = q.hstats->totRecv;
+        q.lastBirths = q.hstats->nBirths; q.lastDeaths = q.hstats->nDeaths; q.lastMoves = q.hstats->nMoves;
+        if (q.sharded) { q.lastSent = q.hstats->nSent; q.lastReceived = q.hstats->nRecv; }
+        if (!q.hstats->halt) {
+            if (hostErr != 0) return hostErr;
+            k += w;
+            continue;
+        }
+        // step `ok` of the window failed on the device: the host state goes back to where that step starts
+        if (q.sharded) return fail("a step of a sharded run could not complete on the fast path (%s)", q.hstats->overflow ? "agent buffers too small" : "cell too large");
+        q.cur = cur0 ^ (ok & 1);
+        q.stepsDone = steps0 + ok;
+        q.tiledSteps = tiled0 + ok;
+        q.cellValid = ok ? false : cellValid0;
+        if (!needAge && ok > 0) { q.ageValid = false; q.lastAgeTime = t0 + k + ok - 1; }
+        else { q.ageValid = needAge ? true : ageValid0; q.lastAgeTime = lastAge0; }
+        q.inStep = false;
+        q.pairingValid = false;
+        const bool overflow = q.hstats->overflow != 0;
+        const int64_t needed = q.hstats->nNew;
+        LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
+        CK(cudaGetLastError());
+        if (overflow && ensureCapacity(p, needed + needed / 2 + 1024) != 0) return -1;
+        rc = qhgb_step(p, t0 + k + ok);
+        k += ok + 1;
+    }
     return rc;
+}
+
+int qhgb_get_run_totals(qhgb_pop *p, int64_t *agent_steps, int64_t *sent, int64_t *received) {
+    if (!p) return fail("qhgb_get_run_totals: NULL population");
+    if (agent_steps) *agent_steps = p->agentSteps;
+    if (sent) *sent = p->totSent;
+    if (received) *received = p->totRecv;
+    return 0;
 }
 
 int qhgb_synchronize(qhgb_pop *p) {

@@ -145,7 +145,14 @@ class GpuPopulation:
         check(self.L.qhgb_step(self.h, float(t)), "qhgb_step")
 
     def run(self, t0: float, nsteps: int):
+        """nsteps steps queued on the device without a host round trip per step (same results as nsteps step() calls)"""
         check(self.L.qhgb_run(self.h, float(t0), int(nsteps)), "qhgb_run")
+
+    def run_totals(self):
+        """(agent-steps, agents sent, agents received) summed over all completed steps since pre_loop"""
+        a, s, r = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(self.L.qhgb_get_run_totals(self.h, C.byref(a), C.byref(s), C.byref(r)), "qhgb_get_run_totals")
+        return a.value, s.value, r.value
 
     def synchronize(self):
         check(self.L.qhgb_synchronize(self.h), "qhgb_synchronize")

@@ -172,6 +172,58 @@ def test_crowded_cells_fall_back_to_generic_path():
         assert_same_population(g, o, k)
 
 
+def test_run_queues_steps_without_host_round_trips(small_world):
+    """qhgb_run queues its steps on the stream and looks at the device's counters once per window: same agents, counts and
+    per-step totals as the same number of qhgb_step calls and as the oracle; the device-side agent-step sum is exact."""
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(40000, alt, seed=5, fertile=True)
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=11)
+    g2, _ = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=11)
+    expect = 0
+    for k in range(13):
+        expect += o.num_agents()
+        o.step(float(k)); g2.step(float(k))
+    g.run(0.0, 13)
+    assert_same_population(g, o, 12)
+    s, s2 = g.step_stats(), g2.step_stats()
+    assert (s.births, s.deaths, s.moves) == o.step_stats() == (s2.births, s2.deaths, s2.moves)
+    assert (s.next_id, s.steps_done) == (s2.next_id, s2.steps_done) == (s2.next_id, 13)
+    assert g.run_totals()[0] == expect == g2.run_totals()[0]
+    g.step(13.0); o.step(13.0)          # and a plain step after a queued run
+    assert_same_population(g, o, 13)
+    g.run(14.0, 1); o.step(14.0)
+    assert_same_population(g, o, 14)
+
+
+def test_run_recovers_when_a_queued_step_cannot_complete():
+    """A queued step that the fast path cannot finish raises a flag on the device, the steps queued after it do nothing, and
+    the host redoes it the way qhgb_step would: (a) cells growing past the fast path's 1024 agents -> generic path,
+    (b) births outgrowing the agent buffers -> larger buffers.  Results stay those of the oracle."""
+    nbr, xyz = make_ico_grid(3)
+    alt = np.full(len(nbr), 800.0)
+    pop = synthetic_population(5400, alt, seed=3, cells=np.array([5, 6, 7, 40, 41, 100]), fertile=True)  # 900 per cell, growing
+    g, o = make_pair(tut_environ_alt(9000.0), nbr, alt, pop, seed=8)
+    g.run(0.0, 7)
+    for k in range(7):
+        o.step(float(k))
+    assert_same_population(g, o, 6)
+    assert g.counts().max() > 1024 and g.run_totals()[0] > 7 * 5400
+    nbr, xyz = make_ico_grid(7)
+    alt = np.full(len(nbr), 800.0)
+    pop = synthetic_population(30000, alt, seed=4, fertile=True)                                   # ~47 per cell, +15 % per step
+    from qhg4_b200.population import GpuPopulation
+    from oracle import port
+    st = seed_state(5)
+    g = GpuPopulation.from_params(tut_environ_alt(9000.0), nbr, alt, state16=st, capacity_hint=40000)
+    o = port.OraclePop(tut_environ_alt(9000.0), nbr, alt, mode=port.MODE_COUNTER, state16=st)
+    g.add_agents(pop); o.add_agents(pop); g.pre_loop(); o.start()
+    g.run(0.0, 9)
+    for k in range(9):
+        o.step(float(k))
+    assert_same_population(g, o, 8)
+    assert g.num_agents() > 60000
+
+
 def test_dense_and_sparse_cells_mix():
     """tile boundaries: dense cells next to long runs of empty cells, tiles of very different cell counts"""
     nbr, xyz = make_ico_grid(31)
