@@ -2,7 +2,7 @@
 # A/B of compile-time knobs / older commits: run the bench with every library variant under build/libs (C4 twice, C2 once)
 cp qhg4_b200/libqhg_b200.so /tmp/lib_keep.so
 show='import sys,json; d=json.loads(sys.stdin.read()); print("%.4g" % d["value"], "%.4f ms" % d["ms_per_step"], "frac %.3f" % d["roofline"]["frac"], {k: v for k, v in d["roofline"]["kernels_ms_per_step"].items() if v > 0.05})'
-for rep in 1 2; do
+for rep in 1; do
 for f in build/libs/*.so; do
   cp "$f" qhg4_b200/libqhg_b200.so
   echo "== C4 $f"

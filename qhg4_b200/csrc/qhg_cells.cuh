@@ -34,6 +34,9 @@ constexpr int DCW = QHG_DCW;     // warps per CTA in the decide pass (1: the per
 #ifndef QHG_BATCH_FETCH
 #define QHG_BATCH_FETCH 0
 #endif
+#ifndef QHG_PRETHRESH
+#define QHG_PRETHRESH 1   // LinearBirth / LinearDeath thresholds come precomputed per cell from k_cell_init
+#endif
 constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles; larger ones -> generic path
 #ifndef QHG_MAXF
 #define QHG_MAXF 512
@@ -205,11 +208,21 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         const double bC = __shfl_sync(FULL, bL, ci), dC = __shfl_sync(FULL, dL, ci);
 #else
         const int nreal = E.nNbr[c];
+#if !QHG_PRETHRESH
         const double bC = I.hasVerhulst ? E.B[c] : 0.0, dC = I.hasVerhulst ? E.D[c] : 0.0;
+#endif
 #endif
         const double *row = S.row;
         // the probability tests of LinearBirth / LinearDeath as exact integer thresholds on the 32-bit draws
+#if QHG_PRETHRESH && !QHG_BATCH_FETCH
+        const unsigned long long tbw = I.hasVerhulst ? E.TB[c] : 0ull;
+        const unsigned long long tDeath = I.hasVerhulst ? E.TD[c] : 0ull;
+        const bool bPos = (tbw >> 62) & 1ull, bNeg = (tbw >> 63) != 0;
+        const unsigned long long tBirth = tbw & 0x1ffffffffull, tBirthNeg = tBirth;
+#else
         const unsigned long long tBirth = prob_threshold(bC), tBirthNeg = prob_threshold(-bC), tDeath = prob_threshold(dC);
+        const bool bPos = bC > 0, bNeg = bC < 0;
+#endif
         auto flush_atan = [&]() {  // ATanDeath::execute, actions/ATanDeath.cpp:75-83, for the queued agents
             for (int e = lane; e < nqa; e += 32) {
                 const double x = __dmul_rn(P.atanSlope, __dadd_rn((double)S.qaAge[e], -P.atanMaxAge));
@@ -350,12 +363,12 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                             else fert = ag > fertMin;
                             f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
                         } else if (op == OP_VERHULST) {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
-                            if (bC > 0) {
+                            if (bPos) {
                                 // a birth needs a mate (LinearBirth.cpp:142); whether this fertile female got one is settled
                                 // once the whole cell has been seen: she is a candidate until then
                                 const bool mayBear = selfMate ? !(f0[u] & F_MALE) : ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE);
                                 if (mayBear && (unsigned long long)r0[u].z < tBirth) cand = true;
-                            } else if (bC < 0) {
+                            } else if (bNeg) {
                                 if ((unsigned long long)r0[u].z < tBirthNeg) alive = false;
                             }
                             if (alive && (unsigned long long)r0[u].w < tDeath) alive = false;

@@ -142,7 +142,8 @@ __device__ __forceinline__ int warp_sum(int v) {
 __global__ void k_cell_init(DevStats *__restrict__ st, int cLo, int cHi, const int *__restrict__ count, double *__restrict__ B, double *__restrict__ D,
                             double b0, double d0, double theta, double K, const double *__restrict__ Kcell, int doVerhulst,
                             int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ cursor,
-                            int *__restrict__ birthCount, int *__restrict__ nFert) {
+                            int *__restrict__ birthCount, int *__restrict__ nFert, unsigned long long *__restrict__ TB,
+                            unsigned long long *__restrict__ TD) {
     if (st->halt) return;  // an earlier queued step failed: leave everything as it is
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // the step's tallies and work counters start from zero
         st->nBirths = 0;
@@ -167,6 +168,13 @@ __global__ void k_cell_init(DevStats *__restrict__ st, int cLo, int cHi, const i
                 B[c] = __dadd_rn(b0, __dmul_rn(__dadd_rn(theta, -b0), q));
                 D[c] = __dadd_rn(d0, __dmul_rn(__dadd_rn(theta, -d0), q));
             }
+            // the fast path's probability tests as exact integer thresholds on the 32-bit draws, once per cell:
+            // TB = threshold of |b| (33 bits) with bit 62 = (b > 0), bit 63 = (b < 0); TD = threshold of d
+            const double b = B[c];
+            unsigned long long tb = prob_threshold(b > 0 ? b : -b);
+            if (tb > (1ull << 32)) tb = 1ull << 32;  // |b| >= 1: every draw is below it
+            TB[c] = tb | (b > 0 ? (1ull << 62) : 0ull) | (b < 0 ? (1ull << 63) : 0ull);
+            TD[c] = prob_threshold(D[c]);
         }
         stay[c] = 0;
         arrive[c] = 0;
@@ -345,6 +353,7 @@ struct CellEnv {
     const double *W;
     const double *B;
     const double *D;
+    const unsigned long long *TB, *TD;  // the same as integer thresholds (k_cell_init), read by the fast path
     // Navigate (actions/Navigate.cpp): ports as CSR (every port has n+1 entries: 0 = stay at home), current bridges
     const int *navRow;       // per cell: port index or -1; NULL if the population does not navigate
     const int *navPtr;       // first entry of port p

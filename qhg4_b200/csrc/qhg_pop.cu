@@ -169,6 +169,7 @@ struct qhgb_pop {
     DevBuf<int> moveBase;  // fast path: first arrival slot of the movers of (cell, direction), MOVE_STRIDE ints per cell
     DevBuf<uint8_t> nNbr, ice;
     DevBuf<double> alt, W, B, D;
+    DevBuf<unsigned long long> TB, TD;  // B, D as integer thresholds for the fast path (k_cell_init)
     DevBuf<int2> tileSums;
     std::map<std::string, DevBuf<double>> envExtra;
     bool haveCells = false, haveAlt = false, haveIce = false;
@@ -701,6 +702,7 @@ int computeWeights(qhgb_pop *p) {
 CellEnv cellEnv(qhgb_pop *p) {
     CellEnv E{};
     E.nbr = p->nbr.p; E.nNbr = p->nNbr.p; E.ice = p->haveIce ? p->ice.p : nullptr; E.alt = p->alt.p; E.W = p->W.p; E.B = p->B.p; E.D = p->D.p;
+    E.TB = p->TB.p; E.TD = p->TD.p;
     if (p->navReady) {
         E.navRow = p->navRow.p; E.navPtr = p->navPtr.p; E.navDest = p->navDest.p; E.navCum = p->navCum.p;
         E.bridges = p->navBridges.p; E.nBridges = p->nCurBridges; E.bridgeProb = p->A("Navigate_bridge_prob");
@@ -713,7 +715,7 @@ int resetCellCounters(qhgb_pop *p, bool doVerhulst) {
     qhgb_pop &q = *p;
     LAUNCH(p, "k_cell_init", k_cell_init, q.gridFor(q.cHi() - q.cLo()), 256, q.dstats.p, q.cLo(), q.cHi(), q.count[q.cur].p, q.B.p, q.D.p, q.A("Verhulst_b0"),
            q.A("Verhulst_d0"), q.A("Verhulst_theta"), q.A("Verhulst_K"), q.findKind(A_VERHULSTVARK) ? q.cap.p : nullptr, doVerhulst ? 1 : 0, q.stay.p, q.arrive.p, q.cursor.p,
-           q.birthCount.p, q.nFert.p);
+           q.birthCount.p, q.nFert.p, q.TB.p, q.TD.p);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1045,6 +1047,8 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(p->W.alloc(nc * WSTRIDE));
     CK(p->B.alloc(nc));
     CK(p->D.alloc(nc));
+    CK(p->TB.alloc(nc));
+    CK(p->TD.alloc(nc));
     CK(p->tileSums.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
     if (!p->subs.empty()) {
         CK(p->cap.alloc(nc));
@@ -1079,7 +1083,7 @@ int qhgb_destroy(qhgb_pop *p) {
     for (auto &k : p->ktimes) for (auto &ev : k.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     p->nbr.release(); p->gid.release(); p->count[0].release(); p->count[1].release(); p->cellStart[0].release(); p->cellStart[1].release(); p->moveBase.release(); p->count64.release();
     p->stay.release(); p->arrive.release(); p->cursor.release(); p->birthCount.release(); p->birthBase.release(); p->nFert.release(); p->nNbr.release();
-    p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->tileSums.release();
+    p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->TB.release(); p->TD.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
     for (auto &kv : p->envDelta) kv.second.release();
     p->cap.release(); p->Wtmp.release();

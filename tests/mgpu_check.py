@@ -57,11 +57,36 @@ def main():
             for f in FIELDS:
                 assert np.array_equal(allg[f][og], oa[f][oo]), (k, f)
             assert np.array_equal(np.sum(cnts, axis=0), o.counts()), k
+    # the same through qhgb_run: the steps are queued on every rank without a host round trip (peer-memory exchange; the NCCL
+    # exchange needs the host in every step and runs them one by one) -- still bit-exact
+    nq = 6
+    a0, s0, _ = g.run_totals()
+    g.run(float(nsteps), nq)
+    a1, s1, _ = g.run_totals()
+    moved += s1 - s0
+    mine = g.agents()
+    parts = [None] * world
+    dist.gather_object({f: mine[f] for f in FIELDS}, parts if rank == 0 else None, dst=0)
+    asteps = [None] * world
+    dist.gather_object(a1 - a0, asteps if rank == 0 else None, dst=0)
+    if rank == 0:
+        expect = 0
+        for k in range(nsteps, nsteps + nq):
+            expect += o.num_agents()
+            o.step(float(k))
+        allg = {f: np.concatenate([p[f] for p in parts]) for f in FIELDS}
+        oa = o.agents()
+        og, oo = np.argsort(allg["id"]), np.argsort(oa["id"])
+        assert len(allg["id"]) == o.num_agents(), ("queued", len(allg["id"]), o.num_agents())
+        for f in FIELDS:
+            assert np.array_equal(allg[f][og], oa[f][oo]), ("queued", f)
+        assert sum(asteps) == expect, (asteps, expect)
+        nsteps += nq
     tot = torch.tensor([moved])
     dist.all_reduce(tot)
     if rank == 0:
         how = "peer-memory" if os.environ.get("QHG_P2P", "1") != "0" else "nccl"
-        print(f"mgpu_check ok: {world} ranks, {nsteps} steps, {o.num_agents()} agents, {int(tot)} cross-rank migrations ({how} exchange), "
+        print(f"mgpu_check ok: {world} ranks, {nsteps} steps (the last {nq} queued by qhgb_run), {o.num_agents()} agents, {int(tot)} cross-rank migrations ({how} exchange), "
               f"bit-exact vs the unsharded oracle")
     dist.barrier()
     dist.destroy_process_group()
