@@ -142,7 +142,7 @@ inline double exp_portable(double x) {
 enum { STREAM_ACT0 = 0, STREAM_ACT1 = 1, STREAM_PAIR = 2, STREAM_BABY = 3 };
 // lanes of STREAM_ACT0 / STREAM_ACT1
 enum { L0_DEATH = 0, L0_MOVE = 1, L0_BIRTH = 2, L0_DEATH2 = 3 };
-enum { L1_MOVE2 = 0, L1_NAV = 1, L1_BRIDGE = 2, L1_OLDAGE = 3 };
+enum { L1_MOVE2 = 0, L1_NAV = 1, L1_SIGDEATH = 2, L1_OLDAGE = 3 };  // (bridges draw from their own streams 0x04000000|b/4)
 
 // ---------------------------------------------------------------------------------------------
 // PolyLine (utils/PolyLine.cpp:60-89 getVal, :92-127 readFromString)
@@ -325,7 +325,7 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
 };
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE};
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH};
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -362,6 +362,8 @@ struct qor_pop {
     double oadMaxAge = 0, oadUncertainty = 0;
     double moveProb = 0;
     double randMoveProb = 0;  // RandomMove_prob (actions/RandomMove.cpp)
+    double moveRandProb = 0;  // WeightedMoveRand_prob (actions/WeightedMoveRand.cpp)
+    double sigMaxAge = 0, sigRange = 0, sigSlope = 0, sigScale = 0;  // SigDeath (actions/SigDeath.cpp)
     // ConfinedMove (actions/ConfinedMove.cpp): centre (lon, lat in degrees) and radius (km) of the region agents may enter
     double confX = 0, confY = 0, confR = 0;
     std::vector<uint8_t> confAllowed;
@@ -725,6 +727,42 @@ struct qor_pop {
             }
             break;
         }
+        case A_WEIGHTEDMOVERAND: {  // actions/WeightedMoveRand.cpp:43-100: the weights decide unless they are all zero, then a uniform pick
+            if (a.life > 0) {
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_MOVE));
+                if (r < moveRandProb) {
+                    int c = a.cell;
+                    int nreal = nNbr[c];
+                    size_t off = (size_t)c * (maxNeigh + 1);
+                    int pick = -1;
+                    uint32_t u2 = draw(a.id, STREAM_ACT1, L1_MOVE2);
+                    if (W[off + maxNeigh] > 0) {
+                        double r2 = u2d(u2) * W[off + maxNeigh];
+                        for (int k = 0; k < maxNeigh + 1; k++) if (r2 < W[off + k]) { pick = k; break; }
+                    } else {
+                        pick = (int)u2range(u2, 0, nreal + 1);  // (int) wrandr(0, iNumActualNeigh+1)
+                    }
+                    if (pick > 0) {
+                        int to = nbr[(size_t)c * maxNeigh + pick - 1];
+                        if (to >= 0) {
+                            bool iced = env.count("Ice") && env["Ice"][to] != 0;
+                            if (!iced) registerMove(c, i, to);
+                        }
+                    }
+                }
+            }
+            break;
+        }
+        case A_SIGDEATH: {  // actions/SigDeath.cpp:66-90: p = scale / (1 + exp(-slope * (age - maxAge))), one draw per agent
+            if (a.life > 0) {
+                a.age = t - a.birth;
+                const double x = -sigSlope * (a.age - sigMaxAge);
+                const double p = sigScale / (1 + (mode == QOR_MODE_WELL ? exp(x) : exp_portable(x)));
+                const double r = u2d(draw(a.id, STREAM_ACT1, L1_SIGDEATH));
+                if (r < p) registerDeath(i);
+            }
+            break;
+        }
         case A_FERTILITY: {  // actions/Fertility.cpp:49-74 (overwrites the whole life state, incl. the MOVING bit)
             if (a.life > 0) {
                 if (a.gender == 0) {
@@ -1041,6 +1079,11 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"ConfinedMove", A_CONFINEDMOVE}};
+    } else if (p->popClass == "tut_EnvironAltVarPop") {
+        // probe class: tut_EnvironAltPop with WeightedMoveRand and SigDeath added (VarProbePop in oracle/ref_driver.cpp)
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"WeightedMoveRand", A_WEIGHTEDMOVERAND}, {"SigDeath", A_SIGDEATH}};
     } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
         // probe classes: tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added and called from
         // makePopSpecificOffspring (GenProbePop<U> in oracle/ref_driver.cpp) -- pin the Genetics action with 1- and 2-bit nucleotides
@@ -1150,6 +1193,10 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "OAD_uncertainty") p->oadUncertainty = v;
     else if (s == "WeightedMove_prob") p->moveProb = v;
     else if (s == "RandomMove_prob") p->randMoveProb = v;
+    else if (s == "WeightedMoveRand_prob") p->moveRandProb = v;
+    else if (s == "SigDeath_max_age") p->sigMaxAge = v;
+    else if (s == "SigDeath_range") p->sigRange = v;
+    else if (s == "SigDeath_slope") p->sigSlope = v;
     else if (s == "ConfinedMove_x") p->confX = v;
     else if (s == "ConfinedMove_y") p->confY = v;
     else if (s == "ConfinedMove_r") p->confR = v;
@@ -1243,6 +1290,7 @@ int qor_add_agents(qor_pop *p, int64_t n, const int32_t *cell, const int64_t *id
 
 int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDeath.cpp:49-59 + app/Simulator.cpp:107-111
     p->atanScale = (PI / 2 - ATAN_EPS) / atan(p->atanSlope * p->atanRange);
+    p->sigScale = 1 + exp(-p->sigRange);  // SigDeath::preLoop, actions/SigDeath.cpp:49-60
     p->nextID = p->maxID + 1;
     p->updateNumAgentsPerCell();
     if (p->find("Genetics")) {  // Genetics::init, actions/Genetics.cpp:196-267

@@ -48,6 +48,10 @@
 #include "Navigate.cpp"  // the reference's action templates, instantiated below for the tutorial agent
 #include "OldAgeDeath.cpp"
 #include "ConfinedMove.cpp"
+#include "WeightedMoveRand.cpp"
+#define EPS EPS_SIGDEATH  // actions/SigDeath.h:14 and actions/ATanDeath.h:14 both define a global `EPS`: no reference TU includes both
+#include "SigDeath.cpp"
+#undef EPS
 #include "GeneUtils.h"
 #include "LayerArrBuf.cpp"
 #include "SequenceIOUtils.cpp"
@@ -213,6 +217,24 @@ public:
     ConfinedMove<tut_EnvironAltAgent> *m_pCM;
 };
 
+// Probe class for pinning WeightedMoveRand (actions/WeightedMoveRand.cpp:43-100; carried by the predator populations PDPredPop,
+// PDAltPredPop, SimplePredPop, which need a prey population beside them) and SigDeath (actions/SigDeath.cpp:49-90; in no shipped
+// class): the reference's own templates added to tut_EnvironAltPop; the parameter file decides by <prio> entries which of
+// WeightedMove / WeightedMoveRand and ATanDeath / SigDeath run.
+class VarProbePop : public tut_EnvironAltPop {
+public:
+    VarProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        m_pWMR = new WeightedMoveRand<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL, m_adEnvWeights);
+        m_prio.addAction(m_pWMR);
+        m_pSD = new SigDeath<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL);
+        m_prio.addAction(m_pSD);
+    }
+    virtual ~VarProbePop() { delete m_pWMR; delete m_pSD; }
+    WeightedMoveRand<tut_EnvironAltAgent> *m_pWMR;
+    SigDeath<tut_EnvironAltAgent> *m_pSD;
+};
+
 // Probe class for pinning the Genetics action itself (actions/Genetics.cpp:285-337 makeOffspring: strand choice, crossover /
 // free recombination of both parents, mutation count and positions, all from the action's OWN generators seeded from
 // aiSeeds[1], :91-123) with 1-bit (genes/BitGeneUtils.cpp) and 2-bit (genes/GeneUtils.cpp) nucleotides.  The shipped classes
@@ -371,6 +393,8 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_OldAgeDiePop, tut_OldAgeDieAgent>(new tut_OldAgeDiePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltConfPop") {
         s->pa = new PopAccessT<ConfProbePop, tut_EnvironAltAgent>(new ConfProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironAltVarPop") {
+        s->pa = new PopAccessT<VarProbePop, tut_EnvironAltAgent>(new VarProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltGenPop") {
         s->pa = new PopAccessT<GenProbePop<BitGeneUtils>, tut_EnvironAltAgent>(new GenProbePop<BitGeneUtils>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltGen2bitPop") {

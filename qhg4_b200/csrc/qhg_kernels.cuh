@@ -20,7 +20,7 @@ constexpr int MAX_OPS = 16;
 // agent flag byte: gender and the FERTILE bit of the reference's life state (core/SPopulation.h:70-74)
 constexpr uint8_t F_MALE = 1, F_FERTILE = 2, F_BORN = 4;  // F_BORN only in the per-step decision byte
 
-enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE, OP_RANDOMMOVE };
+enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE, OP_RANDOMMOVE, OP_WEIGHTEDMOVERAND, OP_SIGDEATH };
 
 struct AgentArrays {
     int64_t *id;
@@ -99,6 +99,8 @@ struct ActParams {
     // ConfinedMove is active (actions/ConfinedMove.cpp:86-101): a move into a cell outside the region becomes a move to the
     // cell it starts from (still counted)
     int confine;
+    // WeightedMoveRand (actions/WeightedMoveRand.cpp) and SigDeath (actions/SigDeath.cpp:49-90), generic path only
+    double moveProbRand, sigMaxAge, sigSlope, sigScale;
 };
 
 __host__ __device__ __forceinline__ int prog_op(const ActParams &P, int k) { return (int)((P.prog >> (4 * k)) & 15ull); }
@@ -433,6 +435,36 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                     if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
                 }
             }
+            break;
+        }
+        case OP_WEIGHTEDMOVERAND: {  // actions/WeightedMoveRand.cpp:43-100: the weights decide unless they are all zero
+            if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+            if (u2d(r0.y) < P.moveProbRand) {
+                if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                const int nreal = E.nNbr[c];
+                const double *row = E.W + (size_t)c * WSTRIDE;
+                int pick = -1;
+                if (row[MAXN] > 0) {
+                    const double r2 = __dmul_rn(u2d(r1.x), row[MAXN]);
+                    for (int q = 0; q < MAXN + 1; q++) {
+                        if (r2 < row[q]) { pick = q; break; }
+                    }
+                } else {
+                    pick = (int)u2range(r1.x, 0.0, (double)(nreal + 1));  // (int) wrandr(0, iNumActualNeigh+1)
+                }
+                if (pick > 0) {
+                    int dst = E.nbr[(size_t)c * MAXN + pick - 1];
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
+                }
+            }
+            break;
+        }
+        case OP_SIGDEATH: {  // actions/SigDeath.cpp:66-90
+            d.age = __fsub_rn(P.t, birth);
+            if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+            const double x = __dmul_rn(-P.sigSlope, __dadd_rn((double)d.age, -P.sigMaxAge));
+            const double p = __ddiv_rn(P.sigScale, __dadd_rn(1.0, exp_rn(x)));
+            if (u2d(r1.z) < p) d.alive = false;
             break;
         }
         case OP_RANDOMMOVE: {  // actions/RandomMove.cpp:65-100: direction = (int)(r2 * (neighbours + 1)), 0 = stay; no ice test

@@ -96,7 +96,7 @@ int loadNccl() {
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -446,6 +446,8 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_OLDAGEDEATH: op = OP_OLDAGEDEATH; break;
         case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
         case A_RANDOMMOVE: op = OP_RANDOMMOVE; break;
+        case A_WEIGHTEDMOVERAND: op = OP_WEIGHTEDMOVERAND; break;
+        case A_SIGDEATH: op = OP_SIGDEATH; break;
         case A_FERTILITY: op = OP_FERTILITY; break;
         case A_VERHULST: op = OP_VERHULST; break;
         case A_VERHULSTVARK: op = OP_VERHULST; break;
@@ -488,6 +490,10 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     P.fertMinAge = (float)p->A("Fertility_min_age");
     P.fertMaxAge = (float)p->A("Fertility_max_age");
     P.fertInterbirth = (float)p->A("Fertility_interbirth");
+    P.moveProbRand = p->A("WeightedMoveRand_prob");
+    P.sigMaxAge = p->A("SigDeath_max_age");
+    P.sigSlope = p->A("SigDeath_slope");
+    P.sigScale = 1 + exp(-p->A("SigDeath_range"));  // SigDeath::preLoop, actions/SigDeath.cpp:49-60
     P.selfMate = p->selfMate ? 1 : 0;
     P.confine = (p->active(A_CONFINEDMOVE) && p->confReady) ? 1 : 0;  // its finalize() runs in every finalizeStep, whatever the levels
     return P;
@@ -498,7 +504,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
 bool programNeedsStoredAge(const ActParams &P) {
     for (int k = 0; k < P.nOps; k++) {
         switch (prog_op(P, k)) {
-        case OP_GETOLD: case OP_ATANDEATH: case OP_OLDAGEDEATH: return false;
+        case OP_GETOLD: case OP_ATANDEATH: case OP_OLDAGEDEATH: case OP_SIGDEATH: return false;
         case OP_FERTILITY: return true;
         default: break;
         }
@@ -768,7 +774,10 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
     bool tiled = binned && !q.forceGeneric && (n > 0 || q.sharded);
-    for (int k = 0; k < P.nOps; k++) if (prog_op(P, k) == OP_NAVIGATE) tiled = false;  // far jumps: generic path only (for now)
+    for (int k = 0; k < P.nOps; k++) {  // far jumps and the rarer actions: generic path only
+        const int op = prog_op(P, k);
+        if (op == OP_NAVIGATE || op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
+    }
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
     long long stepEndBirths = -1;
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // device time of the whole pipeline, gaps between the launches included
@@ -992,6 +1001,12 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltPref"; ea.trigger = QHGB_EVENT_ID_GEO;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false; en.trigger = QHGB_EVENT_ID_VEG;
         p->subs = {ea, en};
+    } else if (p->popClass == "tut_EnvironAltVarPop") {
+        // tut_EnvironAltPop with WeightedMoveRand (actions/WeightedMoveRand.cpp; the predator classes carry it) and SigDeath
+        // (actions/SigDeath.cpp) added: the class the reference driver builds to pin them (VarProbePop, oracle/ref_driver.cpp)
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"WeightedMoveRand", A_WEIGHTEDMOVERAND}, {"SigDeath", A_SIGDEATH}};
     } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
         // tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added: the classes the reference driver
         // builds to pin the Genetics action (GenProbePop<U>, oracle/ref_driver.cpp)
@@ -1212,7 +1227,7 @@ int qhgb_interpolate_env(qhgb_pop *p, int steps) {
 
 static const char *const kNumericAttrs[] = {
     "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob", "RandomMove_prob",
-    "ConfinedMove_x", "ConfinedMove_y", "ConfinedMove_r",
+    "ConfinedMove_x", "ConfinedMove_y", "ConfinedMove_r", "WeightedMoveRand_prob", "SigDeath_max_age", "SigDeath_range", "SigDeath_slope",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
     "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
@@ -1496,7 +1511,7 @@ static bool canDefer(qhgb_pop *p) {
     if (e && *e && *e != '0') return false;
     if (q.forceGeneric || q.genetic || q.nAgents <= 0 || !q.preLooped) return false;
     if (q.sharded && !q.p2p) return false;
-    if (q.active(A_NAVIGATE)) return false;
+    if (q.active(A_NAVIGATE) || q.active(A_WEIGHTEDMOVERAND) || q.active(A_SIGDEATH)) return false;  // generic-path actions
     return true;
 }
 

@@ -18,7 +18,7 @@ namespace qhg {
 // draw streams (counter word 3) and lanes
 enum : uint32_t { STREAM_ACT0 = 0, STREAM_ACT1 = 1, STREAM_PAIR = 2, STREAM_BABY = 3 };
 enum { L0_DEATH = 0, L0_MOVE = 1, L0_BIRTH = 2, L0_DEATH2 = 3 };   // lanes of STREAM_ACT0
-enum { L1_MOVE2 = 0, L1_NAV = 1, L1_BRIDGE = 2, L1_OLDAGE = 3 };   // lanes of STREAM_ACT1
+enum { L1_MOVE2 = 0, L1_NAV = 1, L1_SIGDEATH = 2, L1_OLDAGE = 3 };  // lanes of STREAM_ACT1 (bridges: streams 0x04000000|b/4)
 
 struct RngKey { uint32_t k0, k1; };
 

@@ -188,6 +188,21 @@ def tut_environ_alt_confined(K: float, x: float, y: float, r_km: float, prio: in
     return par
 
 
+def tut_environ_alt_variants(K: float, move_rand: bool = True, sig_death: bool = True, move_prob: float = 0.2) -> PopParams:
+    """tut_EnvironAltPop's parameter set with WeightedMoveRand (actions/WeightedMoveRand.cpp) in place of WeightedMove and / or
+    SigDeath (actions/SigDeath.cpp) in place of ATanDeath: the probe class `tut_EnvironAltVarPop` (all four actions are
+    registered; the <prio> entries decide which run)."""
+    par = tut_environ_alt(K)
+    par.class_name = "tut_EnvironAltVarPop"
+    par.modules["WeightedMoveRand"] = {"WeightedMoveRand_prob": repr(float(move_prob))}
+    par.modules["SigDeath"] = {"SigDeath_max_age": "60.0", "SigDeath_range": "6.0", "SigDeath_slope": "0.5"}
+    if move_rand:
+        par.prios["WeightedMoveRand"] = par.prios.pop("WeightedMove")
+    if sig_death:
+        par.prios["SigDeath"] = par.prios.pop("ATanDeath")
+    return par
+
+
 def tut_environ_alt_genetic(K: float, genome_size: int, num_crossover: int, mutation_rate: float, bits_per_nuc: int = 1) -> PopParams:
     """tut_EnvironAltPop's parameter set plus Genetics (actions/Genetics.cpp) with 1-bit (genes/BitGeneUtils.cpp) or 2-bit
     (genes/GeneUtils.cpp) nucleotides: the probe classes `tut_EnvironAltGenPop` / `tut_EnvironAltGen2bitPop` of

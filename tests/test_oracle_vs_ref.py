@@ -154,6 +154,38 @@ def test_confined_move_equals_reference():
     r.close()
 
 
+@pytest.mark.parametrize("move_rand,sig_death", [(True, False), (False, True), (True, True)])
+def test_weighted_move_rand_and_sig_death_equal_reference(move_rand, sig_death):
+    """WeightedMoveRand (actions/WeightedMoveRand.cpp:43-100: the cumulated weights decide unless they are all zero, then a
+    uniform pick with `wrandr`) and SigDeath (actions/SigDeath.cpp:49-90: p = scale / (1 + exp(-slope (age - max_age))), one
+    draw per agent) pinned against the reference's own templates added to tut_EnvironAltPop (VarProbePop in
+    oracle/ref_driver.cpp); the altitude field has plateaus above the poly-line's range, so all-zero weight rows occur."""
+    from qhg4_b200.params import tut_environ_alt_variants
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    alt[(alt > 400) & (alt < 900)] = 2600.0      # a belt of cells whose own and neighbours' weights are zero
+    pop = synthetic_population(9000, alt, seed=6, fertile=True, max_age=70.0)
+    par = tut_environ_alt_variants(25.0, move_rand, sig_death)
+    st = seed_state(12)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    moves = deaths = 0
+    for k in range(12):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+        b, d, m = o.step_stats()
+        moves += m; deaths += d
+    w = o.weights()
+    assert moves > 3000 and deaths > 500 and (w[np.unique(pop["cell"]), 6] == 0).any()
+    r.close()
+
+
 def test_navigate_equals_reference():
     """Navigate (actions/Navigate.cpp:94-250) pinned against the reference's own action: the reference's Navigate<T> is
     added to the reference's tut_EnvironAltPop (NavProbePop in oracle/ref_driver.cpp; the shipped populations that carry

@@ -606,6 +606,31 @@ def test_env_interpolation_on_device_bit_exact_vs_oracle(path):
     assert np.array_equal(g.env_array("Altitude"), before)
 
 
+@pytest.mark.parametrize("move_rand,sig_death", [(True, False), (False, True), (True, True)])
+def test_weighted_move_rand_and_sig_death_bit_exact_vs_oracle(move_rand, sig_death):
+    """WeightedMoveRand (actions/WeightedMoveRand.cpp) and SigDeath (actions/SigDeath.cpp, portable exp) on the device's
+    generic path against the oracle's counter mode; the oracle's WELL mode equals the reference's own actions
+    (tests/test_oracle_vs_ref.py::test_weighted_move_rand_and_sig_death_equal_reference)."""
+    from qhg4_b200.params import tut_environ_alt_variants
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=5)
+    alt[(alt > 400) & (alt < 900)] = 2600.0
+    pop = synthetic_population(40000, alt, seed=6, fertile=True, max_age=70.0)
+    g, o = make_pair(tut_environ_alt_variants(30.0, move_rand, sig_death), nbr, alt, pop, seed=41)
+    moves = deaths = 0
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        moves += s.moves; deaths += s.deaths
+    assert moves > 10000 and deaths > 2000
+    g.run(12.0, 3)                       # such programs run step by step inside qhgb_run too
+    for k in range(12, 15):
+        o.step(float(k))
+    assert_same_population(g, o, 14)
+
+
 @pytest.mark.parametrize("move_first", [False, True])
 def test_confined_move_bit_exact_vs_oracle(move_first, path):
     """ConfinedMove (actions/ConfinedMove.cpp:44-101; its finalize() filters the whole move list in finalizeStep): moves out
