@@ -139,10 +139,20 @@ struct DevBuf {
         if (e != cudaSuccess) return e;
         return cudaStreamSynchronize(0);
     }
+    // room for `count` elements whose old contents do not matter: the allocation is kept when it is large enough (tables that
+    // are rebuilt on every environment event; cudaFree / cudaMalloc inside a run cost milliseconds)
+    cudaError_t reserve(size_t count) {
+        if (p && cap >= count) { n = count; return cudaSuccess; }
+        cudaError_t e = alloc(count);
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    size_t cap = 0;
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        cap = 0;
     }
 };
 
@@ -654,11 +664,11 @@ int recalcNavigation(qhgb_pop *p) {
         const int a = q.hBridges[k], b = q.hBridges[k + 1];
         if (!q.hAlt.empty() && q.hAlt[a] > 0 && q.hAlt[b] > 0) br.push_back(make_int2(a, b));
     }
-    CK(q.navRow.alloc(q.nCells));
-    CK(q.navPtr.alloc(ptr.size()));
-    CK(q.navDest.alloc(std::max<size_t>(dest.size(), 1)));
-    CK(q.navCum.alloc(std::max<size_t>(cum.size(), 1)));
-    CK(q.navBridges.alloc(std::max<size_t>(br.size(), 1)));
+    CK(q.navRow.reserve(q.nCells));  // every entry is overwritten below
+    CK(q.navPtr.reserve(ptr.size()));
+    CK(q.navDest.reserve(std::max<size_t>(dest.size(), 1)));
+    CK(q.navCum.reserve(std::max<size_t>(cum.size(), 1)));
+    CK(q.navBridges.reserve(std::max<size_t>(br.size(), 1)));
     CK(cudaMemcpyAsync(q.navRow.p, row.data(), row.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
     CK(cudaMemcpyAsync(q.navPtr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
     if (!dest.empty()) CK(cudaMemcpyAsync(q.navDest.p, dest.data(), dest.size() * sizeof(int), cudaMemcpyHostToDevice, q.stream));
