@@ -58,6 +58,18 @@ def main():
                         ages=ages, p_atan=p_atan, totals=np.array(totals), counts_final=r.counts(),
                         **{"fin_" + k: v for k, v in fin.items()})
     r.close()
+    # --- every other population / action the oracle restates: trajectories of the reference with one thread
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_cases as gc
+
+    def ref_factory(par, nbr, alt_, st, env):
+        return refsim.RefSim(par, nbr, alt_, threads=1, state16=st, env=env)
+
+    for name in gc.CASES:
+        d = gc.build_inputs(name)
+        out = gc.run_case(name, ref_factory, d)
+        assert out["totals"][-1] > 0 and out["totals"][-1] != len(d["pop_id"]), name
+        np.savez_compressed(os.path.join(OUT, f"case_{name}.npz"), **d, **{"ref_" + k: v for k, v in out.items()})
     print("wrote", sorted(os.listdir(OUT)))
 
 

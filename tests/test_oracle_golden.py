@@ -76,6 +76,37 @@ def test_trajectory_bit_exact_one_thread():
     assert np.array_equal(o.counts(), g["counts_final"])
 
 
+def _golden_case_names():
+    import golden_cases as gc
+    return sorted(gc.CASES)
+
+
+@pytest.mark.parametrize("name", _golden_case_names())
+def test_golden_trajectories_of_the_reference(name):
+    """Every population class and probed action (tutorial ladder, tut_EnvironCapAltPop, ConfinedMove, Navigate, OldAgeDeath,
+    WeightedMoveRand + SigDeath, Genetics with 1- and 2-bit nucleotides): the oracle's WELL mode replays the trajectory the
+    REFERENCE produced with one thread (tests/make_golden.py, fixtures generated from oracle/_ref) -- per-step totals, the
+    final agent table slot for slot, per-cell counts, capacities and genomes.  Needs neither /root/reference nor oracle/_ref."""
+    import golden_cases as gc
+    path = os.path.join(GOLD, f"case_{name}.npz")
+    z = np.load(path)
+    d = {k: z[k] for k in z.files if not k.startswith("ref_")}
+    ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
+
+    def oracle_factory(par, nbr, alt, st, env):
+        return port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st, env=env)
+
+    well = (ref["gen_well_state"], ref["gen_well_index"]) if "gen_well_state" in ref else None
+    out = gc.run_case(name, oracle_factory, d, well_from=well if well is not None else ())
+    for k, v in ref.items():
+        if k.startswith("gen_well"):
+            continue
+        if k == "fin_last_birth" and name in ("tut_move", "tut_old_age_die"):
+            continue  # these classes' agent structs have no such field (populations/tut_MovePop.h, tut_OldAgeDiePop.h)
+        assert np.array_equal(out[k], v), (name, k)
+    assert ref["totals"][-1] > 0
+
+
 def test_counter_mode_is_order_invariant():
     """counter mode must not depend on the order in which agents are stored"""
     g, pop = _load_case()
