@@ -50,7 +50,10 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
     const unsigned step = st->step;
     const unsigned FULL = 0xffffffffu;
     // software pipeline: the next birth's record and its parents' row handles are fetched while this one is worked on
-    const int nBirths = ctl->nBirths;
+    // rows for the babies: birth e takes the e-th entry from the top of the free stack, or the (e - nFree)-th never-used row --
+    // no counter is touched here (k_genome_ctl_reset books the rows after the kernel), so the births do not queue up on one
+    // atomic; which row a genome lives in is not part of the result
+    const int nBirths = ctl->nBirths, nFree0 = ctl->nFree, hwm0 = ctl->hwm;
     BirthEntry beN{};
     int smN = 0, sfN = 0;
     if (w < nBirths) { beN = births[w]; smN = oldSlot[beN.mother]; sfN = oldSlot[beN.father]; }
@@ -60,8 +63,7 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
         if (e + nW < nBirths) { beN = births[e + nW]; smN = oldSlot[beN.mother]; sfN = oldSlot[beN.father]; }
         int slot = 0;
         if (lane == 0) {  // a row for the baby
-            int idx = atomicSub(&ctl->nFree, 1) - 1;
-            slot = (idx >= 0) ? freeStack[idx] : atomicAdd(&ctl->hwm, 1);
+            slot = (e < nFree0) ? freeStack[nFree0 - 1 - e] : hwm0 + (e - nFree0);
             newSlot[be.babyPos] = slot;
         }
         slot = __shfl_sync(FULL, slot, 0);
@@ -148,16 +150,29 @@ __global__ void k_free_genomes(const DevStats *__restrict__ st, GenomeCtl *__res
                                const int *__restrict__ oldSlot, int *__restrict__ freeStack) {
     if (st->overflow) return;
     const int n = st->nAgents;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (dest[i] < 0) {
-            freeStack[atomicAdd(&ctl->nFree, 1)] = oldSlot[i];
+    const unsigned lt = lanemask_lt();
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {  // one push per warp, not per dead agent
+        const int i = i0 + (int)threadIdx.x;
+        const bool dead = i < n && dest[i] < 0;
+        const unsigned m = __ballot_sync(0xffffffffu, dead);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&ctl->nFree, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (dead) freeStack[base + __popc(m & lt)] = oldSlot[i];
         }
     }
 }
 
-// the births may have popped more rows than the stack held (the rest came from the unused tail): clamp, reset the list
-__global__ void k_genome_ctl_reset(GenomeCtl *ctl, int clampFree, int resetBirths) {
-    if (clampFree && ctl->nFree < 0) ctl->nFree = 0;
+// bookRows: the births of this step took the top min(nBirths, nFree) rows of the free stack and the rest from the unused tail
+// (k_make_offspring); resetBirths: a new step starts with an empty birth list
+__global__ void k_genome_ctl_reset(GenomeCtl *ctl, int bookRows, int resetBirths) {
+    if (bookRows) {
+        const int nb = ctl->nBirths, take = min(nb, ctl->nFree);
+        ctl->nFree -= take;
+        ctl->hwm += nb - take;
+    }
     if (resetBirths) ctl->nBirths = 0;
 }
 

@@ -48,10 +48,19 @@ struct GenomeCtl {
     int pad;
 };
 
+// called by the lanes of a warp that have a birth to record (a divergent branch): one atomic per warp, not per birth --
+// all births of a step bump the same counter
 __device__ __forceinline__ void record_birth(BirthEntry *births, GenomeCtl *ctl, int babyPos, int mother, int father, long long cid) {
     BirthEntry e;
     e.babyPos = babyPos; e.mother = mother; e.father = father; e.pad = 0; e.cid = cid;
-    births[atomicAdd(&ctl->nBirths, 1)] = e;
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1, lane = (int)(threadIdx.x & 31);
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&ctl->nBirths, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    births[base + __popc(m & lt)] = e;
 }
 
 struct DevStats {
