@@ -22,6 +22,7 @@
 // (cell, mother id).  So positions may be handed out by atomics in any order and the result is still identical
 // to the oracle as a set of agents.
 #pragma once
+#include <type_traits>
 #include "qhg_kernels.cuh"
 
 namespace qhg {
@@ -81,6 +82,28 @@ struct WarpSmem {
     alignas(4) uint8_t dec[WCAP + 4];  // provisional decision of every agent of the cell, shifted by (cell start & 3)
 };
 
+// the same for populations with Genetics (k_cell_decide<false, true>): births need the identity of the father, so the fertile
+// males are listed and keyed like the females; fewer ranked agents per cell fit (larger cells take the generic path)
+constexpr int MAXF_G = 192;
+struct WarpSmemG {
+    double row[8];
+    long long qmId[QCAP];
+    float qaAge[QCAP];
+    uint32_t qaU[QCAP];
+    alignas(16) uint32_t keys[MAXF_G];   // pairing keys of the fertile females ...
+    alignas(16) uint32_t mkeys[MAXF_G];  // ... and of the fertile males
+    uint16_t ffJ[MAXF_G];
+    uint16_t mmJ[MAXF_G];                // positions of the fertile males in the cell
+    uint16_t qaJ[QCAP];
+    uint16_t qmJ[QCAP];
+    uint16_t candQ[MAXF_G];
+    uint16_t candR[MAXF_G];              // rank of every birth candidate among the fertile females
+    uint16_t maleOfRank[MAXF_G];         // position of the fertile male of rank r
+    int outC[8];
+    int nbrC[8];
+    alignas(4) uint8_t dec[WCAP + 4];
+};
+
 // the action program the fast path is specialised for at compile time: the tutorial populations' order
 // GetOld, ATanDeath, WeightedMove, Fertility, Verhulst (tutorial_data/xmldat/tut_EnvironAlt.xml priorities)
 constexpr unsigned long long PROG_TUT5 = (unsigned long long)OP_GETOLD | ((unsigned long long)OP_ATANDEATH << 4) |
@@ -116,14 +139,19 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 #define QHG_DECIDE_MINB (32 / QHG_DCW)
 #endif
 constexpr int DECIDE_CTAS_PER_SM = QHG_DECIDE_MINB;
-template <bool SPEC>
+// GEN = true (never together with SPEC): the population has Genetics; `father[i]` receives, for every mother-to-be at position
+// i of the current buffer, the position of her mate (the scatter pass turns the two into a birth record)
+template <bool SPEC, bool GEN = false>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
               int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-              int *__restrict__ moveBase) {
-    __shared__ WarpSmem smem[DCW];
+              int *__restrict__ moveBase, int *__restrict__ father = nullptr) {
+    static_assert(!(SPEC && GEN), "the compile-time program has no Genetics");
+    using WS = typename std::conditional<GEN, WarpSmemG, WarpSmem>::type;
+    constexpr int FCAP = GEN ? MAXF_G : MAXF;
+    __shared__ WS smem[DCW];
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
-    WarpSmem &S = smem[wid];
+    WS &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it
@@ -328,8 +356,16 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
                 // fertile census (for the pairing): positions of the fertile females, number of fertile males
                 const bool fertF = valid && ((f0[u] & (F_FERTILE | F_MALE)) == F_FERTILE);
                 const unsigned mF = __ballot_sync(FULL, fertF);
-                nM += __popc(__ballot_sync(FULL, valid && ((f0[u] & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE))));
-                if (nF + __popc(mF) > MAXF) tooMany = true;
+                if constexpr (GEN) {  // the fertile males are listed too
+                    const bool fertM = valid && ((f0[u] & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE));
+                    const unsigned mMm = __ballot_sync(FULL, fertM);
+                    if (nM + __popc(mMm) > FCAP) tooMany = true;
+                    else if (fertM) S.mmJ[nM + __popc(mMm & lt)] = (uint16_t)j;
+                    nM += __popc(mMm);
+                } else {
+                    nM += __popc(__ballot_sync(FULL, valid && ((f0[u] & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE))));
+                }
+                if (nF + __popc(mF) > FCAP) tooMany = true;
                 else if (fertF) S.ffJ[nF + __popc(mF & lt)] = (uint16_t)j;
                 nF += __popc(mF);
 
@@ -399,6 +435,67 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
         // have a mate" matters to the actions: with nF <= nM every fertile female has one, otherwise the nM females
         // with the smallest keys -- and only the birth candidates need to know.
         bool mates = selfMate || (doPair && nF > 0 && nM > 0);
+        if constexpr (GEN) {
+            // every birth needs her mate's identity: both sexes are ranked by (key, id), equal ranks mate
+            if (mates && !selfMate) {
+                if (tooMany) {
+                    if (lane == 0) atomicExch(&st->oversize, 1);
+                    continue;
+                }
+                int nCand = 0;
+                for (int q0 = 0; q0 < nF; q0 += 32) {
+                    const int q = q0 + lane;
+                    const bool isCand = (q < nF) && (sdec[S.ffJ[q]] & F_BORN);
+                    const unsigned mc = __ballot_sync(FULL, isCand);
+                    if (isCand) S.candQ[nCand + __popc(mc & lt)] = (uint16_t)q;
+                    nCand += __popc(mc);
+                }
+                if (nCand > 0) {  // warp-uniform
+                    for (int q = lane; q < nF; q += 32) S.keys[q] = agent_draws_rk(a.id[s + S.ffJ[q]], step, STREAM_PAIR, RK).x;
+                    for (int m = lane; m < nM; m += 32) S.mkeys[m] = agent_draws_rk(a.id[s + S.mmJ[m]], step, STREAM_PAIR, RK).x;
+                    __syncwarp();
+                    const int np = min(nF, nM);
+                    for (int i = lane; i < nCand; i += 32) {  // rank of every candidate among the fertile females
+                        const int q = S.candQ[i];
+                        const uint32_t k = S.keys[q];
+                        int r = 0;
+                        bool tie = false;
+                        for (int e = 0; e < nF; e++) {
+                            const uint32_t ke = S.keys[e];
+                            r += (ke < k) ? 1 : 0;
+                            tie |= (ke == k) && (e != q);
+                        }
+                        if (tie) {  // equal keys: the id decides
+                            const int64_t myId = a.id[s + S.ffJ[q]];
+                            for (int e = 0; e < nF; e++) if (e != q && S.keys[e] == k && a.id[s + S.ffJ[e]] < myId) r++;
+                        }
+                        S.candR[i] = (uint16_t)r;
+                        if (r >= np) sdec[S.ffJ[q]] &= (uint8_t)~F_BORN;  // no mate: no birth
+                    }
+                    for (int m = lane; m < nM; m += 32) {  // rank of every fertile male; the first np of them are mates
+                        const uint32_t k = S.mkeys[m];
+                        int r = 0;
+                        bool tie = false;
+                        for (int e = 0; e < nM; e++) {
+                            const uint32_t ke = S.mkeys[e];
+                            r += (ke < k) ? 1 : 0;
+                            tie |= (ke == k) && (e != m);
+                        }
+                        if (tie) {
+                            const int64_t myId = a.id[s + S.mmJ[m]];
+                            for (int e = 0; e < nM; e++) if (e != m && S.mkeys[e] == k && a.id[s + S.mmJ[e]] < myId) r++;
+                        }
+                        if (r < np) S.maleOfRank[r] = S.mmJ[m];
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < nCand; i += 32) {
+                        const int r = S.candR[i];
+                        if (r < np) father[s + S.ffJ[S.candQ[i]]] = s + S.maleOfRank[r];
+                    }
+                    __syncwarp();
+                }
+            }
+        } else
         if (mates && !selfMate && nF > nM) {
             if (tooMany) {
                 if (lane == 0) atomicExch(&st->oversize, 1);
@@ -758,6 +855,13 @@ struct alignas(128) WarpSmemS {
     uint16_t mvJ[MVCAP];
     unsigned long long bar[SNST];
 };
+struct alignas(128) WarpSmemSG {  // populations with Genetics: the mothers' positions in the old buffer as well
+    StagedAgents win[SNST];
+    int64_t motherId[MAXMOTHERS];
+    int motherIdx[MAXMOTHERS];
+    uint16_t mvJ[MVCAP];
+    unsigned long long bar[SNST];
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -788,16 +892,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 #define QHG_SCATTER_S_MINB 6
 #endif
 constexpr int SCATTER_CTAS_PER_SM = QHG_SCATTER_S_MINB;  // persistent grid: this many CTAs per SM
+// GEN = true: the population has Genetics -- the genome handle and m_iNumBabies follow the agent (read straight from global
+// memory, like the optional age), every newborn leaves a birth record (baby position, mother, father) for k_make_offspring
+template <bool GEN = false>
 __global__ void __launch_bounds__(CW * 32, QHG_SCATTER_S_MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
-               const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H) {
+               const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H,
+               const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
-    __shared__ WarpSmemS smem[CW];
+    using WSS = typename std::conditional<GEN, WarpSmemSG, WarpSmemS>::type;
+    __shared__ WSS smem[CW];
     if (st->overflow || st->oversize || st->halt) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpSmemS &S = smem[wid];
+    WSS &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const unsigned step = st->step;
@@ -911,6 +1020,10 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                             o.lastBirth[pos] = lastBirth;
                             o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
                             if (storeAge) o.age[pos] = age;
+                            if constexpr (GEN) {
+                                o.gslot[pos] = a.gslot[w0 + x];
+                                o.nbabies[pos] = a.nbabies[w0 + x] + ((v & F_BORN) ? 1 : 0);  // populations/OoANavGenPop.cpp:243
+                            }
                         }
                     }
                 }
@@ -936,8 +1049,13 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                         o.lastBirth[pos] = W.lastBirth[x];
                         o.flags[pos] = (uint8_t)(v & (F_MALE | F_FERTILE));
                         if (storeAge) o.age[pos] = a.age[j];
+                        if constexpr (GEN) {
+                            o.gslot[pos] = a.gslot[j];
+                            o.nbabies[pos] = a.nbabies[j] + (born ? 1 : 0);
+                        }
                     }
                     if (born) S.motherId[nMothers + __popc(mb & lt)] = W.id[x];
+                    if constexpr (GEN) { if (born) S.motherIdx[nMothers + __popc(mb & lt)] = j; }
                     stayBase += __popc(ms);
                     nMothers += __popc(mb);
                     // one call site (code size): the queue could overflow in the next round, or this is the last round of
@@ -963,6 +1081,11 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     // females are born FERTILE, core/SPopulation.cpp:895-898; tut_ParthenoPop turns the drawn males into females
                     o.flags[pos] = (uint8_t)(gnd ? (femaleOnly ? 0 : F_MALE) : F_FERTILE);
                     if (storeAge) o.age[pos] = 0.0f;
+                    if constexpr (GEN) {  // the genome is made by k_make_offspring from the parents' rows in the old buffer
+                        o.nbabies[pos] = 0;
+                        const int mi = S.motherIdx[m];
+                        record_birth(births, gctl, pos, mi, father[mi], cid);
+                    }
                 }
                 __syncwarp();
                 do { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); } while (ci < cEnd - cBase && e == s);

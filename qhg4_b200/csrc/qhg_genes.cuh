@@ -165,6 +165,26 @@ __global__ void k_free_genomes(const DevStats *__restrict__ st, GenomeCtl *__res
     }
 }
 
+// the same on the fast path: an agent died this step if its decision byte says so (move code 7)
+__global__ void k_free_genomes_dec(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, const uint8_t *__restrict__ dec,
+                                   const int *__restrict__ oldSlot, int *__restrict__ freeStack) {
+    if (st->overflow || st->oversize || st->halt) return;
+    const int n = st->nAgents;
+    const unsigned lt = lanemask_lt();
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + (int)threadIdx.x;
+        const bool dead = i < n && (dec[i] >> 3) == 7;
+        const unsigned m = __ballot_sync(0xffffffffu, dead);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&ctl->nFree, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (dead) freeStack[base + __popc(m & lt)] = oldSlot[i];
+        }
+    }
+}
+
 // bookRows: the births of this step took the top min(nBirths, nFree) rows of the free stack and the rest from the unused tail
 // (k_make_offspring); resetBirths: a new step starts with an empty birth list
 __global__ void k_genome_ctl_reset(GenomeCtl *ctl, int bookRows, int resetBirths) {

@@ -218,6 +218,8 @@ struct qhgb_pop {
     DevBuf<int> gslot[2], nbabies[2], gfree;
     DevBuf<unsigned long long> gpool;
     DevBuf<BirthEntry> births;
+    DevBuf<int> father;      // fast path with Genetics: position of the mate of every mother-to-be (k_cell_decide<false, true>)
+    bool genFast = false;    // QHG_GEN_FAST=1: populations with Genetics take the fast path (prepared, not yet the default)
     DevBuf<GenomeCtl> gctl;
     int64_t poolRows = 0;
     // Navigate: the Navigation group as the host handed it over, and the jump tables built from it
@@ -397,6 +399,7 @@ int allocAgents(qhgb_pop *p, int64_t cap) {
         q.gfree.p = nf; q.gfree.n = cap;
         q.poolRows = cap;
         CK(q.births.alloc(cap / 2 + 1024));
+        if (q.genFast) CK(q.father.alloc(cap));
     }
     CK(q.mate.alloc(cap));
     CK(q.prank.alloc(cap));
@@ -789,13 +792,18 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         if (op == OP_NAVIGATE || op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
     }
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
+    if (q.sharded && q.genetic) return fail("populations with Genetics cannot be sharded yet (genome rows do not travel with the migrants)");
     long long stepEndBirths = -1;
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // device time of the whole pipeline, gaps between the launches included
     if (q.timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, q.stream); }
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
             const int gridC = q.numSMs * DECIDE_CTAS_PER_SM;  // persistent: 32 warps per SM, one warp per cell at a time
-            if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
+            if (q.genetic) {  // QHG_GEN_FAST: births carry the father's position, genome handles follow the agents
+                LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
+                LAUNCH(p, "k_cell_decide_genetic", (k_cell_decide<false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p);
+            } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             } else {
@@ -855,7 +863,17 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
-            LAUNCH(p, "k_cell_scatter", k_cell_scatter, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
+            if (q.genetic) {
+                LAUNCH(p, "k_cell_scatter_genetic", k_cell_scatter<true>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
+                       q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H,
+                       q.father.p, q.births.p, q.gctl.p);
+                // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
+                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
+                       q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
+                LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0);
+                LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor(n), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
+            } else
+            LAUNCH(p, "k_cell_scatter", k_cell_scatter<false>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H);
             if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
                 LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p);
@@ -1049,6 +1067,11 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
         const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
+        // QHG_GEN_FAST=1: populations with Genetics take the fast path too (k_cell_decide<false, true> finds the fathers,
+        // k_cell_scatter<true> moves the genome handles and writes the birth records).  Written at the end of round 1 when no GPU
+        // time was left to validate it: OFF unless the variable is set; tests/test_parity_gpu.py has the (skipped) test for it.
+        const char *gf = getenv("QHG_GEN_FAST");
+        if (p->genetic && gf && *gf == '1') { p->genFast = true; p->forceGeneric = false; }
         p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);
     }
     size_t nc = (size_t)n_cells;
@@ -1113,7 +1136,7 @@ int qhgb_destroy(qhgb_pop *p) {
     for (auto &kv : p->envDelta) kv.second.release();
     p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
-    p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release();
+    p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release(); p->father.release();
     p->allowed.release();
     p->navRow.release(); p->navPtr.release(); p->navDest.release(); p->navCum.release(); p->navBridges.release();
     for (int b = 0; b < 2; b++) {

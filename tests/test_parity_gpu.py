@@ -5,6 +5,8 @@
 * whole trajectories: bit-exact against the oracle's counter mode (same random streams), compared
   as sets of agents because the order inside a cell is not part of the result.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -463,6 +465,51 @@ def test_two_bit_genomes_and_genetics_probe_classes_bit_exact_vs_oracle(cls, bit
     assert births > 1500
     with pytest.raises(Exception):  # the nucleotide width belongs to the class (actions/Genetics.cpp:204,259)
         GpuPopulation.from_params(par, nbr, alt, state16=st, env=env).modify_attributes("Genetics_bits_per_nuc", 3 - bits)
+
+
+@pytest.mark.skipif(os.environ.get("QHG_GEN_FAST_TEST") != "1",
+                    reason="the fast path for populations with Genetics (QHG_GEN_FAST=1) was written when no GPU time was left in "
+                           "round 1; it is off by default and this test runs once QHG_GEN_FAST_TEST=1 is set")
+@pytest.mark.parametrize("cls,bits", [("OoANavGenPop", 1), ("OoANavGen2bitPop", 2), ("tut_EnvironAltGenPop", 1)])
+@pytest.mark.parametrize("ncross,mut", [(-1, 2e-3), (3, 5e-3), (0, 0.0)])
+def test_genetic_populations_on_the_fast_path(cls, bits, ncross, mut, monkeypatch):
+    """QHG_GEN_FAST=1: k_cell_decide<false, true> ranks both sexes and hands every birth its father, k_cell_scatter<true> moves
+    the genome handles and writes the birth records -- agents, genomes and NumBabies must equal the oracle's (and hence the
+    generic path's)."""
+    from oracle import port
+    from qhg4_b200.params import ooa_nav_gen, tut_environ_alt_genetic
+    from qhg4_b200.population import GpuPopulation
+    monkeypatch.setenv("QHG_GEN_FAST", "1")
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    G = 200
+    if cls.startswith("OoANavGen"):
+        par = ooa_nav_gen(G, ncross, mut)
+        par.class_name = cls
+        par.modules["Genetics"]["Genetics_bits_per_nuc"] = str(bits)
+    else:
+        par, env = tut_environ_alt_genetic(20.0, G, ncross, mut, bits), None
+    st = seed_state(43)
+    row = 2 * ((G * bits + 63) // 64)
+    gen0 = np.random.default_rng(1).integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    g.add_agents(pop); o.add_agents(pop)
+    g.set_genomes(gen0); o.set_genomes(gen0)
+    g.pre_loop(); o.start()
+    g.reset_kernel_times(True)
+    births = 0
+    for k in range(10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        births += g.step_stats().births
+        ga, oa = g.agents(), o.agents()
+        gg, gnb = g.genomes(row)
+        og, onb = o.genomes(row)
+        si, so = np.argsort(ga["id"]), np.argsort(oa["id"])
+        assert np.array_equal(gg[si], og[so]), f"step {k}: genomes differ"
+        assert np.array_equal(gnb[si], onb[so]), f"step {k}: NumBabies differ"
+    assert births > 1500 and "k_cell_decide_genetic" in g.kernel_times()
 
 
 def test_navigate_sea_crossings_bit_exact_vs_oracle():
