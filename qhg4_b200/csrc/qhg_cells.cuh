@@ -104,6 +104,27 @@ struct WarpSmemG {
     alignas(4) uint8_t dec[WCAP + 4];
 };
 
+// NAV = true (k_cell_decide<false, GEN, true>): Navigate is the last action of the program.  Far jumps have no direction code:
+// the agent is marked as leaving (move code 7, like a dead one, so the scatter pass skips it) and goes into a jump list with a
+// slot among the arrivals of its destination; k_place_jumpers writes it there after the scatter pass.
+struct JumpEntry {
+    int src;    // position in the current buffer
+    int to;     // destination cell
+    int slot;   // slot among the arrivals of that cell
+    int bits;   // bit0 male, bit1 fertile, bit2 gave birth this step
+};
+// does Navigate see the MOVING bit of an earlier move?  (Fertility overwrites the whole life state, actions/Fertility.cpp:56-68)
+__device__ __forceinline__ bool nav_sees_moving(unsigned long long prog, int nOps) {
+    bool moving = false;
+    for (int k = 0; k < nOps; k++) {
+        const int op = (int)((prog >> (4 * k)) & 15ull);
+        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) moving = true;
+        if (op == OP_FERTILITY) moving = false;
+        if (op == OP_NAVIGATE) return moving;
+    }
+    return false;
+}
+
 // the action program the fast path is specialised for at compile time: the tutorial populations' order
 // GetOld, ATanDeath, WeightedMove, Fertility, Verhulst (tutorial_data/xmldat/tut_EnvironAlt.xml priorities)
 constexpr unsigned long long PROG_TUT5 = (unsigned long long)OP_GETOLD | ((unsigned long long)OP_ATANDEATH << 4) |
@@ -141,12 +162,13 @@ __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int
 constexpr int DECIDE_CTAS_PER_SM = QHG_DECIDE_MINB;
 // GEN = true (never together with SPEC): the population has Genetics; `father[i]` receives, for every mother-to-be at position
 // i of the current buffer, the position of her mate (the scatter pass turns the two into a birth record)
-template <bool SPEC, bool GEN = false>
+template <bool SPEC, bool GEN = false, bool NAV = false>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
               int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-              int *__restrict__ moveBase, int *__restrict__ father = nullptr) {
-    static_assert(!(SPEC && GEN), "the compile-time program has no Genetics");
+              int *__restrict__ moveBase, int *__restrict__ father = nullptr, JumpEntry *__restrict__ jumps = nullptr,
+              int *__restrict__ jumpCount = nullptr, int jumpCap = 0) {
+    static_assert(!(SPEC && (GEN || NAV)), "the compile-time program has neither Genetics nor Navigate");
     using WS = typename std::conditional<GEN, WarpSmemG, WarpSmem>::type;
     constexpr int FCAP = GEN ? MAXF_G : MAXF;
     __shared__ WS smem[DCW];
@@ -428,6 +450,54 @@ k_cell_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, 
             // with ConfinedMove the move flush reads the ATanDeath verdicts of its agents: the death queue goes first
             if (nqa > QCAP - 32 * DU || (last && nqa > 0) || (confine && nqa > 0 && (nqm > QCAP - 32 * DU || (last && nqm > 0)))) flush_atan();
             if (nqm > QCAP - 32 * DU || (last && nqm > 0)) flush_move();
+        }
+
+        // ---- Navigate (actions/Navigate.cpp:181-250), the last action of the program: the agents of port and bridge cells ------
+        if constexpr (NAV) {
+            const int port = E.navRow ? E.navRow[c] : -1;
+            bool hasBridge = false;
+            for (int b = 0; b < E.nBridges; b++) { const int2 br = E.bridges[b]; hasBridge |= (br.x == c) || (br.y == c); }
+            if (port >= 0 || hasBridge) {  // warp-uniform
+                const bool seesMoving = nav_sees_moving(prog, nOps);
+                int p0 = 0, nd = 0;
+                if (port >= 0) { p0 = E.navPtr[port]; nd = E.navPtr[port + 1] - p0 - 1; }
+                const int lim = (c < nd) ? c : nd;  // the reference bounds the search by the port's cell index (:194)
+                for (int j = lane; j < n; j += 32) {
+                    const uint8_t b0 = sdec[j];
+                    if (b0 & (T_ATANDIES | T_DEADNOW)) continue;          // dead before the last action
+                    const int code0 = (b0 >> DEC_MOVE_SHIFT) & 7;
+                    if (seesMoving && code0 != 0) continue;               // LIFE_STATE_MOVING is still set
+                    const int64_t idj = a.id[s + j];
+                    int to = -1, navMoves = 0;
+                    if (port >= 0) {
+                        const double r = u2d(agent_draws(idj, step, STREAM_ACT1, key).y);
+                        int i = 0;
+                        while (i < lim && r > E.navCum[p0 + i]) i++;
+                        if (i > 0) {
+                            const int dst = E.navDest[p0 + i];
+                            if (!(E.ice && E.ice[dst])) { to = dst; navMoves++; }
+                        }
+                    }
+                    for (int b = 0; b < E.nBridges; b++) {  // manual bridges: one draw per incident bridge (:228-247)
+                        const int2 br = E.bridges[b];
+                        const int dst = (br.x == c) ? br.y : ((br.y == c) ? br.x : -1);
+                        if (dst >= 0) {
+                            const uint4 db = agent_draws(idj, step, 0x04000000u | (unsigned)(b / 4), key);
+                            const unsigned wv = (b & 3) == 0 ? db.x : (b & 3) == 1 ? db.y : (b & 3) == 2 ? db.z : db.w;
+                            if (u2d(wv) < E.bridgeProb) { to = dst; navMoves++; }
+                        }
+                    }
+                    if (navMoves > 0) {  // the last registered move decides where the agent ends up; every one of them counts
+                        const int slot = atomicAdd(&arrive[to], 1);
+                        const int e = atomicAdd(jumpCount, 1);
+                        if (e < jumpCap) jumps[e] = JumpEntry{s + j, to, slot, (int)(b0 & 7)};
+                        else atomicExch(&st->oversize, 1);  // the list is full: the step is redone on the generic path
+                        sdec[j] = (uint8_t)((b0 & 7) | (DEC_DEAD << DEC_MOVE_SHIFT));
+                        confL += (code0 != 0 ? 1 : 0) + navMoves - 1;  // the commit counts one move for a leaving agent
+                    }
+                }
+                __syncwarp();
+            }
         }
 
         // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------
@@ -799,6 +869,30 @@ __global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable 
         o.lastBirth[pos] = m.lastBirth;
         o.flags[pos] = (uint8_t)m.flags;
         if (storeAge) o.age[pos] = m.age;
+    }
+}
+
+// the agents Navigate sent far away (k_cell_decide<.., true>): written at their slot in the destination cell; their decision
+// byte goes back to "stays" so that k_free_genomes_dec does not take them for dead
+template <bool GEN>
+__global__ void k_place_jumpers(const DevStats *__restrict__ st, const int *__restrict__ jumpCount, const JumpEntry *__restrict__ jumps,
+                                int jumpCap, AgentArrays a, AgentArrays o, const int *__restrict__ newStart,
+                                const int *__restrict__ stay, uint8_t *__restrict__ dec, int storeAge) {
+    if (st->overflow || st->oversize || st->halt) return;
+    const int n = min(*jumpCount, jumpCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const JumpEntry e = jumps[i];
+        const int pos = newStart[e.to] + stay[e.to] + e.slot;
+        o.id[pos] = a.id[e.src];
+        o.birth[pos] = a.birth[e.src];
+        o.lastBirth[pos] = a.lastBirth[e.src];
+        o.flags[pos] = (uint8_t)(e.bits & (F_MALE | F_FERTILE));
+        if (storeAge) o.age[pos] = a.age[e.src];
+        if constexpr (GEN) {
+            o.gslot[pos] = a.gslot[e.src];
+            o.nbabies[pos] = a.nbabies[e.src] + ((e.bits & F_BORN) ? 1 : 0);
+        }
+        dec[e.src] = (uint8_t)(e.bits & 7);
     }
 }
 

@@ -220,6 +220,9 @@ struct qhgb_pop {
     DevBuf<BirthEntry> births;
     DevBuf<int> father;      // fast path with Genetics: position of the mate of every mother-to-be (k_cell_decide<false, true>)
     bool genFast = false;    // QHG_GEN_FAST=1: populations with Genetics take the fast path (prepared, not yet the default)
+    bool navFast = false;    // QHG_NAV_FAST=1: programs that end with Navigate take the fast path (prepared, not yet the default)
+    DevBuf<JumpEntry> jumps; // fast path with Navigate: the agents that jump this step
+    DevBuf<int> jumpCount;
     DevBuf<GenomeCtl> gctl;
     int64_t poolRows = 0;
     // Navigate: the Navigation group as the host handed it over, and the jump tables built from it
@@ -787,10 +790,16 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
     bool tiled = binned && !q.forceGeneric && (n > 0 || q.sharded);
+    bool useNav = false;  // Navigate on the fast path (QHG_NAV_FAST=1): it must be the last action, no ConfinedMove, one GPU
     for (int k = 0; k < P.nOps; k++) {  // far jumps and the rarer actions: generic path only
         const int op = prog_op(P, k);
-        if (op == OP_NAVIGATE || op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
+        if (op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
+        if (op == OP_NAVIGATE) {
+            if (q.navFast && k == P.nOps - 1 && !P.confine && !q.sharded && q.navReady) useNav = true;
+            else tiled = false;
+        }
     }
+    if (!tiled) useNav = false;
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
     if (q.sharded && q.genetic) return fail("populations with Genetics cannot be sharded yet (genome rows do not travel with the migrants)");
     long long stepEndBirths = -1;
@@ -799,10 +808,28 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     for (int attempt = 0; attempt < 2; attempt++) {
         if (tiled) {
             const int gridC = q.numSMs * DECIDE_CTAS_PER_SM;  // persistent: 32 warps per SM, one warp per cell at a time
+            if (useNav) {
+                if (!q.jumps.p) {
+                    CK(q.jumps.alloc((size_t)std::max<int64_t>(1 << 16, q.capacity / 16)));
+                    CK(q.jumpCount.alloc(1));
+                }
+                CK(cudaMemsetAsync(q.jumpCount.p, 0, sizeof(int), q.stream));
+            }
+            const int jumpCap = (int)q.jumps.n;
             if (q.genetic) {  // QHG_GEN_FAST: births carry the father's position, genome handles follow the agents
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
-                LAUNCH(p, "k_cell_decide_genetic", (k_cell_decide<false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p);
+                if (useNav) {
+                    LAUNCH(p, "k_cell_decide_genetic_nav", (k_cell_decide<false, true, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p,
+                           q.jumps.p, q.jumpCount.p, jumpCap);
+                } else {
+                    LAUNCH(p, "k_cell_decide_genetic", (k_cell_decide<false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p);
+                }
+            } else if (useNav) {
+                LAUNCH(p, "k_cell_decide_nav", (k_cell_decide<false, false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, (int *)nullptr,
+                       q.jumps.p, q.jumpCount.p, jumpCap);
             } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
@@ -867,14 +894,19 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_cell_scatter_genetic", k_cell_scatter<true>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                        q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H,
                        q.father.p, q.births.p, q.gctl.p);
+                if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
+                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge);
                 // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
                 LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
                        q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0);
                 LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor(n), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
-            } else
+            } else {
             LAUNCH(p, "k_cell_scatter", k_cell_scatter<false>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H);
+            if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
+                               q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge);
+            }
             if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
                 LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p);
                 LAUNCH(p, "k_place_migrants", k_place_migrants_p2p, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
@@ -1072,6 +1104,9 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         // time was left to validate it: OFF unless the variable is set; tests/test_parity_gpu.py has the (skipped) test for it.
         const char *gf = getenv("QHG_GEN_FAST");
         if (p->genetic && gf && *gf == '1') { p->genFast = true; p->forceGeneric = false; }
+        // QHG_NAV_FAST=1: the same for programs that end with Navigate (k_cell_decide<.., true> + k_place_jumpers); same status
+        const char *nf = getenv("QHG_NAV_FAST");
+        p->navFast = nf && *nf == '1';
         p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);
     }
     size_t nc = (size_t)n_cells;
@@ -1137,6 +1172,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->cap.release(); p->Wtmp.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release(); p->father.release();
+    p->jumps.release(); p->jumpCount.release();
     p->allowed.release();
     p->navRow.release(); p->navPtr.release(); p->navDest.release(); p->navCum.release(); p->navBridges.release();
     for (int b = 0; b < 2; b++) {

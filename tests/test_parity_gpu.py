@@ -562,6 +562,72 @@ def test_navigate_sea_crossings_bit_exact_vs_oracle():
     assert far.size == 0 or g.counts()[far].sum() >= 0
 
 
+@pytest.mark.skipif(os.environ.get("QHG_GEN_FAST_TEST") != "1",
+                    reason="Navigate on the fast path (QHG_NAV_FAST=1) was written when no GPU time was left in round 1; it is "
+                           "off by default and this test runs once QHG_GEN_FAST_TEST=1 is set")
+@pytest.mark.parametrize("cls", ["tut_EnvironAltNavPop", "OoANavGenPop"])
+def test_navigate_on_the_fast_path(cls, monkeypatch):
+    """QHG_NAV_FAST=1 (+ QHG_GEN_FAST=1 for the genetic class): the agents of port and bridge cells get a second pass at the end
+    of their cell in k_cell_decide<.., true>, jumpers go through the jump list and k_place_jumpers -- same agents, totals and
+    genomes as the oracle, across a GEO + NAV event."""
+    from oracle import port
+    from qhg4_b200.params import ooa_nav_gen
+    from qhg4_b200.population import GpuPopulation
+    monkeypatch.setenv("QHG_NAV_FAST", "1")
+    monkeypatch.setenv("QHG_GEN_FAST", "1")
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    rng = np.random.default_rng(3)
+    land = np.flatnonzero(alt > 0)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    occupied = np.unique(pop["cell"])
+    ports = np.concatenate([occupied[:3], rng.choice(occupied[occupied > 8], 60, replace=False)]).astype(np.int32)
+    ptr = np.arange(0, 4 * len(ports) + 1, 4, dtype=np.int32)
+    dests = rng.choice(land, 4 * len(ports)).astype(np.int32)
+    dist = rng.uniform(100, 700, 4 * len(ports))
+    bridges = rng.choice(occupied, (6, 2), replace=False).astype(np.int32)
+    nav = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1", "Navigate_min_dens": "0.0",
+           "Navigate_bridge_prob": "0.3"}
+    genetic = cls == "OoANavGenPop"
+    if genetic:
+        par = ooa_nav_gen(128, -1, 1e-3)
+        par.modules["Navigate"] = nav
+        par.prios["Navigate"] = 10
+    else:
+        par, env = tut_environ_alt(20.0), None
+        par.class_name = cls
+        par.modules["Navigate"] = nav
+        par.prios["Navigate"] = 8
+        par.modules["OldAgeDeath"] = {"OAD_max_age": "60.0", "OAD_uncertainty": "0.1"}
+    st = seed_state(47)
+    gen0 = rng.integers(0, 2 ** 63, size=(len(pop["id"]), 4), dtype=np.int64).astype(np.uint64)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    for q in (g, o):
+        q.set_navigation(ports, ptr, dests, dist, bridges)
+        q.add_agents(pop)
+        if genetic:
+            q.set_genomes(gen0)
+    g.pre_loop(); o.start()
+    g.reset_kernel_times(True)
+    for k in range(10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), k
+        if k == 4:
+            alt2 = alt - 150.0
+            for q in (g, o):
+                q.set_env("Altitude", alt2)
+                q.update_event(2, 5.0); q.update_event(5, 5.0); q.flush_events(5.0)
+            assert_same_population(g, o, "event")
+    if genetic:
+        gg, gnb = g.genomes(4); og, onb = o.genomes(4)
+        ga, oa = g.agents(), o.agents()
+        si, so = np.argsort(ga["id"]), np.argsort(oa["id"])
+        assert np.array_equal(gg[si], og[so]) and np.array_equal(gnb[si], onb[so])
+    assert any(k.endswith("_nav") for k in g.kernel_times())
+
+
 @pytest.mark.parametrize("which", ["tut_SexualPop", "tut_MovePop", "tut_OldAgeDiePop"])
 def test_small_tutorial_populations_bit_exact_vs_oracle(which, path):
     """The rest of the reference's tutorial ladder: RandomMove (actions/RandomMove.cpp:65-100) and the action order of
