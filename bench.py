@@ -1,24 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the per-step agent update on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agents A] [--subdiv S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5]
 
-A "step" is one `PopLooper::doStep` of the tutorial action set (GetOld, ATanDeath, WeightedMove on
-SingleEvaluator(altitude), Fertility, RandomPair, Verhulst) over the whole synthetic population.
-Workload at every N: C4 of SURVEY.md §8 -- 1e8 agents on the subdivision-256 icosahedral grid
-(655,362 cells), K scaled so that N/K ~ 0.7 on land.  Rank 0 prints ONE JSON line.
+A "step" is one `PopLooper::doStep` over the whole synthetic population.  `--config` names the BASELINE.json
+configuration; the default, and what the driver measures, is C4:
 
-* `value`    agent-steps/s with the population resident in HBM, timed with CUDA events on the population's stream.
-* `e2e`      the same loop through the C ABI the way the reference's host loop uses a population: per step the
-             host passes the step's inputs (time, action parameters) and reads back the step's results
-             (totals + the per-cell count array that PopBase::getNumAgents exposes) into host memory.
-* `roofline` whole-step algorithmic bytes (66 B per live agent + 80 B per cell) over the summed
-             device time of the step's kernels, against the measured HBM copy bandwidth.
-* `cpu_baseline` the reference's own OpenMP code (oracle/_ref) on the host cores, on a bounded sample.
+  C2  tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove on SingleEvaluator[Alt], Fertility, RandomPair,
+      Verhulst), 1e7 agents on the subdivision-256 icosahedral grid (655,362 cells)
+  C3  OoANavGenPop without Navigate (OldAgeDeath, VerhulstVarK, NPPCapacity, MultiEvaluator[Alt+NPP], Genetics with 4096
+      one-bit sites = 1 KiB of genome per agent, free recombination, mutation rate 1e-5), 1e7 agents
+  C4  the C2 action set, 1e8 agents, sharded by contiguous cell ranges at N > 1 (migration over NVLink)
+  C5  OoANavGenPop WITH Navigate (2000 ports x 4 destinations anywhere on the globe) and a climate + vegetation + sea-level
+      event every 10 steps (environment interpolated on the device), 1e8 agents (1e7 on a single GPU: the genomes of
+      1e8 agents do not fit one B200)
+
+Rank 0 prints ONE JSON line.
+
+* `value`    agent-steps/s with the population resident in HBM, CUDA events on the population's stream, max over ranks.
+* `e2e`      the same loop through the C ABI the way the reference's host loop uses a population: per step the host passes
+             the step's inputs and reads back the step's results (totals + the per-cell count array that
+             PopBase::getNumAgents exposes) into page-locked host memory.
+* `roofline` whole-step algorithmic bytes (66 B per live agent + 80 B per cell, + 3 genome rows per birth)
+             over the summed device time of the step's kernels, against the measured HBM copy bandwidth.
+* `checksum` 64-bit sum and xor of the agent ids and a hash of the per-cell counts after the last step: the same at every N.
+* `cpu_baseline` / `--impl reference`: the reference's own OpenMP code (oracle/_ref) on the host cores, ON THE SAME
+             CONFIGURATION (same grid, same agents, same parameters), fewer steps.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -33,6 +45,15 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_AGENT = 66.0
 ALG_BYTES_PER_CELL = 80.0
+GENOME_SITES = 4096  # C3 / C5: one-bit sites per strand -> 2 x 64 words = 1 KiB per agent
+EVENT_EVERY = 10     # C5: steps between two environment events
+
+CONFIGS = {
+    "C2": {"cls": "tut", "agents": 10_000_000},
+    "C3": {"cls": "gen", "agents": 10_000_000, "nav": False, "events": False},
+    "C4": {"cls": "tut", "agents": 100_000_000},
+    "C5": {"cls": "gen", "agents": 100_000_000, "agents_1gpu": 10_000_000, "nav": True, "events": True},
+}
 
 
 def measured_peak_gbs():
@@ -43,14 +64,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_per_step(agents):
-    """DRAM bytes per step of the two fast-path kernels (everything else is per-cell and tiny) from the committed
-    ncu --set full capture, scaled to this run's agents."""
+def ncu_traffic(config):
+    """DRAM bytes per launch of the two fast-path kernels from the committed `ncu --set full` capture of THIS configuration
+    (profiles/traffic_r02.json, written by profiles/ncu_summary.py from the .ncu-rep).  Reported as captured -- with the
+    agents of the captured launch beside it, never rescaled; null when no capture of this configuration is committed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            d = json.load(f)
-        per_agent = (d["k_cell_decide"]["dram_bytes_per_launch"] + d["k_cell_scatter"]["dram_bytes_per_launch"]) / d["agents"]
-        return per_agent * agents
+        with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
+            d = json.load(f)[config]
+        return {"bytes_per_launch": {k: v["dram_bytes_per_launch"] for k, v in d["kernels"].items()},
+                "agents_in_captured_launch": d["agents"], "source": d.get("source", "profiles/traffic_r02.json")}
     except Exception:
         return None
 
@@ -107,6 +129,7 @@ class ClockSampler:
 
 
 def build_world(subdiv, n_agents, seed=1):
+    """the tutorial population (C2 / C4) on the icosahedral grid of the given subdivision"""
     from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_population
     from qhg4_b200.params import tut_environ_alt
     nbr, xyz = make_ico_grid(subdiv)
@@ -117,39 +140,101 @@ def build_world(subdiv, n_agents, seed=1):
     return nbr, alt, pop, tut_environ_alt(K), K
 
 
-def workload_name(args):
-    if args.subdiv == 255:
-        return (f"C4: tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove+SingleEvaluator[Alt], Fertility, "
-                f"RandomPair, Verhulst), {args.agents} agents on the subdivision-256 icosahedral grid")
-    return f"tut_EnvironAltPop action set, {args.agents} agents on eq:{args.subdiv}"
+def config_agents(args, world):
+    c = CONFIGS[args.config]
+    if args.agents:
+        return args.agents
+    if world == 1 and "agents_1gpu" in c:
+        return c["agents_1gpu"]
+    return c["agents"]
 
 
-def run_reference(args):
-    """The reference's own OpenMP step loop (oracle/_ref) on the host cores, bounded sample of the workload."""
+def build_workload(args, world):
+    """grid, environment, population and parameters of the configuration -- identical on every rank and for both arms"""
+    from qhg4_b200.icogrid import make_ico_grid, synthetic_altitude, synthetic_climate, synthetic_population
+    from qhg4_b200.params import ooa_nav_gen
+    c = CONFIGS[args.config]
+    n = config_agents(args, world)
+    if c["cls"] == "tut":
+        nbr, alt, pop, par, K = build_world(args.subdiv, n)
+        return {"nbr": nbr, "alt": alt, "pop": pop, "par": par, "K": K, "env": None, "nav": None, "row": 0, "agents": n}
+    nbr, xyz = make_ico_grid(args.subdiv)
+    alt = synthetic_altitude(xyz, seed=1)
+    env = synthetic_climate(xyz, alt, seed=2)
+    pop = synthetic_population(n, alt, seed=1, fertile=True)
+    par = ooa_nav_gen(GENOME_SITES, -1, 1e-5)
+    nav = None
+    if c.get("nav"):
+        rng = np.random.default_rng(11)
+        land = np.flatnonzero(alt > 0)
+        nports = min(2000, len(land) // 4)
+        ports = rng.choice(land, nports, replace=False).astype(np.int32)
+        nav = {"ports": ports, "ptr": np.arange(0, 4 * nports + 1, 4, dtype=np.int32),
+               "dests": rng.choice(land, 4 * nports).astype(np.int32), "dist": rng.uniform(100, 700, 4 * nports)}
+        par.modules["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1",
+                                   "Navigate_min_dens": "0.0", "Navigate_bridge_prob": "0.3"}
+        par.prios["Navigate"] = 10
+    return {"nbr": nbr, "alt": alt, "pop": pop, "par": par, "K": None, "env": env, "nav": nav, "row": 2 * (GENOME_SITES // 64),
+            "agents": n}
+
+
+def synthetic_genomes(ids, row):
+    """random genome rows for the founders, reproducible per agent id at any sharding: row = block[id mod 65,521]"""
+    block = np.random.default_rng(5).integers(0, 2 ** 63, size=(65521, row), dtype=np.int64).astype(np.uint64)
+    return block[np.asarray(ids) % 65521]
+
+
+def workload_name(args, world):
+    n = config_agents(args, world)
+    grid = "the subdivision-256 icosahedral grid (655,362 cells)" if args.subdiv == 255 else f"eq:{args.subdiv}"
+    if CONFIGS[args.config]["cls"] == "tut":
+        return (f"{args.config}: tut_EnvironAltPop action set (GetOld, ATanDeath, WeightedMove+SingleEvaluator[Alt], Fertility, "
+                f"RandomPair, Verhulst), {n} agents on {grid}")
+    extra = (", Navigate (2000 ports x 4 destinations), GEO+CLIMATE+VEG+NAV event every %d steps (environment interpolated on the device)" % EVENT_EVERY
+             if CONFIGS[args.config].get("nav") else " without Navigate")
+    return (f"{args.config}: OoANavGenPop (OldAgeDeath, WeightedMove+MultiEvaluator[Alt+NPP], Fertility, RandomPair, VerhulstVarK, NPPCapacity, "
+            f"Genetics {GENOME_SITES} one-bit sites, free recombination, mutation rate 1e-5){extra}, {n} agents on {grid}")
+
+
+def capacity_scale(cap, n_agents):
+    """NPPCap_efficiency such that N/K ~ 0.7 on the land cells at the start"""
+    land = cap[cap > 0]
+    return float((n_agents / max(1, len(land)) / 0.7) / land.mean()) if len(land) else 1.0
+
+
+def run_reference(args, world, steps, warmup):
+    """The reference's own OpenMP step loop (oracle/_ref) on the host cores, on the SAME configuration as the GPU arm."""
     from oracle import refsim
     if not refsim.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqhgref.so was not built (needs /root/reference at build time)"}))
-        return
+        return {"impl": "reference", "unavailable": "oracle/_ref/libqhgref.so was not built (needs /root/reference at build time)"}
     cores = os.cpu_count() or 1
     threads = int(os.environ.get("QHG_REF_THREADS", cores))
-    dens = args.agents / (0.7 * (10 * (args.subdiv + 1) ** 2 + 2))
-    sub = args.ref_subdiv
-    ncell = 10 * (sub + 1) ** 2 + 2
-    n = int(dens * 0.7 * ncell)
-    nbr, alt, pop, par, K = build_world(sub, n)
-    s = refsim.RefSim(par, nbr, alt, threads=threads)
-    s.add_agents(pop)
+    w = build_workload(args, world)
+    c = CONFIGS[args.config]
+    kind = "reference"
+    if c["cls"] == "gen" and not refsim.has_class("OoANavGenPop"):
+        return {"impl": "reference", "unavailable": "OoANavGenPop is not part of this build of oracle/_ref"}
+    s = refsim.RefSim(w["par"], w["nbr"], w["alt"], threads=threads, env=w["env"])
+    if w["nav"]:
+        s.set_navigation(w["nav"]["ports"], w["nav"]["ptr"], w["nav"]["dests"], w["nav"]["dist"], ())
+    s.add_agents(w["pop"])
+    if c["cls"] == "gen":
+        s.set_genomes(synthetic_genomes(w["pop"]["id"], w["row"]))
     s.start()
-    s.run(0.0, args.ref_warmup)
-    sec, asteps = s.run(float(args.ref_warmup), args.ref_steps)
+    if c["cls"] == "gen":
+        s.modify_attribute("NPPCap_efficiency", capacity_scale(s.capacities(), w["agents"]))
+        s.event(4, 0.0, True)
+    s.run(0.0, warmup)
+    sec, asteps = s.run(float(warmup), steps)
     val = asteps / sec
-    sample = (f"same action set and density ({dens:.0f} agents per land cell, K={K:.0f}) on an eq:{sub} grid ({ncell} cells), "
-              f"{n} agents, {args.ref_warmup} warm-up + {args.ref_steps} timed steps, {threads} OpenMP threads, stdout to /dev/null")
-    line = {"metric": "agent-steps/sec", "value": val, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.ref_steps,
-            "warmup": args.ref_warmup, "ms_per_step": 1e3 * sec / args.ref_steps, "higher_is_better": True,
+    sample = (f"the whole configuration ({w['agents']} agents, {len(w['nbr'])} cells, same parameters and initial population as the GPU arm), "
+              f"{warmup} warm-up + {steps} timed steps of PopLooper::doStep, {threads} OpenMP threads, stdout to /dev/null")
+    line = {"metric": "agent-steps/sec", "value": val, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args), "sample": f"bounded sample of it: {n} agents on eq:{sub} ({ncell} cells), same density and K"},
-            "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": "reference", "sample": sample},
+            "config": {"workload": workload_name(args, world), "cells": len(w["nbr"]), "agents_start": w["agents"],
+                       "agents_end": s.num_agents()},
+            "cpu_baseline": {"value": val, "unit": "agent-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     s.close()
@@ -162,30 +247,67 @@ def run_ours(args, rank, world):
     device = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
-        import torch.distributed as dist  # host-side plumbing only (128-byte NCCL id, scalar reductions); the data
-        dist.init_process_group("gloo", rank=rank, world_size=world)  # path is NCCL inside the C library
+        import torch.distributed as dist  # host-side plumbing only (128-byte NCCL id, IPC handles, scalar reductions)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     t_setup = time.time()
     sampler = ClockSampler(device)
     sampler.start()
-    nbr, alt, pop, par, K = build_world(args.subdiv, args.agents)
+    c = CONFIGS[args.config]
+    genetic, events = c["cls"] == "gen", bool(c.get("events"))
+    w = build_workload(args, world)
+    nbr, alt, pop, par, K, env, nav, row = (w[k] for k in ("nbr", "alt", "pop", "par", "K", "env", "nav", "row"))
+    n_start = w["agents"]
     ncell = len(nbr)
     begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=ncell), world)
     lo, hi = np.searchsorted(pop["cell"], [begin[rank], begin[rank + 1]])  # the population is generated binned by cell
     pop = {k: v[lo:hi] for k, v in pop.items()}
-    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096)
+    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096, env=env)
     if world > 1:
         sharding.connect(g, begin, rank, world)
+    if nav:
+        g.set_navigation(nav["ports"], nav["ptr"], nav["dests"], nav["dist"], ())
     t0 = time.time()
     g.add_agents(pop)
+    if genetic:
+        g.set_genomes(synthetic_genomes(pop["id"], row))
     g.pre_loop()
+    if genetic:  # carrying capacities scaled to the population (N/K ~ 0.7 on land), through modifyAttributes + a VEG event
+        g.modify_attributes("NPPCap_efficiency", capacity_scale(g.capacities(), n_start))
+        g.update_event(4, 0.0); g.flush_events(0.0)
+    if events:  # the environment drifts between two dated files: difference arrays resident on the device (AutoInterpolator)
+        g.set_env_delta("Altitude", np.full(ncell, -0.5))
+        g.set_env_delta("AnnualMeanTemp", np.full(ncell, -0.05))
+        g.set_env_delta("BaseNPP", -0.002 * env["BaseNPP"])
     g.synchronize()
     upload_s = time.time() - t0
     del pop
+
+    def env_event(t):  # app/Simulator.cpp:338-374: interpolate, deliver the interpolator's events, flush
+        g.interpolate_env(EVENT_EVERY)
+        for ev in (2, 3, 4, 5):
+            g.update_event(ev, t)
+        g.flush_events(t)
+
+    state = {"t": 0.0, "k": 0}
+
+    def advance(nsteps, queued):
+        """nsteps steps from state['t'] on; C5 delivers an environment event every EVENT_EVERY steps"""
+        left = nsteps
+        while left > 0:
+            chunk = min(left, EVENT_EVERY - state["k"] % EVENT_EVERY) if events else left
+            if queued:
+                g.run(state["t"], chunk)
+            else:
+                for i in range(chunk):
+                    g.step(state["t"] + i)
+            state["t"] += float(chunk); state["k"] += chunk; left -= chunk
+            if events and state["k"] % EVENT_EVERY == 0:
+                env_event(state["t"])
+
     sampler.begin()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
-    t = 0.0
-    for _ in range(args.warmup):
-        g.step(t); t += 1.0
+    advance(args.warmup, False)
     g.synchronize()
+
     def allsum(x):
         if dist is None:
             return x
@@ -213,7 +335,7 @@ def run_ours(args, rank, world):
     as0, sent0, _ = g.run_totals()
     barrier()
     g.event_record(0)
-    g.run(t, args.steps); t += float(args.steps)
+    advance(args.steps, True)
     g.event_record(1)
     barrier()
     as1, sent1, _ = g.run_totals()
@@ -227,26 +349,30 @@ def run_ours(args, rank, world):
 
     # ---- per-kernel CUDA events over K steps of the same loop (kept out of region 1: the event calls cost host time) ----
     g.reset_kernel_times(True)
-    prof_agent_steps = 0
+    prof_agent_steps, prof_births = 0, 0
     barrier()
     for _ in range(args.steps):
         prof_agent_steps += g.num_agents()
-        g.step(t); t += 1.0
+        advance(1, False)
+        prof_births += g.step_stats().births
     barrier()
     ktimes = g.kernel_times()
     g.reset_kernel_times(False)
     prof_agent_steps = allsum(prof_agent_steps)
+    prof_births = allsum(prof_births)
     pipeline_ms = ktimes.pop("pipeline_total", (0.0, 0))[0]  # device time of the steps, gaps between launches included
 
     # ---- timed region 2: end to end through the C ABI with host buffers --------------------------------------
     counts = g.host_array(ncell, np.uint64)  # page-locked: the per-step result is one DMA into host memory
     e2e_steps = 0
+    levels = sorted(set(g.prios.values()))
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
+        t = state["t"]
         e2e_steps += g.num_agents()
         g.initialize_step(t)
-        for lvl in sorted(set(g.prios.values())):
+        for lvl in levels:
             g.do_actions(lvl, t)
         g.finalize_step()
         st = g.step_stats()          # totals of the step (D2H inside finalize_step)
@@ -254,34 +380,57 @@ def run_ours(args, rank, world):
             g.counts_range(begin[rank], begin[rank + 1], counts)
         else:
             g.counts(counts)         # per-cell counts into host memory, as PopBase::getNumAgentsArray exposes them
-        t += 1.0
+        state["t"] += 1.0; state["k"] += 1
+        if events and state["k"] % EVENT_EVERY == 0:
+            env_event(state["t"])
     barrier()
     e2e_sec = allmax(time.perf_counter() - w0)
     e2e_val = allsum(e2e_steps) / e2e_sec
+
+    # ---- checksum of the final state: the same whatever the number of GPUs -------------------------------------
     t1 = time.time()
     final = g.agents()
     download_s = time.time() - t1
-    n_final = int(allsum(len(final["id"])))
+    ids = final["id"].astype(np.uint64)
+    n_final = int(allsum(len(ids)))
+    id_sum, id_xor = int(ids.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(ids)) if len(ids) else 0
+    cnt = g.counts().astype(np.int64)
+    if dist is not None:
+        import torch
+        parts = [None] * world
+        dist.all_gather_object(parts, (id_sum, id_xor))
+        id_sum = sum(p[0] for p in parts) % (1 << 64)
+        id_xor = 0
+        for p in parts:
+            id_xor ^= p[1]
+        tc = torch.from_numpy(cnt)
+        dist.all_reduce(tc)
+        cnt = tc.numpy()
+    checksum = {"agents": n_final, "id_sum_mod_2_64": f"{id_sum % (1 << 64):016x}", "id_xor": f"{id_xor:016x}",
+                "cell_counts_sha1": hashlib.sha1(np.ascontiguousarray(cnt, np.int64).tobytes()).hexdigest()[:16],
+                "steps_done": int(state["k"])}
     del final
 
     # ---- roofline: whole-step algorithmic bytes over the summed kernel time ------------------------------------
     peak, peak_src = measured_peak_gbs()
     kern_ms = allmax(sum(v[0] for v in ktimes.values()))  # slowest rank
     peak *= world
-    alg_bytes = ALG_BYTES_PER_AGENT * prof_agent_steps + ALG_BYTES_PER_CELL * ncell * args.steps
+    genome_bytes = 3.0 * row * 8.0 * prof_births  # per birth: two parents read, one child written
+    alg_bytes = ALG_BYTES_PER_AGENT * prof_agent_steps + ALG_BYTES_PER_CELL * ncell * args.steps + genome_bytes
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     top = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
     # the two hot kernels against their own algorithmic bytes: pass 1 reads 17 B and writes 1 B per agent,
     # pass 2 reads 18 B per agent and writes 17 B per agent that is alive afterwards (~ the same number)
     per_kernel = {}
-    for kname, bpa in (("k_cell_decide", 18.0), ("k_cell_scatter", 35.0)):
+    for kname, bpa in (("k_cell_decide", 18.0), ("k_cell_decide_genetic", 18.0), ("k_cell_decide_genetic_nav", 18.0),
+                       ("k_cell_scatter", 35.0), ("k_cell_scatter_genetic", 51.0)):
         if kname in ktimes and ktimes[kname][0] > 0:
             kms = allmax(ktimes[kname][0])
             gbs = bpa * prof_agent_steps / (kms * 1e-3) / 1e9
             per_kernel[kname] = {"alg_bytes_per_agent": bpa, "ms_per_step": round(kms / args.steps, 4), "achieved": round(gbs, 1),
                                  "frac": round(gbs / peak, 4)}
     roof = {"bound": "hbm", "kernel": "whole step (all kernels of one doStep, summed device time)", "achieved": achieved,
-            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_step(agent_steps / args.steps),
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_ncu": ncu_traffic(args.config),
             "peak_source": peak_src,
             "alg_bytes_per_step": alg_bytes / args.steps, "dominant_kernel": top,
             "pipeline_ms_per_step": round(pipeline_ms / args.steps, 4), "per_kernel": per_kernel,
@@ -290,14 +439,14 @@ def run_ours(args, rank, world):
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args),
-                       "cells": ncell, "agents_start": args.agents, "agents_end": n_final, "verhulst_K": K,
+            "config": {"workload": workload_name(args, world), "name": args.config,
+                       "cells": ncell, "agents_start": n_start, "agents_end": n_final, "verhulst_K": K,
                        "l2": "agent state per step (>2 GB at 1e8 agents) exceeds the 126 MB L2; no explicit flush",
                        "upload_s": round(upload_s, 2), "download_s": round(download_s, 2), "setup_s": round(t0 - t_setup, 2),
                        "parallelism": (f"cell-range shards x{world}, migration over " + ("peer memory (NVLink stores from the scatter kernel)"
                                        if os.environ.get("QHG_P2P", "1") != "0" else "NCCL send/recv")) if world > 1 else "single GPU",
                        "migrations_per_step": migrated / args.steps},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches, "checksum": checksum,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * int(begin[rank + 1] - begin[rank]) + 48,
                     "what": "initializeStep + doActions per level + finalizeStep through the C ABI, then totals and the per-cell count "
                             "array (ulong per cell, as PopBase::getNumAgentsArray; sharded: every rank its own cell range) copied into "
@@ -315,30 +464,30 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--agents", type=int, default=100_000_000)
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--agents", type=int, default=0, help="override the configuration's agent count (testing)")
     ap.add_argument("--subdiv", type=int, default=255)
-    ap.add_argument("--ref-subdiv", type=int, default=80)
-    ap.add_argument("--ref-steps", type=int, default=3)
-    ap.add_argument("--ref-warmup", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
 
     if args.impl == "reference":
+        # the reference's CPU path on this arm's configuration; every timed step is a full doStep of the whole population
+        # (about 2.7 s at 1e8 agents on 16 cores), so the step count is bounded to keep the run within a few minutes
         if rank == 0:
-            args.ref_steps, args.ref_warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-            line = run_reference(args)
-            if line:
-                print(json.dumps(line))
+            line = run_reference(args, world, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+            print(json.dumps(line))
         return
 
     line = run_ours(args, rank, world)
     if rank == 0:
-        if not args.no_cpu_baseline:
-            ref = run_reference(args)
-            if ref:
+        if not args.no_cpu_baseline and world == 1:
+            ref = run_reference(args, world, 2, 1)  # bounded: 1 warm-up + 2 timed steps of the same configuration
+            if "cpu_baseline" in ref:
                 line["cpu_baseline"] = ref["cpu_baseline"]
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": 0, "kind": "reference", "sample": ref.get("unavailable", "")}
         print(json.dumps(line))
 
 

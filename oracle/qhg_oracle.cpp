@@ -1023,7 +1023,11 @@ struct qor_pop {
     }
     // populations/tut_EnvironAltPop.cpp:93-127
     int updateEvent(int ev, float) {
-        if (ev == EVENT_ID_GEO) {
+        // only the classes that override updateEvent drown their agents (populations/tut_EnvironAltPop.cpp:93-127,
+        // tut_EnvironCapAltPop.cpp, OoANavGenPop.cpp:179-214); tut_SexualPop, tut_MovePop, tut_OldAgeDiePop, tut_ParthenoPop and
+        // tut_StaticPop inherit SPopulation::updateEvent, which does nothing (core/SPopulation.h:116)
+        const bool drowns = popClass.rfind("tut_Environ", 0) == 0 || popClass.rfind("OoANavGen", 0) == 0;
+        if (ev == EVENT_ID_GEO && drowns) {
             const std::vector<double> &alt = env["Altitude"];
             const std::vector<double> *ice = env.count("Ice") ? &env["Ice"] : nullptr;
             for (int i = 0; i < hi(); i++) {

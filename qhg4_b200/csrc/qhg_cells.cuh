@@ -691,8 +691,8 @@ struct Migrant {  // 32 bytes
     long long id;
     float birth, lastBirth, age;
     int cell;
-    unsigned flags;
-    unsigned pad;
+    unsigned flags;  // bits 0-7: the agent's flag byte; bits 8-31: m_iNumBabies (populations with Genetics)
+    unsigned pad;    // peer-memory exchange: slot among the arrivals of `cell`
 };
 
 // Exchange over peer memory (NVLink): every rank owns one XchgBlock and one double-buffered array of remote arrival
@@ -705,12 +705,15 @@ struct XchgBlock {
     unsigned flagB[MAXR];   // stamp of rank r: its migrant records of this step are in
     long long births[MAXR];
     int recvCount;          // migrant records reserved in recv[] this step
-    int pad[31];
+    int recvCap;            // records the owner's buffer holds (read by the peers when they connect)
+    int rowWords;           // 64-bit words per genome row (0: no Genetics); the rows follow the records, one per record slot
+    int pad[29];
 };
 static_assert(sizeof(XchgBlock) % 32 == 0, "the migrant records follow the header");
 struct PeerTable {
     int *arriveRemote[MAXR];  // [2][nCells] per rank
     XchgBlock *x[MAXR];
+    int recvCap[MAXR];        // capacity of every rank's receive buffer (the OWNER's, not the sender's)
 };
 
 struct ShardArgs {
@@ -723,18 +726,66 @@ struct ShardArgs {
     int *sendCursor;        // nranks counters
     long long birthOffset;  // births of the lower ranks this step (newborn ids are global ranks); p2p: in DevStats
     int p2p;                // 1: records go straight into the owner's receive buffer
-    int recvCap;            // records per receive buffer
+    int recvCap;            // records of this rank's own receive buffer
     const int *remoteBase;  // per foreign halo cell: first arrival slot of this rank's movers in the owner's cell
     const PeerTable *peers; // device copy
+    // populations with Genetics: the genome row travels with the agent
+    const unsigned long long *pool;  // this rank's genome pool
+    int rowWords;                    // 64-bit words per row
+    unsigned long long *sendGenomes; // NCCL mode: rows packed like sendBuf
 };
 
 __device__ __forceinline__ Migrant *xchg_recv(XchgBlock *x) { return reinterpret_cast<Migrant *>(x + 1); }
+// the genome rows of the received agents follow the `cap` record slots of the owner's buffer
+__device__ __forceinline__ unsigned long long *xchg_genomes(XchgBlock *x, int cap) {
+    return reinterpret_cast<unsigned long long *>(xchg_recv(x) + cap);
+}
 
 __device__ __forceinline__ int shard_owner(const ShardArgs &H, int c) {
     int q = 0;
     while (q + 1 < H.nranks && c >= H.cellBegin[q + 1]) q++;
     return q;
 }
+
+// One leaver per calling lane (the lanes of `who`, a ballot of the callers): its record goes to the owner of cell m.cell,
+// for populations with Genetics followed by its genome row, copied by the whole warp.  Slots of the owner's receive buffer are
+// reserved with ONE remote atomic per (warp, owner), not one per agent.  ALL lanes of the warp must call (who may be 0).
+template <bool GEN>
+__device__ __forceinline__ void send_leavers(const ShardArgs &H, unsigned who, bool leaves, Migrant m, int srcRow) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31);
+    if (who == 0) return;
+    int qo = -1, slot = -1;
+    if (leaves) {
+        qo = shard_owner(H, m.cell);
+        if (H.p2p) {
+            const unsigned peers = __match_any_sync(who, qo);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd_system(&H.peers->x[qo]->recvCount, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            slot = base + __popc(peers & lanemask_lt());
+            if (slot < H.peers->recvCap[qo]) xchg_recv(H.peers->x[qo])[slot] = m;  // the count still grows: the owner sees the overflow
+            else slot = -1;
+        } else {
+            slot = H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1);
+            H.sendBuf[slot] = m;
+        }
+    }
+    if constexpr (GEN) {
+        unsigned todo = __ballot_sync(FULL, leaves && slot >= 0);
+        while (todo) {
+            const int L = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int q = __shfl_sync(FULL, qo, L), sl = __shfl_sync(FULL, slot, L), sr = __shfl_sync(FULL, srcRow, L);
+            unsigned long long *dst = H.p2p ? xchg_genomes(H.peers->x[q], H.peers->recvCap[q]) + (size_t)sl * H.rowWords
+                                            : H.sendGenomes + (size_t)sl * H.rowWords;
+            const unsigned long long *src = H.pool + (size_t)sr * H.rowWords;
+            for (int w = lane; w < H.rowWords; w += 32) dst[w] = src[w];
+        }
+    }
+}
+
 
 // Arrivals cross a shard boundary only in the halo: the cells with a neighbour owned by another rank (the list is the
 // same on every rank, built in qhgb_comm_init).  Their arrival counts travel as one compact array that is summed over
@@ -809,7 +860,8 @@ k_halo_push(int nHalo, const int *__restrict__ halo, const int *__restrict__ cel
 
 // (2) cross-GPU barrier: one warp; lane r tells rank r "I am at `stamp`" and waits for rank r's word.  A rank that
 //     does not show up within ~4 s of GPU clock raises commError (the host fails the step) instead of hanging.
-__global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, const PeerTable *__restrict__ T, DevStats *__restrict__ st) {
+__global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, const PeerTable *__restrict__ T, DevStats *__restrict__ st,
+                           long long timeoutClocks) {
     const int r = threadIdx.x;
     if (r < nranks) {
         __threadfence_system();
@@ -818,7 +870,10 @@ __global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, cons
         volatile unsigned *mine = which ? &T->x[rank]->flagB[r] : &T->x[rank]->flagA[r];
         const long long t0 = clock64();
         while ((int)(*mine - stamp) < 0) {
-            if (clock64() - t0 > 8000000000ll) { st->commError = 1; break; }
+            // a peer that is busy on the host (read-backs, dumps, I/O) may be many seconds behind: the limit is generous and
+            // configurable (QHG_XBARRIER_TIMEOUT_S).  When it does expire the step is void: `halt` makes the remaining kernels
+            // of this and of the queued steps do nothing, the host reports the error and clears both flags (k_clear_halt).
+            if (clock64() - t0 > timeoutClocks) { st->commError = 1; st->halt = 1; break; }
             __nanosleep(200);
         }
         __threadfence_system();
@@ -851,48 +906,99 @@ __global__ void k_halo_merge(int nHalo, const int *__restrict__ halo, int c0, in
 }
 
 // (4) after barrier B: the records the other ranks wrote into this rank's receive buffer go to their slots
+// GEN: one warp per record -- the agent takes a genome row of this rank's pool (the rows after those of the step's births, in
+// the order k_make_offspring hands them out: top of the free stack, then the unused tail) and its genome is copied in
+template <bool GEN>
 __global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable *__restrict__ T, int rank, int recvCap, AgentArrays o,
                                      const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ cursor,
-                                     int storeAge) {
+                                     int storeAge, const GenomeCtl *__restrict__ ctl = nullptr, const int *__restrict__ freeStack = nullptr,
+                                     unsigned long long *__restrict__ pool = nullptr, int rowWords = 0, int poolRows = 0) {
     if (st->overflow || st->oversize || st->halt) return;
     const int n = T->x[rank]->recvCount;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->nRecv = n;
-        if (n > recvCap) st->commError = 2;
+        if (n > recvCap) { st->commError = 2; st->halt = 1; }  // the step is void (k_step_end keeps the old state)
     }
     const Migrant *in = xchg_recv(T->x[rank]);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < min(n, recvCap); i += gridDim.x * blockDim.x) {
+    const int per = GEN ? 32 : 1;  // threads per record
+    const int lane = GEN ? (int)(threadIdx.x & 31) : 0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) / per; i < min(n, recvCap); i += (gridDim.x * blockDim.x) / per) {
         const Migrant m = in[i];
         const int pos = newStart[m.cell] + stay[m.cell] + cursor[m.cell] + (int)m.pad;
-        o.id[pos] = m.id;
-        o.birth[pos] = m.birth;
-        o.lastBirth[pos] = m.lastBirth;
-        o.flags[pos] = (uint8_t)m.flags;
-        if (storeAge) o.age[pos] = m.age;
+        if (lane == 0) {
+            o.id[pos] = m.id;
+            o.birth[pos] = m.birth;
+            o.lastBirth[pos] = m.lastBirth;
+            o.flags[pos] = (uint8_t)(m.flags & 0xffu);
+            if (storeAge) o.age[pos] = m.age;
+        }
+        if constexpr (GEN) {
+            const int e = ctl->nBirths + i, nFree0 = ctl->nFree;
+            const int slot = (e < nFree0) ? freeStack[nFree0 - 1 - e] : ctl->hwm + (e - nFree0);
+            if (slot >= poolRows) { if (lane == 0) st->overflow = 1; continue; }  // k_step_end turns it into `halt`
+            if (lane == 0) { o.gslot[pos] = slot; o.nbabies[pos] = (int)(m.flags >> 8); }
+            const unsigned long long *src = xchg_genomes(T->x[rank], recvCap) + (size_t)i * rowWords;
+            unsigned long long *dst = pool + (size_t)slot * rowWords;
+            for (int w = lane; w < rowWords; w += 32) dst[w] = src[w];
+        }
     }
 }
 
 // the agents Navigate sent far away (k_cell_decide<.., true>): written at their slot in the destination cell; their decision
 // byte goes back to "stays" so that k_free_genomes_dec does not take them for dead
+// Sharded runs: a destination on another rank (far jumps go anywhere; their destination cells are part of the halo list, so the
+// arrival slots were exchanged like those of the boundary cells) -- the record, and the genome row, go to the owner like those of
+// the neighbour movers; the decision byte stays "gone" so that the row is freed here.
 template <bool GEN>
-__global__ void k_place_jumpers(const DevStats *__restrict__ st, const int *__restrict__ jumpCount, const JumpEntry *__restrict__ jumps,
+__global__ void k_place_jumpers(DevStats *__restrict__ st, const int *__restrict__ jumpCount, const JumpEntry *__restrict__ jumps,
                                 int jumpCap, AgentArrays a, AgentArrays o, const int *__restrict__ newStart,
-                                const int *__restrict__ stay, uint8_t *__restrict__ dec, int storeAge) {
+                                const int *__restrict__ stay, uint8_t *__restrict__ dec, int storeAge, ShardArgs H) {
     if (st->overflow || st->oversize || st->halt) return;
+    const unsigned FULL = 0xffffffffu;
     const int n = min(*jumpCount, jumpCap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const JumpEntry e = jumps[i];
-        const int pos = newStart[e.to] + stay[e.to] + e.slot;
-        o.id[pos] = a.id[e.src];
-        o.birth[pos] = a.birth[e.src];
-        o.lastBirth[pos] = a.lastBirth[e.src];
-        o.flags[pos] = (uint8_t)(e.bits & (F_MALE | F_FERTILE));
-        if (storeAge) o.age[pos] = a.age[e.src];
-        if constexpr (GEN) {
-            o.gslot[pos] = a.gslot[e.src];
-            o.nbabies[pos] = a.nbabies[e.src] + ((e.bits & F_BORN) ? 1 : 0);
+    int nSentL = 0;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {  // whole warps: send_leavers is cooperative
+        const int i = i0 + (int)threadIdx.x;
+        const bool act = i < n;
+        JumpEntry e{};
+        if (act) e = jumps[i];
+        const bool leaves = act && H.on && (e.to < H.c0 || e.to >= H.c1);
+        const unsigned who = H.on ? __ballot_sync(FULL, leaves) : 0u;
+        Migrant m{};
+        int srcRow = 0;
+        if (act) {
+            // the jump entry was written before the pairing was settled: whether the agent gave birth is in the committed byte
+            const uint8_t fin = dec[e.src];
+            if (leaves) {
+                m.id = a.id[e.src]; m.birth = a.birth[e.src]; m.lastBirth = a.lastBirth[e.src];
+                m.age = storeAge ? a.age[e.src] : 0.0f;
+                m.cell = e.to;
+                m.flags = (unsigned)(fin & (F_MALE | F_FERTILE));
+                m.pad = (unsigned)((H.p2p ? H.remoteBase[e.to] : 0) + e.slot);
+                if constexpr (GEN) {
+                    srcRow = a.gslot[e.src];
+                    m.flags |= (unsigned)(a.nbabies[e.src] + ((fin & F_BORN) ? 1 : 0)) << 8;
+                }
+                nSentL++;
+            } else {
+                const int pos = newStart[e.to] + stay[e.to] + e.slot;
+                o.id[pos] = a.id[e.src];
+                o.birth[pos] = a.birth[e.src];
+                o.lastBirth[pos] = a.lastBirth[e.src];
+                o.flags[pos] = (uint8_t)(fin & (F_MALE | F_FERTILE));
+                if (storeAge) o.age[pos] = a.age[e.src];
+                if constexpr (GEN) {
+                    o.gslot[pos] = a.gslot[e.src];
+                    o.nbabies[pos] = a.nbabies[e.src] + ((fin & F_BORN) ? 1 : 0);
+                }
+                dec[e.src] = (uint8_t)(fin & 7);  // not dead: k_free_genomes_dec keeps its row
+            }
         }
-        dec[e.src] = (uint8_t)(e.bits & 7);
+        if (who) send_leavers<GEN>(H, who, leaves, m, srcRow);
+    }
+    if (H.on) {
+        nSentL = __reduce_add_sync(FULL, nSentL);
+        if ((threadIdx.x & 31) == 0 && nSentL) atomicAdd(&st->nSent, nSentL);
     }
 }
 
@@ -908,18 +1014,36 @@ k_fill_cells(int cLo, int cHi, const int *__restrict__ cellStart, int *__restric
     }
 }
 
-__global__ void k_place_migrants(const DevStats *__restrict__ st, const Migrant *__restrict__ in, int n, AgentArrays o,
+template <bool GEN>
+__global__ void k_place_migrants(DevStats *__restrict__ st, const Migrant *__restrict__ in, int n, AgentArrays o,
                                  const int *__restrict__ newStart, const int *__restrict__ stay, int *__restrict__ cursor,
-                                 int storeAge) {
+                                 int storeAge, const GenomeCtl *__restrict__ ctl = nullptr, const int *__restrict__ freeStack = nullptr,
+                                 unsigned long long *__restrict__ pool = nullptr, const unsigned long long *__restrict__ inGenomes = nullptr,
+                                 int rowWords = 0, int poolRows = 0) {
     if (st->overflow || st->oversize) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->nRecv = n;
+    const int per = GEN ? 32 : 1;
+    const int lane = GEN ? (int)(threadIdx.x & 31) : 0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) / per; i < n; i += (gridDim.x * blockDim.x) / per) {
         const Migrant m = in[i];
-        const int pos = newStart[m.cell] + stay[m.cell] + atomicAdd(&cursor[m.cell], 1);
-        o.id[pos] = m.id;
-        o.birth[pos] = m.birth;
-        o.lastBirth[pos] = m.lastBirth;
-        o.flags[pos] = (uint8_t)m.flags;
-        if (storeAge) o.age[pos] = m.age;
+        int pos = 0;
+        if (lane == 0) pos = newStart[m.cell] + stay[m.cell] + atomicAdd(&cursor[m.cell], 1);
+        if (lane == 0) {
+            o.id[pos] = m.id;
+            o.birth[pos] = m.birth;
+            o.lastBirth[pos] = m.lastBirth;
+            o.flags[pos] = (uint8_t)(m.flags & 0xffu);
+            if (storeAge) o.age[pos] = m.age;
+        }
+        if constexpr (GEN) {
+            const int e = ctl->nBirths + i, nFree0 = ctl->nFree;
+            const int slot = (e < nFree0) ? freeStack[nFree0 - 1 - e] : ctl->hwm + (e - nFree0);
+            if (slot >= poolRows) { if (lane == 0) st->overflow = 1; continue; }
+            if (lane == 0) { o.gslot[pos] = slot; o.nbabies[pos] = (int)(m.flags >> 8); }
+            const unsigned long long *src = inGenomes + (size_t)i * rowWords;
+            unsigned long long *dst = pool + (size_t)slot * rowWords;
+            for (int w = lane; w < rowWords; w += 32) dst[w] = src[w];
+        }
     }
 }
 
@@ -994,7 +1118,8 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
                const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H,
-               const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr) {
+               const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
+               uint8_t *decMark = nullptr) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
     using WSS = typename std::conditional<GEN, WarpSmemSG, WarpSmemS>::type;
     __shared__ WSS smem[CW];
@@ -1090,24 +1215,25 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     const int pos = __shfl_sync(FULL, base, max(dir, 0)) + __popc(mine & lt);
                     const int d = __shfl_sync(FULL, dirCell, max(dir, 0));
                     dirOff += cntL;
+                    const bool leaves = act && H.on && (d < H.c0 || d >= H.c1);  // into a cell of another rank
+                    const unsigned who = H.on ? __ballot_sync(FULL, leaves) : 0u;
+                    Migrant m{};
+                    int srcRow = 0;
                     if (act) {
                         const int64_t id = W.id[x];
                         const float birth = W.birth[x], lastBirth = W.lastBirth[x];
                         const float age = storeAge ? a.age[w0 + x] : 0.0f;
-                        if (H.on && (d < H.c0 || d >= H.c1)) {  // leaves this rank: pack for the owner of cell d
-                            const int qo = shard_owner(H, d);
-                            Migrant m;
+                        if (leaves) {  // the record goes to the owner of cell d (straight into its receive buffer over NVLink, or packed for NCCL)
                             m.id = id; m.birth = birth; m.lastBirth = lastBirth; m.age = age; m.cell = d;
-                            m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = 0;
-                            if (H.p2p) {  // straight into the owner's receive buffer over NVLink
-                                XchgBlock *X = H.peers->x[qo];
-                                const int slot = atomicAdd_system(&X->recvCount, 1);
-                                m.pad = (unsigned)pos;
-                                if (slot < H.recvCap) xchg_recv(X)[slot] = m;
-                                nSentL++;
-                            } else {
-                                H.sendBuf[H.sendOff[qo] + atomicAdd(&H.sendCursor[qo], 1)] = m;
+                            m.flags = (unsigned)(v & (F_MALE | F_FERTILE)); m.pad = (unsigned)pos;
+                            if constexpr (GEN) {
+                                srcRow = a.gslot[w0 + x];
+                                m.flags |= (unsigned)(a.nbabies[w0 + x] + ((v & F_BORN) ? 1 : 0)) << 8;
+                                // its genome row is free once the step's births have read their parents: for k_free_genomes_dec
+                                // the agent is as good as dead
+                                decMark[w0 + x] = (uint8_t)((v & 7) | (DEC_DEAD << DEC_MOVE_SHIFT));
                             }
+                            nSentL++;
                         } else {
                             o.id[pos] = id;
                             o.birth[pos] = birth;
@@ -1120,6 +1246,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                             }
                         }
                     }
+                    if (who) send_leavers<GEN>(H, who, leaves, m, srcRow);
                 }
                 nmv = 0;
                 __syncwarp();
@@ -1189,7 +1316,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
             if (lane == 0 && k + SNST < nWin) issue(k + SNST);
         }
     }
-    if (H.p2p) {
+    if (H.on) {
         nSentL = __reduce_add_sync(FULL, nSentL);
         if (lane == 0 && nSentL) atomicAdd(&st->nSent, nSentL);
     }

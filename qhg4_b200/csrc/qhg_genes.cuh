@@ -187,11 +187,14 @@ __global__ void k_free_genomes_dec(const DevStats *__restrict__ st, GenomeCtl *_
 
 // bookRows: the births of this step took the top min(nBirths, nFree) rows of the free stack and the rest from the unused tail
 // (k_make_offspring); resetBirths: a new step starts with an empty birth list
-__global__ void k_genome_ctl_reset(GenomeCtl *ctl, int bookRows, int resetBirths) {
-    if (bookRows) {
-        const int nb = ctl->nBirths, take = min(nb, ctl->nFree);
+// sharded runs: the agents that arrived from other ranks took the rows after those of the births (k_place_migrants*), `st`
+// then carries their number; the pool has `poolRows` rows
+__global__ void k_genome_ctl_reset(GenomeCtl *ctl, int bookRows, int resetBirths, DevStats *st = nullptr, int arrivals = 0, int poolRows = 0) {
+    if (bookRows && !(st && (st->overflow || st->oversize || st->halt))) {
+        const int nb = ctl->nBirths + ((st && arrivals) ? st->nRecv : 0), take = min(nb, ctl->nFree);
         ctl->nFree -= take;
         ctl->hwm += nb - take;
+        if (st && poolRows > 0 && ctl->hwm > poolRows) st->overflow = 1;
     }
     if (resetBirths) ctl->nBirths = 0;
 }

@@ -770,6 +770,7 @@ __global__ void k_clear_halt(DevStats *st) {
     st->halt = 0;
     st->overflow = 0;
     st->oversize = 0;
+    st->commError = 0;
 }
 
 __global__ void k_fill_age(const DevStats *__restrict__ st, const float *__restrict__ birth, float *__restrict__ age, float t) {

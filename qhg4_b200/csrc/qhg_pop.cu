@@ -38,6 +38,19 @@ int fail(const char *fmt, ...) {
     return -1;
 }
 
+// no exception crosses the C boundary (include/qhg_b200.h): entry points that size host containers from their arguments or
+// from a file run under this guard
+template <class F>
+auto guarded(F f) -> decltype(f()) {
+    try {
+        return f();
+    } catch (const std::exception &e) {
+        return (decltype(f()))fail("%s", e.what());
+    } catch (...) {
+        return (decltype(f()))fail("unknown C++ exception");
+    }
+}
+
 #define CK(call)                                                                                          \
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
@@ -219,8 +232,9 @@ struct qhgb_pop {
     DevBuf<unsigned long long> gpool;
     DevBuf<BirthEntry> births;
     DevBuf<int> father;      // fast path with Genetics: position of the mate of every mother-to-be (k_cell_decide<false, true>)
-    bool genFast = false;    // QHG_GEN_FAST=1: populations with Genetics take the fast path (prepared, not yet the default)
-    bool navFast = false;    // QHG_NAV_FAST=1: programs that end with Navigate take the fast path (prepared, not yet the default)
+    bool genFast = false;    // populations with Genetics take the fast path (QHG_GEN_FAST=0 switches it off)
+    bool navFast = false;    // programs that end with Navigate take the fast path (QHG_NAV_FAST=0 switches it off)
+    bool drownsOnGeo = false; // does the class override updateEvent to kill the agents of flooded / iced cells?
     DevBuf<JumpEntry> jumps; // fast path with Navigate: the agents that jump this step
     DevBuf<int> jumpCount;
     DevBuf<GenomeCtl> gctl;
@@ -259,6 +273,7 @@ struct qhgb_pop {
     int cLo() const { return sharded ? cellBegin[shRank] : 0; }
     int cHi() const { return sharded ? cellBegin[shRank + 1] : nCells; }
     DevBuf<Migrant> sendBuf, recvBuf;
+    DevBuf<unsigned long long> sendGenomes, recvGenomes;  // NCCL exchange of populations with Genetics: the migrants' genome rows
     int *hAllInfo = nullptr;  // pinned: nranks * (nranks + 1) ints
     int64_t lastSent = 0, lastReceived = 0;
     int64_t agentSteps = 0, totSent = 0, totRecv = 0;  // host mirrors of the device-side sums (DevStats)
@@ -781,6 +796,72 @@ int launchScan(qhgb_pop *p) {
     return 0;
 }
 
+// the halo of a sharded run: every cell with a neighbour owned by another rank (tools_ico/EQTileLinks.h:20-24 keeps the same sets
+// per tile), plus every cell Navigate can send an agent to (destinations of the sea-ways, ends of the bridges: far jumps cross
+// any number of shard boundaries).  Arrival counts are exchanged for these cells only; the list is the same on every rank.
+int buildHalo(qhgb_pop *p) {
+    const int nranks = p->shRanks;
+    auto owner = [&](int c) { return (int)(std::upper_bound(p->cellBegin.begin() + 1, p->cellBegin.end(), c) - (p->cellBegin.begin() + 1)); };
+    std::vector<uint8_t> mark(p->nCells, 0);
+    for (int c = 0; c < p->nCells; c++) {
+        const int oc = owner(c);
+        for (int j = 0; j < MAXN; j++) {
+            const int d = p->hNbr[(size_t)c * MAXN + j];
+            if (d >= 0 && owner(d) != oc) { mark[c] = 1; mark[d] = 1; }
+        }
+    }
+    for (int d : p->hDestCell) mark[d] = 1;
+    for (int b : p->hBridges) mark[b] = 1;
+    std::vector<int> halo;
+    for (int c = 0; c < p->nCells; c++) if (mark[c]) halo.push_back(c);
+    p->nHalo = (int)halo.size();
+    CK(p->dHalo.alloc(halo.size() + 1));
+    CK(p->dHaloBuf.alloc(halo.size() + (size_t)nranks * (nranks + 1)));
+    if (!halo.empty()) CK(cudaMemcpyAsync(p->dHalo.p, halo.data(), sizeof(int) * halo.size(), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// how long a rank waits for its peers at a cross-GPU barrier, in GPU clocks (QHG_XBARRIER_TIMEOUT_S seconds, default 600)
+long long xbarrierTimeout() {
+    static long long clocks = 0;
+    if (!clocks) {
+        const char *e = getenv("QHG_XBARRIER_TIMEOUT_S");
+        double s = (e && *e) ? atof(e) : 600.0;
+        if (!(s > 0)) s = 600.0;
+        clocks = (long long)(s * 2.0e9);
+    }
+    return clocks;
+}
+
+// the host has seen a communication error of a sharded step: report it, and clear the device's flags so that the population
+// can be read out (the step itself is lost)
+int commFailure(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    const int err = q.hstats->commError, nRecv = q.hstats->nRecv;
+    LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
+    cudaStreamSynchronize(q.stream);
+    if (err == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
+    return fail("receive buffer too small for the migrants of one step (%d > %d)", nRecv, q.recvCap);
+}
+
+// can the fast path (qhg_cells.cuh) run this program?  The rarer actions exist on the generic path only; Navigate's far jumps
+// are handled when it is the last action of the program.
+bool programTiled(qhgb_pop *p, const ActParams &P, bool *useNav) {
+    qhgb_pop &q = *p;
+    bool tiled = !q.forceGeneric, nav = false;
+    for (int k = 0; k < P.nOps; k++) {
+        const int op = prog_op(P, k);
+        if (op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
+        if (op == OP_NAVIGATE) {
+            if (q.navFast && k == P.nOps - 1 && !P.confine && q.navReady) nav = true;
+            else tiled = false;
+        }
+    }
+    if (useNav) *useNav = tiled && nav;
+    return tiled;
+}
+
 // decide -> scan -> scatter with the given program; used by finalizeStep, by the GEO event and (with an empty
 // program, generic path) to bin freshly uploaded agents by cell.
 //   tiled   = the fast path (qhg_cells.cuh, one warp per cell): needs the current buffer binned by cell
@@ -789,19 +870,9 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     qhgb_pop &q = *p;
     const int n = (int)q.nAgents;
     AgentArrays a = q.arrays(q.cur), o = q.arrays(q.cur ^ 1);
-    bool tiled = binned && !q.forceGeneric && (n > 0 || q.sharded);
-    bool useNav = false;  // Navigate on the fast path (QHG_NAV_FAST=1): it must be the last action, no ConfinedMove, one GPU
-    for (int k = 0; k < P.nOps; k++) {  // far jumps and the rarer actions: generic path only
-        const int op = prog_op(P, k);
-        if (op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
-        if (op == OP_NAVIGATE) {
-            if (q.navFast && k == P.nOps - 1 && !P.confine && !q.sharded && q.navReady) useNav = true;
-            else tiled = false;
-        }
-    }
-    if (!tiled) useNav = false;
+    bool useNav = false;  // Navigate on the fast path: it must be the last action, no ConfinedMove
+    bool tiled = binned && (n > 0 || q.sharded) && programTiled(p, P, &useNav);
     if (q.sharded && binned && !tiled) return fail("a sharded population only runs on the fast path");
-    if (q.sharded && q.genetic) return fail("populations with Genetics cannot be sharded yet (genome rows do not travel with the migrants)");
     long long stepEndBirths = -1;
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // device time of the whole pipeline, gaps between the launches included
     if (q.timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, q.stream); }
@@ -846,11 +917,12 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 const int R = q.shRanks, parity = (int)(q.xStep & 1u);
                 LAUNCH(p, "k_halo_push", k_halo_push, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.nCells, parity,
                        q.arrive.p, q.remoteBase.p, q.dPeers.p, q.dstats.p);
-                LAUNCH(p, "k_xbarrier_counts", k_xbarrier, 1, 32, q.shRank, R, 0, q.xStep + 1, q.dPeers.p, q.dstats.p);
+                LAUNCH(p, "k_xbarrier_counts", k_xbarrier, 1, 32, q.shRank, R, 0, q.xStep + 1, q.dPeers.p, q.dstats.p, xbarrierTimeout());
                 LAUNCH(p, "k_halo_merge", k_halo_merge, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
                        q.nCells, parity, q.dPeers.p, q.shRank, q.arrive.p, q.cursor.p);
                 H.on = 1; H.rank = q.shRank; H.nranks = R; H.c0 = q.cellBegin[q.shRank]; H.c1 = q.cellBegin[q.shRank + 1];
                 H.cellBegin = q.dCellBegin.p; H.p2p = 1; H.recvCap = q.recvCap; H.remoteBase = q.remoteBase.p; H.peers = q.dPeers.p;
+                if (q.genetic) { H.pool = q.gpool.p; H.rowWords = 2 * q.gp.nBlocks; }
                 globalBirths = -2;
             } else if (q.sharded) {
                 // (1) what this rank sends to every other rank, (2) arrivals per halo cell summed over all ranks,
@@ -881,6 +953,12 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 globalBirths = total;
                 if ((size_t)sendOff[R] > q.sendBuf.n) CK(q.sendBuf.alloc((size_t)sendOff[R] * 2 + 1024));
                 if ((size_t)nRecv > q.recvBuf.n) CK(q.recvBuf.alloc((size_t)nRecv * 2 + 1024));
+                if (q.genetic) {  // the genome rows travel in a second pair of buffers, indexed like the records
+                    const size_t row = 2 * (size_t)q.gp.nBlocks;
+                    if (q.sendBuf.n * row > q.sendGenomes.n) CK(q.sendGenomes.alloc(q.sendBuf.n * row));
+                    if (q.recvBuf.n * row > q.recvGenomes.n) CK(q.recvGenomes.alloc(q.recvBuf.n * row));
+                    H.pool = q.gpool.p; H.rowWords = (int)row; H.sendGenomes = q.sendGenomes.p;
+                }
                 CK(cudaMemcpyAsync(q.dSendOff.p, sendOff.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, q.stream));
                 CK(cudaMemsetAsync(q.dSendCursor.p, 0, sizeof(int) * R, q.stream));
                 H.on = 1; H.rank = q.shRank; H.nranks = R; H.c0 = q.cellBegin[q.shRank]; H.c1 = q.cellBegin[q.shRank + 1];
@@ -893,24 +971,25 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             if (q.genetic) {
                 LAUNCH(p, "k_cell_scatter_genetic", k_cell_scatter<true>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                        q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H,
-                       q.father.p, q.births.p, q.gctl.p);
+                       q.father.p, q.births.p, q.gctl.p, q.dec.p);
                 if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
-                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge);
-                // genomes of the newborns (parents are read from the old buffer), then the rows of the dead are freed
-                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
-                       q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
-                LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0);
-                LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor(n), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
+                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             } else {
             LAUNCH(p, "k_cell_scatter", k_cell_scatter<false>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
                    q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H);
             if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
-                               q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge);
+                               q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             }
+            const int rowW = q.genetic ? 2 * q.gp.nBlocks : 0;
             if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
-                LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p);
-                LAUNCH(p, "k_place_migrants", k_place_migrants_p2p, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
-                       q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
+                LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p, xbarrierTimeout());
+                if (q.genetic) {
+                    LAUNCH(p, "k_place_migrants", k_place_migrants_p2p<true>, q.numSMs * 4, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge, q.gctl.p, q.gfree.p, q.gpool.p, rowW, (int)q.poolRows);
+                } else {
+                    LAUNCH(p, "k_place_migrants", k_place_migrants_p2p<false>, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
+                }
                 q.xStep++;
             } else if (q.sharded) {  // agent migration: packed records between the GPUs (NCCL over NVLink)
                 const int R = q.shRanks;
@@ -921,15 +1000,30 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 for (int r = 0; r < R; r++) {
                     if (sendCnt[r] > 0) NK(g_nccl.Send(q.sendBuf.p + so, (size_t)sendCnt[r] * sizeof(Migrant), ncclUint8, r, q.comm, q.stream));
                     if (recvCnt[r] > 0) NK(g_nccl.Recv(q.recvBuf.p + ro, (size_t)recvCnt[r] * sizeof(Migrant), ncclUint8, r, q.comm, q.stream));
+                    if (q.genetic) {
+                        if (sendCnt[r] > 0) NK(g_nccl.Send(q.sendGenomes.p + (size_t)so * rowW, (size_t)sendCnt[r] * rowW, ncclUint64, r, q.comm, q.stream));
+                        if (recvCnt[r] > 0) NK(g_nccl.Recv(q.recvGenomes.p + (size_t)ro * rowW, (size_t)recvCnt[r] * rowW, ncclUint64, r, q.comm, q.stream));
+                    }
                     so += sendCnt[r];
                     ro += recvCnt[r];
                 }
                 NK(g_nccl.GroupEnd());
                 if (q.timing) { cudaEventRecord(g1, q.stream); q.kt("nccl_sendrecv_migrants").pending.push_back({g0, g1}); }
-                if (nRecv > 0) {
-                    LAUNCH(p, "k_place_migrants", k_place_migrants, q.gridFor(nRecv), 256, q.dstats.p, q.recvBuf.p, nRecv, o,
+                if (q.genetic) {
+                    LAUNCH(p, "k_place_migrants", k_place_migrants<true>, q.gridFor((int64_t)std::max(nRecv, 1) * 32), 256, q.dstats.p, q.recvBuf.p, nRecv, o,
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge, q.gctl.p, q.gfree.p, q.gpool.p, q.recvGenomes.p, rowW, (int)q.poolRows);
+                } else if (nRecv > 0) {
+                    LAUNCH(p, "k_place_migrants", k_place_migrants<false>, q.gridFor(nRecv), 256, q.dstats.p, q.recvBuf.p, nRecv, o,
                            q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
                 }
+            }
+            if (q.genetic) {
+                // genomes of the newborns (parents are read from the old buffer); the rows they and the arrivals took are booked;
+                // then the rows of the dead and of the agents that left the rank are freed
+                LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
+                       q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
+                LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0, q.dstats.p, q.sharded ? 1 : 0, (int)q.poolRows);
+                LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor(n), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
             }
             stepEndBirths = globalBirths;
         } else {
@@ -962,8 +1056,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             return 0;
         }
         if (pullStats(p) != 0) return -1;
-        if (q.hstats->commError == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
-        if (q.hstats->commError == 2) return fail("receive buffer too small for the migrants of one step (%d > %d)", q.hstats->nRecv, q.recvCap);
+        if (q.hstats->commError) return commFailure(p);
         if (tiled && q.sharded && q.p2p) { q.lastSent = q.hstats->nSent; q.lastReceived = q.hstats->nRecv; }
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
             if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
@@ -1018,7 +1111,7 @@ extern "C" {
 const char *qhgb_last_error(void) { return g_err.c_str(); }
 const char *qhgb_version(void) { return "qhg4_b200 0.1 (sm_100a)"; }
 
-int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, int64_t capacity_hint, qhgb_pop **out) {
+static int create_impl(const char *pop_class, int device, int n_cells, int max_neigh, int64_t capacity_hint, qhgb_pop **out) {
     if (!out) return fail("qhgb_create: out is NULL");
     *out = nullptr;
     if (max_neigh != MAXN) return fail("qhgb_create: connectivity %d not supported (the cell struct holds %d neighbours)", max_neigh, MAXN);
@@ -1028,6 +1121,7 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     if (device < 0 || device >= ndev) return fail("qhgb_create: device %d of %d", device, ndev);
     CK(cudaSetDevice(device));
     qhgb_pop *p = new qhgb_pop;
+    *out = p;  // qhgb_create frees it again if anything below fails
     p->popClass = pop_class;
     p->device = device;
     p->nCells = n_cells;
@@ -1035,6 +1129,12 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     if (p->popClass == "tut_EnvironAltPop") {  // populations/tut_EnvironAltPop.cpp:24-53
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}};
+    } else if (p->popClass == "tut_EnvironAltNavPop") {
+        // tut_EnvironAltPop with Navigate and OldAgeDeath added (actions/Navigate.cpp, actions/OldAgeDeath.cpp): the class the
+        // reference driver builds to pin those two actions (NavProbePop, oracle/ref_driver.cpp)
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"Navigate", A_NAVIGATE}, {"OldAgeDeath", A_OLDAGEDEATH}};
     } else if (p->popClass == "tut_EnvironAltConfPop") {
         // tut_EnvironAltPop with ConfinedMove added (actions/ConfinedMove.cpp; carried by 21 of the shipped OoA* classes): the class
         // the reference driver builds to pin the action (ConfProbePop, oracle/ref_driver.cpp)
@@ -1090,23 +1190,25 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
         p->genetic = true;
         p->forceGeneric = true;   // births need the identity of the father: the generic path keeps the full pairing
     } else {
-        delete p;
         return fail("qhgb_create: unknown population class [%s]", pop_class);
     }
+    // only the classes that override updateEvent drown their agents on EVENT_ID_GEO (populations/tut_EnvironAltPop.cpp:93-127,
+    // tut_EnvironCapAltPop.cpp, OoANavGenPop.cpp:179-214; the probe classes derive from tut_EnvironAltPop); the others inherit
+    // SPopulation::updateEvent, which does nothing (core/SPopulation.h:116)
+    p->drownsOnGeo = p->popClass.rfind("tut_Environ", 0) == 0 || p->popClass.rfind("OoANavGen", 0) == 0;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     p->numSMs = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
         const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
-        // QHG_GEN_FAST=1: populations with Genetics take the fast path too (k_cell_decide<false, true> finds the fathers,
-        // k_cell_scatter<true> moves the genome handles and writes the birth records).  Written at the end of round 1 when no GPU
-        // time was left to validate it: OFF unless the variable is set; tests/test_parity_gpu.py has the (skipped) test for it.
+        // populations with Genetics take the fast path too (k_cell_decide<false, true> finds the fathers, k_cell_scatter<true>
+        // moves the genome handles and writes the birth records); QHG_GEN_FAST=0 sends them back to the generic path (testing)
         const char *gf = getenv("QHG_GEN_FAST");
-        if (p->genetic && gf && *gf == '1') { p->genFast = true; p->forceGeneric = false; }
-        // QHG_NAV_FAST=1: the same for programs that end with Navigate (k_cell_decide<.., true> + k_place_jumpers); same status
+        if (p->genetic && !(gf && *gf == '0')) { p->genFast = true; p->forceGeneric = false; }
+        // QHG_NAV_FAST=0: programs that end with Navigate go back to the generic path (k_cell_decide<.., true> + k_place_jumpers otherwise)
         const char *nf = getenv("QHG_NAV_FAST");
-        p->navFast = nf && *nf == '1';
+        p->navFast = !(nf && *nf == '0');
         p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);
     }
     size_t nc = (size_t)n_cells;
@@ -1153,9 +1255,8 @@ int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, i
     CK(cudaMemsetAsync(p->dstats.p, 0, sizeof(DevStats), p->stream));
     CK(cudaMallocHost(&p->hstats, sizeof(DevStats)));
     memset(p->hstats, 0, sizeof(DevStats));
-    if (capacity_hint > 0 && allocAgents(p, capacity_hint) != 0) { qhgb_destroy(p); return -1; }
+    if (capacity_hint > 0 && allocAgents(p, capacity_hint) != 0) return -1;
     CK(cudaStreamSynchronize(p->stream));
-    *out = p;
     return 0;
 }
 
@@ -1195,7 +1296,7 @@ int qhgb_destroy(qhgb_pop *p) {
     return 0;
 }
 
-int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
+static int set_cells_impl(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
     if (!p || !nbr) return fail("qhgb_set_cells: NULL argument");
     CK(cudaSetDevice(p->device));
     size_t nc = (size_t)p->nCells;
@@ -1221,7 +1322,7 @@ int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
     return 0;
 }
 
-int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n) {
+static int set_env_array_impl(qhgb_pop *p, const char *name, const double *values, int64_t n) {
     if (!p || !name || !values) return fail("qhgb_set_env_array: NULL argument");
     if (n != p->nCells) return fail("qhgb_set_env_array: [%s] has %lld values, grid has %d cells", name, (long long)n, p->nCells);
     CK(cudaSetDevice(p->device));
@@ -1310,9 +1411,15 @@ int qhgb_set_attribute(qhgb_pop *p, const char *name, double value) {
             if (strcmp(name, "Genetics_bits_per_nuc") == 0 && (int)value != std::max(1, p->gp.bitsPerNuc))
                 return fail("[Genetics] This module expects %d bit nucleotides, but the attribute specifies %d bit nucleotides", std::max(1, p->gp.bitsPerNuc), (int)value);
             if (strcmp(name, "Genetics_genome_size") == 0) {
-                if (p->capacity > 0 && p->genetic) return fail("Genetics_genome_size must be set before agents are added");
+                if (p->nAgents > 0 && p->genetic) return fail("Genetics_genome_size must be set before agents are added");
                 p->gp.genomeSize = (int)value;
                 p->gp.nBlocks = ((int)value * std::max(1, p->gp.bitsPerNuc) + 63) / 64;  // numNucs2Blocks, genes/GeneUtils.h:36
+                // buffers made from a capacity hint before the row size was known: the genome pool is sized now
+                if (p->genetic && p->capacity > 0) {
+                    if (cudaSetDevice(p->device) != cudaSuccess) return fail("cudaSetDevice failed");
+                    p->poolRows = 0;
+                    if (allocAgents(p, p->capacity) != 0) return -1;
+                }
             }
             p->attr[name] = value;
             return 0;
@@ -1383,7 +1490,7 @@ int qhgb_set_seed(qhgb_pop *p, const uint32_t *st) {
     return 0;
 }
 
-int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
+static int add_agents_impl(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
                     const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life_state) {
     if (!p || !cell || !id || !birth_time || !gender) return fail("qhgb_add_agents: NULL argument");
     if (p->genetic && p->gp.nBlocks <= 0) return fail("[Genetics] Genetics_genome_size must be set before agents are added");
@@ -1578,10 +1685,10 @@ static bool canDefer(qhgb_pop *p) {
     qhgb_pop &q = *p;
     const char *e = getenv("QHG_RUN_SYNC");
     if (e && *e && *e != '0') return false;
-    if (q.forceGeneric || q.genetic || q.nAgents <= 0 || !q.preLooped) return false;
+    if (q.forceGeneric || q.nAgents <= 0 || !q.preLooped) return false;
     if (q.sharded && !q.p2p) return false;
-    if (q.active(A_NAVIGATE) || q.active(A_WEIGHTEDMOVERAND) || q.active(A_SIGDEATH)) return false;  // generic-path actions
-    return true;
+    const ActParams P = buildProgram(p, nullptr, 0);  // every level of the step
+    return programTiled(p, P, nullptr);  // generic-path actions need the host in every step
 }
 
 // n steps at t0, t0+1, ...  The steps are queued on the stream in windows of up to 64 without a host round trip in between;
@@ -1611,8 +1718,7 @@ int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
         for (; w < W && rc == 0; w++) rc = stepImpl(p, t0 + k + w, true);
         const int hostErr = rc;
         if (pullStats(p) != 0) return -1;
-        if (q.hstats->commError == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
-        if (q.hstats->commError == 2) return fail("receive buffer too small for the migrants of one step (%d > %d)", q.hstats->nRecv, q.recvCap);
+        if (q.hstats->commError) return commFailure(p);
         const int ok = (int)(q.hstats->step - (unsigned)steps0);  // steps of this window the device completed
         q.nAgents = q.hstats->nAgents;
         q.nextID = q.hstats->nextID;
@@ -1664,7 +1770,7 @@ int qhgb_update_event(qhgb_pop *p, int event_id, float t) {
     if (!p) return fail("qhgb_update_event: NULL population");
     if (!p->preLooped) return fail("qhgb_update_event: preLoop has not run");
     CK(cudaSetDevice(p->device));
-    if (event_id == QHGB_EVENT_ID_GEO) {  // populations/tut_EnvironAltPop.cpp:100-127
+    if (event_id == QHGB_EVENT_ID_GEO && p->drownsOnGeo) {  // populations/tut_EnvironAltPop.cpp:100-127
         ActParams P = buildProgram(p, nullptr, t);
         P.nOps = 1;
         P.prog = OP_DROWN;
@@ -1753,7 +1859,7 @@ int qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out) {
     return 0;
 }
 
-int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
+static int64_t get_agents_impl(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
                         uint8_t *gender, float *age, float *last_birth, uint32_t *life_state, int64_t *mate_id) {
     if (!p) { fail("qhgb_get_agents: NULL population"); return -1; }
     if (cudaSetDevice(p->device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1; }
@@ -1817,13 +1923,19 @@ int qhgb_get_birth_death_probs(qhgb_pop *p, double *b, double *d) {
     return 0;
 }
 
-int qhgb_set_navigation(qhgb_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+static int set_navigation_impl(qhgb_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
                         const double *dist, int n_bridges, const int32_t *bridges) {
     if (!p || (n_ports > 0 && (!port_cell || !port_ptr || !dest_cell || !dist)) || (n_bridges > 0 && !bridges))
         return fail("qhgb_set_navigation: NULL argument");
     if (!p->findKind(A_NAVIGATE)) return fail("qhgb_set_navigation: population [%s] has no Navigate action", p->popClass.c_str());
-    p->hPortCell.assign(port_cell, port_cell + n_ports);
-    p->hPortPtr.assign(port_ptr, port_ptr + n_ports + 1);
+    if (n_ports < 0 || n_bridges < 0) return fail("qhgb_set_navigation: negative count");
+    if (n_ports == 0) {  // a Navigation group without sea-ways: bridges only
+        p->hPortCell.clear();
+        p->hPortPtr.assign(1, 0);
+    } else {
+        p->hPortCell.assign(port_cell, port_cell + n_ports);
+        p->hPortPtr.assign(port_ptr, port_ptr + n_ports + 1);
+    }
     const int nd = n_ports > 0 ? port_ptr[n_ports] : 0;
     // the reference keeps the destinations of a port in a std::map keyed by cell (core/Navigation.h:13-16): ascending order
     p->hDestCell.clear(); p->hDist.clear();
@@ -1839,9 +1951,14 @@ int qhgb_set_navigation(qhgb_pop *p, int n_ports, const int32_t *port_cell, cons
     }
     p->hPortPtr[n_ports] = (int)p->hDestCell.size();
     (void)nd;
-    p->hBridges.assign(bridges, bridges + 2 * (size_t)n_bridges);
+    if (n_bridges > 0) p->hBridges.assign(bridges, bridges + 2 * (size_t)n_bridges); else p->hBridges.clear();
     for (int b : p->hBridges) if (b < 0 || b >= p->nCells) return fail("qhgb_set_navigation: bridge cell %d", b);
     p->navNeedUpdate = true;
+    if (!p->cellBegin.empty() && p->shRanks > 1) {  // sharded: the destinations join the cells whose arrivals are exchanged
+        CK(cudaSetDevice(p->device));
+        CK(cudaStreamSynchronize(p->stream));
+        if (buildHalo(p) != 0) return -1;
+    }
     return 0;
 }
 
@@ -1932,7 +2049,7 @@ int qhgb_comm_get_unique_id(void *out, int nbytes) {
     return 0;
 }
 
-int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin) {
+static int comm_init_impl(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin) {
     if (!p || !unique_id || !cell_begin) return fail("qhgb_comm_init: NULL argument");
     if (p->nAgents > 0 || p->preLooped) return fail("qhgb_comm_init: must be called before agents are added");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("qhgb_comm_init: rank %d of %d", rank, nranks);
@@ -1954,25 +2071,7 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
     CK(p->dSendCursor.alloc(nranks));
     CK(cudaMallocHost(&p->hAllInfo, sizeof(int) * nranks * (nranks + 1)));
     CK(cudaMemcpyAsync(p->dCellBegin.p, p->cellBegin.data(), sizeof(int) * (nranks + 1), cudaMemcpyHostToDevice, p->stream));
-    // the halo: every cell with a neighbour owned by another rank (tools_ico/EQTileLinks.h:20-24 keeps the same sets per tile)
-    {
-        auto owner = [&](int c) { return (int)(std::upper_bound(p->cellBegin.begin() + 1, p->cellBegin.end(), c) - (p->cellBegin.begin() + 1)); };
-        std::vector<uint8_t> mark(p->nCells, 0);
-        for (int c = 0; c < p->nCells; c++) {
-            const int oc = owner(c);
-            for (int j = 0; j < MAXN; j++) {
-                const int d = p->hNbr[(size_t)c * MAXN + j];
-                if (d >= 0 && owner(d) != oc) { mark[c] = 1; mark[d] = 1; }
-            }
-        }
-        std::vector<int> halo;
-        for (int c = 0; c < p->nCells; c++) if (mark[c]) halo.push_back(c);
-        p->nHalo = (int)halo.size();
-        CK(p->dHalo.alloc(halo.size() + 1));
-        CK(p->dHaloBuf.alloc(halo.size() + (size_t)nranks * (nranks + 1)));
-        if (!halo.empty()) CK(cudaMemcpyAsync(p->dHalo.p, halo.data(), sizeof(int) * halo.size(), cudaMemcpyHostToDevice, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
-    }
+    if (buildHalo(p) != 0) return -1;
     p->sharded = nranks > 1;
     return 0;
 }
@@ -1983,7 +2082,7 @@ int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, con
 // step), so the whole generator state is the step counter; agents are written as the records qhgb_get_agents returns
 // (their order inside a cell carries no information).  File: one fixed header, then flat little-endian arrays.
 
-int qhgb_dump_state(qhgb_pop *p, const char *path) {
+static int dump_state_impl(qhgb_pop *p, const char *path) {
     if (!p || !path) return fail("qhgb_dump_state: NULL argument");
     if (!p->preLooped || p->inStep) return fail("qhgb_dump_state: only between steps (after preLoop / finalizeStep)");
     if (p->subs.size() > 8) return fail("qhgb_dump_state: more than 8 sub-evaluators");
@@ -2022,7 +2121,7 @@ int qhgb_dump_state(qhgb_pop *p, const char *path) {
     return 0;
 }
 
-int qhgb_restore_state(qhgb_pop *p, const char *path) {
+static int restore_state_impl(qhgb_pop *p, const char *path) {
     if (!p || !path) return fail("qhgb_restore_state: NULL argument");
     if (p->preLooped || p->nAgents > 0) return fail("qhgb_restore_state: the population must be configured (cells, environment, attributes, priorities) but empty");
     FILE *f = fopen(path, "rb");
@@ -2035,6 +2134,15 @@ int qhgb_restore_state(qhgb_pop *p, const char *path) {
         return fail("qhgb_restore_state: the dump is of [%s], %d cells, %d genome words -- not this population", h.popClass, h.nCells, h.rowWords);
     }
     const int64_t n = h.nAgents;
+    {   // a corrupt header must not size the buffers below: the counts have to be plausible and the file as long as they say
+        if (n < 0 || n > (int64_t)2000000000 || h.rowWords < 0 || h.rowWords > (1 << 20)) { fclose(f); return fail("qhgb_restore_state: [%s] has a corrupt header (%lld agents)", path, (long long)n); }
+        const long long per = 4 + 8 + 4 + 1 + 4 + 4 + 4 + 8ll * h.rowWords + (h.genetic ? 4 : 0);
+        const long long need = (long long)sizeof(h) + n * per + 8ll * h.nCells * WSTRIDE + (h.haveCap ? 8ll * h.nCells : 0);
+        fseek(f, 0, SEEK_END);
+        const long long have = ftell(f);
+        fseek(f, (long)sizeof(h), SEEK_SET);
+        if (have < need) { fclose(f); return fail("qhgb_restore_state: [%s] is truncated (%lld of %lld bytes)", path, have, need); }
+    }
     std::vector<int32_t> cell(n);
     std::vector<int64_t> id(n);
     std::vector<float> birth(n), age(n), last(n);
@@ -2079,12 +2187,19 @@ int qhgb_comm_p2p_handle(qhgb_pop *p, void *out, int nbytes) {
     if (p->shRanks > MAXR) return fail("qhgb_comm_p2p_handle: at most %d ranks", MAXR);
     CK(cudaSetDevice(p->device));
     if (!p->xchg) {
+        if (p->genetic && p->gp.nBlocks <= 0) return fail("[Genetics] Genetics_genome_size must be set before the exchange buffers are made");
         p->recvCap = (int)std::max<int64_t>(1 << 16, p->capacity / 8);
-        const size_t xb = sizeof(XchgBlock) + (size_t)p->recvCap * sizeof(Migrant);
+        const int rowWords = p->genetic ? 2 * p->gp.nBlocks : 0;
+        // header, one record slot per migrant, then (Genetics) one genome row per record slot
+        const size_t xb = sizeof(XchgBlock) + (size_t)p->recvCap * (sizeof(Migrant) + (size_t)rowWords * sizeof(unsigned long long));
         CK(cudaMalloc(&p->arriveRemote, sizeof(int) * 2 * (size_t)p->nCells));
         CK(cudaMemset(p->arriveRemote, 0, sizeof(int) * 2 * (size_t)p->nCells));
         CK(cudaMalloc(&p->xchg, xb));
-        CK(cudaMemset(p->xchg, 0, xb));
+        CK(cudaMemset(p->xchg, 0, sizeof(XchgBlock)));
+        XchgBlock hdr{};
+        hdr.recvCap = p->recvCap;  // the peers check their slots against the OWNER's capacity
+        hdr.rowWords = rowWords;
+        CK(cudaMemcpy(p->xchg, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
         CK(p->remoteBase.alloc((size_t)p->nCells));
     }
     cudaIpcMemHandle_t h[2];
@@ -2104,10 +2219,12 @@ int qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles) {
     CK(cudaSetDevice(p->device));
     PeerTable T{};
     const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles);
+    const int myRow = p->genetic ? 2 * p->gp.nBlocks : 0;
     for (int r = 0; r < p->shRanks; r++) {
         if (r == p->shRank) {
             T.arriveRemote[r] = p->arriveRemote;
             T.x[r] = p->xchg;
+            T.recvCap[r] = p->recvCap;
             continue;
         }
         void *a = nullptr, *x = nullptr;
@@ -2120,6 +2237,10 @@ int qhgb_comm_p2p_connect(qhgb_pop *p, const void *all_handles) {
         p->ipcOpened.push_back(x);
         T.arriveRemote[r] = (int *)a;
         T.x[r] = (XchgBlock *)x;
+        XchgBlock hdr{};  // the owner filled its header before it handed out the handle
+        CK(cudaMemcpy(&hdr, x, sizeof(hdr), cudaMemcpyDeviceToHost));
+        if (hdr.recvCap <= 0 || hdr.rowWords != myRow) return fail("qhgb_comm_p2p_connect: rank %d has %d record slots and %d-word genome rows (this rank: %d words)", r, hdr.recvCap, hdr.rowWords, myRow);
+        T.recvCap[r] = hdr.recvCap;
     }
     CK(p->dPeers.alloc(1));
     CK(cudaMemcpyAsync(p->dPeers.p, &T, sizeof(T), cudaMemcpyHostToDevice, p->stream));
@@ -2172,6 +2293,52 @@ int qhgb_get_kernel_times(qhgb_pop *p, int cap, const char **names, double *ms, 
         if (calls) calls[i] = p->ktimes[i].calls;
     }
     return n;
+}
+
+int qhgb_create(const char *pop_class, int device, int n_cells, int max_neigh, int64_t capacity_hint, qhgb_pop **out) {
+    const int rc = guarded([&]() -> int { return create_impl(pop_class, device, n_cells, max_neigh, capacity_hint, out); });
+    if (rc != 0 && out && *out) {  // a half-built population is not handed out
+        const std::string why = g_err;
+        qhgb_destroy(*out);
+        *out = nullptr;
+        g_err = why;
+    }
+    return rc;
+}
+
+int qhgb_set_cells(qhgb_pop *p, const int32_t *nbr, const int32_t *global_id) {
+    return guarded([&]() -> int { return set_cells_impl(p, nbr, global_id); });
+}
+
+int qhgb_set_env_array(qhgb_pop *p, const char *name, const double *values, int64_t n) {
+    return guarded([&]() -> int { return set_env_array_impl(p, name, values, n); });
+}
+
+int qhgb_add_agents(qhgb_pop *p, int64_t n, const int32_t *cell, const int64_t *id, const float *birth_time,
+                    const uint8_t *gender, const float *age, const float *last_birth, const uint32_t *life_state) {
+    return guarded([&]() -> int { return add_agents_impl(p, n, cell, id, birth_time, gender, age, last_birth, life_state); });
+}
+
+int64_t qhgb_get_agents(qhgb_pop *p, int64_t cap, int32_t *cell, int32_t *cell_id, int64_t *id, float *birth_time,
+                        uint8_t *gender, float *age, float *last_birth, uint32_t *life_state, int64_t *mate_id) {
+    return guarded([&]() -> int64_t { return get_agents_impl(p, cap, cell, cell_id, id, birth_time, gender, age, last_birth, life_state, mate_id); });
+}
+
+int qhgb_set_navigation(qhgb_pop *p, int n_ports, const int32_t *port_cell, const int32_t *port_ptr, const int32_t *dest_cell,
+                        const double *dist, int n_bridges, const int32_t *bridges) {
+    return guarded([&]() -> int { return set_navigation_impl(p, n_ports, port_cell, port_ptr, dest_cell, dist, n_bridges, bridges); });
+}
+
+int qhgb_comm_init(qhgb_pop *p, int rank, int nranks, const void *unique_id, const int32_t *cell_begin) {
+    return guarded([&]() -> int { return comm_init_impl(p, rank, nranks, unique_id, cell_begin); });
+}
+
+int qhgb_dump_state(qhgb_pop *p, const char *path) {
+    return guarded([&]() -> int { return dump_state_impl(p, path); });
+}
+
+int qhgb_restore_state(qhgb_pop *p, const char *path) {
+    return guarded([&]() -> int { return restore_state_impl(p, path); });
 }
 
 }  // extern "C"

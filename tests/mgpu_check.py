@@ -19,9 +19,117 @@ from qhg4_b200.population import GpuPopulation  # noqa: E402
 FIELDS = ("cell", "id", "birth", "gender", "age", "last_birth", "life")
 
 
+def gather_sorted(parts, fields):
+    allg = {f: np.concatenate([p[f] for p in parts]) for f in fields}
+    order = np.argsort(allg["id"])
+    return {f: v[order] for f, v in allg.items()}
+
+
+def main_genetic(rank, world):
+    """OoANavGenPop WITH Navigate (BASELINE config #5's class) sharded over the ranks: genome rows and m_iNumBabies travel with
+    the migrants, far jumps cross any number of shard boundaries, a GEO + NAV event in the middle -- agents, genomes and
+    NumBabies bit-exact against the unsharded oracle after every step."""
+    from qhg4_b200.icogrid import synthetic_climate
+    from qhg4_b200.params import ooa_nav_gen
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=5)
+    env = synthetic_climate(xyz, alt, seed=6)
+    pop = synthetic_population(60000, alt, seed=6, fertile=True)
+    rng = np.random.default_rng(3)
+    land = np.flatnonzero(alt > 0)
+    occupied = np.unique(pop["cell"])
+    nports = 150
+    ports = rng.choice(occupied[occupied > 8], nports, replace=False).astype(np.int32)
+    ptr = np.arange(0, 4 * nports + 1, 4, dtype=np.int32)
+    dests = rng.choice(land, 4 * nports).astype(np.int32)  # anywhere on the globe: most jumps cross a shard boundary
+    dist_km = rng.uniform(100, 700, 4 * nports)
+    bridges = rng.choice(occupied, (8, 2), replace=False).astype(np.int32)
+    G = 256
+    par = ooa_nav_gen(G, 3, 2e-3)
+    par.modules["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1",
+                               "Navigate_min_dens": "0.0", "Navigate_bridge_prob": "0.3"}
+    par.prios["Navigate"] = 10
+    st = seed_state(43)
+    row = 2 * (G // 64)
+    gen0 = rng.integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=len(nbr)), world)
+    lo, hi = begin[rank], begin[rank + 1]
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env, device=int(os.environ.get("LOCAL_RANK", 0)))
+    sharding.connect(g, begin, rank, world)
+    g.set_navigation(ports, ptr, dests, dist_km, bridges)
+    g.add_agents(pop)
+    own = (pop["cell"] >= lo) & (pop["cell"] < hi)
+    g.set_genomes(gen0[own])
+    g.pre_loop()
+    o = None
+    if rank == 0:
+        from oracle import port
+        o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+        o.set_navigation(ports, ptr, dests, dist_km, bridges)
+        o.add_agents(pop)
+        o.set_genomes(gen0)
+        o.start()
+    fields = FIELDS + ("genome", "nbabies")
+
+    def compare(tag):
+        mine = g.agents()
+        assert np.all((mine["cell"] >= lo) & (mine["cell"] < hi)), "an agent sits on a rank that does not own its cell"
+        gg, gnb = g.genomes(row)
+        rec = {f: mine[f] for f in FIELDS} | {"genome": gg, "nbabies": gnb}
+        parts = [None] * world
+        dist.gather_object(rec, parts if rank == 0 else None, dst=0)
+        cnts = [None] * world
+        dist.gather_object(g.counts(), cnts if rank == 0 else None, dst=0)
+        if rank == 0:
+            got = gather_sorted(parts, fields)
+            oa = o.agents()
+            og, onb = o.genomes(row)
+            oo = np.argsort(oa["id"])
+            assert len(got["id"]) == o.num_agents(), (tag, len(got["id"]), o.num_agents())
+            for f in FIELDS:
+                assert np.array_equal(got[f], oa[f][oo]), (tag, f)
+            assert np.array_equal(got["genome"], og[oo]), (tag, "genomes")
+            assert np.array_equal(got["nbabies"], onb[oo]), (tag, "NumBabies")
+            assert np.array_equal(np.sum(cnts, axis=0), o.counts()), tag
+
+    nsteps, moved = 10, 0
+    for k in range(nsteps):
+        g.step(float(k))
+        moved += g.comm_traffic()[0]
+        if rank == 0:
+            o.step(float(k))
+        compare(k)
+        if k == 4:  # the sea level rises: some bridges drown, agents of flooded cells die, the jump tables are rebuilt on the flush
+            alt2 = alt - 150.0
+            for q in ([g, o] if rank == 0 else [g]):
+                q.set_env("Altitude", alt2)
+                q.update_event(2, 5.0); q.update_event(5, 5.0); q.flush_events(5.0)
+            compare("event")
+    nq = 5  # queued by qhgb_run without a host round trip (peer-memory exchange)
+    a0, s0, _ = g.run_totals()
+    g.run(float(nsteps), nq)
+    a1, s1, _ = g.run_totals()
+    moved += s1 - s0
+    if rank == 0:
+        for k in range(nsteps, nsteps + nq):
+            o.step(float(k))
+    compare("queued")
+    tot = torch.tensor([moved])
+    dist.all_reduce(tot)
+    if rank == 0:
+        how = "peer-memory" if os.environ.get("QHG_P2P", "1") != "0" else "nccl"
+        print(f"mgpu_check ok [genetic]: OoANavGenPop + Navigate, {world} ranks, {nsteps + nq} steps (the last {nq} queued by qhgb_run), {o.num_agents()} agents, "
+              f"{int(tot)} cross-rank migrations incl. far jumps ({how} exchange), agents + genomes + NumBabies bit-exact vs the unsharded oracle")
+
+
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if len(sys.argv) > 1 and sys.argv[1] == "genetic":
+        main_genetic(rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     nbr, xyz = make_ico_grid(31)
     alt = synthetic_altitude(xyz, seed=3)
     pop = synthetic_population(300000, alt, seed=5, fertile=True)

@@ -317,10 +317,13 @@ def test_genotype_distributions_statistically_equivalent_to_reference(bits, ncro
     assert sg.mean() > 1.0
 
 
+@pytest.mark.parametrize("which", ["tutorial", "genetic"])
 @pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
-def test_two_gpu_shards_equal_unsharded_oracle(exchange):
+def test_two_gpu_shards_equal_unsharded_oracle(exchange, which):
     """cell-range sharding on 2 GPUs, migration over peer memory (default) and over NCCL calls: bit-identical to the
-    unsharded oracle (tests/mgpu_check.py)"""
+    unsharded oracle (tests/mgpu_check.py) -- the tutorial population, and OoANavGenPop with Navigate (genome rows travel with
+    the migrants, far jumps cross shard boundaries).  The driver's GPU box has one GPU; the logs of the runs on 2, 4 and 8
+    B200 are kept in profiles/mgpu_check_r02.txt."""
     import os
     import subprocess
     import sys
@@ -330,8 +333,8 @@ def test_two_gpu_shards_equal_unsharded_oracle(exchange):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, QHG_P2P="1" if exchange == "peer-memory" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(root, "tests", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=600, env=env)
+                        "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(root, "tests", "mgpu_check.py")] +
+                       (["genetic"] if which == "genetic" else []), capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout and exchange in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -389,7 +392,7 @@ def test_cap_alt_population_vs_oracle_and_reference(path):
 
 
 @pytest.mark.parametrize("ncross,mut", [(-1, 1e-3), (0, 0.0), (2, 1e-3), (7, 5e-3)])
-def test_genetic_population_bit_exact_vs_oracle(ncross, mut):
+def test_genetic_population_bit_exact_vs_oracle(ncross, mut, path):
     """OoANavGenPop without Navigate (config C3): OldAgeDeath, VerhulstVarK, NPPCapacity, MultiEvaluator[Alt+NPP] and
     Genetics<BitGeneUtils> -- agents AND genomes bit-exact against the oracle's counter mode, for free recombination,
     no recombination and crossovers, with mutations."""
@@ -428,7 +431,7 @@ def test_genetic_population_bit_exact_vs_oracle(ncross, mut):
 
 @pytest.mark.parametrize("cls,bits", [("OoANavGen2bitPop", 2), ("tut_EnvironAltGen2bitPop", 2), ("tut_EnvironAltGenPop", 1)])
 @pytest.mark.parametrize("ncross,mut", [(-1, 2e-3), (3, 5e-3)])
-def test_two_bit_genomes_and_genetics_probe_classes_bit_exact_vs_oracle(cls, bits, ncross, mut):
+def test_two_bit_genomes_and_genetics_probe_classes_bit_exact_vs_oracle(cls, bits, ncross, mut, path):
     """Genetics<.., GeneUtils> (2-bit nucleotides, genes/GeneUtils.cpp: breaks on nucleotide boundaries, doubled mask bits,
     mutation = XOR with 01/10/11) in OoANavGen2bitPop (populations/OoANavGen2bitPop.cpp) and in the probe classes
     tut_EnvironAlt + Genetics, whose oracle WELL mode equals the reference's own Genetics<T,U> genome for genome
@@ -467,19 +470,15 @@ def test_two_bit_genomes_and_genetics_probe_classes_bit_exact_vs_oracle(cls, bit
         GpuPopulation.from_params(par, nbr, alt, state16=st, env=env).modify_attributes("Genetics_bits_per_nuc", 3 - bits)
 
 
-@pytest.mark.skipif(os.environ.get("QHG_GEN_FAST_TEST") != "1",
-                    reason="the fast path for populations with Genetics (QHG_GEN_FAST=1) was written when no GPU time was left in "
-                           "round 1; it is off by default and this test runs once QHG_GEN_FAST_TEST=1 is set")
 @pytest.mark.parametrize("cls,bits", [("OoANavGenPop", 1), ("OoANavGen2bitPop", 2), ("tut_EnvironAltGenPop", 1)])
 @pytest.mark.parametrize("ncross,mut", [(-1, 2e-3), (3, 5e-3), (0, 0.0)])
 def test_genetic_populations_on_the_fast_path(cls, bits, ncross, mut, monkeypatch):
-    """QHG_GEN_FAST=1: k_cell_decide<false, true> ranks both sexes and hands every birth its father, k_cell_scatter<true> moves
+    """The default path of populations with Genetics: k_cell_decide<false, true> ranks both sexes and hands every birth its father, k_cell_scatter<true> moves
     the genome handles and writes the birth records -- agents, genomes and NumBabies must equal the oracle's (and hence the
     generic path's)."""
     from oracle import port
     from qhg4_b200.params import ooa_nav_gen, tut_environ_alt_genetic
     from qhg4_b200.population import GpuPopulation
-    monkeypatch.setenv("QHG_GEN_FAST", "1")
     nbr, xyz, alt, env = _cap_world(S=7, seed=5)
     pop = synthetic_population(12000, alt, seed=6, fertile=True)
     G = 200
@@ -512,7 +511,7 @@ def test_genetic_populations_on_the_fast_path(cls, bits, ncross, mut, monkeypatc
     assert births > 1500 and "k_cell_decide_genetic" in g.kernel_times()
 
 
-def test_navigate_sea_crossings_bit_exact_vs_oracle():
+def test_navigate_sea_crossings_bit_exact_vs_oracle(path):
     """OoANavGenPop WITH Navigate (config C5's action): jumps from port cells to far cells with distance-dependent
     probability, manual bridges, NAV/GEO events rebuilding the tables -- agents and genomes bit-exact against the oracle."""
     from oracle import port
@@ -562,19 +561,14 @@ def test_navigate_sea_crossings_bit_exact_vs_oracle():
     assert far.size == 0 or g.counts()[far].sum() >= 0
 
 
-@pytest.mark.skipif(os.environ.get("QHG_GEN_FAST_TEST") != "1",
-                    reason="Navigate on the fast path (QHG_NAV_FAST=1) was written when no GPU time was left in round 1; it is "
-                           "off by default and this test runs once QHG_GEN_FAST_TEST=1 is set")
 @pytest.mark.parametrize("cls", ["tut_EnvironAltNavPop", "OoANavGenPop"])
 def test_navigate_on_the_fast_path(cls, monkeypatch):
-    """QHG_NAV_FAST=1 (+ QHG_GEN_FAST=1 for the genetic class): the agents of port and bridge cells get a second pass at the end
+    """The default path of programs that end with Navigate: the agents of port and bridge cells get a second pass at the end
     of their cell in k_cell_decide<.., true>, jumpers go through the jump list and k_place_jumpers -- same agents, totals and
     genomes as the oracle, across a GEO + NAV event."""
     from oracle import port
     from qhg4_b200.params import ooa_nav_gen
     from qhg4_b200.population import GpuPopulation
-    monkeypatch.setenv("QHG_NAV_FAST", "1")
-    monkeypatch.setenv("QHG_GEN_FAST", "1")
     nbr, xyz, alt, env = _cap_world(S=7, seed=5)
     rng = np.random.default_rng(3)
     land = np.flatnonzero(alt > 0)
@@ -647,6 +641,13 @@ def test_small_tutorial_populations_bit_exact_vs_oracle(which, path):
         s = g.step_stats()
         assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
         moves += s.moves
+        if k == 6:  # these classes do not override updateEvent: a GEO event that floods the land kills nobody
+            before = g.num_agents()
+            for q in (g, o):
+                q.set_env("Altitude", alt - 800.0)
+                q.update_event(2, 7.0); q.flush_events(7.0)
+            assert g.num_agents() == before == o.num_agents()
+            assert_same_population(g, o, "event")
     assert (moves > 0) == (which != "tut_OldAgeDiePop")
     if which == "tut_SexualPop":
         assert g.num_agents() > 0 and g.step_stats().births > 0
