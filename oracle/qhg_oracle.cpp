@@ -1121,7 +1121,8 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
     } else if (p->popClass == "OoANavGenPop" || p->popClass == "OoANavGen2bitPop") {
         // populations/OoANavGenPop.cpp:33-97; populations/OoANavGen2bitPop.cpp is the same class with Genetics<.., GeneUtils>
         // (2-bit nucleotides) and WITHOUT addObserver(m_pME)
-        if (mode != QOR_MODE_COUNTER) { delete p; return nullptr; }  // these classes are not built in oracle/_ref (no WELL-mode partner)
+        // WELL mode: OoANavGenPop itself is part of oracle/_ref (tests/test_oracle_vs_ref.py pins the class); its 2-bit sibling is not
+        if (mode != QOR_MODE_COUNTER && p->popClass != "OoANavGenPop") { delete p; return nullptr; }
         p->bitsPerNuc = (p->popClass == "OoANavGen2bitPop") ? 2 : 1;
         p->actions = {{"MultiEvaluator[Alt+NPP]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"GetOld", A_GETOLD}, {"OldAgeDeath", A_OLDAGEDEATH}, {"Fertility", A_FERTILITY},

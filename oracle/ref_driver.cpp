@@ -44,6 +44,7 @@
 #include "tut_OldAgeDiePop.h"
 #include "tut_ParthenoPop.h"
 #include "tut_StaticPop.h"
+#include "OoANavGenPop.h"  // the genetic population of BASELINE configs #3 / #5, compiled from populations/OoANavGenPop.cpp as it lies
 #include "Navigation.h"
 #include "Navigate.cpp"  // the reference's action templates, instantiated below for the tutorial agent
 #include "OldAgeDeath.cpp"
@@ -107,6 +108,7 @@ struct PopAccess {
     virtual ulong *genomeRow(int slot) { return nullptr; }
     virtual WELL512 *geneticsWell() { return nullptr; }
     virtual int geneticsInit(int genomeSize, int numCrossOvers, double mutationRate) { return -1; }
+    virtual int numBabies(int slot) { return -1; }  // m_iNumBabies of the OoANavGen agents
 };
 
 template <class PopT, class AgentT>
@@ -121,6 +123,7 @@ struct PopAccessT : PopAccess {
         a.m_fBirthTime = r.birth; a.m_iGender = r.gender;
         if constexpr (requires { a.m_fAge; }) a.m_fAge = r.age;  // tut_StaticPop keeps the bare Agent
         if constexpr (requires { a.m_fLastBirth; }) { a.m_fLastBirth = r.lastBirth; a.m_iMateIndex = -3; }  // the smaller tutorial agents have no such fields
+        if constexpr (requires { a.m_iNumBabies; }) a.m_iNumBabies = 0;  // populations/OoANavGenPop.h:21-27
         // tut_ParthenoPop never writes the mate index of an agent that was read in (populations/tut_ParthenoPop.cpp:76-89);
         // LinearBirth tests it (actions/LinearBirth.cpp:139,142).  In the reference it is whatever LayerBuf's new T[] holds:
         // zero in fresh pages, so the founders do give birth (the tutorial relies on it).  The driver writes that zero.
@@ -178,6 +181,9 @@ struct PopAccessT : PopAccess {
         } else {
             return -1;
         }
+    }
+    int numBabies(int slot) override {
+        if constexpr (requires { pop->m_aAgents[slot].m_iNumBabies; }) return pop->m_aAgents[slot].m_iNumBabies; else return -1;
     }
     WELL512 *geneticsWell() override {
         if constexpr (requires { pop->m_pGenetics; }) return pop->m_pGenetics->m_apWELL[0]; else return nullptr;
@@ -403,6 +409,8 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_ParthenoPop, tut_ParthenoAgent>(new tut_ParthenoPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_StaticPop") {
         s->pa = new PopAccessT<tut_StaticPop, Agent>(new tut_StaticPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97, the shipped class itself
+        s->pa = new PopAccessT<OoANavGenPop, OoANavGenAgent>(new OoANavGenPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
         s->pa = new PopAccessT<tut_EnvironCapAltPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
 #ifdef QHG_WITH_GPU_ADAPTER
@@ -561,6 +569,34 @@ long qref_get_genomes(void *h, long cap, uint64_t *rows) {
         k++;
     }
     return w;
+}
+// m_iNumBabies of every live agent, in the order of qref_get_agents (populations/OoANavGenPop.cpp:243); -1: the class has none
+long qref_get_num_babies(void *h, long cap, int *out) {
+    RefSim *s = (RefSim *)h;
+    int first = s->pa->first();
+    if (first < 0) return 0;
+    long k = 0;
+    for (int i = first; i <= s->pa->last(); i++) {
+        AgentRec a;
+        if (!s->pa->get(i, a)) continue;
+        if (k < cap) out[k] = s->pa->numBabies(i);
+        k++;
+    }
+    return k;
+}
+// is this population class part of this build?
+int qref_has_class(const char *name) {
+    static const char *const known[] = {"tut_EnvironAltPop", "tut_EnvironAltNavPop", "tut_SexualPop", "tut_MovePop", "tut_OldAgeDiePop",
+                                        "tut_EnvironAltConfPop", "tut_EnvironAltVarPop", "tut_EnvironAltGenPop", "tut_EnvironAltGen2bitPop",
+                                        "tut_ParthenoPop", "tut_StaticPop", "tut_EnvironCapAltPop", "OoANavGenPop"};
+    for (const char *k : known) if (std::string(k) == name) return 1;
+    return 0;
+}
+// PopBase::modifyAttributes(name, value) (core/SPopulation.cpp "modifyAttributes": forwarded to every action)
+int qref_modify_attribute(void *h, const char *name, double value) {
+    RefSim *s = (RefSim *)h;
+    Quiet q(s->quiet);
+    return s->pa->base()->modifyAttributes(name, value);
 }
 // state of the Genetics action's generator of thread 0 (built from aiSeeds[1] by WELLUtils::buildWELLs, MD5 of seed phrases)
 int qref_genetics_well(void *h, uint32_t *state16, uint32_t *index) {

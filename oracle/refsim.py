@@ -29,6 +29,17 @@ def adapter_available() -> bool:
     return os.path.exists(ADAPTER_PATH)
 
 
+def has_class(name: str) -> bool:
+    """is this population class part of the reference build in oracle/_ref?"""
+    if not available():
+        return False
+    L = lib()
+    if not hasattr(L, "qref_has_class"):
+        return name.startswith("tut_")
+    L.qref_has_class.argtypes = [C.c_char_p]
+    return bool(L.qref_has_class(name.encode()))
+
+
 def lib(adapter: bool = False):
     global _lib
     if adapter not in _libs:
@@ -60,6 +71,10 @@ def lib(adapter: bool = False):
         L.qref_get_genomes.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.qref_genetics_well.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.qref_genetics_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        if hasattr(L, "qref_get_num_babies"):
+            L.qref_get_num_babies.restype = C.c_long
+            L.qref_get_num_babies.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+            L.qref_modify_attribute.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         for f in ("qref_gene2_crossover", "qref_gene2_freereco", "qref_gene2_mutate"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p] if f == "qref_gene2_crossover" else \
                 ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p] if f == "qref_gene2_freereco" else [C.c_void_p, C.c_void_p, C.c_int, C.c_int])
@@ -166,6 +181,19 @@ class RefSim:
         g = np.zeros((n, row_words), np.uint64)
         assert self.L.qref_get_genomes(self.h, n, _p(g)) == row_words
         return g
+
+    def num_babies(self):
+        """m_iNumBabies of every live agent in the order of agents() (populations/OoANavGenPop.cpp:243)"""
+        n = self.num_agents()
+        out = np.zeros(n, np.int32)
+        assert self.L.qref_get_num_babies(self.h, n, _p(out)) == n
+        return out
+
+    def modify_attribute(self, name: str, value: float):
+        """PopBase::modifyAttributes(name, value)"""
+        rc = self.L.qref_modify_attribute(self.h, name.encode(), float(value))
+        if rc != 0:
+            raise RuntimeError(f"modifyAttributes({name}) -> {rc}")
 
     def genetics_well(self):
         st, idx = np.zeros(16, np.uint32), np.zeros(1, np.uint32)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqhg_b200.so")
 SOURCES = ["qhg_pop.cu"]
-HEADERS = ["qhg_kernels.cuh", "qhg_cells.cuh", "qhg_genes.cuh", "qhg_rng.cuh", os.path.join("..", "..", "include", "qhg_b200.h")]
+HEADERS = ["qhg_kernels.cuh", "qhg_cells.cuh", "qhg_decide.cuh", "qhg_genes.cuh", "qhg_rng.cuh", os.path.join("..", "..", "include", "qhg_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++", "-I/usr/include", "-ldl"]

@@ -1,0 +1,475 @@
+// qhg_decide.cuh -- pass 1 of the fast path, second generation: one warp per BATCH of consecutive cells.
+//
+// k_cell_decide (qhg_cells.cuh) gives every cell its own warp-level prologue, queue flushes, pairing and commit: about 450
+// warp instructions of fixed cost per cell and idle lanes in the last 32-agent chunk of every cell -- 13 % of the pass at
+// 150 agents per cell and more than half of it at 20 (profiles/README.md, round 1).  Here a warp takes up to SB consecutive
+// cells whose agents are ONE contiguous segment of every array (agents are binned by cell) and walks the segment in chunks
+// of 32 agents that may straddle cell boundaries:
+//   * every lane finds the cell of its agent by comparing its position with the (warp-uniform) cell starts of the batch;
+//     per-cell quantities (the LinearBirth / LinearDeath thresholds, the weight row, the neighbours) sit in shared memory,
+//     indexed by the cell's number inside the batch;
+//   * the fertile census is a pair of counters per cell (segmented popcounts, one writer per cell and chunk); the list of
+//     the fertile females and their pairing keys is only built for the cells that need it -- more fertile females than males,
+//     the only case in which "does this birth candidate have a mate" is not simply yes;
+//   * the queues of the rare expensive work (the double-precision atan of ATanDeath, the neighbour choice of the movers)
+//     are flushed when they run full and once at the end of the BATCH, not once per cell;
+//   * the commit splits the lanes among the cells of the batch; tallies of the whole warp are kept in registers and reduced
+//     once per kernel.
+// The per-agent law is exactly that of k_cell_decide (same draws, same thresholds, same decision byte), so the two are
+// interchangeable bit for bit (QHG_DECIDE=cell selects the old kernel; tests/test_parity_gpu.py runs both).
+// Populations with Genetics or Navigate keep k_cell_decide<false, GEN, NAV> (they need per-cell male lists / a port pass).
+#pragma once
+#include "qhg_cells.cuh"
+
+namespace qhg {
+
+constexpr int SB = 8;          // cells a warp takes per grab of the work counter
+constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the provisional decisions in shared memory)
+
+struct SegSmem {
+    double row[SB][8];                 // cumulated weight rows (7 used)
+    unsigned long long tb[SB + 1], td[SB + 1]; // LinearBirth / LinearDeath thresholds of the cells (k_cell_init)
+    int nbr[SB][8];                    // neighbours (6 used)
+    int out[SB][8];                    // movers per (cell, direction)
+    int cs[SB + 8];                    // starts of the cells inside the segment (cs[nc] = its length)
+    int nF[SB], nM[SB], nreal[SB];
+    union {
+        struct {                       // work queues (empty whenever the pairing needs the space below)
+            long long qmId[QCAP];
+            float qaAge[QCAP];
+            uint32_t qaU[QCAP];
+            uint16_t qaJ[QCAP], qmJ[QCAP];
+        } q;
+        struct {                       // pairing of ONE cell with more fertile females than males
+            alignas(16) uint32_t keys[MAXF];
+            uint16_t ffJ[MAXF], candQ[MAXF];
+        } p;
+    } u;
+    alignas(4) uint8_t dec[SEGCAP + 4];  // provisional decisions, shifted by (segment start & 3)
+};
+
+template <bool SPEC>
+__global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
+k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
+             int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
+             int *__restrict__ moveBase) {
+    __shared__ SegSmem smem[DCW];
+    const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
+    SegSmem &S = smem[wid];
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+    if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it
+    const unsigned step = st->step;
+    const unsigned long long prog = SPEC ? PROG_TUT5 : P.prog;
+    const int nOps = SPEC ? 5 : P.nOps;
+    const ProgramInfo I = program_info(prog, nOps);
+    const float tNow = P.t, fertMin = P.fertMinAge, fertMax = P.fertMaxAge, fertInter = P.fertInterbirth;
+    const float atanAgeLo = P.atanAgeLo, atanAgeHi = P.atanAgeHi;
+    const unsigned long long tMove = P.tMove;  // "draw < WeightedMove_prob" as an integer threshold on the 32-bit draw (host)
+    const RngKey key = P.key;
+    const RoundKeys &RK = P.rk;
+    const bool storeAge = !SPEC && P.storeAge != 0;                        // the tutorial order refreshes the age first: never stored
+    const bool selfMate = !SPEC && P.selfMate != 0;                        // tut_ParthenoPop: every female counts as mated
+    const bool confine = !SPEC && P.confine != 0 && E.allowed != nullptr;  // ConfinedMove filters the chosen destinations
+    const bool pairing = selfMate || doPair != 0;                          // without either nobody has a mate: no births
+    int nDeadL = 0, nMoveL = 0, nBornL = 0;   // lane-local tallies, reduced once at the end of the kernel
+    int pendIdx0 = -1, pendIdx1 = -1, pendVal0 = 0, pendVal1 = 0;  // slot reservations whose atomics are still in flight
+
+    for (;;) {
+    int cBase = 0;
+    if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, SB);
+    cBase = __shfl_sync(FULL, cBase, 0);
+    if (cBase >= cHi) break;
+    const int nB = min(SB, cHi - cBase);
+    const int csL = (lane <= nB) ? cellStart[cBase + lane] : 0;
+    int g0 = 0;
+    while (g0 < nB) {
+        // the sub-batch: as many of the remaining cells as fit the shared-memory segment
+        const int s = __shfl_sync(FULL, csL, g0);
+        const unsigned fit = __ballot_sync(FULL, lane > g0 && lane <= nB && csL - s <= SEGCAP);
+        if (!fit) {  // one cell larger than the segment: the host reruns the step on the generic path
+            if (lane == 0) atomicExch(&st->oversize, 1);
+            g0++;
+            continue;
+        }
+        const int g1 = 31 - __clz(fit);
+        const int nc = g1 - g0;
+        const int n = __shfl_sync(FULL, csL, g1) - s;
+        const int c0 = cBase + g0;
+        if (n == 0) { g0 = g1; continue; }  // sea
+
+        // ---- per-cell data of the sub-batch -----------------------------------------------------------------------------
+        // the cell (inside the sub-batch) of position j of the segment: number of cell starts at or below j
+        auto cell_of = [&](int j) {
+            int ci = 0;
+            for (int k = 1; k < nc; k++) ci += (j >= S.cs[k]) ? 1 : 0;
+            return ci;
+        };
+        const int gOff = s & 3;  // shared-memory word k of dec[] then is an aligned global word
+        uint8_t *const sdec = S.dec + gOff;
+        {
+            const int v = __shfl_sync(FULL, csL, min(g0 + lane, 31));
+            if (lane <= nc) S.cs[lane] = v - s;
+        }
+        if (lane < nc) {
+            S.tb[lane] = I.hasVerhulst ? E.TB[c0 + lane] : 0ull;
+            S.td[lane] = I.hasVerhulst ? E.TD[c0 + lane] : 0ull;
+            S.nreal[lane] = E.nNbr[c0 + lane];
+        }
+        if (lane > nc && lane < SB + 8) S.cs[lane] = 0x7fffffff;  // sentinels: the walk below never runs past the last cell
+        for (int q = lane; q < nc * 8; q += 32) {
+            const int ci = q >> 3, k = q & 7;
+            S.row[ci][k] = (k < WSTRIDE) ? E.W[(size_t)(c0 + ci) * WSTRIDE + k] : 0.0;
+            S.nbr[ci][k] = (k < MAXN) ? E.nbr[(size_t)(c0 + ci) * MAXN + k] : -1;
+            S.out[ci][k] = 0;
+        }
+        __syncwarp();
+
+        int nqa = 0, nqm = 0;
+        int confL = 0;  // moves of this lane that ConfinedMove turned back (still counted: core/SPopulation.cpp:1067)
+        auto flush_atan = [&]() {  // ATanDeath::execute, actions/ATanDeath.cpp:75-83, for the queued agents
+            for (int e = lane; e < nqa; e += 32) {
+                const double x = __dmul_rn(P.atanSlope, __dadd_rn((double)S.u.q.qaAge[e], -P.atanMaxAge));
+                const double p = __dadd_rn(0.5, __ddiv_rn(__dmul_rn(P.atanScale, atan_rn(x)), 3.141592653589793));
+                if (u2d(S.u.q.qaU[e]) < p) sdec[S.u.q.qaJ[e]] |= T_ATANDIES;
+            }
+            nqa = 0;
+            __syncwarp();
+        };
+        auto flush_move = [&]() {  // WeightedMove::execute, actions/WeightedMove.cpp:56-98, for the queued agents
+            for (int e = lane; e < nqm; e += 32) {
+                const int j = S.u.q.qmJ[e];
+                const int ci = cell_of(j);
+                const uint32_t u = agent_draws_rk(S.u.q.qmId[e], step, STREAM_ACT1, RK).x;
+                const int nreal = S.nreal[ci];
+                const double *row = S.row[ci];
+                int pick = -1;
+                if (!SPEC && I.randomMove) {  // RandomMove: uniform over "stay" and the neighbours, no ice test
+                    pick = (int)__dmul_rn(u2d(u), (double)(nreal + 1));
+                    if (pick > 0 && S.nbr[ci][pick - 1] >= 0) {
+                        if (confine && !E.allowed[S.nbr[ci][pick - 1]]) { if (!(I.moveAfterAtan && (sdec[j] & T_ATANDIES))) confL++; }
+                        else sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    }
+                    continue;
+                }
+                const double wmax = row[nreal];
+                if (row[0] == wmax) {
+                    pick = (int)u2int(u, 0, nreal + 1);
+                } else {
+                    const double r2 = __dmul_rn(u2d(u), wmax);
+                    for (int q = 0; q < nreal + 1; q++) {
+                        if (r2 < row[q]) { pick = q; break; }
+                    }
+                }
+                if (pick > 0) {
+                    const int dst = S.nbr[ci][pick - 1];
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) {
+                        // ConfinedMove (actions/ConfinedMove.cpp:86-101): registered and counted, but it leads back to the cell it
+                        // starts from -- unless ATanDeath (flushed before, see below) removed the agent before it moved
+                        if (confine && !E.allowed[dst]) { if (!(I.moveAfterAtan && (sdec[j] & T_ATANDIES))) confL++; }
+                        else sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                    }
+                }
+            }
+            nqm = 0;
+            __syncwarp();
+        };
+
+        // the lanes are split among the cells of the sub-batch (32, 16, 8 or 4 lanes per cell) for the census and the commit
+        const int lpcShift = (nc <= 1) ? 5 : (nc <= 2) ? 4 : (nc <= 4) ? 3 : 2;
+        const int LPC = 1 << lpcShift, myc = lane >> lpcShift, li = lane & (LPC - 1);
+        const uint32_t ONES = 0x01010101u;
+        // ---- fertile census (for the pairing): fertile females and males per cell from the flag bytes at step start, four
+        // agents per 32-bit word (the words also warm the cache for the pass below)
+        if (doPair && I.hasVerhulst) {
+            int fF = 0, fM = 0;
+            if (myc < nc) {
+                const int b0 = gOff + S.cs[myc], b1 = gOff + S.cs[myc + 1];
+                const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.flags + (s - gOff));
+                for (int k = (b0 >> 2) + li; 4 * k < b1; k += LPC) {
+                    const uint32_t w = gw[k];
+                    uint32_t vm = ONES;
+                    if (4 * k < b0 || 4 * k + 4 > b1) {
+                        vm = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) if (4 * k + b >= b0 && 4 * k + b < b1) vm |= 1u << (8 * b);
+                    }
+                    const uint32_t fert = (w >> 1) & vm, male = w & ONES;   // F_MALE = 1, F_FERTILE = 2
+                    fF += __popc(fert & ~male);
+                    fM += __popc(fert & male);
+                }
+            }
+            for (int o = LPC >> 1; o > 0; o >>= 1) {
+                fF += __shfl_xor_sync(FULL, fF, o);
+                fM += __shfl_xor_sync(FULL, fM, o);
+            }
+            if (myc < nc && li == 0) { S.nF[myc] = fF; S.nM[myc] = fM; }
+            __syncwarp();
+        }
+
+        // ---- one pass over the segment: all actions, provisional decisions ----------------------------------------------
+        // (arrays are indexed by the global position s + j: base pointers are kernel parameters, one multiply-add per address)
+        int64_t idN = 0; float birthN = 0, lastN = 0, ageN = 0; uint8_t fN = 0;
+        if (lane < n) {
+            const int g = s + lane;
+            idN = a.id[g]; birthN = a.birth[g]; fN = a.flags[g];
+            if (I.hasFert) lastN = a.lastBirth[g];
+            if (storeAge) ageN = a.age[g];
+        }
+        // every lane walks through the cells as its position advances: the cell number and the cell's thresholds stay in registers
+        int ci = -1, nextStart = 0;
+        unsigned long long tbw = 0, tDeath = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < n;
+            while (j >= nextStart) {  // at most once per chunk unless empty cells lie in between
+                ci++;
+                nextStart = S.cs[ci + 1];
+                tbw = S.tb[ci];
+                tDeath = S.td[ci];
+            }
+            const int64_t id = idN; const float birth = birthN, lastBirth = lastN; const uint8_t f0 = fN;
+            float ag = ageN;
+            if (j + 32 < n) {
+                const int g2 = s + j + 32;
+                idN = a.id[g2]; birthN = a.birth[g2]; fN = a.flags[g2];
+                if (I.hasFert) lastN = a.lastBirth[g2];
+                if (storeAge) ageN = a.age[g2];
+            }
+            const uint4 r0 = (SPEC || I.needAct0) ? agent_draws_rk(id, step, STREAM_ACT0, RK) : make_uint4(0, 0, 0, 0);
+            const bool fertF = valid && ((f0 & (F_FERTILE | F_MALE)) == F_FERTILE);
+            bool needAtan = false, needMove = false;
+            uint8_t f = f0 & (F_MALE | F_FERTILE);
+            bool dead = false, cand = false;
+            if constexpr (SPEC) {
+                // GetOld, ATanDeath, WeightedMove, Fertility, Verhulst as straight-line code (tutorial_data/xmldat/tut_EnvironAlt.xml)
+                ag = __fsub_rn(tNow, birth);                                   // actions/GetOld.cpp:37-48
+                const bool above = ag > atanAgeHi;                             // actions/ATanDeath.cpp:66-90: p > 1 above the window,
+                needAtan = valid && (ag >= atanAgeLo) && !above;               //   decided exactly at the flush inside it,
+                dead = above;                                                  //   nobody dies below it
+                needMove = valid && !above && ((unsigned long long)r0.y < tMove);  // actions/WeightedMove.cpp:45-106, neighbour chosen at the flush
+                // actions/Fertility.cpp:49-74
+                const bool fert = (ag > fertMin) && ((f & F_MALE) || ((ag < fertMax) && (__fsub_rn(tNow, lastBirth) > fertInter)));
+                f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
+                // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
+                const bool bPos = (tbw >> 62) & 1ull, bNeg = (tbw >> 63) != 0;
+                const bool below = (unsigned long long)r0.z < (tbw & 0x1ffffffffull);
+                cand = !above && bPos && pairing && fertF && below;            // a birth needs a mate: settled per cell after the pass
+                dead = dead || (bNeg && below) || ((unsigned long long)r0.w < tDeath);
+            } else {
+                bool alive = true;
+#pragma unroll 1
+                for (int k = 0; k < nOps; k++) {
+                    if (!alive) break;
+                    const int op = (int)((prog >> (4 * k)) & 15ull);
+                    if (op == OP_GETOLD) {  // actions/GetOld.cpp:37-48
+                        ag = __fsub_rn(tNow, birth);
+                    } else if (op == OP_ATANDEATH) {  // actions/ATanDeath.cpp:66-90
+                        ag = __fsub_rn(tNow, birth);
+                        if (ag >= atanAgeLo) {
+                            if (ag <= atanAgeHi) needAtan = true;
+                            else alive = false;
+                        }
+                    } else if (op == OP_OLDAGEDEATH) {  // actions/OldAgeDeath.cpp:48-67
+                        ag = __fsub_rn(tNow, birth);
+                        const uint32_t uo = agent_draws(id, step, STREAM_ACT1, key).w;
+                        if ((double)ag > __dadd_rn(P.oadMaxAge, u2range(uo, P.oadLo, P.oadHi))) alive = false;
+                    } else if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) {  // actions/WeightedMove.cpp:45-106, RandomMove.cpp:65-100
+                        if ((unsigned long long)r0.y < tMove) needMove = true;
+                    } else if (op == OP_FERTILITY) {  // actions/Fertility.cpp:49-74
+                        bool fert;
+                        if (!(f & F_MALE)) fert = (ag > fertMin) && (ag < fertMax) && (__fsub_rn(tNow, lastBirth) > fertInter);
+                        else fert = ag > fertMin;
+                        f = (uint8_t)((f & F_MALE) | (fert ? F_FERTILE : 0));
+                    } else if (op == OP_VERHULST) {  // actions/Verhulst.cpp:101-115 -> LinearBirth.cpp:122-168, LinearDeath.cpp:131-153
+                        const bool bPos = (tbw >> 62) & 1ull, bNeg = (tbw >> 63) != 0;
+                        const bool below = (unsigned long long)r0.z < (tbw & 0x1ffffffffull);
+                        if (bPos) {
+                            const bool mayBear = selfMate ? !(f0 & F_MALE) : fertF;
+                            if (mayBear && pairing && below) cand = true;
+                        } else if (bNeg) {
+                            if (below) alive = false;
+                        }
+                        if (alive && (unsigned long long)r0.w < tDeath) alive = false;
+                    } else if (op == OP_DROWN) {  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
+                        if (E.alt[c0 + ci] < 0 || (E.ice && E.ice[c0 + ci])) alive = false;
+                    }
+                }
+                needAtan = needAtan && valid;
+                needMove = needMove && valid;
+                dead = !alive;
+                if (storeAge && valid) a.age[s + j] = ag;
+            }
+            if (valid) sdec[j] = (uint8_t)(f | (cand ? F_BORN : 0) | (dead ? T_DEADNOW : 0));
+            // queue the rare expensive work
+            const unsigned ma = __ballot_sync(FULL, needAtan), mm = __ballot_sync(FULL, needMove);
+            if (needAtan) { const int e = nqa + __popc(ma & lt); S.u.q.qaAge[e] = ag; S.u.q.qaU[e] = r0.x; S.u.q.qaJ[e] = (uint16_t)j; }
+            if (needMove) { const int e = nqm + __popc(mm & lt); S.u.q.qmJ[e] = (uint16_t)j; S.u.q.qmId[e] = id; }
+            nqa += __popc(ma);
+            nqm += __popc(mm);
+            __syncwarp();
+            // flushed when a queue could overflow in the next round, and at the end of the SEGMENT (not of every cell)
+            const bool last = j0 + 32 >= n;
+            // with ConfinedMove the move flush reads the ATanDeath verdicts of its agents: the death queue goes first
+            if (nqa > QCAP - 32 || (last && nqa > 0) || (confine && nqa > 0 && (nqm > QCAP - 32 || (last && nqm > 0)))) flush_atan();
+            if (nqm > QCAP - 32 || (last && nqm > 0)) flush_move();
+        }
+
+        // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------------
+        // fertile females and males are ranked by (random key, id), equal ranks mate.  With nF <= nM every fertile female has
+        // a mate; otherwise the nM females with the smallest keys -- and only the birth candidates need to know.
+        if (!selfMate && doPair && I.hasVerhulst) {
+            unsigned needM = __ballot_sync(FULL, lane < nc && S.nF[lane] > S.nM[lane]);
+            while (needM) {
+                const int ci = __ffs(needM) - 1;
+                needM &= needM - 1;
+                const int b0 = S.cs[ci], b1 = S.cs[ci + 1], nFc = S.nF[ci], nMc = S.nM[ci];
+                if (nFc > MAXF) {
+                    if (lane == 0) atomicExch(&st->oversize, 1);
+                    continue;
+                }
+                {   // no birth candidate in the cell: nothing to settle
+                    bool any = false;
+                    for (int j = b0 + lane; j < b1; j += 32) any |= (sdec[j] & F_BORN) != 0;
+                    if (!__any_sync(FULL, any)) continue;
+                }
+                // the cell's fertile females (by their flags at step start) and, among them, the birth candidates
+                int nF = 0, nCand = 0;
+                for (int j0 = b0; j0 < b1; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool ff = (j < b1) && ((a.flags[s + j] & (F_FERTILE | F_MALE)) == F_FERTILE);
+                    const unsigned m = __ballot_sync(FULL, ff);
+                    const bool isCand = ff && (sdec[j] & F_BORN);
+                    const unsigned mc = __ballot_sync(FULL, isCand);
+                    if (ff) S.u.p.ffJ[nF + __popc(m & lt)] = (uint16_t)j;
+                    if (isCand) S.u.p.candQ[nCand + __popc(mc & lt)] = (uint16_t)(nF + __popc(m & lt));
+                    nF += __popc(m);
+                    nCand += __popc(mc);
+                }
+                __syncwarp();
+                if (nCand == 0) continue;  // warp-uniform
+                for (int q = lane; q < nF; q += 32) S.u.p.keys[q] = agent_draws_rk(a.id[s + S.u.p.ffJ[q]], step, STREAM_PAIR, RK).x;
+                __syncwarp();
+                for (int i = lane; i < nCand; i += 32) {
+                    const int q = S.u.p.candQ[i];
+                    const uint32_t k = S.u.p.keys[q];
+                    // rank = number of smaller keys; four keys per shared-memory load; "<=" counts reveal ties (the key itself is one)
+                    int r = 0, le = 0;
+                    const int nF4 = nF & ~3;
+                    for (int e = 0; e < nF4; e += 4) {
+                        const uint4 kk = *reinterpret_cast<const uint4 *>(&S.u.p.keys[e]);
+                        r += (kk.x < k) + (kk.y < k) + (kk.z < k) + (kk.w < k);
+                        le += (kk.x <= k) + (kk.y <= k) + (kk.z <= k) + (kk.w <= k);
+                    }
+                    for (int e = nF4; e < nF; e++) {
+                        const uint32_t ke = S.u.p.keys[e];
+                        r += (ke < k) ? 1 : 0;
+                        le += (ke <= k) ? 1 : 0;
+                    }
+                    if ((le - r) > 1) {  // equal keys (about one pair in 10^8): the id decides
+                        const int64_t myId = a.id[s + S.u.p.ffJ[q]];
+                        for (int e = 0; e < nF; e++) {
+                            if (e != q && S.u.p.keys[e] == k && a.id[s + S.u.p.ffJ[e]] < myId) r++;
+                        }
+                    }
+                    if (r >= nMc) sdec[S.u.p.ffJ[q]] &= (uint8_t)~F_BORN;  // no mate: no birth
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- commit: final decision bytes, per-cell counts ---------------------------------------------------------------
+        // four agents (one 32-bit word of decision bytes) per lane and round, all byte lanes in parallel
+        {
+            const uint32_t bornVoid = I.bornAfterAtan ? ONES : 0u, moveVoid = I.moveAfterAtan ? ONES : 0u;
+            int stayL = 0, bornL = 0, moveL = 0, outL = 0, cellN = 0;
+            if (myc < nc) {
+                const int b0 = gOff + S.cs[myc], b1 = gOff + S.cs[myc + 1];  // byte range of my cell in S.dec
+                cellN = b1 - b0;
+                const uint32_t *sw = reinterpret_cast<const uint32_t *>(S.dec);
+                uint32_t *gw32 = reinterpret_cast<uint32_t *>(dec + (s - gOff));
+                for (int k = (b0 >> 2) + li; 4 * k < b1; k += LPC) {
+                    const uint32_t w = sw[k];
+                    uint32_t vm = ONES;  // the bytes of this word that belong to my cell
+                    if (4 * k < b0 || 4 * k + 4 > b1) {
+                        vm = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) if (4 * k + b >= b0 && 4 * k + b < b1) vm |= 1u << (8 * b);
+                    }
+                    const uint32_t at = (w >> 6) & ONES, dn = (w >> 7) & ONES, dd = at | dn;
+                    const uint32_t code = (w >> DEC_MOVE_SHIFT) & 0x07070707u;
+                    const uint32_t nz = ((code + 0x07070707u) >> 3) & ONES;       // move code != 0
+                    const uint32_t born = (w >> 2) & ~(at & bornVoid) & ONES;
+                    const uint32_t alive = ~dd & vm;
+                    const uint32_t out = alive & nz;
+                    const uint32_t d7 = (dd << 3) - dd;                            // 7 in every dead byte
+                    const uint32_t fin = (w & 0x03030303u) | (born << 2) | ((code | d7) << DEC_MOVE_SHIFT);
+                    stayL += __popc(alive & ~nz);
+                    bornL += __popc(born & vm);
+                    moveL += __popc(nz & ~(at & moveVoid) & vm);                   // registered moves (core/SPopulation.cpp:1067)
+                    outL += __popc(out);
+                    if (vm == ONES) {
+                        gw32[k] = fin;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) if (vm & (1u << (8 * b))) dec[s - gOff + 4 * k + b] = (uint8_t)(fin >> (8 * b));
+                    }
+                    if (out) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) if (out & (1u << (8 * b))) atomicAdd(&S.out[myc][((code >> (8 * b)) & 7) - 1], 1);
+                    }
+                }
+            }
+            // sums over the lanes of a cell (xor butterflies stay inside the aligned group)
+            for (int o = LPC >> 1; o > 0; o >>= 1) {
+                stayL += __shfl_xor_sync(FULL, stayL, o);
+                bornL += __shfl_xor_sync(FULL, bornL, o);
+                outL += __shfl_xor_sync(FULL, outL, o);
+                moveL += __shfl_xor_sync(FULL, moveL, o);
+            }
+            if (myc < nc && li == 0) {  // a cell belongs to exactly one warp: plain stores
+                stay[c0 + myc] = stayL;
+                birthCount[c0 + myc] = bornL;
+                if (bornL > MAXMOTHERS) atomicExch(&st->oversize, 1);
+                nBornL += bornL;
+                nMoveL += moveL;
+                nDeadL += cellN - stayL - outL;
+            }
+            nMoveL += confL;
+        }
+        __syncwarp();
+        // the movers towards neighbour k take the slots [base, base+cnt) of that cell's arrivals: pass 2 places them without
+        // atomics.  The returned slot is stored one sub-batch later (the atomic's latency stays off the critical path).
+        {
+            if (pendIdx0 >= 0) moveBase[pendIdx0] = pendVal0;
+            if (pendIdx1 >= 0) moveBase[pendIdx1] = pendVal1;
+            pendIdx0 = pendIdx1 = -1;
+            const int q0 = lane, q1 = lane + 32;
+            if (q0 < nc * 8 && (q0 & 7) < MAXN) {
+                const int ci = q0 >> 3, k = q0 & 7, cnt = S.out[ci][k];
+                pendVal0 = cnt ? atomicAdd(&arrive[S.nbr[ci][k]], cnt) : 0;
+                pendIdx0 = (c0 + ci) * MOVE_STRIDE + k;
+            }
+            if (q1 < nc * 8 && (q1 & 7) < MAXN) {
+                const int ci = q1 >> 3, k = q1 & 7, cnt = S.out[ci][k];
+                pendVal1 = cnt ? atomicAdd(&arrive[S.nbr[ci][k]], cnt) : 0;
+                pendIdx1 = (c0 + ci) * MOVE_STRIDE + k;
+            }
+        }
+        __syncwarp();
+        g0 = g1;
+    }
+    }
+    if (pendIdx0 >= 0) moveBase[pendIdx0] = pendVal0;
+    if (pendIdx1 >= 0) moveBase[pendIdx1] = pendVal1;
+    nDeadL = __reduce_add_sync(FULL, nDeadL);
+    nMoveL = __reduce_add_sync(FULL, nMoveL);
+    nBornL = __reduce_add_sync(FULL, nBornL);
+    if (lane == 0) {
+        if (nDeadL) atomicAdd(&st->nDeaths, nDeadL);
+        if (nMoveL) atomicAdd(&st->nMoves, nMoveL);
+        if (nBornL) atomicAdd(&st->nBirths, nBornL);
+    }
+}
+
+}  // namespace qhg

@@ -98,6 +98,7 @@ struct ActParams {
     double oadMaxAge, oadLo, oadHi;
     // WeightedMove (actions/WeightedMove.cpp:45-106)
     double moveProb;
+    unsigned long long tMove;  // ceil(moveProb * 2^32): "32-bit draw / 2^32 < moveProb" as an exact integer test
     // Fertility (actions/Fertility.cpp:49-74)
     float fertMinAge, fertMaxAge, fertInterbirth;
     RngKey key;

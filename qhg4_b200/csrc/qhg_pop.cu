@@ -7,6 +7,7 @@
 // totals.  No CPU fallback exists: every entry point that computes launches kernels from qhg_kernels.cuh.
 #include "../../include/qhg_b200.h"
 #include "qhg_cells.cuh"
+#include "qhg_decide.cuh"
 #include "qhg_genes.cuh"
 
 #include <dlfcn.h>
@@ -234,6 +235,7 @@ struct qhgb_pop {
     DevBuf<int> father;      // fast path with Genetics: position of the mate of every mother-to-be (k_cell_decide<false, true>)
     bool genFast = false;    // populations with Genetics take the fast path (QHG_GEN_FAST=0 switches it off)
     bool navFast = false;    // programs that end with Navigate take the fast path (QHG_NAV_FAST=0 switches it off)
+    bool segDecide = true;   // pass 1 by batches of cells (qhg_decide.cuh); QHG_DECIDE=cell: one warp per cell (qhg_cells.cuh)
     bool drownsOnGeo = false; // does the class override updateEvent to kill the agents of flooded / iced cells?
     DevBuf<JumpEntry> jumps; // fast path with Navigate: the agents that jump this step
     DevBuf<int> jumpCount;
@@ -518,6 +520,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     P.oadLo = 1 - unc * P.oadMaxAge;
     P.oadHi = 1 + unc * P.oadMaxAge;
     P.moveProb = p->findKind(A_RANDOMMOVE) ? p->A("RandomMove_prob") : p->A("WeightedMove_prob");  // a population has one move action
+    P.tMove = (P.moveProb > 0) ? (unsigned long long)ceil(P.moveProb * 4294967296.0) : 0ull;  // exact: a power-of-two scaling
     P.fertMinAge = (float)p->A("Fertility_min_age");
     P.fertMaxAge = (float)p->A("Fertility_max_age");
     P.fertInterbirth = (float)p->A("Fertility_interbirth");
@@ -901,6 +904,13 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_cell_decide_nav", (k_cell_decide<false, false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, (int *)nullptr,
                        q.jumps.p, q.jumpCount.p, jumpCap);
+            } else if (q.segDecide && P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge) {
+                // one warp per batch of cells, the tutorial action order as straight-line code (qhg_decide.cuh)
+                LAUNCH(p, "k_cell_decide", k_seg_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
+            } else if (q.segDecide) {
+                LAUNCH(p, "k_cell_decide_generic", k_seg_decide<false>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
             } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
@@ -1207,6 +1217,8 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
         const char *gf = getenv("QHG_GEN_FAST");
         if (p->genetic && !(gf && *gf == '0')) { p->genFast = true; p->forceGeneric = false; }
         // QHG_NAV_FAST=0: programs that end with Navigate go back to the generic path (k_cell_decide<.., true> + k_place_jumpers otherwise)
+        const char *dk = getenv("QHG_DECIDE");
+        p->segDecide = !(dk && strcmp(dk, "cell") == 0);
         const char *nf = getenv("QHG_NAV_FAST");
         p->navFast = !(nf && *nf == '0');
         p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);

@@ -37,17 +37,18 @@ class PopParams:
                 out.append(f'  <module name="{base}" id="{ident}">')
             else:
                 out.append(f'  <module name="{name}">')
+            sub = {"AltPref": "Alt", "AltCapPref": "Alt", "NPPPref": "NPP"}  # poly-lines of the evaluators inside a MultiEvaluator
             for k, v in pars.items():
-                if base_is_multi(name) and k == "AltPref":
+                if base_is_multi(name) and k in sub:
                     continue
                 out.append(f'    <param name="{k}" value="{v}"/>')
             if base_is_multi(name):  # tutorial_data/xmldat/tut_EnvironCapAlt.xml: the evaluators are sub-modules
-                out.append('    <module name="SingleEvaluator" id="Alt">')
-                if "AltPref" in pars:
-                    out.append(f'      <param name="AltPref" value="{pars["AltPref"]}"/>')
-                out.append("    </module>")
-                out.append('    <module name="SingleEvaluator" id="NPP">')
-                out.append("    </module>")
+                for ident in ("Alt", "NPP"):
+                    out.append(f'    <module name="SingleEvaluator" id="{ident}">')
+                    for k, v in pars.items():
+                        if sub.get(k) == ident:
+                            out.append(f'      <param name="{k}" value="{v}"/>')
+                    out.append("    </module>")
             out.append("  </module>")
         out.append("  <priorities>")
         for name, p in self.prios.items():
@@ -229,6 +230,10 @@ def ooa_nav_gen(genome_size: int = 4096, num_crossover: int = -1, mutation_rate:
     mods["Genetics"] = {"Genetics_genome_size": str(int(genome_size)), "Genetics_num_crossover": str(int(num_crossover)),
                         "Genetics_mutation_rate": repr(float(mutation_rate)), "Genetics_create_new_genome": "0",
                         "Genetics_bits_per_nuc": "1", "Genetics_initial_muts": "none"}
+    # every registered action needs its module entry (core/Prioritizer.cpp getActionParams), with or without a <prio>: Navigate's
+    # values follow useful_stuff/realistic_sap.xml; config C5 adds the priority
+    mods["Navigate"] = {"Navigate_decay": "-0.001", "Navigate_dist0": "150.0", "Navigate_prob0": "0.1", "Navigate_min_dens": "0.0",
+                        "Navigate_bridge_prob": "0.3"}
     return PopParams("OoANavGenPop", modules=mods,
                      prios={"NPPCapacity": 1, "GetOld": 2, "OldAgeDeath": 3, "WeightedMove": 4, "MultiEvaluator[Alt+NPP]": 5,
                             "Fertility": 6, "RandomPair": 7, "VerhulstVarK": 8, "Genetics": 9})

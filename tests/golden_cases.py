@@ -29,6 +29,13 @@ def _oad_par():
     return par
 
 
+def _ooa_par():
+    """OoANavGenPop itself (populations/OoANavGenPop.cpp), Navigate included: the class of BASELINE configs #3 / #5"""
+    par = P.ooa_nav_gen(100, 3, 5e-3)
+    par.prios["Navigate"] = 10
+    return par
+
+
 # name -> (parameter set, needs climate arrays, needs lon/lat, navigation, genome (size, bits) or None, all agents female)
 CASES = {
     "tut_sexual": (lambda: P.tut_sexual(25.0, 0.2), False, False, False, None, False),
@@ -42,6 +49,7 @@ CASES = {
     "move_rand_sig_death": (lambda: P.tut_environ_alt_variants(25.0, True, True), False, False, False, None, False),
     "genetics_1bit_free": (lambda: P.tut_environ_alt_genetic(20.0, 100, -1, 2e-3, 1), False, False, False, (100, 1), False),
     "genetics_2bit_cross": (lambda: P.tut_environ_alt_genetic(20.0, 100, 3, 5e-3, 2), False, False, False, (100, 2), False),
+    "ooa_nav_gen": (_ooa_par, True, False, True, (100, 1), False),
 }
 
 
@@ -115,6 +123,8 @@ def run_case(name, sim_factory, d, well_from=None):
     if "genomes" in d:
         g = s.genomes(d["genomes"].shape[1])
         out["fin_genomes"] = g[0] if isinstance(g, tuple) else g
+        if par.class_name.startswith("OoANavGen"):  # m_iNumBabies, populations/OoANavGenPop.cpp:243
+            out["fin_nbabies"] = g[1] if isinstance(g, tuple) else s.num_babies()
     if CASES[name][1]:
         out["capacities"] = s.capacities()
     return out

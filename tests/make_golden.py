@@ -20,8 +20,27 @@ OUT = os.path.join(ROOT, "tests", "golden")
 POLY = "-0.1 0 0.1 0.01 1500 1.0 2000 1 3000 -9999"  # AltCapPref of tutorial_data/xmldat/tut_EnvironAlt.xml
 
 
+def cases(names):
+    """trajectories of the reference with one thread for the named cases of tests/golden_cases.py"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_cases as gc
+
+    def ref_factory(par, nbr, alt_, st, env):
+        return refsim.RefSim(par, nbr, alt_, threads=1, state16=st, env=env)
+
+    for name in names:
+        d = gc.build_inputs(name)
+        out = gc.run_case(name, ref_factory, d)
+        assert out["totals"][-1] > 0 and out["totals"][-1] != len(d["pop_id"]), name
+        np.savez_compressed(os.path.join(OUT, f"case_{name}.npz"), **d, **{"ref_" + k: v for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:  # only the named cases (a new case does not have to rewrite the other fixtures)
+        cases(sys.argv[1:])
+        print("wrote", sys.argv[1:])
+        return
     # --- utils/WELL512.cpp: default state (app/SimParams.cpp:82-87) and the thread-0 permutation (core/SPopulation.cpp:171-176)
     st = np.array(DEFAULT_STATE, np.uint32)
     st0 = np.array([st[(13 * j) % 16] for j in range(16)], np.uint32)

@@ -553,3 +553,66 @@ def test_genetic_population_counter_mode_properties():
         o.step(float(k))
     g, _ = o.genomes(row)
     assert np.all((g[:, 0] & np.uint64(1)) == 0) and np.all((g[:, 2] & np.uint64(1)) == 0)
+
+
+@pytest.mark.parametrize("navigate", [False, True])
+def test_ooa_nav_gen_pop_class_equals_reference(navigate):
+    """The shipped class of BASELINE configs #3 / #5 as a whole: `OoANavGenPop` compiled from populations/OoANavGenPop.cpp where
+    it lies (oracle/Makefile), its Climate / Vegetation / Navigation objects filled in memory, Genetics configured the way the
+    QDF reader does it (oracle/ref_driver.cpp) -- against the oracle's WELL mode: action order and wiring of the constructor
+    (:33-97), preLoop (:160-169), makePopSpecificOffspring with `m_aAgents[iMother].m_iNumBabies++` (:231-245), updateEvent /
+    flushEvents with the MultiEvaluator registered as an observer (:59, :179-226).  Agents, genomes and NumBabies of every live
+    agent, slot for slot, across a GEO + CLIMATE + VEG + NAV event."""
+    from qhg4_b200.icogrid import synthetic_climate
+    from qhg4_b200.params import ooa_nav_gen
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    env = synthetic_climate(xyz, alt, seed=6)
+    pop = synthetic_population(8000, alt, seed=6, fertile=True)
+    G = 200
+    row = 2 * ((G + 63) // 64)
+    par = ooa_nav_gen(G, 3, 5e-3)
+    rng = np.random.default_rng(3)
+    if navigate:
+        par.prios["Navigate"] = 10
+    occ = np.unique(pop["cell"])
+    ports = np.concatenate([occ[:3], rng.choice(occ[occ > 8], 40, replace=False)]).astype(np.int32)
+    ptr = np.arange(0, 4 * len(ports) + 1, 4, dtype=np.int32)
+    dests = np.concatenate([rng.choice(np.flatnonzero(alt > 0), 4, replace=False) for _ in ports]).astype(np.int32)
+    dist = rng.uniform(100, 700, 4 * len(ports))
+    bridges = rng.choice(occ, (5, 2), replace=False).astype(np.int32)
+    gen0 = rng.integers(0, 2 ** 63, size=(8000, row), dtype=np.int64).astype(np.uint64)
+    st = seed_state(9)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st, env=env)
+    for q in (r, o):
+        q.set_navigation(ports, ptr, dests, dist, bridges)
+        q.add_agents(pop)
+        q.set_genomes(gen0)
+    o.set_genetics_well(*r.genetics_well())
+    r.start(); o.start()
+    assert np.array_equal(r.capacities(), o.capacities())
+    for k in range(12):
+        r.step(float(k)); o.step(float(k))
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        og, onb = o.genomes(row)
+        assert np.array_equal(r.genomes(row), og), k
+        assert np.array_equal(r.num_babies(), onb), k
+        if k == 0:
+            assert np.array_equal(r.weights(), o.weights())
+        if k == 5:  # the sea level rises and the climate cools: drownings, new capacities and weights, rebuilt jump tables
+            alt2 = alt - 120.0
+            for q in (r, o):
+                q.set_env("Altitude", alt2)
+                q.set_env("AnnualMeanTemp", env["AnnualMeanTemp"] - 2.0)
+                q.set_env("BaseNPP", env["BaseNPP"] * 0.9)
+            for ev in (2, 3, 4, 5):  # app/Simulator.cpp:728-735,372-374: updateEvent per id, then one flushEvents
+                r.event(ev, 6.0, flush=(ev == 5)); o.update_event(ev, 6.0)
+            o.flush_events(6.0)
+            assert r.num_agents() == o.num_agents()
+            assert np.array_equal(r.capacities(), o.capacities())
+    assert np.array_equal(r.weights(), o.weights())
+    assert (oa["id"] >= 8000).sum() > 800 and onb.sum() > 0
+    r.close()

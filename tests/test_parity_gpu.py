@@ -40,10 +40,13 @@ def assert_same_population(g, o, step):
     assert np.array_equal(g.counts(), o.counts()), f"step {step}: per-cell counts differ"
 
 
-@pytest.fixture(params=["tiled", "generic"])
+@pytest.fixture(params=["tiled", "tiled-cell", "generic"])
 def path(request, monkeypatch):
-    """both device paths: the tiled shared-memory one and the one-thread-per-agent one"""
-    monkeypatch.setenv("QHG_B200_PATH", request.param)
+    """the device paths: the fast one with pass 1 by batches of cells (qhg_decide.cuh, the default) and with one warp per cell
+    (qhg_cells.cuh, QHG_DECIDE=cell), and the one-thread-per-agent one"""
+    monkeypatch.setenv("QHG_B200_PATH", "generic" if request.param == "generic" else "tiled")
+    if request.param == "tiled-cell":
+        monkeypatch.setenv("QHG_DECIDE", "cell")
     return request.param
 
 
