@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
 #include <numbers>
@@ -337,6 +338,7 @@ struct SubEval {
     std::string polyName;
     bool first = true, needUpdate = false;
     double weight = 0;
+    bool cumulate = true;   // the bCumulate argument of its constructor (actions/SingleEvaluator.cpp:216-243)
 };
 
 struct Action {
@@ -381,6 +383,9 @@ struct qor_pop {
     std::vector<double> cap;      // m_adCapacities
     std::vector<SubEval> subs;    // evaluators of the MultiEvaluator, in construction order
     bool multiFirst = true, multiObserves = false;
+    int multiMode = 0;                  // MultiEvalModes (actions/MultiEvaluator.h:19-26): ADD_SIMPLE, ADD_BLOCK, MUL_SIMPLE, MAX_SIMPLE, MAX_BLOCK, MIN_SIMPLE
+    std::vector<double> singleW;        // m_adSingleEvalWeights: ONE scratch array shared by all evaluators, never cleared between calls
+    std::vector<uint8_t> multiAllowed;  // m_acAllowed (findBlockings)
     // Genetics<.., BitGeneUtils> (actions/Genetics.cpp)
     int genomeSize = 0, numCrossOvers = 0, nBlocks = 0;
     int bitsPerNuc = 1;     // 1: Genetics<.., BitGeneUtils>, 2: Genetics<.., GeneUtils> (OoANavGen2bitPop ...)
@@ -537,30 +542,61 @@ struct qor_pop {
                 int n = nbr[(size_t)c * maxNeigh + k];
                 double cw = (n >= 0) ? out[(size_t)n * stride] : 0;
                 cw = (cw > 0) ? cw : 0;
-                w = w + cw;
+                w = e.cumulate ? w + cw : cw;
                 out[(size_t)c * stride + k + 1] = w;
             }
         }
     }
-    // MultiEvaluator::initialize + addSingleWeights (actions/MultiEvaluator.cpp:142-182,221-253), MODE_ADD_SIMPLE
+    // SingleEvaluator::initialize (actions/SingleEvaluator.cpp:138-167): the shared scratch array is only rewritten when the
+    // evaluator needs an update (or has never run); otherwise it keeps whatever the previous user left in it
+    void subEvalInit(SubEval &e) {
+        if (e.needUpdate || e.first) {
+            e.first = false;
+            std::fill(singleW.begin(), singleW.end(), 0.0);  // calcValues starts with a memset (:175)
+            subEvalCompute(e, singleW);
+        }
+    }
+    // MultiEvaluator::findBlockings (actions/MultiEvaluator.cpp:579-598): an entry is blocked if ANY evaluator is <= 0 there.
+    // No memset before the evaluators' initialize: an evaluator that does not recompute is judged by the array as it stands.
+    void findBlockings() {
+        multiAllowed.assign(W.size(), 1);
+        for (auto &e : subs) {
+            subEvalInit(e);
+            for (size_t i = 0; i < W.size(); i++) if (singleW[i] <= 0) multiAllowed[i] = 0;
+        }
+    }
+    // MultiEvaluator::initialize and the six combine modes (actions/MultiEvaluator.cpp:142-182, 221-253 ADD_SIMPLE, 263-298
+    // ADD_BLOCK, 308-342 MUL_SIMPLE, 350-381 MAX_SIMPLE (the only one that does not cumulate the rows), 391-432 MAX_BLOCK,
+    // 440-478 MIN_SIMPLE).  An evaluator that needs no update contributes the zeros of the memset.
     void multiEvalInit() {
         bool need = false;
         for (auto &e : subs) need |= e.needUpdate;
         if (!(need || multiFirst)) return;
         multiFirst = false;
-        std::fill(W.begin(), W.end(), 0.0);
-        std::vector<double> scratch(W.size());
+        if (singleW.size() != W.size()) singleW.assign(W.size(), 0.0);
         const int stride = maxNeigh + 1;
+        const bool block = multiMode == 1 || multiMode == 4;
+        if (block) findBlockings();
+        const double inf = std::numeric_limits<double>::infinity();
+        const double init = (multiMode == 2) ? 1.0 : (multiMode == 3 || multiMode == 4) ? -inf : (multiMode == 5) ? inf : 0.0;
+        std::fill(W.begin(), W.end(), init);
         for (auto &e : subs) {
-            std::fill(scratch.begin(), scratch.end(), 0.0);
-            if (e.needUpdate || e.first) {  // an evaluator that needs no update contributes zeros (the reference's behaviour)
-                e.first = false;
-                subEvalCompute(e, scratch);
+            std::fill(singleW.begin(), singleW.end(), 0.0);
+            subEvalInit(e);
+            for (size_t i = 0; i < W.size(); i++) {
+                if (block && !multiAllowed[i]) continue;
+                const double v = singleW[i] * e.weight;
+                switch (multiMode) {
+                case 0: case 1: W[i] += v; break;
+                case 2: W[i] *= v; break;
+                case 3: case 4: if (W[i] < v) W[i] = v; break;
+                case 5: if (W[i] > v) W[i] = v; break;
+                }
             }
-            for (size_t i = 0; i < W.size(); i++) W[i] += scratch[i] * e.weight;
         }
-        for (int c = 0; c < nCells; c++)
-            for (int k = 1; k < stride; k++) W[(size_t)c * stride + k] += W[(size_t)c * stride + k - 1];
+        if (multiMode != 3)
+            for (int c = 0; c < nCells; c++)
+                for (int k = 1; k < stride; k++) W[(size_t)c * stride + k] += W[(size_t)c * stride + k - 1];
     }
     // actions/SingleEvaluator.cpp:174-207 (calcValues) and :216-243 (exchangeAndCumulate), bCumulate = true
     void evaluatorCompute() {
@@ -1056,6 +1092,14 @@ struct qor_pop {
     }
 };
 
+// tut_EnvironCapAlt<Mode>Pop -> MultiEvalModes value, -1 for any other name
+static int multiProbeMode(const std::string &cls) {
+    static const char *const names[] = {nullptr, "tut_EnvironCapAltAddBlockPop", "tut_EnvironCapAltMulPop", "tut_EnvironCapAltMaxPop",
+                                        "tut_EnvironCapAltMaxBlockPop", "tut_EnvironCapAltMinPop"};
+    for (int m = 1; m <= 5; m++) if (cls == names[m]) return m;
+    return -1;
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -1108,13 +1152,22 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}};
     } else if (p->popClass == "tut_OldAgeDiePop") {  // populations/tut_OldAgeDiePop.cpp:17-26
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}};
-    } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
+    } else if (p->popClass == "tut_EnvironCapAltPop" || multiProbeMode(p->popClass) >= 0) {  // populations/tut_EnvironCapAltPop.cpp:27-72
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"NPPCapacity", A_NPPCAP}};
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false;
         p->subs = {ea, en};
+        if (multiProbeMode(p->popClass) >= 0) {
+            // probe classes (MultiProbePop<MODE> in oracle/ref_driver.cpp): tut_EnvironCapAltPop whose MultiEvaluator combines in
+            // another mode over NON-cumulating evaluators and is registered as an observer, the way populations/OoANavPop.cpp:50-62
+            // builds its MODE_MUL_SIMPLE evaluator
+            p->multiMode = multiProbeMode(p->popClass);
+            for (auto &e : p->subs) e.cumulate = false;
+            p->subs[0].trigger = EVENT_ID_GEO; p->subs[1].trigger = 4;
+            p->multiObserves = true;
+        }
         p->cap.assign(n_cells, 0.0);
         for (const char *nm : {"Water", "Coastal", "Latitude", "Longitude", "AnnualMeanTemp", "AnnualRainfall", "BaseNPP"})
             p->env[nm].assign(n_cells, 0.0);

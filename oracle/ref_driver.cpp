@@ -53,6 +53,8 @@
 #define EPS EPS_SIGDEATH  // actions/SigDeath.h:14 and actions/ATanDeath.h:14 both define a global `EPS`: no reference TU includes both
 #include "SigDeath.cpp"
 #undef EPS
+#include "SingleEvaluator.cpp"  // for the MultiEvaluator probe classes below
+#include "MultiEvaluator.cpp"
 #include "GeneUtils.h"
 #include "LayerArrBuf.cpp"
 #include "SequenceIOUtils.cpp"
@@ -266,6 +268,32 @@ public:
     Genetics<tut_EnvironAltAgent, U> *m_pGenetics;
 };
 
+// Probe classes for pinning the other five combine modes of MultiEvaluator (actions/MultiEvaluator.cpp:263-478) and findBlockings
+// (:579-598).  Shipped classes use MODE_ADD_SIMPLE and MODE_MUL_SIMPLE only (OoANavPop and six relatives, which need Genetics-free
+// but QDF-bound set-ups); here the reference's own tut_EnvironCapAltPop gets its MultiEvaluator replaced by one of the given mode
+// over NON-cumulating SingleEvaluators, registered as an observer -- exactly how populations/OoANavPop.cpp:50-62 builds its
+// multiplicative evaluator.  MODE_MAX_BLOCK dereferences m_acAllowed, which the reference only allocates for MODE_ADD_BLOCK
+// (actions/MultiEvaluator.cpp:45-47): the probe allocates the array so that the reference's code can run at all.
+template <int MODE>
+class MultiProbePop : public tut_EnvironCapAltPop {
+public:
+    typedef tut_EnvironCapAltAgent A;
+    MultiProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironCapAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        const std::string name = m_pME->getActionName();
+        delete m_pME;
+        MultiEvaluator<A>::evaluatorinfos info;
+        SingleEvaluator<A> *pAlt = new SingleEvaluator<A>(this, m_pCG, "Alt", NULL, (double *)m_pGeography->m_adAltitude, "AltPref", false, EVENT_ID_GEO);
+        info.push_back(std::pair<std::string, Evaluator<A> *>("Multi_weight_alt", pAlt));
+        SingleEvaluator<A> *pCap = new SingleEvaluator<A>(this, m_pCG, "NPP", NULL, m_adCapacities, "", false, EVENT_ID_VEG);
+        info.push_back(std::pair<std::string, Evaluator<A> *>("Multi_weight_npp", pCap));
+        m_pME = new MultiEvaluator<A>(this, m_pCG, "NPP+Alt", m_adEnvWeights, info, MODE, true);
+        if (MODE == MODE_MAX_BLOCK) m_pME->m_acAllowed = new uchar[m_pCG->m_iNumCells * (m_pCG->m_iConnectivity + 1)];
+        addObserver(m_pME);
+        m_prio.m_names[name] = m_pME;  // takes the place of the evaluator the base class registered
+    }
+};
+
 struct RefSim {
     int nCells = 0;
     int nThreads = 1;
@@ -409,6 +437,16 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_ParthenoPop, tut_ParthenoAgent>(new tut_ParthenoPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_StaticPop") {
         s->pa = new PopAccessT<tut_StaticPop, Agent>(new tut_StaticPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltAddBlockPop") {
+        s->pa = new PopAccessT<MultiProbePop<MODE_ADD_BLOCK>, tut_EnvironCapAltAgent>(new MultiProbePop<MODE_ADD_BLOCK>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltMulPop") {
+        s->pa = new PopAccessT<MultiProbePop<MODE_MUL_SIMPLE>, tut_EnvironCapAltAgent>(new MultiProbePop<MODE_MUL_SIMPLE>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltMaxPop") {
+        s->pa = new PopAccessT<MultiProbePop<MODE_MAX_SIMPLE>, tut_EnvironCapAltAgent>(new MultiProbePop<MODE_MAX_SIMPLE>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltMaxBlockPop") {
+        s->pa = new PopAccessT<MultiProbePop<MODE_MAX_BLOCK>, tut_EnvironCapAltAgent>(new MultiProbePop<MODE_MAX_BLOCK>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    } else if (std::string(class_name) == "tut_EnvironCapAltMinPop") {
+        s->pa = new PopAccessT<MultiProbePop<MODE_MIN_SIMPLE>, tut_EnvironCapAltAgent>(new MultiProbePop<MODE_MIN_SIMPLE>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "OoANavGenPop") {  // populations/OoANavGenPop.cpp:33-97, the shipped class itself
         s->pa = new PopAccessT<OoANavGenPop, OoANavGenAgent>(new OoANavGenPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironCapAltPop") {
@@ -588,7 +626,8 @@ long qref_get_num_babies(void *h, long cap, int *out) {
 int qref_has_class(const char *name) {
     static const char *const known[] = {"tut_EnvironAltPop", "tut_EnvironAltNavPop", "tut_SexualPop", "tut_MovePop", "tut_OldAgeDiePop",
                                         "tut_EnvironAltConfPop", "tut_EnvironAltVarPop", "tut_EnvironAltGenPop", "tut_EnvironAltGen2bitPop",
-                                        "tut_ParthenoPop", "tut_StaticPop", "tut_EnvironCapAltPop", "OoANavGenPop"};
+                                        "tut_ParthenoPop", "tut_StaticPop", "tut_EnvironCapAltPop", "OoANavGenPop", "tut_EnvironCapAltAddBlockPop",
+                                        "tut_EnvironCapAltMulPop", "tut_EnvironCapAltMaxPop", "tut_EnvironCapAltMaxBlockPop", "tut_EnvironCapAltMinPop"};
     for (const char *k : known) if (std::string(k) == name) return 1;
     return 0;
 }

@@ -23,8 +23,12 @@
 
 namespace qhg {
 
-constexpr int SB = 8;          // cells a warp takes per grab of the work counter
+#ifndef QHG_SB
+#define QHG_SB 16
+#endif
+constexpr int SB = QHG_SB;     // most cells a warp takes per grab of the work counter (the host passes the actual number)
 constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the provisional decisions in shared memory)
+constexpr int MAXF_S = 384;    // most fertile females of one cell that can be ranked here (larger cells: generic path)
 
 struct SegSmem {
     double row[SB][8];                 // cumulated weight rows (7 used)
@@ -32,7 +36,8 @@ struct SegSmem {
     int nbr[SB][8];                    // neighbours (6 used)
     int out[SB][8];                    // movers per (cell, direction)
     int cs[SB + 8];                    // starts of the cells inside the segment (cs[nc] = its length)
-    int nF[SB], nM[SB], nreal[SB];
+    int nreal[SB];
+    uint32_t mask[3][SEGCAP / 32];     // per chunk of 32 agents: fertile females / fertile males at step start, birth candidates
     union {
         struct {                       // work queues (empty whenever the pairing needs the space below)
             long long qmId[QCAP];
@@ -41,8 +46,8 @@ struct SegSmem {
             uint16_t qaJ[QCAP], qmJ[QCAP];
         } q;
         struct {                       // pairing of ONE cell with more fertile females than males
-            alignas(16) uint32_t keys[MAXF];
-            uint16_t ffJ[MAXF], candQ[MAXF];
+            alignas(16) uint32_t keys[MAXF_S];
+            uint16_t ffJ[MAXF_S], candQ[MAXF_S];
         } p;
     } u;
     alignas(4) uint8_t dec[SEGCAP + 4];  // provisional decisions, shifted by (segment start & 3)
@@ -52,7 +57,8 @@ template <bool SPEC>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-             int *__restrict__ moveBase) {
+             int *__restrict__ moveBase, int grab) {
+    static_assert(SB + 1 <= 32 && SB * 8 <= 4 * 32, "one lane per cell start; at most four rounds of (cell, direction) lanes");
     __shared__ SegSmem smem[DCW];
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
     SegSmem &S = smem[wid];
@@ -73,14 +79,23 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
     const bool confine = !SPEC && P.confine != 0 && E.allowed != nullptr;  // ConfinedMove filters the chosen destinations
     const bool pairing = selfMate || doPair != 0;                          // without either nobody has a mate: no births
     int nDeadL = 0, nMoveL = 0, nBornL = 0;   // lane-local tallies, reduced once at the end of the kernel
-    int pendIdx0 = -1, pendIdx1 = -1, pendVal0 = 0, pendVal1 = 0;  // slot reservations whose atomics are still in flight
+    constexpr int PEND = (SB * 8 + 31) / 32;
+    int pendIdx[PEND], pendVal[PEND];  // slot reservations whose atomics are still in flight
+#pragma unroll
+    for (int r = 0; r < PEND; r++) { pendIdx[r] = -1; pendVal[r] = 0; }
 
+    // cells are handed out dynamically, `grab` at a time (the host picks it from the density: a grab is a few hundred agents);
+    // towards the end of the range the grabs shrink so that no warp is left with a long tail
+    const int nWarps = gridDim.x * DCW;
+    int lastEnd = cLo;  // where this warp's last grab ended: the work counter is at least there
     for (;;) {
+    const int g = max(1, min(min(grab, SB), (cHi - lastEnd) / (2 * nWarps)));
     int cBase = 0;
-    if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, SB);
+    if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, g);
     cBase = __shfl_sync(FULL, cBase, 0);
     if (cBase >= cHi) break;
-    const int nB = min(SB, cHi - cBase);
+    lastEnd = cBase + g;
+    const int nB = min(g, cHi - cBase);
     const int csL = (lane <= nB) ? cellStart[cBase + lane] : 0;
     int g0 = 0;
     while (g0 < nB) {
@@ -176,37 +191,9 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
         };
 
         // the lanes are split among the cells of the sub-batch (32, 16, 8 or 4 lanes per cell) for the census and the commit
-        const int lpcShift = (nc <= 1) ? 5 : (nc <= 2) ? 4 : (nc <= 4) ? 3 : 2;
+        const int lpcShift = (nc <= 1) ? 5 : (nc <= 2) ? 4 : (nc <= 4) ? 3 : (nc <= 8) ? 2 : 1;
         const int LPC = 1 << lpcShift, myc = lane >> lpcShift, li = lane & (LPC - 1);
         const uint32_t ONES = 0x01010101u;
-        // ---- fertile census (for the pairing): fertile females and males per cell from the flag bytes at step start, four
-        // agents per 32-bit word (the words also warm the cache for the pass below)
-        if (doPair && I.hasVerhulst) {
-            int fF = 0, fM = 0;
-            if (myc < nc) {
-                const int b0 = gOff + S.cs[myc], b1 = gOff + S.cs[myc + 1];
-                const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.flags + (s - gOff));
-                for (int k = (b0 >> 2) + li; 4 * k < b1; k += LPC) {
-                    const uint32_t w = gw[k];
-                    uint32_t vm = ONES;
-                    if (4 * k < b0 || 4 * k + 4 > b1) {
-                        vm = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) if (4 * k + b >= b0 && 4 * k + b < b1) vm |= 1u << (8 * b);
-                    }
-                    const uint32_t fert = (w >> 1) & vm, male = w & ONES;   // F_MALE = 1, F_FERTILE = 2
-                    fF += __popc(fert & ~male);
-                    fM += __popc(fert & male);
-                }
-            }
-            for (int o = LPC >> 1; o > 0; o >>= 1) {
-                fF += __shfl_xor_sync(FULL, fF, o);
-                fM += __shfl_xor_sync(FULL, fM, o);
-            }
-            if (myc < nc && li == 0) { S.nF[myc] = fF; S.nM[myc] = fM; }
-            __syncwarp();
-        }
-
         // ---- one pass over the segment: all actions, provisional decisions ----------------------------------------------
         // (arrays are indexed by the global position s + j: base pointers are kernel parameters, one multiply-add per address)
         int64_t idN = 0; float birthN = 0, lastN = 0, ageN = 0; uint8_t fN = 0;
@@ -219,6 +206,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
         // every lane walks through the cells as its position advances: the cell number and the cell's thresholds stay in registers
         int ci = -1, nextStart = 0;
         unsigned long long tbw = 0, tDeath = 0;
+        const bool wantMasks = !selfMate && doPair && I.hasVerhulst;
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
             const bool valid = j < n;
@@ -238,6 +226,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
             }
             const uint4 r0 = (SPEC || I.needAct0) ? agent_draws_rk(id, step, STREAM_ACT0, RK) : make_uint4(0, 0, 0, 0);
             const bool fertF = valid && ((f0 & (F_FERTILE | F_MALE)) == F_FERTILE);
+            const bool fertM = valid && ((f0 & (F_FERTILE | F_MALE)) == (F_FERTILE | F_MALE));
             bool needAtan = false, needMove = false;
             uint8_t f = f0 & (F_MALE | F_FERTILE);
             bool dead = false, cand = false;
@@ -301,6 +290,10 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                 if (storeAge && valid) a.age[s + j] = ag;
             }
             if (valid) sdec[j] = (uint8_t)(f | (cand ? F_BORN : 0) | (dead ? T_DEADNOW : 0));
+            if (wantMasks) {  // the pairing's census: one bit per agent and kind, one word per chunk
+                const unsigned bF = __ballot_sync(FULL, fertF), bM = __ballot_sync(FULL, fertM), bC = __ballot_sync(FULL, cand && valid);
+                if (lane < 3) S.mask[lane][j0 >> 5] = (lane == 0) ? bF : (lane == 1) ? bM : bC;
+            }
             // queue the rare expensive work
             const unsigned ma = __ballot_sync(FULL, needAtan), mm = __ballot_sync(FULL, needMove);
             if (needAtan) { const int e = nqa + __popc(ma & lt); S.u.q.qaAge[e] = ag; S.u.q.qaU[e] = r0.x; S.u.q.qaJ[e] = (uint16_t)j; }
@@ -318,36 +311,44 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
         // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------------
         // fertile females and males are ranked by (random key, id), equal ranks mate.  With nF <= nM every fertile female has
         // a mate; otherwise the nM females with the smallest keys -- and only the birth candidates need to know.
-        if (!selfMate && doPair && I.hasVerhulst) {
-            unsigned needM = __ballot_sync(FULL, lane < nc && S.nF[lane] > S.nM[lane]);
-            while (needM) {
-                const int ci = __ffs(needM) - 1;
-                needM &= needM - 1;
-                const int b0 = S.cs[ci], b1 = S.cs[ci + 1], nFc = S.nF[ci], nMc = S.nM[ci];
-                if (nFc > MAXF) {
+        if (wantMasks) {
+            __syncwarp();
+            for (int ci = 0; ci < nc; ci++) {  // warp-uniform
+                const int b0 = S.cs[ci], b1 = S.cs[ci + 1];
+                if (b1 == b0) continue;
+                // lane k looks at chunk k of the segment, restricted to the positions [b0, b1) of this cell
+                const int lo = b0 - 32 * lane, hi = b1 - 32 * lane;
+                unsigned rm = 0;
+                if (hi > 0 && lo < 32) rm = ((hi >= 32) ? FULL : ((1u << hi) - 1u)) & ((lo <= 0) ? FULL : ~((1u << lo) - 1u));
+                const unsigned wF = rm ? (S.mask[0][lane] & rm) : 0u, wM = rm ? (S.mask[1][lane] & rm) : 0u;
+                const int cF = __popc(wF);
+                const int nF = __reduce_add_sync(FULL, cF), nMc = __reduce_add_sync(FULL, __popc(wM));
+                if (nF <= nMc) continue;  // every fertile female has a mate
+                const unsigned wC = rm ? (S.mask[2][lane] & rm) : 0u;
+                const int cC = __popc(wC);
+                const int nCand = __reduce_add_sync(FULL, cC);
+                if (nCand == 0) continue;  // no birth candidate in the cell: nothing to settle
+                if (nF > MAXF_S) {
                     if (lane == 0) atomicExch(&st->oversize, 1);
                     continue;
                 }
-                {   // no birth candidate in the cell: nothing to settle
-                    bool any = false;
-                    for (int j = b0 + lane; j < b1; j += 32) any |= (sdec[j] & F_BORN) != 0;
-                    if (!__any_sync(FULL, any)) continue;
+                // the cell's fertile females in position order, and the candidates as indices into that list
+                int inF = cF, inC = cC;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int xF = __shfl_up_sync(FULL, inF, o), xC = __shfl_up_sync(FULL, inC, o);
+                    if (lane >= o) { inF += xF; inC += xC; }
                 }
-                // the cell's fertile females (by their flags at step start) and, among them, the birth candidates
-                int nF = 0, nCand = 0;
-                for (int j0 = b0; j0 < b1; j0 += 32) {
-                    const int j = j0 + lane;
-                    const bool ff = (j < b1) && ((a.flags[s + j] & (F_FERTILE | F_MALE)) == F_FERTILE);
-                    const unsigned m = __ballot_sync(FULL, ff);
-                    const bool isCand = ff && (sdec[j] & F_BORN);
-                    const unsigned mc = __ballot_sync(FULL, isCand);
-                    if (ff) S.u.p.ffJ[nF + __popc(m & lt)] = (uint16_t)j;
-                    if (isCand) S.u.p.candQ[nCand + __popc(mc & lt)] = (uint16_t)(nF + __popc(m & lt));
-                    nF += __popc(m);
-                    nCand += __popc(mc);
+                const int baseF = inF - cF;
+                {
+                    unsigned w = wF;
+                    int idx = baseF;
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.p.ffJ[idx++] = (uint16_t)(32 * lane + t); }
+                    w = wC;
+                    idx = inC - cC;
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.p.candQ[idx++] = (uint16_t)(baseF + __popc(wF & ((1u << t) - 1u))); }
                 }
                 __syncwarp();
-                if (nCand == 0) continue;  // warp-uniform
                 for (int q = lane; q < nF; q += 32) S.u.p.keys[q] = agent_draws_rk(a.id[s + S.u.p.ffJ[q]], step, STREAM_PAIR, RK).x;
                 __syncwarp();
                 for (int i = lane; i < nCand; i += 32) {
@@ -441,27 +442,24 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
         // the movers towards neighbour k take the slots [base, base+cnt) of that cell's arrivals: pass 2 places them without
         // atomics.  The returned slot is stored one sub-batch later (the atomic's latency stays off the critical path).
         {
-            if (pendIdx0 >= 0) moveBase[pendIdx0] = pendVal0;
-            if (pendIdx1 >= 0) moveBase[pendIdx1] = pendVal1;
-            pendIdx0 = pendIdx1 = -1;
-            const int q0 = lane, q1 = lane + 32;
-            if (q0 < nc * 8 && (q0 & 7) < MAXN) {
-                const int ci = q0 >> 3, k = q0 & 7, cnt = S.out[ci][k];
-                pendVal0 = cnt ? atomicAdd(&arrive[S.nbr[ci][k]], cnt) : 0;
-                pendIdx0 = (c0 + ci) * MOVE_STRIDE + k;
-            }
-            if (q1 < nc * 8 && (q1 & 7) < MAXN) {
-                const int ci = q1 >> 3, k = q1 & 7, cnt = S.out[ci][k];
-                pendVal1 = cnt ? atomicAdd(&arrive[S.nbr[ci][k]], cnt) : 0;
-                pendIdx1 = (c0 + ci) * MOVE_STRIDE + k;
+#pragma unroll
+            for (int r = 0; r < PEND; r++) {
+                if (pendIdx[r] >= 0) moveBase[pendIdx[r]] = pendVal[r];
+                pendIdx[r] = -1;
+                const int q = lane + 32 * r;
+                if (q < nc * 8 && (q & 7) < MAXN) {
+                    const int ci = q >> 3, k = q & 7, cnt = S.out[ci][k];
+                    pendVal[r] = cnt ? atomicAdd(&arrive[S.nbr[ci][k]], cnt) : 0;
+                    pendIdx[r] = (c0 + ci) * MOVE_STRIDE + k;
+                }
             }
         }
         __syncwarp();
         g0 = g1;
     }
     }
-    if (pendIdx0 >= 0) moveBase[pendIdx0] = pendVal0;
-    if (pendIdx1 >= 0) moveBase[pendIdx1] = pendVal1;
+#pragma unroll
+    for (int r = 0; r < PEND; r++) if (pendIdx[r] >= 0) moveBase[pendIdx[r]] = pendVal[r];
     nDeadL = __reduce_add_sync(FULL, nDeadL);
     nMoveL = __reduce_add_sync(FULL, nMoveL);
     nBornL = __reduce_add_sync(FULL, nBornL);

@@ -93,38 +93,57 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
             const double r = u2d(g0.z);
             while (nMut < G.nBino && r > G.bino[nMut]) nMut++;
         }
-        for (int q = lane; q < row; q += 32) {
-            const int parent = (q < nb) ? 0 : 1;
-            const int b = q - parent * nb;
-            const unsigned long long *P = parent ? gf : gm;
-            const int pick = parent ? i2 : i1;
-            const unsigned long long p0 = P[b], p1 = P[nb + b];
-            unsigned long long t0 = p0, t1 = p1;
-            if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
-                const uint4 d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(b / 2), key);
-                unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
-                if (G.bitsPerNuc == 2) { L &= 0x5555555555555555ull; L += L << 1; }  // makeFreeMask, genes/GeneUtils.cpp:322-340
-                t0 = (L & p0) | (~L & p1);
-                t1 = (L & p1) | (~L & p0);
-            } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
-                unsigned mine[MAX_CROSS];
-                int cnt = 0, below = 0;
-                for (int i = 0; i < nc; i++) {
-                    const unsigned pos = sbr[wl][parent][i];
-                    const int pb = (int)(pos >> 6);
-                    if (pb < b) below++;
-                    else if (pb == b) mine[cnt++] = pos & 63u;
-                }
-                const int cur = below & 1;
-                const unsigned long long c0 = cur ? p1 : p0, c1 = cur ? p0 : p1;
-                if (cnt == 0) { t0 = c0; t1 = c1; }
-                else {
-                    const unsigned long long L = make_multi_mask(mine, cnt);
-                    t0 = (L & c0) | (~L & c1);
-                    t1 = (L & c1) | (~L & c0);
+        // the words of the parents' rows are all requested before the first child word is stored (the rows live in ONE pool: a
+        // store between the loads would order them one memory round trip after the other)
+        constexpr int GU = 4;
+        for (int q0 = 0; q0 < row; q0 += 32 * GU) {
+            unsigned long long w0[GU], w1[GU];
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                const int q = q0 + u * 32 + lane;
+                w0[u] = 0; w1[u] = 0;
+                if (q < row) {
+                    const int parent = (q < nb) ? 0 : 1;
+                    const int b = q - parent * nb;
+                    const unsigned long long *P = parent ? gf : gm;
+                    w0[u] = P[b]; w1[u] = P[nb + b];
                 }
             }
-            gb[q] = pick ? t1 : t0;
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                const int q = q0 + u * 32 + lane;
+                if (q >= row) continue;
+                const int parent = (q < nb) ? 0 : 1;
+                const int b = q - parent * nb;
+                const int pick = parent ? i2 : i1;
+                const unsigned long long p0 = w0[u], p1 = w1[u];
+                unsigned long long t0 = p0, t1 = p1;
+                if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
+                    const uint4 d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(b / 2), key);
+                    unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
+                    if (G.bitsPerNuc == 2) { L &= 0x5555555555555555ull; L += L << 1; }  // makeFreeMask, genes/GeneUtils.cpp:322-340
+                    t0 = (L & p0) | (~L & p1);
+                    t1 = (L & p1) | (~L & p0);
+                } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
+                    unsigned mine[MAX_CROSS];
+                    int cnt = 0, below = 0;
+                    for (int i = 0; i < nc; i++) {
+                        const unsigned pos = sbr[wl][parent][i];
+                        const int pb = (int)(pos >> 6);
+                        if (pb < b) below++;
+                        else if (pb == b) mine[cnt++] = pos & 63u;
+                    }
+                    const int cur = below & 1;
+                    const unsigned long long c0 = cur ? p1 : p0, c1 = cur ? p0 : p1;
+                    if (cnt == 0) { t0 = c0; t1 = c1; }
+                    else {
+                        const unsigned long long L = make_multi_mask(mine, cnt);
+                        t0 = (L & c0) | (~L & c1);
+                        t1 = (L & c1) | (~L & c0);
+                    }
+                }
+                gb[q] = pick ? t1 : t0;
+            }
         }
         __syncwarp();
         // mutateNucs (genes/BitGeneUtils.cpp:57-75): flips commute, one atomic XOR per mutation
@@ -165,28 +184,48 @@ __global__ void k_free_genomes(const DevStats *__restrict__ st, GenomeCtl *__res
     }
 }
 
-// the same on the fast path: an agent died this step if its decision byte says so (move code 7)
-__global__ void k_free_genomes_dec(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, const uint8_t *__restrict__ dec,
-                                   const int *__restrict__ oldSlot, int *__restrict__ freeStack) {
+// the same on the fast path: an agent died this step (or left this rank) if its decision byte says so (move code 7).  Four
+// decision bytes per thread, one push on the free stack per BLOCK and round (1024 agents), not per warp: every push is an
+// atomic on the same counter.
+__global__ void __launch_bounds__(256)
+k_free_genomes_dec(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, const uint8_t *__restrict__ dec,
+                   const int *__restrict__ oldSlot, int *__restrict__ freeStack) {
+    __shared__ int wsum[8];
+    __shared__ int blockBase;
     if (st->overflow || st->oversize || st->halt) return;
     const int n = st->nAgents;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
-        const int i = i0 + (int)threadIdx.x;
-        const bool dead = i < n && (dec[i] >> 3) == 7;
-        const unsigned m = __ballot_sync(0xffffffffu, dead);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&ctl->nFree, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (dead) freeStack[base + __popc(m & lt)] = oldSlot[i];
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(dec);  // the array has AGENT_SLACK bytes past the last agent
+    for (int i0 = blockIdx.x * 1024; i0 < n; i0 += gridDim.x * 1024) {
+        const int i = i0 + 4 * (int)threadIdx.x;
+        uint32_t dead = 0;  // bit b: agent i + b is gone
+        if (i < n) {
+            const uint32_t w = dw[i >> 2];
+#pragma unroll
+            for (int b = 0; b < 4; b++) if (i + b < n && ((w >> (8 * b + 3)) & 31u) == 7u) dead |= 1u << b;
         }
+        const int cnt = __popc(dead);
+        // exclusive prefix of cnt over the block
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; w++) { const int v = wsum[w]; wsum[w] = tot; tot += v; }
+            blockBase = tot ? atomicAdd(&ctl->nFree, tot) : 0;
+        }
+        __syncthreads();
+        int pos = blockBase + wsum[wid] + incl - cnt;
+#pragma unroll
+        for (int b = 0; b < 4; b++) if (dead & (1u << b)) freeStack[pos++] = oldSlot[i + b];
+        __syncthreads();
     }
+    (void)lt;
 }
 
-// bookRows: the births of this step took the top min(nBirths, nFree) rows of the free stack and the rest from the unused tail
-// (k_make_offspring); resetBirths: a new step starts with an empty birth list
 // sharded runs: the agents that arrived from other ranks took the rows after those of the births (k_place_migrants*), `st`
 // then carries their number; the pool has `poolRows` rows
 __global__ void k_genome_ctl_reset(GenomeCtl *ctl, int bookRows, int resetBirths, DevStats *st = nullptr, int arrivals = 0, int poolRows = 0) {

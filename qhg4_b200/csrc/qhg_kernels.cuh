@@ -241,6 +241,30 @@ __global__ void k_multi_accumulate(size_t n, const double *__restrict__ single, 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = __dadd_rn(out[i], __dmul_rn(single[i], weight));
 }
+// the other combine modes of MultiEvaluator (actions/MultiEvaluator.h:19-26; actions/MultiEvaluator.cpp:263-298 ADD_BLOCK,
+// 308-342 MUL_SIMPLE, 350-381 MAX_SIMPLE, 391-432 MAX_BLOCK, 440-478 MIN_SIMPLE): one elementwise pass per evaluator over the
+// nCells x 7 weight rows; `allowed` (BLOCK modes, else NULL) masks the entries findBlockings ruled out
+enum MultiMode : int { MM_ADD_SIMPLE = 0, MM_ADD_BLOCK = 1, MM_MUL_SIMPLE = 2, MM_MAX_SIMPLE = 3, MM_MAX_BLOCK = 4, MM_MIN_SIMPLE = 5 };
+__global__ void k_multi_combine(size_t n, int mode, const double *__restrict__ single, double weight,
+                                const uint8_t *__restrict__ allowed, double *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (allowed && !allowed[i]) continue;
+        const double v = __dmul_rn(single[i], weight);
+        const double o = out[i];
+        if (mode == MM_ADD_SIMPLE || mode == MM_ADD_BLOCK) out[i] = __dadd_rn(o, v);
+        else if (mode == MM_MUL_SIMPLE) out[i] = __dmul_rn(o, v);
+        else if (mode == MM_MAX_SIMPLE || mode == MM_MAX_BLOCK) { if (o < v) out[i] = v; }
+        else { if (o > v) out[i] = v; }
+    }
+}
+__global__ void k_fill_f64(size_t n, double v, double *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+}
+// MultiEvaluator::findBlockings (actions/MultiEvaluator.cpp:579-598): an entry where ANY evaluator is <= 0 is blocked
+__global__ void k_find_blockings(size_t n, const double *__restrict__ single, uint8_t *__restrict__ allowed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (single[i] <= 0) allowed[i] = 0;
+}
 // ... then the rows are cumulated (again: the evaluators inside were built cumulating, docs/DoubleCumulateArtifactsBug.odt)
 __global__ void k_rows_cumulate(int nCells, double *__restrict__ W) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {

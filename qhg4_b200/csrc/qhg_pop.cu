@@ -120,6 +120,7 @@ struct SubEval {
     std::string polyName;    // attribute holding its poly-line
     int trigger = 0;         // event id that makes it recompute
     bool first = true, needUpdate = false;
+    bool cumulate = true;    // the bCumulate argument of its constructor (actions/SingleEvaluator.cpp:216-243)
 };
 
 struct HostAction {
@@ -225,6 +226,8 @@ struct qhgb_pop {
     std::vector<SubEval> subs;
     bool multiFirst = true, nppNeedUpdate = true, multiObserves = false;
     DevBuf<double> cap, Wtmp;
+    int multiMode = MM_ADD_SIMPLE;   // combine mode of the class's MultiEvaluator (actions/MultiEvaluator.h:19-26)
+    DevBuf<uint8_t> multiAllowed;    // MultiEvaluator::m_acAllowed (the BLOCK modes)
     std::map<std::string, PolyLineDev> polys;
     // Genetics<.., BitGeneUtils>: genome pool (rows are not moved by the re-binning), free stack, birth list
     bool genetic = false;
@@ -577,7 +580,27 @@ int recalcCapacities(qhgb_pop *p) {
     return 0;
 }
 
-// MultiEvaluator::initialize + addSingleWeights, MODE_ADD_SIMPLE (actions/MultiEvaluator.cpp:142-182,221-253)
+// SingleEvaluator::initialize inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167): the evaluators share ONE scratch array
+// (Wtmp = m_adSingleEvalWeights); it is rewritten only when the evaluator needs an update or has never run
+int subEvalInit(qhgb_pop *p, SubEval &e) {
+    qhgb_pop &q = *p;
+    if (!(e.needUpdate || e.first)) return 0;
+    e.first = false;
+    const size_t nW = (size_t)q.nCells * WSTRIDE;
+    const int g = q.gridFor(q.nCells);
+    const double *in = e.input.empty() ? q.cap.p : (e.input == "Altitude" ? q.alt.p : q.envExtra[e.input].p);
+    if (!in) return fail("No array with name [%s] found", e.input.c_str());
+    const bool havePl = e.usePoly && q.polys.count(e.polyName);
+    CK(cudaMemsetAsync(q.Wtmp.p, 0, nW * sizeof(double), q.stream));  // calcValues starts with a memset (:175)
+    LAUNCH(p, "k_weights_own", k_weights_own, g, 256, q.nCells, in, q.haveIce ? q.ice.p : nullptr, havePl ? q.polys[e.polyName] : q.poly, havePl ? 1 : 0, q.Wtmp.p);
+    LAUNCH(p, "k_weights_cumulate", k_weights_cumulate, g, 256, q.nCells, q.nbr.p, q.Wtmp.p, e.cumulate ? 1 : 0);
+    return 0;
+}
+
+// MultiEvaluator::initialize and its six combine modes (actions/MultiEvaluator.cpp:142-182; 221-253 ADD_SIMPLE, 263-298 ADD_BLOCK,
+// 308-342 MUL_SIMPLE, 350-381 MAX_SIMPLE -- the only one whose rows are not cumulated --, 391-432 MAX_BLOCK, 440-478 MIN_SIMPLE;
+// findBlockings 579-598).  An evaluator that needs no update contributes the zeros of the memset before its initialize; in
+// findBlockings there is no memset, so such an evaluator is judged by the scratch array as the previous user left it.
 int computeMultiWeights(qhgb_pop *p) {
     qhgb_pop &q = *p;
     bool need = false;
@@ -585,21 +608,25 @@ int computeMultiWeights(qhgb_pop *p) {
     if (!(need || q.multiFirst)) return 0;
     q.multiFirst = false;
     const size_t nW = (size_t)q.nCells * WSTRIDE;
-    const int g = q.gridFor(q.nCells);
-    CK(cudaMemsetAsync(q.W.p, 0, nW * sizeof(double), q.stream));
+    const int g = q.gridFor(q.nCells), gw = q.gridFor((int64_t)nW);
+    const int mode = q.multiMode;
+    const bool block = mode == MM_ADD_BLOCK || mode == MM_MAX_BLOCK;
+    if (block) {
+        if (q.multiAllowed.n != nW) CK(q.multiAllowed.alloc(nW));
+        CK(cudaMemsetAsync(q.multiAllowed.p, 1, nW, q.stream));
+        for (auto &e : q.subs) {
+            if (subEvalInit(p, e) != 0) return -1;
+            LAUNCH(p, "k_find_blockings", k_find_blockings, gw, 256, nW, q.Wtmp.p, q.multiAllowed.p);
+        }
+    }
+    const double init = (mode == MM_MUL_SIMPLE) ? 1.0 : (mode == MM_MAX_SIMPLE || mode == MM_MAX_BLOCK) ? -INFINITY : (mode == MM_MIN_SIMPLE) ? INFINITY : 0.0;
+    LAUNCH(p, "k_fill_f64", k_fill_f64, gw, 256, nW, init, q.W.p);
     for (auto &e : q.subs) {
         CK(cudaMemsetAsync(q.Wtmp.p, 0, nW * sizeof(double), q.stream));
-        if (e.needUpdate || e.first) {  // an evaluator that needs no update contributes zeros (the reference's behaviour)
-            e.first = false;
-            const double *in = e.input.empty() ? q.cap.p : (e.input == "Altitude" ? q.alt.p : q.envExtra[e.input].p);
-            if (!in) return fail("No array with name [%s] found", e.input.c_str());
-            const bool havePl = e.usePoly && q.polys.count(e.polyName);
-            LAUNCH(p, "k_weights_own", k_weights_own, g, 256, q.nCells, in, q.haveIce ? q.ice.p : nullptr, havePl ? q.polys[e.polyName] : q.poly, havePl ? 1 : 0, q.Wtmp.p);
-            LAUNCH(p, "k_weights_cumulate", k_weights_cumulate, g, 256, q.nCells, q.nbr.p, q.Wtmp.p, 1);
-        }
-        LAUNCH(p, "k_multi_accumulate", k_multi_accumulate, q.gridFor((int64_t)nW), 256, nW, q.Wtmp.p, q.A(e.weightName.c_str()), q.W.p);
+        if (subEvalInit(p, e) != 0) return -1;
+        LAUNCH(p, "k_multi_combine", k_multi_combine, gw, 256, nW, mode, q.Wtmp.p, q.A(e.weightName.c_str()), block ? q.multiAllowed.p : nullptr, q.W.p);
     }
-    LAUNCH(p, "k_rows_cumulate", k_rows_cumulate, g, 256, q.nCells, q.W.p);
+    if (mode != MM_MAX_SIMPLE) LAUNCH(p, "k_rows_cumulate", k_rows_cumulate, g, 256, q.nCells, q.W.p);
     CK(cudaGetLastError());
     return 0;
 }
@@ -825,6 +852,14 @@ int buildHalo(qhgb_pop *p) {
     return 0;
 }
 
+// tut_EnvironCapAlt<Mode>Pop -> MultiEvalModes value, -1 for any other class name
+int multiProbeMode(const std::string &cls) {
+    static const char *const names[] = {nullptr, "tut_EnvironCapAltAddBlockPop", "tut_EnvironCapAltMulPop", "tut_EnvironCapAltMaxPop",
+                                        "tut_EnvironCapAltMaxBlockPop", "tut_EnvironCapAltMinPop"};
+    for (int m = 1; m <= 5; m++) if (cls == names[m]) return m;
+    return -1;
+}
+
 // how long a rank waits for its peers at a cross-GPU barrier, in GPU clocks (QHG_XBARRIER_TIMEOUT_S seconds, default 600)
 long long xbarrierTimeout() {
     static long long clocks = 0;
@@ -846,6 +881,18 @@ int commFailure(qhgb_pop *p) {
     cudaStreamSynchronize(q.stream);
     if (err == 1) return fail("a rank did not reach the cross-GPU barrier (exchange %u)", q.xStep);
     return fail("receive buffer too small for the migrants of one step (%d > %d)", nRecv, q.recvCap);
+}
+
+// cells a warp of k_seg_decide takes per grab: about QHG_SEG_AGENTS (default 600) agents' worth at the mean density, 1..SB
+int segGrab(qhgb_pop *p) {
+    static int target = 0;
+    if (!target) {
+        const char *e = getenv("QHG_SEG_AGENTS");
+        target = (e && atoi(e) > 0) ? atoi(e) : 600;
+    }
+    const int64_t cells = std::max<int64_t>(1, p->cHi() - p->cLo());
+    const double mean = std::max(1.0, (double)p->nAgents / (double)cells);
+    return (int)std::max(1.0, std::min((double)SB, std::floor(target / mean + 0.5)));
 }
 
 // can the fast path (qhg_cells.cuh) run this program?  The rarer actions exist on the generic path only; Navigate's far jumps
@@ -907,10 +954,10 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             } else if (q.segDecide && P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge) {
                 // one warp per batch of cells, the tutorial action order as straight-line code (qhg_decide.cuh)
                 LAUNCH(p, "k_cell_decide", k_seg_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, segGrab(p));
             } else if (q.segDecide) {
                 LAUNCH(p, "k_cell_decide_generic", k_seg_decide<false>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
+                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, segGrab(p));
             } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
@@ -1033,7 +1080,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_make_offspring", k_make_offspring, q.numSMs * 16, 128, q.dstats.p, q.gctl.p, q.births.p, q.gp, q.key,
                        q.gslot[q.cur].p, q.gslot[q.cur ^ 1].p, q.gpool.p, q.gfree.p);
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 1, 0, q.dstats.p, q.sharded ? 1 : 0, (int)q.poolRows);
-                LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor(n), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
+                LAUNCH(p, "k_free_genomes", k_free_genomes_dec, q.gridFor((n + 3) / 4), 256, q.dstats.p, q.gctl.p, q.dec.p, q.gslot[q.cur].p, q.gfree.p);
             }
             stepEndBirths = globalBirths;
         } else {
@@ -1164,13 +1211,21 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"RandomMove", A_RANDOMMOVE}};
     } else if (p->popClass == "tut_OldAgeDiePop") {  // populations/tut_OldAgeDiePop.cpp:17-26
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}};
-    } else if (p->popClass == "tut_EnvironCapAltPop") {  // populations/tut_EnvironCapAltPop.cpp:27-72
+    } else if (p->popClass == "tut_EnvironCapAltPop" || multiProbeMode(p->popClass) >= 0) {  // populations/tut_EnvironCapAltPop.cpp:27-72
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"VerhulstVarK", A_VERHULSTVARK},
                       {"RandomPair", A_RANDOMPAIR}, {"MultiEvaluator[NPP+Alt]", A_MULTIEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"NPPCapacity", A_NPPCAP}};
         SubEval ea; ea.input = "Altitude"; ea.weightName = "Multi_weight_alt"; ea.usePoly = true; ea.polyName = "AltPref"; ea.trigger = QHGB_EVENT_ID_GEO;
         SubEval en; en.input = ""; en.weightName = "Multi_weight_npp"; en.usePoly = false; en.trigger = QHGB_EVENT_ID_VEG;
         p->subs = {ea, en};
+        if (multiProbeMode(p->popClass) >= 0) {
+            // tut_EnvironCapAlt{AddBlock,Mul,Max,MaxBlock,Min}Pop: the same class with its MultiEvaluator combining in another mode
+            // over NON-cumulating evaluators and registered as an observer, the way populations/OoANavPop.cpp:50-62 builds its
+            // MODE_MUL_SIMPLE evaluator -- the classes the reference driver builds to pin those modes (MultiProbePop<MODE>)
+            p->multiMode = multiProbeMode(p->popClass);
+            for (auto &e : p->subs) e.cumulate = false;
+            p->multiObserves = true;
+        }
     } else if (p->popClass == "tut_EnvironAltVarPop") {
         // tut_EnvironAltPop with WeightedMoveRand (actions/WeightedMoveRand.cpp; the predator classes carry it) and SigDeath
         // (actions/SigDeath.cpp) added: the class the reference driver builds to pin them (VarProbePop, oracle/ref_driver.cpp)
@@ -1282,7 +1337,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->TB.release(); p->TD.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
     for (auto &kv : p->envDelta) kv.second.release();
-    p->cap.release(); p->Wtmp.release();
+    p->cap.release(); p->Wtmp.release(); p->multiAllowed.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release(); p->father.release();
     p->jumps.release(); p->jumpCount.release();

