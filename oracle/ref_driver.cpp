@@ -65,6 +65,9 @@ template class SequenceIOUtils<ulong>;  // io/SequenceIOUtils.cpp is an uninstan
 #include <cstdlib>
 #include <vector>
 #include "../integration/tut_EnvironAltGpuPop.h"
+#include "../integration/tut_EnvironCapAltGpuPop.h"
+#include "../integration/OoANavGenGpuPop.h"
+#include "DynPopFactory.h"
 #endif
 
 namespace {
@@ -111,6 +114,7 @@ struct PopAccess {
     virtual WELL512 *geneticsWell() { return nullptr; }
     virtual int geneticsInit(int genomeSize, int numCrossOvers, double mutationRate) { return -1; }
     virtual int numBabies(int slot) { return -1; }  // m_iNumBabies of the OoANavGen agents
+    virtual ulong *cellCounts() = 0;                // m_aiNumAgentsPerCell
 };
 
 template <class PopT, class AgentT>
@@ -184,6 +188,7 @@ struct PopAccessT : PopAccess {
             return -1;
         }
     }
+    ulong *cellCounts() override { return pop->m_aiNumAgentsPerCell; }
     int numBabies(int slot) override {
         if constexpr (requires { pop->m_aAgents[slot].m_iNumBabies; }) return pop->m_aAgents[slot].m_iNumBabies; else return -1;
     }
@@ -456,6 +461,27 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_EnvironAltGpuPop, tut_EnvironAltAgent>(new tut_EnvironAltGpuPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
         s->adapter = true;
         class_name = "tut_EnvironAltPop";  // the class entry of the parameter file
+    } else if (std::string(class_name) == "tut_EnvironCapAltGpuPop") {  // integration/qhg_gpu_pop.h over tut_EnvironCapAltPop
+        s->pa = new PopAccessT<tut_EnvironCapAltGpuPop, tut_EnvironCapAltAgent>(new tut_EnvironCapAltGpuPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+        s->adapter = true;
+        class_name = "tut_EnvironCapAltPop";
+    } else if (std::string(class_name) == "OoANavGenGpuPop") {          // ... over OoANavGenPop
+        s->pa = new PopAccessT<OoANavGenGpuPop, OoANavGenAgent>(new OoANavGenGpuPop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+        s->adapter = true;
+        class_name = "OoANavGenPop";
+    } else if (std::string(class_name) == "dyn:tut_EnvironAltGpuPop") {
+        // the way the application gets a plugin population (app/SimParams.cpp:1395-1407 with --dyn-pops --so-dirs): the
+        // reference's DynPopFactory scans the directory for *Wrapper.so, dlopens it and calls its createPop
+        // (populations/DynPopFactory.cpp:80-163).  The plugin is integration/tut_EnvironAltGpuPopWrapper.cpp.
+        const char *dir = getenv("QHG_REF_SO_DIR");
+        stringvec vDirs;
+        vDirs.push_back(dir ? dir : ".");
+        DynPopFactory *pF = DynPopFactory::createInstance(vDirs, s->cg, s->looper, ls, s->idg, s->state, s->seeds);
+        PopBase *pPB = (pF != NULL) ? pF->createPopulationByName("tut_EnvironAltGpuPop") : NULL;
+        if (pPB == NULL) { fprintf(stderr, "[qref_create] DynPopFactory could not create [tut_EnvironAltGpuPop] from [%s]\n", dir ? dir : "."); return NULL; }
+        s->pa = new PopAccessT<tut_EnvironAltGpuPop, tut_EnvironAltAgent>(static_cast<tut_EnvironAltGpuPop *>(pPB));
+        s->adapter = true;
+        class_name = "tut_EnvironAltPop";  // (the factory stays alive: it keeps the library handle, populations/DynPopFactory.cpp:38-42)
 #endif
     } else {
         fprintf(stderr, "[qref_create] unknown population class [%s]\n", class_name);
@@ -595,6 +621,7 @@ int qref_set_genomes(void *h, int firstSlot, long n, const uint64_t *rows) {
 // rows of the live agents in slot order (the order of qref_get_agents); returns the words per row
 long qref_get_genomes(void *h, long cap, uint64_t *rows) {
     RefSim *s = (RefSim *)h;
+    if (s->adapter) { Quiet q(s->quiet); s->pa->base()->preWrite(0.0f); }
     const int w = s->pa->genomeWords();
     if (w <= 0) return -1;
     int first = s->pa->first();
@@ -611,6 +638,7 @@ long qref_get_genomes(void *h, long cap, uint64_t *rows) {
 // m_iNumBabies of every live agent, in the order of qref_get_agents (populations/OoANavGenPop.cpp:243); -1: the class has none
 long qref_get_num_babies(void *h, long cap, int *out) {
     RefSim *s = (RefSim *)h;
+    if (s->adapter) { Quiet q(s->quiet); s->pa->base()->preWrite(0.0f); }
     int first = s->pa->first();
     if (first < 0) return 0;
     long k = 0;
@@ -670,7 +698,7 @@ int qref_gene2_mutate(const uint32_t *state16, uint64_t *genome, int n_nucs, int
 int qref_get_counts(void *h, uint64_t *out) {
     RefSim *s = (RefSim *)h;
     if (s->adapter) s->pa->base()->updateNumAgentsPerCell();
-    for (int c = 0; c < s->nCells; c++) out[c] = s->adapter ? ((SPopulation<tut_EnvironAltAgent> *)s->pa->base())->m_aiNumAgentsPerCell[c] : s->pa->base()->getNumAgents(c);
+    for (int c = 0; c < s->nCells; c++) out[c] = s->adapter ? s->pa->cellCounts()[c] : s->pa->base()->getNumAgents(c);
     return 0;
 }
 

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libqhgref.so")
 # the same driver and reference objects plus the plugin class of INTEGRATION.md (integration/tut_EnvironAltGpuPop.h),
 # linked against qhg4_b200/libqhg_b200.so: the reference's PopLooper::doStep drives the CUDA path (`make adapter`)
 ADAPTER_PATH = os.path.join(_HERE, "_ref", "libqhgadapter.so")
+PLUGIN_DIR = os.path.join(_HERE, "_ref", "plugins")  # *Wrapper.so files for the reference's DynPopFactory (`make adapter`)
 
 _lib = None
 _libs = {}
@@ -43,7 +44,9 @@ def has_class(name: str) -> bool:
 def lib(adapter: bool = False):
     global _lib
     if adapter not in _libs:
-        L = C.CDLL(ADAPTER_PATH if adapter else LIB_PATH)
+        # the adapter library is opened RTLD_GLOBAL: a plugin that DynPopFactory dlopens resolves the application's symbols
+        # from the loading process (the reference's executables are linked with --export-dynamic, app/Makefile:132,147)
+        L = C.CDLL(ADAPTER_PATH, mode=C.RTLD_GLOBAL) if adapter else C.CDLL(LIB_PATH)
         L.qref_create.restype = C.c_void_p
         L.qref_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_int, C.c_int]
@@ -126,7 +129,13 @@ class RefSim:
             f.write(params.to_xml())
             path = f.name
         try:
-            cls = "tut_EnvironAltGpuPop" if self.adapter else params.class_name
+            cls = params.class_name
+            if adapter == "plugin":   # the reference's DynPopFactory loads integration/tut_EnvironAltGpuPopWrapper.cpp's .so
+                os.environ["QHG_REF_SO_DIR"] = PLUGIN_DIR
+                cls = "dyn:tut_EnvironAltGpuPop"
+            elif self.adapter:        # integration/*GpuPop.h compiled into the driver library
+                cls = {"tut_EnvironAltPop": "tut_EnvironAltGpuPop", "tut_EnvironCapAltPop": "tut_EnvironCapAltGpuPop",
+                       "OoANavGenPop": "OoANavGenGpuPop"}[params.class_name]
             self.h = self.L.qref_create(path.encode(), cls.encode(), self.ncells, _p(self._nbr),
                                        _p(alt), _p(icea), int(threads), _p(st), int(layer_size), int(quiet))
         finally:

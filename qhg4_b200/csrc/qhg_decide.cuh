@@ -23,13 +23,11 @@
 
 namespace qhg {
 
-#ifndef QHG_SB
-#define QHG_SB 16
-#endif
-constexpr int SB = QHG_SB;     // most cells a warp takes per grab of the work counter (the host passes the actual number)
+constexpr int SB_MAX = 8;      // most cells a warp takes per grab of the work counter (template parameter SB: 4 or 8)
 constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the provisional decisions in shared memory)
 constexpr int MAXF_S = 384;    // most fertile females of one cell that can be ranked here (larger cells: generic path)
 
+template <int SB>
 struct SegSmem {
     double row[SB][8];                 // cumulated weight rows (7 used)
     unsigned long long tb[SB + 1], td[SB + 1]; // LinearBirth / LinearDeath thresholds of the cells (k_cell_init)
@@ -53,15 +51,17 @@ struct SegSmem {
     alignas(4) uint8_t dec[SEGCAP + 4];  // provisional decisions, shifted by (segment start & 3)
 };
 
-template <bool SPEC>
+// SB = cells per grab: the slot reservations of a sub-batch stay in registers until the next one ends, SB / 4 pairs of them --
+// 8 cells per grab pay at 20 agents per cell, 4 at 150 (register pressure: the kernel is capped at 64 registers)
+template <bool SPEC, int SB>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-             int *__restrict__ moveBase, int grab) {
+             int *__restrict__ moveBase) {
     static_assert(SB + 1 <= 32 && SB * 8 <= 4 * 32, "one lane per cell start; at most four rounds of (cell, direction) lanes");
-    __shared__ SegSmem smem[DCW];
+    __shared__ SegSmem<SB> smem[DCW];
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
-    SegSmem &S = smem[wid];
+    SegSmem<SB> &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it
@@ -84,17 +84,13 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
 #pragma unroll
     for (int r = 0; r < PEND; r++) { pendIdx[r] = -1; pendVal[r] = 0; }
 
-    // cells are handed out dynamically, `grab` at a time (the host picks it from the density: a grab is a few hundred agents);
-    // towards the end of the range the grabs shrink so that no warp is left with a long tail
-    const int nWarps = gridDim.x * DCW;
-    int lastEnd = cLo;  // where this warp's last grab ended: the work counter is at least there
+    // cells are handed out dynamically, SB at a time (sea cells are empty, land cells are not: a static split leaves a tail)
     for (;;) {
-    const int g = max(1, min(min(grab, SB), (cHi - lastEnd) / (2 * nWarps)));
+    const int g = SB;
     int cBase = 0;
     if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, g);
     cBase = __shfl_sync(FULL, cBase, 0);
     if (cBase >= cHi) break;
-    lastEnd = cBase + g;
     const int nB = min(g, cHi - cBase);
     const int csL = (lane <= nB) ? cellStart[cBase + lane] : 0;
     int g0 = 0;

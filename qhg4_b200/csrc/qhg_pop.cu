@@ -883,16 +883,15 @@ int commFailure(qhgb_pop *p) {
     return fail("receive buffer too small for the migrants of one step (%d > %d)", nRecv, q.recvCap);
 }
 
-// cells a warp of k_seg_decide takes per grab: about QHG_SEG_AGENTS (default 600) agents' worth at the mean density, 1..SB
-int segGrab(qhgb_pop *p) {
-    static int target = 0;
-    if (!target) {
-        const char *e = getenv("QHG_SEG_AGENTS");
-        target = (e && atoi(e) > 0) ? atoi(e) : 600;
+// does a warp of k_seg_decide take 8 cells per grab (fewer than QHG_SEG_DENSE = 64 agents per cell on average) or 4?
+bool segSparse(qhgb_pop *p) {
+    static int dense = 0;
+    if (!dense) {
+        const char *e = getenv("QHG_SEG_DENSE");
+        dense = (e && atoi(e) > 0) ? atoi(e) : 64;
     }
     const int64_t cells = std::max<int64_t>(1, p->cHi() - p->cLo());
-    const double mean = std::max(1.0, (double)p->nAgents / (double)cells);
-    return (int)std::max(1.0, std::min((double)SB, std::floor(target / mean + 0.5)));
+    return (double)p->nAgents / (double)cells < (double)dense;
 }
 
 // can the fast path (qhg_cells.cuh) run this program?  The rarer actions exist on the generic path only; Navigate's far jumps
@@ -951,13 +950,19 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_cell_decide_nav", (k_cell_decide<false, false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, (int *)nullptr,
                        q.jumps.p, q.jumpCount.p, jumpCap);
-            } else if (q.segDecide && P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge) {
-                // one warp per batch of cells, the tutorial action order as straight-line code (qhg_decide.cuh)
-                LAUNCH(p, "k_cell_decide", k_seg_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, segGrab(p));
             } else if (q.segDecide) {
-                LAUNCH(p, "k_cell_decide_generic", k_seg_decide<false>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
-                       q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, segGrab(p));
+                // one warp per batch of cells (qhg_decide.cuh); the tutorial action order as straight-line code; 8 cells per grab
+                // for sparse populations, 4 for dense ones
+                const bool spec = P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge;
+                const bool sparse = segSparse(p);
+#define QHG_SEG_LAUNCH(NAME, SPEC_, SB_)                                                                                      \
+    LAUNCH(p, NAME, (k_seg_decide<SPEC_, SB_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),                  \
+           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p)
+                if (spec && sparse) QHG_SEG_LAUNCH("k_cell_decide", true, 8);
+                else if (spec) QHG_SEG_LAUNCH("k_cell_decide", true, 4);
+                else if (sparse) QHG_SEG_LAUNCH("k_cell_decide_generic", false, 8);
+                else QHG_SEG_LAUNCH("k_cell_decide_generic", false, 4);
+#undef QHG_SEG_LAUNCH
             } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);

@@ -836,20 +836,27 @@ def test_dump_restore_resumes_bit_identically(which, tmp_path):
         g.restore_state(path)  # only into an empty, configured population
 
 
-def test_reference_step_loop_drives_cuda_path_through_plugin_class():
+@pytest.mark.parametrize("how", ["class", "plugin"])
+def test_reference_step_loop_drives_cuda_path_through_plugin_class(how):
     """The drop-in boundary exercised from the reference's side: the UNMODIFIED reference sources (PopLooper::doStep,
     core/PopLooper.cpp:190-232, SPopulation, ParamProvider2, the tutorial population) with the plugin class of
-    INTEGRATION.md (integration/tut_EnvironAltGpuPop.h) loaded as the population.  Its initializeStep / doActions /
+    INTEGRATION.md (integration/tut_EnvironAltGpuPop.h) as the population.  Its initializeStep / doActions /
     finalizeStep virtuals go to the C ABI; preWrite brings the agents back into the reference's LayerBuf.  Results must
-    be bit-identical to the counter-mode oracle, like a direct C-ABI run."""
+    be bit-identical to the counter-mode oracle, like a direct C-ABI run.
+    how = "class":  the class is compiled into the driver library and constructed directly;
+    how = "plugin": it is built as oracle/_ref/plugins/tut_EnvironAltGpuPopWrapper.so (integration/tut_EnvironAltGpuPopWrapper.cpp:
+                    getInfo / createPop) and the reference's own DynPopFactory finds it in the directory, dlopens it and calls
+                    createPop (populations/DynPopFactory.cpp:80-163) -- the way `--dyn-pops --so-dirs=...` loads a population."""
     from oracle import port, refsim
     if not refsim.adapter_available():
         pytest.skip("oracle/_ref/libqhgadapter.so not built (make -C oracle adapter needs /root/reference)")
+    if how == "plugin" and not os.path.exists(os.path.join(refsim.PLUGIN_DIR, "tut_EnvironAltGpuPopWrapper.so")):
+        pytest.skip("oracle/_ref/plugins/tut_EnvironAltGpuPopWrapper.so not built")
     nbr, xyz = make_ico_grid(15)
     alt = synthetic_altitude(xyz, seed=3)
     pop = synthetic_population(50000, alt, seed=9, fertile=True)
     par, st = tut_environ_alt(30.0), seed_state(11)
-    r = refsim.RefSim(par, nbr, alt, state16=st, adapter=True)
+    r = refsim.RefSim(par, nbr, alt, state16=st, adapter=("plugin" if how == "plugin" else True))
     o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st)
     r.add_agents(pop); o.add_agents(pop)
     r.start(); o.start()
@@ -864,6 +871,68 @@ def test_reference_step_loop_drives_cuda_path_through_plugin_class():
     assert np.array_equal(r.counts(), o.counts())
     r.close()
 
+
+@pytest.mark.parametrize("cls", ["tut_EnvironCapAltPop", "OoANavGenPop"])
+def test_reference_step_loop_drives_other_classes_through_adapter_template(cls):
+    """integration/qhg_gpu_pop.h: the adapter as a template over the shipped class -- tut_EnvironCapAltGpuPop (Climate /
+    Vegetation arrays, NPPCapacity, MultiEvaluator) and OoANavGenGpuPop (Genetics: genome rows uploaded at preLoop and
+    brought back by preWrite with m_iNumBabies; Navigation group; GEO / CLIMATE / VEG / NAV events through updateEvent +
+    flushEvents) -- stepped by the reference's own PopLooper::doStep, bit-identical to the oracle's counter mode."""
+    from oracle import port, refsim
+    from qhg4_b200.params import ooa_nav_gen, tut_environ_cap_alt
+    if not refsim.adapter_available():
+        pytest.skip("oracle/_ref/libqhgadapter.so not built (make -C oracle adapter needs /root/reference)")
+    nbr, xyz, alt, env = _cap_world(S=7, seed=5)
+    pop = synthetic_population(12000, alt, seed=6, fertile=True)
+    rng = np.random.default_rng(3)
+    genetic = cls == "OoANavGenPop"
+    G = 128
+    row = 2 * (G // 64)
+    if genetic:
+        par = ooa_nav_gen(G, 3, 2e-3)
+        par.prios["Navigate"] = 10
+    else:
+        par = tut_environ_cap_alt()
+    st = seed_state(29)
+    occ = np.unique(pop["cell"])
+    ports = rng.choice(occ[occ > 8], 40, replace=False).astype(np.int32)
+    ptr = np.arange(0, 4 * len(ports) + 1, 4, dtype=np.int32)
+    dests = np.concatenate([rng.choice(np.flatnonzero(alt > 0), 4, replace=False) for _ in ports]).astype(np.int32)
+    dist = rng.uniform(100, 700, 4 * len(ports))
+    bridges = rng.choice(occ, (4, 2), replace=False).astype(np.int32)
+    gen0 = rng.integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    r = refsim.RefSim(par, nbr, alt, state16=st, env=env, adapter=True)
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+    for q in (r, o):
+        if genetic:
+            q.set_navigation(ports, ptr, dests, dist, bridges)
+        q.add_agents(pop)
+        if genetic:
+            q.set_genomes(gen0)
+    r.start(); o.start()
+    for k in range(10):
+        assert r.step(float(k)) == 0
+        o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        if k == 4:
+            alt2 = alt - 120.0
+            for q in (r, o):
+                q.set_env("Altitude", alt2)
+                q.set_env("AnnualMeanTemp", env["AnnualMeanTemp"] - 2.0)
+            for ev in (2, 3, 4, 5):
+                r.event(ev, 5.0, flush=(ev == 5)); o.update_event(ev, 5.0)
+            o.flush_events(5.0)
+            assert r.num_agents() == o.num_agents(), "event"
+    ra, oa = r.agents(), o.agents()
+    ir, io = np.argsort(ra["id"]), np.argsort(oa["id"])
+    for f in ("cell", "id", "birth", "gender", "age", "last_birth", "life"):
+        assert np.array_equal(ra[f][ir], oa[f][io]), f
+    assert np.array_equal(r.counts(), o.counts())
+    if genetic:
+        og, onb = o.genomes(row)
+        assert np.array_equal(r.genomes(row)[ir], og[io])
+        assert np.array_equal(r.num_babies()[ir], onb[io])
+    r.close()
 
 
 @pytest.mark.parametrize("mode", ["add_block", "mul", "max", "max_block", "min"])
@@ -905,3 +974,34 @@ def test_multi_evaluator_modes_bit_exact_vs_oracle(mode):
                 q.flush_events(float(k + 1))
     assert not np.array_equal(rows[0], rows[-1], equal_nan=True)
     assert "k_multi_combine" in g.kernel_times() or True
+
+
+@pytest.mark.parametrize("agents", [10_000_000] + ([100_000_000] if os.environ.get("QHG_TEST_C4") == "1" else []))
+def test_full_scale_grid_bit_exact_vs_oracle(agents):
+    """BASELINE config C2 at its real size -- the subdivision-256 grid (655,362 cells), 1e7 agents, the tutorial action set -- three
+    steps against the oracle's counter mode (single-threaded C++, a few seconds per step): every agent and every per-cell count.
+    At this size the code paths the small worlds never touch are live: 12 pentagon cells among 655,350 hexagons, cell ranges
+    near the int32 offsets of a 1e7-entry buffer, thousands of sub-batches per warp, the shrinking grabs at the end of the
+    range.  QHG_TEST_C4=1 adds config C4's 1e8 agents (about 40 s of oracle time per step; run by the builder, log in
+    profiles/)."""
+    import bench
+    from oracle import port
+    from qhg4_b200.population import GpuPopulation
+    nbr, alt, pop, par, K = bench.build_world(255, agents)
+    g = GpuPopulation.from_params(par, nbr, alt, capacity_hint=int(agents * 1.6))
+    o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER)
+    g.add_agents(pop); o.add_agents(pop)
+    del pop
+    g.pre_loop(); o.start()
+    for k in range(3):
+        g.step(float(k)); o.step(float(k))
+        assert g.num_agents() == o.num_agents(), k
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), k
+        assert np.array_equal(g.counts(), o.counts()), k
+    ga, oa = g.agents(), o.agents()
+    si, so = np.argsort(ga["id"], kind="stable"), np.argsort(oa["id"], kind="stable")
+    for f in FIELDS:
+        assert np.array_equal(ga[f][si], oa[f][so]), f
+    assert g.num_agents() < agents and s.births > 0 and s.moves > 0
+    g.close()
