@@ -12,9 +12,16 @@ import sys
 import numpy as np
 
 
-def partition_cells(agents_per_cell, nranks: int) -> np.ndarray:
-    """Boundaries (int32, nranks+1) of contiguous cell ranges holding about the same number of agents each."""
+# fixed cost of an occupied cell in agent-equivalents: one step costs about a * agents + b * occupied cells on the device
+# (measured on B200: 1e8 agents -> 1.90 ms, 1e7 agents -> 0.50 ms on the same 459k land cells, so b / a = 44)
+CELL_COST_AGENTS = 44
+
+
+def partition_cells(agents_per_cell, nranks: int, cell_cost: float = CELL_COST_AGENTS) -> np.ndarray:
+    """Boundaries (int32, nranks+1) of contiguous cell ranges of about equal step COST: the agents of a range plus
+    `cell_cost` agent-equivalents for every occupied cell (cell_cost=0: balanced by agents alone)."""
     cnt = np.asarray(agents_per_cell, dtype=np.int64)
+    cnt = cnt + np.int64(cell_cost) * (cnt > 0)
     ncell = len(cnt)
     cum = np.concatenate([[0], np.cumsum(cnt)])
     total = cum[-1]

@@ -19,10 +19,16 @@ def test_partition_cells_balances_agents():
     rng = np.random.default_rng(0)
     cnt = rng.poisson(20, 5000) * (rng.random(5000) > 0.3)
     for n in (1, 2, 4, 8):
-        b = partition_cells(cnt, n)
+        b = partition_cells(cnt, n, cell_cost=0)
         assert b[0] == 0 and b[-1] == 5000 and np.all(np.diff(b) >= 0) and len(b) == n + 1
         per = [cnt[b[r]:b[r + 1]].sum() for r in range(n)]
         assert max(per) - min(per) <= 2 * cnt.max() + 1, per
+        # default: balanced by cost = agents + a fixed number of agent-equivalents per occupied cell
+        from qhg4_b200.sharding import CELL_COST_AGENTS
+        b = partition_cells(cnt, n)
+        cost = cnt + CELL_COST_AGENTS * (cnt > 0)
+        per = [cost[b[r]:b[r + 1]].sum() for r in range(n)]
+        assert b[0] == 0 and b[-1] == 5000 and max(per) - min(per) <= 2 * cost.max() + 1, per
         cells = rng.integers(0, 5000, 100)
         own = owner_of(cells, b)
         assert np.all((cells >= b[own]) & (cells < b[own + 1]))
