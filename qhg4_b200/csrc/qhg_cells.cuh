@@ -858,28 +858,38 @@ k_halo_push(int nHalo, const int *__restrict__ halo, const int *__restrict__ cel
     }
 }
 
-// (2) cross-GPU barrier: one warp; lane r tells rank r "I am at `stamp`" and waits for rank r's word.  A rank that
-//     does not show up within ~4 s of GPU clock raises commError (the host fails the step) instead of hanging.
-__global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, const PeerTable *__restrict__ T, DevStats *__restrict__ st,
-                           long long timeoutClocks) {
+// (2) cross-GPU barrier: every rank tells every other "I am at `stamp`" and waits for the others' words.  A rank that does not
+//     show up within the time limit (QHG_XBARRIER_TIMEOUT_S) raises commError and halt: the host fails the step instead of hanging.
+// the waiting half of a cross-GPU barrier, executed by every block of a kernel that comes after it: block 0 tells the peers
+// "this rank is at `stamp`", every block waits until all peers have said so (the words live in this rank's own memory)
+__device__ __forceinline__ void xbarrier_inline(int rank, int nranks, int which, unsigned stamp, const PeerTable *__restrict__ T,
+                                                DevStats *__restrict__ st, long long timeoutClocks) {
     const int r = threadIdx.x;
     if (r < nranks) {
-        __threadfence_system();
-        volatile unsigned *theirs = which ? &T->x[r]->flagB[rank] : &T->x[r]->flagA[rank];
-        *theirs = stamp;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            volatile unsigned *theirs = which ? &T->x[r]->flagB[rank] : &T->x[r]->flagA[rank];
+            *theirs = stamp;
+        }
         volatile unsigned *mine = which ? &T->x[rank]->flagB[r] : &T->x[rank]->flagA[r];
         const long long t0 = clock64();
         while ((int)(*mine - stamp) < 0) {
-            // a peer that is busy on the host (read-backs, dumps, I/O) may be many seconds behind: the limit is generous and
-            // configurable (QHG_XBARRIER_TIMEOUT_S).  When it does expire the step is void: `halt` makes the remaining kernels
-            // of this and of the queued steps do nothing, the host reports the error and clears both flags (k_clear_halt).
             if (clock64() - t0 > timeoutClocks) { st->commError = 1; st->halt = 1; break; }
-            __nanosleep(200);
+            __nanosleep(100);
         }
         __threadfence_system();
     }
-    __syncwarp();
-    if (which == 0 && r == 0) {  // everybody's births are in: id offset of this rank, total of the step
+    __syncthreads();
+}
+
+// (2)+(3) in one launch: the barrier, then the owned halo cells take the arrivals of the other ranks (the local movers hold the
+// first slots of a cell's arrivals, the migrants follow); block 0 also derives this rank's id offset from everybody's births
+__global__ void __launch_bounds__(256)
+k_xbarrier_merge(int nHalo, const int *__restrict__ halo, int c0, int c1, int nCells, int parity, const PeerTable *__restrict__ T,
+                 int rank, int nranks, unsigned stamp, int *__restrict__ arrive, int *__restrict__ cursor, DevStats *__restrict__ st,
+                 long long timeoutClocks) {
+    xbarrier_inline(rank, nranks, 0, stamp, T, st, timeoutClocks);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         long long below = 0, total = 0;
         for (int q = 0; q < nranks; q++) {
             const long long b = ((volatile long long *)T->x[rank]->births)[q];
@@ -889,18 +899,12 @@ __global__ void k_xbarrier(int rank, int nranks, int which, unsigned stamp, cons
         st->birthOffset = below;
         st->globalBirths = total;
     }
-}
-
-// (3) after barrier A: the owned halo cells take the arrivals of the other ranks; the local movers hold the first
-//     slots of a cell's arrivals, the migrants follow
-__global__ void k_halo_merge(int nHalo, const int *__restrict__ halo, int c0, int c1, int nCells, int parity,
-                             const PeerTable *__restrict__ T, int rank, int *__restrict__ arrive, int *__restrict__ cursor) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nHalo; i += gridDim.x * blockDim.x) {
         const int c = halo[i];
         if (c >= c0 && c < c1) {
             const int local = arrive[c];
             cursor[c] = local;
-            arrive[c] = local + T->arriveRemote[rank][(size_t)parity * nCells + c];
+            arrive[c] = local + ((volatile int *)T->arriveRemote[rank])[(size_t)parity * nCells + c];
         }
     }
 }
@@ -912,12 +916,15 @@ template <bool GEN>
 __global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable *__restrict__ T, int rank, int recvCap, AgentArrays o,
                                      const int *__restrict__ newStart, const int *__restrict__ stay, const int *__restrict__ cursor,
                                      int storeAge, const GenomeCtl *__restrict__ ctl = nullptr, const int *__restrict__ freeStack = nullptr,
-                                     unsigned long long *__restrict__ pool = nullptr, int rowWords = 0, int poolRows = 0) {
-    if (st->overflow || st->oversize || st->halt) return;
-    const int n = T->x[rank]->recvCount;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+                                     unsigned long long *__restrict__ pool = nullptr, int rowWords = 0, int poolRows = 0,
+                                     int nranks = 0, unsigned stamp = 0, long long timeoutClocks = 0, int stepEnd = 0, int advanceStep = 0) {
+    // nranks > 0: barrier B happens here (every block waits for the peers' "my records are in"), not in a kernel of its own
+    if (nranks > 0) xbarrier_inline(rank, nranks, 1, stamp, T, st, timeoutClocks);
+    const bool skip = st->overflow || st->oversize || st->halt;
+    const int n = skip ? 0 : ((volatile int *)&T->x[rank]->recvCount)[0];
+    if (!skip && blockIdx.x == 0 && threadIdx.x == 0) {
         st->nRecv = n;
-        if (n > recvCap) { st->commError = 2; st->halt = 1; }  // the step is void (k_step_end keeps the old state)
+        if (n > recvCap) { st->commError = 2; st->halt = 1; }  // the step is void (the book-keeping below keeps the old state)
     }
     const Migrant *in = xchg_recv(T->x[rank]);
     const int per = GEN ? 32 : 1;  // threads per record
@@ -940,6 +947,17 @@ __global__ void k_place_migrants_p2p(DevStats *__restrict__ st, const PeerTable 
             const unsigned long long *src = xchg_genomes(T->x[rank], recvCap) + (size_t)i * rowWords;
             unsigned long long *dst = pool + (size_t)slot * rowWords;
             for (int w = lane; w < rowWords; w += 32) dst[w] = src[w];
+        }
+    }
+    if (stepEnd) {  // this is the step's last kernel: the block that finishes last does the book-keeping (k_step_end's)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&st->doneBlocks, 1) == (int)gridDim.x - 1) {
+                st->doneBlocks = 0;
+                __threadfence();
+                step_end_body(st, advanceStep, -2);
+            }
         }
     }
 }
@@ -1058,23 +1076,27 @@ __global__ void k_place_migrants(DevStats *__restrict__ st, const Migrant *__res
 #ifndef QHG_SNST
 #define QHG_SNST 1
 #endif
-constexpr int SCH = QHG_SCH;
+constexpr int SCH_DENSE = QHG_SCH;   // agents per window for dense populations (6 CTAs per SM)
+constexpr int SCH_SPARSE = 256;      // ... and for sparse ones: smaller windows, 8 CTAs per SM (measured: -12 % at 20 agents per cell, +8 % at 150)
 constexpr int SNST = QHG_SNST;
 
+template <int SCH>
 struct alignas(128) StagedAgents {
     int64_t id[SCH];
     float birth[SCH];
     float lastBirth[SCH];
     uint8_t dec[SCH];
 };
+template <int SCH>
 struct alignas(128) WarpSmemS {
-    StagedAgents win[SNST];
+    StagedAgents<SCH> win[SNST];
     int64_t motherId[MAXMOTHERS];
     uint16_t mvJ[MVCAP];
     unsigned long long bar[SNST];
 };
+template <int SCH>
 struct alignas(128) WarpSmemSG {  // populations with Genetics: the mothers' positions in the old buffer as well
-    StagedAgents win[SNST];
+    StagedAgents<SCH> win[SNST];
     int64_t motherId[MAXMOTHERS];
     int motherIdx[MAXMOTHERS];
     uint16_t mvJ[MVCAP];
@@ -1109,11 +1131,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 #ifndef QHG_SCATTER_S_MINB
 #define QHG_SCATTER_S_MINB 6
 #endif
-constexpr int SCATTER_CTAS_PER_SM = QHG_SCATTER_S_MINB;  // persistent grid: this many CTAs per SM
+constexpr int SCATTER_CTAS_DENSE = QHG_SCATTER_S_MINB, SCATTER_CTAS_SPARSE = 8;  // persistent grids: this many CTAs per SM
 // GEN = true: the population has Genetics -- the genome handle and m_iNumBabies follow the agent (read straight from global
 // memory, like the optional age), every newborn leaves a birth record (baby position, mother, father) for k_make_offspring
-template <bool GEN = false>
-__global__ void __launch_bounds__(CW * 32, QHG_SCATTER_S_MINB)
+template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE>
+__global__ void __launch_bounds__(CW * 32, MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
@@ -1121,7 +1143,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
                uint8_t *decMark = nullptr) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
-    using WSS = typename std::conditional<GEN, WarpSmemSG, WarpSmemS>::type;
+    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH>, WarpSmemS<SCH>>::type;
     __shared__ WSS smem[CW];
     if (st->overflow || st->oversize || st->halt) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1157,7 +1179,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         auto issue = [&](int k) {  // lane 0: start the copies of window k
             const int w0 = g0 + k * SCH;
             const int cnt = min(SCH, (ge - w0 + 15) & ~15);
-            StagedAgents &W = S.win[k % SNST];
+            StagedAgents<SCH> &W = S.win[k % SNST];
             unsigned long long *bar = &S.bar[k % SNST];
             mbar_expect_tx(bar, (uint32_t)cnt * 17u);
             bulk_g2s(W.id, a.id + w0, (uint32_t)cnt * 8u, bar);
@@ -1191,7 +1213,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         begin_cell();
         for (int k = 0; k < nWin; k++) {
             const int w0 = g0 + k * SCH, w1 = min(w0 + SCH, ge);
-            const StagedAgents &W = S.win[k % SNST];
+            const StagedAgents<SCH> &W = S.win[k % SNST];
             mbar_wait(&S.bar[k % SNST], (phase >> (k % SNST)) & 1u);
             phase ^= 1u << (k % SNST);
             auto flush_movers = [&]() {  // the queued movers of cell cBase+ci; their records are in this window

@@ -17,7 +17,9 @@
 //     once per kernel.
 // The per-agent law is exactly that of k_cell_decide (same draws, same thresholds, same decision byte), so the two are
 // interchangeable bit for bit (QHG_DECIDE=cell selects the old kernel; tests/test_parity_gpu.py runs both).
-// Populations with Genetics or Navigate keep k_cell_decide<false, GEN, NAV> (they need per-cell male lists / a port pass).
+// GEN: populations with Genetics -- every birth needs the identity of the father, so in every cell with a birth candidate both
+// sexes are listed, keyed and ranked (father[] receives the mate's position).  NAV: programs that end with Navigate -- the
+// agents of port and bridge cells get a second look after the move queue is flushed (far jumps go through the jump list).
 #pragma once
 #include "qhg_cells.cuh"
 
@@ -26,6 +28,7 @@ namespace qhg {
 constexpr int SB_MAX = 8;      // most cells a warp takes per grab of the work counter (template parameter SB: 4 or 8)
 constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the provisional decisions in shared memory)
 constexpr int MAXF_S = 384;    // most fertile females of one cell that can be ranked here (larger cells: generic path)
+constexpr int MAXF_SG = 160;   // the same per sex for populations with Genetics
 
 template <int SB>
 struct SegSmem {
@@ -47,17 +50,24 @@ struct SegSmem {
             alignas(16) uint32_t keys[MAXF_S];
             uint16_t ffJ[MAXF_S], candQ[MAXF_S];
         } p;
+        struct {                       // populations with Genetics: the males are listed, keyed and ranked too
+            alignas(16) uint32_t keys[MAXF_SG];
+            alignas(16) uint32_t mkeys[MAXF_SG];
+            uint16_t ffJ[MAXF_SG], mmJ[MAXF_SG], candQ[MAXF_SG], candR[MAXF_SG], maleOfRank[MAXF_SG];
+        } g;
     } u;
     alignas(4) uint8_t dec[SEGCAP + 4];  // provisional decisions, shifted by (segment start & 3)
 };
 
 // SB = cells per grab: the slot reservations of a sub-batch stay in registers until the next one ends, SB / 4 pairs of them --
 // 8 cells per grab pay at 20 agents per cell, 4 at 150 (register pressure: the kernel is capped at 64 registers)
-template <bool SPEC, int SB>
+template <bool SPEC, int SB, bool GEN = false, bool NAV = false>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-             int *__restrict__ moveBase) {
+             int *__restrict__ moveBase, int *__restrict__ father = nullptr, JumpEntry *__restrict__ jumps = nullptr,
+             int *__restrict__ jumpCount = nullptr, int jumpCap = 0) {
+    static_assert(!(SPEC && (GEN || NAV)), "the compile-time program has neither Genetics nor Navigate");
     static_assert(SB + 1 <= 32 && SB * 8 <= 4 * 32, "one lane per cell start; at most four rounds of (cell, direction) lanes");
     __shared__ SegSmem<SB> smem[DCW];
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
@@ -304,9 +314,61 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
             if (nqm > QCAP - 32 || (last && nqm > 0)) flush_move();
         }
 
+        // ---- Navigate (actions/Navigate.cpp:181-250), the last action of the program: the agents of port and bridge cells --------
+        if constexpr (NAV) {
+            const bool seesMoving = nav_sees_moving(prog, nOps);
+            for (int ci = 0; ci < nc; ci++) {  // warp-uniform
+                const int c = c0 + ci, b0 = S.cs[ci], b1 = S.cs[ci + 1];
+                if (b1 == b0) continue;
+                const int port = E.navRow ? E.navRow[c] : -1;
+                bool hasBridge = false;
+                for (int b = 0; b < E.nBridges; b++) { const int2 br = E.bridges[b]; hasBridge |= (br.x == c) || (br.y == c); }
+                if (port < 0 && !hasBridge) continue;
+                int p0 = 0, nd = 0;
+                if (port >= 0) { p0 = E.navPtr[port]; nd = E.navPtr[port + 1] - p0 - 1; }
+                const int lim = (c < nd) ? c : nd;  // the reference bounds the search by the port's cell index (:194)
+                for (int j = b0 + lane; j < b1; j += 32) {
+                    const uint8_t v0 = sdec[j];
+                    if (v0 & (T_ATANDIES | T_DEADNOW)) continue;          // dead before the last action
+                    const int code0 = (v0 >> DEC_MOVE_SHIFT) & 7;
+                    if (seesMoving && code0 != 0) continue;               // LIFE_STATE_MOVING is still set
+                    const int64_t idj = a.id[s + j];
+                    int to = -1, navMoves = 0;
+                    if (port >= 0) {
+                        const double r = u2d(agent_draws(idj, step, STREAM_ACT1, key).y);
+                        int i = 0;
+                        while (i < lim && r > E.navCum[p0 + i]) i++;
+                        if (i > 0) {
+                            const int dst = E.navDest[p0 + i];
+                            if (!(E.ice && E.ice[dst])) { to = dst; navMoves++; }
+                        }
+                    }
+                    for (int b = 0; b < E.nBridges; b++) {  // manual bridges: one draw per incident bridge (:228-247)
+                        const int2 br = E.bridges[b];
+                        const int dst = (br.x == c) ? br.y : ((br.y == c) ? br.x : -1);
+                        if (dst >= 0) {
+                            const uint4 db = agent_draws(idj, step, 0x04000000u | (unsigned)(b / 4), key);
+                            const unsigned wv = (b & 3) == 0 ? db.x : (b & 3) == 1 ? db.y : (b & 3) == 2 ? db.z : db.w;
+                            if (u2d(wv) < E.bridgeProb) { to = dst; navMoves++; }
+                        }
+                    }
+                    if (navMoves > 0) {  // the last registered move decides where the agent ends up; every one of them counts
+                        const int slot = atomicAdd(&arrive[to], 1);
+                        const int e = atomicAdd(jumpCount, 1);
+                        if (e < jumpCap) jumps[e] = JumpEntry{s + j, to, slot, (int)(v0 & 7)};
+                        else atomicExch(&st->oversize, 1);  // the list is full: the step is redone on the generic path
+                        sdec[j] = (uint8_t)((v0 & 7) | (DEC_DEAD << DEC_MOVE_SHIFT));
+                        confL += (code0 != 0 ? 1 : 0) + navMoves - 1;  // the commit counts one move for a leaving agent
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
         // ---- pairing: RandomPair::findMates (actions/RandomPair.cpp:146-279) under the counter-mode law ------------------
         // fertile females and males are ranked by (random key, id), equal ranks mate.  With nF <= nM every fertile female has
-        // a mate; otherwise the nM females with the smallest keys -- and only the birth candidates need to know.
+        // a mate; otherwise the nM females with the smallest keys -- and only the birth candidates need to know.  Populations
+        // with Genetics need the father of every birth: there both sexes are ranked in every cell that has a candidate.
         if (wantMasks) {
             __syncwarp();
             for (int ci = 0; ci < nc; ci++) {  // warp-uniform
@@ -317,59 +379,99 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                 unsigned rm = 0;
                 if (hi > 0 && lo < 32) rm = ((hi >= 32) ? FULL : ((1u << hi) - 1u)) & ((lo <= 0) ? FULL : ~((1u << lo) - 1u));
                 const unsigned wF = rm ? (S.mask[0][lane] & rm) : 0u, wM = rm ? (S.mask[1][lane] & rm) : 0u;
-                const int cF = __popc(wF);
-                const int nF = __reduce_add_sync(FULL, cF), nMc = __reduce_add_sync(FULL, __popc(wM));
-                if (nF <= nMc) continue;  // every fertile female has a mate
+                const int cF = __popc(wF), cM = __popc(wM);
+                const int nF = __reduce_add_sync(FULL, cF), nMc = __reduce_add_sync(FULL, cM);
+                if (!GEN && nF <= nMc) continue;  // every fertile female has a mate
                 const unsigned wC = rm ? (S.mask[2][lane] & rm) : 0u;
                 const int cC = __popc(wC);
                 const int nCand = __reduce_add_sync(FULL, cC);
                 if (nCand == 0) continue;  // no birth candidate in the cell: nothing to settle
-                if (nF > MAXF_S) {
+                if (nF > (GEN ? MAXF_SG : MAXF_S) || (GEN && nMc > MAXF_SG)) {
                     if (lane == 0) atomicExch(&st->oversize, 1);
                     continue;
                 }
                 // the cell's fertile females in position order, and the candidates as indices into that list
-                int inF = cF, inC = cC;
+                int inF = cF, inC = cC, inM = cM;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int xF = __shfl_up_sync(FULL, inF, o), xC = __shfl_up_sync(FULL, inC, o);
                     if (lane >= o) { inF += xF; inC += xC; }
+                    if constexpr (GEN) { const int xM = __shfl_up_sync(FULL, inM, o); if (lane >= o) inM += xM; }
                 }
                 const int baseF = inF - cF;
+                uint16_t *const ffJ = GEN ? S.u.g.ffJ : S.u.p.ffJ, *const candQ = GEN ? S.u.g.candQ : S.u.p.candQ;
+                uint32_t *const keys = GEN ? S.u.g.keys : S.u.p.keys;
                 {
                     unsigned w = wF;
                     int idx = baseF;
-                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.p.ffJ[idx++] = (uint16_t)(32 * lane + t); }
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; ffJ[idx++] = (uint16_t)(32 * lane + t); }
                     w = wC;
                     idx = inC - cC;
-                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.p.candQ[idx++] = (uint16_t)(baseF + __popc(wF & ((1u << t) - 1u))); }
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; candQ[idx++] = (uint16_t)(baseF + __popc(wF & ((1u << t) - 1u))); }
+                    if constexpr (GEN) {
+                        w = wM;
+                        idx = inM - cM;
+                        while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.g.mmJ[idx++] = (uint16_t)(32 * lane + t); }
+                    }
                 }
                 __syncwarp();
-                for (int q = lane; q < nF; q += 32) S.u.p.keys[q] = agent_draws_rk(a.id[s + S.u.p.ffJ[q]], step, STREAM_PAIR, RK).x;
+                for (int q = lane; q < nF; q += 32) keys[q] = agent_draws_rk(a.id[s + ffJ[q]], step, STREAM_PAIR, RK).x;
+                if constexpr (GEN) {
+                    for (int m = lane; m < nMc; m += 32) S.u.g.mkeys[m] = agent_draws_rk(a.id[s + S.u.g.mmJ[m]], step, STREAM_PAIR, RK).x;
+                }
                 __syncwarp();
+                const int np = min(nF, nMc);  // couples
                 for (int i = lane; i < nCand; i += 32) {
-                    const int q = S.u.p.candQ[i];
-                    const uint32_t k = S.u.p.keys[q];
+                    const int q = candQ[i];
+                    const uint32_t k = keys[q];
                     // rank = number of smaller keys; four keys per shared-memory load; "<=" counts reveal ties (the key itself is one)
                     int r = 0, le = 0;
                     const int nF4 = nF & ~3;
                     for (int e = 0; e < nF4; e += 4) {
-                        const uint4 kk = *reinterpret_cast<const uint4 *>(&S.u.p.keys[e]);
+                        const uint4 kk = *reinterpret_cast<const uint4 *>(&keys[e]);
                         r += (kk.x < k) + (kk.y < k) + (kk.z < k) + (kk.w < k);
                         le += (kk.x <= k) + (kk.y <= k) + (kk.z <= k) + (kk.w <= k);
                     }
                     for (int e = nF4; e < nF; e++) {
-                        const uint32_t ke = S.u.p.keys[e];
+                        const uint32_t ke = keys[e];
                         r += (ke < k) ? 1 : 0;
                         le += (ke <= k) ? 1 : 0;
                     }
                     if ((le - r) > 1) {  // equal keys (about one pair in 10^8): the id decides
-                        const int64_t myId = a.id[s + S.u.p.ffJ[q]];
+                        const int64_t myId = a.id[s + ffJ[q]];
                         for (int e = 0; e < nF; e++) {
-                            if (e != q && S.u.p.keys[e] == k && a.id[s + S.u.p.ffJ[e]] < myId) r++;
+                            if (e != q && keys[e] == k && a.id[s + ffJ[e]] < myId) r++;
                         }
                     }
-                    if (r >= nMc) sdec[S.u.p.ffJ[q]] &= (uint8_t)~F_BORN;  // no mate: no birth
+                    if (r >= np) sdec[ffJ[q]] &= (uint8_t)~F_BORN;  // no mate: no birth
+                    if constexpr (GEN) S.u.g.candR[i] = (uint16_t)r;
+                }
+                if constexpr (GEN) {
+                    for (int m = lane; m < nMc; m += 32) {  // rank of every fertile male; the first np of them are mates
+                        const uint32_t k = S.u.g.mkeys[m];
+                        int r = 0, le = 0;
+                        const int nM4 = nMc & ~3;
+                        for (int e = 0; e < nM4; e += 4) {
+                            const uint4 kk = *reinterpret_cast<const uint4 *>(&S.u.g.mkeys[e]);
+                            r += (kk.x < k) + (kk.y < k) + (kk.z < k) + (kk.w < k);
+                            le += (kk.x <= k) + (kk.y <= k) + (kk.z <= k) + (kk.w <= k);
+                        }
+                        for (int e = nM4; e < nMc; e++) {
+                            const uint32_t ke = S.u.g.mkeys[e];
+                            r += (ke < k) ? 1 : 0;
+                            le += (ke <= k) ? 1 : 0;
+                        }
+                        if ((le - r) > 1) {
+                            const int64_t myId = a.id[s + S.u.g.mmJ[m]];
+                            for (int e = 0; e < nMc; e++) if (e != m && S.u.g.mkeys[e] == k && a.id[s + S.u.g.mmJ[e]] < myId) r++;
+                        }
+                        if (r < np) S.u.g.maleOfRank[r] = S.u.g.mmJ[m];
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < nCand; i += 32) {  // the mate of rank r is the father
+                        const int r = S.u.g.candR[i];
+                        if (r < np) father[s + ffJ[candQ[i]]] = s + S.u.g.maleOfRank[r];
+                    }
                 }
                 __syncwarp();
             }

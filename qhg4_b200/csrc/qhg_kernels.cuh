@@ -82,6 +82,8 @@ struct DevStats {
     // finds the state as it was before that step (`step` tells which one) and redoes it the slow way
     int halt;
     int pad0;
+    int doneBlocks;               // blocks of the step's last kernel that have finished (the last one does the step's book-keeping)
+    int pad1;
     long long agentSteps;         // sum over the completed steps of the live agents at step start
     long long totSent, totRecv;   // agents sent to / received from other ranks, summed over the completed steps
 };
@@ -775,7 +777,8 @@ k_scatter(const DevStats *__restrict__ st, AgentArrays a, AgentArrays o, const i
     }
 }
 
-__global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) {
+// the step's book-keeping on the device (one thread): the new buffer becomes the current one, ids and the step counter advance
+__device__ __forceinline__ void step_end_body(DevStats *st, int advanceStep, long long globalBirths) {
     if (st->overflow || st->oversize || st->halt) { st->halt = 1; return; }
     if (advanceStep) { st->agentSteps += st->nAgents; st->totSent += st->nSent; st->totRecv += st->nRecv; }
     st->nAgents = st->nNew;
@@ -783,6 +786,7 @@ __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths
     st->nextID += (globalBirths >= 0) ? globalBirths : (globalBirths == -2 ? st->globalBirths : (long long)st->nBirths);
     if (advanceStep) st->step++;
 }
+__global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) { step_end_body(st, advanceStep, globalBirths); }
 
 // PopBase::getNumAgentsArray hands out ulong counts (core/SPopulation.h); a shard reports 0 for the cells of other ranks
 __global__ void k_counts_u64(int nCells, int cLo, int cHi, const int *__restrict__ count, unsigned long long *__restrict__ out) {

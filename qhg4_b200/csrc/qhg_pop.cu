@@ -926,6 +926,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     cudaEvent_t t0 = nullptr, t1 = nullptr;  // device time of the whole pipeline, gaps between the launches included
     if (q.timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, q.stream); }
     for (int attempt = 0; attempt < 2; attempt++) {
+        bool stepEndFused = false;  // did the step's last kernel do k_step_end's book-keeping itself?
         if (tiled) {
             const int gridC = q.numSMs * DECIDE_CTAS_PER_SM;  // persistent: 32 warps per SM, one warp per cell at a time
             if (useNav) {
@@ -936,9 +937,17 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 CK(cudaMemsetAsync(q.jumpCount.p, 0, sizeof(int), q.stream));
             }
             const int jumpCap = (int)q.jumps.n;
-            if (q.genetic) {  // QHG_GEN_FAST: births carry the father's position, genome handles follow the agents
+            const bool sparse = segSparse(p);
+#define QHG_SEG_LAUNCH_X(NAME, SB_, GEN_, NAV_)                                                                                \
+    LAUNCH(p, NAME, (k_seg_decide<false, SB_, GEN_, NAV_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),      \
+           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p,                     \
+           GEN_ ? q.father.p : (int *)nullptr, NAV_ ? q.jumps.p : (JumpEntry *)nullptr, NAV_ ? q.jumpCount.p : (int *)nullptr, jumpCap)
+            if (q.genetic) {  // births carry the father's position, genome handles follow the agents
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
-                if (useNav) {
+                if (q.segDecide) {
+                    if (useNav) { if (sparse) QHG_SEG_LAUNCH_X("k_cell_decide_genetic_nav", 8, true, true); else QHG_SEG_LAUNCH_X("k_cell_decide_genetic_nav", 4, true, true); }
+                    else { if (sparse) QHG_SEG_LAUNCH_X("k_cell_decide_genetic", 8, true, false); else QHG_SEG_LAUNCH_X("k_cell_decide_genetic", 4, true, false); }
+                } else if (useNav) {
                     LAUNCH(p, "k_cell_decide_genetic_nav", (k_cell_decide<false, true, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                            q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p,
                            q.jumps.p, q.jumpCount.p, jumpCap);
@@ -946,6 +955,8 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                     LAUNCH(p, "k_cell_decide_genetic", (k_cell_decide<false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                            q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, q.father.p);
                 }
+            } else if (useNav && q.segDecide) {
+                if (sparse) QHG_SEG_LAUNCH_X("k_cell_decide_nav", 8, false, true); else QHG_SEG_LAUNCH_X("k_cell_decide_nav", 4, false, true);
             } else if (useNav) {
                 LAUNCH(p, "k_cell_decide_nav", (k_cell_decide<false, false, true>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, (int *)nullptr,
@@ -954,7 +965,6 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 // one warp per batch of cells (qhg_decide.cuh); the tutorial action order as straight-line code; 8 cells per grab
                 // for sparse populations, 4 for dense ones
                 const bool spec = P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge;
-                const bool sparse = segSparse(p);
 #define QHG_SEG_LAUNCH(NAME, SPEC_, SB_)                                                                                      \
     LAUNCH(p, NAME, (k_seg_decide<SPEC_, SB_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),                  \
            q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p)
@@ -963,6 +973,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 else if (sparse) QHG_SEG_LAUNCH("k_cell_decide_generic", false, 8);
                 else QHG_SEG_LAUNCH("k_cell_decide_generic", false, 4);
 #undef QHG_SEG_LAUNCH
+#undef QHG_SEG_LAUNCH_X
             } else if (P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine) {  // the tutorial action order: compile-time specialised kernel
                 LAUNCH(p, "k_cell_decide", k_cell_decide<true>, gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),
                        q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p);
@@ -979,9 +990,9 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 const int R = q.shRanks, parity = (int)(q.xStep & 1u);
                 LAUNCH(p, "k_halo_push", k_halo_push, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.dCellBegin.p, q.shRank, R, q.nCells, parity,
                        q.arrive.p, q.remoteBase.p, q.dPeers.p, q.dstats.p);
-                LAUNCH(p, "k_xbarrier_counts", k_xbarrier, 1, 32, q.shRank, R, 0, q.xStep + 1, q.dPeers.p, q.dstats.p, xbarrierTimeout());
-                LAUNCH(p, "k_halo_merge", k_halo_merge, q.gridFor(q.nHalo), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
-                       q.nCells, parity, q.dPeers.p, q.shRank, q.arrive.p, q.cursor.p);
+                // barrier A and the merge of the remote arrivals in one launch
+                LAUNCH(p, "k_xbarrier_merge", k_xbarrier_merge, q.gridFor(std::max(q.nHalo, 1)), 256, q.nHalo, q.dHalo.p, q.cellBegin[q.shRank], q.cellBegin[q.shRank + 1],
+                       q.nCells, parity, q.dPeers.p, q.shRank, R, q.xStep + 1, q.arrive.p, q.cursor.p, q.dstats.p, xbarrierTimeout());
                 H.on = 1; H.rank = q.shRank; H.nranks = R; H.c0 = q.cellBegin[q.shRank]; H.c1 = q.cellBegin[q.shRank + 1];
                 H.cellBegin = q.dCellBegin.p; H.p2p = 1; H.recvCap = q.recvCap; H.remoteBase = q.remoteBase.p; H.peers = q.dPeers.p;
                 if (q.genetic) { H.pool = q.gpool.p; H.rowWords = 2 * q.gp.nBlocks; }
@@ -1030,27 +1041,36 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
+            // pass 2: 384-agent windows and 6 CTAs per SM for dense populations, 256 and 8 for sparse ones
+#define QHG_SCATTER_ARGS q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p, q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, \
+                         q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H
+            const bool sparseS = segSparse(p);
             if (q.genetic) {
-                LAUNCH(p, "k_cell_scatter_genetic", k_cell_scatter<true>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
-                       q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H,
-                       q.father.p, q.births.p, q.gctl.p, q.dec.p);
+                if (sparseS) LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32,
+                                    QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p);
+                else LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32,
+                            QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p);
                 if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
                                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             } else {
-            LAUNCH(p, "k_cell_scatter", k_cell_scatter<false>, q.numSMs * SCATTER_CTAS_PER_SM, CW * 32, q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p,
-                   q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H);
-            if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
-                               q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
+                if (sparseS) LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32, QHG_SCATTER_ARGS);
+                else LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32, QHG_SCATTER_ARGS);
+                if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
+                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             }
+#undef QHG_SCATTER_ARGS
             const int rowW = q.genetic ? 2 * q.gp.nBlocks : 0;
             if (q.sharded && q.p2p) {  // the records are already in the owners' buffers: barrier, then everybody places what it got
-                LAUNCH(p, "k_xbarrier_records", k_xbarrier, 1, 32, q.shRank, q.shRanks, 1, q.xStep + 1, q.dPeers.p, q.dstats.p, xbarrierTimeout());
+                // barrier B inside the placement kernel; without Genetics it is the step's last kernel and ends the step as well
                 if (q.genetic) {
                     LAUNCH(p, "k_place_migrants", k_place_migrants_p2p<true>, q.numSMs * 4, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
-                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge, q.gctl.p, q.gfree.p, q.gpool.p, rowW, (int)q.poolRows);
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge, q.gctl.p, q.gfree.p, q.gpool.p, rowW, (int)q.poolRows,
+                           q.shRanks, q.xStep + 1, xbarrierTimeout(), 0, 0);
                 } else {
                     LAUNCH(p, "k_place_migrants", k_place_migrants_p2p<false>, q.numSMs * 2, 256, q.dstats.p, q.dPeers.p, q.shRank, q.recvCap, o,
-                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge);
+                           q.cellStart[q.cur ^ 1].p, q.stay.p, q.cursor.p, P.storeAge, (const GenomeCtl *)nullptr, (const int *)nullptr,
+                           (unsigned long long *)nullptr, 0, 0, q.shRanks, q.xStep + 1, xbarrierTimeout(), 1, advanceStep ? 1 : 0);
+                    stepEndFused = true;
                 }
                 q.xStep++;
             } else if (q.sharded) {  // agent migration: packed records between the GPUs (NCCL over NVLink)
@@ -1107,7 +1127,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 LAUNCH(p, "k_free_genomes", k_free_genomes, ga, 256, q.dstats.p, q.gctl.p, q.dest.p, q.gslot[q.cur].p, q.gfree.p);
             }
         }
-        LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
+        if (!stepEndFused) LAUNCH(p, "k_step_end", k_step_end, 1, 1, q.dstats.p, advanceStep ? 1 : 0, stepEndBirths);
         CK(cudaGetLastError());
         if (q.timing && attempt == 0) { cudaEventRecord(t1, q.stream); q.kt("pipeline_total").pending.push_back({t0, t1}); }
         if (defer && tiled) {  // qhgb_run: the host does not wait for the step; the device raises `halt` if it could not complete
