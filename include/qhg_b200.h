@@ -158,6 +158,10 @@ int     qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out);
 /* the same for the cells [cell_begin, cell_end) only, out[0] = cell_begin's count: what a rank of a sharded run reads
  * back every step (its own cell range; the other cells are some other rank's and 0 here) */
 int     qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end, uint64_t *out);
+/* OccTracker::calcBitMap (core/OccTracker.cpp:95-106, called per tracked cell by updateCounts :36-45 after every step): is any agent
+ * of this population in cell cells[i]?  out[i] = 1 / 0.  n bytes cross the bus instead of the whole count array; a shard answers
+ * for its own cells (the host ORs the ranks' answers). */
+int     qhgb_get_occupied(qhgb_pop *p, int32_t n, const int32_t *cells, uint8_t *out);
 int     qhgb_get_step_stats(qhgb_pop *p, qhgb_step_stats *out);
 /* parity probes for the deterministic sub-steps: the arrays the reference keeps in
  * m_adEnvWeights (n_cells*(max_neigh+1) doubles, actions/SingleEvaluator.cpp:174-243), LinearBirth::m_adB /

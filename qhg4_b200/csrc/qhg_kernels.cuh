@@ -794,6 +794,15 @@ __global__ void k_counts_u64(int nCells, int cLo, int cHi, const int *__restrict
         out[c] = (c >= cLo && c < cHi) ? (unsigned long long)count[c] : 0ull;
 }
 
+// OccTracker::calcBitMap (core/OccTracker.cpp:95-106) asks every population "is anybody in this cell?" for a short list of
+// tracked cells after every step: one byte per tracked cell instead of the whole per-cell count array
+__global__ void k_occupied(int n, const int *__restrict__ cells, int cLo, int cHi, const int *__restrict__ count, uint8_t *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cells[i];
+        out[i] = (c >= cLo && c < cHi && count[c] > 0) ? 1 : 0;
+    }
+}
+
 // the host has seen the failed step and is about to redo it (or to retry on the generic path)
 __global__ void k_clear_halt(DevStats *st) {
     st->halt = 0;

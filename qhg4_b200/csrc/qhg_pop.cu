@@ -191,6 +191,8 @@ struct qhgb_pop {
     // grid / env
     DevBuf<int> nbr, gid, count[2], cellStart[2], stay, arrive, cursor, birthCount, birthBase, nFert;
     DevBuf<unsigned long long> count64;  // per-cell counts widened for qhgb_get_num_agents_array
+    DevBuf<int> occCells;                // qhgb_get_occupied: the tracked cells and their answer
+    DevBuf<uint8_t> occOut;
     DevBuf<int> moveBase;  // fast path: first arrival slot of the movers of (cell, direction), MOVE_STRIDE ints per cell
     DevBuf<uint8_t> nNbr, ice;
     DevBuf<double> alt, W, B, D;
@@ -1362,7 +1364,7 @@ int qhgb_destroy(qhgb_pop *p) {
     p->ice.release(); p->alt.release(); p->W.release(); p->B.release(); p->D.release(); p->TB.release(); p->TD.release(); p->tileSums.release();
     for (auto &kv : p->envExtra) kv.second.release();
     for (auto &kv : p->envDelta) kv.second.release();
-    p->cap.release(); p->Wtmp.release(); p->multiAllowed.release();
+    p->cap.release(); p->Wtmp.release(); p->multiAllowed.release(); p->occCells.release(); p->occOut.release();
     for (int b = 0; b < 2; b++) { p->gslot[b].release(); p->nbabies[b].release(); }
     p->gfree.release(); p->gpool.release(); p->births.release(); p->gctl.release(); p->father.release();
     p->jumps.release(); p->jumpCount.release();
@@ -1925,6 +1927,19 @@ int qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end,
     CK(cudaSetDevice(p->device));
     LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
     CK(cudaMemcpyAsync(out, p->count64.p + cell_begin, sizeof(uint64_t) * (size_t)(cell_end - cell_begin), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_occupied(qhgb_pop *p, int32_t n, const int32_t *cells, uint8_t *out) {
+    if (!p || (n > 0 && (!cells || !out))) return fail("qhgb_get_occupied: NULL argument");
+    if (n <= 0) return 0;
+    for (int i = 0; i < n; i++) if (cells[i] < 0 || cells[i] >= p->nCells) return fail("qhgb_get_occupied: cell index %d", cells[i]);
+    CK(cudaSetDevice(p->device));
+    if (p->occCells.n < (size_t)n) { CK(p->occCells.alloc(n)); CK(p->occOut.alloc(n)); }
+    CK(cudaMemcpyAsync(p->occCells.p, cells, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, p->stream));
+    LAUNCH(p, "k_occupied", k_occupied, p->gridFor(n), 256, n, p->occCells.p, p->cLo(), p->cHi(), p->count[p->cur].p, p->occOut.p);
+    CK(cudaMemcpyAsync(out, p->occOut.p, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }

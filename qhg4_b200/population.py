@@ -178,6 +178,13 @@ class GpuPopulation:
         check(self.L.qhgb_get_num_agents_range(self.h, int(c0), int(c1), _p(out)), "qhgb_get_num_agents_range")
         return out
 
+    def occupied(self, cells):
+        """OccTracker::calcBitMap for this population: one byte per listed cell, 1 = somebody is there"""
+        c = np.ascontiguousarray(cells, np.int32)
+        out = np.zeros(len(c), np.uint8)
+        check(self.L.qhgb_get_occupied(self.h, len(c), _p(c), _p(out)), "qhgb_get_occupied")
+        return out
+
     def step_stats(self) -> StepStats:
         s = StepStats()
         check(self.L.qhgb_get_step_stats(self.h, C.byref(s)), "qhgb_get_step_stats")

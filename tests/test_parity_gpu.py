@@ -246,6 +246,19 @@ def test_dense_and_sparse_cells_mix():
         assert_same_population(g, o, k)
 
 
+def test_occupancy_of_tracked_cells(small_world):
+    """qhgb_get_occupied = OccTracker::calcBitMap for one population (core/OccTracker.cpp:95-106): one byte per tracked cell,
+    equal to (count > 0) of the per-cell counts, which are bit-exact against the reference (test_deterministic_substeps)."""
+    nbr, alt, pop, par = small_world
+    g, o = make_pair(par, nbr, alt, pop)
+    cells = np.random.default_rng(1).choice(len(nbr), 500, replace=False).astype(np.int32)
+    for k in range(4):
+        g.step(float(k)); o.step(float(k))
+        assert np.array_equal(g.occupied(cells), (o.counts()[cells] > 0).astype(np.uint8)), k
+    with pytest.raises(Exception):
+        g.occupied(np.array([len(nbr)], np.int32))
+
+
 def test_empty_population_and_late_agents(small_world):
     nbr, xyz, alt = small_world
     from qhg4_b200.population import GpuPopulation
