@@ -179,7 +179,11 @@ int  qhgb_get_capacities(qhgb_pop *p, double *out);
  * flags); qhgb_restore_state loads it into a population that was created and configured like the dumped one (cells,
  * environment arrays as of the dump, attributes, priorities, navigation) but holds no agents, and replaces
  * qhgb_add_agents + qhgb_pre_loop.  The continued run is bit-identical to the uninterrupted one.  The file format is
- * this library's own (HDF5, which the reference's QDF dumps use, is outside the path). */
+ * this library's own (HDF5, which the reference's QDF dumps use, is outside the path).
+ * `path` of qhgb_restore_state may name several files separated by '\n' -- the dumps of all ranks of a sharded run; a sharded
+ * population then keeps the agents (and genome rows) of its own cell range from every file.  That is how a run is re-split
+ * over new cell ranges, or another number of GPUs, when its load has shifted (after environment events):
+ * every rank dumps, the host computes new ranges, new populations restore (qhg4_b200/sharding.py::rebalance). */
 int  qhgb_dump_state(qhgb_pop *p, const char *path);
 int  qhgb_restore_state(qhgb_pop *p, const char *path);
 

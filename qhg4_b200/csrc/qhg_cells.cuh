@@ -1141,7 +1141,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
                const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H,
                const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
-               uint8_t *decMark = nullptr) {
+               uint8_t *decMark = nullptr, int shrink = 0) {
     static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
     using WSS = typename std::conditional<GEN, WarpSmemSG<SCH>, WarpSmemS<SCH>>::type;
     __shared__ WSS smem[CW];
@@ -1161,12 +1161,17 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
     }
     __syncwarp();
     unsigned phase = 0;  // parity of the next completion of every stage's barrier
+    const int nWarpsS = gridDim.x * CW;
+    int lastEnd = cLo;
     for (;;) {
+        // (short ranges -- the shards of a many-GPU run -- get grabs that shrink towards the end: no tail of a whole batch)
+        const int g = shrink ? max(1, min(CELL_BATCH, (cHi - lastEnd) / (2 * nWarpsS))) : CELL_BATCH;
         int cBase = 0;
-        if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, CELL_BATCH);
+        if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, g);
         cBase = __shfl_sync(FULL, cBase, 0);
         if (cBase >= cHi) break;
-        const int cEnd = min(cBase + CELL_BATCH, cHi);
+        lastEnd = cBase + g;
+        const int cEnd = min(cBase + g, cHi);
         // lane l keeps the numbers of cell cBase+l (lane CELL_BATCH-or-less: the end of the batch)
         int csL = 0, nsL = 0, arL = 0, bbL = 0, nbL = -1;
         if (cBase + lane <= cEnd) csL = cellStart[cBase + lane];

@@ -65,7 +65,7 @@ template <bool SPEC, int SB, bool GEN = false, bool NAV = false>
 __global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
 k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
-             int *__restrict__ moveBase, int *__restrict__ father = nullptr, JumpEntry *__restrict__ jumps = nullptr,
+             int *__restrict__ moveBase, int shrink, int *__restrict__ father = nullptr, JumpEntry *__restrict__ jumps = nullptr,
              int *__restrict__ jumpCount = nullptr, int jumpCap = 0) {
     static_assert(!(SPEC && (GEN || NAV)), "the compile-time program has neither Genetics nor Navigate");
     static_assert(SB + 1 <= 32 && SB * 8 <= 4 * 32, "one lane per cell start; at most four rounds of (cell, direction) lanes");
@@ -94,13 +94,19 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
 #pragma unroll
     for (int r = 0; r < PEND; r++) { pendIdx[r] = -1; pendVal[r] = 0; }
 
-    // cells are handed out dynamically, SB at a time (sea cells are empty, land cells are not: a static split leaves a tail)
+    // cells are handed out dynamically, SB at a time (sea cells are empty, land cells are not: a static split leaves a tail).
+    // A range with few grabs per warp (a shard of an 8-GPU run: about four) would end with a tail of up to one grab -- 20 % of
+    // the pass there -- so the host asks for grabs that shrink towards the end of the range (`shrink`; it costs 2 % where the
+    // range is long and is off there)
+    const int nWarps = gridDim.x * DCW;
+    int lastEnd = cLo;  // where this warp's last grab ended: the work counter is at least there
     for (;;) {
-    const int g = SB;
+    const int g = shrink ? max(1, min(SB, (cHi - lastEnd) / (2 * nWarps))) : SB;
     int cBase = 0;
     if (lane == 0) cBase = cLo + atomicAdd(&st->workDecide, g);
     cBase = __shfl_sync(FULL, cBase, 0);
     if (cBase >= cHi) break;
+    lastEnd = cBase + g;
     const int nB = min(g, cHi - cBase);
     const int csL = (lane <= nB) ? cellStart[cBase + lane] : 0;
     int g0 = 0;

@@ -940,9 +940,11 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             }
             const int jumpCap = (int)q.jumps.n;
             const bool sparse = segSparse(p);
+            // few grabs per warp (the shards of a many-GPU run): the grabs shrink towards the end of the range
+            const int shrinkGrabs = (q.cHi() - q.cLo()) < 128 * q.numSMs * 32 ? 1 : 0;
 #define QHG_SEG_LAUNCH_X(NAME, SB_, GEN_, NAV_)                                                                                \
     LAUNCH(p, NAME, (k_seg_decide<false, SB_, GEN_, NAV_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),      \
-           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p,                     \
+           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, shrinkGrabs,        \
            GEN_ ? q.father.p : (int *)nullptr, NAV_ ? q.jumps.p : (JumpEntry *)nullptr, NAV_ ? q.jumpCount.p : (int *)nullptr, jumpCap)
             if (q.genetic) {  // births carry the father's position, genome handles follow the agents
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
@@ -969,7 +971,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 const bool spec = P.prog == PROG_TUT5 && P.nOps == 5 && !P.selfMate && !P.confine && !P.storeAge;
 #define QHG_SEG_LAUNCH(NAME, SPEC_, SB_)                                                                                      \
     LAUNCH(p, NAME, (k_seg_decide<SPEC_, SB_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),                  \
-           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p)
+           q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, shrinkGrabs)
                 if (spec && sparse) QHG_SEG_LAUNCH("k_cell_decide", true, 8);
                 else if (spec) QHG_SEG_LAUNCH("k_cell_decide", true, 4);
                 else if (sparse) QHG_SEG_LAUNCH("k_cell_decide_generic", false, 8);
@@ -1049,14 +1051,16 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             const bool sparseS = segSparse(p);
             if (q.genetic) {
                 if (sparseS) LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32,
-                                    QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p);
+                                    QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkGrabs);
                 else LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32,
-                            QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p);
+                            QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkGrabs);
                 if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
                                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             } else {
-                if (sparseS) LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32, QHG_SCATTER_ARGS);
-                else LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32, QHG_SCATTER_ARGS);
+                if (sparseS) LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32, QHG_SCATTER_ARGS,
+                                    (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkGrabs);
+                else LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32, QHG_SCATTER_ARGS,
+                            (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkGrabs);
                 if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
                                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             }
@@ -2228,40 +2232,82 @@ static int dump_state_impl(qhgb_pop *p, const char *path) {
     return 0;
 }
 
-static int restore_state_impl(qhgb_pop *p, const char *path) {
-    if (!p || !path) return fail("qhgb_restore_state: NULL argument");
+static int restore_state_impl(qhgb_pop *p, const char *paths) {
+    if (!p || !paths) return fail("qhgb_restore_state: NULL argument");
     if (p->preLooped || p->nAgents > 0) return fail("qhgb_restore_state: the population must be configured (cells, environment, attributes, priorities) but empty");
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail("qhgb_restore_state: cannot open [%s]", path);
+    // one file, or several separated by newlines: the dumps of ALL ranks of a sharded run.  A sharded population keeps the
+    // agents of its own cell range from every file -- which is how a run is re-split over other ranges (or another number of
+    // GPUs) after its load has shifted: dump, new ranges, restore.
+    std::vector<std::string> files;
+    {
+        std::string all(paths);
+        size_t pos = 0;
+        while (pos <= all.size()) {
+            const size_t e = all.find('\n', pos);
+            const std::string one = all.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+            if (!one.empty()) files.push_back(one);
+            if (e == std::string::npos) break;
+            pos = e + 1;
+        }
+    }
+    if (files.empty()) return fail("qhgb_restore_state: no file name");
     DumpHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "QHGB200D", 8) != 0 || h.version != 1) { fclose(f); return fail("qhgb_restore_state: [%s] is not a qhg4_b200 dump", path); }
-    if (p->popClass != h.popClass || h.nCells != p->nCells || h.maxNeigh != p->maxNeigh || (h.genetic != 0) != p->genetic ||
-        (p->genetic && h.rowWords != 2 * p->gp.nBlocks) || h.nSubs != (int)p->subs.size()) {
+    std::vector<int32_t> cell;
+    std::vector<int64_t> id;
+    std::vector<float> birth, age, last;
+    std::vector<uint8_t> gender;
+    std::vector<uint32_t> life;
+    std::vector<uint64_t> genomes;
+    std::vector<int32_t> nbab;
+    std::vector<double> W, cap;
+    const int c0 = p->cLo(), c1 = p->cHi();
+    for (size_t fi = 0; fi < files.size(); fi++) {
+        const char *path = files[fi].c_str();
+        FILE *f = fopen(path, "rb");
+        if (!f) return fail("qhgb_restore_state: cannot open [%s]", path);
+        DumpHeader hf{};
+        if (fread(&hf, sizeof(hf), 1, f) != 1 || memcmp(hf.magic, "QHGB200D", 8) != 0 || hf.version != 1) { fclose(f); return fail("qhgb_restore_state: [%s] is not a qhg4_b200 dump", path); }
+        if (p->popClass != hf.popClass || hf.nCells != p->nCells || hf.maxNeigh != p->maxNeigh || (hf.genetic != 0) != p->genetic ||
+            (p->genetic && hf.rowWords != 2 * p->gp.nBlocks) || hf.nSubs != (int)p->subs.size()) {
+            fclose(f);
+            return fail("qhgb_restore_state: the dump is of [%s], %d cells, %d genome words -- not this population", hf.popClass, hf.nCells, hf.rowWords);
+        }
+        const int64_t nf = hf.nAgents;
+        {   // a corrupt header must not size the buffers below: the counts have to be plausible and the file as long as they say
+            if (nf < 0 || nf > (int64_t)2000000000 || hf.rowWords < 0 || hf.rowWords > (1 << 20)) { fclose(f); return fail("qhgb_restore_state: [%s] has a corrupt header (%lld agents)", path, (long long)nf); }
+            const long long per = 4 + 8 + 4 + 1 + 4 + 4 + 4 + 8ll * hf.rowWords + (hf.genetic ? 4 : 0);
+            const long long need = (long long)sizeof(hf) + nf * per + 8ll * hf.nCells * WSTRIDE + (hf.haveCap ? 8ll * hf.nCells : 0);
+            fseek(f, 0, SEEK_END);
+            const long long have = ftell(f);
+            fseek(f, (long)sizeof(hf), SEEK_SET);
+            if (have < need) { fclose(f); return fail("qhgb_restore_state: [%s] is truncated (%lld of %lld bytes)", path, have, need); }
+        }
+        std::vector<int32_t> fcell(nf);
+        std::vector<int64_t> fid(nf);
+        std::vector<float> fbirth(nf), fage(nf), flast(nf);
+        std::vector<uint8_t> fgender(nf);
+        std::vector<uint32_t> flife(nf);
+        std::vector<uint64_t> fgen((size_t)nf * hf.rowWords);
+        std::vector<int32_t> fnb(hf.genetic ? nf : 0);
+        std::vector<double> fW((size_t)hf.nCells * WSTRIDE), fcap(hf.haveCap ? hf.nCells : 0);
+        const bool ok = rd(f, fcell) && rd(f, fid) && rd(f, fbirth) && rd(f, fgender) && rd(f, fage) && rd(f, flast) && rd(f, flife) && rd(f, fgen) &&
+                        rd(f, fnb) && rd(f, fW) && rd(f, fcap);
         fclose(f);
-        return fail("qhgb_restore_state: the dump is of [%s], %d cells, %d genome words -- not this population", h.popClass, h.nCells, h.rowWords);
+        if (!ok) return fail("qhgb_restore_state: [%s] is truncated", path);
+        if (fi == 0) { h = hf; W.swap(fW); cap.swap(fcap); }
+        else if (hf.stepsDone != h.stepsDone) return fail("qhgb_restore_state: [%s] was dumped after %lld steps, the first file after %lld", path, (long long)hf.stepsDone, (long long)h.stepsDone);
+        h.nextID = std::max(h.nextID, hf.nextID);
+        for (int64_t i = 0; i < nf; i++) {
+            if (p->sharded && (fcell[i] < c0 || fcell[i] >= c1)) continue;  // another rank's cell under the ranges in force now
+            cell.push_back(fcell[i]); id.push_back(fid[i]); birth.push_back(fbirth[i]); gender.push_back(fgender[i]);
+            age.push_back(fage[i]); last.push_back(flast[i]); life.push_back(flife[i]);
+            if (hf.genetic) {
+                nbab.push_back(fnb[i]);
+                genomes.insert(genomes.end(), fgen.begin() + (size_t)i * hf.rowWords, fgen.begin() + (size_t)(i + 1) * hf.rowWords);
+            }
+        }
     }
-    const int64_t n = h.nAgents;
-    {   // a corrupt header must not size the buffers below: the counts have to be plausible and the file as long as they say
-        if (n < 0 || n > (int64_t)2000000000 || h.rowWords < 0 || h.rowWords > (1 << 20)) { fclose(f); return fail("qhgb_restore_state: [%s] has a corrupt header (%lld agents)", path, (long long)n); }
-        const long long per = 4 + 8 + 4 + 1 + 4 + 4 + 4 + 8ll * h.rowWords + (h.genetic ? 4 : 0);
-        const long long need = (long long)sizeof(h) + n * per + 8ll * h.nCells * WSTRIDE + (h.haveCap ? 8ll * h.nCells : 0);
-        fseek(f, 0, SEEK_END);
-        const long long have = ftell(f);
-        fseek(f, (long)sizeof(h), SEEK_SET);
-        if (have < need) { fclose(f); return fail("qhgb_restore_state: [%s] is truncated (%lld of %lld bytes)", path, have, need); }
-    }
-    std::vector<int32_t> cell(n);
-    std::vector<int64_t> id(n);
-    std::vector<float> birth(n), age(n), last(n);
-    std::vector<uint8_t> gender(n);
-    std::vector<uint32_t> life(n);
-    std::vector<uint64_t> genomes((size_t)n * h.rowWords);
-    std::vector<int32_t> nbab(h.genetic ? n : 0);
-    std::vector<double> W((size_t)h.nCells * WSTRIDE), cap(h.haveCap ? h.nCells : 0);
-    bool ok = rd(f, cell) && rd(f, id) && rd(f, birth) && rd(f, gender) && rd(f, age) && rd(f, last) && rd(f, life) && rd(f, genomes) && rd(f, nbab) &&
-              rd(f, W) && rd(f, cap);
-    fclose(f);
-    if (!ok) return fail("qhgb_restore_state: [%s] is truncated", path);
+    const int64_t n = (int64_t)cell.size();
     CK(cudaSetDevice(p->device));
     p->key.k0 = h.key[0]; p->key.k1 = h.key[1];
     if (n > 0 && qhgb_add_agents(p, n, cell.data(), id.data(), birth.data(), gender.data(), age.data(), last.data(), life.data()) != 0) return -1;

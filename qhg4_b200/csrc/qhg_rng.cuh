@@ -94,7 +94,9 @@ __device__ __forceinline__ uint32_t u2int_s(uint32_t x, uint32_t a, uint32_t b, 
 
 // atan in double, argument reduction + odd polynomial (the classic fdlibm scheme), written with
 // explicitly rounded operations so that the oracle's counter mode (same operation order on the CPU)
-// gives the identical bits.  |error| < 1 ulp against libm (tests/test_kernels_gpu.py).
+// gives the identical bits.  The resulting p(age) is within 1e-6 relative of the reference's libm value
+// (tests/test_parity_gpu.py::test_deterministic_substeps_vs_reference) and equal to the golden curve generated from the
+// reference through the oracle (tests/test_oracle_golden.py).
 __device__ __forceinline__ double atan_rn(double x) {
     const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01,
                            -1.11111104054623557880e-01, 9.09088713343650656196e-02, -7.69187620504482999495e-02,

@@ -84,3 +84,46 @@ def connect(pop, begin, rank: int, nranks: int, p2p: bool | None = None):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag) == 0:
             pop.comm_p2p_connect(None)
+
+
+def rebalance(pop, make_population, rank: int, nranks: int, workdir: str, p2p: bool | None = None):
+    """Re-split a sharded run over new cell ranges when its load has shifted ("may need re-splitting after env
+    events").  Collective over all ranks, between two steps:
+
+      1. every rank dumps its state (`qhgb_dump_state`) into `workdir` (a directory all ranks see) and frees its GPU memory;
+      2. the per-cell counts of all ranks give the new cost-balanced ranges (`partition_cells`);
+      3. `make_population()` builds a population configured like the old one -- cells, the CURRENT environment arrays,
+         attributes, priorities, seed; not yet connected -- and `prepare(new_pop)` (optional attribute of the factory) sets what
+         must follow the connection (navigation tables);
+      4. the new population joins the run with the new ranges and restores from ALL ranks' dumps, keeping the agents (and
+         genome rows) of its own range (`qhgb_restore_state` with several files).
+
+    Returns (new population, new boundaries).  The continued run is bit-identical to one that was never re-split: results do
+    not depend on which rank owns a cell."""
+    import os
+    import torch
+    import torch.distributed as dist
+    cnt = torch.from_numpy(pop.counts().astype(np.int64))
+    if nranks > 1:
+        dist.all_reduce(cnt)
+    begin = partition_cells(cnt.numpy(), nranks)
+    path = os.path.join(workdir, f"rebalance_rank{rank}.qhgb")
+    pop.dump_state(path)
+    pop.close()
+    if nranks > 1:
+        dist.barrier()
+    new = make_population()
+    connect(new, begin, rank, nranks, p2p=p2p)
+    prepare = getattr(make_population, "prepare", None)
+    if prepare is not None:
+        prepare(new)
+    new.restore_state("\n".join(os.path.join(workdir, f"rebalance_rank{r}.qhgb") for r in range(nranks)))
+    if nranks > 1:
+        dist.barrier()
+    if rank == 0:
+        for r in range(nranks):
+            try:
+                os.unlink(os.path.join(workdir, f"rebalance_rank{r}.qhgb"))
+            except OSError:
+                pass
+    return new, begin

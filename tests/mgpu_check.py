@@ -122,11 +122,93 @@ def main_genetic(rank, world):
               f"{int(tot)} cross-rank migrations incl. far jumps ({how} exchange), agents + genomes + NumBabies bit-exact vs the unsharded oracle")
 
 
+def main_rebalance(rank, world, genetic):
+    """A run that starts on a poor split (equal numbers of CELLS per rank: the sea is empty) and is re-split in the middle with
+    sharding.rebalance -- every rank dumps, new cost-balanced ranges, new populations restore from all dumps -- then goes on:
+    bit-exact against the unsharded oracle before and after, agents (and genomes, NumBabies)."""
+    import tempfile
+    from qhg4_b200.icogrid import synthetic_climate
+    from qhg4_b200.params import ooa_nav_gen
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=5)
+    env = synthetic_climate(xyz, alt, seed=6) if genetic else None
+    pop = synthetic_population(60000, alt, seed=6, fertile=True)
+    G = 128
+    row = 2 * (G // 64)
+    par = ooa_nav_gen(G, -1, 2e-3) if genetic else tut_environ_alt(45.0)
+    st = seed_state(51)
+    gen0 = np.random.default_rng(4).integers(0, 2 ** 63, size=(len(pop["id"]), row), dtype=np.int64).astype(np.uint64)
+    begin = sharding.partition_cells(np.ones(len(nbr), np.int64), world, cell_cost=0)  # by cells: unbalanced on purpose
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+
+    def make():
+        return GpuPopulation.from_params(par, nbr, alt, state16=st, env=env, device=dev)
+
+    g = make()
+    sharding.connect(g, begin, rank, world)
+    g.add_agents(pop)
+    if genetic:
+        own = (pop["cell"] >= begin[rank]) & (pop["cell"] < begin[rank + 1])
+        g.set_genomes(gen0[own])
+    g.pre_loop()
+    o = None
+    if rank == 0:
+        from oracle import port
+        o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st, env=env)
+        o.add_agents(pop)
+        if genetic:
+            o.set_genomes(gen0)
+        o.start()
+
+    def compare(tag, lo, hi):
+        mine = g.agents()
+        assert np.all((mine["cell"] >= lo) & (mine["cell"] < hi)), "an agent sits on a rank that does not own its cell"
+        rec = {f: mine[f] for f in FIELDS}
+        if genetic:
+            rec["genome"], rec["nbabies"] = g.genomes(row)
+        parts = [None] * world
+        dist.gather_object(rec, parts if rank == 0 else None, dst=0)
+        if rank == 0:
+            got = gather_sorted(parts, tuple(rec.keys()))
+            oa = o.agents()
+            oo = np.argsort(oa["id"])
+            assert len(got["id"]) == o.num_agents(), (tag, len(got["id"]), o.num_agents())
+            for f in FIELDS:
+                assert np.array_equal(got[f], oa[f][oo]), (tag, f)
+            if genetic:
+                og, onb = o.genomes(row)
+                assert np.array_equal(got["genome"], og[oo]) and np.array_equal(got["nbabies"], onb[oo]), tag
+
+    sizes = [g.num_agents()]
+    for k in range(12):
+        if k == 6:  # re-split: the shared directory is rank 0's temporary directory
+            box = [tempfile.mkdtemp(prefix="qhg_rebalance_")] if rank == 0 else [None]
+            dist.broadcast_object_list(box, src=0)
+            g, begin = sharding.rebalance(g, make, rank, world, box[0])
+            sizes.append(g.num_agents())
+            compare("after the re-split", begin[rank], begin[rank + 1])
+        g.step(float(k))
+        if rank == 0:
+            o.step(float(k))
+        compare(k, begin[rank], begin[rank + 1])
+    per = [None] * world
+    dist.gather_object(sizes, per if rank == 0 else None, dst=0)
+    if rank == 0:
+        before, after = [p[0] for p in per], [p[1] for p in per]
+        assert max(after) - min(after) < max(before) - min(before), (before, after)
+        how = "peer-memory" if os.environ.get("QHG_P2P", "1") != "0" else "nccl"
+        print(f"mgpu_check ok [rebalance{', genetic' if genetic else ''}]: {world} ranks, agents per rank {before} -> {after} after sharding.rebalance at step 6, "
+              f"12 steps, {o.num_agents()} agents ({how} exchange), bit-exact vs the unsharded oracle before and after")
+
+
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    if len(sys.argv) > 1 and sys.argv[1] == "genetic":
-        main_genetic(rank, world)
+    if len(sys.argv) > 1 and sys.argv[1] in ("genetic", "rebalance", "rebalance-genetic"):
+        if sys.argv[1] == "genetic":
+            main_genetic(rank, world)
+        else:
+            main_rebalance(rank, world, sys.argv[1].endswith("genetic"))
         dist.barrier()
         dist.destroy_process_group()
         return

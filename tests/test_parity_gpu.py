@@ -273,8 +273,28 @@ def test_empty_population_and_late_agents(small_world):
     assert 800 < g.num_agents() <= 1000
 
 
+def _run_summaries(make_sim, par, nbr, alt, nseeds, nsteps):
+    """one vector of summary statistics per seed (independent samples): live agents, mean / 90th percentile / standard deviation
+    of the ages, share of occupied cells, variance of the per-cell counts, share of males; plus the pooled ages and counts"""
+    rows, ages, occ = [], [], []
+    for s in range(nseeds):
+        pop = synthetic_population(6000, alt, seed=100 + s)
+        sim = make_sim(par, nbr, alt, seed_state(1000 + s), pop)
+        for k in range(nsteps):
+            sim.step(float(k))
+        a, c = sim.agents(), np.asarray(sim.counts(), np.float64)
+        rows.append([sim.num_agents(), a["age"].mean(), np.percentile(a["age"], 90), a["age"].std(), (c > 0).mean(), c.var(), a["gender"].mean()])
+        ages.append(a["age"]); occ.append(c)
+        sim.close()
+    return np.array(rows), np.concatenate(ages), np.concatenate(occ)
+
+
 def test_statistical_equivalence_vs_reference():
-    """stochastic sub-steps: per-cell population and age distributions over 32 seeds, two-sample KS, p > 0.01."""
+    """Stochastic sub-steps, device against the reference with two OpenMP threads over 32 seeds.  The gate is a two-sample KS test,
+    p > 0.01, on statistics whose samples are INDEPENDENT -- one value per seed: population size, mean, 90th percentile and spread
+    of the ages, share of occupied cells, variance of the per-cell counts, sex ratio -- so the whole sample counts (no thinning).
+    The pooled per-agent ages and per-cell counts (correlated inside a run, hence thinned) are checked as before.
+    Negative control: the same device runs with Verhulst_K = 23 instead of 20 must FAIL the gate."""
     from scipy import stats
     from oracle import refsim
     if not refsim.available():
@@ -283,27 +303,29 @@ def test_statistical_equivalence_vs_reference():
     nbr = make_torus_grid(24, 24)
     alt = np.full(len(nbr), 800.0)
     alt[::7] = 1400.0
-    par = tut_environ_alt(20.0)
     nseeds, nsteps = 32, 40
-    tot_g, tot_r, age_g, age_r, occ_g, occ_r = [], [], [], [], [], []
-    for s in range(nseeds):
-        pop = synthetic_population(6000, alt, seed=100 + s)
-        st = seed_state(1000 + s)
-        g = GpuPopulation.from_params(par, nbr, alt, state16=st)
+
+    def gpu(par, nbr_, alt_, st, pop):
+        g = GpuPopulation.from_params(par, nbr_, alt_, state16=st)
         g.add_agents(pop); g.pre_loop()
-        r = refsim.RefSim(par, nbr, alt, threads=2, state16=st)
+        return g
+
+    def ref(par, nbr_, alt_, st, pop):
+        r = refsim.RefSim(par, nbr_, alt_, threads=2, state16=st)
         r.add_agents(pop); r.start()
-        for k in range(nsteps):
-            g.step(float(k)); r.step(float(k))
-        ga, ra = g.agents(), r.agents()
-        tot_g.append(g.num_agents()); tot_r.append(r.num_agents())
-        age_g.append(ga["age"]); age_r.append(ra["age"])
-        occ_g.append(g.counts()); occ_r.append(r.counts())
-        r.close(); g.close()
-    p_tot = stats.ks_2samp(tot_g, tot_r).pvalue
-    p_age = stats.ks_2samp(np.concatenate(age_g)[::7], np.concatenate(age_r)[::7]).pvalue
-    p_occ = stats.ks_2samp(np.concatenate(occ_g)[::3], np.concatenate(occ_r)[::3]).pvalue
-    assert p_tot > 0.01 and p_age > 0.01 and p_occ > 0.01, (p_tot, p_age, p_occ)
+        return r
+
+    sg, age_g, occ_g = _run_summaries(gpu, tut_environ_alt(20.0), nbr, alt, nseeds, nsteps)
+    sr, age_r, occ_r = _run_summaries(ref, tut_environ_alt(20.0), nbr, alt, nseeds, nsteps)
+    ps = [stats.ks_2samp(sg[:, j], sr[:, j]).pvalue for j in range(sg.shape[1])]
+    assert min(ps) > 0.01, ps
+    p_age = stats.ks_2samp(age_g[::7], age_r[::7]).pvalue
+    p_occ = stats.ks_2samp(occ_g[::3], occ_r[::3]).pvalue
+    assert p_age > 0.01 and p_occ > 0.01, (p_age, p_occ)
+    # the gate has power: a 15 % larger carrying capacity is told apart
+    sx, _, _ = _run_summaries(gpu, tut_environ_alt(23.0), nbr, alt, nseeds, nsteps)
+    px = [stats.ks_2samp(sx[:, j], sr[:, j]).pvalue for j in range(sx.shape[1])]
+    assert min(px) < 0.01, px
 
 
 @pytest.mark.parametrize("bits,ncross", [(1, -1), (2, 2)])
@@ -333,7 +355,7 @@ def test_genotype_distributions_statistically_equivalent_to_reference(bits, ncro
     assert sg.mean() > 1.0
 
 
-@pytest.mark.parametrize("which", ["tutorial", "genetic"])
+@pytest.mark.parametrize("which", ["tutorial", "genetic", "rebalance", "rebalance-genetic"])
 @pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
 def test_two_gpu_shards_equal_unsharded_oracle(exchange, which):
     """cell-range sharding on 2 GPUs, migration over peer memory (default) and over NCCL calls: bit-identical to the
@@ -350,7 +372,7 @@ def test_two_gpu_shards_equal_unsharded_oracle(exchange, which):
     env = dict(os.environ, QHG_P2P="1" if exchange == "peer-memory" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(root, "tests", "mgpu_check.py")] +
-                       (["genetic"] if which == "genetic" else []), capture_output=True, text=True, timeout=600, env=env)
+                       ([which] if which != "tutorial" else []), capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout and exchange in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
