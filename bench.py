@@ -413,6 +413,12 @@ def run_ours(args, rank, world):
 
     # ---- roofline: whole-step algorithmic bytes over the summed kernel time ------------------------------------
     peak, peak_src = measured_peak_gbs()
+    wait_names = ("k_xbarrier_merge", "k_place_migrants")  # kernels that contain a cross-GPU barrier: their time is mostly waiting
+    my_busy = sum(v[0] for k, v in ktimes.items() if k not in wait_names) / args.steps
+    per_rank_busy = [my_busy]
+    if dist is not None:
+        per_rank_busy = [None] * world
+        dist.all_gather_object(per_rank_busy, my_busy)
     kern_ms = allmax(sum(v[0] for v in ktimes.values()))  # slowest rank
     peak *= world
     genome_bytes = 3.0 * row * 8.0 * prof_births  # per birth: two parents read, one child written
@@ -434,6 +440,7 @@ def run_ours(args, rank, world):
             "peak_source": peak_src,
             "alg_bytes_per_step": alg_bytes / args.steps, "dominant_kernel": top,
             "pipeline_ms_per_step": round(pipeline_ms / args.steps, 4), "per_kernel": per_kernel,
+            "per_rank_busy_ms_per_step": [round(x, 4) for x in per_rank_busy],
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}}
 
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
