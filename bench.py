@@ -363,8 +363,14 @@ def run_ours(args, rank, world):
     pipeline_ms = ktimes.pop("pipeline_total", (0.0, 0))[0]  # device time of the steps, gaps between launches included
 
     # ---- timed region 2: end to end through the C ABI with host buffers --------------------------------------
-    counts = g.host_array(ncell, np.uint64)  # page-locked: the per-step result is one DMA into host memory
+    # the per-cell counts live in a page-locked host array that the library keeps current after every step, like the reference's
+    # m_aiNumAgentsPerCell (PopBase::getNumAgentsArray hands out the pointer): the copy is queued behind the step's kernels and
+    # arrives under the step's own synchronisation
+    c_lo, c_hi = (begin[rank], begin[rank + 1]) if world > 1 else (0, ncell)   # a shard reads back the counts of its own cell range
+    counts = g.host_array(c_hi - c_lo, np.uint64)
+    g.mirror_counts(counts, c_lo, c_hi)
     e2e_steps = 0
+    seen = 0
     levels = sorted(set(g.prios.values()))
     barrier()
     w0 = time.perf_counter()
@@ -374,18 +380,17 @@ def run_ours(args, rank, world):
         g.initialize_step(t)
         for lvl in levels:
             g.do_actions(lvl, t)
-        g.finalize_step()
-        st = g.step_stats()          # totals of the step (D2H inside finalize_step)
-        if world > 1:                # a shard reads back the counts of its own cell range
-            g.counts_range(begin[rank], begin[rank + 1], counts)
-        else:
-            g.counts(counts)         # per-cell counts into host memory, as PopBase::getNumAgentsArray exposes them
+        g.finalize_step()            # D2H inside: the step's totals and the per-cell counts of the mirror
+        st = g.step_stats()
+        seen += int(counts[0]) + int(counts[-1])  # the host touches the result of every step
         state["t"] += 1.0; state["k"] += 1
         if events and state["k"] % EVENT_EVERY == 0:
             env_event(state["t"])
     barrier()
     e2e_sec = allmax(time.perf_counter() - w0)
     e2e_val = allsum(e2e_steps) / e2e_sec
+    mirror_ok = bool(np.array_equal(counts, g.counts_range(c_lo, c_hi)))  # the mirrored array is the library's own read-back
+    g.mirror_counts(None)
 
     # ---- checksum of the final state: the same whatever the number of GPUs -------------------------------------
     t1 = time.time()
@@ -416,9 +421,15 @@ def run_ours(args, rank, world):
     wait_names = ("k_xbarrier_merge", "k_place_migrants")  # kernels that contain a cross-GPU barrier: their time is mostly waiting
     my_busy = sum(v[0] for k, v in ktimes.items() if k not in wait_names) / args.steps
     per_rank_busy = [my_busy]
+    per_rank_kernels = None
     if dist is not None:
         per_rank_busy = [None] * world
         dist.all_gather_object(per_rank_busy, my_busy)
+        per_rank_kernels = [None] * world  # where the ranks differ: the two passes of every rank, its agents and occupied cells
+        mine = {k: round(v[0] / args.steps, 4) for k, v in ktimes.items() if k.startswith(("k_cell_decide", "k_cell_scatter"))}
+        own = cnt_own = g.counts_range(int(begin[rank]), int(begin[rank + 1]))
+        mine.update({"agents": int(own.sum()), "occupied_cells": int((cnt_own > 0).sum()), "cells": int(begin[rank + 1] - begin[rank])})
+        dist.all_gather_object(per_rank_kernels, mine)
     kern_ms = allmax(sum(v[0] for v in ktimes.values()))  # slowest rank
     peak *= world
     genome_bytes = 3.0 * row * 8.0 * prof_births  # per birth: two parents read, one child written
@@ -440,7 +451,7 @@ def run_ours(args, rank, world):
             "peak_source": peak_src,
             "alg_bytes_per_step": alg_bytes / args.steps, "dominant_kernel": top,
             "pipeline_ms_per_step": round(pipeline_ms / args.steps, 4), "per_kernel": per_kernel,
-            "per_rank_busy_ms_per_step": [round(x, 4) for x in per_rank_busy],
+            "per_rank_busy_ms_per_step": [round(x, 4) for x in per_rank_busy], "per_rank": per_rank_kernels,
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}}
 
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
@@ -455,9 +466,11 @@ def run_ours(args, rank, world):
                        "migrations_per_step": migrated / args.steps},
             "clocks": clocks, "gpu_launches": launches, "checksum": checksum,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * int(begin[rank + 1] - begin[rank]) + 48,
-                    "what": "initializeStep + doActions per level + finalizeStep through the C ABI, then totals and the per-cell count "
-                            "array (ulong per cell, as PopBase::getNumAgentsArray; sharded: every rank its own cell range) copied into "
-                            "page-locked host memory every step"},
+                    "what": "initializeStep + doActions per level + finalizeStep through the C ABI; every step ends with the step's "
+                            "totals and the per-cell count array (ulong per cell, as PopBase::getNumAgentsArray; sharded: every rank "
+                            "its own cell range) in page-locked host memory (qhgb_mirror_num_agents_array: queued behind the step's "
+                            "kernels, one synchronisation), and the host reads them",
+                    "mirror_equals_readback": mirror_ok},
             "roofline": roof}
     g.close()
     if dist is not None:

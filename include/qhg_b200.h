@@ -158,6 +158,11 @@ int     qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out);
 /* the same for the cells [cell_begin, cell_end) only, out[0] = cell_begin's count: what a rank of a sharded run reads
  * back every step (its own cell range; the other cells are some other rank's and 0 here) */
 int     qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end, uint64_t *out);
+/* m_aiNumAgentsPerCell (core/SPopulation.cpp:236-247, updated by updateNumAgentsPerCell at the end of every step, :1250-1290) is
+ * a host array that is simply current whenever the host looks at it.  The same here: `host` (cell_end - cell_begin ulongs,
+ * best page-locked, qhgb_host_alloc) is refreshed by every step, event and upload under the synchronisation the call does
+ * anyway -- no second round trip for the counts.  A run of queued steps (qhgb_run) refreshes it once per window.  NULL ends it. */
+int     qhgb_mirror_num_agents_array(qhgb_pop *p, uint64_t *host, int32_t cell_begin, int32_t cell_end);
 /* OccTracker::calcBitMap (core/OccTracker.cpp:95-106, called per tracked cell by updateCounts :36-45 after every step): is any agent
  * of this population in cell cells[i]?  out[i] = 1 / 0.  n bytes cross the bus instead of the whole count array; a shard answers
  * for its own cells (the host ORs the ranks' answers). */

@@ -1087,20 +1087,20 @@ struct alignas(128) StagedAgents {
     float lastBirth[SCH];
     uint8_t dec[SCH];
 };
-template <int SCH>
+template <int SCH, int NST>
 struct alignas(128) WarpSmemS {
-    StagedAgents<SCH> win[SNST];
+    StagedAgents<SCH> win[NST];
     int64_t motherId[MAXMOTHERS];
     uint16_t mvJ[MVCAP];
-    unsigned long long bar[SNST];
+    unsigned long long bar[NST];
 };
-template <int SCH>
+template <int SCH, int NST>
 struct alignas(128) WarpSmemSG {  // populations with Genetics: the mothers' positions in the old buffer as well
-    StagedAgents<SCH> win[SNST];
+    StagedAgents<SCH> win[NST];
     int64_t motherId[MAXMOTHERS];
     int motherIdx[MAXMOTHERS];
     uint16_t mvJ[MVCAP];
-    unsigned long long bar[SNST];
+    unsigned long long bar[NST];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1134,7 +1134,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 constexpr int SCATTER_CTAS_DENSE = QHG_SCATTER_S_MINB, SCATTER_CTAS_SPARSE = 8;  // persistent grids: this many CTAs per SM
 // GEN = true: the population has Genetics -- the genome handle and m_iNumBabies follow the agent (read straight from global
 // memory, like the optional age), every newborn leaves a birth record (baby position, mother, father) for k_make_offspring
-template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE>
+// SG = cells per grab of the work counter: their agents are ONE contiguous range of every array, streamed through NST windows
+// of SCH agents -- the copies of the next window run while this one is consumed, and only the first window of a grab is waited
+// for with nothing else in flight (with 4-cell grabs that was every window at 20 agents per cell and every second one at 150)
+template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE, int SG = CELL_BATCH, int NST = SNST>
 __global__ void __launch_bounds__(CW * 32, MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
@@ -1142,8 +1145,8 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H,
                const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
                uint8_t *decMark = nullptr, int shrink = 0) {
-    static_assert(CELL_BATCH * MAXN <= 32, "one lane per (cell of the batch, direction)");
-    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH>, WarpSmemS<SCH>>::type;
+    static_assert(SG + 1 <= 32, "one lane per cell start of the grab");
+    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST>, WarpSmemS<SCH, NST>>::type;
     __shared__ WSS smem[CW];
     if (st->overflow || st->oversize || st->halt) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1155,7 +1158,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
     const long long birthOffset = H.p2p ? st->birthOffset : H.birthOffset;
     int nSentL = 0;
     if (lane == 0) {
-        for (int k = 0; k < SNST; k++) mbar_init(&S.bar[k], 1);
+        for (int k = 0; k < NST; k++) mbar_init(&S.bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1165,17 +1168,16 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
     int lastEnd = cLo;
     for (;;) {
         // (short ranges -- the shards of a many-GPU run -- get grabs that shrink towards the end: no tail of a whole batch)
-        const int g = shrink ? max(1, min(CELL_BATCH, (cHi - lastEnd) / (2 * nWarpsS))) : CELL_BATCH;
+        const int g = shrink ? max(1, min(SG, (cHi - lastEnd) / (2 * nWarpsS))) : SG;
         int cBase = 0;
         if (lane == 0) cBase = cLo + atomicAdd(&st->workScatter, g);
         cBase = __shfl_sync(FULL, cBase, 0);
         if (cBase >= cHi) break;
         lastEnd = cBase + g;
         const int cEnd = min(cBase + g, cHi);
-        // lane l keeps the numbers of cell cBase+l (lane CELL_BATCH-or-less: the end of the batch)
-        int csL = 0, nsL = 0, arL = 0, bbL = 0, nbL = -1;
+        // lane l keeps the numbers of cell cBase+l (lane SG-or-less: the end of the grab)
+        int csL = 0, nsL = 0, arL = 0, bbL = 0;
         if (cBase + lane <= cEnd) csL = cellStart[cBase + lane];
-        if (cBase + lane / MAXN < cEnd && lane < CELL_BATCH * MAXN) nbL = nbr[(size_t)cBase * MAXN + lane];  // lane = cell*MAXN + direction
         if (cBase + lane < cEnd) { nsL = newStart[cBase + lane]; arL = arrive[cBase + lane]; bbL = birthBase[cBase + lane]; }
         const int gs = __shfl_sync(FULL, csL, 0), ge = __shfl_sync(FULL, csL, cEnd - cBase);
         if (ge == gs) continue;
@@ -1184,15 +1186,15 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         auto issue = [&](int k) {  // lane 0: start the copies of window k
             const int w0 = g0 + k * SCH;
             const int cnt = min(SCH, (ge - w0 + 15) & ~15);
-            StagedAgents<SCH> &W = S.win[k % SNST];
-            unsigned long long *bar = &S.bar[k % SNST];
+            StagedAgents<SCH> &W = S.win[k % NST];
+            unsigned long long *bar = &S.bar[k % NST];
             mbar_expect_tx(bar, (uint32_t)cnt * 17u);
             bulk_g2s(W.id, a.id + w0, (uint32_t)cnt * 8u, bar);
             bulk_g2s(W.birth, a.birth + w0, (uint32_t)cnt * 4u, bar);
             bulk_g2s(W.lastBirth, a.lastBirth + w0, (uint32_t)cnt * 4u, bar);
             bulk_g2s(W.dec, dec + w0, (uint32_t)cnt, bar);
         };
-        if (lane == 0) for (int k = 0; k < min(nWin, SNST); k++) issue(k);
+        if (lane == 0) for (int k = 0; k < min(nWin, NST); k++) issue(k);
 
         int ci = 0;  // cell of the batch the walk is in
         int s = gs, e = __shfl_sync(FULL, csL, 1);
@@ -1200,11 +1202,15 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         int ns = 0, stayBase = 0, nMothers = 0, nmv = 0;
         // lane k < MAXN: where the movers of this cell towards neighbour k go.  The three loads are issued when the
         // cell begins and first used when its movers are flushed.
+        // (the neighbours of the cell after this one are fetched a cell ahead: land cells come in runs)
         int dirCell = -1, dirA = 0, dirB = 0, dirC = 0, dirOff = 0;
+        int dPre = -1, dPreCi = -1;
         auto begin_cell = [&]() {
             ns = __shfl_sync(FULL, nsL, ci);
             stayBase = 0; nMothers = 0;
-            const int d = __shfl_sync(FULL, nbL, min(ci * MAXN + lane, 31));
+            int d = dPre;
+            if (dPreCi != ci) d = (lane < MAXN) ? nbr[(size_t)(cBase + ci) * MAXN + lane] : -1;
+            if (cBase + ci + 1 < cEnd) { dPre = (lane < MAXN) ? nbr[(size_t)(cBase + ci + 1) * MAXN + lane] : -1; dPreCi = ci + 1; }
             dirCell = -1; dirA = 0; dirB = 0; dirC = 0; dirOff = 0;
             if (lane < MAXN && d >= 0) {
                 dirCell = d;
@@ -1218,9 +1224,9 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         begin_cell();
         for (int k = 0; k < nWin; k++) {
             const int w0 = g0 + k * SCH, w1 = min(w0 + SCH, ge);
-            const StagedAgents<SCH> &W = S.win[k % SNST];
-            mbar_wait(&S.bar[k % SNST], (phase >> (k % SNST)) & 1u);
-            phase ^= 1u << (k % SNST);
+            const StagedAgents<SCH> &W = S.win[k % NST];
+            mbar_wait(&S.bar[k % NST], (phase >> (k % NST)) & 1u);
+            phase ^= 1u << (k % NST);
             auto flush_movers = [&]() {  // the queued movers of cell cBase+ci; their records are in this window
                 __syncwarp();
                 for (int q0 = 0; q0 < nmv; q0 += 32) {
@@ -1340,7 +1346,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                 if (ci < cEnd - cBase) begin_cell();
             }
             __syncwarp();  // every lane is done with the window: it can be overwritten
-            if (lane == 0 && k + SNST < nWin) issue(k + SNST);
+            if (lane == 0 && k + NST < nWin) issue(k + NST);
         }
     }
     if (H.on) {

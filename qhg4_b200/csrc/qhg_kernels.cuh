@@ -789,8 +789,8 @@ __device__ __forceinline__ void step_end_body(DevStats *st, int advanceStep, lon
 __global__ void k_step_end(DevStats *st, int advanceStep, long long globalBirths) { step_end_body(st, advanceStep, globalBirths); }
 
 // PopBase::getNumAgentsArray hands out ulong counts (core/SPopulation.h); a shard reports 0 for the cells of other ranks
-__global__ void k_counts_u64(int nCells, int cLo, int cHi, const int *__restrict__ count, unsigned long long *__restrict__ out) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x)
+__global__ void k_counts_u64(int cBegin, int cEnd, int cLo, int cHi, const int *__restrict__ count, unsigned long long *__restrict__ out) {
+    for (int c = cBegin + blockIdx.x * blockDim.x + threadIdx.x; c < cEnd; c += gridDim.x * blockDim.x)
         out[c] = (c >= cLo && c < cHi) ? (unsigned long long)count[c] : 0ull;
 }
 

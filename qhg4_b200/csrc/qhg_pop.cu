@@ -191,6 +191,11 @@ struct qhgb_pop {
     // grid / env
     DevBuf<int> nbr, gid, count[2], cellStart[2], stay, arrive, cursor, birthCount, birthBase, nFert;
     DevBuf<unsigned long long> count64;  // per-cell counts widened for qhgb_get_num_agents_array
+    uint64_t *mirror = nullptr;          // host array kept current after every step (qhgb_mirror_num_agents_array), cells [mirrorLo, mirrorHi)
+    int mirrorLo = 0, mirrorHi = 0;
+    cudaStream_t copyStream = nullptr;   // the mirror's copy runs beside the scatter pass: the counts are final after the scan
+    cudaEvent_t evScan = nullptr, evCopy = nullptr;
+    bool mirrorQueued = false;
     DevBuf<int> occCells;                // qhgb_get_occupied: the tracked cells and their answer
     DevBuf<uint8_t> occOut;
     DevBuf<int> moveBase;  // fast path: first arrival slot of the movers of (cell, direction), MOVE_STRIDE ints per cell
@@ -454,6 +459,24 @@ int pushStats(qhgb_pop *p) {
     CK(cudaMemcpyAsync(p->dstats.p, &s, sizeof(s), cudaMemcpyHostToDevice, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
+}
+
+void enqueueMirror(qhgb_pop *p, int buf) {
+    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->mirrorHi - p->mirrorLo), 256, p->mirrorLo, p->mirrorHi, p->cLo(), p->cHi(), p->count[buf].p,
+           p->count64.p);
+    cudaMemcpyAsync(p->mirror, p->count64.p + p->mirrorLo, sizeof(uint64_t) * (size_t)(p->mirrorHi - p->mirrorLo), cudaMemcpyDeviceToHost, p->stream);
+}
+
+// inside a step: the next counts are final once the scan has run (every arrival, birth and death is decided in pass 1), so the
+// host's copy is made on a second stream WHILE pass 2 moves the agents; the step's stream waits for it before the host does
+void mirrorAfterScan(qhgb_pop *p, int buf) {
+    cudaEventRecord(p->evScan, p->stream);
+    cudaStreamWaitEvent(p->copyStream, p->evScan, 0);
+    k_counts_u64<<<p->gridFor(p->mirrorHi - p->mirrorLo), 256, 0, p->copyStream>>>(p->mirrorLo, p->mirrorHi, p->cLo(), p->cHi(), p->count[buf].p, p->count64.p);
+    p->launches++;
+    cudaMemcpyAsync(p->mirror, p->count64.p + p->mirrorLo, sizeof(uint64_t) * (size_t)(p->mirrorHi - p->mirrorLo), cudaMemcpyDeviceToHost, p->copyStream);
+    cudaEventRecord(p->evCopy, p->copyStream);
+    p->mirrorQueued = true;
 }
 
 int pullStats(qhgb_pop *p) {
@@ -885,6 +908,19 @@ int commFailure(qhgb_pop *p) {
     return fail("receive buffer too small for the migrants of one step (%d > %d)", nRecv, q.recvCap);
 }
 
+// pass 2 comes in several compiled shapes: (agents per window, CTAs per SM, cells per grab, window stages)
+#define QHG_SCATTER_VARIANTS(X) \
+    X(384, 6, 4, 1) X(256, 8, 4, 1) X(384, 6, 2, 1) X(384, 6, 8, 1) X(384, 6, 16, 1) X(192, 6, 4, 2) X(192, 6, 8, 2) \
+    X(256, 8, 8, 1) X(256, 8, 12, 1) X(256, 8, 16, 1) X(256, 8, 24, 1) X(256, 8, 30, 1) X(128, 8, 16, 2)
+struct ScatterVariant { int sch, minb, sg, nst; };
+ScatterVariant scatterVariant(bool sparse) {
+    // (the environment is looked at on every call: an A/B run switches between the variants from one step to the next)
+    const char *e = getenv(sparse ? "QHG_SCATTER_SPARSE" : "QHG_SCATTER_DENSE");
+    ScatterVariant t{};
+    if (e && sscanf(e, "%d,%d,%d,%d", &t.sch, &t.minb, &t.sg, &t.nst) == 4) return t;
+    return sparse ? ScatterVariant{256, 8, 16, 1} : ScatterVariant{384, 6, 4, 1};  // measured: profiles/ab_scatter_r02.txt
+}
+
 // does a warp of k_seg_decide take 8 cells per grab (fewer than QHG_SEG_DENSE = 64 agents per cell on average) or 4?
 bool segSparse(qhgb_pop *p) {
     static int dense = 0;
@@ -1045,24 +1081,36 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 q.lastReceived = nRecv;
             }
             launchScan(p);
-            // pass 2: 384-agent windows and 6 CTAs per SM for dense populations, 256 and 8 for sparse ones
+            if (q.mirror && !defer) mirrorAfterScan(p, q.cur ^ 1);
+            // pass 2: windows of 384 agents, 6 CTAs per SM and 4 cells per grab for dense populations; 256, 8 and 16 for sparse ones
 #define QHG_SCATTER_ARGS q.dstats.p, a, o, q.cLo(), q.cHi(), q.cellStart[q.cur].p, q.dec.p, q.nbr.p, q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, \
                          q.moveBase.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, H
-            const bool sparseS = segSparse(p);
-            if (q.genetic) {
-                if (sparseS) LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32,
-                                    QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkGrabs);
-                else LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32,
-                            QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkGrabs);
-                if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
-                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
-            } else {
-                if (sparseS) LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_SPARSE, SCATTER_CTAS_SPARSE>), q.numSMs * SCATTER_CTAS_SPARSE, CW * 32, QHG_SCATTER_ARGS,
-                                    (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkGrabs);
-                else LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_DENSE, SCATTER_CTAS_DENSE>), q.numSMs * SCATTER_CTAS_DENSE, CW * 32, QHG_SCATTER_ARGS,
-                            (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkGrabs);
-                if (useNav) LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
-                                   q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
+            // (window size, CTAs per SM, cells per grab, stages): by density, QHG_SCATTER_DENSE / QHG_SCATTER_SPARSE choose another
+            // of the compiled variants (A/B runs)
+            const ScatterVariant sv = scatterVariant(segSparse(p));
+            bool launchedS = false;
+#define QHG_SCATTER_CASE(SCH_, MINB_, SG_, NST_)                                                                                            \
+    if (!launchedS && sv.sch == SCH_ && sv.minb == MINB_ && sv.sg == SG_ && sv.nst == NST_) {                                              \
+        launchedS = true;                                                                                                               \
+        if (q.genetic)                                                                                                                  \
+            LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,  \
+                   q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkS);                                                                 \
+        else                                                                                                                            \
+            LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,         \
+                   (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkS);                      \
+    }
+            {
+                // grabs that shrink towards the end of the range: whenever a warp gets fewer than about 24 full grabs
+                const int shrinkS = (shrinkGrabs || (int64_t)(q.cHi() - q.cLo()) < (int64_t)24 * sv.sg * q.numSMs * sv.minb * CW) ? 1 : 0;
+                QHG_SCATTER_VARIANTS(QHG_SCATTER_CASE)
+            }
+#undef QHG_SCATTER_CASE
+            if (!launchedS) return fail("no scatter kernel compiled for windows of %d agents, %d CTAs per SM, %d cells per grab, %d stages", sv.sch, sv.minb, sv.sg, sv.nst);
+            if (useNav) {
+                if (q.genetic) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
+                                      q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
+                else LAUNCH(p, "k_place_jumpers", k_place_jumpers<false>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
+                            q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
             }
 #undef QHG_SCATTER_ARGS
             const int rowW = q.genetic ? 2 * q.gp.nBlocks : 0;
@@ -1123,6 +1171,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, cellEnv(p), q.arrive.p, q.birthCount.p,
                    q.dest.p, q.rank.p, q.oflags.p);
             launchScan(p);
+            if (q.mirror && !defer) mirrorAfterScan(p, q.cur ^ 1);
             LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
                    q.cellStart[q.cur ^ 1].p, q.stay.p, q.arrive.p, q.birthBase.p, P.t, P.storeAge, P.selfMate, q.key, q.mate.p,
                    q.genetic ? q.births.p : nullptr, q.gctl.p);
@@ -1143,6 +1192,13 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             q.pairingValid = false;
             return 0;
         }
+        // the host's copy of the per-cell counts (m_aiNumAgentsPerCell is current after every step in the reference): queued
+        // behind the step, it arrives under the same synchronisation as the step's totals
+        if (q.mirror) {
+            if (q.mirrorQueued) cudaStreamWaitEvent(q.stream, q.evCopy, 0);
+            else enqueueMirror(p, q.cur ^ 1);
+            q.mirrorQueued = false;
+        }
         if (pullStats(p) != 0) return -1;
         if (q.hstats->commError) return commFailure(p);
         if (tiled && q.sharded && q.p2p) { q.lastSent = q.hstats->nSent; q.lastReceived = q.hstats->nRecv; }
@@ -1159,6 +1215,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     }
     if (q.hstats->overflow) {
         LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);  // the step did not happen; the population is as it was
+        if (q.mirror) { enqueueMirror(p, q.cur); cudaStreamSynchronize(q.stream); }
         return fail("agent buffers overflowed (capacity %lld, needed %d)", (long long)q.capacity, q.hstats->nNew);
     }
     q.cur ^= 1;
@@ -1296,6 +1353,9 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
     CK(cudaGetDeviceProperties(&prop, device));
     p->numSMs = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->copyStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->evScan, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->evCopy, cudaEventDisableTiming));
     {
         const char *e = getenv("QHG_B200_PATH");  // "generic" forces the one-thread-per-agent path (testing)
         // populations with Genetics take the fast path too (k_cell_decide<false, true> finds the fathers, k_cell_scatter<true>
@@ -1389,6 +1449,9 @@ int qhgb_destroy(qhgb_pop *p) {
     p->sendBuf.release(); p->recvBuf.release();
     for (auto &e : p->userEv) if (e) cudaEventDestroy(e);
     if (p->hstats) cudaFreeHost(p->hstats);
+    if (p->evScan) cudaEventDestroy(p->evScan);
+    if (p->evCopy) cudaEventDestroy(p->evCopy);
+    if (p->copyStream) cudaStreamDestroy(p->copyStream);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return 0;
@@ -1815,6 +1878,7 @@ int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
         int w = 0;
         for (; w < W && rc == 0; w++) rc = stepImpl(p, t0 + k + w, true);
         const int hostErr = rc;
+        if (q.mirror) enqueueMirror(p, q.cur);  // the host's copy of the per-cell counts: once per window of queued steps
         if (pullStats(p) != 0) return -1;
         if (q.hstats->commError) return commFailure(p);
         const int ok = (int)(q.hstats->step - (unsigned)steps0);  // steps of this window the device completed
@@ -1917,7 +1981,7 @@ int qhgb_get_num_agents_array(qhgb_pop *p, uint64_t *out) {
     CK(cudaSetDevice(p->device));
     // widened to the reference's ulong on the device (cells of other ranks: 0), then one copy into the caller's array --
     // a single DMA when that array is page-locked (qhgb_host_alloc)
-    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
+    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, 0, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
     CK(cudaMemcpyAsync(out, p->count64.p, sizeof(uint64_t) * (size_t)p->nCells, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
@@ -1929,8 +1993,20 @@ int qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_end,
     if (cell_begin < 0 || cell_end > p->nCells || cell_begin > cell_end) return fail("qhgb_get_num_agents_range: [%d, %d) is not inside [0, %d)", cell_begin, cell_end, p->nCells);
     if (cell_begin == cell_end) return 0;
     CK(cudaSetDevice(p->device));
-    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(p->nCells), 256, p->nCells, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
+    LAUNCH(p, "k_counts_u64", k_counts_u64, p->gridFor(cell_end - cell_begin), 256, cell_begin, cell_end, p->cLo(), p->cHi(), p->count[p->cur].p, p->count64.p);
     CK(cudaMemcpyAsync(out, p->count64.p + cell_begin, sizeof(uint64_t) * (size_t)(cell_end - cell_begin), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_mirror_num_agents_array(qhgb_pop *p, uint64_t *host, int32_t cell_begin, int32_t cell_end) {
+    if (!p) return fail("qhgb_mirror_num_agents_array: NULL population");
+    if (!host) { p->mirror = nullptr; return 0; }
+    if (!p->haveCells) return fail("qhgb_mirror_num_agents_array: call qhgb_set_cells first");
+    if (cell_begin < 0 || cell_end > p->nCells || cell_begin >= cell_end) return fail("qhgb_mirror_num_agents_array: [%d, %d) is not inside [0, %d)", cell_begin, cell_end, p->nCells);
+    CK(cudaSetDevice(p->device));
+    p->mirror = host; p->mirrorLo = cell_begin; p->mirrorHi = cell_end;
+    enqueueMirror(p, p->cur);
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }

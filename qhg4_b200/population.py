@@ -178,6 +178,19 @@ class GpuPopulation:
         check(self.L.qhgb_get_num_agents_range(self.h, int(c0), int(c1), _p(out)), "qhgb_get_num_agents_range")
         return out
 
+    def mirror_counts(self, host=None, c0: int = 0, c1: int = None):
+        """keep `host` (ulong per cell of [c0, c1)) current after every step, the way m_aiNumAgentsPerCell is in the reference;
+        None ends it"""
+        if host is None:
+            check(self.L.qhgb_mirror_num_agents_array(self.h, None, 0, 0), "qhgb_mirror_num_agents_array")
+            self._mirror = None
+            return None
+        c1 = self.ncells if c1 is None else c1
+        assert host.dtype == np.uint64 and len(host) >= c1 - c0
+        check(self.L.qhgb_mirror_num_agents_array(self.h, _p(host), int(c0), int(c1)), "qhgb_mirror_num_agents_array")
+        self._mirror = host  # keeps the array alive
+        return host
+
     def occupied(self, cells):
         """OccTracker::calcBitMap for this population: one byte per listed cell, 1 = somebody is there"""
         c = np.ascontiguousarray(cells, np.int32)

@@ -249,14 +249,42 @@ def test_dense_and_sparse_cells_mix():
 def test_occupancy_of_tracked_cells(small_world):
     """qhgb_get_occupied = OccTracker::calcBitMap for one population (core/OccTracker.cpp:95-106): one byte per tracked cell,
     equal to (count > 0) of the per-cell counts, which are bit-exact against the reference (test_deterministic_substeps)."""
-    nbr, alt, pop, par = small_world
-    g, o = make_pair(par, nbr, alt, pop)
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(6000, alt, seed=8)   # sparse: a good part of the tracked cells is empty
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=3)
     cells = np.random.default_rng(1).choice(len(nbr), 500, replace=False).astype(np.int32)
     for k in range(4):
         g.step(float(k)); o.step(float(k))
         assert np.array_equal(g.occupied(cells), (o.counts()[cells] > 0).astype(np.uint8)), k
     with pytest.raises(Exception):
         g.occupied(np.array([len(nbr)], np.int32))
+
+
+def test_count_mirror_is_current_after_every_step(small_world):
+    """qhgb_mirror_num_agents_array: the host array is what qhgb_get_num_agents_array would return after every step, event and
+    window of queued steps (m_aiNumAgentsPerCell of the reference is always current: core/SPopulation.cpp:1250-1290)"""
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(30000, alt, seed=6)
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=2)
+    lo, hi = 100, 2000
+    m = g.mirror_counts(g.host_array(hi - lo, np.uint64), lo, hi)
+    assert np.array_equal(m, o.counts()[lo:hi])
+    for k in range(5):
+        g.step(float(k)); o.step(float(k))
+        assert np.array_equal(m, o.counts()[lo:hi]), k
+    alt2 = alt.copy(); alt2[::3] = -5.0
+    g.set_env("Altitude", alt2); o.set_env("Altitude", alt2)
+    g.update_event(2, 5.0); g.flush_events(5.0)         # GEO: agents on the new sea cells drown
+    o.update_event(2, 5.0)
+    assert np.array_equal(m, o.counts()[lo:hi])
+    g.run(5.0, 6)
+    for k in range(6):
+        o.step(5.0 + k)
+    assert np.array_equal(m, o.counts()[lo:hi])
+    g.mirror_counts(None)
+    g.step(11.0); o.step(11.0)
+    assert not np.array_equal(m, o.counts()[lo:hi])     # no longer refreshed
+    assert_same_population(g, o, 11)
 
 
 def test_empty_population_and_late_agents(small_world):
