@@ -163,6 +163,9 @@ int     qhgb_get_num_agents_range(qhgb_pop *p, int32_t cell_begin, int32_t cell_
  * best page-locked, qhgb_host_alloc) is refreshed by every step, event and upload under the synchronisation the call does
  * anyway -- no second round trip for the counts.  A run of queued steps (qhgb_run) refreshes it once per window.  NULL ends it. */
 int     qhgb_mirror_num_agents_array(qhgb_pop *p, uint64_t *host, int32_t cell_begin, int32_t cell_end);
+/* MoveStats' per-cell arrays, the datasets "Hops", "Dist", "Time" it writes into the species' action group
+ * (actions/MoveStats.cpp:363-384 writeAdditionalDataQDF; m_aiHops int, m_adDist / m_adTime double, -1 = never reached) */
+int     qhgb_get_move_stats(qhgb_pop *p, int32_t *hops, double *dist, double *time);
 /* OccTracker::calcBitMap (core/OccTracker.cpp:95-106, called per tracked cell by updateCounts :36-45 after every step): is any agent
  * of this population in cell cells[i]?  out[i] = 1 / 0.  n bytes cross the bus instead of the whole count array; a shard answers
  * for its own cells (the host ORs the ranks' answers). */

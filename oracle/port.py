@@ -60,6 +60,7 @@ def lib():
         L.qor_get_birth_death_probs.argtypes = [vp, vp, vp]
         L.qor_atan_death_prob.argtypes = [vp, i32, vp, vp]
         L.qor_get_capacities.argtypes = [vp, vp]
+        L.qor_get_move_stats.argtypes = [vp, vp, vp, vp]
         L.qor_set_navigation.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
         L.qor_set_genomes.argtypes = [vp, i64, vp]
         L.qor_get_genomes.restype = i64
@@ -188,6 +189,12 @@ class OraclePop:
         out = np.zeros(self.ncells)
         assert lib().qor_get_capacities(self.h, _p(out)) == 0
         return out
+
+    def move_stats(self):
+        """MoveStats' per-cell arrays (hops, dist, time)"""
+        h, d, t = np.zeros(self.ncells, np.int32), np.zeros(self.ncells), np.zeros(self.ncells)
+        assert lib().qor_get_move_stats(self.h, _p(h), _p(d), _p(t)) == 0
+        return h, d, t
 
     def set_navigation(self, port_cell, port_ptr, dest_cell, dist, bridges=()):
         pc, pp = np.ascontiguousarray(port_cell, np.int32), np.ascontiguousarray(port_ptr, np.int32)

@@ -18,6 +18,7 @@
 #include <memory>
 #include <numbers>
 #include <queue>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -326,7 +327,8 @@ struct Agent {  // core/SPopulation.h:43-50 + populations/tut_EnvironAltPop.h:16
 };
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST, A_OLDAGEDEATH,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH};
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH,
+               A_CONDWEIGHTEDMOVE, A_RANDPERMPAIR, A_MOVESTATS};
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -366,6 +368,15 @@ struct qor_pop {
     double randMoveProb = 0;  // RandomMove_prob (actions/RandomMove.cpp)
     double moveRandProb = 0;  // WeightedMoveRand_prob (actions/WeightedMoveRand.cpp)
     double sigMaxAge = 0, sigRange = 0, sigSlope = 0, sigScale = 0;  // SigDeath (actions/SigDeath.cpp)
+    // CondWeightedMove (actions/CondWeightedMove.cpp) with a SimpleCondition over the altitudes (actions/SimpleCondition.cpp):
+    // the mode is a constructor argument in the reference; the probe classes carry it in their name (tut_EnvironAltCond<m>Pop)
+    double condMoveProb = 0;
+    int condMode = 0;
+    // MoveStats (actions/MoveStats.cpp): per cell, hops / distance / time of the arrival that counts under MoveStats_Mode
+    // (0 first, 1 minimum, 2 last); the Temp arrays are the per-thread arrays of the reference (one thread), never reset
+    int msMode = -1;
+    std::vector<int> msHops, msHopsTemp;
+    std::vector<double> msDist, msTime, msDistTemp, msTimeTemp;
     // ConfinedMove (actions/ConfinedMove.cpp): centre (lon, lat in degrees) and radius (km) of the region agents may enter
     double confX = 0, confY = 0, confR = 0;
     std::vector<uint8_t> confAllowed;
@@ -697,6 +708,110 @@ struct qor_pop {
         }
     }
 
+    // actions/SimpleCondition.cpp:12-19,73-77: the candidate's value enters scaled by 0.2 (and "less" also asks for < 10)
+    bool condAllow(int cur, int to) {
+        const std::vector<double> &ref = env["Altitude"];
+        const double c = ref[cur], n = 0.2 * ref[to];
+        switch (condMode) {
+        case 1: return true;
+        case 2: return n > c;
+        case 3: return (n < 10) && (n < c);
+        case 4: return n == c;
+        case 5: return n >= c;
+        case 6: return n <= c;
+        case 7: return n != c;
+        default: return false;
+        }
+    }
+
+    // actions/RandPermPair.cpp:67-83 (initialize) and :99-178 (findMates), :187-196 (permute): the fertile agents of a cell in
+    // slot order; the larger sex is shuffled (a partial Fisher-Yates over its first min(nF, nM) places), equal places mate.
+    // Counter mode: a uniformly random injection of the smaller sex into the larger one is exactly what the rank-by-key
+    // pairing of RandomPair produces there -- the two actions share the law, so they share the code.
+    void randPermPairInit() {
+        if (mode != QOR_MODE_WELL) { randomPairInit(); return; }
+        for (int i = 0; i < hi(); i++) slots[i].mate = -3;
+        std::vector<std::vector<int>> F(nCells), M(nCells);
+        for (int i = 0; i < hi(); i++) {
+            if (!active[i]) continue;
+            const Agent &a = slots[i];
+            if (a.life > 0 && a.life == LIFE_FERTILE) {
+                if (a.gender == 0) F[a.cell].push_back(i);
+                else if (a.gender == 1) M[a.cell].push_back(i);
+            }
+        }
+        auto permute = [&](std::vector<int> &v, int nSel) {
+            for (int i = 0; i < nSel; i++) {
+                const int k = (int)u2int(well.next(), i, (int)v.size());
+                std::swap(v[k], v[i]);
+            }
+        };
+        for (int c = 0; c < nCells; c++) {
+            if (counts[c] <= 1) continue;
+            const int nf = (int)F[c].size(), nm = (int)M[c].size();
+            if (nf == 0 || nm == 0) continue;
+            int np;
+            if (nf <= nm) { np = nf; permute(M[c], nf); }
+            else { np = nm; permute(F[c], nm); }
+            for (int k = 0; k < np; k++) { slots[F[c][k]].mate = M[c][k]; slots[M[c][k]].mate = F[c][k]; }
+        }
+    }
+
+    // great-circle distance as MoveStats computes it: utils/geomutils.cpp:309-333 with the radius of the Geography
+    double msDistance(int from, int to) {
+        const std::vector<double> &lon = env["Longitude"], &lat = env["Latitude"];
+        const double Q_PI = 3.14159265358979323846;  // (x * Q_PI) / 180 as spherdistDeg writes it: the rounding differs from x * (Q_PI / 180)
+        const double lo1 = lon[from] * Q_PI / 180, la1 = lat[from] * Q_PI / 180, lo2 = lon[to] * Q_PI / 180, la2 = lat[to] * Q_PI / 180;
+        const double x1 = cos(lo1) * cos(la1), y1 = sin(lo1) * cos(la1), z1 = sin(la1);
+        const double x2 = cos(lo2) * cos(la2), y2 = sin(lo2) * cos(la2), z2 = sin(la2);
+        double pr = x1 * x2 + y1 * y2 + z1 * z2;
+        if (pr > 1) pr = 1; else if (pr < -1) pr = -1;
+        return 6371.3 * acos(pr);
+    }
+    // actions/MoveStats.cpp:107-143 (preLoop) and :148-186 (initializeOccupied: every slot between the first and the last agent)
+    void moveStatsPreLoop() {
+        msHops.assign(nCells, -1); msDist.assign(nCells, -1.0); msTime.assign(nCells, -1.0);
+        msHopsTemp.assign(nCells, -1); msDistTemp.assign(nCells, -1.0); msTimeTemp.assign(nCells, -1.0);
+        for (int i = 0; i < hi(); i++) {
+            if (!active[i]) continue;
+            const int c = slots[i].cell;
+            msHops[c] = 0; msDist[c] = 0; msTime[c] = 0;
+        }
+    }
+    // actions/MoveStats.cpp:195-285 (finalize, one thread): the move list is still complete -- ConfinedMove may already have turned
+    // some of its entries around, depending on the order of the two in the Prioritizer.  WELL mode follows the list; counter
+    // mode does not know an order of the agents: "first" is the move of the agent with the smallest id, "last" the largest.
+    void moveStatsFinalize(float t) {
+        std::vector<size_t> ord(moveList.size() / 3);
+        for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
+        if (mode != QOR_MODE_WELL)
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return slots[moveList[3 * x + 1]].id < slots[moveList[3 * y + 1]].id; });
+        std::set<int> changed;
+        for (size_t k : ord) {
+            const int from = moveList[3 * k], to = moveList[3 * k + 2];
+            const int newHops = msHops[from] + 1;
+            const double newDist = msDist[from] + msDistance(from, to), newTime = t;
+            if (msHopsTemp[to] < 0 || msMode == 2) {
+                msHopsTemp[to] = newHops; msDistTemp[to] = newDist; msTimeTemp[to] = newTime;
+                changed.insert(to);
+            } else if (msMode == 1) {
+                if (newHops < msHopsTemp[to]) msHopsTemp[to] = newHops;
+                if (newDist < msDistTemp[to]) msDistTemp[to] = newDist;
+                msTimeTemp[to] = newTime;
+                changed.insert(to);
+            }
+        }
+        for (int c : changed) {
+            if (msHops[c] < 0 || msMode == 2) {
+                msHops[c] = msHopsTemp[c]; msDist[c] = msDistTemp[c]; msTime[c] = msTimeTemp[c];
+            } else if (msMode == 1) {
+                if (msHopsTemp[c] < msHops[c]) msHops[c] = msHopsTemp[c];
+                if (msDistTemp[c] < msDist[c]) msDist[c] = msDistTemp[c];
+                if (msTimeTemp[c] < msTime[c]) msTime[c] = msTimeTemp[c];
+            }
+        }
+    }
+
     // ---- execute() of each action -------------------------------------------------------------
     void execute(const Action &act, int i, float t) {
         Agent &a = slots[i];
@@ -789,6 +904,25 @@ struct qor_pop {
             }
             break;
         }
+        case A_CONDWEIGHTEDMOVE: {  // actions/CondWeightedMove.cpp:41-86: no special case for equal weights, the row is read
+            // up to the grid's connectivity, the ice test looks at the cell the agent is IN, the condition decides last
+            if (a.life > 0) {
+                double r = u2d(draw(a.id, STREAM_ACT0, L0_MOVE));
+                if (r < condMoveProb) {
+                    int c = a.cell;
+                    size_t off = (size_t)c * (maxNeigh + 1);
+                    int pick = -1;
+                    double r2 = u2d(draw(a.id, STREAM_ACT1, L1_MOVE2)) * W[off + maxNeigh];
+                    for (int k = 0; k < maxNeigh + 1; k++) if (r2 < W[off + k]) { pick = k; break; }
+                    if (pick > 0) {
+                        int to = nbr[(size_t)c * maxNeigh + pick - 1];
+                        bool iced = env.count("Ice") && env["Ice"][c] != 0;
+                        if (to >= 0 && !iced && condAllow(c, to)) registerMove(c, i, to);
+                    }
+                }
+            }
+            break;
+        }
         case A_SIGDEATH: {  // actions/SigDeath.cpp:66-90: p = scale / (1 + exp(-slope * (age - maxAge))), one draw per agent
             if (a.life > 0) {
                 a.age = t - a.birth;
@@ -862,6 +996,8 @@ struct qor_pop {
         case A_NPPCAP:
         case A_GENETICS:
         case A_RANDOMPAIR:
+        case A_RANDPERMPAIR:
+        case A_MOVESTATS:
         case A_CONFINEDMOVE:
             break;  // execute() is empty for these (actions/Action.h:36 default)
         }
@@ -890,6 +1026,7 @@ struct qor_pop {
             case A_VERHULSTVARK: verhulstVarKInit(); break;
             case A_MULTIEVAL: multiEvalInit(); break;
             case A_RANDOMPAIR: randomPairInit(); break;
+            case A_RANDPERMPAIR: randPermPairInit(); break;
             case A_SINGLEEVAL: evaluatorInit(); break;
             default: break;
             }
@@ -1042,6 +1179,7 @@ struct qor_pop {
             // region is turned into a move to the cell it starts from (it stays in the list and is counted)
             if (a->enabled && a->kind == A_CONFINEDMOVE)
                 for (size_t k = 0; k < moveList.size(); k += 3) if (!confAllowed[moveList[k + 2]]) moveList[k + 2] = moveList[k];
+            if (a->enabled && a->kind == A_MOVESTATS) moveStatsFinalize(curTime);
         }
         recycleDeadSpace();
         performMoves();
@@ -1132,6 +1270,15 @@ qor_pop *qor_create(const char *pop_class, int n_cells, int max_neigh, int mode)
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"WeightedMoveRand", A_WEIGHTEDMOVERAND}, {"SigDeath", A_SIGDEATH}};
+    } else if (p->popClass.size() == 22 && p->popClass.rfind("tut_EnvironAltCond", 0) == 0 && p->popClass.substr(19) == "Pop" &&
+               p->popClass[18] >= '0' && p->popClass[18] <= '7') {
+        // probe classes tut_EnvironAltCond<m>Pop: tut_EnvironAltPop with CondWeightedMove (a SimpleCondition of mode m over the
+        // altitudes), RandPermPair and MoveStats added (ExtProbePop<m> in oracle/ref_driver.cpp); the <prio> entries decide which
+        // of WeightedMove / CondWeightedMove and RandomPair / RandPermPair run
+        p->condMode = p->popClass[18] - '0';
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"CondWeightedMove", A_CONDWEIGHTEDMOVE}, {"RandPermPair", A_RANDPERMPAIR}, {"MoveStats", A_MOVESTATS}};
     } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
         // probe classes: tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added and called from
         // makePopSpecificOffspring (GenProbePop<U> in oracle/ref_driver.cpp) -- pin the Genetics action with 1- and 2-bit nucleotides
@@ -1252,6 +1399,8 @@ int qor_set_attribute(qor_pop *p, const char *name, double v) {
     else if (s == "WeightedMove_prob") p->moveProb = v;
     else if (s == "RandomMove_prob") p->randMoveProb = v;
     else if (s == "WeightedMoveRand_prob") p->moveRandProb = v;
+    else if (s == "CondWeightedMove_prob") p->condMoveProb = v;
+    else if (s == "MoveStats_Mode") p->msMode = (int)v;
     else if (s == "SigDeath_max_age") p->sigMaxAge = v;
     else if (s == "SigDeath_range") p->sigRange = v;
     else if (s == "SigDeath_slope") p->sigSlope = v;
@@ -1358,6 +1507,7 @@ int qor_pre_loop(qor_pop *p) {  // core/SPopulation.cpp:273-292 + actions/ATanDe
     }
     { Action *nv = p->find("Navigate"); if (nv && nv->prio >= 0 && p->navRecalculate() != 0) return -1; }  // Navigate::preLoop
     if (p->find("NPPCapacity")) p->nppRecalculate();  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
+    { Action *ms = p->find("MoveStats"); if (ms && ms->prio >= 0) { if (!p->env.count("Longitude") || !p->env.count("Latitude")) return -1; p->moveStatsPreLoop(); } }
     { Action *cm = p->find("ConfinedMove"); if (cm && cm->prio >= 0) { if (!p->env.count("Longitude") || !p->env.count("Latitude")) return -1; p->confinedPreLoop(); } }
     return 0;
 }
@@ -1498,6 +1648,14 @@ int qor_binomial_get_n(double prob, int n, double eps, double r) { return binomi
 int qor_get_capacities(qor_pop *p, double *out) {
     if (p->cap.empty()) return -1;
     memcpy(out, p->cap.data(), sizeof(double) * p->nCells);
+    return 0;
+}
+
+int qor_get_move_stats(qor_pop *p, int32_t *hops, double *dist, double *time) {  /* MoveStats: m_aiHops, m_adDist, m_adTime */
+    if (p->msHops.empty()) return -1;
+    memcpy(hops, p->msHops.data(), sizeof(int32_t) * p->nCells);
+    memcpy(dist, p->msDist.data(), sizeof(double) * p->nCells);
+    memcpy(time, p->msTime.data(), sizeof(double) * p->nCells);
     return 0;
 }
 

@@ -56,6 +56,7 @@ int64_t  qor_get_agents(qor_pop *p, int64_t cap, int32_t *cell, int64_t *id, flo
 int      qor_get_env_weights(qor_pop *p, double *out);             /* nCells*(maxNeigh+1) */
 int      qor_get_birth_death_probs(qor_pop *p, double *b, double *d);
 int      qor_get_capacities(qor_pop *p, double *out);
+int      qor_get_move_stats(qor_pop *p, int32_t *hops, double *dist, double *time);  /* actions/MoveStats.cpp: per-cell arrays */
 int      qor_atan_death_prob(qor_pop *p, int n, const float *age, double *out);
 int      qor_get_step_stats(qor_pop *p, uint64_t *births, uint64_t *deaths, uint64_t *moves);
 

@@ -50,6 +50,10 @@
 #include "OldAgeDeath.cpp"
 #include "ConfinedMove.cpp"
 #include "WeightedMoveRand.cpp"
+#include "CondWeightedMove.cpp"
+#include "SimpleCondition.h"
+#include "RandPermPair.cpp"
+#include "MoveStats.cpp"
 #define EPS EPS_SIGDEATH  // actions/SigDeath.h:14 and actions/ATanDeath.h:14 both define a global `EPS`: no reference TU includes both
 #include "SigDeath.cpp"
 #undef EPS
@@ -115,6 +119,7 @@ struct PopAccess {
     virtual int geneticsInit(int genomeSize, int numCrossOvers, double mutationRate) { return -1; }
     virtual int numBabies(int slot) { return -1; }  // m_iNumBabies of the OoANavGen agents
     virtual ulong *cellCounts() = 0;                // m_aiNumAgentsPerCell
+    virtual int moveStats(int *&hops, double *&dist, double *&time) { return -1; }  // the arrays of a MoveStats action
 };
 
 template <class PopT, class AgentT>
@@ -189,6 +194,15 @@ struct PopAccessT : PopAccess {
         }
     }
     ulong *cellCounts() override { return pop->m_aiNumAgentsPerCell; }
+    int moveStats(int *&hops, double *&dist, double *&time) override {
+        if constexpr (requires { pop->m_pMS; }) {
+            if (pop->m_pMS->m_aiHops == NULL) return -1;
+            hops = pop->m_pMS->m_aiHops; dist = pop->m_pMS->m_adDist; time = pop->m_pMS->m_adTime;
+            return 0;
+        } else {
+            return -1;
+        }
+    }
     int numBabies(int slot) override {
         if constexpr (requires { pop->m_aAgents[slot].m_iNumBabies; }) return pop->m_aAgents[slot].m_iNumBabies; else return -1;
     }
@@ -246,6 +260,32 @@ public:
     virtual ~VarProbePop() { delete m_pWMR; delete m_pSD; }
     WeightedMoveRand<tut_EnvironAltAgent> *m_pWMR;
     SigDeath<tut_EnvironAltAgent> *m_pSD;
+};
+
+// Probe classes for pinning CondWeightedMove (actions/CondWeightedMove.cpp:41-86, with the reference's only MoveCondition,
+// actions/SimpleCondition.cpp, over the altitudes: its mode is a constructor argument, hence one class per mode), RandPermPair
+// (actions/RandPermPair.cpp:67-196) and MoveStats (actions/MoveStats.cpp:107-285).  None of the three is configured by a shipped
+// parameter file (MoveStats sits in RabbitPop, NewMoveStatTestPop and OoANavSHybYchMTDPop); the reference's own templates are
+// added to tut_EnvironAltPop, the <prio> entries of the parameter file decide which of WeightedMove / CondWeightedMove and
+// RandomPair / RandPermPair run.
+template <int MODE>
+class ExtProbePop : public tut_EnvironAltPop {
+public:
+    ExtProbePop(SCellGrid *pCG, PopFinder *pPF, int iLayerSize, IDGen **apIDG, uint32_t *aulState, uint *aiSeeds)
+        : tut_EnvironAltPop(pCG, pPF, iLayerSize, apIDG, aulState, aiSeeds) {
+        m_pCond = new SimpleCondition(m_pCG->m_pGeography->m_adAltitude, MODE);
+        m_pCWM = new CondWeightedMove<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL, m_adEnvWeights, m_pCond);
+        m_prio.addAction(m_pCWM);
+        m_pRPP = new RandPermPair<tut_EnvironAltAgent>(this, m_pCG, "", m_apWELL);
+        m_prio.addAction(m_pRPP);
+        m_pMS = new MoveStats<tut_EnvironAltAgent>(this, m_pCG, "");
+        m_prio.addAction(m_pMS);
+    }
+    virtual ~ExtProbePop() { delete m_pCWM; delete m_pRPP; delete m_pMS; delete m_pCond; }
+    SimpleCondition *m_pCond;
+    CondWeightedMove<tut_EnvironAltAgent> *m_pCWM;
+    RandPermPair<tut_EnvironAltAgent> *m_pRPP;
+    MoveStats<tut_EnvironAltAgent> *m_pMS;
 };
 
 // Probe class for pinning the Genetics action itself (actions/Genetics.cpp:285-337 makeOffspring: strand choice, crossover /
@@ -432,6 +472,11 @@ void *qref_create(const char *xml_path, const char *class_name, int nCells, cons
         s->pa = new PopAccessT<tut_OldAgeDiePop, tut_OldAgeDieAgent>(new tut_OldAgeDiePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltConfPop") {
         s->pa = new PopAccessT<ConfProbePop, tut_EnvironAltAgent>(new ConfProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+#define QHG_EXT_PROBE(M)                                                                                                              \
+    } else if (std::string(class_name) == "tut_EnvironAltCond" #M "Pop") {                                                            \
+        s->pa = new PopAccessT<ExtProbePop<M>, tut_EnvironAltAgent>(new ExtProbePop<M>(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
+    QHG_EXT_PROBE(0) QHG_EXT_PROBE(1) QHG_EXT_PROBE(2) QHG_EXT_PROBE(3) QHG_EXT_PROBE(4) QHG_EXT_PROBE(5) QHG_EXT_PROBE(6) QHG_EXT_PROBE(7)
+#undef QHG_EXT_PROBE
     } else if (std::string(class_name) == "tut_EnvironAltVarPop") {
         s->pa = new PopAccessT<VarProbePop, tut_EnvironAltAgent>(new VarProbePop(s->cg, s->looper, ls, s->idg, s->state, s->seeds));
     } else if (std::string(class_name) == "tut_EnvironAltGenPop") {
@@ -657,6 +702,8 @@ int qref_has_class(const char *name) {
                                         "tut_ParthenoPop", "tut_StaticPop", "tut_EnvironCapAltPop", "OoANavGenPop", "tut_EnvironCapAltAddBlockPop",
                                         "tut_EnvironCapAltMulPop", "tut_EnvironCapAltMaxPop", "tut_EnvironCapAltMaxBlockPop", "tut_EnvironCapAltMinPop"};
     for (const char *k : known) if (std::string(k) == name) return 1;
+    const std::string n(name);
+    if (n.size() == 22 && n.rfind("tut_EnvironAltCond", 0) == 0 && n.substr(19) == "Pop" && n[18] >= '0' && n[18] <= '7') return 1;
     return 0;
 }
 // PopBase::modifyAttributes(name, value) (core/SPopulation.cpp "modifyAttributes": forwarded to every action)
@@ -723,6 +770,17 @@ int qref_get_capacities(void *h, double *out) {
     double *k = s->pa->capacities();
     if (k == NULL) return -1;
     memcpy(out, k, sizeof(double) * s->nCells);
+    return 0;
+}
+
+// MoveStats' per-cell arrays (actions/MoveStats.h:49-51); -1 for populations without the action or before preLoop
+int qref_get_move_stats(void *h, int *hops, double *dist, double *time) {
+    RefSim *s = (RefSim *)h;
+    int *ph; double *pd, *pt;
+    if (s->pa->moveStats(ph, pd, pt) != 0) return -1;
+    memcpy(hops, ph, sizeof(int) * s->nCells);
+    memcpy(dist, pd, sizeof(double) * s->nCells);
+    memcpy(time, pt, sizeof(double) * s->nCells);
     return 0;
 }
 

@@ -67,6 +67,8 @@ def lib(adapter: bool = False):
         L.qref_geo_event.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.qref_timers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.qref_get_capacities.argtypes = [C.c_void_p, C.c_void_p]
+        if hasattr(L, "qref_get_move_stats"):
+            L.qref_get_move_stats.argtypes = [C.c_void_p] * 4
         L.qref_set_env.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.qref_event.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.qref_set_genomes.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p]
@@ -169,6 +171,12 @@ class RefSim:
         out = np.zeros(self.ncells)
         assert self.L.qref_get_capacities(self.h, _p(out)) == 0
         return out
+
+    def move_stats(self):
+        """MoveStats' per-cell arrays (m_aiHops, m_adDist, m_adTime)"""
+        h, d, t = np.zeros(self.ncells, np.int32), np.zeros(self.ncells), np.zeros(self.ncells)
+        assert self.L.qref_get_move_stats(self.h, _p(h), _p(d), _p(t)) == 0
+        return h, d, t
 
     def add_agents(self, pop: dict):
         n = len(pop["cell"])

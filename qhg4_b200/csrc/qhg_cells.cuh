@@ -118,7 +118,7 @@ __device__ __forceinline__ bool nav_sees_moving(unsigned long long prog, int nOp
     bool moving = false;
     for (int k = 0; k < nOps; k++) {
         const int op = (int)((prog >> (4 * k)) & 15ull);
-        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) moving = true;
+        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE || op == OP_CONDWEIGHTEDMOVE) moving = true;
         if (op == OP_FERTILITY) moving = false;
         if (op == OP_NAVIGATE) return moving;
     }
@@ -135,15 +135,19 @@ struct ProgramInfo {  // warp-uniform facts about the action program
     bool needAct0, hasFert, hasVerhulst;
     bool moveAfterAtan, bornAfterAtan;
     bool randomMove;  // the move action is RandomMove (uniform direction, no ice test) instead of WeightedMove
+    bool condMove;    // ... or CondWeightedMove (k_seg_decide only)
 };
 
 __device__ __forceinline__ ProgramInfo program_info(unsigned long long prog, int nOps) {
-    ProgramInfo I{false, false, false, false, false, false};
+    ProgramInfo I{false, false, false, false, false, false, false};
     int ka = -1;
     for (int k = 0; k < nOps; k++) {
         int op = (int)((prog >> (4 * k)) & 15ull);
         if (op == OP_ATANDEATH) { ka = k; I.needAct0 = true; }
-        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) { I.needAct0 = true; I.randomMove = (op == OP_RANDOMMOVE); if (ka >= 0) I.moveAfterAtan = true; }
+        if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE || op == OP_CONDWEIGHTEDMOVE) {
+            I.needAct0 = true; I.randomMove = (op == OP_RANDOMMOVE); I.condMove = (op == OP_CONDWEIGHTEDMOVE);
+            if (ka >= 0) I.moveAfterAtan = true;
+        }
         if (op == OP_VERHULST) { I.needAct0 = true; I.hasVerhulst = true; if (ka >= 0) I.bornAfterAtan = true; }
         if (op == OP_FERTILITY) I.hasFert = true;
     }

@@ -179,6 +179,21 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                     }
                     continue;
                 }
+                if (!SPEC && I.condMove) {  // CondWeightedMove (actions/CondWeightedMove.cpp:41-86): the whole row, the ice of the cell
+                    // the agent is in, the MoveCondition (a SimpleCondition over the altitudes)
+                    const double r2 = __dmul_rn(u2d(u), row[MAXN]);
+                    for (int q = 0; q < MAXN + 1; q++) {
+                        if (r2 < row[q]) { pick = q; break; }
+                    }
+                    if (pick > 0) {
+                        const int dst = S.nbr[ci][pick - 1];
+                        if (dst >= 0 && !(E.ice && E.ice[c0 + ci]) && cond_allow(P.condMode, E.alt[c0 + ci], E.alt[dst])) {
+                            if (confine && !E.allowed[dst]) { if (!(I.moveAfterAtan && (sdec[j] & T_ATANDIES))) confL++; }
+                            else sdec[j] |= (uint8_t)(pick << DEC_MOVE_SHIFT);
+                        }
+                    }
+                    continue;
+                }
                 const double wmax = row[nreal];
                 if (row[0] == wmax) {
                     pick = (int)u2int(u, 0, nreal + 1);
@@ -275,7 +290,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                         ag = __fsub_rn(tNow, birth);
                         const uint32_t uo = agent_draws(id, step, STREAM_ACT1, key).w;
                         if ((double)ag > __dadd_rn(P.oadMaxAge, u2range(uo, P.oadLo, P.oadHi))) alive = false;
-                    } else if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE) {  // actions/WeightedMove.cpp:45-106, RandomMove.cpp:65-100
+                    } else if (op == OP_WEIGHTEDMOVE || op == OP_RANDOMMOVE || op == OP_CONDWEIGHTEDMOVE) {  // actions/WeightedMove.cpp:45-106, RandomMove.cpp:65-100, CondWeightedMove.cpp:41-86
                         if ((unsigned long long)r0.y < tMove) needMove = true;
                     } else if (op == OP_FERTILITY) {  // actions/Fertility.cpp:49-74
                         bool fert;

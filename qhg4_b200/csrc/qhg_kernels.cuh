@@ -20,7 +20,7 @@ constexpr int MAX_OPS = 16;
 // agent flag byte: gender and the FERTILE bit of the reference's life state (core/SPopulation.h:70-74)
 constexpr uint8_t F_MALE = 1, F_FERTILE = 2, F_BORN = 4;  // F_BORN only in the per-step decision byte
 
-enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE, OP_RANDOMMOVE, OP_WEIGHTEDMOVERAND, OP_SIGDEATH };
+enum Op : uint8_t { OP_GETOLD = 1, OP_ATANDEATH, OP_OLDAGEDEATH, OP_WEIGHTEDMOVE, OP_FERTILITY, OP_VERHULST, OP_DROWN, OP_NAVIGATE, OP_RANDOMMOVE, OP_WEIGHTEDMOVERAND, OP_SIGDEATH, OP_CONDWEIGHTEDMOVE };
 
 struct AgentArrays {
     int64_t *id;
@@ -113,7 +113,26 @@ struct ActParams {
     int confine;
     // WeightedMoveRand (actions/WeightedMoveRand.cpp) and SigDeath (actions/SigDeath.cpp:49-90), generic path only
     double moveProbRand, sigMaxAge, sigSlope, sigScale;
+    // CondWeightedMove (actions/CondWeightedMove.cpp) with a SimpleCondition over the altitudes (actions/SimpleCondition.cpp:
+    // 0 never, 1 always, 2 greater, 3 less, 4 equal, 5 greater or equal, 6 less or equal, 7 different)
+    int condMode;
 };
+
+// SimpleCondition::allow (actions/SimpleCondition.cpp:12-19,73-77): the candidate's value enters scaled by 0.2, and "less"
+// also asks for a scaled value below 10
+__device__ __forceinline__ bool cond_allow(int mode, double cur, double cand) {
+    const double n = __dmul_rn(0.2, cand);
+    switch (mode) {
+    case 1: return true;
+    case 2: return n > cur;
+    case 3: return (n < 10.0) && (n < cur);
+    case 4: return n == cur;
+    case 5: return n >= cur;
+    case 6: return n <= cur;
+    case 7: return n != cur;
+    default: return false;
+    }
+}
 
 __host__ __device__ __forceinline__ int prog_op(const ActParams &P, int k) { return (int)((P.prog >> (4 * k)) & 15ull); }
 
@@ -383,6 +402,101 @@ __global__ void k_pair_match(const DevStats *__restrict__ st, AgentArrays a, con
 
 // ---------------------------------------------------------------------------------------------
 // per-cell read-only data the actions touch (L2 resident)
+// MoveStats (actions/MoveStats.cpp): per cell, hops / distance / time of the arrival that counts under MoveStats_Mode (0 the
+// first, 1 the minimum, 2 the last).  The reference walks the step's move list; the device knows no order of the agents, so
+// "first" is the move of the agent with the smallest id and "last" that of the largest (the oracle's counter mode).
+// Every registered move leaves one atomic in the per-step arrays; k_move_stats_temp / k_move_stats_merge apply the step.
+struct MoveStatsDev {
+    int mode;
+    int *hops; double *dist, *time;          // m_aiHops, m_adDist, m_adTime
+    int *hopsT; double *distT, *timeT;       // the reference's per-thread arrays (one thread): never reset
+    unsigned long long *key;                 // modes 0 / 2: (agent id << 20 | source cell) of the move that counts, +1
+    int *stepHops; unsigned long long *stepDist;  // mode 1: minima over this step's moves (the distance as ordered bits)
+    uint8_t *changed;
+    const double *lon, *lat;
+};
+constexpr int MS_CELL_BITS = 20;
+
+// utils/geomutils.cpp:309-333 (spherdistDeg -> spherdist) with the radius of the Geography (6371.3 km)
+__device__ __forceinline__ double ms_distance(const MoveStatsDev &M, int from, int to) {
+    const double PI_ = 3.14159265358979323846;
+    const double lo1 = __ddiv_rn(__dmul_rn(M.lon[from], PI_), 180.0), la1 = __ddiv_rn(__dmul_rn(M.lat[from], PI_), 180.0);
+    const double lo2 = __ddiv_rn(__dmul_rn(M.lon[to], PI_), 180.0), la2 = __ddiv_rn(__dmul_rn(M.lat[to], PI_), 180.0);
+    const double x1 = __dmul_rn(cos(lo1), cos(la1)), y1 = __dmul_rn(sin(lo1), cos(la1)), z1 = sin(la1);
+    const double x2 = __dmul_rn(cos(lo2), cos(la2)), y2 = __dmul_rn(sin(lo2), cos(la2)), z2 = sin(la2);
+    double pr = __dadd_rn(__dadd_rn(__dmul_rn(x1, x2), __dmul_rn(y1, y2)), __dmul_rn(z1, z2));
+    if (pr > 1) pr = 1; else if (pr < -1) pr = -1;
+    return __dmul_rn(6371.3, acos(pr));
+}
+
+// one registered move (SPopulation::registerMove) as MoveStats::finalize will see it in the move list
+__device__ __forceinline__ void ms_register(const MoveStatsDev *M, int from, int to, long long id) {
+    if (!M) return;
+    const unsigned long long k = (((unsigned long long)id << MS_CELL_BITS) | (unsigned long long)from) + 1ull;
+    if (M->mode == 0) atomicMin(&M->key[to], k);
+    else if (M->mode == 2) atomicMax(&M->key[to], k);
+    else {
+        atomicMin(&M->stepHops[to], M->hops[from] + 1);
+        atomicMin(&M->stepDist[to], (unsigned long long)__double_as_longlong(__dadd_rn(M->dist[from], ms_distance(*M, from, to))));
+    }
+}
+
+// MoveStats::finalize, first half (actions/MoveStats.cpp:204-241): the step's moves into every cell update the Temp arrays --
+// all values come from the arrays as they stood BEFORE the step
+__global__ void k_move_stats_temp(MoveStatsDev M, int nCells, double t) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        if (M.mode == 1) {
+            const int h = M.stepHops[c];
+            if (h == 0x7fffffff) continue;
+            const double d = __longlong_as_double((long long)M.stepDist[c]);
+            if (M.hopsT[c] < 0) { M.hopsT[c] = h; M.distT[c] = d; }
+            else { if (h < M.hopsT[c]) M.hopsT[c] = h; if (d < M.distT[c]) M.distT[c] = d; }
+            M.timeT[c] = t;
+            M.changed[c] = 1;
+            M.stepHops[c] = 0x7fffffff; M.stepDist[c] = ~0ull;
+        } else {
+            const unsigned long long none = (M.mode == 0) ? ~0ull : 0ull;
+            const unsigned long long k = M.key[c];
+            if (k == none) continue;
+            M.key[c] = none;
+            if (M.hopsT[c] < 0 || M.mode == 2) {
+                const int from = (int)((k - 1ull) & ((1ull << MS_CELL_BITS) - 1ull));
+                M.hopsT[c] = M.hops[from] + 1;
+                M.distT[c] = __dadd_rn(M.dist[from], ms_distance(M, from, c));
+                M.timeT[c] = t;
+                M.changed[c] = 1;
+            }
+        }
+    }
+}
+
+// ... second half (:249-283): the cells touched in this step take over what their Temp entries say
+__global__ void k_move_stats_merge(MoveStatsDev M, int nCells) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        if (!M.changed[c]) continue;
+        M.changed[c] = 0;
+        if (M.hops[c] < 0 || M.mode == 2) {
+            M.hops[c] = M.hopsT[c]; M.dist[c] = M.distT[c]; M.time[c] = M.timeT[c];
+        } else if (M.mode == 1) {
+            if (M.hopsT[c] < M.hops[c]) M.hops[c] = M.hopsT[c];
+            if (M.distT[c] < M.dist[c]) M.dist[c] = M.distT[c];
+            if (M.timeT[c] < M.time[c]) M.time[c] = M.timeT[c];
+        }
+    }
+}
+
+// MoveStats::preLoop + initializeOccupied (actions/MoveStats.cpp:107-186): -1 everywhere, 0 in the cells that are occupied
+__global__ void k_move_stats_init(MoveStatsDev M, int nCells, const int *__restrict__ count) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        const bool occ = count[c] > 0;
+        M.hops[c] = occ ? 0 : -1; M.dist[c] = occ ? 0.0 : -1.0; M.time[c] = occ ? 0.0 : -1.0;
+        M.hopsT[c] = -1; M.distT[c] = -1.0; M.timeT[c] = -1.0;
+        M.key[c] = (M.mode == 0) ? ~0ull : 0ull;
+        M.stepHops[c] = 0x7fffffff; M.stepDist[c] = ~0ull;
+        M.changed[c] = 0;
+    }
+}
+
 struct CellEnv {
     const int *nbr;
     const uint8_t *nNbr;
@@ -401,6 +515,7 @@ struct CellEnv {
     int nBridges;
     double bridgeProb;
     const uint8_t *allowed;  // ConfinedMove::m_bAllowed (actions/ConfinedMove.cpp:44-78), NULL without the action
+    const MoveStatsDev *ms;  // MoveStats is active in this step (generic path only), else NULL
 };
 
 struct Decision {
@@ -468,7 +583,27 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 }
                 if (pick > 0) {
                     int dst = E.nbr[(size_t)c * MAXN + pick - 1];
-                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id); }
+                }
+            }
+            break;
+        }
+        case OP_CONDWEIGHTEDMOVE: {  // actions/CondWeightedMove.cpp:41-86: the whole row up to the grid's connectivity, no special
+            // case for equal weights, the ice test looks at the cell the agent is IN, the MoveCondition decides last
+            if (!have0) { r0 = agent_draws(id, step, STREAM_ACT0, P.key); have0 = true; }
+            if (u2d(r0.y) < P.moveProb) {
+                if (!have1) { r1 = agent_draws(id, step, STREAM_ACT1, P.key); have1 = true; }
+                const double *row = E.W + (size_t)c * WSTRIDE;
+                int pick = -1;
+                const double r2 = __dmul_rn(u2d(r1.x), row[MAXN]);
+                for (int q = 0; q < MAXN + 1; q++) {
+                    if (r2 < row[q]) { pick = q; break; }
+                }
+                if (pick > 0) {
+                    const int dst = E.nbr[(size_t)c * MAXN + pick - 1];
+                    if (dst >= 0 && !(E.ice && E.ice[c]) && cond_allow(P.condMode, E.alt[c], E.alt[dst])) {
+                        d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id);
+                    }
                 }
             }
             break;
@@ -490,7 +625,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 }
                 if (pick > 0) {
                     int dst = E.nbr[(size_t)c * MAXN + pick - 1];
-                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
+                    if (dst >= 0 && !(E.ice && E.ice[dst])) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id); }
                 }
             }
             break;
@@ -510,7 +645,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 const int pick = (int)__dmul_rn(u2d(r1.x), (double)(E.nNbr[c] + 1));
                 if (pick > 0) {
                     int dst = E.nbr[(size_t)c * MAXN + pick - 1];
-                    if (dst >= 0) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; }
+                    if (dst >= 0) { d.to = dst; d.pick = pick; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id); }
                 }
             }
             break;
@@ -538,7 +673,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 while (i < lim && r > E.navCum[p0 + i]) i++;
                 if (i > 0) {
                     const int dst = E.navDest[p0 + i];
-                    if (!(E.ice && E.ice[dst])) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; }
+                    if (!(E.ice && E.ice[dst])) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id); }
                 }
             }
             for (int b = 0; b < E.nBridges; b++) {  // manual bridges: one draw per incident bridge (:228-247)
@@ -547,7 +682,7 @@ __device__ __forceinline__ Decision run_actions(const ActParams &P, const CellEn
                 if (dst >= 0) {
                     const uint4 db = agent_draws(id, step, 0x04000000u | (unsigned)(b / 4), P.key);
                     const unsigned wv = (b & 3) == 0 ? db.x : (b & 3) == 1 ? db.y : (b & 3) == 2 ? db.z : db.w;
-                    if (u2d(wv) < E.bridgeProb) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; }
+                    if (u2d(wv) < E.bridgeProb) { d.to = dst; d.pick = 0; d.moving = true; d.movingBit = true; d.nMoves++; ms_register(E.ms, c, dst, id); }
                 }
             }
             break;

@@ -110,7 +110,8 @@ int loadNccl() {
     } while (0)
 
 enum ActKind { A_GETOLD, A_ATANDEATH, A_OLDAGEDEATH, A_WEIGHTEDMOVE, A_SINGLEEVAL, A_FERTILITY, A_RANDOMPAIR, A_VERHULST,
-               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH };
+               A_VERHULSTVARK, A_MULTIEVAL, A_NPPCAP, A_GENETICS, A_NAVIGATE, A_RANDOMMOVE, A_CONFINEDMOVE, A_WEIGHTEDMOVERAND, A_SIGDEATH,
+               A_CONDWEIGHTEDMOVE, A_RANDPERMPAIR, A_MOVESTATS };
 
 // one SingleEvaluator inside a MultiEvaluator (actions/SingleEvaluator.cpp:138-167)
 struct SubEval {
@@ -265,6 +266,15 @@ struct qhgb_pop {
     // ConfinedMove: the cells inside the region (ConfinedMove::m_bAllowed, actions/ConfinedMove.cpp:44-78), built at preLoop
     DevBuf<uint8_t> allowed;
     bool confReady = false;
+    // MoveStats (actions/MoveStats.cpp): main arrays, the reference's Temp arrays, the per-step atomics (qhg_kernels.cuh)
+    DevBuf<int> msHops, msHopsT, msStepHops;
+    DevBuf<double> msDist, msTime, msDistT, msTimeT, msLon, msLat;
+    DevBuf<unsigned long long> msKey, msStepDist;
+    DevBuf<uint8_t> msChanged;
+    DevBuf<MoveStatsDev> msDev;
+    MoveStatsDev msHost{};
+    bool msReady = false;
+    int condMode = 0;  // SimpleCondition mode of a CondWeightedMove (the probe classes tut_EnvironAltCond<m>Pop carry it in their name)
     std::vector<double> hLon, hLat;  // host copies of Longitude / Latitude for it
     bool selfMate = false;           // tut_ParthenoPop: every female counts as mated, newborns are female
     float curTime = -1;
@@ -508,6 +518,7 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
         case A_WEIGHTEDMOVE: op = OP_WEIGHTEDMOVE; break;
         case A_RANDOMMOVE: op = OP_RANDOMMOVE; break;
         case A_WEIGHTEDMOVERAND: op = OP_WEIGHTEDMOVERAND; break;
+        case A_CONDWEIGHTEDMOVE: op = OP_CONDWEIGHTEDMOVE; break;
         case A_SIGDEATH: op = OP_SIGDEATH; break;
         case A_FERTILITY: op = OP_FERTILITY; break;
         case A_VERHULST: op = OP_VERHULST; break;
@@ -548,6 +559,8 @@ ActParams buildProgram(qhgb_pop *p, const std::vector<unsigned> *levels, float t
     P.oadLo = 1 - unc * P.oadMaxAge;
     P.oadHi = 1 + unc * P.oadMaxAge;
     P.moveProb = p->findKind(A_RANDOMMOVE) ? p->A("RandomMove_prob") : p->A("WeightedMove_prob");  // a population has one move action
+    if (p->active(A_CONDWEIGHTEDMOVE)) P.moveProb = p->A("CondWeightedMove_prob");  // (the probe classes carry two: the <prio> entries choose)
+    P.condMode = p->condMode;
     P.tMove = (P.moveProb > 0) ? (unsigned long long)ceil(P.moveProb * 4294967296.0) : 0ull;  // exact: a power-of-two scaling
     P.fertMinAge = (float)p->A("Fertility_min_age");
     P.fertMaxAge = (float)p->A("Fertility_max_age");
@@ -781,6 +794,34 @@ int recalcConfined(qhgb_pop *p) {
     return 0;
 }
 
+// MoveStats::preLoop (actions/MoveStats.cpp:107-143) + initializeOccupied (:148-186)
+int setupMoveStats(qhgb_pop *p) {
+    qhgb_pop &q = *p;
+    if (q.hLon.size() != (size_t)q.nCells || q.hLat.size() != (size_t)q.nCells) return fail("[MoveStats] no geography (Longitude / Latitude)");
+    if (q.nCells > (1 << MS_CELL_BITS)) return fail("[MoveStats] more than %d cells", 1 << MS_CELL_BITS);
+    if (q.active(A_CONFINEDMOVE)) return fail("[MoveStats] together with ConfinedMove is not supported (the order of their finalize() calls decides what MoveStats sees)");
+    if (q.sharded) return fail("[MoveStats] runs on the generic path, which sharded populations do not have");
+    const int mode = (int)q.A("MoveStats_Mode");
+    if (mode < 0 || mode > 2) return fail("[MoveStats] MoveStats_Mode %d", mode);
+    const size_t n = (size_t)q.nCells;
+    CK(q.msHops.alloc(n)); CK(q.msHopsT.alloc(n)); CK(q.msStepHops.alloc(n));
+    CK(q.msDist.alloc(n)); CK(q.msTime.alloc(n)); CK(q.msDistT.alloc(n)); CK(q.msTimeT.alloc(n)); CK(q.msLon.alloc(n)); CK(q.msLat.alloc(n));
+    CK(q.msKey.alloc(n)); CK(q.msStepDist.alloc(n)); CK(q.msChanged.alloc(n)); CK(q.msDev.alloc(1));
+    CK(cudaMemcpyAsync(q.msLon.p, q.hLon.data(), sizeof(double) * n, cudaMemcpyHostToDevice, q.stream));
+    CK(cudaMemcpyAsync(q.msLat.p, q.hLat.data(), sizeof(double) * n, cudaMemcpyHostToDevice, q.stream));
+    MoveStatsDev &M = q.msHost;
+    M.mode = mode;
+    M.hops = q.msHops.p; M.dist = q.msDist.p; M.time = q.msTime.p;
+    M.hopsT = q.msHopsT.p; M.distT = q.msDistT.p; M.timeT = q.msTimeT.p;
+    M.key = q.msKey.p; M.stepHops = q.msStepHops.p; M.stepDist = q.msStepDist.p; M.changed = q.msChanged.p;
+    M.lon = q.msLon.p; M.lat = q.msLat.p;
+    CK(cudaMemcpyAsync(q.msDev.p, &M, sizeof(M), cudaMemcpyHostToDevice, q.stream));
+    LAUNCH(p, "k_move_stats_init", k_move_stats_init, q.gridFor(q.nCells), 256, M, q.nCells, q.count[q.cur].p);
+    CK(cudaStreamSynchronize(q.stream));
+    q.msReady = true;
+    return 0;
+}
+
 int computeWeights(qhgb_pop *p) {
     if (!p->haveAlt) return fail("SingleEvaluator[Alt]: no array with name [Altitude]");
     int g = p->gridFor(p->nCells);
@@ -940,11 +981,13 @@ bool programTiled(qhgb_pop *p, const ActParams &P, bool *useNav) {
     for (int k = 0; k < P.nOps; k++) {
         const int op = prog_op(P, k);
         if (op == OP_WEIGHTEDMOVERAND || op == OP_SIGDEATH) tiled = false;
+        if (op == OP_CONDWEIGHTEDMOVE && !q.segDecide) tiled = false;  // only the batched decide kernel knows it
         if (op == OP_NAVIGATE) {
             if (q.navFast && k == P.nOps - 1 && !P.confine && q.navReady) nav = true;
             else tiled = false;
         }
     }
+    if (q.msReady && q.active(A_MOVESTATS)) tiled = false;  // MoveStats sees every registered move: generic path
     if (useNav) *useNav = tiled && nav;
     return tiled;
 }
@@ -1168,8 +1211,18 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             q.needPair = doPair;
             if (ensurePairing(p) != 0) return -1;
             if (q.genetic) LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
-            LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, cellEnv(p), q.arrive.p, q.birthCount.p,
+            CellEnv Eg = cellEnv(p);
+            const bool doStats = advanceStep && q.msReady && q.active(A_MOVESTATS);  // MoveStats::finalize sees the step's move list
+            if (doStats) {
+                if (q.nextID >= (1ll << (63 - MS_CELL_BITS))) return fail("[MoveStats] agent ids beyond 2^%d", 63 - MS_CELL_BITS);
+                Eg.ms = q.msDev.p;
+            }
+            LAUNCH(p, "k_actions", k_actions, ga, 256, q.dstats.p, a, q.mate.p, P, Eg, q.arrive.p, q.birthCount.p,
                    q.dest.p, q.rank.p, q.oflags.p);
+            if (doStats) {
+                LAUNCH(p, "k_move_stats_temp", k_move_stats_temp, q.gridFor(q.nCells), 256, q.msHost, q.nCells, (double)P.t);
+                LAUNCH(p, "k_move_stats_merge", k_move_stats_merge, q.gridFor(q.nCells), 256, q.msHost, q.nCells);
+            }
             launchScan(p);
             if (q.mirror && !defer) mirrorAfterScan(p, q.cur ^ 1);
             LAUNCH(p, "k_scatter", k_scatter, ga, 256, q.dstats.p, a, o, q.cellStart[q.cur].p, q.dest.p, q.rank.p, q.oflags.p,
@@ -1320,6 +1373,15 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
         p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
                       {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
                       {"WeightedMoveRand", A_WEIGHTEDMOVERAND}, {"SigDeath", A_SIGDEATH}};
+    } else if (p->popClass.size() == 22 && p->popClass.rfind("tut_EnvironAltCond", 0) == 0 && p->popClass.substr(19) == "Pop" &&
+               p->popClass[18] >= '0' && p->popClass[18] <= '7') {
+        // tut_EnvironAltPop with CondWeightedMove (actions/CondWeightedMove.cpp; a SimpleCondition of mode m over the altitudes),
+        // RandPermPair (actions/RandPermPair.cpp) and MoveStats (actions/MoveStats.cpp) added: the classes the reference driver
+        // builds to pin them (ExtProbePop<m>, oracle/ref_driver.cpp)
+        p->condMode = p->popClass[18] - '0';
+        p->actions = {{"GetOld", A_GETOLD}, {"ATanDeath", A_ATANDEATH}, {"Fertility", A_FERTILITY}, {"Verhulst", A_VERHULST},
+                      {"RandomPair", A_RANDOMPAIR}, {"SingleEvaluator[Alt]", A_SINGLEEVAL}, {"WeightedMove", A_WEIGHTEDMOVE},
+                      {"CondWeightedMove", A_CONDWEIGHTEDMOVE}, {"RandPermPair", A_RANDPERMPAIR}, {"MoveStats", A_MOVESTATS}};
     } else if (p->popClass == "tut_EnvironAltGenPop" || p->popClass == "tut_EnvironAltGen2bitPop") {
         // tut_EnvironAltPop with Genetics<.., BitGeneUtils> resp. Genetics<.., GeneUtils> added: the classes the reference driver
         // builds to pin the Genetics action (GenProbePop<U>, oracle/ref_driver.cpp)
@@ -1558,7 +1620,7 @@ int qhgb_interpolate_env(qhgb_pop *p, int steps) {
 
 static const char *const kNumericAttrs[] = {
     "ATanDeath_max_age", "ATanDeath_range", "ATanDeath_slope", "OAD_max_age", "OAD_uncertainty", "WeightedMove_prob", "RandomMove_prob",
-    "ConfinedMove_x", "ConfinedMove_y", "ConfinedMove_r", "WeightedMoveRand_prob", "SigDeath_max_age", "SigDeath_range", "SigDeath_slope",
+    "ConfinedMove_x", "ConfinedMove_y", "ConfinedMove_r", "WeightedMoveRand_prob", "CondWeightedMove_prob", "MoveStats_Mode", "SigDeath_max_age", "SigDeath_range", "SigDeath_slope",
     "Fertility_min_age", "Fertility_max_age", "Fertility_interbirth", "Verhulst_b0", "Verhulst_d0", "Verhulst_theta",
     "Verhulst_K", "NPPCap_water_factor", "NPPCap_coastal_factor", "NPPCap_coastal_min_latitude", "NPPCap_coastal_max_latitude",
     "NPPCap_NPP_min", "NPPCap_NPP_max", "NPPCap_K_max", "NPPCap_K_min", "NPPCap_efficiency", "Multi_weight_alt", "Multi_weight_npp",
@@ -1758,6 +1820,7 @@ int qhgb_pre_loop(qhgb_pop *p) {
     }
     if (p->findKind(A_NPPCAP) && recalcCapacities(p) != 0) return -1;  // NPPCapacity::preLoop, actions/NPPCapacity.cpp:92-115
     if (p->findKind(A_CONFINEDMOVE) && p->findKind(A_CONFINEDMOVE)->prio >= 0 && recalcConfined(p) != 0) return -1;  // ConfinedMove::preLoop
+    if (p->findKind(A_MOVESTATS) && p->findKind(A_MOVESTATS)->prio >= 0 && setupMoveStats(p) != 0) return -1;           // MoveStats::preLoop
     p->preLooped = true;
     p->evalFirst = true;
     return 0;
@@ -1781,6 +1844,9 @@ int qhgb_initialize_step(qhgb_pop *p, float t) {
     // pairing (RandomPair::initialize) is fused into the decide pass of finalizeStep; ensurePairing() runs it
     // stand-alone if the host looks at the mates before that
     q.needPair = pair && pair->prio >= 0 && pair->enabled;
+    // RandPermPair (actions/RandPermPair.cpp:99-196) shuffles the larger sex and mates equal places: a uniformly random injection
+    // of the smaller sex into the larger one -- the law the rank-by-key pairing of the device implements for RandomPair
+    if (q.active(A_RANDPERMPAIR)) q.needPair = true;
     q.doVerhulst = doVer;
     q.pairingValid = false;
     if (ev && ev->prio >= 0 && ev->enabled && (q.evalNeedUpdate || q.evalFirst)) {
@@ -2007,6 +2073,18 @@ int qhgb_mirror_num_agents_array(qhgb_pop *p, uint64_t *host, int32_t cell_begin
     CK(cudaSetDevice(p->device));
     p->mirror = host; p->mirrorLo = cell_begin; p->mirrorHi = cell_end;
     enqueueMirror(p, p->cur);
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qhgb_get_move_stats(qhgb_pop *p, int32_t *hops, double *dist, double *time) {
+    if (!p || !hops || !dist || !time) return fail("qhgb_get_move_stats: NULL argument");
+    if (!p->msReady) return fail("qhgb_get_move_stats: the population has no active MoveStats (or preLoop has not run)");
+    CK(cudaSetDevice(p->device));
+    const size_t n = (size_t)p->nCells;
+    CK(cudaMemcpyAsync(hops, p->msHops.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(dist, p->msDist.p, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(time, p->msTime.p, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
 }

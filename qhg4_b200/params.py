@@ -204,6 +204,24 @@ def tut_environ_alt_variants(K: float, move_rand: bool = True, sig_death: bool =
     return par
 
 
+def tut_environ_alt_ext(K: float, cond_mode: int = -1, perm_pair: bool = False, move_stats: int = -1, move_prob: float = 0.2) -> PopParams:
+    """tut_EnvironAltPop's parameter set for the probe classes `tut_EnvironAltCond<m>Pop` (ExtProbePop<m> of oracle/ref_driver.cpp):
+    CondWeightedMove (actions/CondWeightedMove.cpp, a SimpleCondition of mode m over the altitudes) in place of WeightedMove when
+    cond_mode >= 0, RandPermPair (actions/RandPermPair.cpp) in place of RandomPair, and MoveStats (actions/MoveStats.cpp) with
+    MoveStats_Mode = move_stats (0 first, 1 minimum, 2 last) as the step's last action when move_stats >= 0."""
+    par = tut_environ_alt(K)
+    par.class_name = f"tut_EnvironAltCond{max(cond_mode, 0)}Pop"
+    par.modules["CondWeightedMove"] = {"CondWeightedMove_prob": repr(float(move_prob))}
+    par.modules["MoveStats"] = {"MoveStats_Mode": str(int(max(move_stats, 0)))}
+    if cond_mode >= 0:
+        par.prios["CondWeightedMove"] = par.prios.pop("WeightedMove")
+    if perm_pair:
+        par.prios["RandPermPair"] = par.prios.pop("RandomPair")
+    if move_stats >= 0:
+        par.prios["MoveStats"] = max(par.prios.values()) + 1
+    return par
+
+
 def tut_environ_alt_genetic(K: float, genome_size: int, num_crossover: int, mutation_rate: float, bits_per_nuc: int = 1) -> PopParams:
     """tut_EnvironAltPop's parameter set plus Genetics (actions/Genetics.cpp) with 1-bit (genes/BitGeneUtils.cpp) or 2-bit
     (genes/GeneUtils.cpp) nucleotides: the probe classes `tut_EnvironAltGenPop` / `tut_EnvironAltGen2bitPop` of

@@ -191,6 +191,12 @@ class GpuPopulation:
         self._mirror = host  # keeps the array alive
         return host
 
+    def move_stats(self):
+        """MoveStats' per-cell arrays (hops, dist, time); -1 = never reached"""
+        h, d, t = np.zeros(self.ncells, np.int32), np.zeros(self.ncells), np.zeros(self.ncells)
+        check(self.L.qhgb_get_move_stats(self.h, _p(h), _p(d), _p(t)), "qhgb_get_move_stats")
+        return h, d, t
+
     def occupied(self, cells):
         """OccTracker::calcBitMap for this population: one byte per listed cell, 1 = somebody is there"""
         c = np.ascontiguousarray(cells, np.int32)

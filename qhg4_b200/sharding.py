@@ -15,13 +15,19 @@ import numpy as np
 # fixed cost of an occupied cell in agent-equivalents: one step costs about a * agents + b * occupied cells on the device
 # (measured on B200: 1e8 agents -> 1.90 ms, 1e7 agents -> 0.50 ms on the same 459k land cells, so b / a = 44)
 CELL_COST_AGENTS = 44
+# ... and an EMPTY cell of the range is not free either: both passes hand out cells, not agents (8 B200, 1e8 agents: the ranks
+# whose ranges hold 80,000 more sea cells than the others need 22-28 us more per step, at 0.028 ns per agent-step: 11)
+EMPTY_CELL_COST_AGENTS = 11
 
 
-def partition_cells(agents_per_cell, nranks: int, cell_cost: float = CELL_COST_AGENTS) -> np.ndarray:
+def partition_cells(agents_per_cell, nranks: int, cell_cost: float = CELL_COST_AGENTS, empty_cost: float = None) -> np.ndarray:
     """Boundaries (int32, nranks+1) of contiguous cell ranges of about equal step COST: the agents of a range plus
-    `cell_cost` agent-equivalents for every occupied cell (cell_cost=0: balanced by agents alone)."""
+    `cell_cost` agent-equivalents for every occupied cell and `empty_cost` for every empty one (cell_cost=0: balanced by
+    agents alone)."""
     cnt = np.asarray(agents_per_cell, dtype=np.int64)
-    cnt = cnt + np.int64(cell_cost) * (cnt > 0)
+    if empty_cost is None:
+        empty_cost = EMPTY_CELL_COST_AGENTS if cell_cost > 0 else 0
+    cnt = cnt + np.int64(cell_cost) * (cnt > 0) + np.int64(empty_cost) * (cnt == 0)
     ncell = len(cnt)
     cum = np.concatenate([[0], np.cumsum(cnt)])
     total = cum[-1]

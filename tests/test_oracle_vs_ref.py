@@ -194,6 +194,49 @@ def test_weighted_move_rand_and_sig_death_equal_reference(move_rand, sig_death):
     r.close()
 
 
+@pytest.mark.parametrize("cond_mode,perm_pair,move_stats", [(2, False, -1), (3, True, -1), (6, True, 2), (7, False, 0), (-1, True, 0),
+                                                            (1, False, 1), (5, True, 2), (-1, False, 1)])
+def test_cond_weighted_move_rand_perm_pair_and_move_stats_equal_reference(cond_mode, perm_pair, move_stats):
+    """CondWeightedMove (actions/CondWeightedMove.cpp:41-86 with actions/SimpleCondition.cpp over the altitudes: greater, less,
+    less-or-equal, different ...), RandPermPair (actions/RandPermPair.cpp:67-196: partial Fisher-Yates over the larger sex) and
+    MoveStats (actions/MoveStats.cpp:107-285: hops / distance / time of the first, the minimal or the last arrival per cell)
+    pinned against the reference's own templates added to tut_EnvironAltPop (ExtProbePop<m> in oracle/ref_driver.cpp)."""
+    from qhg4_b200.params import tut_environ_alt_ext
+    nbr, xyz = make_ico_grid(7)
+    alt = synthetic_altitude(xyz, seed=5)
+    ice = (xyz[:, 2] > 0.9).astype(np.float64)       # CondWeightedMove looks at the ice of the cell the agent is IN
+    land = np.flatnonzero(alt > 0)
+    alt[land[::3]] = 30.0                             # lowlands: what "less" (0.2 x new < 10 and < current) and "greater" need
+    start = land[np.argsort(xyz[land, 0])[:60]]       # a small home range: most cells are reached during the run
+    pop = synthetic_population(6000, alt, seed=6, fertile=True, cells=start)
+    par = tut_environ_alt_ext(150.0, cond_mode, perm_pair, move_stats, move_prob=0.3)
+    lon = np.degrees(np.arctan2(xyz[:, 1], xyz[:, 0])); lat = np.degrees(np.arcsin(xyz[:, 2]))
+    env = {"Longitude": lon, "Latitude": lat}
+    st = seed_state(21)
+    r = refsim.RefSim(par, nbr, alt, ice=ice, threads=1, state16=st, env=env)
+    o = port.OraclePop(par, nbr, alt, ice=ice, mode=port.MODE_WELL, state16=st, env=env)
+    r.add_agents(pop); o.add_agents(pop)
+    r.start(); o.start()
+    moves = births = 0
+    for k in range(14):
+        r.step(float(k)); o.step(float(k))
+        assert r.num_agents() == o.num_agents(), k
+        ra, oa = r.agents(), o.agents()
+        for f in FIELDS:
+            assert np.array_equal(ra[f], oa[f]), (k, f)
+        assert np.array_equal(r.counts(), o.counts()), k
+        if move_stats >= 0:
+            for x, y, name in zip(r.move_stats(), o.move_stats(), ("hops", "dist", "time")):
+                assert np.array_equal(x, y), (k, name)
+        b, d, m = o.step_stats()
+        moves += m; births += b
+    assert moves > (100 if cond_mode in (2, 3) else 1500) and births > 300   # "greater" / "less" with the 0.2 factor allow few moves
+    if move_stats >= 0:
+        h, dist, tm = o.move_stats()
+        assert (h > 0).sum() > 5 and (h < 0).any() and dist[h > 0].min() > 50.0
+    r.close()
+
+
 def test_navigate_equals_reference():
     """Navigate (actions/Navigate.cpp:94-250) pinned against the reference's own action: the reference's Navigate<T> is
     added to the reference's tut_EnvironAltPop (NavProbePop in oracle/ref_driver.cpp; the shipped populations that carry

@@ -811,6 +811,61 @@ def test_weighted_move_rand_and_sig_death_bit_exact_vs_oracle(move_rand, sig_dea
     assert_same_population(g, o, 14)
 
 
+@pytest.mark.parametrize("cond_mode,perm_pair", [(2, False), (3, True), (6, False), (7, True), (1, False)])
+def test_cond_weighted_move_and_rand_perm_pair_bit_exact_vs_oracle(cond_mode, perm_pair, path):
+    """CondWeightedMove (actions/CondWeightedMove.cpp with a SimpleCondition over the altitudes) on both device paths, RandPermPair
+    (actions/RandPermPair.cpp) through the pairing it shares its law with; the oracle's WELL mode equals the reference's own
+    templates (tests/test_oracle_vs_ref.py::test_cond_weighted_move_rand_perm_pair_and_move_stats_equal_reference)."""
+    from qhg4_b200.params import tut_environ_alt_ext
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=5)
+    land = np.flatnonzero(alt > 0)
+    alt[land[::3]] = 30.0
+    ice = (xyz[:, 2] > 0.9).astype(np.float64)
+    pop = synthetic_population(40000, alt, seed=6, fertile=True)
+    g, o = make_pair(tut_environ_alt_ext(30.0, cond_mode, perm_pair, -1, move_prob=0.3), nbr, alt, pop, ice=ice, seed=17)
+    moves = births = 0
+    for k in range(10):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        s = g.step_stats()
+        assert (s.births, s.deaths, s.moves) == o.step_stats(), f"step {k}"
+        moves += s.moves; births += s.births
+    assert moves > (300 if cond_mode in (2, 3) else 20000) and births > 2000
+    g.run(10.0, 4)
+    for k in range(10, 14):
+        o.step(float(k))
+    assert_same_population(g, o, 13)
+
+
+@pytest.mark.parametrize("mode,cond_mode", [(0, -1), (1, -1), (2, -1), (0, 7), (1, 6)])
+def test_move_stats_vs_oracle(mode, cond_mode):
+    """MoveStats (actions/MoveStats.cpp:107-285) on the device: hops and time of every cell equal the oracle's counter mode, the
+    distances (great circles summed along the path; sin / cos / acos of the device's library) to 1e-12 relative.  "First" and
+    "last" are the moves of the smallest / largest agent id there; the oracle's WELL mode follows the reference's move list."""
+    from qhg4_b200.params import tut_environ_alt_ext
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=5)
+    land = np.flatnonzero(alt > 0)
+    start = land[np.argsort(xyz[land, 0])[:200]]
+    pop = synthetic_population(30000, alt, seed=6, fertile=True, cells=start)
+    lon = np.degrees(np.arctan2(xyz[:, 1], xyz[:, 0])); lat = np.degrees(np.arcsin(xyz[:, 2]))
+    env = {"Longitude": lon, "Latitude": lat}
+    g, o = make_pair(tut_environ_alt_ext(200.0, cond_mode, False, mode, move_prob=0.3), nbr, alt, pop, seed=23, env=env)
+    for k in range(12):
+        g.step(float(k)); o.step(float(k))
+        assert_same_population(g, o, k)
+        (gh, gd, gt), (oh, od, ot) = g.move_stats(), o.move_stats()
+        assert np.array_equal(gh, oh) and np.array_equal(gt, ot), k
+        assert np.allclose(gd, od, rtol=1e-12, atol=0), k
+    assert (oh > 3).sum() > 100 and (oh < 0).any()
+    g.run(12.0, 3)                       # inside qhgb_run such populations step one by one
+    for k in range(12, 15):
+        o.step(float(k))
+    (gh, gd, gt), (oh, od, ot) = g.move_stats(), o.move_stats()
+    assert np.array_equal(gh, oh) and np.array_equal(gt, ot) and np.allclose(gd, od, rtol=1e-12, atol=0)
+
+
 @pytest.mark.parametrize("move_first", [False, True])
 def test_confined_move_bit_exact_vs_oracle(move_first, path):
     """ConfinedMove (actions/ConfinedMove.cpp:44-101; its finalize() filters the whole move list in finalizeStep): moves out

@@ -23,10 +23,10 @@ def test_partition_cells_balances_agents():
         assert b[0] == 0 and b[-1] == 5000 and np.all(np.diff(b) >= 0) and len(b) == n + 1
         per = [cnt[b[r]:b[r + 1]].sum() for r in range(n)]
         assert max(per) - min(per) <= 2 * cnt.max() + 1, per
-        # default: balanced by cost = agents + a fixed number of agent-equivalents per occupied cell
-        from qhg4_b200.sharding import CELL_COST_AGENTS
+        # default: balanced by cost = agents + a fixed number of agent-equivalents per occupied cell (fewer per empty cell)
+        from qhg4_b200.sharding import CELL_COST_AGENTS, EMPTY_CELL_COST_AGENTS
         b = partition_cells(cnt, n)
-        cost = cnt + CELL_COST_AGENTS * (cnt > 0)
+        cost = cnt + CELL_COST_AGENTS * (cnt > 0) + EMPTY_CELL_COST_AGENTS * (cnt == 0)
         per = [cost[b[r]:b[r + 1]].sum() for r in range(n)]
         assert b[0] == 0 and b[-1] == 5000 and max(per) - min(per) <= 2 * cost.max() + 1, per
         cells = rng.integers(0, 5000, 100)
