@@ -50,6 +50,10 @@ CASES = {
     "genetics_1bit_free": (lambda: P.tut_environ_alt_genetic(20.0, 100, -1, 2e-3, 1), False, False, False, (100, 1), False),
     "genetics_2bit_cross": (lambda: P.tut_environ_alt_genetic(20.0, 100, 3, 5e-3, 2), False, False, False, (100, 2), False),
     "ooa_nav_gen": (_ooa_par, True, False, True, (100, 1), False),
+    # CondWeightedMove ("different" / "less or equal" over the altitudes), RandPermPair, MoveStats (first / minimum) -- ExtProbePop<m>
+    "cond_move_perm_pair_stats_first": (lambda: P.tut_environ_alt_ext(150.0, 7, True, 0, 0.3), False, True, False, None, False),
+    "cond_move_stats_min": (lambda: P.tut_environ_alt_ext(150.0, 6, False, 1, 0.3), False, True, False, None, False),
+    "perm_pair_stats_last": (lambda: P.tut_environ_alt_ext(150.0, -1, True, 2, 0.3), False, True, False, None, False),
 }
 
 
@@ -64,7 +68,11 @@ def build_inputs(name):
         alt = np.minimum(np.abs(alt) + 50.0, 1400.0)
     d = {"nbr": nbr, "alt": alt}
     seed = sum(map(ord, name)) % 97
-    pop = synthetic_population(4000, alt, seed=11 + seed, fertile=True, max_age=70.0 if "death" in name else 60.0)
+    cells = None
+    if "stats" in name:  # MoveStats: a home range, so that cells are reached for the first time during the run
+        land = np.flatnonzero(alt > 0)
+        cells = land[np.argsort(xyz[land, 0])[: len(land) // 5]]
+    pop = synthetic_population(4000, alt, seed=11 + seed, fertile=True, max_age=70.0 if "death" in name else 60.0, cells=cells)
     if female:
         pop["gender"][:] = 0
     for k, v in pop.items():
@@ -127,4 +135,6 @@ def run_case(name, sim_factory, d, well_from=None):
             out["fin_nbabies"] = g[1] if isinstance(g, tuple) else s.num_babies()
     if CASES[name][1]:
         out["capacities"] = s.capacities()
+    if par.prios.get("MoveStats") is not None:  # m_aiHops, m_adDist, m_adTime (actions/MoveStats.h:49-51)
+        out["move_hops"], out["move_dist"], out["move_time"] = s.move_stats()
     return out

@@ -858,7 +858,7 @@ def test_move_stats_vs_oracle(mode, cond_mode):
         (gh, gd, gt), (oh, od, ot) = g.move_stats(), o.move_stats()
         assert np.array_equal(gh, oh) and np.array_equal(gt, ot), k
         assert np.allclose(gd, od, rtol=1e-12, atol=0), k
-    assert (oh > 3).sum() > 100 and (oh < 0).any()
+    assert (oh > 0).sum() > 80 and oh.max() >= 3 and (oh < 0).any()
     g.run(12.0, 3)                       # inside qhgb_run such populations step one by one
     for k in range(12, 15):
         o.step(float(k))
