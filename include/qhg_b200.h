@@ -228,6 +228,11 @@ int   qhgb_host_free(void *ptr);
 
 /* ---- measurement hooks ------------------------------------------------------------------------------
  * number of kernels launched by this population since creation, and the CUDA stream they run on */
+/* which kernels the pipeline runs (steps, events, uploads) took so far: the fast path (one warp per batch of cells), the generic path
+ * (one thread per agent: rare actions, cells beyond the fast path's limits on a single GPU), and -- sharded runs -- steps redone
+ * with the recovery kernels because some rank met a cell beyond the default limits (1024 agents, 128 births, 384 ranked fertile
+ * females per cell; the recovery kernels take 8192 / 2048 / 4096) */
+int  qhgb_get_path_counts(qhgb_pop *p, int64_t *fast, int64_t *generic, int64_t *recovery);
 int64_t qhgb_get_launch_count(qhgb_pop *p);
 void   *qhgb_get_stream(qhgb_pop *p);
 /* device time (ms, CUDA events on the population's stream) accumulated per kernel name since the last reset;

@@ -55,6 +55,7 @@ SYMBOLS = {
     "qhgb_get_num_agents_range": (i32, [vp, i32, i32, vp]),
     "qhgb_mirror_num_agents_array": (i32, [vp, vp, i32, i32]),
     "qhgb_get_move_stats": (i32, [vp, vp, vp, vp]),
+    "qhgb_get_path_counts": (i32, [vp, vp, vp, vp]),
     "qhgb_get_occupied": (i32, [vp, i32, vp, vp]),
     "qhgb_get_step_stats": (i32, [vp, C.POINTER(StepStats)]),
     "qhgb_get_env_weights": (i32, [vp, vp]),

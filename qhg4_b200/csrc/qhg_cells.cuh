@@ -823,7 +823,7 @@ k_halo_gather(int nHalo, const int *__restrict__ halo, const int *__restrict__ c
         __syncthreads();
         for (int q = threadIdx.x; q < nranks; q += blockDim.x) if (sInfo[q]) atomicAdd(&info[q], sInfo[q]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) info[nranks] = st->nBirths;
+    if (blockIdx.x == 0 && threadIdx.x == 0) info[nranks] = st->oversize ? -1 : st->nBirths;  // -1: a cell beyond the limits of pass 1, see k_halo_push
 }
 
 // after the all-reduce of the halo array: the owned halo cells take the sum over all ranks
@@ -857,7 +857,9 @@ k_halo_push(int nHalo, const int *__restrict__ halo, const int *__restrict__ cel
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < nranks) {
-        T->x[threadIdx.x]->births[rank] = (long long)st->nBirths;
+        // (a rank whose pass 1 met a cell beyond its limits says so instead: every rank then leaves the step undone and all of
+        // them redo it with the recovery kernels)
+        T->x[threadIdx.x]->births[rank] = st->oversize ? -1ll : (long long)st->nBirths;
         if (threadIdx.x == 0) T->x[rank]->recvCount = 0;  // nobody reserves records before the barrier that follows
     }
 }
@@ -895,11 +897,14 @@ k_xbarrier_merge(int nHalo, const int *__restrict__ halo, int c0, int c1, int nC
     xbarrier_inline(rank, nranks, 0, stamp, T, st, timeoutClocks);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         long long below = 0, total = 0;
+        bool peerOversize = false;
         for (int q = 0; q < nranks; q++) {
             const long long b = ((volatile long long *)T->x[rank]->births)[q];
+            peerOversize |= b < 0;
             if (q < rank) below += b;
             total += b;
         }
+        if (peerOversize) st->oversize = 1;  // the kernels that follow do nothing, the step's end raises `halt`
         st->birthOffset = below;
         st->globalBirths = total;
     }
@@ -1091,18 +1096,18 @@ struct alignas(128) StagedAgents {
     float lastBirth[SCH];
     uint8_t dec[SCH];
 };
-template <int SCH, int NST>
+template <int SCH, int NST, int MM = MAXMOTHERS>
 struct alignas(128) WarpSmemS {
     StagedAgents<SCH> win[NST];
-    int64_t motherId[MAXMOTHERS];
+    int64_t motherId[MM];
     uint16_t mvJ[MVCAP];
     unsigned long long bar[NST];
 };
-template <int SCH, int NST>
+template <int SCH, int NST, int MM = MAXMOTHERS>
 struct alignas(128) WarpSmemSG {  // populations with Genetics: the mothers' positions in the old buffer as well
     StagedAgents<SCH> win[NST];
-    int64_t motherId[MAXMOTHERS];
-    int motherIdx[MAXMOTHERS];
+    int64_t motherId[MM];
+    int motherIdx[MM];
     uint16_t mvJ[MVCAP];
     unsigned long long bar[NST];
 };
@@ -1141,7 +1146,10 @@ constexpr int SCATTER_CTAS_DENSE = QHG_SCATTER_S_MINB, SCATTER_CTAS_SPARSE = 8; 
 // SG = cells per grab of the work counter: their agents are ONE contiguous range of every array, streamed through NST windows
 // of SCH agents -- the copies of the next window run while this one is consumed, and only the first window of a grab is waited
 // for with nothing else in flight (with 4-cell grabs that was every window at 20 agents per cell and every second one at 150)
-template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE, int SG = CELL_BATCH, int NST = SNST>
+// BIG = the recovery variant (see k_seg_decide<..., BIG>): up to 2048 births per cell, per-warp slices in dynamic shared memory
+constexpr int MAXMOTHERS_BIG = 2048;
+extern __shared__ __align__(128) unsigned char qhg_dyn_smem_s[];
+template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE, int SG = CELL_BATCH, int NST = SNST, bool BIG = false>
 __global__ void __launch_bounds__(CW * 32, MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
@@ -1150,8 +1158,15 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
                uint8_t *decMark = nullptr, int shrink = 0) {
     static_assert(SG + 1 <= 32, "one lane per cell start of the grab");
-    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST>, WarpSmemS<SCH, NST>>::type;
-    __shared__ WSS smem[CW];
+    constexpr int MM = BIG ? MAXMOTHERS_BIG : MAXMOTHERS;
+    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST, MM>, WarpSmemS<SCH, NST, MM>>::type;
+    WSS *smem;
+    if constexpr (BIG) {
+        smem = reinterpret_cast<WSS *>(qhg_dyn_smem_s);
+    } else {
+        __shared__ WSS smemStatic[CW];
+        smem = smemStatic;
+    }
     if (st->overflow || st->oversize || st->halt) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WSS &S = smem[wid];

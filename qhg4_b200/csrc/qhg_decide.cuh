@@ -30,15 +30,27 @@ constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the pro
 constexpr int MAXF_S = 384;    // most fertile females of one cell that can be ranked here (larger cells: generic path)
 constexpr int MAXF_SG = 160;   // the same per sex for populations with Genetics
 
-template <int SB>
+// BIG = the recovery variant of the pass: cells of up to 8192 agents, 4096 ranked fertile females (2048 per sex with Genetics) and
+// 2048 births per cell, one CTA per SM with its per-warp slices in dynamic shared memory.  A sharded run redoes a step with it
+// when any rank met a cell the default limits do not hold (a single GPU redoes such a step on the generic path).
+template <bool BIG>
+struct SegLim {
+    static constexpr int CAP = BIG ? 8192 : SEGCAP;
+    static constexpr int MF = BIG ? 4096 : MAXF_S;
+    static constexpr int MFG = BIG ? 2048 : MAXF_SG;
+    static constexpr int MM = BIG ? 2048 : MAXMOTHERS;
+};
+
+template <int SB, bool BIG = false>
 struct SegSmem {
+    static constexpr int CAP = SegLim<BIG>::CAP, MF = SegLim<BIG>::MF, MFG = SegLim<BIG>::MFG;
     double row[SB][8];                 // cumulated weight rows (7 used)
     unsigned long long tb[SB + 1], td[SB + 1]; // LinearBirth / LinearDeath thresholds of the cells (k_cell_init)
     int nbr[SB][8];                    // neighbours (6 used)
     int out[SB][8];                    // movers per (cell, direction)
     int cs[SB + 8];                    // starts of the cells inside the segment (cs[nc] = its length)
     int nreal[SB];
-    uint32_t mask[3][SEGCAP / 32];     // per chunk of 32 agents: fertile females / fertile males at step start, birth candidates
+    uint32_t mask[3][CAP / 32];        // per chunk of 32 agents: fertile females / fertile males at step start, birth candidates
     union {
         struct {                       // work queues (empty whenever the pairing needs the space below)
             long long qmId[QCAP];
@@ -47,31 +59,40 @@ struct SegSmem {
             uint16_t qaJ[QCAP], qmJ[QCAP];
         } q;
         struct {                       // pairing of ONE cell with more fertile females than males
-            alignas(16) uint32_t keys[MAXF_S];
-            uint16_t ffJ[MAXF_S], candQ[MAXF_S];
+            alignas(16) uint32_t keys[MF];
+            uint16_t ffJ[MF], candQ[MF];
         } p;
         struct {                       // populations with Genetics: the males are listed, keyed and ranked too
-            alignas(16) uint32_t keys[MAXF_SG];
-            alignas(16) uint32_t mkeys[MAXF_SG];
-            uint16_t ffJ[MAXF_SG], mmJ[MAXF_SG], candQ[MAXF_SG], candR[MAXF_SG], maleOfRank[MAXF_SG];
+            alignas(16) uint32_t keys[MFG];
+            alignas(16) uint32_t mkeys[MFG];
+            uint16_t ffJ[MFG], mmJ[MFG], candQ[MFG], candR[MFG], maleOfRank[MFG];
         } g;
     } u;
-    alignas(4) uint8_t dec[SEGCAP + 4];  // provisional decisions, shifted by (segment start & 3)
+    alignas(4) uint8_t dec[CAP + 4];     // provisional decisions, shifted by (segment start & 3)
 };
 
 // SB = cells per grab: the slot reservations of a sub-batch stay in registers until the next one ends, SB / 4 pairs of them --
 // 8 cells per grab pay at 20 agents per cell, 4 at 150 (register pressure: the kernel is capped at 64 registers)
-template <bool SPEC, int SB, bool GEN = false, bool NAV = false>
-__global__ void __launch_bounds__(DCW * 32, QHG_DECIDE_MINB)
+extern __shared__ __align__(16) unsigned char qhg_dyn_smem[];
+
+template <bool SPEC, int SB, bool GEN = false, bool NAV = false, bool BIG = false>
+__global__ void __launch_bounds__(DCW * 32, BIG ? 1 : QHG_DECIDE_MINB)
 k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, int cLo, int cHi, const int *__restrict__ cellStart,
              int doPair, int *__restrict__ stay, int *__restrict__ arrive, int *__restrict__ birthCount, uint8_t *__restrict__ dec,
              int *__restrict__ moveBase, int shrink, int *__restrict__ father = nullptr, JumpEntry *__restrict__ jumps = nullptr,
              int *__restrict__ jumpCount = nullptr, int jumpCap = 0) {
     static_assert(!(SPEC && (GEN || NAV)), "the compile-time program has neither Genetics nor Navigate");
     static_assert(SB + 1 <= 32 && SB * 8 <= 4 * 32, "one lane per cell start; at most four rounds of (cell, direction) lanes");
-    __shared__ SegSmem<SB> smem[DCW];
+    using L = SegLim<BIG>;
+    SegSmem<SB, BIG> *smem;
+    if constexpr (BIG) {
+        smem = reinterpret_cast<SegSmem<SB, true> *>(qhg_dyn_smem);
+    } else {
+        __shared__ SegSmem<SB, false> smemStatic[DCW];
+        smem = smemStatic;
+    }
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
-    SegSmem<SB> &S = smem[wid];
+    SegSmem<SB, BIG> &S = smem[wid];
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it
@@ -113,7 +134,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
     while (g0 < nB) {
         // the sub-batch: as many of the remaining cells as fit the shared-memory segment
         const int s = __shfl_sync(FULL, csL, g0);
-        const unsigned fit = __ballot_sync(FULL, lane > g0 && lane <= nB && csL - s <= SEGCAP);
+        const unsigned fit = __ballot_sync(FULL, lane > g0 && lane <= nB && csL - s <= L::CAP);
         if (!fit) {  // one cell larger than the segment: the host reruns the step on the generic path
             if (lane == 0) atomicExch(&st->oversize, 1);
             g0++;
@@ -395,44 +416,62 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
             for (int ci = 0; ci < nc; ci++) {  // warp-uniform
                 const int b0 = S.cs[ci], b1 = S.cs[ci + 1];
                 if (b1 == b0) continue;
-                // lane k looks at chunk k of the segment, restricted to the positions [b0, b1) of this cell
-                const int lo = b0 - 32 * lane, hi = b1 - 32 * lane;
-                unsigned rm = 0;
-                if (hi > 0 && lo < 32) rm = ((hi >= 32) ? FULL : ((1u << hi) - 1u)) & ((lo <= 0) ? FULL : ~((1u << lo) - 1u));
-                const unsigned wF = rm ? (S.mask[0][lane] & rm) : 0u, wM = rm ? (S.mask[1][lane] & rm) : 0u;
-                const int cF = __popc(wF), cM = __popc(wM);
+                // lane k looks at chunk k (of every group of 32 chunks: one group unless BIG) of the segment, restricted to the
+                // positions [b0, b1) of this cell
+                constexpr int NG = L::CAP / 1024;
+                unsigned wF[NG], wM[NG], wC[NG], rmG[NG];
+                int cF = 0, cM = 0;
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const int ch = 32 * g + lane;
+                    const int lo = b0 - 32 * ch, hi = b1 - 32 * ch;
+                    unsigned rm = 0;
+                    if (hi > 0 && lo < 32) rm = ((hi >= 32) ? FULL : ((1u << hi) - 1u)) & ((lo <= 0) ? FULL : ~((1u << lo) - 1u));
+                    rmG[g] = rm;
+                    wF[g] = rm ? (S.mask[0][ch] & rm) : 0u;
+                    wM[g] = rm ? (S.mask[1][ch] & rm) : 0u;
+                    cF += __popc(wF[g]); cM += __popc(wM[g]);
+                }
                 const int nF = __reduce_add_sync(FULL, cF), nMc = __reduce_add_sync(FULL, cM);
                 if (!GEN && nF <= nMc) continue;  // every fertile female has a mate
-                const unsigned wC = rm ? (S.mask[2][lane] & rm) : 0u;
-                const int cC = __popc(wC);
+                int cC = 0;
+#pragma unroll
+                for (int g = 0; g < NG; g++) { wC[g] = rmG[g] ? (S.mask[2][32 * g + lane] & rmG[g]) : 0u; cC += __popc(wC[g]); }
                 const int nCand = __reduce_add_sync(FULL, cC);
                 if (nCand == 0) continue;  // no birth candidate in the cell: nothing to settle
-                if (nF > (GEN ? MAXF_SG : MAXF_S) || (GEN && nMc > MAXF_SG)) {
+                if (nF > (GEN ? L::MFG : L::MF) || (GEN && nMc > L::MFG)) {
                     if (lane == 0) atomicExch(&st->oversize, 1);
                     continue;
                 }
                 // the cell's fertile females in position order, and the candidates as indices into that list
-                int inF = cF, inC = cC, inM = cM;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int xF = __shfl_up_sync(FULL, inF, o), xC = __shfl_up_sync(FULL, inC, o);
-                    if (lane >= o) { inF += xF; inC += xC; }
-                    if constexpr (GEN) { const int xM = __shfl_up_sync(FULL, inM, o); if (lane >= o) inM += xM; }
-                }
-                const int baseF = inF - cF;
                 uint16_t *const ffJ = GEN ? S.u.g.ffJ : S.u.p.ffJ, *const candQ = GEN ? S.u.g.candQ : S.u.p.candQ;
                 uint32_t *const keys = GEN ? S.u.g.keys : S.u.p.keys;
-                {
-                    unsigned w = wF;
+                int offF = 0, offC = 0, offM = 0;  // entries of the groups before this one
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const int gF = __popc(wF[g]), gC = __popc(wC[g]), gM = __popc(wM[g]);
+                    int inF = gF, inC = gC, inM = gM;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int xF = __shfl_up_sync(FULL, inF, o), xC = __shfl_up_sync(FULL, inC, o);
+                        if (lane >= o) { inF += xF; inC += xC; }
+                        if constexpr (GEN) { const int xM = __shfl_up_sync(FULL, inM, o); if (lane >= o) inM += xM; }
+                    }
+                    const int baseF = offF + inF - gF;
+                    unsigned w = wF[g];
                     int idx = baseF;
-                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; ffJ[idx++] = (uint16_t)(32 * lane + t); }
-                    w = wC;
-                    idx = inC - cC;
-                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; candQ[idx++] = (uint16_t)(baseF + __popc(wF & ((1u << t) - 1u))); }
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; ffJ[idx++] = (uint16_t)(32 * (32 * g + lane) + t); }
+                    w = wC[g];
+                    idx = offC + inC - gC;
+                    while (w) { const int t = __ffs(w) - 1; w &= w - 1; candQ[idx++] = (uint16_t)(baseF + __popc(wF[g] & ((1u << t) - 1u))); }
                     if constexpr (GEN) {
-                        w = wM;
-                        idx = inM - cM;
-                        while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.g.mmJ[idx++] = (uint16_t)(32 * lane + t); }
+                        w = wM[g];
+                        idx = offM + inM - gM;
+                        while (w) { const int t = __ffs(w) - 1; w &= w - 1; S.u.g.mmJ[idx++] = (uint16_t)(32 * (32 * g + lane) + t); }
+                    }
+                    if constexpr (NG > 1) {
+                        offF += __shfl_sync(FULL, inF, 31); offC += __shfl_sync(FULL, inC, 31);
+                        if constexpr (GEN) offM += __shfl_sync(FULL, inM, 31);
                     }
                 }
                 __syncwarp();
@@ -550,7 +589,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
             if (myc < nc && li == 0) {  // a cell belongs to exactly one warp: plain stores
                 stay[c0 + myc] = stayL;
                 birthCount[c0 + myc] = bornL;
-                if (bornL > MAXMOTHERS) atomicExch(&st->oversize, 1);
+                if (bornL > L::MM) atomicExch(&st->oversize, 1);
                 nBornL += bornL;
                 nMoveL += moveL;
                 nDeadL += cellN - stayL - outL;

@@ -225,6 +225,8 @@ struct qhgb_pop {
 
     // step state
     bool preLooped = false, inStep = false, pairingValid = false, needPair = false, doVerhulst = false;
+    bool forceBig = false;  // QHG_FORCE_BIG=1: sharded runs use the recovery kernels in every step (tests)
+    int64_t bigSteps = 0;   // steps a sharded run had to redo with the recovery kernels
     bool forceGeneric = false;
     bool cellValid = true;  // does cell[cur] hold the per-agent cell index? (the fast path leaves it implied by cellStart)
     int64_t genericSteps = 0, tiledSteps = 0;
@@ -1025,6 +1027,24 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
     LAUNCH(p, NAME, (k_seg_decide<false, SB_, GEN_, NAV_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),      \
            q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, shrinkGrabs,        \
            GEN_ ? q.father.p : (int *)nullptr, NAV_ ? q.jumps.p : (JumpEntry *)nullptr, NAV_ ? q.jumpCount.p : (int *)nullptr, jumpCap)
+            // the recovery variant of both passes (sharded runs: a rank met a cell beyond the default limits in the first attempt)
+            const bool big = q.sharded && (attempt == 1 || q.forceBig);
+#define QHG_SEG_LAUNCH_BIG(NAME, GEN_, NAV_)                                                                                          \
+    do {                                                                                                                              \
+        auto kern = k_seg_decide<false, 4, GEN_, NAV_, true>;                                                                          \
+        const int bytes = (int)(DCW * sizeof(SegSmem<4, true>));                                                                       \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));                                            \
+        LAUNCH_SMEM(p, NAME, kern, q.numSMs, DCW * 32, bytes, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(), q.cellStart[q.cur].p,    \
+                    doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, 1, GEN_ ? q.father.p : (int *)nullptr,  \
+                    NAV_ ? q.jumps.p : (JumpEntry *)nullptr, NAV_ ? q.jumpCount.p : (int *)nullptr, jumpCap);                          \
+    } while (0)
+            if (big) {
+                if (q.genetic) LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
+                if (q.genetic && useNav) QHG_SEG_LAUNCH_BIG("k_cell_decide_big", true, true);
+                else if (q.genetic) QHG_SEG_LAUNCH_BIG("k_cell_decide_big", true, false);
+                else if (useNav) QHG_SEG_LAUNCH_BIG("k_cell_decide_big", false, true);
+                else QHG_SEG_LAUNCH_BIG("k_cell_decide_big", false, false);
+            } else
             if (q.genetic) {  // births carry the father's position, genome handles follow the agents
                 LAUNCH(p, "k_genome_ctl_reset", k_genome_ctl_reset, 1, 1, q.gctl.p, 0, 1);
                 if (q.segDecide) {
@@ -1098,6 +1118,15 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 sendCnt.assign(R, 0); recvCnt.assign(R, 0);
                 std::vector<int> sendOff(R + 1, 0);
                 long long below = 0, total = 0;
+                bool peerOversize = false;  // a rank's pass 1 met a cell beyond its limits: it announced -1 births
+                for (int r = 0; r < R; r++) peerOversize |= q.hAllInfo[r * (R + 1) + R] < 0;
+                if (peerOversize) {
+                    if (attempt == 1 || q.forceBig) return fail("a cell is beyond the limits of the recovery kernels too (8192 agents, 2048 births, 4096 ranked fertile females)");
+                    LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
+                    if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
+                    q.bigSteps++;
+                    continue;
+                }
                 for (int r = 0; r < R; r++) {
                     sendCnt[r] = q.hAllInfo[q.shRank * (R + 1) + r];
                     recvCnt[r] = q.hAllInfo[r * (R + 1) + q.shRank];
@@ -1142,7 +1171,21 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,         \
                    (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkS);                      \
     }
-            {
+            if (big) {
+                launchedS = true;
+                if (q.genetic) {
+                    auto kern = k_cell_scatter<true, SCH_DENSE, 1, CELL_BATCH, 1, true>;
+                    const int bytes = (int)(CW * sizeof(WarpSmemSG<SCH_DENSE, 1, MAXMOTHERS_BIG>));
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                    LAUNCH_SMEM(p, "k_cell_scatter_big", kern, q.numSMs, CW * 32, bytes, QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, 1);
+                } else {
+                    auto kern = k_cell_scatter<false, SCH_DENSE, 1, CELL_BATCH, 1, true>;
+                    const int bytes = (int)(CW * sizeof(WarpSmemS<SCH_DENSE, 1, MAXMOTHERS_BIG>));
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                    LAUNCH_SMEM(p, "k_cell_scatter_big", kern, q.numSMs, CW * 32, bytes, QHG_SCATTER_ARGS, (const int *)nullptr, (BirthEntry *)nullptr,
+                                (GenomeCtl *)nullptr, (uint8_t *)nullptr, 1);
+                }
+            } else {
                 // grabs that shrink towards the end of the range: whenever a warp gets fewer than about 24 full grabs
                 const int shrinkS = (shrinkGrabs || (int64_t)(q.cHi() - q.cLo()) < (int64_t)24 * sv.sg * q.numSMs * sv.minb * CW) ? 1 : 0;
                 QHG_SCATTER_VARIANTS(QHG_SCATTER_CASE)
@@ -1256,7 +1299,15 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         if (q.hstats->commError) return commFailure(p);
         if (tiled && q.sharded && q.p2p) { q.lastSent = q.hstats->nSent; q.lastReceived = q.hstats->nRecv; }
         if (tiled && q.hstats->oversize) {  // a cell too large for the fast path: redo the step on the generic path
-            if (q.sharded) return fail("a cell is too large for the fast path (sharded populations have no generic path)");
+            if (q.sharded) {
+                // every rank has seen the flag (it travels with the births through the first cross-GPU barrier) and left the step
+                // undone: all of them redo it with the recovery kernels
+                if (attempt == 1 || q.forceBig) return fail("a cell is beyond the limits of the recovery kernels too (8192 agents, 2048 births, 4096 ranked fertile females)");
+                LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
+                if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
+                q.bigSteps++;
+                continue;
+            }
             tiled = false;
             LAUNCH(p, "k_clear_halt", k_clear_halt, 1, 1, q.dstats.p);
             if (resetCellCounters(p, q.doVerhulst) != 0) return -1;
@@ -1430,6 +1481,8 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
         const char *nf = getenv("QHG_NAV_FAST");
         p->navFast = !(nf && *nf == '0');
         p->forceGeneric = p->forceGeneric || (e && strcmp(e, "generic") == 0);
+        const char *fb = getenv("QHG_FORCE_BIG");
+        p->forceBig = fb && *fb == '1';
     }
     size_t nc = (size_t)n_cells;
     CK(p->nbr.alloc(nc * MAXN));
@@ -1959,7 +2012,9 @@ int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
             continue;
         }
         // step `ok` of the window failed on the device: the host state goes back to where that step starts
-        if (q.sharded) return fail("a step of a sharded run could not complete on the fast path (%s)", q.hstats->overflow ? "agent buffers too small" : "cell too large");
+        // (sharded: every rank stopped at the same step -- the flag of a cell beyond the limits travels through the first cross-GPU
+        // barrier -- and every rank redoes it below; qhgb_step then takes the recovery kernels)
+        if (q.sharded && q.hstats->overflow) return fail("a step of a sharded run could not complete on the fast path (agent buffers too small)");
         q.cur = cur0 ^ (ok & 1);
         q.stepsDone = steps0 + ok;
         q.tiledSteps = tiled0 + ok;
@@ -1977,6 +2032,14 @@ int qhgb_run(qhgb_pop *p, float t0, int n_steps) {
         k += ok + 1;
     }
     return rc;
+}
+
+int qhgb_get_path_counts(qhgb_pop *p, int64_t *fast, int64_t *generic, int64_t *recovery) {
+    if (!p) return fail("qhgb_get_path_counts: NULL population");
+    if (fast) *fast = p->tiledSteps;
+    if (generic) *generic = p->genericSteps;
+    if (recovery) *recovery = p->bigSteps;
+    return 0;
 }
 
 int qhgb_get_run_totals(qhgb_pop *p, int64_t *agent_steps, int64_t *sent, int64_t *received) {

@@ -191,6 +191,12 @@ class GpuPopulation:
         self._mirror = host  # keeps the array alive
         return host
 
+    def path_counts(self):
+        """(fast-path, generic-path, recovery-kernel) pipeline runs so far"""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(self.L.qhgb_get_path_counts(self.h, C.byref(a), C.byref(b), C.byref(c)), "qhgb_get_path_counts")
+        return a.value, b.value, c.value
+
     def move_stats(self):
         """MoveStats' per-cell arrays (hops, dist, time); -1 = never reached"""
         h, d, t = np.zeros(self.ncells, np.int32), np.zeros(self.ncells), np.zeros(self.ncells)

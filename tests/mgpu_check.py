@@ -201,11 +201,72 @@ def main_rebalance(rank, world, genetic):
               f"12 steps, {o.num_agents()} agents ({how} exchange), bit-exact vs the unsharded oracle before and after")
 
 
+def main_bigcell(rank, world):
+    """A few cells far beyond the fast path's limits (2500 agents, hundreds of births and ranked fertile females per cell) in ONE
+    rank's range: that rank's pass 1 raises the flag, it travels to every rank through the first cross-GPU barrier, all of them
+    leave the step undone and redo it with the recovery kernels -- step by step and inside a run of queued steps."""
+    nbr, xyz = make_ico_grid(15)
+    alt = synthetic_altitude(xyz, seed=3)
+    base = synthetic_population(40000, alt, seed=5, fertile=True)
+    land = np.flatnonzero(alt > 0)
+    hot = land[:3]                                     # the lowest land cells: rank 0's
+    extra = synthetic_population(7500, alt, seed=9, fertile=True, cells=hot)
+    pop = {k: np.concatenate([base[k], extra[k]]) for k in base}
+    order = np.argsort(pop["cell"], kind="stable")
+    pop = {k: v[order] for k, v in pop.items()}
+    pop["id"] = np.arange(len(pop["id"]), dtype=np.int64)
+    par, st = tut_environ_alt(4000.0), seed_state(31)
+    begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=len(nbr)), world)
+    g = GpuPopulation.from_params(par, nbr, alt, state16=st, device=int(os.environ.get("LOCAL_RANK", 0)), capacity_hint=200000)
+    sharding.connect(g, begin, rank, world)
+    g.add_agents(pop)
+    g.pre_loop()
+    o = None
+    if rank == 0:
+        from oracle import port
+        o = port.OraclePop(par, nbr, alt, mode=port.MODE_COUNTER, state16=st)
+        o.add_agents(pop)
+        o.start()
+
+    def compare(tag):
+        mine = g.agents()
+        parts = [None] * world
+        dist.gather_object({f: mine[f] for f in FIELDS}, parts if rank == 0 else None, dst=0)
+        if rank == 0:
+            allg = {f: np.concatenate([p[f] for p in parts]) for f in FIELDS}
+            oa = o.agents()
+            og, oo = np.argsort(allg["id"]), np.argsort(oa["id"])
+            assert len(allg["id"]) == o.num_agents(), (tag, len(allg["id"]), o.num_agents())
+            for f in FIELDS:
+                assert np.array_equal(allg[f][og], oa[f][oo]), (tag, f)
+
+    for k in range(3):
+        g.step(float(k))
+        if rank == 0:
+            o.step(float(k))
+        compare(k)
+    g.run(3.0, 3)
+    if rank == 0:
+        for k in range(3, 6):
+            o.step(float(k))
+    compare("queued")
+    rec = [None] * world
+    dist.gather_object(g.path_counts()[2], rec if rank == 0 else None, dst=0)
+    if rank == 0:
+        assert min(rec) >= 4 and len(set(rec)) == 1, rec   # every rank redid the same steps
+        how = "peer-memory" if os.environ.get("QHG_P2P", "1") != "0" else "nccl"
+        biggest = int(o.counts().max())
+        print(f"mgpu_check ok [bigcell]: {world} ranks, 6 steps (3 queued by qhgb_run), largest cell {biggest} agents, {rec[0]} steps redone with the "
+              f"recovery kernels on every rank, {o.num_agents()} agents ({how} exchange), bit-exact vs the unsharded oracle")
+
+
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    if len(sys.argv) > 1 and sys.argv[1] in ("genetic", "rebalance", "rebalance-genetic"):
-        if sys.argv[1] == "genetic":
+    if len(sys.argv) > 1 and sys.argv[1] in ("genetic", "rebalance", "rebalance-genetic", "bigcell"):
+        if sys.argv[1] == "bigcell":
+            main_bigcell(rank, world)
+        elif sys.argv[1] == "genetic":
             main_genetic(rank, world)
         else:
             main_rebalance(rank, world, sys.argv[1].endswith("genetic"))

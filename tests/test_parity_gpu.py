@@ -383,12 +383,13 @@ def test_genotype_distributions_statistically_equivalent_to_reference(bits, ncro
     assert sg.mean() > 1.0
 
 
-@pytest.mark.parametrize("which", ["tutorial", "genetic", "rebalance", "rebalance-genetic"])
+@pytest.mark.parametrize("which", ["tutorial", "genetic", "rebalance", "rebalance-genetic", "bigcell"])
 @pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
 def test_two_gpu_shards_equal_unsharded_oracle(exchange, which):
     """cell-range sharding on 2 GPUs, migration over peer memory (default) and over NCCL calls: bit-identical to the
     unsharded oracle (tests/mgpu_check.py) -- the tutorial population, and OoANavGenPop with Navigate (genome rows travel with
-    the migrants, far jumps cross shard boundaries).  The driver's GPU box has one GPU; the logs of the runs on 2, 4 and 8
+    the migrants, far jumps cross shard boundaries), a re-split in the middle of a run, and cells far beyond the fast path's limits
+    (every rank redoes those steps with the recovery kernels).  The driver's GPU box has one GPU; the logs of the runs on 2, 4 and 8
     B200 are kept in profiles/mgpu_check_r02.txt."""
     import os
     import subprocess
