@@ -12,7 +12,7 @@ for what in ${WHAT:-tutorial genetic rebalance rebalance-genetic bigcell}; do
   done
 done
 cat $OUT
-for c in ${CONFIGS:-C4 C5}; do
+for c in ${CONFIGS-C4 C5}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --config $c --steps 10 --warmup 3 > gpurun_out/bench_${c}_${R}_n$N.json 2> gpurun_out/bench_${c}_${R}_n$N.err
   tail -c 600 gpurun_out/bench_${c}_${R}_n$N.json
 done
