@@ -773,6 +773,62 @@ int qref_get_capacities(void *h, double *out) {
     return 0;
 }
 
+// ---- the agent dataset of a QDF file, through the reference's own writers and readers ---------------------------------
+// HDF5 is not installed here; oracle/stubs/hdf5_stubs.cpp backs the handful of calls of this path with memory.
+extern "C" long qhgstub_dataset_info(hid_t dset, size_t *elem, hid_t *type);
+extern "C" int qhgstub_dataset_bytes(hid_t dset, void *out);
+extern "C" hid_t qhgstub_dataset_from_bytes(hid_t type, hsize_t n, const void *bytes);
+extern "C" int qhgstub_type_member(hid_t type, int i, char *name, int cap, size_t *offset, hid_t *mtype);
+
+// what PopLooper::preWrite (core/PopLooper.cpp:146-157, called from app/Simulator.cpp:601) and the agent part of PopWriter::write
+// (io/PopWriter.cpp:84-118) do for one population: preWrite, a dataspace of getNumAgentsEffective() records, the dataset,
+// PopBase::writeAgentDataQDF.  Returns the dataset handle (< 0: failure).
+long long qref_qdf_write_agents(void *h, float t) {
+    RefSim *s = (RefSim *)h;
+    Quiet q(s->quiet);
+    PopBase *pb = s->pa->base();
+    if (pb->preWrite(t) != 0) return -2;
+    hsize_t dims = pb->getNumAgentsEffective();
+    hid_t hSpace = H5Screate_simple(1, &dims, NULL);
+    hid_t hType = pb->getAgentQDFDataType();
+    hid_t hSet = H5Dcreate2(0, "AgentDataSet", hType, hSpace, H5P_DEFAULT, H5P_DEFAULT, H5P_DEFAULT);
+    if (hSet < 0) return -3;
+    const int rc = pb->writeAgentDataQDF(hSpace, hSet, hType);
+    H5Sclose(hSpace);
+    return rc == 0 ? (long long)hSet : -4;
+}
+// records and record size of a dataset; its bytes if `out` is not NULL
+long qref_qdf_dataset(long long dset, size_t *elem, void *out) {
+    const long n = qhgstub_dataset_info((hid_t)dset, elem, NULL);
+    if (n >= 0 && out != NULL) qhgstub_dataset_bytes((hid_t)dset, out);
+    return n;
+}
+// member i of the compound type the population registered for its agents (core/SPopulation.cpp:1356-1372 + the class's
+// addPopSpecificAgentDataTypeQDF): name, offset, stub type code (oracle/stubs/hdf5.h)
+int qref_qdf_agent_member(void *h, int i, char *name, int cap, size_t *offset, int *typeCode) {
+    RefSim *s = (RefSim *)h;
+    hid_t hType = s->pa->base()->getAgentQDFDataType();
+    if (hType <= 0) hType = s->pa->base()->createAgentDataTypeQDF();
+    hid_t m = -1;
+    const int rc = qhgstub_type_member(hType, i, name, cap, offset, &m);
+    *typeCode = (int)m;
+    return rc;
+}
+// the agent part of PopReader::read (io/PopReader.cpp:143-170) on a dataset holding `n` records: PopBase::readAgentDataQDF
+int qref_qdf_read_agents(void *h, long n, const void *bytes) {
+    RefSim *s = (RefSim *)h;
+    Quiet q(s->quiet);
+    PopBase *pb = s->pa->base();
+    hid_t hType = pb->getAgentQDFDataType();
+    if (hType <= 0) hType = pb->createAgentDataTypeQDF();
+    hid_t hSet = qhgstub_dataset_from_bytes(hType, (hsize_t)n, bytes);
+    if (hSet < 0) return -2;
+    hid_t hSpace = H5Dget_space(hSet);
+    const int rc = pb->readAgentDataQDF(hSpace, hSet, hType);
+    H5Sclose(hSpace);
+    return rc;
+}
+
 // MoveStats' per-cell arrays (actions/MoveStats.h:49-51); -1 for populations without the action or before preLoop
 int qref_get_move_stats(void *h, int *hops, double *dist, double *time) {
     RefSim *s = (RefSim *)h;

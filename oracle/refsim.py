@@ -69,6 +69,13 @@ def lib(adapter: bool = False):
         L.qref_get_capacities.argtypes = [C.c_void_p, C.c_void_p]
         if hasattr(L, "qref_get_move_stats"):
             L.qref_get_move_stats.argtypes = [C.c_void_p] * 4
+        if hasattr(L, "qref_qdf_write_agents"):
+            L.qref_qdf_write_agents.restype = C.c_longlong
+            L.qref_qdf_write_agents.argtypes = [C.c_void_p, C.c_float]
+            L.qref_qdf_dataset.restype = C.c_long
+            L.qref_qdf_dataset.argtypes = [C.c_longlong, C.c_void_p, C.c_void_p]
+            L.qref_qdf_agent_member.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.qref_qdf_read_agents.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
         L.qref_set_env.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.qref_event.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.qref_set_genomes.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p]
@@ -171,6 +178,41 @@ class RefSim:
         out = np.zeros(self.ncells)
         assert self.L.qref_get_capacities(self.h, _p(out)) == 0
         return out
+
+    # ---- the agent dataset of a QDF file through the reference's own writer / reader (HDF5 backed by memory, oracle/stubs) ----
+    _QDF_TYPES = {101: "i1", 102: "u1", 103: "<i2", 104: "<u2", 105: "<i4", 106: "<u4", 107: "<i8", 108: "<u8", 109: "<i8", 110: "<u8",
+                  111: "<f4", 112: "<f8", 113: "<i4", 114: "<u4", 115: "<i8", 116: "<u8", 118: "u1", 119: "i1", 120: "u1", 122: "<i2", 123: "<u2"}
+
+    def qdf_agent_dtype(self, itemsize):
+        """numpy dtype of the compound type the population registers for its agents (names and offsets as given to H5Tinsert)"""
+        names, formats, offsets = [], [], []
+        i = 0
+        while True:
+            name = C.create_string_buffer(128)
+            off, code = C.c_size_t(0), C.c_int(0)
+            if self.L.qref_qdf_agent_member(self.h, i, name, 128, C.byref(off), C.byref(code)) != 0:
+                break
+            names.append(name.value.decode()); offsets.append(off.value); formats.append(self._QDF_TYPES[code.value])
+            i += 1
+        return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": itemsize})
+
+    def qdf_write_agents(self, t=0.0):
+        """preWrite + the agent part of PopWriter::write; returns the records HDF5 was handed, as a structured array"""
+        ds = self.L.qref_qdf_write_agents(self.h, float(t))
+        if ds < 0:
+            raise RuntimeError(f"writeAgentDataQDF failed ({ds})")
+        elem = C.c_size_t(0)
+        n = self.L.qref_qdf_dataset(ds, C.byref(elem), None)
+        raw = np.zeros(n * elem.value, np.uint8)
+        self.L.qref_qdf_dataset(ds, C.byref(elem), _p(raw))
+        return raw.view(self.qdf_agent_dtype(elem.value))
+
+    def qdf_read_agents(self, records):
+        """the agent part of PopReader::read on a dataset holding `records`"""
+        raw = np.ascontiguousarray(records).view(np.uint8)
+        rc = self.L.qref_qdf_read_agents(self.h, len(records), _p(raw))
+        if rc != 0:
+            raise RuntimeError(f"readAgentDataQDF failed ({rc})")
 
     def move_stats(self):
         """MoveStats' per-cell arrays (m_aiHops, m_adDist, m_adTime)"""
