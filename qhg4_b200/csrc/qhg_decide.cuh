@@ -92,7 +92,16 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
         smem = smemStatic;
     }
     const int lane = threadIdx.x & 31, wid = (DCW == 1) ? 0 : (int)(threadIdx.x >> 5);
+#if QHG_OPAQUE_SMEM
+    // the address of the warp's slice as a value the compiler cannot recompute (it would otherwise rebuild it from the CTA's
+    // shared-memory window and the thread index at every use rather than keep it in a register)
+    SegSmem<SB, BIG> *Sp = &smem[wid];
+    asm volatile("" : "+l"(Sp));
+    __builtin_assume(__isShared(Sp));
+    SegSmem<SB, BIG> &S = *Sp;
+#else
     SegSmem<SB, BIG> &S = smem[wid];
+#endif
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     if (st->halt) return;  // an earlier queued step failed (qhgb_run): nothing happens until the host has dealt with it

@@ -94,55 +94,64 @@ k_make_offspring(const DevStats *__restrict__ st, GenomeCtl *__restrict__ ctl, c
             while (nMut < G.nBino && r > G.bino[nMut]) nMut++;
         }
         // the words of the parents' rows are all requested before the first child word is stored (the rows live in ONE pool: a
-        // store between the loads would order them one memory round trip after the other)
-        constexpr int GU = 4;
-        for (int q0 = 0; q0 < row; q0 += 32 * GU) {
-            unsigned long long w0[GU], w1[GU];
+        // store between the loads would order them one memory round trip after the other).  A lane takes TWO consecutive blocks
+        // of one parent: one Philox call yields the 128 mask bits of both (blocks 2c and 2c+1 share counter c)
+        constexpr int GU = 2;
+        const int npair = (nb + 1) >> 1;  // pairs of blocks per parent (the last one may be half empty)
+        for (int q0 = 0; q0 < 2 * npair; q0 += 32 * GU) {
+            unsigned long long w0[GU][2], w1[GU][2];
 #pragma unroll
             for (int u = 0; u < GU; u++) {
                 const int q = q0 + u * 32 + lane;
-                w0[u] = 0; w1[u] = 0;
-                if (q < row) {
-                    const int parent = (q < nb) ? 0 : 1;
-                    const int b = q - parent * nb;
+                w0[u][0] = w0[u][1] = w1[u][0] = w1[u][1] = 0;
+                if (q < 2 * npair) {
+                    const int parent = (q < npair) ? 0 : 1;
+                    const int b = 2 * (q - parent * npair);
                     const unsigned long long *P = parent ? gf : gm;
-                    w0[u] = P[b]; w1[u] = P[nb + b];
+                    w0[u][0] = P[b]; w1[u][0] = P[nb + b];
+                    if (b + 1 < nb) { w0[u][1] = P[b + 1]; w1[u][1] = P[nb + b + 1]; }
                 }
             }
 #pragma unroll
             for (int u = 0; u < GU; u++) {
                 const int q = q0 + u * 32 + lane;
-                if (q >= row) continue;
-                const int parent = (q < nb) ? 0 : 1;
-                const int b = q - parent * nb;
+                if (q >= 2 * npair) continue;
+                const int parent = (q < npair) ? 0 : 1;
+                const int bb = 2 * (q - parent * npair);
                 const int pick = parent ? i2 : i1;
-                const unsigned long long p0 = w0[u], p1 = w1[u];
-                unsigned long long t0 = p0, t1 = p1;
-                if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
-                    const uint4 d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(b / 2), key);
-                    unsigned long long L = (b & 1) ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
-                    if (G.bitsPerNuc == 2) { L &= 0x5555555555555555ull; L += L << 1; }  // makeFreeMask, genes/GeneUtils.cpp:322-340
-                    t0 = (L & p0) | (~L & p1);
-                    t1 = (L & p1) | (~L & p0);
-                } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
-                    unsigned mine[MAX_CROSS];
-                    int cnt = 0, below = 0;
-                    for (int i = 0; i < nc; i++) {
-                        const unsigned pos = sbr[wl][parent][i];
-                        const int pb = (int)(pos >> 6);
-                        if (pb < b) below++;
-                        else if (pb == b) mine[cnt++] = pos & 63u;
+                uint4 d = make_uint4(0, 0, 0, 0);
+                if (nc == -1) d = agent_draws(be.cid, step, 0x01000000u | ((unsigned)parent << 20) | (unsigned)(bb / 2), key);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int b = bb + h;
+                    if (b >= nb) continue;
+                    const unsigned long long p0 = w0[u][h], p1 = w1[u][h];
+                    unsigned long long t0 = p0, t1 = p1;
+                    if (nc == -1) {  // free recombination, genes/BitGeneUtils.cpp:190-220
+                        unsigned long long L = h ? (((unsigned long long)d.z << 32) + d.w) : (((unsigned long long)d.x << 32) + d.y);
+                        if (G.bitsPerNuc == 2) { L &= 0x5555555555555555ull; L += L << 1; }  // makeFreeMask, genes/GeneUtils.cpp:322-340
+                        t0 = (L & p0) | (~L & p1);
+                        t1 = (L & p1) | (~L & p0);
+                    } else if (nc > 0) {  // crossover, genes/BitGeneUtils.cpp:116-186
+                        unsigned mine[MAX_CROSS];
+                        int cnt = 0, below = 0;
+                        for (int i = 0; i < nc; i++) {
+                            const unsigned pos = sbr[wl][parent][i];
+                            const int pb = (int)(pos >> 6);
+                            if (pb < b) below++;
+                            else if (pb == b) mine[cnt++] = pos & 63u;
+                        }
+                        const int cur = below & 1;
+                        const unsigned long long c0 = cur ? p1 : p0, c1 = cur ? p0 : p1;
+                        if (cnt == 0) { t0 = c0; t1 = c1; }
+                        else {
+                            const unsigned long long L = make_multi_mask(mine, cnt);
+                            t0 = (L & c0) | (~L & c1);
+                            t1 = (L & c1) | (~L & c0);
+                        }
                     }
-                    const int cur = below & 1;
-                    const unsigned long long c0 = cur ? p1 : p0, c1 = cur ? p0 : p1;
-                    if (cnt == 0) { t0 = c0; t1 = c1; }
-                    else {
-                        const unsigned long long L = make_multi_mask(mine, cnt);
-                        t0 = (L & c0) | (~L & c1);
-                        t1 = (L & c1) | (~L & c0);
-                    }
+                    gb[parent * nb + b] = pick ? t1 : t0;
                 }
-                gb[q] = pick ? t1 : t0;
             }
         }
         __syncwarp();
