@@ -25,6 +25,9 @@
 
 namespace qhg {
 
+#ifndef QHG_SMALL_CELL_PAIRING
+#define QHG_SMALL_CELL_PAIRING 1  // cells of at most 32 agents are paired with one lane per agent (no lists, no scans)
+#endif
 constexpr int SB_MAX = 8;      // most cells a warp takes per grab of the work counter (template parameter SB: 4 or 8)
 constexpr int SEGCAP = WCAP;   // most agents of one sub-batch (bytes of the provisional decisions in shared memory)
 constexpr int MAXF_S = 384;    // most fertile females of one cell that can be ranked here (larger cells: generic path)
@@ -425,6 +428,54 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
             for (int ci = 0; ci < nc; ci++) {  // warp-uniform
                 const int b0 = S.cs[ci], b1 = S.cs[ci + 1];
                 if (b1 == b0) continue;
+#if QHG_SMALL_CELL_PAIRING
+                if (b1 - b0 <= 32) {
+                    // a cell of at most 32 agents: one lane per agent, no lists.  The cell's bits of the three chunk masks are cut
+                    // out by every lane alike (two broadcast loads and a funnel shift each: no reduction to learn the counts), both
+                    // sexes get their keys from ONE Philox execution, a lane's rank is a walk over the set bits of its sex's mask
+                    const int len = b1 - b0, w = b0 >> 5, sh = b0 & 31;
+                    const unsigned cm = (len == 32) ? FULL : ((1u << len) - 1u);
+                    const bool two = sh + len > 32;
+                    const unsigned Fm = __funnelshift_r(S.mask[0][w], two ? S.mask[0][w + 1] : 0u, sh) & cm;
+                    const unsigned Mm = __funnelshift_r(S.mask[1][w], two ? S.mask[1][w + 1] : 0u, sh) & cm;
+                    const int nF = __popc(Fm), nMc = __popc(Mm);
+                    if (!GEN && nF <= nMc) continue;  // every fertile female has a mate
+                    const unsigned Cm = __funnelshift_r(S.mask[2][w], two ? S.mask[2][w + 1] : 0u, sh) & cm;
+                    if (Cm == 0) continue;            // no birth candidate in the cell: nothing to settle
+                    const int j = b0 + lane;
+                    const bool isF = (Fm >> lane) & 1u, isM = GEN && ((Mm >> lane) & 1u), isC = (Cm >> lane) & 1u;
+                    uint32_t *const keys = GEN ? S.u.g.keys : S.u.p.keys;
+                    uint32_t key = 0;
+                    if (isF || isM) key = agent_draws_rk(a.id[s + j], step, STREAM_PAIR, RK).x;
+                    keys[lane] = key;
+                    __syncwarp();
+                    int r = 0;
+                    bool tie = false;
+                    const unsigned mine = isF ? Fm : (isM ? Mm : 0u);
+                    for (unsigned m = mine; m; m &= m - 1u) {
+                        const int t = __ffs(m) - 1;
+                        const uint32_t kt = keys[t];
+                        r += (kt < key) ? 1 : 0;
+                        tie = tie || (kt == key && t != lane);
+                    }
+                    if (tie) {  // equal keys (about one pair in 10^8): the id decides
+                        const int64_t myId = a.id[s + j];
+                        for (unsigned m = mine; m; m &= m - 1u) {
+                            const int t = __ffs(m) - 1;
+                            if (t != lane && keys[t] == key && a.id[s + b0 + t] < myId) r++;
+                        }
+                    }
+                    const int np = min(nF, nMc);  // couples
+                    if (isC && r >= np) sdec[j] &= (uint8_t)~F_BORN;  // no mate: no birth
+                    if constexpr (GEN) {
+                        if (isM && r < np) S.u.g.maleOfRank[r] = (uint16_t)j;
+                        __syncwarp();
+                        if (isC && r < np) father[s + j] = s + S.u.g.maleOfRank[r];  // the mate of rank r is the father
+                    }
+                    __syncwarp();
+                    continue;
+                }
+#endif
                 // lane k looks at chunk k (of every group of 32 chunks: one group unless BIG) of the segment, restricted to the
                 // positions [b0, b1) of this cell
                 constexpr int NG = L::CAP / 1024;
