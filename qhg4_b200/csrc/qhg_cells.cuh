@@ -1152,10 +1152,10 @@ constexpr int SCATTER_CTAS_DENSE = QHG_SCATTER_S_MINB, SCATTER_CTAS_SPARSE = 8; 
 // BIG = the recovery variant (see k_seg_decide<..., BIG>): up to 2048 births per cell, per-warp slices in dynamic shared memory
 constexpr int MAXMOTHERS_BIG = 2048;
 extern __shared__ __align__(128) unsigned char qhg_dyn_smem_s[];
-// PF = true: the NEXT grab is taken while this one is worked on -- its cell starts are on their way, and when the last windows of
-// this grab are consumed the freed stages take the first windows of the next one: a warp never waits for a copy with nothing else
-// in flight (round 1: 19 % of the pass's samples sat in the window wait, 12 % behind the work counter and the cell starts)
-template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE, int SG = CELL_BATCH, int NST = SNST, bool BIG = false, bool PF = false>
+// (Taking the NEXT grab while this one is worked on and handing the freed stages to its first windows -- so that a warp never
+// waits for a copy with nothing else in flight -- was built and measured: no gain at 150 agents per cell, -13 % at 22,
+// profiles/ab_scatter_r02c.txt.  The other warps of the SM already cover those waits.)
+template <bool GEN = false, int SCH = SCH_DENSE, int MINB = SCATTER_CTAS_DENSE, int SG = CELL_BATCH, int NST = SNST, bool BIG = false>
 __global__ void __launch_bounds__(CW * 32, MINB)
 k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo, int cHi, const int *__restrict__ cellStart,
                const uint8_t *__restrict__ dec, const int *__restrict__ nbr, const int *__restrict__ newStart,
@@ -1201,9 +1201,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
     int wIss = 0, wCons = 0;  // windows issued / consumed so far by this warp: stage = count % NST, at most NST in flight
     // a grab: lane l keeps the numbers of cell cBase+l (lane SG-or-less: the end of the grab)
     int cBase = 0, cEnd = 0, csL = 0, nsL = 0, arL = 0, bbL = 0;
-    int nxBase = 0, nxEnd = 0, nxCs = 0, nxNs = 0, nxAr = 0, nxBb = 0;  // the next one (PF)
-    bool nxValid = false;
-    int curIssued = 0;        // windows of the current grab that are already in flight when its turn comes
+    int curIssued = 0;        // windows of the current grab that are in flight
     auto fetch = [&](int &B, int &E, int &cs, int &ns_, int &ar, int &bb) -> bool {
         // (short ranges -- the shards of a many-GPU run -- get grabs that shrink towards the end: no tail of a whole batch)
         const int g = shrink ? max(1, min(SG, (cHi - lastEnd) / (2 * nWarpsS))) : SG;
@@ -1243,8 +1241,6 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         const int g0 = gs & ~15;
         const int nWin = (ge - g0 + SCH - 1) / SCH;
         while (curIssued < min(nWin, NST)) { issueWin(g0, ge, curIssued); curIssued++; }
-        int nxG0 = 0, nxGe = 0, nxWin = -1, nxIssued = 0;  // nxWin < 0: the next grab's cell starts have not been looked at yet
-        if constexpr (PF) nxValid = fetch(nxBase, nxEnd, nxCs, nxNs, nxAr, nxBb);
 
         int ci = 0;  // cell of the batch the walk is in
         int s = gs, e = __shfl_sync(FULL, csL, 1);
@@ -1399,24 +1395,9 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
             __syncwarp();  // every lane is done with the window: it can be overwritten
             wCons++;
             if (curIssued < nWin) { issueWin(g0, ge, curIssued); curIssued++; }
-            else if (PF && nxValid) {  // the freed stage takes a window of the next grab
-                if (nxWin < 0) {
-                    const int ngs = __shfl_sync(FULL, nxCs, 0);
-                    nxGe = __shfl_sync(FULL, nxCs, nxEnd - nxBase);
-                    nxG0 = ngs & ~15;
-                    nxWin = (nxGe == ngs) ? 0 : (nxGe - nxG0 + SCH - 1) / SCH;
-                }
-                if (nxIssued < min(nxWin, NST)) { issueWin(nxG0, nxGe, nxIssued); nxIssued++; }
-            }
         }
-        if constexpr (PF) {
-            have = nxValid;
-            cBase = nxBase; cEnd = nxEnd; csL = nxCs; nsL = nxNs; arL = nxAr; bbL = nxBb;
-            curIssued = nxIssued;
-        } else {
-            have = fetch(cBase, cEnd, csL, nsL, arL, bbL);
-            curIssued = 0;
-        }
+        have = fetch(cBase, cEnd, csL, nsL, arL, bbL);
+        curIssued = 0;
     }
     if (H.on) {
         nSentL = __reduce_add_sync(FULL, nSentL);

@@ -429,7 +429,7 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                 const int b0 = S.cs[ci], b1 = S.cs[ci + 1];
                 if (b1 == b0) continue;
 #if QHG_SMALL_CELL_PAIRING
-                if (b1 - b0 <= 32) {
+                if (SB >= 8 && b1 - b0 <= 32) {  // (only in the kernels for sparse populations: at 150 agents per cell the extra code costs 3 %)
                     // a cell of at most 32 agents: one lane per agent, no lists.  The cell's bits of the three chunk masks are cut
                     // out by every lane alike (two broadcast loads and a funnel shift each: no reduction to learn the counts), both
                     // sexes get their keys from ONE Philox execution, a lane's rank is a walk over the set bits of its sex's mask

@@ -953,15 +953,14 @@ int commFailure(qhgb_pop *p) {
 
 // pass 2 comes in several compiled shapes: (agents per window, CTAs per SM, cells per grab, window stages)
 #define QHG_SCATTER_VARIANTS(X) \
-    X(384, 6, 4, 1, 0) X(256, 8, 4, 1, 0) X(192, 6, 4, 2, 0) X(256, 8, 16, 1, 0) X(256, 8, 12, 1, 0) \
-    X(384, 6, 4, 1, 1) X(192, 6, 4, 2, 1) X(192, 6, 8, 2, 1) X(256, 5, 4, 2, 1) X(128, 6, 4, 3, 1) X(256, 8, 16, 1, 1) X(128, 8, 16, 2, 1) X(128, 8, 8, 2, 1)
-struct ScatterVariant { int sch, minb, sg, nst, pf; };
+    X(384, 6, 4, 1) X(256, 8, 4, 1) X(192, 6, 4, 2) X(256, 8, 16, 1) X(256, 8, 12, 1) X(384, 6, 16, 1) X(128, 8, 16, 2)
+struct ScatterVariant { int sch, minb, sg, nst; };
 ScatterVariant scatterVariant(bool sparse) {
     // (the environment is looked at on every call: an A/B run switches between the variants from one step to the next)
     const char *e = getenv(sparse ? "QHG_SCATTER_SPARSE" : "QHG_SCATTER_DENSE");
     ScatterVariant t{};
-    if (e && sscanf(e, "%d,%d,%d,%d,%d", &t.sch, &t.minb, &t.sg, &t.nst, &t.pf) >= 4) return t;
-    return sparse ? ScatterVariant{256, 8, 16, 1, 0} : ScatterVariant{384, 6, 4, 1, 0};  // measured: profiles/ab_scatter_r02.txt
+    if (e && sscanf(e, "%d,%d,%d,%d", &t.sch, &t.minb, &t.sg, &t.nst) == 4) return t;
+    return sparse ? ScatterVariant{256, 8, 16, 1} : ScatterVariant{384, 6, 4, 1};  // measured: profiles/ab_scatter_r02*.txt
 }
 
 // does a warp of k_seg_decide take 8 cells per grab (fewer than QHG_SEG_DENSE = 64 agents per cell on average) or 4?
@@ -1161,14 +1160,14 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             // of the compiled variants (A/B runs)
             const ScatterVariant sv = scatterVariant(segSparse(p));
             bool launchedS = false;
-#define QHG_SCATTER_CASE(SCH_, MINB_, SG_, NST_, PF_)                                                                                       \
-    if (!launchedS && sv.sch == SCH_ && sv.minb == MINB_ && sv.sg == SG_ && sv.nst == NST_ && sv.pf == PF_) {                              \
+#define QHG_SCATTER_CASE(SCH_, MINB_, SG_, NST_)                                                                                            \
+    if (!launchedS && sv.sch == SCH_ && sv.minb == MINB_ && sv.sg == SG_ && sv.nst == NST_) {                                              \
         launchedS = true;                                                                                                               \
         if (q.genetic)                                                                                                                  \
-            LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_, MINB_, SG_, NST_, false, PF_ != 0>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,  \
+            LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,  \
                    q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkS);                                                                 \
         else                                                                                                                            \
-            LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_, MINB_, SG_, NST_, false, PF_ != 0>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,         \
+            LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,         \
                    (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkS);                      \
     }
             if (big) {
@@ -1191,7 +1190,7 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                 QHG_SCATTER_VARIANTS(QHG_SCATTER_CASE)
             }
 #undef QHG_SCATTER_CASE
-            if (!launchedS) return fail("no scatter kernel compiled for windows of %d agents, %d CTAs per SM, %d cells per grab, %d stages, prefetch %d", sv.sch, sv.minb, sv.sg, sv.nst, sv.pf);
+            if (!launchedS) return fail("no scatter kernel compiled for windows of %d agents, %d CTAs per SM, %d cells per grab, %d stages", sv.sch, sv.minb, sv.sg, sv.nst);
             if (useNav) {
                 if (q.genetic) LAUNCH(p, "k_place_jumpers", k_place_jumpers<true>, q.numSMs * 2, 256, q.dstats.p, q.jumpCount.p, q.jumps.p, jumpCap, a, o,
                                       q.cellStart[q.cur ^ 1].p, q.stay.p, q.dec.p, P.storeAge, H);
