@@ -50,10 +50,11 @@ constexpr int WCAP = 1024;       // largest cell (agents) the fast path handles;
 #endif
 constexpr int MAXF = QHG_MAXF;   // most fertile females of one cell that can be ranked in shared memory
 constexpr int QCAP = QHG_QCAP;   // work-queue entries per warp (flushed when the next round could overflow them)
-constexpr int MVCAP = 64;        // movers queued per warp in the scatter pass
+constexpr int MVCAP = 96;        // movers queued per warp in the scatter pass (flushed once per window, or when the next round could overflow); 64 for the smaller windows
 constexpr int MOVE_STRIDE = 8;    // ints per cell in moveBase[] (one 32-byte sector)
 constexpr int AGENT_SLACK = 64;  // elements allocated past the capacity of every per-agent array (aligned bulk reads)
 constexpr int MAXMOTHERS = 128;  // most births of one cell per step on the fast path
+constexpr int BIRTH_FLUSH = 24;  // pass 2 collects the mothers of several cells and places their babies together once it has this many
 #ifndef QHG_CELL_BATCH
 #define QHG_CELL_BATCH 4
 #endif
@@ -1099,19 +1100,27 @@ struct alignas(128) StagedAgents {
     float lastBirth[SCH];
     uint8_t dec[SCH];
 };
-template <int SCH, int NST, int MM = MAXMOTHERS>
+template <int SCH, int NST, int MM = MAXMOTHERS, int SG = CELL_BATCH>
 struct alignas(128) WarpSmemS {
     StagedAgents<SCH> win[NST];
-    int64_t motherId[MM];
-    uint16_t mvJ[MVCAP];
+    int64_t motherId[MM + BIRTH_FLUSH + 8];  // the mothers of the cells since the last placement of babies (a cell adds at most MM)
+    uint8_t motherC[MM + BIRTH_FLUSH + 8];   // ... and the cell of the grab each belongs to
+    static constexpr int MVC = (SCH >= 384) ? MVCAP : 64;
+    uint16_t mvJ[MVC];                       // queued movers: position in the window
+    uint8_t mvC[MVC];                        // ... and cell of the grab
+    uint16_t dirOff[SG][8];                  // movers of (cell, direction) placed so far
     unsigned long long bar[NST];
 };
-template <int SCH, int NST, int MM = MAXMOTHERS>
+template <int SCH, int NST, int MM = MAXMOTHERS, int SG = CELL_BATCH>
 struct alignas(128) WarpSmemSG {  // populations with Genetics: the mothers' positions in the old buffer as well
     StagedAgents<SCH> win[NST];
-    int64_t motherId[MM];
-    int motherIdx[MM];
-    uint16_t mvJ[MVCAP];
+    int64_t motherId[MM + BIRTH_FLUSH + 8];
+    int motherIdx[MM + BIRTH_FLUSH + 8];
+    uint8_t motherC[MM + BIRTH_FLUSH + 8];
+    static constexpr int MVC = (SCH >= 384) ? MVCAP : 64;
+    uint16_t mvJ[MVC];
+    uint8_t mvC[MVC];
+    uint16_t dirOff[SG][8];
     unsigned long long bar[NST];
 };
 
@@ -1165,7 +1174,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                uint8_t *decMark = nullptr, int shrink = 0) {
     static_assert(SG + 1 <= 32, "one lane per cell start of the grab");
     constexpr int MM = BIG ? MAXMOTHERS_BIG : MAXMOTHERS;
-    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST, MM>, WarpSmemS<SCH, NST, MM>>::type;
+    using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST, MM, SG>, WarpSmemS<SCH, NST, MM, SG>>::type;
     WSS *smem;
     if constexpr (BIG) {
         smem = reinterpret_cast<WSS *>(qhg_dyn_smem_s);
@@ -1242,30 +1251,51 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         const int nWin = (ge - g0 + SCH - 1) / SCH;
         while (curIssued < min(nWin, NST)) { issueWin(g0, ge, curIssued); curIssued++; }
 
-        int ci = 0;  // cell of the batch the walk is in
+        int ci = 0;  // cell of the grab the walk is in
         int s = gs, e = __shfl_sync(FULL, csL, 1);
         while (ci < cEnd - cBase && e == s) { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); }
-        int ns = 0, stayBase = 0, nMothers = 0, nmv = 0;
-        // lane k < MAXN: where the movers of this cell towards neighbour k go.  The three loads are issued when the
-        // cell begins and first used when its movers are flushed.
-        // (the neighbours of the cell after this one are fetched a cell ahead: land cells come in runs)
-        int dirCell = -1, dirA = 0, dirB = 0, dirC = 0, dirOff = 0;
-        int dPre = -1, dPreCi = -1;
+        int ns = 0, stayBase = 0, nMothers = 0, nmv = 0, cellM0 = 0;
+        int mFirstL = 0, mCntL = 0, babyBaseL = 0;  // lane c: the mothers of cell c in the list, where its babies go
+        for (int i = lane; i < SG * 8; i += 32) (&S.dirOff[0][0])[i] = 0;
+        __syncwarp();
         auto begin_cell = [&]() {
             ns = __shfl_sync(FULL, nsL, ci);
-            stayBase = 0; nMothers = 0;
-            int d = dPre;
-            if (dPreCi != ci) d = (lane < MAXN) ? nbr[(size_t)(cBase + ci) * MAXN + lane] : -1;
-            if (cBase + ci + 1 < cEnd) { dPre = (lane < MAXN) ? nbr[(size_t)(cBase + ci + 1) * MAXN + lane] : -1; dPreCi = ci + 1; }
-            dirCell = -1; dirA = 0; dirB = 0; dirC = 0; dirOff = 0;
-            if (lane < MAXN && d >= 0) {
-                dirCell = d;
-                if (!(H.on && (d < H.c0 || d >= H.c1))) {
-                    dirA = newStart[d]; dirB = stay[d]; dirC = moveBase[(size_t)(cBase + ci) * MOVE_STRIDE + lane];
-                } else if (H.p2p) {  // slot among the arrivals of the owner's cell (k_halo_push)
-                    dirA = H.remoteBase[d]; dirC = moveBase[(size_t)(cBase + ci) * MOVE_STRIDE + lane];
+            stayBase = 0;
+            cellM0 = nMothers;
+        };
+        // the babies of the cells collected so far: newborn id = nextID + rank of (cell, mother id) among this step's births; the
+        // same rank places the baby.  One pass for the mothers of several cells (a pass per cell leaves most lanes idle where
+        // cells hold a few dozen agents).  Only called between two cells: the list holds whole cells.
+        auto place_babies = [&]() {
+            __syncwarp();
+            for (int m0 = 0; m0 < nMothers; m0 += 32) {
+                const int m = m0 + lane;
+                const bool act = m < nMothers;
+                const int c = act ? S.motherC[m] : 0;
+                const int first = __shfl_sync(FULL, mFirstL, c), cnt = __shfl_sync(FULL, mCntL, c);
+                const int babyBase = __shfl_sync(FULL, babyBaseL, c), bb = __shfl_sync(FULL, bbL, c);
+                if (act) {
+                    const int64_t mid = S.motherId[m];
+                    int r = 0;
+                    for (int q = first; q < first + cnt; q++) r += (S.motherId[q] < mid) ? 1 : 0;
+                    const int64_t cid = nextID + birthOffset + bb + r;
+                    const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
+                    const int pos = babyBase + r;
+                    o.id[pos] = cid;
+                    o.birth[pos] = t;
+                    o.lastBirth[pos] = 0.0f;
+                    // females are born FERTILE, core/SPopulation.cpp:895-898; tut_ParthenoPop turns the drawn males into females
+                    o.flags[pos] = (uint8_t)(gnd ? (femaleOnly ? 0 : F_MALE) : F_FERTILE);
+                    if (storeAge) o.age[pos] = 0.0f;
+                    if constexpr (GEN) {  // the genome is made by k_make_offspring from the parents' rows in the old buffer
+                        o.nbabies[pos] = 0;
+                        const int mi = S.motherIdx[m];
+                        record_birth(births, gctl, pos, mi, father[mi], cid);
+                    }
                 }
             }
+            nMothers = 0;
+            __syncwarp();
         };
         begin_cell();
         for (int k = 0; k < nWin; k++) {
@@ -1274,28 +1304,32 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
             const StagedAgents<SCH> &W = S.win[stg];
             mbar_wait(&S.bar[stg], (phase >> stg) & 1u);
             phase ^= 1u << stg;
-            auto flush_movers = [&]() {  // the queued movers of cell cBase+ci; their records are in this window
+            // the queued movers (of any cell of the grab; their records are in this window): every lane looks up where ITS mover
+            // goes -- the neighbour, that cell's new start and stayers, the slot pass 1 reserved for (cell, direction) -- and takes
+            // the next free place of its (cell, direction)
+            auto flush_movers = [&]() {
                 __syncwarp();
                 for (int q0 = 0; q0 < nmv; q0 += 32) {
                     const int q = q0 + lane;
                     const bool act = q < nmv;
-                    const int x = act ? S.mvJ[q] : 0;
+                    const int x = act ? S.mvJ[q] : 0, cx = act ? S.mvC[q] : 0;
                     const uint8_t v = act ? W.dec[x] : (uint8_t)0;
-                    const int dir = act ? (v >> DEC_MOVE_SHIFT) - 1 : -1;
-                    // rank among the movers of the same direction: slots were reserved per (cell, direction) in pass 1
-                    unsigned mine = 0;
-                    int cntL = 0;
-#pragma unroll
-                    for (int L = 0; L < MAXN; L++) {
-                        const unsigned b = __ballot_sync(FULL, dir == L);
-                        if (dir == L) mine = b;
-                        if (lane == L) cntL = __popc(b);
-                    }
-                    const int base = dirA + dirB + dirC + dirOff;
-                    const int pos = __shfl_sync(FULL, base, max(dir, 0)) + __popc(mine & lt);
-                    const int d = __shfl_sync(FULL, dirCell, max(dir, 0));
-                    dirOff += cntL;
+                    const int dir = act ? (v >> DEC_MOVE_SHIFT) - 1 : 0;
+                    const int c = cBase + cx;
+                    const int d = act ? nbr[(size_t)c * MAXN + dir] : 0;
                     const bool leaves = act && H.on && (d < H.c0 || d >= H.c1);  // into a cell of another rank
+                    int base = 0;
+                    if (act) {
+                        const int mb = moveBase[(size_t)c * MOVE_STRIDE + dir];
+                        if (!leaves) base = newStart[d] + stay[d] + mb;
+                        else if (H.p2p) base = H.remoteBase[d] + mb;  // slot among the arrivals of the owner's cell (k_halo_push)
+                    }
+                    // slots were reserved per (cell, direction) in pass 1: the movers of one take consecutive places
+                    const unsigned peers = __match_any_sync(FULL, act ? ((cx << 3) | dir) : (0x1000 | lane));
+                    const int off = act ? (int)S.dirOff[cx][dir] : 0;
+                    __syncwarp();
+                    if (act && lane == __ffs(peers) - 1) S.dirOff[cx][dir] = (uint16_t)(off + __popc(peers));
+                    const int pos = base + off + __popc(peers & lt);
                     const unsigned who = H.on ? __ballot_sync(FULL, leaves) : 0u;
                     Migrant m{};
                     int srcRow = 0;
@@ -1341,7 +1375,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                     const bool alive = code != DEC_DEAD, born = (v & F_BORN) != 0;
                     const bool stays = alive && code == 0, mover = alive && code != 0;
                     const unsigned ms = __ballot_sync(FULL, stays), mb = __ballot_sync(FULL, born), mm = __ballot_sync(FULL, mover);
-                    if (mover) S.mvJ[nmv + __popc(mm & lt)] = (uint16_t)x;
+                    if (mover) { const int qe = nmv + __popc(mm & lt); S.mvJ[qe] = (uint16_t)x; S.mvC[qe] = (uint8_t)ci; }
                     nmv += __popc(mm);
                     if (stays) {
                         const int pos = ns + stayBase + __popc(ms & lt);
@@ -1355,47 +1389,25 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                             o.nbabies[pos] = a.nbabies[j] + (born ? 1 : 0);
                         }
                     }
-                    if (born) S.motherId[nMothers + __popc(mb & lt)] = W.id[x];
+                    if (born) { const int me = nMothers + __popc(mb & lt); S.motherId[me] = W.id[x]; S.motherC[me] = (uint8_t)ci; }
                     if constexpr (GEN) { if (born) S.motherIdx[nMothers + __popc(mb & lt)] = j; }
                     stayBase += __popc(ms);
                     nMothers += __popc(mb);
-                    // one call site (code size): the queue could overflow in the next round, or this is the last round of
-                    // the range -- the cell is complete (its slot bases end here) or the window is about to be recycled
-                    if (nmv > MVCAP - 32 || (j0 + 32 >= hi && nmv > 0)) flush_movers();
+                    if (nmv > WSS::MVC - 32) flush_movers();  // the queue could overflow in the next round
                 }
-                __syncwarp();
                 if (e > w1) break;  // the cell goes on in the next window
                 // ---- the cell is complete ----
-                // newborn id = nextID + rank of (cell, mother id) among this step's births; the same rank places the baby
-                const int babyBase = ns + stayBase + __shfl_sync(FULL, arL, ci);
-                const int bb = __shfl_sync(FULL, bbL, ci);
-                for (int m = lane; m < nMothers; m += 32) {
-                    const int64_t mid = S.motherId[m];
-                    int r = 0;
-                    for (int q = 0; q < nMothers; q++) r += (S.motherId[q] < mid) ? 1 : 0;
-                    const int64_t cid = nextID + birthOffset + bb + r;
-                    const uint32_t gnd = agent_draws(cid, step, STREAM_BABY, key).x >> 31;  // (uchar)(2*wrandd())
-                    const int pos = babyBase + r;
-                    o.id[pos] = cid;
-                    o.birth[pos] = t;
-                    o.lastBirth[pos] = 0.0f;
-                    // females are born FERTILE, core/SPopulation.cpp:895-898; tut_ParthenoPop turns the drawn males into females
-                    o.flags[pos] = (uint8_t)(gnd ? (femaleOnly ? 0 : F_MALE) : F_FERTILE);
-                    if (storeAge) o.age[pos] = 0.0f;
-                    if constexpr (GEN) {  // the genome is made by k_make_offspring from the parents' rows in the old buffer
-                        o.nbabies[pos] = 0;
-                        const int mi = S.motherIdx[m];
-                        record_birth(births, gctl, pos, mi, father[mi], cid);
-                    }
-                }
-                __syncwarp();
+                if (lane == ci) { mFirstL = cellM0; mCntL = nMothers - cellM0; babyBaseL = ns + stayBase + arL; }
+                if (nMothers >= BIRTH_FLUSH) place_babies();
                 do { ci++; s = e; e = __shfl_sync(FULL, csL, min(ci + 1, 31)); } while (ci < cEnd - cBase && e == s);
                 if (ci < cEnd - cBase) begin_cell();
             }
+            if (nmv > 0) flush_movers();  // the window is about to be recycled
             __syncwarp();  // every lane is done with the window: it can be overwritten
             wCons++;
             if (curIssued < nWin) { issueWin(g0, ge, curIssued); curIssued++; }
         }
+        if (nMothers > 0) place_babies();
         have = fetch(cBase, cEnd, csL, nsL, arL, bbL);
         curIssued = 0;
     }
