@@ -1171,8 +1171,21 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ moveBase,
                const int *__restrict__ birthBase, float t, int storeAge, int femaleOnly, RngKey key, ShardArgs H,
                const int *__restrict__ father = nullptr, BirthEntry *__restrict__ births = nullptr, GenomeCtl *__restrict__ gctl = nullptr,
-               uint8_t *decMark = nullptr, int shrink = 0) {
+               uint8_t *decMark = nullptr, int shrink = 0, int stepEnd = 0, int advanceStep = 0) {
     static_assert(SG + 1 <= 32, "one lane per cell start of the grab");
+    // stepEnd: this is the step's last kernel (one GPU, no Genetics, no Navigate): the block that finishes last does the step's
+    // book-keeping (k_step_end's), also when the step has already failed
+    auto step_end = [&]() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&st->doneBlocks, 1) == (int)gridDim.x - 1) {
+                st->doneBlocks = 0;
+                __threadfence();
+                step_end_body(st, advanceStep, -1);
+            }
+        }
+    };
     constexpr int MM = BIG ? MAXMOTHERS_BIG : MAXMOTHERS;
     using WSS = typename std::conditional<GEN, WarpSmemSG<SCH, NST, MM, SG>, WarpSmemS<SCH, NST, MM, SG>>::type;
     WSS *smem;
@@ -1182,7 +1195,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         __shared__ WSS smemStatic[CW];
         smem = smemStatic;
     }
-    if (st->overflow || st->oversize || st->halt) return;
+    if (st->overflow || st->oversize || st->halt) { if (stepEnd) step_end(); return; }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #if QHG_OPAQUE_SMEM
     WSS *Sp = &smem[wid];  // kept in a register (see k_seg_decide)
@@ -1415,6 +1428,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
         nSentL = __reduce_add_sync(FULL, nSentL);
         if (lane == 0 && nSentL) atomicAdd(&st->nSent, nSentL);
     }
+    if (stepEnd) step_end();
 }
 
 }  // namespace qhg

@@ -204,6 +204,10 @@ struct qhgb_pop {
     DevBuf<double> alt, W, B, D;
     DevBuf<unsigned long long> TB, TD;  // B, D as integer thresholds for the fast path (k_cell_init)
     DevBuf<int2> tileSums;
+    DevBuf<int4> tileSums4;        // k_scan_fused: (sum, births, epoch) per tile
+    DevBuf<unsigned> scanTicket;
+    unsigned scanTicketBase = 0;   // tickets taken by the launches so far
+    int scanEpoch = 0;
     std::map<std::string, DevBuf<double>> envExtra;
     bool haveCells = false, haveAlt = false, haveIce = false;
     std::vector<int32_t> hGid;
@@ -888,9 +892,17 @@ int launchScan(qhgb_pop *p) {
     qhgb_pop &q = *p;
     const int cA = q.cLo() & ~7, cHi = q.cHi();  // own cells; the start rounded down for aligned 128-bit accesses
     const int nTiles = std::max(1, (cHi - cA + SCAN_TILE - 1) / SCAN_TILE);
-    LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, cA, cHi, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p);
-    LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, cA, cHi, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p,
-           q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count[q.cur ^ 1].p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
+    static const bool twoKernels = [] { const char *e = getenv("QHG_SCAN"); return e && strcmp(e, "two") == 0; }();  // A/B
+    if (twoKernels) {
+        LAUNCH(p, "k_scan_tiles", k_scan_tiles, nTiles, 256, cA, cHi, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p);
+        LAUNCH(p, "k_scan_apply", k_scan_apply, nTiles, 256, cA, cHi, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums.p,
+               q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count[q.cur ^ 1].p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
+        return 0;
+    }
+    q.scanEpoch++;
+    LAUNCH(p, "k_scan", k_scan_fused, nTiles, 256, cA, cHi, nTiles, q.stay.p, q.arrive.p, q.birthCount.p, q.tileSums4.p, q.scanTicket.p, q.scanTicketBase,
+           q.scanEpoch, q.cellStart[q.cur ^ 1].p, q.birthBase.p, q.count[q.cur ^ 1].p, q.dstats.p, (int)std::min<int64_t>(q.capacity, 2147483647));
+    q.scanTicketBase += (unsigned)nTiles;
     return 0;
 }
 
@@ -1020,6 +1032,10 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
             }
             const int jumpCap = (int)q.jumps.n;
             const bool sparse = segSparse(p);
+            // below 32 agents per cell the compile-time program takes sixteen cells per grab (C2: -9 %; the interpreted kernels with
+            // Genetics lose 5 % to the registers of the pending slot reservations and stay at eight; QHG_SEG_SB=8 for A/B)
+            static const bool sb8 = [] { const char *e = getenv("QHG_SEG_SB"); return e && atoi(e) == 8; }();
+            const bool vsparse = sparse && !sb8 && (double)q.nAgents / (double)std::max<int64_t>(1, q.cHi() - q.cLo()) < 32.0;
             // few grabs per warp (the shards of a many-GPU run): the grabs shrink towards the end of the range
             const int shrinkGrabs = (q.cHi() - q.cLo()) < 128 * q.numSMs * 32 ? 1 : 0;
 #define QHG_SEG_LAUNCH_X(NAME, SB_, GEN_, NAV_)                                                                                \
@@ -1070,7 +1086,8 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
 #define QHG_SEG_LAUNCH(NAME, SPEC_, SB_)                                                                                      \
     LAUNCH(p, NAME, (k_seg_decide<SPEC_, SB_>), gridC, DCW * 32, q.dstats.p, a, P, cellEnv(p), q.cLo(), q.cHi(),                  \
            q.cellStart[q.cur].p, doPair ? 1 : 0, q.stay.p, q.arrive.p, q.birthCount.p, q.dec.p, q.moveBase.p, shrinkGrabs)
-                if (spec && sparse) QHG_SEG_LAUNCH("k_cell_decide", true, 8);
+                if (spec && vsparse) QHG_SEG_LAUNCH("k_cell_decide", true, 16);
+                else if (spec && sparse) QHG_SEG_LAUNCH("k_cell_decide", true, 8);
                 else if (spec) QHG_SEG_LAUNCH("k_cell_decide", true, 4);
                 else if (sparse) QHG_SEG_LAUNCH("k_cell_decide_generic", false, 8);
                 else QHG_SEG_LAUNCH("k_cell_decide_generic", false, 4);
@@ -1165,10 +1182,10 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
         launchedS = true;                                                                                                               \
         if (q.genetic)                                                                                                                  \
             LAUNCH(p, "k_cell_scatter_genetic", (k_cell_scatter<true, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,  \
-                   q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkS);                                                                 \
+                   q.father.p, q.births.p, q.gctl.p, q.dec.p, shrinkS, 0, 0);                                                           \
         else                                                                                                                            \
             LAUNCH(p, "k_cell_scatter", (k_cell_scatter<false, SCH_, MINB_, SG_, NST_>), q.numSMs * MINB_, CW * 32, QHG_SCATTER_ARGS,         \
-                   (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkS);                      \
+                   (const int *)nullptr, (BirthEntry *)nullptr, (GenomeCtl *)nullptr, (uint8_t *)nullptr, shrinkS, seS, advanceStep ? 1 : 0); \
     }
             if (big) {
                 launchedS = true;
@@ -1176,16 +1193,19 @@ int runPipeline(qhgb_pop *p, const ActParams &P, bool advanceStep, bool binned, 
                     auto kern = k_cell_scatter<true, SCH_DENSE, 1, CELL_BATCH, 1, true>;
                     const int bytes = (int)(CW * sizeof(WarpSmemSG<SCH_DENSE, 1, MAXMOTHERS_BIG>));
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-                    LAUNCH_SMEM(p, "k_cell_scatter_big", kern, q.numSMs, CW * 32, bytes, QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, 1);
+                    LAUNCH_SMEM(p, "k_cell_scatter_big", kern, q.numSMs, CW * 32, bytes, QHG_SCATTER_ARGS, q.father.p, q.births.p, q.gctl.p, q.dec.p, 1, 0, 0);
                 } else {
                     auto kern = k_cell_scatter<false, SCH_DENSE, 1, CELL_BATCH, 1, true>;
                     const int bytes = (int)(CW * sizeof(WarpSmemS<SCH_DENSE, 1, MAXMOTHERS_BIG>));
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                     LAUNCH_SMEM(p, "k_cell_scatter_big", kern, q.numSMs, CW * 32, bytes, QHG_SCATTER_ARGS, (const int *)nullptr, (BirthEntry *)nullptr,
-                                (GenomeCtl *)nullptr, (uint8_t *)nullptr, 1);
+                                (GenomeCtl *)nullptr, (uint8_t *)nullptr, 1, 0, 0);
                 }
             } else {
                 // grabs that shrink towards the end of the range: whenever a warp gets fewer than about 24 full grabs
+                // without Genetics, Navigate and other ranks pass 2 is the step's last kernel: its last block ends the step
+                const int seS = (!q.sharded && !useNav) ? 1 : 0;
+                if (seS && !q.genetic) stepEndFused = true;
                 const int shrinkS = (shrinkGrabs || (int64_t)(q.cHi() - q.cLo()) < (int64_t)24 * sv.sg * q.numSMs * sv.minb * CW) ? 1 : 0;
                 QHG_SCATTER_VARIANTS(QHG_SCATTER_CASE)
             }
@@ -1507,6 +1527,10 @@ static int create_impl(const char *pop_class, int device, int n_cells, int max_n
     CK(p->TB.alloc(nc));
     CK(p->TD.alloc(nc));
     CK(p->tileSums.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
+    CK(p->tileSums4.alloc((nc + SCAN_TILE - 1) / SCAN_TILE + 1));
+    CK(p->scanTicket.alloc(1));
+    CK(cudaMemsetAsync(p->tileSums4.p, 0, sizeof(int4) * ((nc + SCAN_TILE - 1) / SCAN_TILE + 1), p->stream));
+    CK(cudaMemsetAsync(p->scanTicket.p, 0, sizeof(unsigned), p->stream));
     if (!p->subs.empty()) {
         CK(p->cap.alloc(nc));
         CK(p->Wtmp.alloc(nc * WSTRIDE));
