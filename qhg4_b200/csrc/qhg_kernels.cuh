@@ -781,78 +781,6 @@ __device__ __forceinline__ void store8(int *__restrict__ p, int c0, int cHi, con
     }
 }
 
-// K2 in ONE launch: every block scans its own tile of 2048 cells, publishes the tile's sums and waits for the tiles before it
-// (a tile is taken by ticket, so every tile a block waits for is already being worked on; `epoch` marks this launch's entries,
-// nothing has to be reset between launches).  Replaces k_scan_tiles + k_scan_apply: one launch and one pass over the counts less.
-__global__ void __launch_bounds__(256)
-k_scan_fused(int cA, int cHi, int nTiles, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
-             volatile int4 *__restrict__ tileSums, unsigned *__restrict__ ticket, unsigned ticketBase, int epoch,
-             int *__restrict__ newStart, int *__restrict__ birthBase, int *__restrict__ count, DevStats *__restrict__ st, int capacity) {
-    __shared__ int sa[8], sb[8];
-    __shared__ int baseA, baseB, sTile;
-    if (threadIdx.x == 0) sTile = (int)(atomicAdd(ticket, 1u) - ticketBase);  // (taken even by a launch that does nothing: the host counts them)
-    __syncthreads();
-    const int tile = sTile;
-    if (st->halt) return;  // an earlier queued step failed: the other buffer's cell starts are the valid ones, keep them
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // each thread owns 8 consecutive cells
-    const int c0 = cA + tile * SCAN_TILE + threadIdx.x * 8;
-    int s8[8], a8[8], b8[8], va[8], vb[8], vc[8];
-    load8(stay, c0, cHi, s8); load8(arrive, c0, cHi, a8); load8(birthCount, c0, cHi, b8);
-    int ta = 0, tb = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        vc[k] = s8[k] + a8[k] + b8[k];
-        va[k] = ta; vb[k] = tb;
-        ta += vc[k]; tb += b8[k];
-    }
-    // block inclusive scan of (ta, tb)
-    int ia = ta, ib = tb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += xa; ib += xb; }
-    }
-    if (lane == 31) { sa[wid] = ia; sb[wid] = ib; }
-    __syncthreads();
-    int wa = 0, wb = 0, totA = 0, totB = 0;
-    for (int w = 0; w < 8; w++) { if (w < wid) { wa += sa[w]; wb += sb[w]; } totA += sa[w]; totB += sb[w]; }
-    if (threadIdx.x == 0) {  // this tile's sums, for the tiles after it
-        tileSums[tile].x = totA; tileSums[tile].y = totB;
-        __threadfence();
-        tileSums[tile].z = epoch;
-    }
-    // sum of the tiles before this one
-    int pa = 0, pb = 0;
-    for (int k = threadIdx.x; k < tile; k += 256) {
-        while (tileSums[k].z != epoch) __nanosleep(20);
-        __threadfence();
-        pa += tileSums[k].x; pb += tileSums[k].y;
-    }
-    pa = warp_sum(pa); pb = warp_sum(pb);
-    __syncthreads();
-    if (lane == 0) { sa[wid] = pa; sb[wid] = pb; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int A = 0, Bq = 0;
-        for (int w = 0; w < 8; w++) { A += sa[w]; Bq += sb[w]; }
-        baseA = A; baseB = Bq;
-    }
-    __syncthreads();
-    const int exA = baseA + wa + ia - ta, exB = baseB + wb + ib - tb;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { va[k] += exA; vb[k] += exB; }
-    store8(newStart, c0, cHi, va);
-    store8(birthBase, c0, cHi, vb);
-    store8(count, c0, cHi, vc);
-    if (tile == nTiles - 1 && threadIdx.x == 255) {
-        const int total = exA + ta;
-        newStart[cHi] = total;
-        st->nNew = total;
-        if (total > capacity) st->overflow = 1;
-    }
-}
-
 __global__ void __launch_bounds__(256)
 k_scan_tiles(int cA, int cHi, const int *__restrict__ stay, const int *__restrict__ arrive, const int *__restrict__ birthCount,
              int2 *__restrict__ tileSums) {
