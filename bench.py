@@ -258,7 +258,20 @@ def run_ours(args, rank, world):
     nbr, alt, pop, par, K, env, nav, row = (w[k] for k in ("nbr", "alt", "pop", "par", "K", "env", "nav", "row"))
     n_start = w["agents"]
     ncell = len(nbr)
-    begin = sharding.partition_cells(np.bincount(pop["cell"], minlength=ncell), world)
+    load = np.bincount(pop["cell"], minlength=ncell).astype(np.float64)
+    if genetic and world > 1:
+        # VerhulstVarK: the population settles where the carrying capacity is (NPP), away from the uniform start -- the ranges are
+        # balanced for the mean of the initial and the expected load (capacities from a population without agents on this GPU)
+        try:
+            probe = GpuPopulation.from_params(par, nbr, alt, device=device, env=env)
+            probe.pre_loop()
+            cap = np.maximum(probe.capacities(), 0.0)
+            probe.close()
+            if cap.sum() > 0:
+                load = 0.5 * load + 0.5 * cap * (load.sum() / cap.sum())
+        except Exception as e:  # noqa: BLE001 -- the ranges then follow the initial load alone
+            print(f"[bench] capacity probe failed ({e}); partition by the initial population", file=sys.stderr)
+    begin = sharding.partition_cells(np.rint(load).astype(np.int64), world)
     lo, hi = np.searchsorted(pop["cell"], [begin[rank], begin[rank + 1]])  # the population is generated binned by cell
     pop = {k: v[lo:hi] for k, v in pop.items()}
     g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096, env=env)
