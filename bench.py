@@ -272,6 +272,10 @@ def run_ours(args, rank, world):
         except Exception as e:  # noqa: BLE001 -- the ranges then follow the initial load alone
             print(f"[bench] capacity probe failed ({e}); partition by the initial population", file=sys.stderr)
     begin = sharding.partition_cells(np.rint(load).astype(np.int64), world)
+    if dist is not None:  # one table for everybody (rank 0's)
+        box = [begin]
+        dist.broadcast_object_list(box, src=0)
+        begin = box[0]
     lo, hi = np.searchsorted(pop["cell"], [begin[rank], begin[rank + 1]])  # the population is generated binned by cell
     pop = {k: v[lo:hi] for k, v in pop.items()}
     g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096, env=env)
