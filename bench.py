@@ -263,7 +263,9 @@ def run_ours(args, rank, world):
         # VerhulstVarK: the population settles where the carrying capacity is (NPP), away from the uniform start -- the ranges are
         # balanced for the mean of the initial and the expected load (capacities from a population without agents on this GPU)
         try:
-            probe = GpuPopulation.from_params(par, nbr, alt, device=device, env=env)
+            par_probe = par.copy()
+            par_probe.prios.pop("Navigate", None)   # (its preLoop wants the Navigation group; the capacities do not)
+            probe = GpuPopulation.from_params(par_probe, nbr, alt, device=device, env=env)
             probe.pre_loop()
             cap = np.maximum(probe.capacities(), 0.0)
             probe.close()

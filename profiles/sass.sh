@@ -10,8 +10,8 @@ dump() {  # dump <symbol> <file> <what>
   echo "$2: $(grep -c '^\s*/\*[0-9a-f]\{4\}\*/' $2) instructions"
 }
 dump "$(pick 'k_seg_decideILb1ELi4ELb0ELb0E')" profiles/sass_${R}_k_seg_decide_tut5_sb4.txt "k_seg_decide<SPEC=true, SB=4>: pass 1 of the fast path, tutorial action order, dense populations (the bench's C4 kernel)"
-dump "$(pick 'k_seg_decideILb1ELi8ELb0ELb0E')" profiles/sass_${R}_k_seg_decide_tut5_sb8.txt "k_seg_decide<SPEC=true, SB=8>: the same for sparse populations (C2)"
+dump "$(pick 'k_seg_decideILb1ELi16ELb0ELb0E')" profiles/sass_${R}_k_seg_decide_tut5_sb16.txt "k_seg_decide<SPEC=true, SB=16>: the same for sparse populations (C2: below 32 agents per cell; SB=8 below 64)"
 dump "$(pick 'k_seg_decideILb0ELi8ELb1ELb1E')" profiles/sass_${R}_k_seg_decide_gen_nav_sb8.txt "k_seg_decide<SPEC=false, SB=8, GEN, NAV>: interpreted program, Genetics + Navigate (C5)"
-dump "$(pick 'k_cell_scatterILb0ELi384ELi6E')" profiles/sass_${R}_k_cell_scatter_dense.txt "k_cell_scatter<GEN=false, SCH=384, 6 CTAs per SM>: pass 2, dense populations (UBLKCP = cp.async.bulk, SYNCS = mbarrier)"
-dump "$(pick 'k_cell_scatterILb1ELi256ELi8E')" profiles/sass_${R}_k_cell_scatter_genetic_sparse.txt "k_cell_scatter<GEN=true, SCH=256, 8 CTAs per SM>: pass 2 with genome handles, birth records and genome rows for the migrants"
+dump "$(pick 'k_cell_scatterILb0ELi384ELi6ELi4ELi1ELb0E')" profiles/sass_${R}_k_cell_scatter_dense.txt "k_cell_scatter<GEN=false, SCH=384, 6 CTAs per SM, 4 cells per grab, 1 stage>: pass 2, dense populations (UBLKCP = cp.async.bulk, SYNCS = mbarrier, MATCH = the movers of one (cell, direction))"
+dump "$(pick 'k_cell_scatterILb1ELi256ELi8ELi16ELi1ELb0E')" profiles/sass_${R}_k_cell_scatter_genetic_sparse.txt "k_cell_scatter<GEN=true, SCH=256, 8 CTAs per SM, 16 cells per grab>: pass 2 with genome handles, birth records and genome rows for the migrants"
 dump "$(pick 'k_make_offspring')" profiles/sass_${R}_k_make_offspring.txt "k_make_offspring: Genetics::makeOffspring, one warp per birth"

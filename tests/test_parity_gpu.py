@@ -260,6 +260,26 @@ def test_occupancy_of_tracked_cells(small_world):
         g.occupied(np.array([len(nbr)], np.int32))
 
 
+def test_path_counts_tell_which_kernels_ran(small_world):
+    """qhgb_get_path_counts: the tutorial population steps on the fast path; a population with a generic-path action
+    (WeightedMoveRand) does not; a single GPU never needs the recovery kernels"""
+    from qhg4_b200.params import tut_environ_alt_variants
+    nbr, xyz, alt = small_world
+    pop = synthetic_population(20000, alt, seed=4)
+    g, o = make_pair(tut_environ_alt(20.0), nbr, alt, pop, seed=5)
+    f0, g0, r0 = g.path_counts()
+    for k in range(4):
+        g.step(float(k))
+    f1, g1, r1 = g.path_counts()
+    assert f1 - f0 == 4 and g1 == g0 and r1 == 0
+    g2, o2 = make_pair(tut_environ_alt_variants(25.0, True, False), nbr, alt, pop, seed=5)
+    a0 = g2.path_counts()
+    for k in range(3):
+        g2.step(float(k))
+    a1 = g2.path_counts()
+    assert a1[1] - a0[1] == 3 and a1[0] == a0[0] and a1[2] == 0
+
+
 def test_count_mirror_is_current_after_every_step(small_world):
     """qhgb_mirror_num_agents_array: the host array is what qhgb_get_num_agents_array would return after every step, event and
     window of queued steps (m_aiNumAgentsPerCell of the reference is always current: core/SPopulation.cpp:1250-1290)"""
