@@ -259,6 +259,7 @@ def run_ours(args, rank, world):
     n_start = w["agents"]
     ncell = len(nbr)
     load = np.bincount(pop["cell"], minlength=ncell).astype(np.float64)
+    expected = load  # where the population is expected to settle (the agent buffers are sized for the larger of the two)
     if genetic and world > 1:
         # VerhulstVarK: the population settles where the carrying capacity is (NPP), away from the uniform start -- the ranges are
         # balanced for the mean of the initial and the expected load (capacities from a population without agents on this GPU)
@@ -270,7 +271,8 @@ def run_ours(args, rank, world):
             cap = np.maximum(probe.capacities(), 0.0)
             probe.close()
             if cap.sum() > 0:
-                load = 0.5 * load + 0.5 * cap * (load.sum() / cap.sum())
+                expected = cap * (load.sum() / cap.sum())
+                load = 0.5 * load + 0.5 * expected
         except Exception as e:  # noqa: BLE001 -- the ranges then follow the initial load alone
             print(f"[bench] capacity probe failed ({e}); partition by the initial population", file=sys.stderr)
     begin = sharding.partition_cells(np.rint(load).astype(np.int64), world)
@@ -280,7 +282,8 @@ def run_ours(args, rank, world):
         begin = box[0]
     lo, hi = np.searchsorted(pop["cell"], [begin[rank], begin[rank + 1]])  # the population is generated binned by cell
     pop = {k: v[lo:hi] for k, v in pop.items()}
-    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int((hi - lo) * 1.6) + 4096, env=env)
+    n_own = max(int(hi - lo), int(expected[begin[rank]:begin[rank + 1]].sum()))
+    g = GpuPopulation.from_params(par, nbr, alt, device=device, capacity_hint=int(n_own * 1.6) + 4096, env=env)
     if world > 1:
         sharding.connect(g, begin, rank, world)
     if nav:
