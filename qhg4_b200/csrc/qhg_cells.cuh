@@ -1374,6 +1374,7 @@ k_cell_scatter(DevStats *__restrict__ st, AgentArrays a, AgentArrays o, int cLo,
                         }
                     }
                     if (who) send_leavers<GEN>(H, who, leaves, m, srcRow);
+                    __syncwarp();  // the next round reads the places taken in this one
                 }
                 nmv = 0;
                 __syncwarp();
