@@ -341,7 +341,8 @@ k_seg_decide(DevStats *__restrict__ st, AgentArrays a, ActParams P, CellEnv E, i
                         }
                         if (alive && (unsigned long long)r0.w < tDeath) alive = false;
                     } else if (op == OP_DROWN) {  // populations/tut_EnvironAltPop.cpp:100-116 (EVENT_ID_GEO)
-                        if (E.alt[c0 + ci] < 0 || (E.ice && E.ice[c0 + ci])) alive = false;
+                        // (lanes past the end of the segment have walked to cell nc: they must not read a cell past the grid)
+                        if (valid && (E.alt[c0 + ci] < 0 || (E.ice && E.ice[c0 + ci]))) alive = false;
                     }
                 }
                 needAtan = needAtan && valid;
