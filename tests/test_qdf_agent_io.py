@@ -67,6 +67,34 @@ def test_reference_writes_and_reads_its_agent_dataset():
     r.close(); r2.close()
 
 
+def test_reference_writes_the_agent_dataset_of_ooa_nav_gen_pop():
+    """the same for the class of BASELINE configurations #3 / #5: OoANavGenPop registers the same eight members (m_iNumBabies is
+    not part of its dataset, populations/OoANavGenPop.cpp addPopSpecificAgentDataTypeQDF) and writes exactly its live agents"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import golden_cases as gc
+    if not refsim.has_class("OoANavGenPop"):
+        pytest.skip("OoANavGenPop is not part of this build of oracle/_ref")
+    d = gc.build_inputs("ooa_nav_gen")
+    par = gc.CASES["ooa_nav_gen"][0]()
+    env = {k[4:]: d[k] for k in d if k.startswith("env_")}
+    pop = {k[4:]: d[k] for k in d if k.startswith("pop_")}
+    r = refsim.RefSim(par, d["nbr"], d["alt"], threads=1, state16=d["seed_state"], env=env)
+    r.set_navigation(d["nav_ports"], d["nav_ptr"], d["nav_dests"], d["nav_dist"], d["nav_bridges"])
+    r.add_agents(pop); r.set_genomes(d["genomes"]); r.start()
+    for k in range(5):
+        r.step(float(k))
+    rec = r.qdf_write_agents(5.0)
+    assert rec.dtype.names == ("LifeState", "CellIdx", "CellID", "AgentID", "BirthTime", "Gender", "Age", "LastBirth")
+    live = r.agents()
+    assert len(rec) == r.num_agents() and len(rec) != len(pop["id"])
+    a, b = by_id(as_table(rec)), by_id({f: live[f] for f in FIELDS})
+    for f in FIELDS:
+        assert np.array_equal(a[f], b[f]), f
+    r.close()
+
+
 @pytest.mark.gpu
 def test_gpu_population_goes_through_the_reference_qdf_writer_and_reader():
     """a population that lives on the GPU (the adapter class of INTEGRATION.md, driven by the reference's PopLooper): PopWriter's
